@@ -1,0 +1,216 @@
+/*
+ * tokzig_b200.h -- C ABI of the B200-native batch encoder that replaces the encode hot path of
+ * jrc2139/tokenizer-zig (Tokenizer.encode, src/lib.zig:109-160, applied to a batch of documents).
+ *
+ * The reference has no FFI of its own: its plug points are in-process Zig vtables that take ONE
+ * pre-token per call (Model.tokenize src/model/model.zig:7,26-28; Normalizer.normalize src/normalizer/normalizer.zig:9,20;
+ * PreTokenizer.preTokenize src/pretokenizer/pretokenizer.zig:16,27; PostProcessor.process src/processor/processor.zig:10,23).
+ * This header is therefore the boundary the new src/lib.zig binds with `extern fn` (tokenizer-zig_b200/zig/src/cuda.zig);
+ * every entry point names the reference interface it stands in for.
+ *
+ * Two layers, one shared library (libtokzig_b200.so) / static archive (libtokzig_b200.a):
+ *   tkz_*   device layer: flattened model tables in, CSR batch encoding out.  No JSON, no strings.
+ *   tkzh_*  host mirror of the reference's public API (Tokenizer.fromJson / encode / tokenToId ...), written in C++
+ *           because no Zig toolchain exists in the build image; the Zig host layer binds the same tkz_* symbols.
+ *
+ * Conventions: plain pointers and sizes; 0 = ok, negative = error (codes below, mapped 1:1 onto the Zig error set);
+ * inputs are borrowed for the duration of the call; results are owned by the context and stay valid until the next
+ * encode on that context or tkz_ctx_destroy (the contract of SpanEncoding, "valid until next encode", src/lib.zig:353-356).
+ * One context per GPU, not re-entrant.  There is NO CPU fallback: every call fails with TKZ_ERR_CUDA without a device.
+ */
+#ifndef TOKZIG_B200_H
+#define TOKZIG_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------ status codes */
+#define TKZ_OK 0
+#define TKZ_ERR_OOM (-1)              /* error.OutOfMemory */
+#define TKZ_ERR_MISSING_UNK (-2)      /* error.MissingUnkToken      src/model/wordpiece.zig:150,212 */
+#define TKZ_ERR_INVALID_UTF8 (-3)     /* reference: `unreachable` in std.unicode.Utf8Iterator (src/model/bpe.zig:186-187) */
+#define TKZ_ERR_CUDA (-4)             /* no device / driver error / extension not built for this device */
+#define TKZ_ERR_INVALID_ARG (-5)
+#define TKZ_ERR_INVALID_JSON (-10)    /* ConfigError.InvalidJson            src/config.zig:18-30 */
+#define TKZ_ERR_MISSING_MODEL (-11)   /* ConfigError.MissingModel */
+#define TKZ_ERR_UNSUPPORTED_MODEL (-12) /* ConfigError.UnsupportedModelType */
+#define TKZ_ERR_MISSING_VOCAB (-13)   /* ConfigError.MissingVocab */
+#define TKZ_ERR_INVALID_VOCAB_ENTRY (-14) /* ConfigError.InvalidVocabEntry */
+#define TKZ_ERR_IO (-20)              /* file errors of Tokenizer.fromFile  src/lib.zig:48-56 */
+
+/* ------------------------------------------------------------------ device layer */
+typedef struct tkz_ctx tkz_ctx;   /* one per GPU: stream, device arenas (replace src/arena.zig), uploaded tables */
+
+#define TKZ_MODEL_BPE 0           /* src/model/bpe.zig */
+#define TKZ_MODEL_WORDPIECE 1     /* src/model/wordpiece.zig */
+
+/* byte classes of the composed pre-tokenizer (class_lut) */
+#define TKZ_CLS_WORD 0            /* part of a maximal run = one pre-token */
+#define TKZ_CLS_DELIM 1           /* dropped separator */
+#define TKZ_CLS_ISOLATE 2         /* its own one-byte pre-token (punctuation) */
+#define TKZ_NORM_DROP 0xFFFFu     /* norm_lut value: byte removed by the normalizer */
+
+/* Flattened model.  Built on the host from tokenizer.json (src/config.zig:59-117) or by hand, uploaded once.
+ * The reference's normalizers and pre-tokenizers are all byte-wise: any chain of them composes
+ * into one 256-entry byte map and one 256-entry class table, which is what crosses the ABI. */
+typedef struct tkz_model_desc {
+    int32_t model_kind;                 /* TKZ_MODEL_*                               src/config.zig:130-138 */
+    const uint16_t* norm_lut;           /* [256] normalised byte or TKZ_NORM_DROP; NULL = no normalizer
+                                           (src/config.zig:364-379, src/normalizer/normalizer.zig:47-152) */
+    const uint8_t* class_lut;           /* [256] TKZ_CLS_* of the NORMALISED byte; NULL = no pre-tokenizer: the whole
+                                           document is one pre-token (src/lib.zig:121; src/config.zig:405-450,
+                                           src/pretokenizer/pretokenizer.zig:49-241) */
+    /* model vocabulary: n keys, bytes concatenated, off[n+1] (src/model/bpe.zig:38, src/model/wordpiece.zig:15) */
+    const uint8_t* vocab_bytes;
+    const uint64_t* vocab_off;
+    const uint32_t* vocab_ids;
+    uint32_t vocab_n;
+    /* BPE merges already filtered and ranked by the loader rule of src/config.zig:228-273, in put order (a later
+     * entry for the same pair overwrites): key = first<<32|second (Pair.hash src/model/bpe.zig:24-26) */
+    const uint32_t* merge_first;
+    const uint32_t* merge_second;
+    const uint32_t* merge_rank;
+    const uint32_t* merge_new;
+    uint32_t merges_n;
+    /* unknown token.  BPE: optional, used only if configured AND present in vocab (src/model/bpe.zig:198-207), else
+     * the character is dropped.  WordPiece: has_unk = unk_token present in vocab; needing it when absent is
+     * TKZ_ERR_MISSING_UNK (src/model/wordpiece.zig:150,212). */
+    int32_t has_unk;
+    uint32_t unk_id;
+    /* WordPiece only (src/model/wordpiece.zig:17-19) */
+    const uint8_t* prefix;              /* continuing_subword_prefix */
+    uint32_t prefix_len;
+    uint64_t max_input_chars_per_word;  /* compared with the pre-token's BYTE length */
+} tkz_model_desc;
+
+/* which output arrays a call materialises (ids always) */
+#define TKZ_OUT_IDS 1u
+#define TKZ_OUT_OFFSETS 2u
+#define TKZ_OUT_ATTENTION 4u
+#define TKZ_OUT_TYPE_IDS 8u
+#define TKZ_OUT_SPECIAL 16u
+#define TKZ_OUT_ALL 31u
+
+/* Per-call knobs = the public fields Tokenizer.truncation / Tokenizer.padding (src/lib.zig:41-42,149-157;
+ * src/types.zig:39-45,55-59).  stride / strategy / pad_token are ignored by the reference's encode. */
+typedef struct tkz_encode_params {
+    int32_t has_truncation;
+    uint64_t max_length;                /* Encoding.truncate  src/encoding.zig:363-380 */
+    int32_t has_padding;                /* padding != null AND padding.length != null (src/encoding.zig:386) */
+    uint64_t pad_length;                /* Encoding.pad       src/encoding.zig:385-463 */
+    uint32_t pad_id;
+    uint32_t pad_type_id;
+    int32_t pad_left;
+    uint32_t outputs;                   /* TKZ_OUT_* mask; 0 means TKZ_OUT_ALL */
+} tkz_encode_params;
+
+/* CSR batch encoding = n_docs Encodings (src/encoding.zig:231-243) back to back.  Document d owns slots
+ * [doc_tok_off[d], doc_tok_off[d+1]).  offsets holds (start,end) pairs (Offset, src/types.zig:4-11), byte offsets into
+ * the NORMALISED PRE-TOKEN (the reference never adds the pre-token start, src/lib.zig:133-137).  Arrays not requested
+ * in `outputs` are NULL.  Token strings are not materialised: tokens[i] == idToToken(ids[i]) always. */
+typedef struct tkz_batch_result {
+    uint64_t n_docs;
+    uint64_t n_tokens;                  /* total slots incl. padding */
+    uint64_t n_real_tokens;             /* model tokens before truncation/padding */
+    const uint64_t* doc_tok_off;        /* n_docs + 1 */
+    const uint32_t* ids;
+    const uint32_t* offsets;            /* 2 * n_tokens */
+    const uint32_t* attention_mask;
+    const uint32_t* type_ids;
+    const uint32_t* special_tokens_mask;
+    int64_t err_doc;                    /* document index of the first error, -1 if none */
+} tkz_batch_result;
+
+/* counters of the last encode (FastTokenizer.arenaMemoryUsage analogue, src/lib.zig:451-453) */
+typedef struct tkz_stats {
+    uint64_t arena_bytes;               /* device bytes held by the context */
+    uint64_t n_words;                   /* pre-tokens */
+    uint64_t n_unique_words;            /* pre-tokens actually run through the model (after per-batch dedup) */
+    uint64_t n_long_words;              /* pre-tokens taken by the block-per-word path */
+    uint64_t kernel_launches;           /* kernels launched by the last encode */
+    /* device time of the last encode by stage, CUDA events on the context's stream (ms) */
+    float ms_split;                     /* K0 + K1: normalise / classify / split */
+    float ms_model;                     /* K3 | K4: BPE merge loop or WordPiece match */
+    float ms_scan;                      /* prefix sums: tokens per word -> per document -> CSR */
+    float ms_emit;                      /* K5: fused truncate / pad / output write */
+    float ms_total;                     /* first kernel to last kernel */
+} tkz_stats;
+
+/* `device` = CUDA ordinal.  `stream` = a cudaStream_t the caller owns (e.g. torch's current stream) or NULL for a
+ * private stream.  arena_hint_bytes pre-sizes the device arenas (0 = grow on demand). */
+int tkz_ctx_create(int device, void* stream, uint64_t arena_hint_bytes, tkz_ctx** out);
+void tkz_ctx_destroy(tkz_ctx* ctx);
+const char* tkz_last_error(tkz_ctx* ctx);           /* NULL ctx: last error of a failed tkz_ctx_create */
+int tkz_ctx_get_stats(tkz_ctx* ctx, tkz_stats* out);
+
+/* replaces BPE.init / WordPiece.init table construction (src/model/bpe.zig:84-110, src/model/wordpiece.zig:51-74) */
+int tkz_model_upload(tkz_ctx* ctx, const tkz_model_desc* desc);
+
+/* Replaces the caller loop over Tokenizer.encode (src/lib.zig:109-160): text = all documents back to back,
+ * doc_off[n_docs+1] byte offsets into text.  HOST pointers (pinned preferred); result arrays are HOST pointers owned
+ * by the context.  Total text must be < 4 GiB per call (offsets are u32, src/types.zig:4-6). */
+int tkz_encode_batch(tkz_ctx* ctx, const uint8_t* text, const uint64_t* doc_off, uint64_t n_docs,
+                     const tkz_encode_params* params, tkz_batch_result* out);
+
+/* Same, text and doc_off already DEVICE resident; result arrays are DEVICE pointers (scalars in *out are host
+ * values).  All work is enqueued on the context's stream; the call returns after the stream has drained. */
+int tkz_encode_batch_device(tkz_ctx* ctx, const void* d_text, const void* d_doc_off, uint64_t n_docs,
+                            uint64_t text_bytes, const tkz_encode_params* params, tkz_batch_result* out);
+
+/* ------------------------------------------------------------------ host mirror of src/lib.zig (C++ behind a C ABI) */
+typedef struct tkzh_tokenizer tkzh_tokenizer;
+
+/* Tokenizer.fromJson / fromFile  src/lib.zig:48-85 (+ src/config.zig:59-117).  `device` as in tkz_ctx_create;
+ * device < 0 loads the configuration only (no context; encode then fails with TKZ_ERR_CUDA). */
+int tkzh_from_json(const char* json, uint64_t len, int device, void* stream, tkzh_tokenizer** out);
+int tkzh_from_file(const char* path, int device, void* stream, tkzh_tokenizer** out);
+void tkzh_free(tkzh_tokenizer* t);                                   /* Tokenizer.deinit src/lib.zig:87-106 */
+const char* tkzh_last_error(tkzh_tokenizer* t);                      /* NULL: last error of a failed tkzh_from_* */
+tkz_ctx* tkzh_ctx(tkzh_tokenizer* t);
+
+/* public fields truncation / padding  src/lib.zig:41-42 */
+int tkzh_set_truncation(tkzh_tokenizer* t, int has, uint64_t max_length);
+int tkzh_set_padding(tkzh_tokenizer* t, int has, int has_length, uint64_t length, uint32_t pad_id, uint32_t pad_type_id,
+                     int pad_left);
+/* hand-wiring normalizer_impl / pretokenizer_impl (src/lib.zig:37-38): op lists, see TKZH_NORM_* / TKZH_PT_*.
+ * n = -1 removes the component (null); n = 0 installs an empty Sequence. */
+#define TKZH_NORM_CFG_LOWER 1      /* src/config.zig:364-379 */
+#define TKZH_NORM_BERT_STRUCT 2    /* src/normalizer/normalizer.zig:32-74  flags: 1 clean_text | 2 lowercase */
+#define TKZH_NORM_LOWER_STRUCT 3   /* src/normalizer/normalizer.zig:77-98 */
+#define TKZH_PT_WS_CFG 1           /* src/config.zig:440-450 */
+#define TKZH_PT_BERT_CFG 2         /* src/config.zig:405-438 */
+#define TKZH_PT_WS_STRUCT 3        /* src/pretokenizer/pretokenizer.zig:39-78 */
+#define TKZH_PT_BERT_STRUCT 4      /* src/pretokenizer/pretokenizer.zig:81-133 */
+#define TKZH_PT_BYTELEVEL_STRUCT 5 /* src/pretokenizer/pretokenizer.zig:136-183 */
+int tkzh_set_normalizer(tkzh_tokenizer* t, const int32_t* kinds, const int32_t* flags, int32_t n);
+int tkzh_set_pretokenizer(tkzh_tokenizer* t, const int32_t* kinds, int32_t n);
+
+/* Tokenizer.encode src/lib.zig:109-160 for a batch (n_docs = 1 is the reference call).  add_special_tokens is
+ * accepted and has no effect: every post-processor of the reference is a no-op (src/config.zig:551-555). */
+int tkzh_encode_batch(tkzh_tokenizer* t, const uint8_t* text, const uint64_t* doc_off, uint64_t n_docs,
+                      int add_special_tokens, uint32_t outputs, tkz_batch_result* out);
+
+/* lookups  src/lib.zig:203-223 (added vocab first, then the model) */
+uint64_t tkzh_get_vocab_size(tkzh_tokenizer* t);
+int tkzh_token_to_id(tkzh_tokenizer* t, const uint8_t* token, uint64_t len, uint32_t* id);       /* 1 found, 0 not */
+int tkzh_id_to_token(tkzh_tokenizer* t, uint32_t id, const uint8_t** token, uint64_t* len);       /* 1 found, 0 not */
+int tkzh_add_special_tokens(tkzh_tokenizer* t, const uint8_t* contents, const uint64_t* off, uint64_t n, uint64_t* added);
+/* loader facts used by the parity tests */
+uint64_t tkzh_model_vocab_count(tkzh_tokenizer* t);
+uint64_t tkzh_merge_count(tkzh_tokenizer* t);      /* distinct pairs in the merge map */
+int tkzh_has_normalizer(tkzh_tokenizer* t);
+int tkzh_has_pretokenizer(tkzh_tokenizer* t);
+int tkzh_has_post_processor(tkzh_tokenizer* t);
+uint64_t tkzh_added_token_count(tkzh_tokenizer* t);
+int tkzh_added_token(tkzh_tokenizer* t, uint64_t i, const uint8_t** content, uint64_t* len, int64_t* id, int* special);
+/* flattened model as uploaded (so a test can diff it against the oracle's loader) */
+int tkzh_model_desc(tkzh_tokenizer* t, tkz_model_desc* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TOKZIG_B200_H */

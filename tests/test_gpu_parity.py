@@ -1,0 +1,290 @@
+"""GPU parity: the CUDA path (through the C ABI) against the CPU oracle, bit-exact on ids / offsets / masks / CSR offsets.
+Covers the reference's own known-answer vectors, random vocabularies and texts (proper, improper, degenerate and aliased
+merge tables; every normalizer / pre-tokenizer chain; truncation and padding), ragged and empty inputs, words longer
+than the shared-memory path, equal-symbol runs across warp chunks, malformed UTF-8, and the real-size synthesised
+tokenizers on corpus samples."""
+import json
+import random
+
+import numpy as np
+import pytest
+
+import tokzig_b200 as tz
+from oracle import oracle as orc
+from gen_util import rand_bpe_json, rand_docs, rand_text, rand_wp_json
+from kat_util import NORM_OPS, PT_OPS, check_encoding_against_case, load_kats, model_case_to_json, norm_flags
+from tools import corpus, tokenizers_io
+
+pytestmark = pytest.mark.gpu
+CASES = load_kats()
+
+
+def assert_same(got: tz.BatchEncoding, ref: orc.BatchEncoding, what=""):
+    assert np.array_equal(got.doc_tok_off, ref.doc_tok_off), f"{what}: doc_tok_off"
+    if not np.array_equal(got.ids, ref.ids):
+        bad = int(np.nonzero(got.ids != ref.ids)[0][0]) if len(got.ids) == len(ref.ids) else -1
+        raise AssertionError(f"{what}: ids differ (first at {bad}, {len(got.ids)} vs {len(ref.ids)} tokens)")
+    assert np.array_equal(got.offsets, ref.offsets), f"{what}: offsets"
+    assert np.array_equal(got.attention_mask, ref.attention_mask), f"{what}: attention_mask"
+    assert np.array_equal(got.type_ids, ref.type_ids), f"{what}: type_ids"
+    assert np.array_equal(got.special_tokens_mask, ref.special_tokens_mask), f"{what}: special_tokens_mask"
+
+
+def pair(js):
+    return tz.Tokenizer.from_json(js, device=0), orc.OracleTokenizer.from_json(js)
+
+
+# ----------------------------------------------------------------------------- the reference's known-answer vectors
+@pytest.mark.parametrize("c", [c for c in CASES if c["kind"] in ("json", "model") and any(a in (0, 1) for a in c["algos"])], ids=lambda c: c["id"])
+def test_reference_kats_on_gpu(c):
+    js = c["json"] if c["kind"] == "json" else model_case_to_json(c["model"])
+    t = tz.Tokenizer.from_json(js, device=0)
+    if c.get("truncation") is not None:
+        t.truncation = {"max_length": c["truncation"]}
+    if c.get("padding") is not None:
+        t.padding = c["padding"]
+    text = bytes.fromhex(c["input_hex"])
+    for add in (True, False):        # examples/basic_tokenize.zig calls encode(text, true); no post-processor does anything
+        e = t.encode(text, add_special_tokens=add)
+        check_encoding_against_case(c, e.ids, e.offsets, e.attention_mask, e.type_ids, e.special_tokens_mask)
+    t.close()
+
+
+def test_example_basic_tokenize_call_sequence(tmp_path):
+    """examples/basic_tokenize.zig:24-45: fromFile -> encode("Hello, world!", true) -> ids / tokens."""
+    js = tokenizers_io.tokenizer_json("gpt2_bytelevel")
+    p = tmp_path / "tokenizer.json"
+    p.write_text(js, encoding="utf-8")
+    t = tz.Tokenizer.from_file(str(p), device=0)
+    o = orc.OracleTokenizer.from_json(js)
+    e = t.encode("Hello, world!", True)
+    ids, offs, *_ = o.encode(b"Hello, world!")
+    assert e.ids.tolist() == ids.tolist() and e.offsets.tolist() == offs.tolist()
+    assert len(e.get_tokens()) == len(e.ids)
+    # tokens[i] == idToToken(ids[i])  (bpe.zig:258)
+    assert b"".join(e.get_tokens()) == b"Hello,world!"       # the space is not a vocab key of a byte-level vocab: dropped
+    t.close()
+
+
+# ----------------------------------------------------------------------------- random property tests
+@pytest.mark.parametrize("seed", range(48))
+def test_bpe_random(seed):
+    rng = random.Random(seed)
+    mode = seed % 4
+    js, alpha = rand_bpe_json(rng, n_merges=rng.randint(0, 80), unk="<unk>" if seed % 3 == 0 else None,
+                              improper=[0.0, 0.3, 0.0, 0.5][mode], degenerate=[0.0, 0.0, 0.3, 0.2][mode], alias=[0.0, 0.0, 0.1, 0.2][mode],
+                              pretok=[None, "Whitespace", "BertPreTokenizer", "ByteLevel"][(seed // 4) % 4],
+                              normalizer=[None, "Lowercase"][(seed // 16) % 2])
+    t, o = pair(js)
+    docs = rand_docs(rng, alpha, 400, max_len=90, p_upper=0.2)
+    assert_same(t.encode_batch(docs), o.encode_batch(docs), f"seed {seed}")
+    t.close()
+
+
+@pytest.mark.parametrize("seed", range(32))
+def test_wordpiece_random(seed):
+    rng = random.Random(500 + seed)
+    js, alpha = rand_wp_json(rng, n_words=rng.randint(5, 120), prefix=["##", "", "@@@", "#"][seed % 4], max_chars=[None, 4, 7, 100][(seed // 4) % 4],
+                             pretok=["BertPreTokenizer", "Whitespace", None, "BertPreTokenizer"][(seed // 2) % 4],
+                             normalizer=["BertNormalizer", None][(seed // 8) % 2])
+    t, o = pair(js)
+    docs = rand_docs(rng, alpha, 400, max_len=70, p_upper=0.3)
+    assert_same(t.encode_batch(docs), o.encode_batch(docs), f"seed {seed}")
+    t.close()
+
+
+@pytest.mark.parametrize("seed", range(16))
+def test_truncation_and_padding(seed):
+    rng = random.Random(900 + seed)
+    if seed % 2:
+        js, alpha = rand_wp_json(rng)
+    else:
+        js, alpha = rand_bpe_json(rng, n_merges=30, pretok="Whitespace")
+    t, o = pair(js)
+    docs = rand_docs(rng, alpha, 300, max_len=60)
+    trunc = [None, 0, 1, 5, 8, 64][seed % 6]
+    pad = [None, {"length": 8, "pad_id": 7, "pad_type_id": 3, "direction": "right"}, {"length": 5, "pad_id": 0, "direction": "left"},
+           {"length": None, "pad_id": 9}][(seed // 2) % 4]
+    t.truncation = None if trunc is None else {"max_length": trunc}
+    o.truncation = trunc
+    t.padding = pad
+    o.padding = pad
+    assert_same(t.encode_batch(docs), o.encode_batch(docs), f"seed {seed} trunc {trunc} pad {pad}")
+    # a subset of the output arrays can be requested; ids always come back
+    sub = t.encode_batch(docs, outputs=tz.OUT_IDS | tz.OUT_ATTENTION)
+    ref = o.encode_batch(docs)
+    assert np.array_equal(sub.ids, ref.ids) and np.array_equal(sub.attention_mask, ref.attention_mask) and sub.offsets is None
+    t.close()
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_struct_chains(seed):
+    """hand-wired normalizer_impl / pretokenizer_impl (struct variants and Sequences), incl. byte-dropping normalizers."""
+    rng = random.Random(1300 + seed)
+    tzn = {"cfg_lower": tz.NORM_CFG_LOWER, "bert_struct": tz.NORM_BERT_STRUCT, "lower_struct": tz.NORM_LOWER_STRUCT}
+    tzp = {"ws_cfg": tz.PT_WS_CFG, "bert_cfg": tz.PT_BERT_CFG, "ws_struct": tz.PT_WS_STRUCT, "bert_struct": tz.PT_BERT_STRUCT,
+           "bytelevel_struct": tz.PT_BYTELEVEL_STRUCT}
+    if seed % 2:
+        js, alpha = rand_wp_json(rng, pretok=None, normalizer=None)
+    else:
+        js, alpha = rand_bpe_json(rng, n_merges=30, unk="<unk>" if seed % 4 == 0 else None)
+    t, o = pair(js)
+    nn = [rng.choice(list(tzn)) for _ in range(rng.randint(0, 3))]
+    fl = [rng.randint(0, 3) for _ in nn]
+    pn = [rng.choice(list(tzp)) for _ in range(rng.randint(0, 3))]
+    use_norm, use_pt = seed % 3 != 0, seed % 5 != 0
+    t.set_normalizer([(tzn[n], f) for n, f in zip(nn, fl)] if use_norm else None)
+    o.normalizers = [(NORM_OPS[n], f) for n, f in zip(nn, fl)] if use_norm else []
+    t.set_pretokenizer([tzp[n] for n in pn] if use_pt else None)
+    o.pretokenizers = [PT_OPS[n] for n in pn] if use_pt else None
+    docs = []
+    for _ in range(300):
+        d = bytearray(rand_text(rng, alpha, rng.randint(0, 60), p_upper=0.3))
+        for _ in range(rng.randint(0, 3)):          # control bytes (ASCII, keeps UTF-8 valid) for clean_text
+            d.insert(rng.randint(0, len(d)), rng.choice(b"\x00\x01\x08\x1f\x7f\x0b\x0c"))
+        docs.append(_fix_utf8(bytes(d)))
+    assert_same(t.encode_batch(docs), o.encode_batch(docs), f"seed {seed} norm {nn}{fl} pt {pn}")
+    t.close()
+
+
+def _fix_utf8(b: bytes) -> bytes:
+    return b.decode("utf-8", "ignore").encode("utf-8")
+
+
+# ----------------------------------------------------------------------------- edge cases
+def test_empty_and_ragged_inputs():
+    js, alpha = rand_bpe_json(random.Random(1), n_merges=20, pretok="Whitespace")
+    t, o = pair(js)
+    for docs in ([], [b""], [b"", b"", b""], [b" "], [b"  \n\t "], [b"a"], [b"", b"a", b""], [b"ab", b"", b"", b"ba ab"], [b"a" * 5000, b"", b"b"]):
+        assert_same(t.encode_batch(docs), o.encode_batch(docs), repr(docs)[:40])
+    t.close()
+
+
+def test_document_boundary_splits_words():
+    js = json.dumps({"model": {"type": "BPE", "vocab": {"a": 0, "b": 1, "ab": 2, "ba": 3, "abab": 4}, "merges": ["a b", "b a", "ab ab"]},
+                     "pre_tokenizer": {"type": "Whitespace"}})
+    t, o = pair(js)
+    docs = [b"abab", b"ab", b"ab", b"a", b"b", b"", b"a b", b"ab"] * 700        # boundaries fall inside tiles and on tile edges
+    assert_same(t.encode_batch(docs), o.encode_batch(docs))
+    t.close()
+
+
+@pytest.mark.parametrize("n", [31, 32, 33, 63, 64, 65, 95, 96, 97, 511, 512, 513, 1000, 5000])
+def test_equal_symbol_runs_across_chunks(n):
+    # aaaaa -> aa aa a; runs crossing 32-lane chunks, the shared-memory limit and the HBM path
+    js = json.dumps({"model": {"type": "BPE", "vocab": {"a": 0, "b": 1, "aa": 2, "aaaa": 3, "ab": 4}, "merges": ["a a", "aa aa", "a b"]}})
+    t, o = pair(js)
+    docs = [b"a" * n, b"b" + b"a" * n, b"a" * n + b"b", (b"a" * 7 + b"b") * (n // 8 + 1), b"ab" * n]
+    assert_same(t.encode_batch(docs), o.encode_batch(docs), f"n {n}")
+    t.close()
+
+
+def test_survey_adversarial_cascades():
+    v = {"w": 0, "x": 1, "y": 2, "z": 3, "u": 4, "wx": 5, "wxy": 6, "wxyz": 7, "zu": 8, "xy": 9, "yz": 10}
+    merges = [["w", "x"], ["wx", "y"], ["wxy", "z"], ["z", "u"], ["x", "y"], ["y", "z"]]
+    t, o = pair(json.dumps({"model": {"type": "BPE", "vocab": v, "merges": merges}}))
+    docs = [b"wxyzu", b"wxyzu" * 40, b"uzyxw" * 30, b"xyzuwxyzu" * 100]
+    assert_same(t.encode_batch(docs), o.encode_batch(docs))
+    assert t.encode(b"wxyzu").ids.tolist() == [7, 4]
+    t.close()
+    v = {"d": 0, "a": 1, "b": 2, "c": 3, "bc": 4, "ab": 5, "da": 6, "abc": 7}
+    t, o = pair(json.dumps({"model": {"type": "BPE", "vocab": v, "merges": ["b c", "a b", "x x", "d a", "y y", "a bc"]}}))
+    assert t.encode(b"dabc").ids.tolist() == [6, 4]           # canonical BPE.tokenize answer, not tokenizeFast's [d, abc]
+    t.close()
+
+
+def test_long_words_take_the_hbm_path():
+    rng = random.Random(5)
+    js, alpha = rand_bpe_json(rng, n_merges=150, alphabet=list("abcdefgh") + ["é", "中"], dead_merges=0.0)
+    t, o = pair(js)
+    docs = ["".join(rng.choice(alpha) for _ in range(n)).encode() for n in (600, 1500, 4000, 20000, 3, 0, 513)]
+    assert_same(t.encode_batch(docs), o.encode_batch(docs, algo=1))
+    t.close()
+
+
+def test_malformed_utf8():
+    js = json.dumps({"model": {"type": "BPE", "vocab": {"a": 0, "b": 1, "é": 2, "ab": 3, "Ã(": 4}, "merges": ["a b"]}}, ensure_ascii=False)
+    t, o = pair(js)
+    # malformed but in bounds: the reference's iterator takes the length from the lead byte only -> defined behaviour
+    ok_docs = [b"ab\xc3(ab", b"a\xe4ab", b"\xc3\xa9ab\xc3\xa9", b"ab\xf0abcab"]
+    assert_same(t.encode_batch(ok_docs), o.encode_batch(ok_docs))
+    # invalid lead byte / truncated tail: `unreachable` in the reference -> an error here, with the document index
+    for bad, where in (([b"ab", b"a\x80b"], 1), ([b"ab\xc3"], 0), ([b"ok", b"ok", b"\xff"], 2), ([b"a\xe4\xb8"], 0)):
+        with pytest.raises(tz.TokzigError) as e:
+            t.encode_batch(bad)
+        assert e.value.code == tz.ERR_INVALID_UTF8 and e.value.doc == where
+        with pytest.raises(orc.OracleError) as e2:
+            o.encode_batch(bad)
+        assert e2.value.code == orc.ERR_INVALID_UTF8 and e2.value.doc == where
+    t.close()
+
+
+def test_wordpiece_missing_unk_is_an_error():
+    js = json.dumps({"model": {"type": "WordPiece", "vocab": {"hello": 1, "##s": 2}, "unk_token": "[UNK]"}, "pre_tokenizer": {"type": "Whitespace"}})
+    t, o = pair(js)
+    assert_same(t.encode_batch([b"hello hellos"]), o.encode_batch([b"hello hellos"]))
+    with pytest.raises(tz.TokzigError) as e:
+        t.encode_batch([b"hello", b"hello xyz", b"q"])
+    assert e.value.code == tz.ERR_MISSING_UNK and e.value.doc == 1
+    with pytest.raises(orc.OracleError) as e2:
+        o.encode_batch([b"hello", b"hello xyz", b"q"])
+    assert e2.value.code == orc.ERR_MISSING_UNK and e2.value.doc == 1
+    t.close()
+
+
+def test_wordpiece_long_keys_and_512_byte_rule():
+    long_piece = "x" * 600
+    vocab = {"[UNK]": 0, "a": 1, "##" + long_piece: 2, long_piece: 3, "##b": 4, "ab": 5}
+    js = json.dumps({"model": {"type": "WordPiece", "vocab": vocab, "max_input_chars_per_word": 5000}})
+    t, o = pair(js)
+    docs = [long_piece.encode(), b"a" + long_piece.encode(), b"ab", b"a" + b"b" * 3, (long_piece + long_piece).encode()]
+    assert_same(t.encode_batch(docs), o.encode_batch(docs))
+    t.close()
+
+
+# ----------------------------------------------------------------------------- real-size tokenizers on corpus samples
+@pytest.mark.parametrize("name,cname,algo,nbytes", [("gpt2_whitespace", "c2", 0, 3 << 20), ("gpt2_bytelevel", "c2", 1, 3 << 20),
+                                                     ("bert_wordpiece", "c3", 0, 3 << 20), ("llama3_whitespace", "c4", 0, 2 << 20),
+                                                     ("llama3_sequence", "c4", 1, 2 << 20), ("gpt2_whitespace", "c5", 1, 6 << 20),
+                                                     ("gpt2_bytelevel", "c5", 1, 6 << 20)])
+def test_synthesised_tokenizers_on_corpus(name, cname, algo, nbytes):
+    js = tokenizers_io.tokenizer_json(name)
+    t, o = pair(js)
+    text, off = corpus.generate(cname, nbytes, seed=2024)
+    if name == "bert_wordpiece":
+        t.truncation = {"max_length": 512}
+        o.truncation = 512
+        t.padding = {"length": 64, "pad_id": 0}
+        o.padding = {"length": 64, "pad_id": 0}
+    got = t.encode_packed(text, off)
+    ref = o.encode_packed(text, off, algo=algo, threads=8)
+    assert_same(got, ref, name)
+    t.close()
+
+
+def test_batch_split_invariance_and_roundtrip_property():
+    """size-independent properties at a larger size: encoding a batch == concatenating the encodings of its halves, and
+    (BPE, no unk) the token strings of a document concatenate to the document minus the characters the vocab lacks."""
+    js = tokenizers_io.tokenizer_json("gpt2_whitespace")
+    t = tz.Tokenizer.from_json(js, device=0)
+    text, off = corpus.generate("c2", 48 << 20, seed=77)
+    full = t.encode_packed(text, off)
+    nd = len(off) - 1
+    h = nd // 2
+    a = t.encode_packed(text[: int(off[h])], off[: h + 1])
+    b = t.encode_packed(text[int(off[h]):], off[h:] - off[h])
+    assert np.array_equal(full.ids, np.concatenate([a.ids, b.ids]))
+    assert np.array_equal(full.offsets, np.concatenate([a.offsets, b.offsets]))
+    assert np.array_equal(full.doc_tok_off, np.concatenate([a.doc_tok_off, b.doc_tok_off[1:] + a.doc_tok_off[-1]]))
+    # round trip on a sample of documents
+    d = t.model_desc()
+    id2tok = {int(i): k for k, i in zip(d["keys"], d["ids"])}
+    single = {k for k in d["keys"] if len(k.decode("utf-8", "ignore")) == 1}
+    rng = random.Random(3)
+    raw = text.tobytes()
+    for i in rng.sample(range(nd), 200):
+        doc = raw[int(off[i]):int(off[i + 1])]
+        kept = b"".join(ch.encode() for w in doc.split() for ch in w.decode("utf-8") if ch.encode() in single)
+        sl = full.doc_slice(i)
+        assert b"".join(id2tok[int(x)] for x in full.ids[sl]) == kept
+    t.close()

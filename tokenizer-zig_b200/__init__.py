@@ -1,0 +1,470 @@
+"""tokzig_b200 -- Python (ctypes) face of the B200-native batch encoder for jrc2139/tokenizer-zig's encode path.
+
+The names mirror the reference's public API (/root/reference/src/lib.zig:32-224): ``Tokenizer.from_json`` /
+``from_file`` (fromJson / fromFile), ``encode(text, add_special_tokens)``, ``token_to_id``, ``id_to_token``,
+``get_vocab_size``, ``add_special_tokens``, and the public fields ``truncation`` / ``padding``; ``Encoding`` carries
+ids / type_ids / tokens / offsets / special_tokens_mask / attention_mask (src/encoding.zig:231-243).  ``encode_batch``
+is the batch form the GPU path exists for.  Everything computes on the GPU through the C ABI of
+include/tokzig_b200.h; there is no CPU fallback and the import fails loudly when the CUDA library is not built.
+
+The directory name contains a hyphen, so import it through ``tokzig_b200`` (the shim at the repo root).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "_lib", "libtokzig_b200.so")
+
+# status codes (include/tokzig_b200.h)
+OK, ERR_OOM, ERR_MISSING_UNK, ERR_INVALID_UTF8, ERR_CUDA, ERR_INVALID_ARG = 0, -1, -2, -3, -4, -5
+ERR_INVALID_JSON, ERR_MISSING_MODEL, ERR_UNSUPPORTED_MODEL, ERR_MISSING_VOCAB, ERR_INVALID_VOCAB_ENTRY, ERR_IO = -10, -11, -12, -13, -14, -20
+_ERR_NAMES = {ERR_OOM: "OutOfMemory", ERR_MISSING_UNK: "MissingUnkToken", ERR_INVALID_UTF8: "InvalidUtf8", ERR_CUDA: "CudaError",
+              ERR_INVALID_ARG: "InvalidArgument", ERR_INVALID_JSON: "InvalidJson", ERR_MISSING_MODEL: "MissingModel",
+              ERR_UNSUPPORTED_MODEL: "UnsupportedModelType", ERR_MISSING_VOCAB: "MissingVocab",
+              ERR_INVALID_VOCAB_ENTRY: "InvalidVocabEntry", ERR_IO: "IoError"}
+
+OUT_IDS, OUT_OFFSETS, OUT_ATTENTION, OUT_TYPE_IDS, OUT_SPECIAL, OUT_ALL = 1, 2, 4, 8, 16, 31
+NORM_CFG_LOWER, NORM_BERT_STRUCT, NORM_LOWER_STRUCT = 1, 2, 3
+PT_WS_CFG, PT_BERT_CFG, PT_WS_STRUCT, PT_BERT_STRUCT, PT_BYTELEVEL_STRUCT = 1, 2, 3, 4, 5
+MODEL_BPE, MODEL_WORDPIECE = 0, 1
+
+
+class TokzigError(Exception):
+    def __init__(self, code: int, msg: str = "", doc: int = -1):
+        self.code = code
+        self.name = _ERR_NAMES.get(code, str(code))
+        self.doc = doc
+        super().__init__(f"{self.name}: {msg}" if msg else self.name)
+
+
+class ModelDesc(C.Structure):
+    _fields_ = [
+        ("model_kind", C.c_int32),
+        ("norm_lut", C.POINTER(C.c_uint16)),
+        ("class_lut", C.POINTER(C.c_uint8)),
+        ("vocab_bytes", C.POINTER(C.c_uint8)),
+        ("vocab_off", C.POINTER(C.c_uint64)),
+        ("vocab_ids", C.POINTER(C.c_uint32)),
+        ("vocab_n", C.c_uint32),
+        ("merge_first", C.POINTER(C.c_uint32)),
+        ("merge_second", C.POINTER(C.c_uint32)),
+        ("merge_rank", C.POINTER(C.c_uint32)),
+        ("merge_new", C.POINTER(C.c_uint32)),
+        ("merges_n", C.c_uint32),
+        ("has_unk", C.c_int32),
+        ("unk_id", C.c_uint32),
+        ("prefix", C.POINTER(C.c_uint8)),
+        ("prefix_len", C.c_uint32),
+        ("max_input_chars_per_word", C.c_uint64),
+    ]
+
+
+class EncodeParams(C.Structure):
+    _fields_ = [
+        ("has_truncation", C.c_int32),
+        ("max_length", C.c_uint64),
+        ("has_padding", C.c_int32),
+        ("pad_length", C.c_uint64),
+        ("pad_id", C.c_uint32),
+        ("pad_type_id", C.c_uint32),
+        ("pad_left", C.c_int32),
+        ("outputs", C.c_uint32),
+    ]
+
+
+class BatchResult(C.Structure):
+    _fields_ = [
+        ("n_docs", C.c_uint64),
+        ("n_tokens", C.c_uint64),
+        ("n_real_tokens", C.c_uint64),
+        ("doc_tok_off", C.c_void_p),
+        ("ids", C.c_void_p),
+        ("offsets", C.c_void_p),
+        ("attention_mask", C.c_void_p),
+        ("type_ids", C.c_void_p),
+        ("special_tokens_mask", C.c_void_p),
+        ("err_doc", C.c_int64),
+    ]
+
+
+class Stats(C.Structure):
+    _fields_ = [("arena_bytes", C.c_uint64), ("n_words", C.c_uint64), ("n_unique_words", C.c_uint64),
+                ("n_long_words", C.c_uint64), ("kernel_launches", C.c_uint64),
+                ("ms_split", C.c_float), ("ms_model", C.c_float), ("ms_scan", C.c_float), ("ms_emit", C.c_float), ("ms_total", C.c_float)]
+
+
+# every symbol include/tokzig_b200.h declares (checked by tests/test_cabi_symbols.py)
+EXPORTED_SYMBOLS = [
+    "tkz_ctx_create", "tkz_ctx_destroy", "tkz_last_error", "tkz_ctx_get_stats", "tkz_model_upload", "tkz_encode_batch",
+    "tkz_encode_batch_device",
+    "tkzh_from_json", "tkzh_from_file", "tkzh_free", "tkzh_last_error", "tkzh_ctx", "tkzh_set_truncation", "tkzh_set_padding",
+    "tkzh_set_normalizer", "tkzh_set_pretokenizer", "tkzh_encode_batch", "tkzh_get_vocab_size", "tkzh_token_to_id",
+    "tkzh_id_to_token", "tkzh_add_special_tokens", "tkzh_model_vocab_count", "tkzh_merge_count", "tkzh_has_normalizer",
+    "tkzh_has_pretokenizer", "tkzh_has_post_processor", "tkzh_added_token_count", "tkzh_added_token", "tkzh_model_desc",
+]
+
+_lib = None
+
+
+def lib():
+    """Loads the in-tree CUDA library.  No fallback: a missing library is a hard error."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                          "(tokzig_b200 has no CPU fallback)")
+    L = C.CDLL(LIB_PATH)
+    vp, u64, u32, i32 = C.c_void_p, C.c_uint64, C.c_uint32, C.c_int
+    L.tkz_ctx_create.argtypes = [i32, vp, u64, C.POINTER(vp)]
+    L.tkz_ctx_destroy.argtypes = [vp]
+    L.tkz_last_error.argtypes = [vp]
+    L.tkz_last_error.restype = C.c_char_p
+    L.tkz_ctx_get_stats.argtypes = [vp, C.POINTER(Stats)]
+    L.tkz_model_upload.argtypes = [vp, C.POINTER(ModelDesc)]
+    L.tkz_encode_batch.argtypes = [vp, vp, vp, u64, C.POINTER(EncodeParams), C.POINTER(BatchResult)]
+    L.tkz_encode_batch_device.argtypes = [vp, vp, vp, u64, u64, C.POINTER(EncodeParams), C.POINTER(BatchResult)]
+    L.tkzh_from_json.argtypes = [C.c_char_p, u64, i32, vp, C.POINTER(vp)]
+    L.tkzh_from_file.argtypes = [C.c_char_p, i32, vp, C.POINTER(vp)]
+    L.tkzh_free.argtypes = [vp]
+    L.tkzh_last_error.argtypes = [vp]
+    L.tkzh_last_error.restype = C.c_char_p
+    L.tkzh_ctx.argtypes = [vp]
+    L.tkzh_ctx.restype = vp
+    L.tkzh_set_truncation.argtypes = [vp, i32, u64]
+    L.tkzh_set_padding.argtypes = [vp, i32, i32, u64, u32, u32, i32]
+    L.tkzh_set_normalizer.argtypes = [vp, vp, vp, C.c_int32]
+    L.tkzh_set_pretokenizer.argtypes = [vp, vp, C.c_int32]
+    L.tkzh_encode_batch.argtypes = [vp, vp, vp, u64, i32, u32, C.POINTER(BatchResult)]
+    L.tkzh_get_vocab_size.argtypes = [vp]
+    L.tkzh_get_vocab_size.restype = u64
+    L.tkzh_token_to_id.argtypes = [vp, C.c_char_p, u64, C.POINTER(u32)]
+    L.tkzh_id_to_token.argtypes = [vp, u32, C.POINTER(vp), C.POINTER(u64)]
+    L.tkzh_add_special_tokens.argtypes = [vp, C.c_char_p, vp, u64, C.POINTER(u64)]
+    L.tkzh_model_vocab_count.argtypes = [vp]
+    L.tkzh_model_vocab_count.restype = u64
+    L.tkzh_merge_count.argtypes = [vp]
+    L.tkzh_merge_count.restype = u64
+    for f in ("tkzh_has_normalizer", "tkzh_has_pretokenizer", "tkzh_has_post_processor"):
+        getattr(L, f).argtypes = [vp]
+    L.tkzh_added_token_count.argtypes = [vp]
+    L.tkzh_added_token_count.restype = u64
+    L.tkzh_added_token.argtypes = [vp, u64, C.POINTER(vp), C.POINTER(u64), C.POINTER(C.c_int64), C.POINTER(i32)]
+    L.tkzh_model_desc.argtypes = [vp, C.POINTER(ModelDesc)]
+    _lib = L
+    return L
+
+
+def _copy(ptr, n, dtype):
+    if not ptr or n == 0:
+        return np.zeros(0, dtype)
+    buf = (C.c_uint8 * (n * np.dtype(dtype).itemsize)).from_address(ptr)
+    return np.frombuffer(buf, dtype=dtype, count=n).copy()
+
+
+# --------------------------------------------------------------------------- results
+@dataclass
+class Encoding:
+    """src/encoding.zig:231-243 (words is always null and overflowing always empty in the reference)."""
+    ids: np.ndarray
+    type_ids: np.ndarray
+    tokens: List[bytes]
+    offsets: np.ndarray              # (n, 2) u32, byte offsets into the normalised pre-token
+    special_tokens_mask: np.ndarray
+    attention_mask: np.ndarray
+
+    def __len__(self):
+        return len(self.ids)
+
+    def get_ids(self):
+        return self.ids
+
+    def get_tokens(self):
+        return self.tokens
+
+    def get_attention_mask(self):
+        return self.attention_mask
+
+
+@dataclass
+class BatchEncoding:
+    """CSR over documents (tkz_batch_result)."""
+    doc_tok_off: np.ndarray
+    ids: np.ndarray
+    offsets: Optional[np.ndarray]
+    attention_mask: Optional[np.ndarray]
+    type_ids: Optional[np.ndarray]
+    special_tokens_mask: Optional[np.ndarray]
+    n_real_tokens: int = 0
+
+    def __len__(self):
+        return len(self.doc_tok_off) - 1
+
+    def doc_slice(self, i):
+        return slice(int(self.doc_tok_off[i]), int(self.doc_tok_off[i + 1]))
+
+
+def _result_to_batch(r: BatchResult) -> BatchEncoding:
+    T, n = int(r.n_tokens), int(r.n_docs)
+    offs = _copy(r.offsets, 2 * T, np.uint32).reshape(-1, 2) if r.offsets else None
+    return BatchEncoding(
+        doc_tok_off=_copy(r.doc_tok_off, n + 1, np.uint64),
+        ids=_copy(r.ids, T, np.uint32),
+        offsets=offs,
+        attention_mask=_copy(r.attention_mask, T, np.uint32) if r.attention_mask else None,
+        type_ids=_copy(r.type_ids, T, np.uint32) if r.type_ids else None,
+        special_tokens_mask=_copy(r.special_tokens_mask, T, np.uint32) if r.special_tokens_mask else None,
+        n_real_tokens=int(r.n_real_tokens),
+    )
+
+
+def pack_docs(docs: Sequence[bytes]):
+    lens = np.fromiter((len(d) for d in docs), dtype=np.uint64, count=len(docs))
+    off = np.zeros(len(docs) + 1, dtype=np.uint64)
+    np.cumsum(lens, out=off[1:])
+    text = np.frombuffer(b"".join(docs), dtype=np.uint8) if len(docs) else np.zeros(0, np.uint8)
+    return np.ascontiguousarray(text), off
+
+
+# --------------------------------------------------------------------------- device layer
+class Context:
+    """tkz_ctx: one per GPU.  ``stream`` is a raw cudaStream_t (e.g. torch.cuda.current_stream().cuda_stream) or 0."""
+
+    def __init__(self, device: int = 0, stream: int = 0):
+        self._L = lib()
+        h = C.c_void_p()
+        rc = self._L.tkz_ctx_create(device, C.c_void_p(stream) if stream else None, 0, C.byref(h))
+        if rc != OK:
+            raise TokzigError(rc, (self._L.tkz_last_error(None) or b"").decode())
+        self._h = h
+        self.device = device
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.tkz_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _err(self):
+        return (self._L.tkz_last_error(self._h) or b"").decode()
+
+    def upload(self, desc: ModelDesc):
+        rc = self._L.tkz_model_upload(self._h, C.byref(desc))
+        if rc != OK:
+            raise TokzigError(rc, self._err())
+
+    def stats(self) -> Stats:
+        s = Stats()
+        self._L.tkz_ctx_get_stats(self._h, C.byref(s))
+        return s
+
+    def encode_batch(self, text: np.ndarray, doc_off: np.ndarray, params: Optional[EncodeParams] = None) -> BatchEncoding:
+        """Host buffers in, host arrays out (tkz_encode_batch)."""
+        text = np.ascontiguousarray(text, dtype=np.uint8)
+        doc_off = np.ascontiguousarray(doc_off, dtype=np.uint64)
+        r = BatchResult()
+        p = params if params is not None else EncodeParams()
+        rc = self._L.tkz_encode_batch(self._h, text.ctypes.data if text.size else None, doc_off.ctypes.data, len(doc_off) - 1,
+                                      C.byref(p), C.byref(r))
+        if rc != OK:
+            raise TokzigError(rc, self._err(), int(r.err_doc))
+        return _result_to_batch(r)
+
+    def encode_batch_device(self, d_text_ptr: int, d_doc_off_ptr: int, n_docs: int, text_bytes: int,
+                            params: Optional[EncodeParams] = None) -> BatchResult:
+        """Device pointers in, device pointers out (tkz_encode_batch_device); returns the raw result struct."""
+        r = BatchResult()
+        p = params if params is not None else EncodeParams()
+        rc = self._L.tkz_encode_batch_device(self._h, C.c_void_p(d_text_ptr), C.c_void_p(d_doc_off_ptr), n_docs, text_bytes,
+                                             C.byref(p), C.byref(r))
+        if rc != OK:
+            raise TokzigError(rc, self._err(), int(r.err_doc))
+        return r
+
+
+# --------------------------------------------------------------------------- host mirror of src/lib.zig
+class Tokenizer:
+    """Tokenizer (src/lib.zig:32-224) on the GPU.  ``device=None`` loads the configuration only."""
+
+    def __init__(self, handle, L):
+        self._h = handle
+        self._L = L
+        self.truncation: Optional[dict] = None     # {"max_length": 512}          src/types.zig:55-59
+        self.padding: Optional[dict] = None        # {"length":..,"pad_id":..,"pad_type_id":..,"direction":"right"}  src/types.zig:39-45
+
+    @classmethod
+    def from_json(cls, json_content, device: Optional[int] = 0, stream: int = 0) -> "Tokenizer":
+        L = lib()
+        if isinstance(json_content, str):
+            json_content = json_content.encode("utf-8", "surrogatepass")
+        h = C.c_void_p()
+        rc = L.tkzh_from_json(json_content, len(json_content), -1 if device is None else device, C.c_void_p(stream) if stream else None, C.byref(h))
+        if rc != OK:
+            raise TokzigError(rc, (L.tkzh_last_error(None) or b"").decode())
+        return cls(h, L)
+
+    @classmethod
+    def from_file(cls, path: str, device: Optional[int] = 0, stream: int = 0) -> "Tokenizer":
+        L = lib()
+        h = C.c_void_p()
+        rc = L.tkzh_from_file(path.encode(), -1 if device is None else device, C.c_void_p(stream) if stream else None, C.byref(h))
+        if rc != OK:
+            raise TokzigError(rc, (L.tkzh_last_error(None) or b"").decode())
+        return cls(h, L)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.tkzh_free(self._h)
+            self._h = None
+
+    deinit = close
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- hand-wiring (normalizer_impl / pretokenizer_impl are public fields in the reference)
+    def set_normalizer(self, ops: Optional[Sequence]):
+        """ops: None (no normalizer) or a list of (kind, flags) -- a list is a normalizer.Sequence."""
+        if ops is None:
+            self._L.tkzh_set_normalizer(self._h, None, None, -1)
+            return
+        k = np.array([o[0] for o in ops], dtype=np.int32)
+        f = np.array([o[1] for o in ops], dtype=np.int32)
+        self._L.tkzh_set_normalizer(self._h, k.ctypes.data if len(ops) else None, f.ctypes.data if len(ops) else None, len(ops))
+
+    def set_pretokenizer(self, ops: Optional[Sequence[int]]):
+        if ops is None:
+            self._L.tkzh_set_pretokenizer(self._h, None, -1)
+            return
+        k = np.array(list(ops), dtype=np.int32)
+        self._L.tkzh_set_pretokenizer(self._h, k.ctypes.data if len(ops) else None, len(ops))
+
+    def _push_params(self):
+        if self.truncation is None:
+            self._L.tkzh_set_truncation(self._h, 0, 0)
+        else:
+            self._L.tkzh_set_truncation(self._h, 1, int(self.truncation.get("max_length", 512)))
+        if self.padding is None:
+            self._L.tkzh_set_padding(self._h, 0, 0, 0, 0, 0, 0)
+        else:
+            p = self.padding
+            length = p.get("length")
+            self._L.tkzh_set_padding(self._h, 1, 0 if length is None else 1, 0 if length is None else int(length), int(p.get("pad_id", 0)),
+                                     int(p.get("pad_type_id", 0)), 1 if p.get("direction", "right") == "left" else 0)
+
+    def encode_packed(self, text: np.ndarray, doc_off: np.ndarray, add_special_tokens: bool = True, outputs: int = OUT_ALL) -> BatchEncoding:
+        self._push_params()
+        text = np.ascontiguousarray(text, dtype=np.uint8)
+        doc_off = np.ascontiguousarray(doc_off, dtype=np.uint64)
+        r = BatchResult()
+        rc = self._L.tkzh_encode_batch(self._h, text.ctypes.data if text.size else None, doc_off.ctypes.data, len(doc_off) - 1,
+                                       1 if add_special_tokens else 0, outputs, C.byref(r))
+        if rc != OK:
+            raise TokzigError(rc, (self._L.tkzh_last_error(self._h) or b"").decode(), int(r.err_doc))
+        return _result_to_batch(r)
+
+    def encode_batch(self, docs: Sequence, add_special_tokens: bool = True, outputs: int = OUT_ALL) -> BatchEncoding:
+        text, off = pack_docs([d if isinstance(d, (bytes, bytearray)) else d.encode("utf-8") for d in docs])
+        return self.encode_packed(text, off, add_special_tokens, outputs)
+
+    def encode(self, text, add_special_tokens: bool = True) -> Encoding:
+        """Tokenizer.encode (src/lib.zig:109-160)."""
+        b = self.encode_batch([text], add_special_tokens)
+        pad_token = (self.padding or {}).get("pad_token", "[PAD]")
+        toks = []
+        for i, a in zip(b.ids.tolist(), b.attention_mask.tolist()):
+            if a == 0:
+                toks.append(pad_token.encode() if isinstance(pad_token, str) else pad_token)     # encoding.zig:410,421
+            else:
+                toks.append(self._model_id_to_token(i) or b"")                                    # bpe.zig:258, wordpiece.zig:200-205
+        return Encoding(b.ids, b.type_ids, toks, b.offsets, b.special_tokens_mask, b.attention_mask)
+
+    # -- lookups (src/lib.zig:203-223)
+    def get_vocab_size(self) -> int:
+        return int(self._L.tkzh_get_vocab_size(self._h))
+
+    def token_to_id(self, token) -> Optional[int]:
+        t = token.encode() if isinstance(token, str) else token
+        out = C.c_uint32(0)
+        return int(out.value) if self._L.tkzh_token_to_id(self._h, t, len(t), C.byref(out)) else None
+
+    def id_to_token(self, i: int) -> Optional[bytes]:
+        p, n = C.c_void_p(), C.c_uint64(0)
+        if not self._L.tkzh_id_to_token(self._h, i, C.byref(p), C.byref(n)):
+            return None
+        return C.string_at(p.value, n.value) if n.value else b""
+
+    def _model_id_to_token(self, i: int) -> Optional[bytes]:
+        return self.id_to_token(i)
+
+    def add_special_tokens(self, tokens: Sequence) -> int:
+        bs = [t.encode() if isinstance(t, str) else t for t in tokens]
+        off = np.zeros(len(bs) + 1, dtype=np.uint64)
+        np.cumsum(np.array([len(b) for b in bs], dtype=np.uint64), out=off[1:])
+        added = C.c_uint64(0)
+        self._L.tkzh_add_special_tokens(self._h, b"".join(bs), off.ctypes.data, len(bs), C.byref(added))
+        return int(added.value)
+
+    # -- loader facts
+    def model_vocab_count(self) -> int:
+        return int(self._L.tkzh_model_vocab_count(self._h))
+
+    def merge_count(self) -> int:
+        return int(self._L.tkzh_merge_count(self._h))
+
+    def has_normalizer(self) -> bool:
+        return bool(self._L.tkzh_has_normalizer(self._h))
+
+    def has_pretokenizer(self) -> bool:
+        return bool(self._L.tkzh_has_pretokenizer(self._h))
+
+    def has_post_processor(self) -> bool:
+        return bool(self._L.tkzh_has_post_processor(self._h))
+
+    def added_tokens(self):
+        out = []
+        for i in range(int(self._L.tkzh_added_token_count(self._h))):
+            p, n, idv, sp = C.c_void_p(), C.c_uint64(0), C.c_int64(0), C.c_int(0)
+            self._L.tkzh_added_token(self._h, i, C.byref(p), C.byref(n), C.byref(idv), C.byref(sp))
+            out.append((C.string_at(p.value, n.value) if n.value else b"", None if idv.value < 0 else int(idv.value), bool(sp.value)))
+        return out
+
+    def model_desc(self) -> dict:
+        """The flattened model exactly as it is uploaded to the GPU, as numpy arrays (for loader parity tests)."""
+        d = ModelDesc()
+        self._L.tkzh_model_desc(self._h, C.byref(d))
+        n, mn = d.vocab_n, d.merges_n
+        off = np.ctypeslib.as_array(d.vocab_off, shape=(n + 1,)).copy() if n else np.zeros(1, np.uint64)
+        blob = bytes(np.ctypeslib.as_array(d.vocab_bytes, shape=(int(off[-1]),))) if n and off[-1] else b""
+        keys = [blob[int(off[i]):int(off[i + 1])] for i in range(n)]
+        ids = np.ctypeslib.as_array(d.vocab_ids, shape=(n,)).copy() if n else np.zeros(0, np.uint32)
+
+        def arr(p):
+            return np.ctypeslib.as_array(p, shape=(mn,)).copy() if mn else np.zeros(0, np.uint32)
+
+        return dict(
+            model_kind=d.model_kind, keys=keys, ids=ids,
+            merges=np.stack([arr(d.merge_first), arr(d.merge_second), arr(d.merge_rank), arr(d.merge_new)], axis=1) if mn else np.zeros((0, 4), np.uint32),
+            has_unk=bool(d.has_unk), unk_id=int(d.unk_id),
+            prefix=bytes(np.ctypeslib.as_array(d.prefix, shape=(d.prefix_len,))) if d.prefix_len else b"",
+            max_chars=int(d.max_input_chars_per_word),
+            norm_lut=np.ctypeslib.as_array(d.norm_lut, shape=(256,)).copy() if d.norm_lut else None,
+            class_lut=np.ctypeslib.as_array(d.class_lut, shape=(256,)).copy() if d.class_lut else None,
+        )
+
+    def context_handle(self):
+        return self._L.tkzh_ctx(self._h)

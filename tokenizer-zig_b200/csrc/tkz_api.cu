@@ -1,0 +1,515 @@
+// tkz_api.cu -- device layer of the C ABI (include/tokzig_b200.h): context, device arenas, model upload, and the
+// batch-encode pipeline that replaces the caller loop over Tokenizer.encode (src/lib.zig:109-160):
+//
+//   [K0 normalise-compact]  only when the normalizer drops bytes (struct BertNormalizer, normalizer.zig:47-73)
+//   K1 split                byte-class scan -> pre-token spans            (config.zig:364-457, pretokenizer.zig:49-241)
+//   K3 bpe / K4 wordpiece   one warp per pre-token -> tokens in the pool  (bpe.zig:173-263 / wordpiece.zig:141-222)
+//   scans                   tokens per word -> per document -> CSR offsets
+//   K5 emit                 fromTokens + truncate + pad fused in the write (encoding.zig:246-294, 363-463)
+//
+// There is no CPU fallback: without a usable CUDA device every entry point fails with TKZ_ERR_CUDA.
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/tokzig_b200.h"
+#include "tkz_bpe.cuh"
+#include "tkz_common.cuh"
+#include "tkz_emit.cuh"
+#include "tkz_scan.cuh"
+#include "tkz_split.cuh"
+#include "tkz_wordpiece.cuh"
+
+using namespace tkz;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+};
+struct HostBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+};
+
+}  // namespace
+
+struct tkz_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int sm_count = 148;
+    std::string err;
+    bool has_model = false;
+    DevModel dm{}, dm_post{};
+    // model tables
+    DevBuf t_lut, t_lut_post, t_char_ascii, t_char_tab, t_merges, t_wp_tab, t_wp_pool;
+    // arenas (grow-only; replace src/arena.zig)
+    DevBuf a_text, a_doc_off, a_norm_text, a_norm_doc_off, a_chunk, a_tiles, a_word_start, a_word_end, a_word_doc, a_doc_word_off,
+        a_word_ntok, a_pool_id, a_pool_s, a_pool_e, a_pool_rk, a_scan_tmp, a_doc_tok_off, a_out_ids, a_out_off, a_out_attn,
+        a_out_type, a_out_special, a_ctrl;
+    HostBuf h_ctrl, h_doc_tok_off, h_ids, h_off, h_attn, h_type, h_special;
+    uint64_t arena_bytes = 0;
+    tkz_stats stats{};
+    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // stage boundaries of the last encode
+};
+
+namespace {
+
+#define CK(call)                                                                                     \
+    do {                                                                                             \
+        cudaError_t e__ = (call);                                                                    \
+        if (e__ != cudaSuccess) {                                                                    \
+            ctx->err = std::string(#call) + ": " + cudaGetErrorString(e__);                          \
+            return e__ == cudaErrorMemoryAllocation ? TKZ_ERR_OOM : TKZ_ERR_CUDA;                    \
+        }                                                                                            \
+    } while (0)
+
+int ensure(tkz_ctx* ctx, DevBuf& b, size_t bytes) {
+    if (bytes == 0) bytes = 16;
+    if (b.cap >= bytes) return TKZ_OK;
+    if (b.p) { CK(cudaStreamSynchronize(ctx->stream)); CK(cudaFree(b.p)); ctx->arena_bytes -= b.cap; b.p = nullptr; b.cap = 0; }
+    size_t want = bytes + bytes / 8 + 256;      // head-room so steady-state batches of similar size do not re-allocate
+    cudaError_t e = cudaMalloc(&b.p, want);
+    if (e != cudaSuccess) { want = bytes; e = cudaMalloc(&b.p, want); }
+    if (e != cudaSuccess) { ctx->err = std::string("cudaMalloc: ") + cudaGetErrorString(e); b.p = nullptr; return TKZ_ERR_OOM; }
+    b.cap = want; ctx->arena_bytes += want;
+    return TKZ_OK;
+}
+int ensure_host(tkz_ctx* ctx, HostBuf& b, size_t bytes) {
+    if (bytes == 0) bytes = 16;
+    if (b.cap >= bytes) return TKZ_OK;
+    if (b.p) { CK(cudaStreamSynchronize(ctx->stream)); CK(cudaFreeHost(b.p)); b.p = nullptr; b.cap = 0; }
+    size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaHostAlloc(&b.p, want, cudaHostAllocDefault);
+    if (e != cudaSuccess) { ctx->err = std::string("cudaHostAlloc: ") + cudaGetErrorString(e); b.p = nullptr; return TKZ_ERR_OOM; }
+    b.cap = want;
+    return TKZ_OK;
+}
+void release(DevBuf& b) { if (b.p) cudaFree(b.p); b.p = nullptr; b.cap = 0; }
+void release_host(HostBuf& b) { if (b.p) cudaFreeHost(b.p); b.p = nullptr; b.cap = 0; }
+
+#define TRY(x) do { int rc__ = (x); if (rc__ != TKZ_OK) return rc__; } while (0)
+
+int upload(tkz_ctx* ctx, DevBuf& b, const void* src, size_t bytes) {
+    TRY(ensure(ctx, b, bytes));
+    if (bytes) CK(cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    return TKZ_OK;
+}
+
+uint32_t pow2_at_least(uint64_t n) { uint32_t c = 2; while (c < n) c <<= 1; return c; }
+
+__global__ void ctrl_reset_kernel(unsigned long long* ctrl) {
+    // ctrl[0] = error word, ctrl[1] = work counter (u32 view), ctrl[2..] = read-back scalars
+    ctrl[0] = TKZ_ERRW_NONE; ctrl[1] = 0; ctrl[2] = 0; ctrl[3] = 0; ctrl[4] = 0;
+}
+__global__ void gather_scalars_kernel(unsigned long long* ctrl, const uint32_t* word_tok_off, uint32_t n_words,
+                                      const unsigned long long* doc_tok_off, uint32_t n_docs, const uint32_t* word_doc) {
+    ctrl[2] = word_tok_off[n_words];
+    ctrl[3] = doc_tok_off[n_docs];
+    const unsigned long long ew = ctrl[0];
+    ctrl[4] = (ew != TKZ_ERRW_NONE && n_words) ? word_doc[(uint32_t)(ew >> 8)] : 0;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------ context
+extern "C" int tkz_ctx_create(int device, void* stream, uint64_t arena_hint_bytes, tkz_ctx** out) {
+    if (!out) return TKZ_ERR_INVALID_ARG;
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        g_create_error = std::string("no CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0") +
+                         " (tokzig_b200 has no CPU fallback)";
+        return TKZ_ERR_CUDA;
+    }
+    if (device < 0 || device >= n) { g_create_error = "invalid device ordinal"; return TKZ_ERR_INVALID_ARG; }
+    e = cudaSetDevice(device);
+    if (e != cudaSuccess) { g_create_error = std::string("cudaSetDevice: ") + cudaGetErrorString(e); return TKZ_ERR_CUDA; }
+    tkz_ctx* ctx = new tkz_ctx();
+    ctx->device = device;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
+    if (stream) { ctx->stream = (cudaStream_t)stream; ctx->own_stream = false; }
+    else {
+        e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+        if (e != cudaSuccess) { g_create_error = std::string("cudaStreamCreate: ") + cudaGetErrorString(e); delete ctx; return TKZ_ERR_CUDA; }
+        ctx->own_stream = true;
+    }
+    e = cudaFuncSetAttribute(bpe_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BPE_SMEM_BYTES);
+    if (e != cudaSuccess) {
+        g_create_error = std::string("kernel image not usable on this device (built for sm_100a): ") + cudaGetErrorString(e);
+        if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+        delete ctx; return TKZ_ERR_CUDA;
+    }
+    if (ensure(ctx, ctx->a_ctrl, 64 * sizeof(unsigned long long)) != TKZ_OK || ensure_host(ctx, ctx->h_ctrl, 64 * sizeof(unsigned long long)) != TKZ_OK) {
+        g_create_error = ctx->err; if (ctx->own_stream) cudaStreamDestroy(ctx->stream); delete ctx; return TKZ_ERR_OOM;
+    }
+    (void)arena_hint_bytes;
+    for (auto& ev : ctx->ev) cudaEventCreate(&ev);
+    *out = ctx;
+    return TKZ_OK;
+}
+
+extern "C" void tkz_ctx_destroy(tkz_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    DevBuf* bufs[] = {&ctx->t_lut, &ctx->t_lut_post, &ctx->t_char_ascii, &ctx->t_char_tab, &ctx->t_merges, &ctx->t_wp_tab, &ctx->t_wp_pool,
+                      &ctx->a_text, &ctx->a_doc_off, &ctx->a_norm_text, &ctx->a_norm_doc_off, &ctx->a_chunk, &ctx->a_tiles, &ctx->a_word_start,
+                      &ctx->a_word_end, &ctx->a_word_doc, &ctx->a_doc_word_off, &ctx->a_word_ntok, &ctx->a_pool_id, &ctx->a_pool_s, &ctx->a_pool_e,
+                      &ctx->a_pool_rk, &ctx->a_scan_tmp, &ctx->a_doc_tok_off, &ctx->a_out_ids, &ctx->a_out_off, &ctx->a_out_attn, &ctx->a_out_type,
+                      &ctx->a_out_special, &ctx->a_ctrl};
+    for (DevBuf* b : bufs) release(*b);
+    HostBuf* hb[] = {&ctx->h_ctrl, &ctx->h_doc_tok_off, &ctx->h_ids, &ctx->h_off, &ctx->h_attn, &ctx->h_type, &ctx->h_special};
+    for (HostBuf* b : hb) release_host(*b);
+    for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+extern "C" const char* tkz_last_error(tkz_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+extern "C" int tkz_ctx_get_stats(tkz_ctx* ctx, tkz_stats* out) {
+    if (!ctx || !out) return TKZ_ERR_INVALID_ARG;
+    *out = ctx->stats; out->arena_bytes = ctx->arena_bytes;
+    return TKZ_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ model upload
+extern "C" int tkz_model_upload(tkz_ctx* ctx, const tkz_model_desc* d) {
+    if (!ctx || !d) return TKZ_ERR_INVALID_ARG;
+    CK(cudaSetDevice(ctx->device));
+    if (d->model_kind != TKZ_MODEL_BPE && d->model_kind != TKZ_MODEL_WORDPIECE) { ctx->err = "unknown model_kind"; return TKZ_ERR_INVALID_ARG; }
+    if (d->vocab_n && (!d->vocab_bytes || !d->vocab_off || !d->vocab_ids)) { ctx->err = "vocab arrays missing"; return TKZ_ERR_INVALID_ARG; }
+    DevModel m{};
+    m.kind = d->model_kind;
+    m.has_pretok = d->class_lut != nullptr;
+    // ---- byte pipeline LUTs: [0,256) normalised byte, [256,512) class of the raw byte, [512,768) dropped flag
+    std::vector<uint8_t> lut(768, 0), lut_post(768, 0);
+    bool identity = true, has_drop = false;
+    for (int b = 0; b < 256; b++) {
+        uint16_t nb = d->norm_lut ? d->norm_lut[b] : (uint16_t)b;
+        const bool drop = nb == TKZ_NORM_DROP;
+        if (!drop && nb > 0xFF) { ctx->err = "norm_lut entry out of range"; return TKZ_ERR_INVALID_ARG; }
+        if (drop) { has_drop = true; nb = 0; }
+        if (nb != b || drop) identity = false;
+        lut[b] = (uint8_t)nb;
+        lut[512 + b] = drop ? 1 : 0;
+        uint8_t c = d->class_lut ? d->class_lut[nb] : (uint8_t)TKZ_CLS_WORD;
+        if (c > 2) { ctx->err = "class_lut entry out of range"; return TKZ_ERR_INVALID_ARG; }
+        lut[256 + b] = drop ? (uint8_t)TKZ_CLS_DELIM : c;
+        lut_post[b] = (uint8_t)b;
+        lut_post[256 + b] = d->class_lut ? d->class_lut[b] : (uint8_t)TKZ_CLS_WORD;
+    }
+    m.norm_identity = identity; m.norm_has_drop = has_drop;
+    TRY(upload(ctx, ctx->t_lut, lut.data(), lut.size()));
+    TRY(upload(ctx, ctx->t_lut_post, lut_post.data(), lut_post.size()));
+    m.lut = (const uint8_t*)ctx->t_lut.p;
+    m.has_unk = d->has_unk; m.unk_id = d->unk_id;
+
+    if (d->model_kind == TKZ_MODEL_BPE) {
+        // single-codepoint keys (bpe.zig:192: only the bytes of one UTF-8 sequence are ever looked up)
+        std::vector<uint32_t> ascii(128, TKZ_NONE);
+        std::vector<std::pair<uint32_t, uint32_t>> multi;
+        for (uint32_t i = 0; i < d->vocab_n; i++) {
+            const uint64_t a = d->vocab_off[i], len = d->vocab_off[i + 1] - a;
+            if (len < 1 || len > 4) continue;
+            const uint8_t* k = d->vocab_bytes + a;
+            if ((uint64_t)utf8_seq_len(k[0]) != len) continue;
+            if (len == 1) ascii[k[0]] = d->vocab_ids[i];
+            else { uint32_t key = 0; for (uint64_t j = 0; j < len; j++) key |= (uint32_t)k[j] << (8 * j); multi.push_back({key, d->vocab_ids[i]}); }
+        }
+        const uint32_t ccap = pow2_at_least(multi.size() * 2 + 2);
+        std::vector<CharEnt> ctab(ccap, CharEnt{0, 0});
+        for (auto& kv : multi) {
+            uint32_t s = char_hash32(kv.first) & (ccap - 1);
+            while (ctab[s].key != 0 && ctab[s].key != kv.first) s = (s + 1) & (ccap - 1);
+            ctab[s].key = kv.first; ctab[s].id = kv.second;            // put: later entry overwrites
+        }
+        TRY(upload(ctx, ctx->t_char_ascii, ascii.data(), ascii.size() * 4));
+        TRY(upload(ctx, ctx->t_char_tab, ctab.data(), ctab.size() * sizeof(CharEnt)));
+        m.char_ascii = (const uint32_t*)ctx->t_char_ascii.p; m.char_tab = (const CharEnt*)ctx->t_char_tab.p; m.char_mask = ccap - 1;
+        // merges (bpe.zig:40): put semantics, later entry for the same pair overwrites (config.zig:269)
+        if (d->merges_n && (!d->merge_first || !d->merge_second || !d->merge_rank || !d->merge_new)) { ctx->err = "merge arrays missing"; return TKZ_ERR_INVALID_ARG; }
+        const uint32_t mcap = pow2_at_least((uint64_t)d->merges_n * 2 + 2);
+        std::vector<MergeEnt> mtab(mcap, MergeEnt{0, 0, TKZ_NONE, 0});
+        uint32_t live = 0;
+        for (uint32_t i = 0; i < d->merges_n; i++) {
+            const uint32_t a = d->merge_first[i], b = d->merge_second[i], r = d->merge_rank[i];
+            if (r == TKZ_DIRTY) { ctx->err = "merge rank 0xFFFFFFFE is reserved"; return TKZ_ERR_INVALID_ARG; }
+            uint32_t s = pair_hash32(a, b) & (mcap - 1);
+            while (mtab[s].rank != TKZ_NONE && !(mtab[s].first == a && mtab[s].second == b)) s = (s + 1) & (mcap - 1);
+            if (mtab[s].rank == TKZ_NONE) {
+                if (r == TKZ_NONE) continue;      // rank maxInt(u32) can never win the strict `<` of bpe.zig:225: same as absent
+                live++;
+            } else if (r == TKZ_NONE) {
+                // overwritten by an unselectable rank: keep the slot occupied (probe chains) but make it never match a rank
+                // by storing the reserved value; handled as "no rank" by giving it the largest selectable rank is NOT exact,
+                // so re-build without the pair instead.
+                ctx->err = "merge rank 0xFFFFFFFF overwriting an earlier rank is not supported"; return TKZ_ERR_INVALID_ARG;
+            }
+            mtab[s] = MergeEnt{a, b, r, d->merge_new[i]};
+        }
+        TRY(upload(ctx, ctx->t_merges, mtab.data(), mtab.size() * sizeof(MergeEnt)));
+        m.merges = (const MergeEnt*)ctx->t_merges.p; m.merge_mask = mcap - 1; m.n_merges = live;
+    } else {
+        if (d->prefix_len > TKZ_MAX_PREFIX) { ctx->err = "continuing_subword_prefix longer than 64 bytes"; return TKZ_ERR_INVALID_ARG; }
+        m.prefix_len = d->prefix_len;
+        uint64_t st = TKZ_FNV_OFFSET;
+        for (uint32_t i = 0; i < d->prefix_len; i++) { m.prefix[i] = d->prefix[i]; st = fnv1a_step(st, d->prefix[i]); }
+        m.prefix_state = st;
+        m.max_chars = d->max_input_chars_per_word;
+        const uint32_t wcap = pow2_at_least((uint64_t)d->vocab_n * 2 + 2);
+        std::vector<WpEnt> wtab(wcap, WpEnt{0, 0, 0, 0, 0});
+        uint32_t max_first = 0, max_cont = 0;
+        const uint64_t pool_bytes = d->vocab_n ? d->vocab_off[d->vocab_n] : 0;
+        if (pool_bytes >= 0xFFFFFFFFull) { ctx->err = "vocabulary larger than 4 GiB"; return TKZ_ERR_INVALID_ARG; }
+        for (uint32_t i = 0; i < d->vocab_n; i++) {
+            const uint64_t a = d->vocab_off[i], len = d->vocab_off[i + 1] - a;
+            const uint8_t* k = d->vocab_bytes + a;
+            uint64_t h = TKZ_FNV_OFFSET;
+            for (uint64_t j = 0; j < len; j++) h = fnv1a_step(h, k[j]);
+            uint32_t s = wp_slot(h) & (wcap - 1);
+            while (wtab[s].used && !(wtab[s].hash == h && wtab[s].len == len && memcmp(d->vocab_bytes + wtab[s].str_off, k, len) == 0)) s = (s + 1) & (wcap - 1);
+            wtab[s] = WpEnt{h, d->vocab_ids[i], (uint32_t)a, (uint32_t)len, 1u};       // put: later entry overwrites
+            if (len > max_first) max_first = (uint32_t)len;
+            if (len >= d->prefix_len && (d->prefix_len == 0 || memcmp(k, d->prefix, d->prefix_len) == 0)) {
+                const uint32_t c = (uint32_t)(len - d->prefix_len);
+                if (c > max_cont) max_cont = c;
+            }
+        }
+        TRY(upload(ctx, ctx->t_wp_tab, wtab.data(), wtab.size() * sizeof(WpEnt)));
+        TRY(upload(ctx, ctx->t_wp_pool, d->vocab_bytes, (size_t)pool_bytes));
+        m.wp_tab = (const WpEnt*)ctx->t_wp_tab.p; m.wp_mask = wcap - 1; m.wp_pool = (const uint8_t*)ctx->t_wp_pool.p;
+        m.max_key_first = max_first; m.max_key_cont = max_cont;
+    }
+    CK(cudaStreamSynchronize(ctx->stream));      // host staging vectors die at return
+    ctx->dm = m;
+    ctx->dm_post = m;
+    ctx->dm_post.lut = (const uint8_t*)ctx->t_lut_post.p;
+    ctx->dm_post.norm_identity = 1; ctx->dm_post.norm_has_drop = 0;
+    ctx->has_model = true;
+    return TKZ_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ encode
+namespace {
+
+int encode_device_impl(tkz_ctx* ctx, const uint8_t* d_text, const uint64_t* d_doc_off, uint64_t n_docs, uint64_t N,
+                       const tkz_encode_params* params, tkz_batch_result* out) {
+    memset(out, 0, sizeof *out);
+    out->err_doc = -1;
+    if (!ctx->has_model) { ctx->err = "no model uploaded"; return TKZ_ERR_INVALID_ARG; }
+    if (N >= 0xFFFFF000ull) { ctx->err = "batch text must be < 4 GiB (u32 offsets, types.zig:4-6): split the batch"; return TKZ_ERR_INVALID_ARG; }
+    if (n_docs >= 0xFFFFFFF0ull) { ctx->err = "too many documents in one batch"; return TKZ_ERR_INVALID_ARG; }
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    uint64_t launches = 0;
+    tkz_encode_params P{};
+    if (params) P = *params;
+    if (P.outputs == 0) P.outputs = TKZ_OUT_ALL;
+    P.outputs |= TKZ_OUT_IDS;
+    const uint32_t nd = (uint32_t)n_docs;
+    DevModel m = ctx->dm;
+
+    // misaligned text: stage into the arena (the split scan uses 16-byte vector loads)
+    if (((uintptr_t)d_text & 15u) != 0 && N) {
+        TRY(ensure(ctx, ctx->a_text, N));
+        CK(cudaMemcpyAsync(ctx->a_text.p, d_text, N, cudaMemcpyDeviceToDevice, st));
+        d_text = (const uint8_t*)ctx->a_text.p;
+    }
+    unsigned long long* ctrl = (unsigned long long*)ctx->a_ctrl.p;
+    unsigned long long* hctrl = (unsigned long long*)ctx->h_ctrl.p;
+    CK(cudaEventRecord(ctx->ev[0], st));
+    ctrl_reset_kernel<<<1, 1, 0, st>>>(ctrl); launches++;
+
+    // ---- K0: normalizer that drops bytes
+    if (m.norm_has_drop) {
+        const uint64_t n_chunks = N / NORM_CHUNK + 1;
+        TRY(ensure(ctx, ctx->a_chunk, (n_chunks + 1) * 4));
+        TRY(ensure(ctx, ctx->a_scan_tmp, scan_tmp_elems(n_chunks) * 8));
+        TRY(ensure(ctx, ctx->a_norm_text, N));
+        TRY(ensure(ctx, ctx->a_norm_doc_off, (n_docs + 1) * 8));
+        uint32_t* chunk = (uint32_t*)ctx->a_chunk.p;
+        norm_count_kernel<<<(unsigned)n_chunks, 256, 0, st>>>(m, d_text, N, chunk); launches++;
+        launches += exclusive_scan<uint32_t>(chunk, n_chunks, chunk, (unsigned long long*)ctx->a_scan_tmp.p, st);
+        norm_write_kernel<<<(unsigned)n_chunks, 256, 0, st>>>(m, d_text, N, chunk, (uint8_t*)ctx->a_norm_text.p); launches++;
+        norm_docoff_kernel<<<(unsigned)((n_docs + 1 + 255) / 256), 256, 0, st>>>(m, d_text, N, chunk, d_doc_off, nd, (uint64_t*)ctx->a_norm_doc_off.p); launches++;
+        CK(cudaMemcpyAsync(hctrl + 8, chunk + n_chunks, 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        N = *(uint32_t*)(hctrl + 8);
+        d_text = (const uint8_t*)ctx->a_norm_text.p;
+        d_doc_off = (const uint64_t*)ctx->a_norm_doc_off.p;
+        m = ctx->dm_post;
+    }
+
+    // ---- K1: pre-token spans
+    uint64_t W = 0;
+    TRY(ensure(ctx, ctx->a_doc_word_off, (n_docs + 1) * 4));
+    uint32_t* doc_word_off = (uint32_t*)ctx->a_doc_word_off.p;
+    if (m.has_pretok) {
+        const uint64_t n_tiles = N / SPLIT_TILE + 1;
+        TRY(ensure(ctx, ctx->a_tiles, (n_tiles + 1) * 8));
+        TRY(ensure(ctx, ctx->a_scan_tmp, scan_tmp_elems(n_tiles) * 8));
+        unsigned long long* tiles = (unsigned long long*)ctx->a_tiles.p;
+        split_count_kernel<<<(unsigned)n_tiles, SPLIT_THREADS, 0, st>>>(m, d_text, N, d_doc_off, nd, tiles); launches++;
+        launches += exclusive_scan<unsigned long long>(tiles, n_tiles, tiles, (unsigned long long*)ctx->a_scan_tmp.p, st);
+        CK(cudaMemcpyAsync(hctrl + 8, tiles + n_tiles, 8, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        const unsigned long long tot = hctrl[8];
+        W = tot >> 32;
+        if ((tot & 0xFFFFFFFFull) != W) { ctx->err = "internal: word start/end counts differ"; return TKZ_ERR_CUDA; }
+        TRY(ensure(ctx, ctx->a_word_start, (W + 1) * 4));
+        TRY(ensure(ctx, ctx->a_word_end, (W + 1) * 4));
+        TRY(ensure(ctx, ctx->a_word_doc, (W + 1) * 4));
+        split_write_kernel<<<(unsigned)n_tiles, SPLIT_THREADS, 0, st>>>(m, d_text, N, d_doc_off, nd, tiles, (uint32_t*)ctx->a_word_start.p,
+                                                                        (uint32_t*)ctx->a_word_end.p, (uint32_t*)ctx->a_word_doc.p, doc_word_off); launches++;
+    } else {
+        W = n_docs;
+        TRY(ensure(ctx, ctx->a_word_start, (W + 1) * 4));
+        TRY(ensure(ctx, ctx->a_word_end, (W + 1) * 4));
+        TRY(ensure(ctx, ctx->a_word_doc, (W + 1) * 4));
+        words_from_docs_kernel<<<(unsigned)((n_docs + 1 + 255) / 256), 256, 0, st>>>(d_doc_off, nd, (uint32_t*)ctx->a_word_start.p,
+                                                                                     (uint32_t*)ctx->a_word_end.p, (uint32_t*)ctx->a_word_doc.p, doc_word_off); launches++;
+    }
+    const uint32_t nw = (uint32_t)W;
+    uint32_t* word_start = (uint32_t*)ctx->a_word_start.p;
+    uint32_t* word_end = (uint32_t*)ctx->a_word_end.p;
+    uint32_t* word_doc = (uint32_t*)ctx->a_word_doc.p;
+
+    CK(cudaEventRecord(ctx->ev[1], st));
+    // ---- K3 / K4: model, one warp per pre-token
+    TRY(ensure(ctx, ctx->a_word_ntok, (W + 2) * 4));
+    TRY(ensure(ctx, ctx->a_pool_id, N * 4));
+    TRY(ensure(ctx, ctx->a_pool_s, N * 4));
+    TRY(ensure(ctx, ctx->a_pool_e, N * 4));
+    uint32_t* word_ntok = (uint32_t*)ctx->a_word_ntok.p;
+    unsigned int* work_counter = (unsigned int*)(ctrl + 1);
+    if (nw) {
+        if (m.kind == TKZ_MODEL_BPE) {
+            TRY(ensure(ctx, ctx->a_pool_rk, N * 4));
+            BpeArgs a{d_text, word_start, word_end, nw, (uint32_t*)ctx->a_pool_id.p, (uint32_t*)ctx->a_pool_s.p, (uint32_t*)ctx->a_pool_e.p,
+                      (uint32_t*)ctx->a_pool_rk.p, word_ntok, work_counter, ctrl};
+            uint64_t blocks = (W + BPE_WARPS - 1) / BPE_WARPS;
+            const uint64_t cap = (uint64_t)ctx->sm_count * 3;
+            if (blocks > cap) blocks = cap;
+            bpe_warp_kernel<<<(unsigned)blocks, BPE_WARPS * 32, BPE_SMEM_BYTES, st>>>(m, a); launches++;
+        } else {
+            WpArgs a{d_text, word_start, word_end, nw, (uint32_t*)ctx->a_pool_id.p, (uint32_t*)ctx->a_pool_s.p, (uint32_t*)ctx->a_pool_e.p,
+                     word_ntok, work_counter, ctrl};
+            uint64_t blocks = (W + WP_WARPS - 1) / WP_WARPS;
+            const uint64_t cap = (uint64_t)ctx->sm_count * 8;
+            if (blocks > cap) blocks = cap;
+            wordpiece_warp_kernel<<<(unsigned)blocks, WP_WARPS * 32, 0, st>>>(m, a); launches++;
+        }
+    }
+
+    CK(cudaEventRecord(ctx->ev[2], st));
+    // ---- scans: tokens per word -> per document -> CSR
+    TRY(ensure(ctx, ctx->a_scan_tmp, (scan_tmp_elems(W) + scan_tmp_elems(n_docs)) * 8));
+    launches += exclusive_scan<uint32_t>(word_ntok, W, word_ntok, (unsigned long long*)ctx->a_scan_tmp.p, st);
+    const uint32_t* word_tok_off = word_ntok;
+    TRY(ensure(ctx, ctx->a_doc_tok_off, (n_docs + 1) * 8));
+    unsigned long long* doc_tok_off = (unsigned long long*)ctx->a_doc_tok_off.p;
+    EmitParams ep{P.has_truncation, P.max_length, P.has_padding, P.pad_length, P.pad_id, P.pad_type_id, P.pad_left, P.outputs};
+    if (nd) { doc_len_kernel<<<(nd + 255) / 256, 256, 0, st>>>(ep, word_tok_off, doc_word_off, nd, doc_tok_off); launches++; }
+    launches += exclusive_scan<unsigned long long>(doc_tok_off, n_docs, doc_tok_off, (unsigned long long*)ctx->a_scan_tmp.p, st);
+    gather_scalars_kernel<<<1, 1, 0, st>>>(ctrl, word_tok_off, nw, doc_tok_off, nd, word_doc); launches++;
+    CK(cudaMemcpyAsync(hctrl, ctrl, 5 * 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    const unsigned long long errw = hctrl[0];
+    const uint64_t T_real = hctrl[2], T = hctrl[3];
+    ctx->stats.n_words = W; ctx->stats.n_unique_words = W; ctx->stats.n_long_words = 0;
+    if (errw != TKZ_ERRW_NONE) {
+        out->err_doc = (int64_t)hctrl[4];
+        const uint32_t code = (uint32_t)(errw & 0xFF);
+        ctx->err = code == TKZ_ECODE_UTF8 ? "invalid UTF-8 in a BPE pre-token (reference behaviour undefined)" : "MissingUnkToken";
+        ctx->stats.kernel_launches = launches;
+        return code == TKZ_ECODE_UTF8 ? TKZ_ERR_INVALID_UTF8 : TKZ_ERR_MISSING_UNK;
+    }
+
+    CK(cudaEventRecord(ctx->ev[3], st));
+    // ---- K5: emit
+    TRY(ensure(ctx, ctx->a_out_ids, T * 4));
+    if (P.outputs & TKZ_OUT_OFFSETS) TRY(ensure(ctx, ctx->a_out_off, T * 8));
+    if (P.outputs & TKZ_OUT_ATTENTION) TRY(ensure(ctx, ctx->a_out_attn, T * 4));
+    if (P.outputs & TKZ_OUT_TYPE_IDS) TRY(ensure(ctx, ctx->a_out_type, T * 4));
+    if (P.outputs & TKZ_OUT_SPECIAL) TRY(ensure(ctx, ctx->a_out_special, T * 4));
+    EmitOut eo{(uint32_t*)ctx->a_out_ids.p, (uint32_t*)ctx->a_out_off.p, (uint32_t*)ctx->a_out_attn.p, (uint32_t*)ctx->a_out_type.p,
+               (uint32_t*)ctx->a_out_special.p};
+    if (nw) {
+        emit_words_kernel<<<(nw + 255) / 256, 256, 0, st>>>(ep, eo, nw, word_start, word_doc, word_tok_off, doc_word_off, doc_tok_off,
+                                                            (const uint32_t*)ctx->a_pool_id.p, (const uint32_t*)ctx->a_pool_s.p,
+                                                            (const uint32_t*)ctx->a_pool_e.p); launches++;
+    }
+    if (P.has_padding && nd) {
+        emit_pad_kernel<<<(unsigned)(((uint64_t)nd * 32 + 255) / 256), 256, 0, st>>>(ep, eo, nd, word_tok_off, doc_word_off, doc_tok_off); launches++;
+    }
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(ctx->ev[4], st));
+    CK(cudaStreamSynchronize(st));
+    ctx->stats.kernel_launches = launches;
+    cudaEventElapsedTime(&ctx->stats.ms_split, ctx->ev[0], ctx->ev[1]);
+    cudaEventElapsedTime(&ctx->stats.ms_model, ctx->ev[1], ctx->ev[2]);
+    cudaEventElapsedTime(&ctx->stats.ms_scan, ctx->ev[2], ctx->ev[3]);
+    cudaEventElapsedTime(&ctx->stats.ms_emit, ctx->ev[3], ctx->ev[4]);
+    cudaEventElapsedTime(&ctx->stats.ms_total, ctx->ev[0], ctx->ev[4]);
+    out->n_docs = n_docs; out->n_tokens = T; out->n_real_tokens = T_real;
+    out->doc_tok_off = (const uint64_t*)doc_tok_off;
+    out->ids = eo.ids;
+    out->offsets = (P.outputs & TKZ_OUT_OFFSETS) ? eo.offsets : nullptr;
+    out->attention_mask = (P.outputs & TKZ_OUT_ATTENTION) ? eo.attention : nullptr;
+    out->type_ids = (P.outputs & TKZ_OUT_TYPE_IDS) ? eo.type_ids : nullptr;
+    out->special_tokens_mask = (P.outputs & TKZ_OUT_SPECIAL) ? eo.special : nullptr;
+    return TKZ_OK;
+}
+
+}  // namespace
+
+extern "C" int tkz_encode_batch_device(tkz_ctx* ctx, const void* d_text, const void* d_doc_off, uint64_t n_docs, uint64_t text_bytes,
+                                       const tkz_encode_params* params, tkz_batch_result* out) {
+    if (!ctx || !out || !d_doc_off || (text_bytes && !d_text)) return TKZ_ERR_INVALID_ARG;
+    return encode_device_impl(ctx, (const uint8_t*)d_text, (const uint64_t*)d_doc_off, n_docs, text_bytes, params, out);
+}
+
+extern "C" int tkz_encode_batch(tkz_ctx* ctx, const uint8_t* text, const uint64_t* doc_off, uint64_t n_docs,
+                                const tkz_encode_params* params, tkz_batch_result* out) {
+    if (!ctx || !out || !doc_off) return TKZ_ERR_INVALID_ARG;
+    if (doc_off[0] != 0) { ctx->err = "doc_off[0] must be 0"; return TKZ_ERR_INVALID_ARG; }
+    const uint64_t N = doc_off[n_docs];
+    if (N && !text) return TKZ_ERR_INVALID_ARG;
+    CK(cudaSetDevice(ctx->device));
+    TRY(ensure(ctx, ctx->a_text, N));
+    TRY(ensure(ctx, ctx->a_doc_off, (n_docs + 1) * 8));
+    if (N) CK(cudaMemcpyAsync(ctx->a_text.p, text, N, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->a_doc_off.p, doc_off, (n_docs + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+    tkz_batch_result dev{};
+    int rc = encode_device_impl(ctx, (const uint8_t*)ctx->a_text.p, (const uint64_t*)ctx->a_doc_off.p, n_docs, N, params, &dev);
+    *out = dev;
+    out->doc_tok_off = nullptr; out->ids = nullptr; out->offsets = nullptr; out->attention_mask = nullptr; out->type_ids = nullptr;
+    out->special_tokens_mask = nullptr;
+    if (rc != TKZ_OK) return rc;
+    const uint64_t T = dev.n_tokens;
+    cudaStream_t st = ctx->stream;
+    TRY(ensure_host(ctx, ctx->h_doc_tok_off, (n_docs + 1) * 8));
+    CK(cudaMemcpyAsync(ctx->h_doc_tok_off.p, dev.doc_tok_off, (n_docs + 1) * 8, cudaMemcpyDeviceToHost, st));
+    out->doc_tok_off = (const uint64_t*)ctx->h_doc_tok_off.p;
+    struct { const uint32_t* src; HostBuf* hb; const uint32_t** dst; size_t elem; } cp[] = {
+        {dev.ids, &ctx->h_ids, &out->ids, 4}, {dev.offsets, &ctx->h_off, &out->offsets, 8},
+        {dev.attention_mask, &ctx->h_attn, &out->attention_mask, 4}, {dev.type_ids, &ctx->h_type, &out->type_ids, 4},
+        {dev.special_tokens_mask, &ctx->h_special, &out->special_tokens_mask, 4}};
+    for (auto& c : cp) {
+        if (!c.src) continue;
+        TRY(ensure_host(ctx, *c.hb, T * c.elem));
+        if (T) CK(cudaMemcpyAsync(c.hb->p, c.src, T * c.elem, cudaMemcpyDeviceToHost, st));
+        *c.dst = (const uint32_t*)c.hb->p;
+    }
+    CK(cudaStreamSynchronize(st));
+    return TKZ_OK;
+}

@@ -1,0 +1,112 @@
+// tkz_emit.cuh -- K5: Encoding.fromTokens + truncate + pad fused into the output write.
+//
+// Replaces Encoding.fromTokens (src/encoding.zig:246-294: ids, type_ids = 0, offsets, special_token_mask = 0,
+// attention_mask = 1), Encoding.truncate (src/encoding.zig:363-380: keep the first max_length, stride ignored) and
+// Encoding.pad (src/encoding.zig:385-463: right / left fill with pad_id, pad_type_id, offset (0,0), special 1,
+// attention 0; no-op when already long enough).  Post-processing inserts nothing (src/config.zig:551-555).
+// Output is CSR over documents: slots of document d = [doc_tok_off[d], doc_tok_off[d+1]).
+#pragma once
+#include "tkz_common.cuh"
+
+namespace tkz {
+
+struct EmitParams {
+    int has_trunc; unsigned long long max_length;
+    int has_pad; unsigned long long pad_length;
+    uint32_t pad_id, pad_type_id; int pad_left;
+    uint32_t outputs;
+};
+
+// slots a document occupies after truncate + pad
+__device__ __forceinline__ unsigned long long doc_out_len(const EmitParams& p, unsigned long long t, unsigned long long* kept) {
+    unsigned long long k = t;
+    if (p.has_trunc && k > p.max_length) k = p.max_length;
+    *kept = k;
+    return (p.has_pad && k < p.pad_length) ? p.pad_length : k;
+}
+
+// per document: real token count -> output slot count
+__global__ void doc_len_kernel(EmitParams p, const uint32_t* __restrict__ word_tok_off, const uint32_t* __restrict__ doc_word_off, uint32_t n_docs,
+                               unsigned long long* __restrict__ doc_len) {
+    const uint32_t d = blockIdx.x * blockDim.x + threadIdx.x;
+    if (d >= n_docs) return;
+    const unsigned long long t = word_tok_off[doc_word_off[d + 1]] - word_tok_off[doc_word_off[d]];
+    unsigned long long kept;
+    doc_len[d] = doc_out_len(p, t, &kept);
+}
+
+struct EmitOut { uint32_t* ids; uint32_t* offsets; uint32_t* attention; uint32_t* type_ids; uint32_t* special; };
+
+__device__ __forceinline__ void emit_real(const EmitParams& p, const EmitOut& o, unsigned long long dst, uint32_t id, uint32_t s, uint32_t e) {
+    o.ids[dst] = id;
+    if (p.outputs & 2u) reinterpret_cast<uint2*>(o.offsets)[dst] = make_uint2(s, e);
+    if (p.outputs & 4u) o.attention[dst] = 1u;
+    if (p.outputs & 8u) o.type_ids[dst] = 0u;
+    if (p.outputs & 16u) o.special[dst] = 0u;
+}
+
+// one lane per word; words with many tokens are copied by the whole warp
+__global__ void __launch_bounds__(256) emit_words_kernel(EmitParams p, EmitOut o, uint32_t n_words,
+                                                         const uint32_t* __restrict__ word_start, const uint32_t* __restrict__ word_doc,
+                                                         const uint32_t* __restrict__ word_tok_off, const uint32_t* __restrict__ doc_word_off,
+                                                         const unsigned long long* __restrict__ doc_tok_off,
+                                                         const uint32_t* __restrict__ pool_id, const uint32_t* __restrict__ pool_s,
+                                                         const uint32_t* __restrict__ pool_e) {
+    const uint32_t FULL = 0xFFFFFFFFu;
+    const uint32_t lane = lane_id();
+    const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t cnt = 0, src = 0; unsigned long long dst = 0; unsigned long long room = 0;
+    if (w < n_words) {
+        const uint32_t t0 = word_tok_off[w];
+        cnt = word_tok_off[w + 1] - t0;
+        if (cnt) {
+            const uint32_t d = word_doc[w];
+            const unsigned long long doc_t0 = word_tok_off[doc_word_off[d]];
+            const unsigned long long doc_t = (unsigned long long)word_tok_off[doc_word_off[d + 1]] - doc_t0;
+            unsigned long long kept;
+            const unsigned long long olen = doc_out_len(p, doc_t, &kept);
+            const unsigned long long j0 = (unsigned long long)t0 - doc_t0;          // index of the word's first token in its document
+            room = j0 < kept ? kept - j0 : 0;                                       // truncation: tokens j >= kept are dropped
+            const unsigned long long shift = (p.has_pad && p.pad_left) ? olen - kept : 0;
+            dst = doc_tok_off[d] + shift + j0;
+            src = word_start[w];
+            if ((unsigned long long)cnt > room) cnt = (uint32_t)room;
+        }
+    }
+    // short words: each lane copies its own tokens
+    if (cnt > 0 && cnt <= 4) {
+        for (uint32_t k = 0; k < cnt; k++) emit_real(p, o, dst + k, pool_id[src + k], pool_s[src + k], pool_e[src + k]);
+    }
+    // long words: warp-cooperative copy
+    uint32_t big = __ballot_sync(FULL, cnt > 4);
+    while (big) {
+        const int l = __ffs(big) - 1; big &= big - 1;
+        const uint32_t c = __shfl_sync(FULL, cnt, l), s = __shfl_sync(FULL, src, l);
+        const unsigned long long dd = __shfl_sync(FULL, dst, l);
+        for (uint32_t k = lane; k < c; k += 32) emit_real(p, o, dd + k, pool_id[s + k], pool_s[s + k], pool_e[s + k]);
+    }
+}
+
+// padding slots, one warp per document (src/encoding.zig:407-414, 418-425)
+__global__ void __launch_bounds__(256) emit_pad_kernel(EmitParams p, EmitOut o, uint32_t n_docs, const uint32_t* __restrict__ word_tok_off,
+                                                       const uint32_t* __restrict__ doc_word_off, const unsigned long long* __restrict__ doc_tok_off) {
+    const uint32_t d = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t lane = lane_id();
+    if (d >= n_docs) return;
+    const unsigned long long t = word_tok_off[doc_word_off[d + 1]] - word_tok_off[doc_word_off[d]];
+    unsigned long long kept;
+    const unsigned long long olen = doc_out_len(p, t, &kept);
+    if (olen == kept) return;
+    const unsigned long long base = doc_tok_off[d] + (p.pad_left ? 0 : kept);
+    const unsigned long long npad = olen - kept;
+    for (unsigned long long k = lane; k < npad; k += 32) {
+        const unsigned long long dst = base + k;
+        o.ids[dst] = p.pad_id;
+        if (p.outputs & 2u) reinterpret_cast<uint2*>(o.offsets)[dst] = make_uint2(0u, 0u);
+        if (p.outputs & 4u) o.attention[dst] = 0u;
+        if (p.outputs & 8u) o.type_ids[dst] = p.pad_type_id;
+        if (p.outputs & 16u) o.special[dst] = 1u;
+    }
+}
+
+}  // namespace tkz
