@@ -1,0 +1,83 @@
+"""Multi-GPU host logic on CPU: byte-balanced document sharding (no collective on the data path) and, with two gloo
+ranks, that concatenating the per-rank encodings in rank order reproduces the single-process result.  The per-rank
+encode is stood in for by the oracle here (this container has no GPU); the GPU run of the same property is
+tests/test_gpu_parity.py::test_batch_split_invariance_and_roundtrip_property."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+import tokzig_b200 as tz
+from tools import corpus
+
+
+def test_shard_bounds_properties():
+    rng = np.random.default_rng(0)
+    for _ in range(50):
+        nd = int(rng.integers(0, 200))
+        lens = rng.integers(0, 5000, size=nd) * (rng.random(nd) < 0.9)
+        off = np.zeros(nd + 1, dtype=np.uint64)
+        np.cumsum(lens, out=off[1:])
+        for world in (1, 2, 3, 8):
+            b = tz.shard_bounds(off, world)
+            assert b[0] == 0 and b[-1] == nd and np.all(np.diff(b) >= 0)
+            if nd and off[-1] > 0:
+                sizes = off[b[1:]].astype(np.int64) - off[b[:-1]].astype(np.int64)
+                assert sizes.sum() == int(off[-1])
+                # no shard is further from its target cut than the largest document
+                assert np.abs(sizes - int(off[-1]) / world).max() <= lens.max() + 1
+
+
+def test_skewed_corpus_balance():
+    text, off = corpus.generate("c2", 8 << 20, 5)
+    b = tz.shard_bounds(off, 8)
+    sizes = off[b[1:]].astype(np.int64) - off[b[:-1]].astype(np.int64)
+    assert sizes.max() / sizes.mean() < 1.05
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import torch
+    import torch.distributed as dist
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from oracle import oracle as orc
+    from tools import tokenizers_io
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    text, off = corpus.generate("c2", 1 << 20, 42)
+    o = orc.OracleTokenizer.from_json(tokenizers_io.tokenizer_json("gpt2_whitespace"))
+    t_s, off_s, (lo, hi) = tz.shard(text, off, rank, world)
+    enc = o.encode_packed(t_s, off_s)
+    # "results are gathered to host only for verification": gather object lists on rank 0
+    gathered = [None] * world
+    dist.gather_object((lo, hi, enc.ids, enc.offsets, enc.doc_tok_off), gathered if rank == 0 else None, dst=0)
+    # timing plumbing used by bench.py: max over ranks
+    t = torch.tensor([float(rank + 1)], dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    assert t.item() == world
+    if rank == 0:
+        full = o.encode_packed(text, off)
+        ids = np.concatenate([g[2] for g in gathered])
+        offs = np.concatenate([g[3] for g in gathered])
+        dto, acc = [np.zeros(1, np.uint64)], 0
+        for g in gathered:
+            dto.append(g[4][1:] + np.uint64(acc)); acc += int(g[4][-1])
+        ok = (np.array_equal(ids, full.ids) and np.array_equal(offs, full.offsets) and np.array_equal(np.concatenate(dto), full.doc_tok_off)
+              and gathered[0][0] == 0 and gathered[-1][1] == len(off) - 1 and all(gathered[i][1] == gathered[i + 1][0] for i in range(world - 1)))
+        q.put(ok)
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_sharded_encode_matches_single():
+    import torch.multiprocessing as mp
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(180)
+        assert p.exitcode == 0
+    assert q.get(timeout=10) is True

@@ -468,3 +468,29 @@ class Tokenizer:
 
     def context_handle(self):
         return self._L.tkzh_ctx(self._h)
+
+
+# --------------------------------------------------------------------------- multi-GPU sharding (host logic, no collective)
+def shard_bounds(doc_off: np.ndarray, n_shards: int) -> np.ndarray:
+    """Byte-balanced contiguous document ranges (north star: "sharded ... by byte-balanced ranges with no collective"):
+    shard k takes documents [b[k], b[k+1]), cut at the document boundary nearest to k * total / n_shards."""
+    doc_off = np.asarray(doc_off, dtype=np.uint64)
+    nd = len(doc_off) - 1
+    total = int(doc_off[-1]) - int(doc_off[0])
+    b = np.zeros(n_shards + 1, dtype=np.int64)
+    for k in range(1, n_shards):
+        target = int(doc_off[0]) + (total * k) // n_shards
+        i = int(np.searchsorted(doc_off, target, side="left"))
+        if i > 0 and i <= nd and (target - int(doc_off[i - 1])) < (int(doc_off[min(i, nd)]) - target):
+            i -= 1
+        b[k] = max(b[k - 1], min(i, nd))
+    b[n_shards] = nd
+    return b
+
+
+def shard(text: np.ndarray, doc_off: np.ndarray, rank: int, world: int):
+    """The (text, doc_off) slice rank `rank` of `world` encodes; offsets rebased to 0."""
+    b = shard_bounds(doc_off, world)
+    lo, hi = int(b[rank]), int(b[rank + 1])
+    base = int(doc_off[lo])
+    return text[base:int(doc_off[hi])], (np.asarray(doc_off[lo:hi + 1], dtype=np.uint64) - np.uint64(base)), (lo, hi)

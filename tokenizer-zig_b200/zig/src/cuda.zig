@@ -1,0 +1,93 @@
+//! cuda.zig -- `extern fn` mirror of include/tokzig_b200.h (device layer only).
+//! The host side of tokenizer-zig stays in Zig: src/lib.zig keeps its public API and calls these symbols, which
+//! build.zig links from the static sm_100a library (libtokzig_b200.a) plus cudart.
+//! NOT COMPILED in the build image (no zig toolchain there): kept a 1:1 transcription of the C header so review is
+//! mechanical.
+
+pub const Ctx = opaque {};
+
+pub const OK: c_int = 0;
+pub const ERR_OOM: c_int = -1; // error.OutOfMemory
+pub const ERR_MISSING_UNK: c_int = -2; // error.MissingUnkToken (src/model/wordpiece.zig:150,212)
+pub const ERR_INVALID_UTF8: c_int = -3; // reference: unreachable in Utf8Iterator (src/model/bpe.zig:186-187)
+pub const ERR_CUDA: c_int = -4;
+pub const ERR_INVALID_ARG: c_int = -5;
+
+pub const MODEL_BPE: i32 = 0;
+pub const MODEL_WORDPIECE: i32 = 1;
+pub const CLS_WORD: u8 = 0;
+pub const CLS_DELIM: u8 = 1;
+pub const CLS_ISOLATE: u8 = 2;
+pub const NORM_DROP: u16 = 0xFFFF;
+
+pub const OUT_IDS: u32 = 1;
+pub const OUT_OFFSETS: u32 = 2;
+pub const OUT_ATTENTION: u32 = 4;
+pub const OUT_TYPE_IDS: u32 = 8;
+pub const OUT_SPECIAL: u32 = 16;
+pub const OUT_ALL: u32 = 31;
+
+pub const ModelDesc = extern struct {
+    model_kind: i32,
+    norm_lut: ?[*]const u16, // [256] or null
+    class_lut: ?[*]const u8, // [256] or null
+    vocab_bytes: ?[*]const u8,
+    vocab_off: ?[*]const u64,
+    vocab_ids: ?[*]const u32,
+    vocab_n: u32,
+    merge_first: ?[*]const u32,
+    merge_second: ?[*]const u32,
+    merge_rank: ?[*]const u32,
+    merge_new: ?[*]const u32,
+    merges_n: u32,
+    has_unk: i32,
+    unk_id: u32,
+    prefix: ?[*]const u8,
+    prefix_len: u32,
+    max_input_chars_per_word: u64,
+};
+
+pub const EncodeParams = extern struct {
+    has_truncation: i32 = 0,
+    max_length: u64 = 0,
+    has_padding: i32 = 0,
+    pad_length: u64 = 0,
+    pad_id: u32 = 0,
+    pad_type_id: u32 = 0,
+    pad_left: i32 = 0,
+    outputs: u32 = OUT_ALL,
+};
+
+pub const BatchResult = extern struct {
+    n_docs: u64,
+    n_tokens: u64,
+    n_real_tokens: u64,
+    doc_tok_off: ?[*]const u64,
+    ids: ?[*]const u32,
+    offsets: ?[*]const u32,
+    attention_mask: ?[*]const u32,
+    type_ids: ?[*]const u32,
+    special_tokens_mask: ?[*]const u32,
+    err_doc: i64,
+};
+
+pub const Stats = extern struct {
+    arena_bytes: u64,
+    n_words: u64,
+    n_unique_words: u64,
+    n_long_words: u64,
+    kernel_launches: u64,
+    ms_split: f32,
+    ms_model: f32,
+    ms_scan: f32,
+    ms_emit: f32,
+    ms_total: f32,
+};
+
+pub extern fn tkz_ctx_create(device: c_int, stream: ?*anyopaque, arena_hint_bytes: u64, out: *?*Ctx) c_int;
+pub extern fn tkz_ctx_destroy(ctx: ?*Ctx) void;
+pub extern fn tkz_last_error(ctx: ?*Ctx) [*:0]const u8;
+pub extern fn tkz_ctx_get_stats(ctx: *Ctx, out: *Stats) c_int;
+pub extern fn tkz_model_upload(ctx: *Ctx, desc: *const ModelDesc) c_int;
+pub extern fn tkz_encode_batch(ctx: *Ctx, text: ?[*]const u8, doc_off: [*]const u64, n_docs: u64, params: *const EncodeParams, out: *BatchResult) c_int;
+pub extern fn tkz_encode_batch_device(ctx: *Ctx, d_text: ?*const anyopaque, d_doc_off: *const anyopaque, n_docs: u64, text_bytes: u64, params: *const EncodeParams, out: *BatchResult) c_int;
