@@ -30,8 +30,16 @@ def assert_same(got: tz.BatchEncoding, ref: orc.BatchEncoding, what=""):
     assert np.array_equal(got.special_tokens_mask, ref.special_tokens_mask), f"{what}: special_tokens_mask"
 
 
-def pair(js):
-    return tz.Tokenizer.from_json(js, device=0), orc.OracleTokenizer.from_json(js)
+def pair(js, dedup=True):
+    """(GPU tokenizer, oracle).  dedup=False forces the per-occurrence pipeline (the context reads TKZ_NO_DEDUP when it
+    is created), so both device pipelines are held to the same oracle."""
+    import os
+    os.environ["TKZ_NO_DEDUP"] = "0" if dedup else "1"
+    try:
+        t = tz.Tokenizer.from_json(js, device=0)
+    finally:
+        os.environ["TKZ_NO_DEDUP"] = "0"
+    return t, orc.OracleTokenizer.from_json(js)
 
 
 # ----------------------------------------------------------------------------- the reference's known-answer vectors
@@ -75,7 +83,7 @@ def test_bpe_random(seed):
                               improper=[0.0, 0.3, 0.0, 0.5][mode], degenerate=[0.0, 0.0, 0.3, 0.2][mode], alias=[0.0, 0.0, 0.1, 0.2][mode],
                               pretok=[None, "Whitespace", "BertPreTokenizer", "ByteLevel"][(seed // 4) % 4],
                               normalizer=[None, "Lowercase"][(seed // 16) % 2])
-    t, o = pair(js)
+    t, o = pair(js, dedup=seed % 3 != 0)
     docs = rand_docs(rng, alpha, 400, max_len=90, p_upper=0.2)
     assert_same(t.encode_batch(docs), o.encode_batch(docs), f"seed {seed}")
     t.close()
@@ -87,7 +95,7 @@ def test_wordpiece_random(seed):
     js, alpha = rand_wp_json(rng, n_words=rng.randint(5, 120), prefix=["##", "", "@@@", "#"][seed % 4], max_chars=[None, 4, 7, 100][(seed // 4) % 4],
                              pretok=["BertPreTokenizer", "Whitespace", None, "BertPreTokenizer"][(seed // 2) % 4],
                              normalizer=["BertNormalizer", None][(seed // 8) % 2])
-    t, o = pair(js)
+    t, o = pair(js, dedup=seed % 3 != 0)
     docs = rand_docs(rng, alpha, 400, max_len=70, p_upper=0.3)
     assert_same(t.encode_batch(docs), o.encode_batch(docs), f"seed {seed}")
     t.close()
@@ -100,7 +108,7 @@ def test_truncation_and_padding(seed):
         js, alpha = rand_wp_json(rng)
     else:
         js, alpha = rand_bpe_json(rng, n_merges=30, pretok="Whitespace")
-    t, o = pair(js)
+    t, o = pair(js, dedup=seed % 4 != 3)
     docs = rand_docs(rng, alpha, 300, max_len=60)
     trunc = [None, 0, 1, 5, 8, 64][seed % 6]
     pad = [None, {"length": 8, "pad_id": 7, "pad_type_id": 3, "direction": "right"}, {"length": 5, "pad_id": 0, "direction": "left"},
@@ -128,7 +136,7 @@ def test_struct_chains(seed):
         js, alpha = rand_wp_json(rng, pretok=None, normalizer=None)
     else:
         js, alpha = rand_bpe_json(rng, n_merges=30, unk="<unk>" if seed % 4 == 0 else None)
-    t, o = pair(js)
+    t, o = pair(js, dedup=seed % 3 != 1)
     nn = [rng.choice(list(tzn)) for _ in range(rng.randint(0, 3))]
     fl = [rng.randint(0, 3) for _ in nn]
     pn = [rng.choice(list(tzp)) for _ in range(rng.randint(0, 3))]
@@ -152,18 +160,20 @@ def _fix_utf8(b: bytes) -> bytes:
 
 
 # ----------------------------------------------------------------------------- edge cases
-def test_empty_and_ragged_inputs():
+@pytest.mark.parametrize("dedup", [True, False])
+def test_empty_and_ragged_inputs(dedup):
     js, alpha = rand_bpe_json(random.Random(1), n_merges=20, pretok="Whitespace")
-    t, o = pair(js)
+    t, o = pair(js, dedup)
     for docs in ([], [b""], [b"", b"", b""], [b" "], [b"  \n\t "], [b"a"], [b"", b"a", b""], [b"ab", b"", b"", b"ba ab"], [b"a" * 5000, b"", b"b"]):
         assert_same(t.encode_batch(docs), o.encode_batch(docs), repr(docs)[:40])
     t.close()
 
 
-def test_document_boundary_splits_words():
+@pytest.mark.parametrize("dedup", [True, False])
+def test_document_boundary_splits_words(dedup):
     js = json.dumps({"model": {"type": "BPE", "vocab": {"a": 0, "b": 1, "ab": 2, "ba": 3, "abab": 4}, "merges": ["a b", "b a", "ab ab"]},
                      "pre_tokenizer": {"type": "Whitespace"}})
-    t, o = pair(js)
+    t, o = pair(js, dedup)
     docs = [b"abab", b"ab", b"ab", b"a", b"b", b"", b"a b", b"ab"] * 700        # boundaries fall inside tiles and on tile edges
     assert_same(t.encode_batch(docs), o.encode_batch(docs))
     t.close()
@@ -219,9 +229,10 @@ def test_malformed_utf8():
     t.close()
 
 
-def test_wordpiece_missing_unk_is_an_error():
+@pytest.mark.parametrize("dedup", [True, False])
+def test_wordpiece_missing_unk_is_an_error(dedup):
     js = json.dumps({"model": {"type": "WordPiece", "vocab": {"hello": 1, "##s": 2}, "unk_token": "[UNK]"}, "pre_tokenizer": {"type": "Whitespace"}})
-    t, o = pair(js)
+    t, o = pair(js, dedup)
     assert_same(t.encode_batch([b"hello hellos"]), o.encode_batch([b"hello hellos"]))
     with pytest.raises(tz.TokzigError) as e:
         t.encode_batch([b"hello", b"hello xyz", b"q"])
@@ -287,4 +298,60 @@ def test_batch_split_invariance_and_roundtrip_property():
         kept = b"".join(ch.encode() for w in doc.split() for ch in w.decode("utf-8") if ch.encode() in single)
         sl = full.doc_slice(i)
         assert b"".join(id2tok[int(x)] for x in full.ids[sl]) == kept
+    t.close()
+
+
+# ----------------------------------------------------------------------------- dedup pipeline specifics
+@pytest.mark.parametrize("model", ["bpe", "wp"])
+def test_dedup_word_lengths_around_the_key_limit(model):
+    """words of 14 / 15 / 16 / 17 bytes straddle the 128-bit key (15 bytes + length), incl. NUL bytes inside words,
+    words crossing 4 KiB tile edges and document boundaries inside a run."""
+    rng = random.Random(17)
+    if model == "bpe":
+        js, alpha = rand_bpe_json(rng, n_merges=60, alphabet=list("abcde") + ["é"], pretok="Whitespace", dead_merges=0.0)
+    else:
+        js, alpha = rand_wp_json(rng, n_words=80, alphabet=list("abcde") + ["é"], pretok="Whitespace", normalizer=None)
+    t, o = pair(js)
+    docs = []
+    for i in range(3000):
+        words = []
+        for _ in range(rng.randint(0, 12)):
+            L = rng.choice([1, 2, 3, 7, 13, 14, 15, 16, 17, 31, 40])
+            w = "".join(rng.choice(alpha) for _ in range(L)).encode()[:L]
+            words.append(w.decode("utf-8", "ignore").encode())
+        d = b" ".join(words)
+        if model == "wp" and rng.random() < 0.2:
+            d = d.replace(b"a", b"\x00", 1)          # NUL is an ordinary word byte for the whitespace split
+        docs.append(d)
+    assert_same(t.encode_batch(docs), o.encode_batch(docs), model)
+    t.close()
+
+
+def test_dedup_and_per_occurrence_pipelines_agree_on_errors():
+    js = json.dumps({"model": {"type": "BPE", "vocab": {"a": 0, "b": 1, "ab": 2}, "merges": ["a b"]}, "pre_tokenizer": {"type": "Whitespace"}})
+    for dedup in (True, False):
+        t, o = pair(js, dedup)
+        docs = [b"ab ab", b"ab \xffab ab", b"a\x80 ab", b"ab"]            # first failing document in TEXT order is 1
+        with pytest.raises(tz.TokzigError) as e:
+            t.encode_batch(docs)
+        assert e.value.code == tz.ERR_INVALID_UTF8 and e.value.doc == 1
+        # a long failing word (>15 bytes) in an earlier document wins over a short failing word later
+        docs = [b"ab", b"ab " + b"a" * 20 + b"\xc3", b"\xff"]
+        with pytest.raises(tz.TokzigError) as e:
+            t.encode_batch(docs)
+        assert e.value.doc == 1
+        t.close()
+
+
+@pytest.mark.parametrize("n_words", [60000, 200000])
+def test_dedup_table_pressure_and_overflow(n_words):
+    """more unique words than the batch's table holds: insertions that find no slot fall back to the long list, and when
+    the long list overflows as well the batch is re-run by the per-occurrence pipeline -- results stay exact."""
+    rng = random.Random(23)
+    js, alpha = rand_bpe_json(rng, n_merges=100, alphabet=list("abcdefghijklmnop"), pretok="Whitespace", dead_merges=0.0)
+    t, o = pair(js)
+    chars = "abcdefghijklmnopqrstuvwxyzABCDEFGHIJKLMNOPQRSTUVWXYZ0123456789"
+    words = ["".join(rng.choice(chars) for _ in range(4)) for _ in range(n_words)]
+    docs = [" ".join(words[i:i + 50]).encode() for i in range(0, len(words), 50)]
+    assert_same(t.encode_batch(docs), o.encode_batch(docs, threads=8))
     t.close()

@@ -16,6 +16,7 @@
 #include "../../include/tokzig_b200.h"
 #include "tkz_bpe.cuh"
 #include "tkz_common.cuh"
+#include "tkz_dedup.cuh"
 #include "tkz_emit.cuh"
 #include "tkz_scan.cuh"
 #include "tkz_split.cuh"
@@ -52,6 +53,10 @@ struct tkz_ctx {
     DevBuf a_text, a_doc_off, a_norm_text, a_norm_doc_off, a_chunk, a_tiles, a_word_start, a_word_end, a_word_doc, a_doc_word_off,
         a_word_ntok, a_pool_id, a_pool_s, a_pool_e, a_pool_rk, a_scan_tmp, a_doc_tok_off, a_out_ids, a_out_off, a_out_attn,
         a_out_type, a_out_special, a_ctrl;
+    // dedup pipeline arenas
+    DevBuf a_table, a_uniq, a_long_start, a_long_end, a_long_ntok, a_tile_words, a_tile_nwords, a_tile_ntok, a_doc_word_ref,
+        a_doc_tok_local, a_doc_tok_start, a_doc_real, a_upool;
+    bool use_dedup = true;
     HostBuf h_ctrl, h_doc_tok_off, h_ids, h_off, h_attn, h_type, h_special;
     uint64_t arena_bytes = 0;
     tkz_stats stats{};
@@ -104,8 +109,31 @@ int upload(tkz_ctx* ctx, DevBuf& b, const void* src, size_t bytes) {
 uint32_t pow2_at_least(uint64_t n) { uint32_t c = 2; while (c < n) c <<= 1; return c; }
 
 __global__ void ctrl_reset_kernel(unsigned long long* ctrl) {
-    // ctrl[0] = error word, ctrl[1] = work counter (u32 view), ctrl[2..] = read-back scalars
-    ctrl[0] = TKZ_ERRW_NONE; ctrl[1] = 0; ctrl[2] = 0; ctrl[3] = 0; ctrl[4] = 0;
+    // ctrl[0] = error word, ctrl[1] = work counter (u32 view), ctrl[2..4] = read-back scalars,
+    // dedup: ctrl[5] second work counter, [6] n_uniq, [7] n_long, [8] overflow, [9] upool_count, [10] n_words
+    ctrl[0] = TKZ_ERRW_NONE;
+    for (int i = 1; i < 16; i++) ctrl[i] = 0;
+}
+#define TKZ_RETRY_NO_DEDUP 1
+__global__ void tile_words_total_kernel(const uint32_t* tile_nwords, uint32_t n_tiles, unsigned long long* ctrl) {
+    unsigned long long s = 0;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_tiles; i += gridDim.x * blockDim.x) s += tile_nwords[i];
+    for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(0xFFFFFFFFu, s, d);
+    if ((threadIdx.x & 31) == 0 && s) atomicAdd(ctrl + 10, s);
+}
+__global__ void gather_scalars_dedup_kernel(unsigned long long* ctrl, const uint32_t* tile_tok_base, uint32_t n_tiles,
+                                            const unsigned long long* doc_tok_off, uint32_t n_docs, const uint32_t* doc_word_ref) {
+    ctrl[2] = tile_tok_base[n_tiles];
+    ctrl[3] = doc_tok_off[n_docs];
+    const unsigned long long ew = ctrl[0];
+    unsigned long long d = 0;
+    if (ew != TKZ_ERRW_NONE) {
+        const uint32_t v = (uint32_t)(ew >> 8);            // virtual word index of the first failing word (text order)
+        uint32_t lo = 0, hi = n_docs;                      // last document with doc_word_ref <= v
+        while (lo < hi) { const uint32_t mid = lo + ((hi - lo) >> 1); if (doc_word_ref[mid] <= v) lo = mid + 1; else hi = mid; }
+        d = lo ? lo - 1 : 0;
+    }
+    ctrl[4] = d;
 }
 __global__ void gather_scalars_kernel(unsigned long long* ctrl, const uint32_t* word_tok_off, uint32_t n_words,
                                       const unsigned long long* doc_tok_off, uint32_t n_docs, const uint32_t* word_doc) {
@@ -151,6 +179,7 @@ extern "C" int tkz_ctx_create(int device, void* stream, uint64_t arena_hint_byte
         g_create_error = ctx->err; if (ctx->own_stream) cudaStreamDestroy(ctx->stream); delete ctx; return TKZ_ERR_OOM;
     }
     (void)arena_hint_bytes;
+    if (const char* e = getenv("TKZ_NO_DEDUP")) ctx->use_dedup = !(e[0] == '1');     // A/B switch for the parity tests
     for (auto& ev : ctx->ev) cudaEventCreate(&ev);
     *out = ctx;
     return TKZ_OK;
@@ -164,7 +193,9 @@ extern "C" void tkz_ctx_destroy(tkz_ctx* ctx) {
                       &ctx->a_text, &ctx->a_doc_off, &ctx->a_norm_text, &ctx->a_norm_doc_off, &ctx->a_chunk, &ctx->a_tiles, &ctx->a_word_start,
                       &ctx->a_word_end, &ctx->a_word_doc, &ctx->a_doc_word_off, &ctx->a_word_ntok, &ctx->a_pool_id, &ctx->a_pool_s, &ctx->a_pool_e,
                       &ctx->a_pool_rk, &ctx->a_scan_tmp, &ctx->a_doc_tok_off, &ctx->a_out_ids, &ctx->a_out_off, &ctx->a_out_attn, &ctx->a_out_type,
-                      &ctx->a_out_special, &ctx->a_ctrl};
+                      &ctx->a_out_special, &ctx->a_ctrl, &ctx->a_table, &ctx->a_uniq, &ctx->a_long_start, &ctx->a_long_end, &ctx->a_long_ntok,
+                      &ctx->a_tile_words, &ctx->a_tile_nwords, &ctx->a_tile_ntok, &ctx->a_doc_word_ref, &ctx->a_doc_tok_local,
+                      &ctx->a_doc_tok_start, &ctx->a_doc_real, &ctx->a_upool};
     for (DevBuf* b : bufs) release(*b);
     HostBuf* hb[] = {&ctx->h_ctrl, &ctx->h_doc_tok_off, &ctx->h_ids, &ctx->h_off, &ctx->h_attn, &ctx->h_type, &ctx->h_special};
     for (HostBuf* b : hb) release_host(*b);
@@ -301,6 +332,141 @@ extern "C" int tkz_model_upload(tkz_ctx* ctx, const tkz_model_desc* d) {
 // ------------------------------------------------------------------------------------------------ encode
 namespace {
 
+// The dedup pipeline (tkz_dedup.cuh).  Returns TKZ_RETRY_NO_DEDUP when the long list overflowed.
+int encode_dedup(tkz_ctx* ctx, const DevModel& m, const uint8_t* d_text, const uint64_t* d_doc_off, uint32_t nd, uint64_t N,
+                 const tkz_encode_params& P, tkz_batch_result* out, uint64_t& launches) {
+    cudaStream_t st = ctx->stream;
+    unsigned long long* ctrl = (unsigned long long*)ctx->a_ctrl.p;
+    unsigned long long* hctrl = (unsigned long long*)ctx->h_ctrl.p;
+    const uint64_t n_docs = nd;
+    const uint32_t n_tiles = (uint32_t)(N / DT_TILE + 1);
+    uint64_t want = N / 8; if (want < (1u << 16)) want = 1u << 16; if (want > (1u << 24)) want = 1u << 24;
+    const uint32_t tcap = pow2_at_least(want);
+    const uint32_t long_cap = (uint32_t)(N / 16 + 1024);
+    TRY(ensure(ctx, ctx->a_table, (size_t)tcap * sizeof(DedupSlot)));
+    TRY(ensure(ctx, ctx->a_uniq, (size_t)tcap * 4));
+    TRY(ensure(ctx, ctx->a_long_start, (size_t)long_cap * 4));
+    TRY(ensure(ctx, ctx->a_long_end, (size_t)long_cap * 4));
+    TRY(ensure(ctx, ctx->a_tile_words, (size_t)n_tiles * DT_WCAP * 4));
+    TRY(ensure(ctx, ctx->a_tile_nwords, ((size_t)n_tiles + 2) * 4));
+    TRY(ensure(ctx, ctx->a_tile_ntok, ((size_t)n_tiles + 2) * 4));
+    TRY(ensure(ctx, ctx->a_doc_word_ref, (n_docs + 2) * 4));
+    TRY(ensure(ctx, ctx->a_doc_tok_local, (n_docs + 2) * 4));
+    TRY(ensure(ctx, ctx->a_doc_tok_start, (n_docs + 2) * 4));
+    TRY(ensure(ctx, ctx->a_doc_real, (n_docs + 2) * 4));
+    TRY(ensure(ctx, ctx->a_doc_tok_off, (n_docs + 1) * 8));
+    TRY(ensure(ctx, ctx->a_scan_tmp, (scan_tmp_elems(n_tiles) + scan_tmp_elems(n_docs)) * 8));
+    CK(cudaMemsetAsync(ctx->a_table.p, 0, (size_t)tcap * sizeof(DedupSlot), st));
+    DedupArgs da{};
+    da.text = d_text; da.n = N; da.doc_off = d_doc_off; da.n_docs = nd;
+    da.table = (DedupSlot*)ctx->a_table.p; da.table_mask = tcap - 1;
+    da.uniq_slots = (uint32_t*)ctx->a_uniq.p; da.n_uniq = (unsigned int*)(ctrl + 6);
+    da.long_start = (uint32_t*)ctx->a_long_start.p; da.long_end = (uint32_t*)ctx->a_long_end.p; da.n_long = (unsigned int*)(ctrl + 7);
+    da.long_cap = long_cap; da.overflow = (unsigned int*)(ctrl + 8);
+    da.tile_words = (uint32_t*)ctx->a_tile_words.p; da.tile_nwords = (uint32_t*)ctx->a_tile_nwords.p; da.doc_word_ref = (uint32_t*)ctx->a_doc_word_ref.p;
+    tile_split_dedup_kernel<<<n_tiles, DT_THREADS, 0, st>>>(m, da); launches++;
+    CK(cudaMemcpyAsync(hctrl + 16, ctrl + 6, 3 * 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaEventRecord(ctx->ev[1], st));
+    CK(cudaStreamSynchronize(st));
+    const uint32_t n_uniq = (uint32_t)hctrl[16], n_long = (uint32_t)hctrl[17];
+    if (hctrl[18] != 0) return TKZ_RETRY_NO_DEDUP;
+
+    // ---- P2: the model on unique words (identity byte map: keys are stored normalised) and on the long list
+    DevModel mu = m; mu.lut = (const uint8_t*)ctx->t_lut_post.p;
+    TRY(ensure(ctx, ctx->a_upool, ((size_t)n_uniq * DT_MAX_SHORT + 16) * 8));
+    TRY(ensure(ctx, ctx->a_long_ntok, ((size_t)n_long + 2) * 4));
+    if (n_uniq) {
+        UniqueArgs ua{(DedupSlot*)ctx->a_table.p, (const uint32_t*)ctx->a_uniq.p, n_uniq, (unsigned long long*)ctx->a_upool.p,
+                      (unsigned int*)(ctrl + 9), (unsigned int*)(ctrl + 1)};
+        uint64_t blocks = ((uint64_t)n_uniq + UQ_WARPS - 1) / UQ_WARPS;
+        const uint64_t cap = (uint64_t)ctx->sm_count * 8; if (blocks > cap) blocks = cap;
+        if (m.kind == TKZ_MODEL_BPE) bpe_unique_kernel<<<(unsigned)blocks, UQ_WARPS * 32, 0, st>>>(mu, ua);
+        else wordpiece_unique_kernel<<<(unsigned)blocks, UQ_WARPS * 32, 0, st>>>(mu, ua);
+        launches++;
+    }
+    if (n_long) {
+        TRY(ensure(ctx, ctx->a_pool_id, N * 4));
+        TRY(ensure(ctx, ctx->a_pool_s, N * 4));
+        TRY(ensure(ctx, ctx->a_pool_e, N * 4));
+        if (m.kind == TKZ_MODEL_BPE) {
+            TRY(ensure(ctx, ctx->a_pool_rk, N * 4));
+            BpeArgs a{d_text, da.long_start, da.long_end, n_long, (uint32_t*)ctx->a_pool_id.p, (uint32_t*)ctx->a_pool_s.p, (uint32_t*)ctx->a_pool_e.p,
+                      (uint32_t*)ctx->a_pool_rk.p, (uint32_t*)ctx->a_long_ntok.p, (unsigned int*)(ctrl + 5), ctrl, 1};
+            uint64_t blocks = ((uint64_t)n_long + BPE_WARPS - 1) / BPE_WARPS;
+            const uint64_t cap = (uint64_t)ctx->sm_count * 3; if (blocks > cap) blocks = cap;
+            bpe_warp_kernel<<<(unsigned)blocks, BPE_WARPS * 32, BPE_SMEM_BYTES, st>>>(m, a); launches++;
+        } else {
+            WpArgs a{d_text, da.long_start, da.long_end, n_long, (uint32_t*)ctx->a_pool_id.p, (uint32_t*)ctx->a_pool_s.p, (uint32_t*)ctx->a_pool_e.p,
+                     (uint32_t*)ctx->a_long_ntok.p, (unsigned int*)(ctrl + 5), ctrl, 1};
+            uint64_t blocks = ((uint64_t)n_long + WP_WARPS - 1) / WP_WARPS;
+            const uint64_t cap = (uint64_t)ctx->sm_count * 8; if (blocks > cap) blocks = cap;
+            wordpiece_warp_kernel<<<(unsigned)blocks, WP_WARPS * 32, 0, st>>>(m, a); launches++;
+        }
+    }
+    CK(cudaEventRecord(ctx->ev[2], st));
+
+    // ---- P3a: tokens per tile, per document; CSR offsets
+    EmitParams ep{P.has_truncation, P.max_length, P.has_padding, P.pad_length, P.pad_id, P.pad_type_id, P.pad_left, P.outputs};
+    TileOutArgs ta{};
+    ta.doc_off = d_doc_off; ta.n_docs = nd; ta.n = N;
+    ta.table = (const DedupSlot*)ctx->a_table.p; ta.upool = (const unsigned long long*)ctx->a_upool.p;
+    ta.long_start = da.long_start; ta.long_ntok = (const uint32_t*)ctx->a_long_ntok.p;
+    ta.pool_id = (const uint32_t*)ctx->a_pool_id.p; ta.pool_s = (const uint32_t*)ctx->a_pool_s.p; ta.pool_e = (const uint32_t*)ctx->a_pool_e.p;
+    ta.tile_words = da.tile_words; ta.tile_nwords = da.tile_nwords; ta.doc_word_ref = da.doc_word_ref;
+    ta.tile_ntok = (uint32_t*)ctx->a_tile_ntok.p; ta.doc_tok_local = (uint32_t*)ctx->a_doc_tok_local.p;
+    ta.doc_tok_start = (uint32_t*)ctx->a_doc_tok_start.p; ta.doc_tok_off = (unsigned long long*)ctx->a_doc_tok_off.p;
+    ta.errw = ctrl; ta.err_code = m.kind == TKZ_MODEL_BPE ? TKZ_ECODE_UTF8 : TKZ_ECODE_UNK;
+    tile_count_kernel<<<n_tiles, DT_THREADS, 0, st>>>(ta); launches++;
+    tile_words_total_kernel<<<64, 256, 0, st>>>(da.tile_nwords, n_tiles, ctrl); launches++;
+    launches += exclusive_scan<uint32_t>(ta.tile_ntok, n_tiles, ta.tile_ntok, (unsigned long long*)ctx->a_scan_tmp.p, st);
+    doc_finish_kernel<<<(nd + 1 + 255) / 256, 256, 0, st>>>(ta, ep, (uint32_t*)ctx->a_doc_real.p); launches++;
+    launches += exclusive_scan<unsigned long long>(ta.doc_tok_off, n_docs, ta.doc_tok_off, (unsigned long long*)ctx->a_scan_tmp.p, st);
+    gather_scalars_dedup_kernel<<<1, 1, 0, st>>>(ctrl, ta.tile_ntok, n_tiles, ta.doc_tok_off, nd, da.doc_word_ref); launches++;
+    CK(cudaMemcpyAsync(hctrl, ctrl, 11 * 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    const unsigned long long errw = hctrl[0];
+    const uint64_t T_real = hctrl[2], T = hctrl[3];
+    ctx->stats.n_words = hctrl[10]; ctx->stats.n_unique_words = n_uniq; ctx->stats.n_long_words = n_long;
+    if (errw != TKZ_ERRW_NONE) {
+        out->err_doc = (int64_t)hctrl[4];
+        const uint32_t code = (uint32_t)(errw & 0xFF);
+        ctx->err = code == TKZ_ECODE_UTF8 ? "invalid UTF-8 in a BPE pre-token (reference behaviour undefined)" : "MissingUnkToken";
+        ctx->stats.kernel_launches = launches;
+        return code == TKZ_ECODE_UTF8 ? TKZ_ERR_INVALID_UTF8 : TKZ_ERR_MISSING_UNK;
+    }
+    CK(cudaEventRecord(ctx->ev[3], st));
+
+    // ---- P3b: emit
+    TRY(ensure(ctx, ctx->a_out_ids, T * 4));
+    if (P.outputs & TKZ_OUT_OFFSETS) TRY(ensure(ctx, ctx->a_out_off, T * 8));
+    if (P.outputs & TKZ_OUT_ATTENTION) TRY(ensure(ctx, ctx->a_out_attn, T * 4));
+    if (P.outputs & TKZ_OUT_TYPE_IDS) TRY(ensure(ctx, ctx->a_out_type, T * 4));
+    if (P.outputs & TKZ_OUT_SPECIAL) TRY(ensure(ctx, ctx->a_out_special, T * 4));
+    EmitOut eo{(uint32_t*)ctx->a_out_ids.p, (uint32_t*)ctx->a_out_off.p, (uint32_t*)ctx->a_out_attn.p, (uint32_t*)ctx->a_out_type.p,
+               (uint32_t*)ctx->a_out_special.p};
+    tile_emit_kernel<<<n_tiles, DT_THREADS, 0, st>>>(ta, ep, eo); launches++;
+    if (P.has_padding && nd) {
+        emit_pad_real_kernel<<<(unsigned)(((uint64_t)nd * 32 + 255) / 256), 256, 0, st>>>(ep, eo, nd, (const uint32_t*)ctx->a_doc_real.p, ta.doc_tok_off); launches++;
+    }
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(ctx->ev[4], st));
+    CK(cudaStreamSynchronize(st));
+    ctx->stats.kernel_launches = launches;
+    cudaEventElapsedTime(&ctx->stats.ms_split, ctx->ev[0], ctx->ev[1]);
+    cudaEventElapsedTime(&ctx->stats.ms_model, ctx->ev[1], ctx->ev[2]);
+    cudaEventElapsedTime(&ctx->stats.ms_scan, ctx->ev[2], ctx->ev[3]);
+    cudaEventElapsedTime(&ctx->stats.ms_emit, ctx->ev[3], ctx->ev[4]);
+    cudaEventElapsedTime(&ctx->stats.ms_total, ctx->ev[0], ctx->ev[4]);
+    out->n_docs = n_docs; out->n_tokens = T; out->n_real_tokens = T_real;
+    out->doc_tok_off = (const uint64_t*)ta.doc_tok_off;
+    out->ids = eo.ids;
+    out->offsets = (P.outputs & TKZ_OUT_OFFSETS) ? eo.offsets : nullptr;
+    out->attention_mask = (P.outputs & TKZ_OUT_ATTENTION) ? eo.attention : nullptr;
+    out->type_ids = (P.outputs & TKZ_OUT_TYPE_IDS) ? eo.type_ids : nullptr;
+    out->special_tokens_mask = (P.outputs & TKZ_OUT_SPECIAL) ? eo.special : nullptr;
+    return TKZ_OK;
+}
+
 int encode_device_impl(tkz_ctx* ctx, const uint8_t* d_text, const uint64_t* d_doc_off, uint64_t n_docs, uint64_t N,
                        const tkz_encode_params* params, tkz_batch_result* out) {
     memset(out, 0, sizeof *out);
@@ -349,6 +515,14 @@ int encode_device_impl(tkz_ctx* ctx, const uint8_t* d_text, const uint64_t* d_do
         m = ctx->dm_post;
     }
 
+    // ---- dedup pipeline (tkz_dedup.cuh) whenever there is a pre-tokenizer; falls through to the per-occurrence
+    //      pipeline below only if its long list overflowed (pathological: > N/16 long words)
+    if (m.has_pretok && ctx->use_dedup) {
+        int rc = encode_dedup(ctx, m, d_text, d_doc_off, nd, N, P, out, launches);
+        if (rc != TKZ_RETRY_NO_DEDUP) return rc;
+        ctrl_reset_kernel<<<1, 1, 0, st>>>(ctrl); launches++;
+    }
+
     // ---- K1: pre-token spans
     uint64_t W = 0;
     TRY(ensure(ctx, ctx->a_doc_word_off, (n_docs + 1) * 4));
@@ -395,14 +569,14 @@ int encode_device_impl(tkz_ctx* ctx, const uint8_t* d_text, const uint64_t* d_do
         if (m.kind == TKZ_MODEL_BPE) {
             TRY(ensure(ctx, ctx->a_pool_rk, N * 4));
             BpeArgs a{d_text, word_start, word_end, nw, (uint32_t*)ctx->a_pool_id.p, (uint32_t*)ctx->a_pool_s.p, (uint32_t*)ctx->a_pool_e.p,
-                      (uint32_t*)ctx->a_pool_rk.p, word_ntok, work_counter, ctrl};
+                      (uint32_t*)ctx->a_pool_rk.p, word_ntok, work_counter, ctrl, 0};
             uint64_t blocks = (W + BPE_WARPS - 1) / BPE_WARPS;
             const uint64_t cap = (uint64_t)ctx->sm_count * 3;
             if (blocks > cap) blocks = cap;
             bpe_warp_kernel<<<(unsigned)blocks, BPE_WARPS * 32, BPE_SMEM_BYTES, st>>>(m, a); launches++;
         } else {
             WpArgs a{d_text, word_start, word_end, nw, (uint32_t*)ctx->a_pool_id.p, (uint32_t*)ctx->a_pool_s.p, (uint32_t*)ctx->a_pool_e.p,
-                     word_ntok, work_counter, ctrl};
+                     word_ntok, work_counter, ctrl, 0};
             uint64_t blocks = (W + WP_WARPS - 1) / WP_WARPS;
             const uint64_t cap = (uint64_t)ctx->sm_count * 8;
             if (blocks > cap) blocks = cap;

@@ -29,6 +29,7 @@ struct BpeArgs {
     uint32_t* word_ntok;
     unsigned int* work_counter;
     unsigned long long* errw;
+    int sentinel_errors;          // 1: write word_ntok = TKZ_NONE on error instead of reporting (dedup pipeline)
 };
 
 // exact sequential form of the apply loop (bpe.zig:240-252), used when new_id == first (the re-check at the same index
@@ -63,6 +64,144 @@ __device__ __forceinline__ uint32_t bpe_init_sequential(const DevModel& m, const
     return k;
 }
 
+// One pre-token through BPE.tokenize (bpe.zig:173-263) by one warp.  `wt` = the word's bytes (m.lut is applied on read),
+// ids/ss/ee/rk = symbol arrays (shared memory or the word's pool slice) with room for `len` entries.
+// Returns the token count, or TKZ_NONE for an invalid lead byte / truncated tail (reference: unreachable).
+__device__ __forceinline__ uint32_t bpe_encode_word(const DevModel& m, const uint8_t* __restrict__ wt, uint32_t len,
+                                                    uint32_t* ids, uint32_t* ss, uint32_t* ee, uint32_t* rk) {
+    const uint32_t lane = lane_id();
+    const uint32_t FULL = 0xFFFFFFFFu;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    // ---------------- initial symbols (bpe.zig:185-211), 32 bytes per step
+    uint32_t n = 0; bool malformed = false;
+    for (uint32_t c0 = 0; c0 < len; c0 += 32) {
+        const uint32_t p = c0 + lane;
+        uint32_t b0 = 0x80; int L = 0; bool start = false, bad = false;
+        if (p < len) {
+            b0 = m.lut[__ldg(wt + p)];
+            if ((b0 & 0xC0) == 0x80) {
+                // continuation byte: must be covered by a lead byte at most 3 positions back
+                bool covered = false;
+                for (uint32_t back = 1; back <= 3 && back <= p; back++) {
+                    const uint32_t q = m.lut[__ldg(wt + p - back)];
+                    if ((q & 0xC0) != 0x80) { covered = (uint32_t)utf8_seq_len(q) > back; break; }
+                }
+                bad = !covered;
+            } else {
+                start = true; L = utf8_seq_len(b0);
+                if (L == 0 || p + (uint32_t)L > len) bad = true;
+            }
+        }
+        uint32_t key = b0; uint32_t id = TKZ_NONE;
+        if (start && !bad) {
+            for (int j = 1; j < L; j++) {
+                const uint32_t bj = m.lut[__ldg(wt + p + j)];
+                if ((bj & 0xC0) != 0x80) bad = true;
+                key |= bj << (8 * j);
+            }
+            if (!bad) { id = char_lookup(m, key, L); if (id == TKZ_NONE && m.has_unk) id = m.unk_id; }
+        }
+        if (__any_sync(FULL, bad)) { malformed = true; break; }
+        const uint32_t keep = __ballot_sync(FULL, id != TKZ_NONE);
+        if (id != TKZ_NONE) { const uint32_t k = n + __popc(keep & lt_mask); ids[k] = id; ss[k] = p; ee[k] = p + (uint32_t)L; }
+        n += __popc(keep);
+    }
+    if (malformed) {
+        // rare: re-do the word with the exact sequential iterator; invalid lead / truncated tail is an error
+        if (lane == 0) n = bpe_init_sequential(m, wt, len, ids, ss, ee);
+        n = __shfl_sync(FULL, n, 0);
+        if (n == TKZ_NONE) return TKZ_NONE;
+    }
+    __syncwarp();
+
+    // ---------------- pair ranks
+    for (uint32_t i = lane; i + 1 < n; i += 32) rk[i] = merge_rank_lookup(m, ids[i], ids[i + 1], nullptr);
+    __syncwarp();
+
+    // ---------------- merge rounds (bpe.zig:214-253)
+    while (n > 1) {
+        unsigned long long best = ~0ULL;
+        for (uint32_t i = lane; i + 1 < n; i += 32) {
+            const uint32_t r = rk[i];
+            if (r != TKZ_NONE) { const unsigned long long k = ((unsigned long long)r << 32) | i; best = k < best ? k : best; }
+        }
+        best = warp_min64(best);
+        if (best == ~0ULL) break;                                   // bpe.zig:232-234
+        const uint32_t bp = (uint32_t)best;
+        const uint32_t A = ids[bp], B = ids[bp + 1];
+        uint32_t N = 0;
+        merge_rank_lookup(m, A, B, &N);                             // bpe.zig:238
+        __syncwarp();
+        if (N == A) {
+            if (lane == 0) n = bpe_apply_sequential(ids, ss, ee, n, A, B, N);
+            n = __shfl_sync(FULL, n, 0);
+            __syncwarp();
+            for (uint32_t i = lane; i + 1 < n; i += 32) rk[i] = merge_rank_lookup(m, ids[i], ids[i + 1], nullptr);
+            __syncwarp();
+            continue;
+        }
+        // parallel apply: `head` = merges with its right neighbour, `removed` = swallowed by its left neighbour.
+        // For A == B the occurrences overlap inside a run of A's: the literal scan pairs them greedily from the run
+        // start (aaaaa -> aa aa a), i.e. heads sit at even distance from the run start.
+        const bool same = (A == B);
+        uint32_t wpos = 0;            // compacted length so far (always <= chunk base)
+        uint32_t run_par = 0;         // A == B: parity of the length of the A-run that ends right before this chunk
+        bool prev_head = false;       // A != B: last symbol of the previous chunk was a head
+        for (uint32_t c0 = 0; c0 < n; c0 += 32) {
+            const uint32_t i = c0 + lane;
+            const bool v0 = i < n, v1 = i + 1 < n, v2 = i + 2 < n;
+            const uint32_t x0 = v0 ? ids[i] : 0, x1 = v1 ? ids[i + 1] : 0, x2 = v2 ? ids[i + 2] : 0;
+            const uint32_t s0 = v0 ? ss[i] : 0, e0 = v0 ? ee[i] : 0, e1 = v1 ? ee[i + 1] : 0;
+            const uint32_t r0 = (v0 && v1) ? rk[i] : TKZ_NONE;
+            bool head, removed, next_head;
+            if (!same) {
+                head = v1 && x0 == A && x1 == B;
+                next_head = v2 && x1 == A && x2 == B;
+                const uint32_t hb = __ballot_sync(FULL, head);
+                removed = lane == 0 ? prev_head : ((hb >> (lane - 1)) & 1u);
+                prev_head = (hb >> 31) & 1u;
+            } else {
+                const bool isA = v0 && x0 == A;
+                const uint32_t am = __ballot_sync(FULL, isA);
+                // distance from the start of the run of A's that contains i
+                const uint32_t below = ~am & lt_mask;
+                const uint32_t o = below ? (lane - (32u - __clz(below))) : (lane + run_par);
+                const bool odd = o & 1u;
+                head = isA && !odd && v1 && x1 == A;
+                removed = isA && odd;
+                // the next symbol's distance is o+1 when it continues this run, else 0
+                const bool nA = v1 && x1 == A;
+                const bool n_odd = isA ? !odd : false;
+                next_head = nA && !n_odd && v2 && x2 == A;
+                // carry: parity of the trailing run of this chunk
+                const uint32_t lead_ones = __clz(~am);               // A's at lanes 31, 30, ...
+                run_par = (lead_ones == 32) ? (run_par ^ 0u) : (lead_ones & 1u);   // 32 is even: parity unchanged
+            }
+            __syncwarp();                                            // all reads of this chunk done before its writes
+            const bool keep = v0 && !removed;
+            const uint32_t km = __ballot_sync(FULL, keep);
+            if (keep) {
+                const uint32_t q = wpos + __popc(km & lt_mask);
+                ids[q] = head ? N : x0;
+                ss[q] = s0;
+                ee[q] = head ? e1 : e0;
+                rk[q] = (head || next_head) ? TKZ_DIRTY : r0;
+            }
+            wpos += __popc(km);
+            __syncwarp();
+        }
+        n = wpos;
+        __syncwarp();
+        // ranks of the pairs a merge touched
+        for (uint32_t i = lane; i < n; i += 32) {
+            if (i + 1 < n) { if (rk[i] == TKZ_DIRTY) rk[i] = merge_rank_lookup(m, ids[i], ids[i + 1], nullptr); }
+        }
+        __syncwarp();
+    }
+
+    return n;
+}
+
 __global__ void __launch_bounds__(BPE_WARPS * 32) bpe_warp_kernel(DevModel m, BpeArgs a) {
     extern __shared__ uint32_t bpe_dyn_smem[];      // [4 arrays][BPE_WARPS][BPE_SMEM_SYMS]
     const uint32_t lane = lane_id(), wid = threadIdx.x >> 5;
@@ -71,7 +210,6 @@ __global__ void __launch_bounds__(BPE_WARPS * 32) bpe_warp_kernel(DevModel m, Bp
     uint32_t* const sh_e = bpe_dyn_smem + (2 * BPE_WARPS + wid) * BPE_SMEM_SYMS;
     uint32_t* const sh_rk = bpe_dyn_smem + (3 * BPE_WARPS + wid) * BPE_SMEM_SYMS;
     const uint32_t FULL = 0xFFFFFFFFu;
-    const uint32_t lt_mask = (1u << lane) - 1u;
 
     for (;;) {
         uint32_t w = 0;
@@ -80,141 +218,18 @@ __global__ void __launch_bounds__(BPE_WARPS * 32) bpe_warp_kernel(DevModel m, Bp
         if (w >= a.n_words) break;
         const uint32_t ws = a.word_start[w], len = a.word_end[w] - ws;
         if (len == 0) { if (lane == 0) a.word_ntok[w] = 0; continue; }       // bpe.zig:174-176
-        const uint8_t* __restrict__ wt = a.text + ws;
         const bool in_smem = len <= BPE_SMEM_SYMS;
         uint32_t* ids = in_smem ? sh_id : a.pool_id + ws;
         uint32_t* ss = in_smem ? sh_s : a.pool_s + ws;
         uint32_t* ee = in_smem ? sh_e : a.pool_e + ws;
         uint32_t* rk = in_smem ? sh_rk : a.pool_rk + ws;
-
-        // ---------------- initial symbols (bpe.zig:185-211), 32 bytes per step
-        uint32_t n = 0; bool malformed = false;
-        for (uint32_t c0 = 0; c0 < len; c0 += 32) {
-            const uint32_t p = c0 + lane;
-            uint32_t b0 = 0x80; int L = 0; bool start = false, bad = false;
-            if (p < len) {
-                b0 = m.lut[__ldg(wt + p)];
-                if ((b0 & 0xC0) == 0x80) {
-                    // continuation byte: must be covered by a lead byte at most 3 positions back
-                    bool covered = false;
-                    for (uint32_t back = 1; back <= 3 && back <= p; back++) {
-                        const uint32_t q = m.lut[__ldg(wt + p - back)];
-                        if ((q & 0xC0) != 0x80) { covered = (uint32_t)utf8_seq_len(q) > back; break; }
-                    }
-                    bad = !covered;
-                } else {
-                    start = true; L = utf8_seq_len(b0);
-                    if (L == 0 || p + (uint32_t)L > len) bad = true;
-                }
-            }
-            uint32_t key = b0; uint32_t id = TKZ_NONE;
-            if (start && !bad) {
-                for (int j = 1; j < L; j++) {
-                    const uint32_t bj = m.lut[__ldg(wt + p + j)];
-                    if ((bj & 0xC0) != 0x80) bad = true;
-                    key |= bj << (8 * j);
-                }
-                if (!bad) { id = char_lookup(m, key, L); if (id == TKZ_NONE && m.has_unk) id = m.unk_id; }
-            }
-            if (__any_sync(FULL, bad)) { malformed = true; break; }
-            const uint32_t keep = __ballot_sync(FULL, id != TKZ_NONE);
-            if (id != TKZ_NONE) { const uint32_t k = n + __popc(keep & lt_mask); ids[k] = id; ss[k] = p; ee[k] = p + (uint32_t)L; }
-            n += __popc(keep);
+        const uint32_t n = bpe_encode_word(m, a.text + ws, len, ids, ss, ee, rk);
+        if (n == TKZ_NONE) {
+            // sentinel mode (dedup pipeline): the emit pass finds the first failing word in TEXT order
+            if (lane == 0) { if (a.sentinel_errors) a.word_ntok[w] = TKZ_NONE; else { report_error(a.errw, w, TKZ_ECODE_UTF8); a.word_ntok[w] = 0; } }
+            continue;
         }
-        if (malformed) {
-            // rare: re-do the word with the exact sequential iterator; invalid lead / truncated tail is an error
-            if (lane == 0) n = bpe_init_sequential(m, wt, len, ids, ss, ee);
-            n = __shfl_sync(FULL, n, 0);
-            if (n == TKZ_NONE) { if (lane == 0) { report_error(a.errw, w, TKZ_ECODE_UTF8); a.word_ntok[w] = 0; } continue; }
-        }
-        __syncwarp();
-
-        // ---------------- pair ranks
-        for (uint32_t i = lane; i + 1 < n; i += 32) rk[i] = merge_rank_lookup(m, ids[i], ids[i + 1], nullptr);
-        __syncwarp();
-
-        // ---------------- merge rounds (bpe.zig:214-253)
-        while (n > 1) {
-            unsigned long long best = ~0ULL;
-            for (uint32_t i = lane; i + 1 < n; i += 32) {
-                const uint32_t r = rk[i];
-                if (r != TKZ_NONE) { const unsigned long long k = ((unsigned long long)r << 32) | i; best = k < best ? k : best; }
-            }
-            best = warp_min64(best);
-            if (best == ~0ULL) break;                                   // bpe.zig:232-234
-            const uint32_t bp = (uint32_t)best;
-            const uint32_t A = ids[bp], B = ids[bp + 1];
-            uint32_t N = 0;
-            merge_rank_lookup(m, A, B, &N);                             // bpe.zig:238
-            __syncwarp();
-            if (N == A) {
-                if (lane == 0) n = bpe_apply_sequential(ids, ss, ee, n, A, B, N);
-                n = __shfl_sync(FULL, n, 0);
-                __syncwarp();
-                for (uint32_t i = lane; i + 1 < n; i += 32) rk[i] = merge_rank_lookup(m, ids[i], ids[i + 1], nullptr);
-                __syncwarp();
-                continue;
-            }
-            // parallel apply: `head` = merges with its right neighbour, `removed` = swallowed by its left neighbour.
-            // For A == B the occurrences overlap inside a run of A's: the literal scan pairs them greedily from the run
-            // start (aaaaa -> aa aa a), i.e. heads sit at even distance from the run start.
-            const bool same = (A == B);
-            uint32_t wpos = 0;            // compacted length so far (always <= chunk base)
-            uint32_t run_par = 0;         // A == B: parity of the length of the A-run that ends right before this chunk
-            bool prev_head = false;       // A != B: last symbol of the previous chunk was a head
-            for (uint32_t c0 = 0; c0 < n; c0 += 32) {
-                const uint32_t i = c0 + lane;
-                const bool v0 = i < n, v1 = i + 1 < n, v2 = i + 2 < n;
-                const uint32_t x0 = v0 ? ids[i] : 0, x1 = v1 ? ids[i + 1] : 0, x2 = v2 ? ids[i + 2] : 0;
-                const uint32_t s0 = v0 ? ss[i] : 0, e0 = v0 ? ee[i] : 0, e1 = v1 ? ee[i + 1] : 0;
-                const uint32_t r0 = (v0 && v1) ? rk[i] : TKZ_NONE;
-                bool head, removed, next_head;
-                if (!same) {
-                    head = v1 && x0 == A && x1 == B;
-                    next_head = v2 && x1 == A && x2 == B;
-                    const uint32_t hb = __ballot_sync(FULL, head);
-                    removed = lane == 0 ? prev_head : ((hb >> (lane - 1)) & 1u);
-                    prev_head = (hb >> 31) & 1u;
-                } else {
-                    const bool isA = v0 && x0 == A;
-                    const uint32_t am = __ballot_sync(FULL, isA);
-                    // distance from the start of the run of A's that contains i
-                    const uint32_t below = ~am & lt_mask;
-                    const uint32_t o = below ? (lane - (32u - __clz(below))) : (lane + run_par);
-                    const bool odd = o & 1u;
-                    head = isA && !odd && v1 && x1 == A;
-                    removed = isA && odd;
-                    // the next symbol's distance is o+1 when it continues this run, else 0
-                    const bool nA = v1 && x1 == A;
-                    const bool n_odd = isA ? !odd : false;
-                    next_head = nA && !n_odd && v2 && x2 == A;
-                    // carry: parity of the trailing run of this chunk
-                    const uint32_t lead_ones = __clz(~am);               // A's at lanes 31, 30, ...
-                    run_par = (lead_ones == 32) ? (run_par ^ 0u) : (lead_ones & 1u);   // 32 is even: parity unchanged
-                }
-                __syncwarp();                                            // all reads of this chunk done before its writes
-                const bool keep = v0 && !removed;
-                const uint32_t km = __ballot_sync(FULL, keep);
-                if (keep) {
-                    const uint32_t q = wpos + __popc(km & lt_mask);
-                    ids[q] = head ? N : x0;
-                    ss[q] = s0;
-                    ee[q] = head ? e1 : e0;
-                    rk[q] = (head || next_head) ? TKZ_DIRTY : r0;
-                }
-                wpos += __popc(km);
-                __syncwarp();
-            }
-            n = wpos;
-            __syncwarp();
-            // ranks of the pairs a merge touched
-            for (uint32_t i = lane; i < n; i += 32) {
-                if (i + 1 < n) { if (rk[i] == TKZ_DIRTY) rk[i] = merge_rank_lookup(m, ids[i], ids[i + 1], nullptr); }
-            }
-            __syncwarp();
-        }
-
-        // ---------------- result (bpe.zig:256-260): tokens go to the word's pool slice
+        // result (bpe.zig:256-260): tokens go to the word's pool slice
         if (in_smem) {
             for (uint32_t i = lane; i < n; i += 32) { a.pool_id[ws + i] = ids[i]; a.pool_s[ws + i] = ss[i]; a.pool_e[ws + i] = ee[i]; }
         }
