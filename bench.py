@@ -232,6 +232,7 @@ def run_ours(args, rank, local_rank, world):
             if collect:
                 L.tkz_ctx_get_stats(ctx_h, C.byref(stats))
                 launches += stats.kernel_launches; words += stats.n_words
+                agg["uniq"] = agg.get("uniq", 0) * 0 + int(stats.n_unique_words); agg["long"] = int(stats.n_long_words)
                 for i, k in enumerate(("ms_split", "ms_model", "ms_scan", "ms_emit", "ms_total")):
                     ms[i] += getattr(stats, k)
         return tot_tokens, tot_real, launches, ms, words
@@ -338,7 +339,7 @@ def run_ours(args, rank, local_rank, world):
             "data": f"synthetic ({cname} generator, seed 1234+rank, generated in {t_gen:.1f} s)",
             "tokens_per_s": all_real / (ms_step * 1e-3), "slots_per_s": all_slots / (ms_step * 1e-3),
             "config": {"workload": f"{args.workload}: {desc}", "tokenizer": tok_name, "corpus": cname, "bytes_per_gpu": nbytes, "docs_per_gpu": nd,
-                       "words_per_gpu": agg["words"], "tokens_per_gpu": agg["real"], "sub_batches": len(batches), "outputs_mask": int(params.outputs),
+                       "words_per_gpu": agg["words"], "unique_words_last_batch": agg.get("uniq"), "long_words_last_batch": agg.get("long"), "tokens_per_gpu": agg["real"], "sub_batches": len(batches), "outputs_mask": int(params.outputs),
                        "l2": "inputs (>= 1 GiB per step) larger than the 126 MB L2; no flush needed", "parallelism": f"documents sharded x{world}, no collective"},
             "roofline": roofline, "cpu_baseline": cb, "e2e": e2e, "gpu_launches": int(agg["launches"]), "clocks": sampler.summary(),
             "parity_checked_vs_oracle": parity}

@@ -55,7 +55,7 @@ struct tkz_ctx {
         a_out_type, a_out_special, a_ctrl;
     // dedup pipeline arenas
     DevBuf a_table, a_uniq, a_long_start, a_long_end, a_long_ntok, a_tile_words, a_tile_nwords, a_tile_ntok, a_doc_word_ref,
-        a_doc_tok_local, a_doc_tok_start, a_doc_real, a_upool;
+        a_doc_tok_local, a_doc_tok_start, a_doc_real, a_upool, a_tile_doc_lo;
     bool use_dedup = true;
     HostBuf h_ctrl, h_doc_tok_off, h_ids, h_off, h_attn, h_type, h_special;
     uint64_t arena_bytes = 0;
@@ -195,7 +195,7 @@ extern "C" void tkz_ctx_destroy(tkz_ctx* ctx) {
                       &ctx->a_pool_rk, &ctx->a_scan_tmp, &ctx->a_doc_tok_off, &ctx->a_out_ids, &ctx->a_out_off, &ctx->a_out_attn, &ctx->a_out_type,
                       &ctx->a_out_special, &ctx->a_ctrl, &ctx->a_table, &ctx->a_uniq, &ctx->a_long_start, &ctx->a_long_end, &ctx->a_long_ntok,
                       &ctx->a_tile_words, &ctx->a_tile_nwords, &ctx->a_tile_ntok, &ctx->a_doc_word_ref, &ctx->a_doc_tok_local,
-                      &ctx->a_doc_tok_start, &ctx->a_doc_real, &ctx->a_upool};
+                      &ctx->a_doc_tok_start, &ctx->a_doc_real, &ctx->a_upool, &ctx->a_tile_doc_lo};
     for (DevBuf* b : bufs) release(*b);
     HostBuf* hb[] = {&ctx->h_ctrl, &ctx->h_doc_tok_off, &ctx->h_ids, &ctx->h_off, &ctx->h_attn, &ctx->h_type, &ctx->h_special};
     for (HostBuf* b : hb) release_host(*b);
@@ -354,6 +354,7 @@ int encode_dedup(tkz_ctx* ctx, const DevModel& m, const uint8_t* d_text, const u
     TRY(ensure(ctx, ctx->a_doc_tok_local, (n_docs + 2) * 4));
     TRY(ensure(ctx, ctx->a_doc_tok_start, (n_docs + 2) * 4));
     TRY(ensure(ctx, ctx->a_doc_real, (n_docs + 2) * 4));
+    TRY(ensure(ctx, ctx->a_tile_doc_lo, ((size_t)n_tiles + 2) * 4));
     TRY(ensure(ctx, ctx->a_doc_tok_off, (n_docs + 1) * 8));
     TRY(ensure(ctx, ctx->a_scan_tmp, (scan_tmp_elems(n_tiles) + scan_tmp_elems(n_docs)) * 8));
     CK(cudaMemsetAsync(ctx->a_table.p, 0, (size_t)tcap * sizeof(DedupSlot), st));
@@ -364,6 +365,8 @@ int encode_dedup(tkz_ctx* ctx, const DevModel& m, const uint8_t* d_text, const u
     da.long_start = (uint32_t*)ctx->a_long_start.p; da.long_end = (uint32_t*)ctx->a_long_end.p; da.n_long = (unsigned int*)(ctrl + 7);
     da.long_cap = long_cap; da.overflow = (unsigned int*)(ctrl + 8);
     da.tile_words = (uint32_t*)ctx->a_tile_words.p; da.tile_nwords = (uint32_t*)ctx->a_tile_nwords.p; da.doc_word_ref = (uint32_t*)ctx->a_doc_word_ref.p;
+    da.tile_doc_lo = (const uint32_t*)ctx->a_tile_doc_lo.p;
+    tile_doc_index_kernel<<<(n_tiles + 1 + 255) / 256, 256, 0, st>>>(d_doc_off, nd, n_tiles, (uint32_t*)ctx->a_tile_doc_lo.p); launches++;
     tile_split_dedup_kernel<<<n_tiles, DT_THREADS, 0, st>>>(m, da); launches++;
     CK(cudaMemcpyAsync(hctrl + 16, ctrl + 6, 3 * 8, cudaMemcpyDeviceToHost, st));
     CK(cudaEventRecord(ctx->ev[1], st));
@@ -412,7 +415,7 @@ int encode_dedup(tkz_ctx* ctx, const DevModel& m, const uint8_t* d_text, const u
     ta.table = (const DedupSlot*)ctx->a_table.p; ta.upool = (const unsigned long long*)ctx->a_upool.p;
     ta.long_start = da.long_start; ta.long_ntok = (const uint32_t*)ctx->a_long_ntok.p;
     ta.pool_id = (const uint32_t*)ctx->a_pool_id.p; ta.pool_s = (const uint32_t*)ctx->a_pool_s.p; ta.pool_e = (const uint32_t*)ctx->a_pool_e.p;
-    ta.tile_words = da.tile_words; ta.tile_nwords = da.tile_nwords; ta.doc_word_ref = da.doc_word_ref;
+    ta.tile_words = da.tile_words; ta.tile_nwords = da.tile_nwords; ta.doc_word_ref = da.doc_word_ref; ta.tile_doc_lo = da.tile_doc_lo;
     ta.tile_ntok = (uint32_t*)ctx->a_tile_ntok.p; ta.doc_tok_local = (uint32_t*)ctx->a_doc_tok_local.p;
     ta.doc_tok_start = (uint32_t*)ctx->a_doc_tok_start.p; ta.doc_tok_off = (unsigned long long*)ctx->a_doc_tok_off.p;
     ta.errw = ctrl; ta.err_code = m.kind == TKZ_MODEL_BPE ? TKZ_ECODE_UTF8 : TKZ_ECODE_UNK;
@@ -444,7 +447,9 @@ int encode_dedup(tkz_ctx* ctx, const DevModel& m, const uint8_t* d_text, const u
     if (P.outputs & TKZ_OUT_SPECIAL) TRY(ensure(ctx, ctx->a_out_special, T * 4));
     EmitOut eo{(uint32_t*)ctx->a_out_ids.p, (uint32_t*)ctx->a_out_off.p, (uint32_t*)ctx->a_out_attn.p, (uint32_t*)ctx->a_out_type.p,
                (uint32_t*)ctx->a_out_special.p};
-    tile_emit_kernel<<<n_tiles, DT_THREADS, 0, st>>>(ta, ep, eo); launches++;
+    if (!P.has_truncation && !P.has_padding) tile_emit_kernel<true><<<n_tiles, DT_THREADS, 0, st>>>(ta, ep, eo);
+    else tile_emit_kernel<false><<<n_tiles, DT_THREADS, 0, st>>>(ta, ep, eo);
+    launches++;
     if (P.has_padding && nd) {
         emit_pad_real_kernel<<<(unsigned)(((uint64_t)nd * 32 + 255) / 256), 256, 0, st>>>(ep, eo, nd, (const uint32_t*)ctx->a_doc_real.p, ta.doc_tok_off); launches++;
     }

@@ -147,4 +147,20 @@ __device__ __forceinline__ unsigned long long block_excl_scan64(unsigned long lo
     return r;
 }
 
+// 32-bit block exclusive scan with ONE barrier per call: `sh` holds 2 * (NW + 1) u32 and is double-buffered on `phase`
+// (callers alternate phase 0/1 between consecutive calls), every thread sums the warp totals below its own warp itself.
+template <int NW>
+__device__ __forceinline__ uint32_t block_excl_scan32(uint32_t v, uint32_t* sh, uint32_t phase, uint32_t* total) {
+    const uint32_t lane = lane_id(), wid = threadIdx.x >> 5;
+    uint32_t* s = sh + (phase & 1u) * (NW + 1);
+    const uint32_t inc = warp_incl_scan(v);
+    if (lane == 31) s[wid] = inc;
+    __syncthreads();
+    uint32_t base = 0, tot = 0;
+#pragma unroll
+    for (int w = 0; w < NW; w++) { const uint32_t x = s[w]; tot += x; if ((uint32_t)w < wid) base += x; }
+    *total = tot;
+    return base + inc - v;
+}
+
 }  // namespace tkz

@@ -34,7 +34,7 @@ constexpr int DT_MAX_PROBE = 48;
 struct __align__(16) DedupSlot {
     unsigned long long k0, k1;                    // the word: bytes 0..14, length in byte 15; all zero = empty
     uint32_t tok_off, ntok;                       // token records upool[tok_off .. +ntok); ntok == TKZ_NONE: model error
-    uint32_t pad0, pad1;
+    unsigned long long rec0;                      // copy of the first record: single-token words need no second look-up
 };
 static_assert(sizeof(DedupSlot) == 32, "slot is one 32-byte sector");
 
@@ -60,7 +60,16 @@ struct DedupArgs {
     uint32_t* uniq_slots; unsigned int* n_uniq;
     uint32_t* long_start; uint32_t* long_end; unsigned int* n_long; uint32_t long_cap; unsigned int* overflow;
     uint32_t* tile_words; uint32_t* tile_nwords; uint32_t* doc_word_ref;
+    const uint32_t* tile_doc_lo;                  // first document with doc_off >= tile start (n_tiles + 1 entries)
 };
+
+// first document that starts at or after each tile start; entry n_tiles = n_docs + 1.  One thread per tile, so the
+// binary searches overlap instead of stalling a whole block behind thread 0.
+__global__ void tile_doc_index_kernel(const uint64_t* __restrict__ doc_off, uint32_t n_docs, uint32_t n_tiles, uint32_t* __restrict__ tile_doc_lo) {
+    const uint32_t tile = blockIdx.x * blockDim.x + threadIdx.x;
+    if (tile < n_tiles) tile_doc_lo[tile] = lower_bound_u64(doc_off, 0, n_docs + 1, (uint64_t)tile * 4096u);
+    else if (tile == n_tiles) tile_doc_lo[tile] = n_docs + 1;
+}
 
 struct DedupShared {
     uint8_t norm[256];
@@ -70,8 +79,7 @@ struct DedupShared {
     uint32_t docbits[(DT_TILE + 2 * DT_SEG) / 32 + 2]; // bit p: a document starts at tile_base + p
     uint32_t seg_smask[DT_THREADS];
     uint32_t seg_sprefix[DT_THREADS];
-    unsigned long long scan[DT_THREADS / 32 + 2];
-    uint32_t d_lo, d_hi;
+    uint32_t scan[2 * (DT_THREADS / 32 + 1)];
 };
 
 // classify + normalise one 16-byte segment; bytes at or beyond n read as DELIM
@@ -121,13 +129,12 @@ __global__ void __launch_bounds__(DT_THREADS) tile_split_dedup_kernel(DevModel m
     sh.norm[t] = m.lut[t];
     sh.cls[t] = m.lut[256 + t];
     if (t < (DT_TILE + 2 * DT_SEG) / 32 + 2) sh.docbits[t] = 0;
-    if (t == 0) {
-        sh.d_lo = lower_bound_u64(a.doc_off, 0, a.n_docs + 1, tile_base);
-        sh.d_hi = upper_bound_u64(a.doc_off, sh.d_lo, a.n_docs + 1, tile_base + DT_TILE + 2 * DT_SEG);
-    }
+    const uint32_t d_lo = __ldg(a.tile_doc_lo + tile);
     __syncthreads();
-    for (uint32_t d = sh.d_lo + t; d < sh.d_hi; d += DT_THREADS) {
-        const uint32_t p = (uint32_t)(__ldg(a.doc_off + d) - tile_base);
+    for (uint32_t d = d_lo + t; d <= a.n_docs; d += DT_THREADS) {
+        const uint64_t off = __ldg(a.doc_off + d);
+        if (off > tile_base + DT_TILE + 2 * DT_SEG) break;
+        const uint32_t p = (uint32_t)(off - tile_base);
         atomicOr(&sh.docbits[p >> 5], 1u << (p & 31));
     }
     dt_load_segment(a.text, a.n, tile_base + (uint64_t)t * DT_SEG, t, sh);
@@ -144,8 +151,8 @@ __global__ void __launch_bounds__(DT_THREADS) tile_split_dedup_kernel(DevModel m
     const uint32_t ds = (uint32_t)d48 & 0xFFFFu;
     const uint32_t word_prev = ((word << 1) | prev_word) & 0xFFFFu;
     uint32_t smask = (iso | (word & (~word_prev | ds))) & 0xFFFFu;
-    unsigned long long total;
-    const uint32_t ex = (uint32_t)block_excl_scan64<DT_THREADS / 32>((unsigned long long)__popc(smask), sh.scan, &total);
+    uint32_t total;
+    const uint32_t ex = block_excl_scan32<DT_THREADS / 32>(__popc(smask), sh.scan, 0, &total);
     sh.seg_smask[t] = smask;
     sh.seg_sprefix[t] = ex;
 
@@ -199,7 +206,7 @@ __global__ void __launch_bounds__(DT_THREADS) tile_split_dedup_kernel(DevModel m
         } else {
             // long word: find its end (first non-WORD byte or next document start)
             const uint64_t start = tile_base + p;
-            const uint32_t dn = upper_bound_u64(a.doc_off, sh.d_lo > 0 ? sh.d_lo - 1 : 0, a.n_docs + 1, start);
+            const uint32_t dn = upper_bound_u64(a.doc_off, d_lo > 0 ? d_lo - 1 : 0, a.n_docs + 1, start);
             uint64_t limit = dn <= a.n_docs ? __ldg(a.doc_off + dn) : a.n;
             if (limit > a.n) limit = a.n;
             uint64_t q = start + DT_MAX_SHORT + 1;
@@ -214,10 +221,10 @@ __global__ void __launch_bounds__(DT_THREADS) tile_split_dedup_kernel(DevModel m
         }
         *out++ = entry;
     }
-    if (t == 0) a.tile_nwords[tile] = (uint32_t)total;
+    if (t == 0) a.tile_nwords[tile] = total;
     __syncthreads();
     // ---- first word (virtual index = tile * WCAP + local index) of every document that starts inside this tile
-    for (uint32_t d = sh.d_lo + t; d < sh.d_hi; d += DT_THREADS) {
+    for (uint32_t d = d_lo + t; d <= a.n_docs; d += DT_THREADS) {
         const uint64_t off = __ldg(a.doc_off + d);
         if (off >= tile_base + DT_TILE) break;
         const uint32_t p = (uint32_t)(off - tile_base);
@@ -253,8 +260,11 @@ __global__ void __launch_bounds__(UQ_WARPS * 32) bpe_unique_kernel(DevModel m, U
             else { off = atomicAdd(a.upool_count, n); s->tok_off = off; s->ntok = n; }
         }
         off = __shfl_sync(FULL, off, 0);
-        if (n != TKZ_NONE && lane < n)
-            a.upool[off + lane] = (unsigned long long)s_id[wid][lane] | ((unsigned long long)s_s[wid][lane] << 32) | ((unsigned long long)s_e[wid][lane] << 40);
+        if (n != TKZ_NONE && lane < n) {
+            const unsigned long long r = (unsigned long long)s_id[wid][lane] | ((unsigned long long)s_s[wid][lane] << 32) | ((unsigned long long)s_e[wid][lane] << 40);
+            a.upool[off + lane] = r;
+            if (lane == 0) s->rec0 = r;
+        }
         __syncwarp();
     }
 }
@@ -279,8 +289,11 @@ __global__ void __launch_bounds__(UQ_WARPS * 32) wordpiece_unique_kernel(DevMode
             else { off = atomicAdd(a.upool_count, n); s->tok_off = off; s->ntok = n; }
         }
         off = __shfl_sync(FULL, off, 0);
-        if (n != TKZ_NONE && lane < n)
-            a.upool[off + lane] = (unsigned long long)s_id[wid][lane] | ((unsigned long long)s_s[wid][lane] << 32) | ((unsigned long long)s_e[wid][lane] << 40);
+        if (n != TKZ_NONE && lane < n) {
+            const unsigned long long r = (unsigned long long)s_id[wid][lane] | ((unsigned long long)s_s[wid][lane] << 32) | ((unsigned long long)s_e[wid][lane] << 40);
+            a.upool[off + lane] = r;
+            if (lane == 0) s->rec0 = r;
+        }
         __syncwarp();
     }
 }
@@ -291,7 +304,7 @@ struct TileOutArgs {
     const DedupSlot* table; const unsigned long long* upool;
     const uint32_t* long_start; const uint32_t* long_ntok;
     const uint32_t* pool_id; const uint32_t* pool_s; const uint32_t* pool_e;
-    const uint32_t* tile_words; const uint32_t* tile_nwords; const uint32_t* doc_word_ref;
+    const uint32_t* tile_words; const uint32_t* tile_nwords; const uint32_t* doc_word_ref; const uint32_t* tile_doc_lo;
     uint32_t* tile_ntok;               // P3a out; after the scan: exclusive token base per tile (n_tiles + 1)
     uint32_t* doc_tok_local;           // P3a out: token prefix (tile-local) at the document's first word
     uint32_t* doc_tok_start;           // doc_finish out: global real-token index at the document start (n_docs + 1)
@@ -305,32 +318,27 @@ __device__ __forceinline__ uint32_t entry_ntok(const TileOutArgs& a, uint32_t e)
 
 __global__ void __launch_bounds__(DT_THREADS) tile_count_kernel(TileOutArgs a) {
     __shared__ uint32_t prefix[DT_WCAP + 1];
-    __shared__ unsigned long long scan[DT_THREADS / 32 + 2];
-    __shared__ uint32_t d_lo_s, d_hi_s;
+    __shared__ uint32_t scan[2 * (DT_THREADS / 32 + 1)];
     const uint32_t t = threadIdx.x, tile = blockIdx.x;
     const uint32_t nw = a.tile_nwords[tile];
+    const uint32_t d_lo = __ldg(a.tile_doc_lo + tile), d_hi = __ldg(a.tile_doc_lo + tile + 1);
     const uint32_t* words = a.tile_words + (size_t)tile * DT_WCAP;
-    uint32_t carry = 0;
-    for (uint32_t i0 = 0; i0 < nw; i0 += DT_THREADS) {
+    uint32_t carry = 0, phase = 0;
+    for (uint32_t i0 = 0; i0 < nw; i0 += DT_THREADS, phase ^= 1u) {
         const uint32_t k = i0 + t;
         uint32_t nt = 0;
         if (k < nw) {
             nt = entry_ntok(a, words[k]);
             if (nt == TKZ_NONE) { atomicMin(a.errw, ((unsigned long long)(tile * (uint32_t)DT_WCAP + k) << 8) | a.err_code); nt = 0; }
         }
-        unsigned long long tot;
-        const uint32_t ex = (uint32_t)block_excl_scan64<DT_THREADS / 32>(nt, scan, &tot);
+        uint32_t tot;
+        const uint32_t ex = block_excl_scan32<DT_THREADS / 32>(nt, scan, phase, &tot);
         if (k < nw) prefix[k] = carry + ex;
-        carry += (uint32_t)tot;
+        carry += tot;
     }
     if (t == 0) { prefix[nw] = carry; a.tile_ntok[tile] = carry; }
-    const uint64_t tile_base = (uint64_t)tile * DT_TILE;
-    if (t == 0) {
-        d_lo_s = lower_bound_u64(a.doc_off, 0, a.n_docs + 1, tile_base);
-        d_hi_s = lower_bound_u64(a.doc_off, d_lo_s, a.n_docs + 1, tile_base + DT_TILE);
-    }
     __syncthreads();
-    for (uint32_t d = d_lo_s + t; d < d_hi_s; d += DT_THREADS) {
+    for (uint32_t d = d_lo + t; d < d_hi; d += DT_THREADS) {
         uint32_t j = a.doc_word_ref[d] - tile * DT_WCAP;
         if (j > nw) j = nw;
         a.doc_tok_local[d] = prefix[j];
@@ -352,36 +360,33 @@ __global__ void doc_finish_kernel(TileOutArgs a, EmitParams p, uint32_t* __restr
     }
 }
 
+// PLAIN = no truncation and no padding: the output is the plain concatenation of all tokens in text order, so the
+// destination of a token is its global index and no document look-up is needed.
+template <bool PLAIN>
 __global__ void __launch_bounds__(DT_THREADS) tile_emit_kernel(TileOutArgs a, EmitParams p, EmitOut o) {
-    __shared__ unsigned long long scan[DT_THREADS / 32 + 2];
-    __shared__ uint32_t d_lo_s, d_hi_s;
+    __shared__ uint32_t scan[2 * (DT_THREADS / 32 + 1)];
     const uint32_t FULL = 0xFFFFFFFFu;
     const uint32_t t = threadIdx.x, lane = lane_id(), tile = blockIdx.x;
     const uint32_t nw = a.tile_nwords[tile];
     const uint32_t* words = a.tile_words + (size_t)tile * DT_WCAP;
-    const uint64_t tile_base = (uint64_t)tile * DT_TILE;
-    if (t == 0) {
-        d_lo_s = lower_bound_u64(a.doc_off, 0, a.n_docs + 1, tile_base);
-        d_hi_s = lower_bound_u64(a.doc_off, d_lo_s, a.n_docs + 1, tile_base + DT_TILE);
-    }
-    __syncthreads();
-    const uint32_t d_lo = d_lo_s, d_hi = d_hi_s;
+    const uint32_t d_lo = PLAIN ? 0u : __ldg(a.tile_doc_lo + tile), d_hi = PLAIN ? 0u : __ldg(a.tile_doc_lo + tile + 1);
     uint32_t carry = a.tile_ntok[tile];                       // global real-token index of the tile's first token
-    for (uint32_t i0 = 0; i0 < nw; i0 += DT_THREADS) {
+    uint32_t phase = 0;
+    for (uint32_t i0 = 0; i0 < nw; i0 += DT_THREADS, phase ^= 1u) {
         const uint32_t k = i0 + t;
-        uint32_t e = 0, nt = 0, tok_off = 0;
+        uint32_t e = 0, nt = 0, tok_off = 0; unsigned long long rec0 = 0;
         if (k < nw) {
             e = words[k];
             if (e & DT_LONG) { nt = __ldg(a.long_ntok + (e & ~DT_LONG)); tok_off = __ldg(a.long_start + (e & ~DT_LONG)); }
-            else { const uint2 v = __ldg(reinterpret_cast<const uint2*>(&a.table[e].tok_off)); tok_off = v.x; nt = v.y; }
+            else { const uint4 v = __ldg(reinterpret_cast<const uint4*>(&a.table[e].tok_off)); tok_off = v.x; nt = v.y; rec0 = (unsigned long long)v.z | ((unsigned long long)v.w << 32); }
             if (nt == TKZ_NONE) nt = 0;
         }
-        unsigned long long tot;
-        const uint32_t t0 = carry + (uint32_t)block_excl_scan64<DT_THREADS / 32>(nt, scan, &tot);
-        carry += (uint32_t)tot;
+        uint32_t tot;
+        const uint32_t t0 = carry + block_excl_scan32<DT_THREADS / 32>(nt, scan, phase, &tot);
+        carry += tot;
         // destination of the word's first token
-        uint32_t cnt = nt; unsigned long long dst = 0;
-        if (nt) {
+        uint32_t cnt = nt; unsigned long long dst = t0;
+        if (!PLAIN && nt) {
             // owning document = last document whose first-word reference is <= this word's virtual index
             const uint32_t v = tile * DT_WCAP + k;
             uint32_t lo = d_lo, hi = d_hi;
@@ -398,7 +403,8 @@ __global__ void __launch_bounds__(DT_THREADS) tile_emit_kernel(TileOutArgs a, Em
         }
         const bool is_long = (e & DT_LONG) != 0;
         if (cnt && !is_long) {
-            for (uint32_t i = 0; i < cnt; i++) {
+            emit_real(p, o, dst, (uint32_t)rec0, (uint32_t)(rec0 >> 32) & 0xFFu, (uint32_t)(rec0 >> 40) & 0xFFu);
+            for (uint32_t i = 1; i < cnt; i++) {
                 const unsigned long long r = __ldg(a.upool + tok_off + i);
                 emit_real(p, o, dst + i, (uint32_t)r, (uint32_t)(r >> 32) & 0xFFu, (uint32_t)(r >> 40) & 0xFFu);
             }
