@@ -10,11 +10,14 @@
 // There is no CPU fallback: without a usable CUDA device every entry point fails with TKZ_ERR_CUDA.
 #include <cstdio>
 #include <cstring>
+#include <algorithm>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "../../include/tokzig_b200.h"
 #include "tkz_bpe.cuh"
+#include "tkz_bpe_block.cuh"
 #include "tkz_common.cuh"
 #include "tkz_dedup.cuh"
 #include "tkz_emit.cuh"
@@ -48,14 +51,22 @@ struct tkz_ctx {
     bool has_model = false;
     DevModel dm{}, dm_post{};
     // model tables
-    DevBuf t_lut, t_lut_post, t_char_ascii, t_char_tab, t_merges, t_wp_tab, t_wp_pool;
+    DevBuf t_lut, t_lut_post, t_char_ascii, t_char_tab, t_merges, t_merge_win, t_wp_tab, t_wp_pool;
     // arenas (grow-only; replace src/arena.zig)
     DevBuf a_text, a_doc_off, a_norm_text, a_norm_doc_off, a_chunk, a_tiles, a_word_start, a_word_end, a_word_doc, a_doc_word_off,
-        a_word_ntok, a_pool_id, a_pool_s, a_pool_e, a_pool_rk, a_scan_tmp, a_doc_tok_off, a_out_ids, a_out_off, a_out_attn,
-        a_out_type, a_out_special, a_ctrl;
+        a_word_ntok, a_pool_id, a_pool_s, a_pool_e, a_pool_rk, a_scan_tmp, a_ctrl;
+    // output arrays, double-buffered so that the D2H copy of one chunk overlaps the kernels of the next (tkz_encode_batch)
+    struct OutSet { DevBuf doc_tok_off, ids, off, attn, type, special; } outs[2];
+    int out_sel = 0;
+    OutSet& O() { return outs[out_sel]; }
+    DevBuf in_text[2], in_doc_off[2];
+    HostBuf h_doc_stage[2];
+    cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
+    cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_d2h[2] = {nullptr, nullptr};
+    uint64_t chunk_bytes = 64ull << 20;
     // dedup pipeline arenas
     DevBuf a_table, a_uniq, a_long_start, a_long_end, a_long_ntok, a_tile_words, a_tile_nwords, a_tile_ntok, a_doc_word_ref,
-        a_doc_tok_local, a_doc_tok_start, a_doc_real, a_upool, a_tile_doc_lo;
+        a_doc_tok_local, a_doc_tok_start, a_doc_real, a_upool, a_tile_doc_lo, a_g_first, a_g_win, a_g_flag;
     bool use_dedup = true;
     HostBuf h_ctrl, h_doc_tok_off, h_ids, h_off, h_attn, h_type, h_special;
     uint64_t arena_bytes = 0;
@@ -77,7 +88,12 @@ namespace {
 int ensure(tkz_ctx* ctx, DevBuf& b, size_t bytes) {
     if (bytes == 0) bytes = 16;
     if (b.cap >= bytes) return TKZ_OK;
-    if (b.p) { CK(cudaStreamSynchronize(ctx->stream)); CK(cudaFree(b.p)); ctx->arena_bytes -= b.cap; b.p = nullptr; b.cap = 0; }
+    if (b.p) {
+        CK(cudaStreamSynchronize(ctx->stream));
+        if (ctx->s_h2d) CK(cudaStreamSynchronize(ctx->s_h2d));
+        if (ctx->s_d2h) CK(cudaStreamSynchronize(ctx->s_d2h));
+        CK(cudaFree(b.p)); ctx->arena_bytes -= b.cap; b.p = nullptr; b.cap = 0;
+    }
     size_t want = bytes + bytes / 8 + 256;      // head-room so steady-state batches of similar size do not re-allocate
     cudaError_t e = cudaMalloc(&b.p, want);
     if (e != cudaSuccess) { want = bytes; e = cudaMalloc(&b.p, want); }
@@ -135,6 +151,19 @@ __global__ void gather_scalars_dedup_kernel(unsigned long long* ctrl, const uint
     }
     ctrl[4] = d;
 }
+// word-length classes of the BPE kernels: [0] 65..2048 bytes, [1] > 2048, [2] > 12288 (needs global state arrays)
+constexpr uint32_t BB_WARP_MAX = 64, BB_SMALL_MAX = 2048, BB_BIG_CAP = 12288;
+__global__ void len_class_count_kernel(const uint32_t* word_start, const uint32_t* word_end, uint32_t n_fixed, const unsigned int* n_dev,
+                                       unsigned long long* counts) {
+    const uint32_t n = n_dev ? *n_dev : n_fixed;
+    unsigned int c0 = 0, c1 = 0, c2 = 0;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint32_t len = word_end[i] - word_start[i];
+        c0 += (len > BB_WARP_MAX && len <= BB_SMALL_MAX); c1 += (len > BB_SMALL_MAX); c2 += (len > BB_BIG_CAP);
+    }
+    for (int d = 16; d > 0; d >>= 1) { c0 += __shfl_xor_sync(0xFFFFFFFFu, c0, d); c1 += __shfl_xor_sync(0xFFFFFFFFu, c1, d); c2 += __shfl_xor_sync(0xFFFFFFFFu, c2, d); }
+    if ((threadIdx.x & 31) == 0) { if (c0) atomicAdd(counts, (unsigned long long)c0); if (c1) atomicAdd(counts + 1, (unsigned long long)c1); if (c2) atomicAdd(counts + 2, (unsigned long long)c2); }
+}
 __global__ void gather_scalars_kernel(unsigned long long* ctrl, const uint32_t* word_tok_off, uint32_t n_words,
                                       const unsigned long long* doc_tok_off, uint32_t n_docs, const uint32_t* word_doc) {
     ctrl[2] = word_tok_off[n_words];
@@ -169,6 +198,7 @@ extern "C" int tkz_ctx_create(int device, void* stream, uint64_t arena_hint_byte
         if (e != cudaSuccess) { g_create_error = std::string("cudaStreamCreate: ") + cudaGetErrorString(e); delete ctx; return TKZ_ERR_CUDA; }
         ctx->own_stream = true;
     }
+    cudaFuncSetAttribute(bpe_block_kernel<1024, 12288>, cudaFuncAttributeMaxDynamicSharedMemorySize, 12288 * 15);
     e = cudaFuncSetAttribute(bpe_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BPE_SMEM_BYTES);
     if (e != cudaSuccess) {
         g_create_error = std::string("kernel image not usable on this device (built for sm_100a): ") + cudaGetErrorString(e);
@@ -180,6 +210,10 @@ extern "C" int tkz_ctx_create(int device, void* stream, uint64_t arena_hint_byte
     }
     (void)arena_hint_bytes;
     if (const char* e = getenv("TKZ_NO_DEDUP")) ctx->use_dedup = !(e[0] == '1');     // A/B switch for the parity tests
+    if (const char* e = getenv("TKZ_CHUNK_BYTES")) { const long long v = atoll(e); if (v > 0) ctx->chunk_bytes = (uint64_t)v; }
+    cudaStreamCreateWithFlags(&ctx->s_h2d, cudaStreamNonBlocking);
+    cudaStreamCreateWithFlags(&ctx->s_d2h, cudaStreamNonBlocking);
+    for (int i = 0; i < 2; i++) { cudaEventCreateWithFlags(&ctx->ev_h2d[i], cudaEventDisableTiming); cudaEventCreateWithFlags(&ctx->ev_d2h[i], cudaEventDisableTiming); }
     for (auto& ev : ctx->ev) cudaEventCreate(&ev);
     *out = ctx;
     return TKZ_OK;
@@ -189,16 +223,22 @@ extern "C" void tkz_ctx_destroy(tkz_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    DevBuf* bufs[] = {&ctx->t_lut, &ctx->t_lut_post, &ctx->t_char_ascii, &ctx->t_char_tab, &ctx->t_merges, &ctx->t_wp_tab, &ctx->t_wp_pool,
+    DevBuf* bufs[] = {&ctx->t_lut, &ctx->t_lut_post, &ctx->t_char_ascii, &ctx->t_char_tab, &ctx->t_merges, &ctx->t_merge_win, &ctx->t_wp_tab, &ctx->t_wp_pool,
                       &ctx->a_text, &ctx->a_doc_off, &ctx->a_norm_text, &ctx->a_norm_doc_off, &ctx->a_chunk, &ctx->a_tiles, &ctx->a_word_start,
                       &ctx->a_word_end, &ctx->a_word_doc, &ctx->a_doc_word_off, &ctx->a_word_ntok, &ctx->a_pool_id, &ctx->a_pool_s, &ctx->a_pool_e,
-                      &ctx->a_pool_rk, &ctx->a_scan_tmp, &ctx->a_doc_tok_off, &ctx->a_out_ids, &ctx->a_out_off, &ctx->a_out_attn, &ctx->a_out_type,
-                      &ctx->a_out_special, &ctx->a_ctrl, &ctx->a_table, &ctx->a_uniq, &ctx->a_long_start, &ctx->a_long_end, &ctx->a_long_ntok,
+                      &ctx->a_pool_rk, &ctx->a_scan_tmp, &ctx->outs[0].doc_tok_off, &ctx->outs[0].ids, &ctx->outs[0].off, &ctx->outs[0].attn,
+                      &ctx->outs[0].type, &ctx->outs[0].special, &ctx->outs[1].doc_tok_off, &ctx->outs[1].ids, &ctx->outs[1].off,
+                      &ctx->outs[1].attn, &ctx->outs[1].type, &ctx->outs[1].special, &ctx->in_text[0], &ctx->in_text[1], &ctx->in_doc_off[0],
+                      &ctx->in_doc_off[1], &ctx->a_ctrl, &ctx->a_table, &ctx->a_uniq, &ctx->a_long_start, &ctx->a_long_end, &ctx->a_long_ntok,
                       &ctx->a_tile_words, &ctx->a_tile_nwords, &ctx->a_tile_ntok, &ctx->a_doc_word_ref, &ctx->a_doc_tok_local,
-                      &ctx->a_doc_tok_start, &ctx->a_doc_real, &ctx->a_upool, &ctx->a_tile_doc_lo};
+                      &ctx->a_doc_tok_start, &ctx->a_doc_real, &ctx->a_upool, &ctx->a_tile_doc_lo, &ctx->a_g_first, &ctx->a_g_win, &ctx->a_g_flag};
     for (DevBuf* b : bufs) release(*b);
-    HostBuf* hb[] = {&ctx->h_ctrl, &ctx->h_doc_tok_off, &ctx->h_ids, &ctx->h_off, &ctx->h_attn, &ctx->h_type, &ctx->h_special};
+    HostBuf* hb[] = {&ctx->h_ctrl, &ctx->h_doc_tok_off, &ctx->h_ids, &ctx->h_off, &ctx->h_attn, &ctx->h_type, &ctx->h_special,
+                     &ctx->h_doc_stage[0], &ctx->h_doc_stage[1]};
     for (HostBuf* b : hb) release_host(*b);
+    if (ctx->s_h2d) cudaStreamDestroy(ctx->s_h2d);
+    if (ctx->s_d2h) cudaStreamDestroy(ctx->s_d2h);
+    for (int i = 0; i < 2; i++) { if (ctx->ev_h2d[i]) cudaEventDestroy(ctx->ev_h2d[i]); if (ctx->ev_d2h[i]) cudaEventDestroy(ctx->ev_d2h[i]); }
     for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -289,6 +329,50 @@ extern "C" int tkz_model_upload(tkz_ctx* ctx, const tkz_model_desc* d) {
         }
         TRY(upload(ctx, ctx->t_merges, mtab.data(), mtab.size() * sizeof(MergeEnt)));
         m.merges = (const MergeEnt*)ctx->t_merges.p; m.merge_mask = mcap - 1; m.n_merges = live;
+        // ---- is the table "proper"?  (every producer of a symbol has a lower rank than every merge that consumes it, ranks
+        // are unique).  Then the round order of bpe.zig:214-253 equals strict rank order and merges can be scheduled by
+        // windowed local minima (tkz_bpe_block.cuh); otherwise long words keep the literal round kernel.
+        {
+            std::vector<uint32_t> order;                       // live slots sorted by rank
+            for (uint32_t sl = 0; sl < mcap; sl++) if (mtab[sl].rank != TKZ_NONE) order.push_back(sl);
+            std::sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) { return mtab[x].rank < mtab[y].rank; });
+            bool proper = true;
+            for (size_t i = 1; i < order.size() && proper; i++) if (mtab[order[i]].rank == mtab[order[i - 1]].rank) proper = false;
+            std::unordered_map<uint32_t, uint32_t> max_prod, min_cons, nsym;    // per symbol id
+            for (uint32_t sl : order) {
+                const MergeEnt& e = mtab[sl];
+                auto it = max_prod.find(e.new_id);
+                if (it == max_prod.end() || it->second < e.rank) max_prod[e.new_id] = e.rank;
+                for (uint32_t x : {e.first, e.second}) { auto c = min_cons.find(x); if (c == min_cons.end() || c->second > e.rank) min_cons[x] = e.rank; }
+            }
+            for (auto& kv : max_prod) { auto c = min_cons.find(kv.first); if (c != min_cons.end() && c->second <= kv.second) { proper = false; break; } }
+            std::vector<uint16_t> win(mcap, 0);
+            if (proper) {
+                auto ns = [&](uint32_t id) -> uint32_t { auto it = nsym.find(id); return it == nsym.end() ? 1u : it->second; };
+                for (uint32_t sl : order) {                    // rank order: operands are final before they are consumed
+                    const MergeEnt& e = mtab[sl];
+                    const uint32_t v = ns(e.first) + ns(e.second);
+                    auto it = nsym.find(e.new_id);
+                    if (it == nsym.end() || it->second < v) nsym[e.new_id] = v;
+                }
+                std::unordered_map<uint32_t, uint32_t> WL, WR;  // WL[a] = max nsym(X) over merges (X, a); WR[b] = max nsym(Z) over (b, Z)
+                for (uint32_t sl : order) {
+                    const MergeEnt& e = mtab[sl];
+                    uint32_t& l = WL[e.second]; l = std::max(l, ns(e.first));
+                    uint32_t& r = WR[e.first]; r = std::max(r, ns(e.second));
+                }
+                for (uint32_t sl : order) {
+                    const MergeEnt& e = mtab[sl];
+                    const uint32_t wl = WL[e.first], wr = WR[e.second];     // threats to `first` from its left, to `second` from its right
+                    if (wl > 250 || wr > 250) { proper = false; break; }
+                    win[sl] = (uint16_t)(wl | (wr << 8));
+                }
+            }
+            TRY(upload(ctx, ctx->t_merge_win, win.data(), win.size() * 2));
+            m.merge_win = (const uint16_t*)ctx->t_merge_win.p;
+            m.windowed_ok = proper ? 1 : 0;
+            if (const char* e = getenv("TKZ_NO_WINDOWED")) if (e[0] == '1') m.windowed_ok = 0;
+        }
     } else {
         if (d->prefix_len > TKZ_MAX_PREFIX) { ctx->err = "continuing_subword_prefix longer than 64 bytes"; return TKZ_ERR_INVALID_ARG; }
         m.prefix_len = d->prefix_len;
@@ -332,6 +416,39 @@ extern "C" int tkz_model_upload(tkz_ctx* ctx, const tkz_model_desc* d) {
 // ------------------------------------------------------------------------------------------------ encode
 namespace {
 
+// BPE over a word list: warp kernel (literal rounds) for short words or improper tables, block kernels with the windowed
+// schedule for long words of proper tables.  cls = {#65..2048, #>2048, #>12288} from len_class_count_kernel.
+int launch_bpe(tkz_ctx* ctx, const DevModel& m, const uint8_t* d_text, const uint32_t* word_start, const uint32_t* word_end, uint32_t nw,
+               uint32_t* word_ntok, unsigned long long* ctrl, int ctr_slot, int sentinel, const unsigned long long* cls, uint64_t N,
+               uint64_t& launches) {
+    cudaStream_t st = ctx->stream;
+    const bool windowed = m.windowed_ok && (cls[0] || cls[1]);
+    TRY(ensure(ctx, ctx->a_pool_rk, N * 4));
+    BpeArgs a{d_text, word_start, word_end, nw, (uint32_t*)ctx->a_pool_id.p, (uint32_t*)ctx->a_pool_s.p, (uint32_t*)ctx->a_pool_e.p,
+              (uint32_t*)ctx->a_pool_rk.p, word_ntok, (unsigned int*)(ctrl + ctr_slot), ctrl, sentinel, windowed ? BB_WARP_MAX : 0xFFFFFFFFu};
+    uint64_t blocks = ((uint64_t)nw + BPE_WARPS - 1) / BPE_WARPS;
+    const uint64_t cap = (uint64_t)ctx->sm_count * 3; if (blocks > cap) blocks = cap;
+    bpe_warp_kernel<<<(unsigned)blocks, BPE_WARPS * 32, BPE_SMEM_BYTES, st>>>(m, a); launches++;
+    if (!windowed) return TKZ_OK;
+    if (cls[2]) { TRY(ensure(ctx, ctx->a_g_first, N * 4)); TRY(ensure(ctx, ctx->a_g_win, N * 2)); TRY(ensure(ctx, ctx->a_g_flag, N)); }
+    BlockBpeArgs b{};
+    b.text = d_text; b.word_start = word_start; b.word_end = word_end; b.n_words = nw;
+    b.pool_id = (uint32_t*)ctx->a_pool_id.p; b.pool_s = (uint32_t*)ctx->a_pool_s.p; b.pool_e = (uint32_t*)ctx->a_pool_e.p; b.pool_rk = (uint32_t*)ctx->a_pool_rk.p;
+    b.g_first = (uint32_t*)ctx->a_g_first.p; b.g_win = (uint16_t*)ctx->a_g_win.p; b.g_flag = (uint8_t*)ctx->a_g_flag.p;
+    b.word_ntok = word_ntok; b.errw = ctrl; b.sentinel_errors = sentinel;
+    if (cls[0]) {
+        b.min_len = BB_WARP_MAX + 1; b.max_len = BB_SMALL_MAX; b.work_counter = (unsigned int*)(ctrl + 11);
+        uint64_t g = cls[0]; const uint64_t gc = (uint64_t)ctx->sm_count * 6; if (g > gc) g = gc;
+        bpe_block_kernel<256, BB_SMALL_MAX><<<(unsigned)g, 256, BB_SMALL_MAX * 15, st>>>(m, b); launches++;
+    }
+    if (cls[1]) {
+        b.min_len = BB_SMALL_MAX + 1; b.max_len = 0xFFFFFFFFu; b.work_counter = (unsigned int*)(ctrl + 12);
+        uint64_t g = cls[1]; const uint64_t gc = (uint64_t)ctx->sm_count; if (g > gc) g = gc;
+        bpe_block_kernel<1024, BB_BIG_CAP><<<(unsigned)g, 1024, BB_BIG_CAP * 15, st>>>(m, b); launches++;
+    }
+    return TKZ_OK;
+}
+
 // The dedup pipeline (tkz_dedup.cuh).  Returns TKZ_RETRY_NO_DEDUP when the long list overflowed.
 int encode_dedup(tkz_ctx* ctx, const DevModel& m, const uint8_t* d_text, const uint64_t* d_doc_off, uint32_t nd, uint64_t N,
                  const tkz_encode_params& P, tkz_batch_result* out, uint64_t& launches) {
@@ -355,7 +472,7 @@ int encode_dedup(tkz_ctx* ctx, const DevModel& m, const uint8_t* d_text, const u
     TRY(ensure(ctx, ctx->a_doc_tok_start, (n_docs + 2) * 4));
     TRY(ensure(ctx, ctx->a_doc_real, (n_docs + 2) * 4));
     TRY(ensure(ctx, ctx->a_tile_doc_lo, ((size_t)n_tiles + 2) * 4));
-    TRY(ensure(ctx, ctx->a_doc_tok_off, (n_docs + 1) * 8));
+    TRY(ensure(ctx, ctx->O().doc_tok_off, (n_docs + 1) * 8));
     TRY(ensure(ctx, ctx->a_scan_tmp, (scan_tmp_elems(n_tiles) + scan_tmp_elems(n_docs)) * 8));
     CK(cudaMemsetAsync(ctx->a_table.p, 0, (size_t)tcap * sizeof(DedupSlot), st));
     DedupArgs da{};
@@ -368,7 +485,9 @@ int encode_dedup(tkz_ctx* ctx, const DevModel& m, const uint8_t* d_text, const u
     da.tile_doc_lo = (const uint32_t*)ctx->a_tile_doc_lo.p;
     tile_doc_index_kernel<<<(n_tiles + 1 + 255) / 256, 256, 0, st>>>(d_doc_off, nd, n_tiles, (uint32_t*)ctx->a_tile_doc_lo.p); launches++;
     tile_split_dedup_kernel<<<n_tiles, DT_THREADS, 0, st>>>(m, da); launches++;
+    if (m.kind == TKZ_MODEL_BPE) { len_class_count_kernel<<<128, 256, 0, st>>>(da.long_start, da.long_end, 0, da.n_long, ctrl + 13); launches++; }
     CK(cudaMemcpyAsync(hctrl + 16, ctrl + 6, 3 * 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(hctrl + 24, ctrl + 13, 3 * 8, cudaMemcpyDeviceToHost, st));
     CK(cudaEventRecord(ctx->ev[1], st));
     CK(cudaStreamSynchronize(st));
     const uint32_t n_uniq = (uint32_t)hctrl[16], n_long = (uint32_t)hctrl[17];
@@ -392,12 +511,7 @@ int encode_dedup(tkz_ctx* ctx, const DevModel& m, const uint8_t* d_text, const u
         TRY(ensure(ctx, ctx->a_pool_s, N * 4));
         TRY(ensure(ctx, ctx->a_pool_e, N * 4));
         if (m.kind == TKZ_MODEL_BPE) {
-            TRY(ensure(ctx, ctx->a_pool_rk, N * 4));
-            BpeArgs a{d_text, da.long_start, da.long_end, n_long, (uint32_t*)ctx->a_pool_id.p, (uint32_t*)ctx->a_pool_s.p, (uint32_t*)ctx->a_pool_e.p,
-                      (uint32_t*)ctx->a_pool_rk.p, (uint32_t*)ctx->a_long_ntok.p, (unsigned int*)(ctrl + 5), ctrl, 1};
-            uint64_t blocks = ((uint64_t)n_long + BPE_WARPS - 1) / BPE_WARPS;
-            const uint64_t cap = (uint64_t)ctx->sm_count * 3; if (blocks > cap) blocks = cap;
-            bpe_warp_kernel<<<(unsigned)blocks, BPE_WARPS * 32, BPE_SMEM_BYTES, st>>>(m, a); launches++;
+            TRY(launch_bpe(ctx, m, d_text, da.long_start, da.long_end, n_long, (uint32_t*)ctx->a_long_ntok.p, ctrl, 5, 1, hctrl + 24, N, launches));
         } else {
             WpArgs a{d_text, da.long_start, da.long_end, n_long, (uint32_t*)ctx->a_pool_id.p, (uint32_t*)ctx->a_pool_s.p, (uint32_t*)ctx->a_pool_e.p,
                      (uint32_t*)ctx->a_long_ntok.p, (unsigned int*)(ctrl + 5), ctrl, 1};
@@ -417,7 +531,7 @@ int encode_dedup(tkz_ctx* ctx, const DevModel& m, const uint8_t* d_text, const u
     ta.pool_id = (const uint32_t*)ctx->a_pool_id.p; ta.pool_s = (const uint32_t*)ctx->a_pool_s.p; ta.pool_e = (const uint32_t*)ctx->a_pool_e.p;
     ta.tile_words = da.tile_words; ta.tile_nwords = da.tile_nwords; ta.doc_word_ref = da.doc_word_ref; ta.tile_doc_lo = da.tile_doc_lo;
     ta.tile_ntok = (uint32_t*)ctx->a_tile_ntok.p; ta.doc_tok_local = (uint32_t*)ctx->a_doc_tok_local.p;
-    ta.doc_tok_start = (uint32_t*)ctx->a_doc_tok_start.p; ta.doc_tok_off = (unsigned long long*)ctx->a_doc_tok_off.p;
+    ta.doc_tok_start = (uint32_t*)ctx->a_doc_tok_start.p; ta.doc_tok_off = (unsigned long long*)ctx->O().doc_tok_off.p;
     ta.errw = ctrl; ta.err_code = m.kind == TKZ_MODEL_BPE ? TKZ_ECODE_UTF8 : TKZ_ECODE_UNK;
     tile_count_kernel<<<n_tiles, DT_THREADS, 0, st>>>(ta); launches++;
     tile_words_total_kernel<<<64, 256, 0, st>>>(da.tile_nwords, n_tiles, ctrl); launches++;
@@ -440,13 +554,13 @@ int encode_dedup(tkz_ctx* ctx, const DevModel& m, const uint8_t* d_text, const u
     CK(cudaEventRecord(ctx->ev[3], st));
 
     // ---- P3b: emit
-    TRY(ensure(ctx, ctx->a_out_ids, T * 4));
-    if (P.outputs & TKZ_OUT_OFFSETS) TRY(ensure(ctx, ctx->a_out_off, T * 8));
-    if (P.outputs & TKZ_OUT_ATTENTION) TRY(ensure(ctx, ctx->a_out_attn, T * 4));
-    if (P.outputs & TKZ_OUT_TYPE_IDS) TRY(ensure(ctx, ctx->a_out_type, T * 4));
-    if (P.outputs & TKZ_OUT_SPECIAL) TRY(ensure(ctx, ctx->a_out_special, T * 4));
-    EmitOut eo{(uint32_t*)ctx->a_out_ids.p, (uint32_t*)ctx->a_out_off.p, (uint32_t*)ctx->a_out_attn.p, (uint32_t*)ctx->a_out_type.p,
-               (uint32_t*)ctx->a_out_special.p};
+    TRY(ensure(ctx, ctx->O().ids, T * 4));
+    if (P.outputs & TKZ_OUT_OFFSETS) TRY(ensure(ctx, ctx->O().off, T * 8));
+    if (P.outputs & TKZ_OUT_ATTENTION) TRY(ensure(ctx, ctx->O().attn, T * 4));
+    if (P.outputs & TKZ_OUT_TYPE_IDS) TRY(ensure(ctx, ctx->O().type, T * 4));
+    if (P.outputs & TKZ_OUT_SPECIAL) TRY(ensure(ctx, ctx->O().special, T * 4));
+    EmitOut eo{(uint32_t*)ctx->O().ids.p, (uint32_t*)ctx->O().off.p, (uint32_t*)ctx->O().attn.p, (uint32_t*)ctx->O().type.p,
+               (uint32_t*)ctx->O().special.p};
     if (!P.has_truncation && !P.has_padding) tile_emit_kernel<true><<<n_tiles, DT_THREADS, 0, st>>>(ta, ep, eo);
     else tile_emit_kernel<false><<<n_tiles, DT_THREADS, 0, st>>>(ta, ep, eo);
     launches++;
@@ -572,13 +686,10 @@ int encode_device_impl(tkz_ctx* ctx, const uint8_t* d_text, const uint64_t* d_do
     unsigned int* work_counter = (unsigned int*)(ctrl + 1);
     if (nw) {
         if (m.kind == TKZ_MODEL_BPE) {
-            TRY(ensure(ctx, ctx->a_pool_rk, N * 4));
-            BpeArgs a{d_text, word_start, word_end, nw, (uint32_t*)ctx->a_pool_id.p, (uint32_t*)ctx->a_pool_s.p, (uint32_t*)ctx->a_pool_e.p,
-                      (uint32_t*)ctx->a_pool_rk.p, word_ntok, work_counter, ctrl, 0};
-            uint64_t blocks = (W + BPE_WARPS - 1) / BPE_WARPS;
-            const uint64_t cap = (uint64_t)ctx->sm_count * 3;
-            if (blocks > cap) blocks = cap;
-            bpe_warp_kernel<<<(unsigned)blocks, BPE_WARPS * 32, BPE_SMEM_BYTES, st>>>(m, a); launches++;
+            len_class_count_kernel<<<128, 256, 0, st>>>(word_start, word_end, nw, nullptr, ctrl + 13); launches++;
+            CK(cudaMemcpyAsync(hctrl + 24, ctrl + 13, 3 * 8, cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            TRY(launch_bpe(ctx, m, d_text, word_start, word_end, nw, word_ntok, ctrl, 1, 0, hctrl + 24, N, launches));
         } else {
             WpArgs a{d_text, word_start, word_end, nw, (uint32_t*)ctx->a_pool_id.p, (uint32_t*)ctx->a_pool_s.p, (uint32_t*)ctx->a_pool_e.p,
                      word_ntok, work_counter, ctrl, 0};
@@ -594,8 +705,8 @@ int encode_device_impl(tkz_ctx* ctx, const uint8_t* d_text, const uint64_t* d_do
     TRY(ensure(ctx, ctx->a_scan_tmp, (scan_tmp_elems(W) + scan_tmp_elems(n_docs)) * 8));
     launches += exclusive_scan<uint32_t>(word_ntok, W, word_ntok, (unsigned long long*)ctx->a_scan_tmp.p, st);
     const uint32_t* word_tok_off = word_ntok;
-    TRY(ensure(ctx, ctx->a_doc_tok_off, (n_docs + 1) * 8));
-    unsigned long long* doc_tok_off = (unsigned long long*)ctx->a_doc_tok_off.p;
+    TRY(ensure(ctx, ctx->O().doc_tok_off, (n_docs + 1) * 8));
+    unsigned long long* doc_tok_off = (unsigned long long*)ctx->O().doc_tok_off.p;
     EmitParams ep{P.has_truncation, P.max_length, P.has_padding, P.pad_length, P.pad_id, P.pad_type_id, P.pad_left, P.outputs};
     if (nd) { doc_len_kernel<<<(nd + 255) / 256, 256, 0, st>>>(ep, word_tok_off, doc_word_off, nd, doc_tok_off); launches++; }
     launches += exclusive_scan<unsigned long long>(doc_tok_off, n_docs, doc_tok_off, (unsigned long long*)ctx->a_scan_tmp.p, st);
@@ -615,13 +726,13 @@ int encode_device_impl(tkz_ctx* ctx, const uint8_t* d_text, const uint64_t* d_do
 
     CK(cudaEventRecord(ctx->ev[3], st));
     // ---- K5: emit
-    TRY(ensure(ctx, ctx->a_out_ids, T * 4));
-    if (P.outputs & TKZ_OUT_OFFSETS) TRY(ensure(ctx, ctx->a_out_off, T * 8));
-    if (P.outputs & TKZ_OUT_ATTENTION) TRY(ensure(ctx, ctx->a_out_attn, T * 4));
-    if (P.outputs & TKZ_OUT_TYPE_IDS) TRY(ensure(ctx, ctx->a_out_type, T * 4));
-    if (P.outputs & TKZ_OUT_SPECIAL) TRY(ensure(ctx, ctx->a_out_special, T * 4));
-    EmitOut eo{(uint32_t*)ctx->a_out_ids.p, (uint32_t*)ctx->a_out_off.p, (uint32_t*)ctx->a_out_attn.p, (uint32_t*)ctx->a_out_type.p,
-               (uint32_t*)ctx->a_out_special.p};
+    TRY(ensure(ctx, ctx->O().ids, T * 4));
+    if (P.outputs & TKZ_OUT_OFFSETS) TRY(ensure(ctx, ctx->O().off, T * 8));
+    if (P.outputs & TKZ_OUT_ATTENTION) TRY(ensure(ctx, ctx->O().attn, T * 4));
+    if (P.outputs & TKZ_OUT_TYPE_IDS) TRY(ensure(ctx, ctx->O().type, T * 4));
+    if (P.outputs & TKZ_OUT_SPECIAL) TRY(ensure(ctx, ctx->O().special, T * 4));
+    EmitOut eo{(uint32_t*)ctx->O().ids.p, (uint32_t*)ctx->O().off.p, (uint32_t*)ctx->O().attn.p, (uint32_t*)ctx->O().type.p,
+               (uint32_t*)ctx->O().special.p};
     if (nw) {
         emit_words_kernel<<<(nw + 255) / 256, 256, 0, st>>>(ep, eo, nw, word_start, word_doc, word_tok_off, doc_word_off, doc_tok_off,
                                                             (const uint32_t*)ctx->a_pool_id.p, (const uint32_t*)ctx->a_pool_s.p,
@@ -657,13 +768,26 @@ extern "C" int tkz_encode_batch_device(tkz_ctx* ctx, const void* d_text, const v
     return encode_device_impl(ctx, (const uint8_t*)d_text, (const uint64_t*)d_doc_off, n_docs, text_bytes, params, out);
 }
 
-extern "C" int tkz_encode_batch(tkz_ctx* ctx, const uint8_t* text, const uint64_t* doc_off, uint64_t n_docs,
-                                const tkz_encode_params* params, tkz_batch_result* out) {
-    if (!ctx || !out || !doc_off) return TKZ_ERR_INVALID_ARG;
-    if (doc_off[0] != 0) { ctx->err = "doc_off[0] must be 0"; return TKZ_ERR_INVALID_ARG; }
-    const uint64_t N = doc_off[n_docs];
-    if (N && !text) return TKZ_ERR_INVALID_ARG;
-    CK(cudaSetDevice(ctx->device));
+namespace {
+
+// grows a pinned host result array keeping its first `keep` bytes
+int ensure_host_keep(tkz_ctx* ctx, HostBuf& b, size_t bytes, size_t keep) {
+    if (bytes == 0) bytes = 16;
+    if (b.cap >= bytes) return TKZ_OK;
+    CK(cudaStreamSynchronize(ctx->s_d2h));
+    void* np = nullptr;
+    const size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaHostAlloc(&np, want, cudaHostAllocDefault);
+    if (e != cudaSuccess) { ctx->err = std::string("cudaHostAlloc: ") + cudaGetErrorString(e); return TKZ_ERR_OOM; }
+    if (b.p) { if (keep) memcpy(np, b.p, keep); cudaFreeHost(b.p); }
+    b.p = np; b.cap = want;
+    return TKZ_OK;
+}
+
+// one shot: H2D everything, encode, D2H everything (small batches)
+int encode_host_single(tkz_ctx* ctx, const uint8_t* text, const uint64_t* doc_off, uint64_t n_docs, uint64_t N,
+                       const tkz_encode_params* params, tkz_batch_result* out) {
+    ctx->out_sel = 0;
     TRY(ensure(ctx, ctx->a_text, N));
     TRY(ensure(ctx, ctx->a_doc_off, (n_docs + 1) * 8));
     if (N) CK(cudaMemcpyAsync(ctx->a_text.p, text, N, cudaMemcpyHostToDevice, ctx->stream));
@@ -691,4 +815,107 @@ extern "C" int tkz_encode_batch(tkz_ctx* ctx, const uint8_t* text, const uint64_
     }
     CK(cudaStreamSynchronize(st));
     return TKZ_OK;
+}
+
+// chunked: documents are cut into ~chunk_bytes pieces; the H2D copy of chunk i+1 and the D2H copy of chunk i-1 run on
+// their own streams while the kernels of chunk i run (PCIe is full duplex).  Input and output device buffers are
+// double-buffered; results land in one set of pinned host arrays at their final positions.
+int encode_host_chunked(tkz_ctx* ctx, const uint8_t* text, const uint64_t* doc_off, uint64_t n_docs, uint64_t N,
+                        const tkz_encode_params* params, tkz_batch_result* out) {
+    memset(out, 0, sizeof *out);
+    out->err_doc = -1;
+    // chunk boundaries (document indices)
+    std::vector<uint64_t> cb; cb.push_back(0);
+    while (cb.back() < n_docs) {
+        const uint64_t d0 = cb.back(), target = doc_off[d0] + ctx->chunk_bytes;
+        uint64_t lo = d0 + 1, hi = n_docs;                       // last boundary with doc_off <= target, at least one document
+        while (lo < hi) { const uint64_t mid = lo + (hi - lo + 1) / 2; if (doc_off[mid] <= target) lo = mid; else hi = mid - 1; }
+        cb.push_back(lo);
+    }
+    const size_t nc = cb.size() - 1;
+    uint32_t outputs = params ? params->outputs : 0; if (outputs == 0) outputs = TKZ_OUT_ALL; outputs |= TKZ_OUT_IDS;
+    TRY(ensure_host(ctx, ctx->h_doc_tok_off, (n_docs + 1) * 8));
+    uint64_t* h_dto = (uint64_t*)ctx->h_doc_tok_off.p;
+    std::vector<uint64_t> tok_base(nc + 1, 0);
+    auto stage_in = [&](size_t i) -> int {
+        const int b = (int)(i & 1);
+        const uint64_t d0 = cb[i], d1 = cb[i + 1], base = doc_off[d0], nb = doc_off[d1] - base, nd = d1 - d0;
+        TRY(ensure(ctx, ctx->in_text[b], nb));
+        TRY(ensure(ctx, ctx->in_doc_off[b], (nd + 1) * 8));
+        TRY(ensure_host(ctx, ctx->h_doc_stage[b], (nd + 1) * 8));
+        uint64_t* st = (uint64_t*)ctx->h_doc_stage[b].p;
+        for (uint64_t k = 0; k <= nd; k++) st[k] = doc_off[d0 + k] - base;
+        if (nb) CK(cudaMemcpyAsync(ctx->in_text[b].p, text + base, nb, cudaMemcpyHostToDevice, ctx->s_h2d));
+        CK(cudaMemcpyAsync(ctx->in_doc_off[b].p, st, (nd + 1) * 8, cudaMemcpyHostToDevice, ctx->s_h2d));
+        CK(cudaEventRecord(ctx->ev_h2d[b], ctx->s_h2d));
+        return TKZ_OK;
+    };
+    TRY(stage_in(0));
+    uint64_t T_total = 0, T_real = 0;
+    for (size_t i = 0; i < nc; i++) {
+        const int b = (int)(i & 1);
+        const uint64_t d0 = cb[i], d1 = cb[i + 1], nd = d1 - d0, nb = doc_off[d1] - doc_off[d0];
+        if (i + 1 < nc) {
+            // buffer (i+1)&1 was read by the kernels of chunk i-1 (finished: the device path drains its stream) and its staging
+            // area by the H2D of chunk i-1 (same stream as the copy about to be enqueued)
+            CK(cudaStreamSynchronize(ctx->s_h2d));
+            TRY(stage_in(i + 1));
+        }
+        CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_h2d[b], 0));
+        CK(cudaEventSynchronize(ctx->ev_d2h[b]));              // output set b is free once chunk i-2 has been copied out
+        ctx->out_sel = b;
+        tkz_batch_result dev{};
+        int rc = encode_device_impl(ctx, (const uint8_t*)ctx->in_text[b].p, (const uint64_t*)ctx->in_doc_off[b].p, nd, nb, params, &dev);
+        if (rc != TKZ_OK) {
+            cudaStreamSynchronize(ctx->s_h2d); cudaStreamSynchronize(ctx->s_d2h);
+            out->err_doc = dev.err_doc >= 0 ? (int64_t)d0 + dev.err_doc : -1;
+            ctx->out_sel = 0;
+            return rc;
+        }
+        const uint64_t T = dev.n_tokens;
+        tok_base[i] = T_total;
+        // size the host arrays from the first chunk's token density
+        uint64_t est = T_total + T;
+        if (i == 0 && nb) est = (uint64_t)((double)T * ((double)N / (double)nb) * 1.03) + 4096;
+        if (est < T_total + T) est = T_total + T;
+        struct { const uint32_t* src; HostBuf* hb; size_t elem; } cp[] = {
+            {dev.ids, &ctx->h_ids, 4}, {dev.offsets, &ctx->h_off, 8}, {dev.attention_mask, &ctx->h_attn, 4},
+            {dev.type_ids, &ctx->h_type, 4}, {dev.special_tokens_mask, &ctx->h_special, 4}};
+        for (auto& c : cp) {
+            if (!c.src) continue;
+            TRY(ensure_host_keep(ctx, *c.hb, est * c.elem, T_total * c.elem));
+            if (T) CK(cudaMemcpyAsync((uint8_t*)c.hb->p + T_total * c.elem, c.src, T * c.elem, cudaMemcpyDeviceToHost, ctx->s_d2h));
+        }
+        CK(cudaMemcpyAsync(h_dto + d0, dev.doc_tok_off, (nd + 1) * 8, cudaMemcpyDeviceToHost, ctx->s_d2h));
+        CK(cudaEventRecord(ctx->ev_d2h[b], ctx->s_d2h));
+        T_total += T; T_real += dev.n_real_tokens;
+    }
+    tok_base[nc] = T_total;
+    CK(cudaStreamSynchronize(ctx->s_d2h));
+    CK(cudaStreamSynchronize(ctx->s_h2d));
+    // chunk-relative CSR offsets -> global
+    for (size_t i = 1; i < nc; i++) { const uint64_t base = tok_base[i]; for (uint64_t d = cb[i]; d < cb[i + 1]; d++) h_dto[d] += base; }
+    h_dto[n_docs] = T_total;
+    ctx->out_sel = 0;
+    out->n_docs = n_docs; out->n_tokens = T_total; out->n_real_tokens = T_real;
+    out->doc_tok_off = h_dto;
+    out->ids = (const uint32_t*)ctx->h_ids.p;
+    out->offsets = (outputs & TKZ_OUT_OFFSETS) ? (const uint32_t*)ctx->h_off.p : nullptr;
+    out->attention_mask = (outputs & TKZ_OUT_ATTENTION) ? (const uint32_t*)ctx->h_attn.p : nullptr;
+    out->type_ids = (outputs & TKZ_OUT_TYPE_IDS) ? (const uint32_t*)ctx->h_type.p : nullptr;
+    out->special_tokens_mask = (outputs & TKZ_OUT_SPECIAL) ? (const uint32_t*)ctx->h_special.p : nullptr;
+    return TKZ_OK;
+}
+
+}  // namespace
+
+extern "C" int tkz_encode_batch(tkz_ctx* ctx, const uint8_t* text, const uint64_t* doc_off, uint64_t n_docs,
+                                const tkz_encode_params* params, tkz_batch_result* out) {
+    if (!ctx || !out || !doc_off) return TKZ_ERR_INVALID_ARG;
+    if (doc_off[0] != 0) { ctx->err = "doc_off[0] must be 0"; return TKZ_ERR_INVALID_ARG; }
+    const uint64_t N = doc_off[n_docs];
+    if (N && !text) return TKZ_ERR_INVALID_ARG;
+    CK(cudaSetDevice(ctx->device));
+    if (n_docs >= 2 && N > ctx->chunk_bytes + ctx->chunk_bytes / 2) return encode_host_chunked(ctx, text, doc_off, n_docs, N, params, out);
+    return encode_host_single(ctx, text, doc_off, n_docs, N, params, out);
 }

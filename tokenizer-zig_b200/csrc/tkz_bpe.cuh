@@ -30,6 +30,7 @@ struct BpeArgs {
     unsigned int* work_counter;
     unsigned long long* errw;
     int sentinel_errors;          // 1: write word_ntok = TKZ_NONE on error instead of reporting (dedup pipeline)
+    uint32_t max_len;             // words longer than this belong to the block kernels (tkz_bpe_block.cuh); 0xFFFFFFFF = all
 };
 
 // exact sequential form of the apply loop (bpe.zig:240-252), used when new_id == first (the re-check at the same index
@@ -218,6 +219,7 @@ __global__ void __launch_bounds__(BPE_WARPS * 32) bpe_warp_kernel(DevModel m, Bp
         if (w >= a.n_words) break;
         const uint32_t ws = a.word_start[w], len = a.word_end[w] - ws;
         if (len == 0) { if (lane == 0) a.word_ntok[w] = 0; continue; }       // bpe.zig:174-176
+        if (len > a.max_len) continue;
         const bool in_smem = len <= BPE_SMEM_SYMS;
         uint32_t* ids = in_smem ? sh_id : a.pool_id + ws;
         uint32_t* ss = in_smem ? sh_s : a.pool_s + ws;

@@ -66,6 +66,9 @@ struct DevModel {
     const uint32_t* char_ascii;      // [128] id or TKZ_NONE
     const CharEnt* char_tab; uint32_t char_mask;
     const MergeEnt* merges; uint32_t merge_mask; uint32_t n_merges;
+    // windowed schedule (tkz_bpe_block.cuh): per merge-table slot, how far a competing merge can reach: low byte = WL of the
+    // pair's first symbol, high byte = WR of its second symbol; valid only when windowed_ok (table proven "proper" at upload)
+    const uint16_t* merge_win; int windowed_ok;
     int has_unk; uint32_t unk_id;
     // WordPiece
     const WpEnt* wp_tab; uint32_t wp_mask;
@@ -94,6 +97,17 @@ __device__ __forceinline__ uint32_t merge_rank_lookup(const DevModel& m, uint32_
         const uint4 e = __ldg(reinterpret_cast<const uint4*>(m.merges) + slot);
         if (e.z == TKZ_NONE) return TKZ_NONE;
         if (e.x == a && e.y == b) { if (new_id) *new_id = e.w; return e.z; }
+        slot = (slot + 1) & m.merge_mask;
+    }
+}
+// rank + new id + window of the pair (a, b); TKZ_NONE when the pair has no merge
+__device__ __forceinline__ uint32_t merge_lookup_win(const DevModel& m, uint32_t a, uint32_t b, uint32_t* new_id, uint32_t* win) {
+    if (m.n_merges == 0) return TKZ_NONE;
+    uint32_t slot = pair_hash32(a, b) & m.merge_mask;
+    for (;;) {
+        const uint4 e = __ldg(reinterpret_cast<const uint4*>(m.merges) + slot);
+        if (e.z == TKZ_NONE) return TKZ_NONE;
+        if (e.x == a && e.y == b) { *new_id = e.w; *win = __ldg(m.merge_win + slot); return e.z; }
         slot = (slot + 1) & m.merge_mask;
     }
 }
