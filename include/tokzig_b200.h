@@ -138,6 +138,7 @@ typedef struct tkz_stats {
     float ms_scan;                      /* prefix sums: tokens per word -> per document -> CSR */
     float ms_emit;                      /* K5: fused truncate / pad / output write */
     float ms_total;                     /* first kernel to last kernel */
+    uint32_t model_flags;               /* bit 0: merge table proven "proper" -> long words use the windowed block kernels */
 } tkz_stats;
 
 /* `device` = CUDA ordinal.  `stream` = a cudaStream_t the caller owns (e.g. torch's current stream) or NULL for a

@@ -7,7 +7,7 @@ ALPHA_MB = ["é", "ß", "ж", "中", "界", "😀", "¡"]
 
 
 def rand_bpe_json(rng: random.Random, n_merges=40, alphabet=None, unk=None, improper=0.0, degenerate=0.0, alias=0.0,
-                  pretok=None, normalizer=None, merges_as_arrays=None, dead_merges=0.1):
+                  pretok=None, normalizer=None, merges_as_arrays=None, dead_merges=0.1, unique_products=False):
     """A BPE tokenizer.json.  `improper`: probability that a merge is listed out of creation order (ranks then violate
     creation order); `degenerate`: extra vocab ids aliased so that a merge's new_id equals its first id;
     `alias`: probability that a new token re-uses an existing id; `dead_merges`: merges whose parts/result are not in
@@ -27,6 +27,8 @@ def rand_bpe_json(rng: random.Random, n_merges=40, alphabet=None, unk=None, impr
         m = a + b
         if len(m.encode()) > 40:
             continue
+        if unique_products and m in vocab:
+            continue                          # every token has exactly one producing merge ("proper" table)
         if m not in vocab:
             if rng.random() < alias:
                 vocab[m] = rng.choice(list(vocab.values()))

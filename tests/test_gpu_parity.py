@@ -257,7 +257,7 @@ def test_wordpiece_long_keys_and_512_byte_rule():
 @pytest.mark.parametrize("name,cname,algo,nbytes", [("gpt2_whitespace", "c2", 0, 3 << 20), ("gpt2_bytelevel", "c2", 1, 3 << 20),
                                                      ("bert_wordpiece", "c3", 0, 3 << 20), ("llama3_whitespace", "c4", 0, 2 << 20),
                                                      ("llama3_sequence", "c4", 1, 2 << 20), ("gpt2_whitespace", "c5", 1, 6 << 20),
-                                                     ("gpt2_bytelevel", "c5", 1, 1 << 20)])
+                                                     ("gpt2_bytelevel", "c5", 1, 6 << 20)])
 def test_synthesised_tokenizers_on_corpus(name, cname, algo, nbytes):
     js = tokenizers_io.tokenizer_json(name)
     t, o = pair(js)
@@ -354,4 +354,102 @@ def test_dedup_table_pressure_and_overflow(n_words):
     words = ["".join(rng.choice(chars) for _ in range(4)) for _ in range(n_words)]
     docs = [" ".join(words[i:i + 50]).encode() for i in range(0, len(words), 50)]
     assert_same(t.encode_batch(docs), o.encode_batch(docs, threads=8))
+    t.close()
+
+
+# ----------------------------------------------------------------------------- windowed block kernels (long words)
+def _long_docs(rng, alpha, lengths, p_run=0.1):
+    docs = []
+    for n in lengths:
+        out = []
+        while len(out) < n:
+            if rng.random() < p_run:
+                out.extend([rng.choice(alpha)] * rng.randint(2, 40))          # equal-symbol runs
+            elif rng.random() < 0.03:
+                out.append(rng.choice(["z", "Z", "語", " "]))                  # not in the vocab: dropped or <unk>
+            else:
+                out.append(rng.choice(alpha))
+        docs.append("".join(out[:n]).encode())
+    return docs
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_windowed_block_kernel_random_proper_tables(seed):
+    rng = random.Random(4000 + seed)
+    alpha = list("abcdefgh")[: rng.randint(2, 8)] + (["é", "中"] if seed % 2 else [])
+    js, alpha = rand_bpe_json(rng, n_merges=rng.randint(5, 400), alphabet=alpha, unk="<unk>" if seed % 4 == 0 else None,
+                              dead_merges=0.0, unique_products=True, pretok=[None, "Whitespace"][seed % 2])
+    t, o = pair(js)
+    lengths = [65, 66, 100, 255, 256, 257, 1000, 2047, 2048, 2049, 5000, 12287, 12288, 12289, 30000, 3, 0, 64]
+    docs = _long_docs(rng, alpha, lengths)
+    got = t.encode_batch(docs)
+    assert t.stats().model_flags & 1, "a table with unique producers listed in creation order must be recognised as proper"
+    assert_same(got, o.encode_batch(docs, algo=1), f"seed {seed}")
+    t.close()
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_long_words_with_improper_tables_use_literal_rounds(seed):
+    rng = random.Random(4100 + seed)
+    js, alpha = rand_bpe_json(rng, n_merges=80, alphabet=list("abcdef"), improper=0.4, degenerate=0.1 * (seed % 2), dead_merges=0.0)
+    t, o = pair(js)
+    docs = _long_docs(rng, alpha, [70, 300, 2100, 4000, 13000])
+    assert_same(t.encode_batch(docs), o.encode_batch(docs, algo=1), f"seed {seed}")
+    t.close()
+
+
+def test_windowed_cascades_and_runs_at_length():
+    # the SURVEY.md section 7 cascade (local minima merged in parallel would give [wxy, zu]) repeated past every kernel boundary
+    v = {"w": 0, "x": 1, "y": 2, "z": 3, "u": 4, "wx": 5, "wxy": 6, "wxyz": 7, "zu": 8, "xy": 9, "yz": 10}
+    merges = [["w", "x"], ["wx", "y"], ["wxy", "z"], ["z", "u"], ["x", "y"], ["y", "z"]]
+    t, o = pair(json.dumps({"model": {"type": "BPE", "vocab": v, "merges": merges}}))
+    docs = [b"wxyzu" * k for k in (13, 14, 410, 2500, 7000)] + [b"uzyxw" * 3000, b"xyzuwxyzu" * 1500, b"wxyzuzu" * 2000]
+    got = t.encode_batch(docs)
+    assert t.stats().model_flags & 1
+    assert_same(got, o.encode_batch(docs, algo=1))
+    t.close()
+    v = {"a": 0, "b": 1, "aa": 2, "aaaa": 3, "ab": 4, "aab": 5}
+    t, o = pair(json.dumps({"model": {"type": "BPE", "vocab": v, "merges": ["a a", "aa aa", "a b", "aa b"]}}))
+    docs = [b"a" * n for n in (65, 66, 67, 1023, 1024, 1025, 4097, 20001)] + [(b"a" * 9 + b"b") * 700, b"b" + b"a" * 3000 + b"b" * 5, (b"aab" * 5 + b"aaaab") * 600]
+    assert_same(t.encode_batch(docs), o.encode_batch(docs, algo=1))
+    t.close()
+
+
+def test_windowed_vs_literal_switch(monkeypatch):
+    """TKZ_NO_WINDOWED=1 forces the literal round kernel for long words: both schedules must give the oracle's answer."""
+    js = tokenizers_io.tokenizer_json("gpt2_bytelevel")
+    text, off = corpus.generate("c2", 1 << 20, seed=31)
+    o = orc.OracleTokenizer.from_json(js)
+    ref = o.encode_packed(text, off, algo=1, threads=8)
+    for flag in ("0", "1"):
+        monkeypatch.setenv("TKZ_NO_WINDOWED", flag)
+        t = tz.Tokenizer.from_json(js, device=0)
+        got = t.encode_packed(text, off)
+        assert bool(t.stats().model_flags & 1) == (flag == "0")
+        assert_same(got, ref, f"TKZ_NO_WINDOWED={flag}")
+        t.close()
+
+
+# ----------------------------------------------------------------------------- chunked (pipelined) host path
+@pytest.mark.parametrize("chunk", [4096, 65536])
+def test_chunked_host_path_matches_single_shot(monkeypatch, chunk):
+    monkeypatch.setenv("TKZ_CHUNK_BYTES", str(chunk))
+    for name, cname, trunc, pad in (("gpt2_whitespace", "c2", None, None), ("bert_wordpiece", "c3", 16, {"length": 24, "pad_id": 0, "direction": "left"})):
+        js = tokenizers_io.tokenizer_json(name)
+        t = tz.Tokenizer.from_json(js, device=0)
+        o = orc.OracleTokenizer.from_json(js)
+        t.truncation = None if trunc is None else {"max_length": trunc}
+        o.truncation = trunc
+        t.padding = pad
+        o.padding = pad
+        text, off = corpus.generate(cname, 1 << 20, seed=5)
+        assert_same(t.encode_packed(text, off), o.encode_packed(text, off, threads=8), f"{name} chunk {chunk}")
+        t.close()
+    # the error position is reported in whole-batch document numbering
+    js = json.dumps({"model": {"type": "BPE", "vocab": {"a": 0, "b": 1, "ab": 2}, "merges": ["a b"]}, "pre_tokenizer": {"type": "Whitespace"}})
+    t = tz.Tokenizer.from_json(js, device=0)
+    docs = [b"ab ab ab"] * 3000 + [b"ab \xff"] + [b"ab"] * 10
+    with pytest.raises(tz.TokzigError) as e:
+        t.encode_batch(docs)
+    assert e.value.code == tz.ERR_INVALID_UTF8 and e.value.doc == 3000
     t.close()

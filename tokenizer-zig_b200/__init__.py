@@ -96,7 +96,8 @@ class BatchResult(C.Structure):
 class Stats(C.Structure):
     _fields_ = [("arena_bytes", C.c_uint64), ("n_words", C.c_uint64), ("n_unique_words", C.c_uint64),
                 ("n_long_words", C.c_uint64), ("kernel_launches", C.c_uint64),
-                ("ms_split", C.c_float), ("ms_model", C.c_float), ("ms_scan", C.c_float), ("ms_emit", C.c_float), ("ms_total", C.c_float)]
+                ("ms_split", C.c_float), ("ms_model", C.c_float), ("ms_scan", C.c_float), ("ms_emit", C.c_float), ("ms_total", C.c_float),
+                ("model_flags", C.c_uint32)]
 
 
 # every symbol include/tokzig_b200.h declares (checked by tests/test_cabi_symbols.py)
@@ -468,6 +469,11 @@ class Tokenizer:
 
     def context_handle(self):
         return self._L.tkzh_ctx(self._h)
+
+    def stats(self) -> Stats:
+        s = Stats()
+        self._L.tkz_ctx_get_stats(self.context_handle(), C.byref(s))
+        return s
 
 
 # --------------------------------------------------------------------------- multi-GPU sharding (host logic, no collective)

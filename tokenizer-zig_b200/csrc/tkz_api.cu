@@ -249,6 +249,7 @@ extern "C" const char* tkz_last_error(tkz_ctx* ctx) { return ctx ? ctx->err.c_st
 extern "C" int tkz_ctx_get_stats(tkz_ctx* ctx, tkz_stats* out) {
     if (!ctx || !out) return TKZ_ERR_INVALID_ARG;
     *out = ctx->stats; out->arena_bytes = ctx->arena_bytes;
+    out->model_flags = (ctx->has_model && ctx->dm.windowed_ok) ? 1u : 0u;
     return TKZ_OK;
 }
 

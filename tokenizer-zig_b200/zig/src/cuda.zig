@@ -82,6 +82,7 @@ pub const Stats = extern struct {
     ms_scan: f32,
     ms_emit: f32,
     ms_total: f32,
+    model_flags: u32,
 };
 
 pub extern fn tkz_ctx_create(device: c_int, stream: ?*anyopaque, arena_hint_bytes: u64, out: *?*Ctx) c_int;
