@@ -66,7 +66,7 @@ struct tkz_ctx {
     uint64_t chunk_bytes = 64ull << 20;
     // dedup pipeline arenas
     DevBuf a_table, a_uniq, a_long_start, a_long_end, a_long_ntok, a_tile_words, a_tile_nwords, a_tile_ntok, a_doc_word_ref,
-        a_doc_tok_local, a_doc_tok_start, a_doc_real, a_upool, a_tile_doc_lo, a_g_first, a_g_win, a_g_flag;
+        a_doc_tok_local, a_doc_tok_start, a_doc_real, a_upool, a_tile_doc_lo, a_g_first, a_g_win, a_g_flag, a_big;
     bool use_dedup = true;
     HostBuf h_ctrl, h_doc_tok_off, h_ids, h_off, h_attn, h_type, h_special;
     uint64_t arena_bytes = 0;
@@ -231,7 +231,7 @@ extern "C" void tkz_ctx_destroy(tkz_ctx* ctx) {
                       &ctx->outs[1].attn, &ctx->outs[1].type, &ctx->outs[1].special, &ctx->in_text[0], &ctx->in_text[1], &ctx->in_doc_off[0],
                       &ctx->in_doc_off[1], &ctx->a_ctrl, &ctx->a_table, &ctx->a_uniq, &ctx->a_long_start, &ctx->a_long_end, &ctx->a_long_ntok,
                       &ctx->a_tile_words, &ctx->a_tile_nwords, &ctx->a_tile_ntok, &ctx->a_doc_word_ref, &ctx->a_doc_tok_local,
-                      &ctx->a_doc_tok_start, &ctx->a_doc_real, &ctx->a_upool, &ctx->a_tile_doc_lo, &ctx->a_g_first, &ctx->a_g_win, &ctx->a_g_flag};
+                      &ctx->a_doc_tok_start, &ctx->a_doc_real, &ctx->a_upool, &ctx->a_tile_doc_lo, &ctx->a_g_first, &ctx->a_g_win, &ctx->a_g_flag, &ctx->a_big};
     for (DevBuf* b : bufs) release(*b);
     HostBuf* hb[] = {&ctx->h_ctrl, &ctx->h_doc_tok_off, &ctx->h_ids, &ctx->h_off, &ctx->h_attn, &ctx->h_type, &ctx->h_special,
                      &ctx->h_doc_stage[0], &ctx->h_doc_stage[1]};
@@ -461,8 +461,9 @@ int encode_dedup(tkz_ctx* ctx, const DevModel& m, const uint8_t* d_text, const u
     uint64_t want = N / 8; if (want < (1u << 16)) want = 1u << 16; if (want > (1u << 24)) want = 1u << 24;
     const uint32_t tcap = pow2_at_least(want);
     const uint32_t long_cap = (uint32_t)(N / 16 + 1024);
-    TRY(ensure(ctx, ctx->a_table, (size_t)tcap * sizeof(DedupSlot)));
-    TRY(ensure(ctx, ctx->a_uniq, (size_t)tcap * 4));
+    const uint32_t mcap = tcap >= (1u << 17) ? tcap / 8 : (1u << 14);          // medium-word slots behind the short-word slots
+    TRY(ensure(ctx, ctx->a_table, ((size_t)tcap + mcap) * sizeof(DedupSlot)));
+    TRY(ensure(ctx, ctx->a_uniq, ((size_t)tcap + mcap) * 4));
     TRY(ensure(ctx, ctx->a_long_start, (size_t)long_cap * 4));
     TRY(ensure(ctx, ctx->a_long_end, (size_t)long_cap * 4));
     TRY(ensure(ctx, ctx->a_tile_words, (size_t)n_tiles * DT_WCAP * 4));
@@ -475,10 +476,11 @@ int encode_dedup(tkz_ctx* ctx, const DevModel& m, const uint8_t* d_text, const u
     TRY(ensure(ctx, ctx->a_tile_doc_lo, ((size_t)n_tiles + 2) * 4));
     TRY(ensure(ctx, ctx->O().doc_tok_off, (n_docs + 1) * 8));
     TRY(ensure(ctx, ctx->a_scan_tmp, (scan_tmp_elems(n_tiles) + scan_tmp_elems(n_docs)) * 8));
-    CK(cudaMemsetAsync(ctx->a_table.p, 0, (size_t)tcap * sizeof(DedupSlot), st));
+    CK(cudaMemsetAsync(ctx->a_table.p, 0, ((size_t)tcap + mcap) * sizeof(DedupSlot), st));
     DedupArgs da{};
     da.text = d_text; da.n = N; da.doc_off = d_doc_off; da.n_docs = nd;
     da.table = (DedupSlot*)ctx->a_table.p; da.table_mask = tcap - 1;
+    da.med_base = tcap; da.med_mask = mcap - 1; da.n_uniq_med = (unsigned int*)(ctrl + 6) + 1;
     da.uniq_slots = (uint32_t*)ctx->a_uniq.p; da.n_uniq = (unsigned int*)(ctrl + 6);
     da.long_start = (uint32_t*)ctx->a_long_start.p; da.long_end = (uint32_t*)ctx->a_long_end.p; da.n_long = (unsigned int*)(ctrl + 7);
     da.long_cap = long_cap; da.overflow = (unsigned int*)(ctrl + 8);
@@ -491,15 +493,15 @@ int encode_dedup(tkz_ctx* ctx, const DevModel& m, const uint8_t* d_text, const u
     CK(cudaMemcpyAsync(hctrl + 24, ctrl + 13, 3 * 8, cudaMemcpyDeviceToHost, st));
     CK(cudaEventRecord(ctx->ev[1], st));
     CK(cudaStreamSynchronize(st));
-    const uint32_t n_uniq = (uint32_t)hctrl[16], n_long = (uint32_t)hctrl[17];
+    const uint32_t n_uniq = (uint32_t)hctrl[16], n_uniq_med = (uint32_t)(hctrl[16] >> 32), n_long = (uint32_t)hctrl[17];
     if (hctrl[18] != 0) return TKZ_RETRY_NO_DEDUP;
 
     // ---- P2: the model on unique words (identity byte map: keys are stored normalised) and on the long list
     DevModel mu = m; mu.lut = (const uint8_t*)ctx->t_lut_post.p;
-    TRY(ensure(ctx, ctx->a_upool, ((size_t)n_uniq * DT_MAX_SHORT + 16) * 8));
+    TRY(ensure(ctx, ctx->a_upool, ((size_t)(n_uniq - n_uniq_med) * DT_MAX_SHORT + (size_t)n_uniq_med * DT_MAX_MED + 16) * 8));
     TRY(ensure(ctx, ctx->a_long_ntok, ((size_t)n_long + 2) * 4));
     if (n_uniq) {
-        UniqueArgs ua{(DedupSlot*)ctx->a_table.p, (const uint32_t*)ctx->a_uniq.p, n_uniq, (unsigned long long*)ctx->a_upool.p,
+        UniqueArgs ua{d_text, m.lut, tcap, (DedupSlot*)ctx->a_table.p, (const uint32_t*)ctx->a_uniq.p, n_uniq, (unsigned long long*)ctx->a_upool.p,
                       (unsigned int*)(ctrl + 9), (unsigned int*)(ctrl + 1)};
         uint64_t blocks = ((uint64_t)n_uniq + UQ_WARPS - 1) / UQ_WARPS;
         const uint64_t cap = (uint64_t)ctx->sm_count * 8; if (blocks > cap) blocks = cap;
@@ -562,9 +564,13 @@ int encode_dedup(tkz_ctx* ctx, const DevModel& m, const uint8_t* d_text, const u
     if (P.outputs & TKZ_OUT_SPECIAL) TRY(ensure(ctx, ctx->O().special, T * 4));
     EmitOut eo{(uint32_t*)ctx->O().ids.p, (uint32_t*)ctx->O().off.p, (uint32_t*)ctx->O().attn.p, (uint32_t*)ctx->O().type.p,
                (uint32_t*)ctx->O().special.p};
+    const uint32_t big_cap = (uint32_t)(N / EMIT_BIG + 16);
+    TRY(ensure(ctx, ctx->a_big, (size_t)big_cap * sizeof(uint4)));
+    ta.big = BigList{(uint4*)ctx->a_big.p, (unsigned int*)(ctrl + 9) + 1, big_cap};       // upper half of ctrl[9] (zeroed by ctrl_reset)
     if (!P.has_truncation && !P.has_padding) tile_emit_kernel<true><<<n_tiles, DT_THREADS, 0, st>>>(ta, ep, eo);
     else tile_emit_kernel<false><<<n_tiles, DT_THREADS, 0, st>>>(ta, ep, eo);
     launches++;
+    if (n_long) { emit_big_kernel<<<ctx->sm_count * 4, 256, 0, st>>>(ep, eo, ta.big, ta.pool_id, ta.pool_s, ta.pool_e); launches++; }
     if (P.has_padding && nd) {
         emit_pad_real_kernel<<<(unsigned)(((uint64_t)nd * 32 + 255) / 256), 256, 0, st>>>(ep, eo, nd, (const uint32_t*)ctx->a_doc_real.p, ta.doc_tok_off); launches++;
     }
@@ -735,9 +741,14 @@ int encode_device_impl(tkz_ctx* ctx, const uint8_t* d_text, const uint64_t* d_do
     EmitOut eo{(uint32_t*)ctx->O().ids.p, (uint32_t*)ctx->O().off.p, (uint32_t*)ctx->O().attn.p, (uint32_t*)ctx->O().type.p,
                (uint32_t*)ctx->O().special.p};
     if (nw) {
+        const uint32_t big_cap = (uint32_t)(N / EMIT_BIG + 16);
+        TRY(ensure(ctx, ctx->a_big, (size_t)big_cap * sizeof(uint4)));
+        BigList bl{(uint4*)ctx->a_big.p, (unsigned int*)(ctrl + 9) + 1, big_cap};
         emit_words_kernel<<<(nw + 255) / 256, 256, 0, st>>>(ep, eo, nw, word_start, word_doc, word_tok_off, doc_word_off, doc_tok_off,
                                                             (const uint32_t*)ctx->a_pool_id.p, (const uint32_t*)ctx->a_pool_s.p,
-                                                            (const uint32_t*)ctx->a_pool_e.p); launches++;
+                                                            (const uint32_t*)ctx->a_pool_e.p, bl); launches++;
+        emit_big_kernel<<<ctx->sm_count * 4, 256, 0, st>>>(ep, eo, bl, (const uint32_t*)ctx->a_pool_id.p, (const uint32_t*)ctx->a_pool_s.p,
+                                                           (const uint32_t*)ctx->a_pool_e.p); launches++;
     }
     if (P.has_padding && nd) {
         emit_pad_kernel<<<(unsigned)(((uint64_t)nd * 32 + 255) / 256), 256, 0, st>>>(ep, eo, nd, word_tok_off, doc_word_off, doc_tok_off); launches++;

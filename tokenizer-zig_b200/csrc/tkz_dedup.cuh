@@ -30,6 +30,7 @@ constexpr int DT_WCAP = DT_TILE;                  // word entries reserved per t
 constexpr uint32_t DT_LONG = 0x80000000u;         // entry flag: index into the long list
 constexpr int DT_MAX_SHORT = 15;                  // bytes that fit the 128-bit key next to the length byte
 constexpr int DT_MAX_PROBE = 48;
+constexpr int DT_MAX_MED = 64;                    // medium words (16..64 bytes): dedup by 64-bit tag + byte verification
 
 struct __align__(16) DedupSlot {
     unsigned long long k0, k1;                    // the word: bytes 0..14, length in byte 15; all zero = empty
@@ -37,6 +38,8 @@ struct __align__(16) DedupSlot {
     unsigned long long rec0;                      // copy of the first record: single-token words need no second look-up
 };
 static_assert(sizeof(DedupSlot) == 32, "slot is one 32-byte sector");
+// Medium words share the slot array (indices >= med_base) with the same value layout; their key is a 64-bit tag (k0) and
+// the representative occurrence (k1 = text position | length << 32, published after the tag), verified byte by byte.
 
 struct K128 { unsigned long long lo, hi; };
 
@@ -57,6 +60,8 @@ struct DedupArgs {
     const uint8_t* text; uint64_t n;
     const uint64_t* doc_off; uint32_t n_docs;
     DedupSlot* table; uint32_t table_mask;
+    uint32_t med_base, med_mask;                  // medium-word slots: table[med_base + (h & med_mask)]
+    unsigned int* n_uniq_med;
     uint32_t* uniq_slots; unsigned int* n_uniq;
     uint32_t* long_start; uint32_t* long_end; unsigned int* n_long; uint32_t long_cap; unsigned int* overflow;
     uint32_t* tile_words; uint32_t* tile_nwords; uint32_t* doc_word_ref;
@@ -120,7 +125,7 @@ __device__ __forceinline__ unsigned long long bits48(const uint32_t* a, uint32_t
     return (lo | (mid << 32)) & 0xFFFFFFFFFFFFULL;
 }
 
-__global__ void __launch_bounds__(DT_THREADS) tile_split_dedup_kernel(DevModel m, DedupArgs a) {
+__global__ void __launch_bounds__(DT_THREADS, 8) tile_split_dedup_kernel(DevModel m, DedupArgs a) {
     __shared__ DedupShared sh;
     const uint32_t t = threadIdx.x;
     const uint32_t tile = blockIdx.x;
@@ -212,6 +217,43 @@ __global__ void __launch_bounds__(DT_THREADS) tile_split_dedup_kernel(DevModel m
             uint64_t q = start + DT_MAX_SHORT + 1;
             while (q < limit && sh.cls[__ldg(a.text + q)] == 0) q++;
             end_abs = (uint32_t)q;
+            const uint32_t wlen = (uint32_t)(q - start);
+            if (wlen <= DT_MAX_MED) {
+                // medium word: 64-bit tag over the normalised bytes, exactness by comparing with the representative
+                const uint8_t* __restrict__ wp = a.text + start;
+                unsigned long long h = TKZ_FNV_OFFSET ^ wlen;
+                for (uint32_t j = 0; j < wlen; j++) h = fnv1a_step(h, sh.norm[__ldg(wp + j)]);
+                h ^= h >> 29; h *= 0xD6E8FEB86659FD93ULL; h ^= h >> 32;
+                const unsigned long long tag = h | 0x8000000000000000ULL;
+                const unsigned long long meta = (unsigned long long)(uint32_t)start | ((unsigned long long)wlen << 32);
+                uint32_t slot = (uint32_t)h & a.med_mask;
+                for (int probe = 0; probe < DT_MAX_PROBE; probe++) {
+                    DedupSlot* s = a.table + a.med_base + slot;
+                    unsigned long long cur = __ldcg(&s->k0);
+                    if (cur == 0) {
+                        cur = atomicCAS(&s->k0, 0ULL, tag);
+                        if (cur == 0) {                                    // owner: publish the representative
+                            __stcg(&s->k1, meta);
+                            __threadfence();
+                            const uint32_t u = atomicAdd(a.n_uniq, 1u);
+                            a.uniq_slots[u] = a.med_base + slot;
+                            atomicAdd(a.n_uniq_med, 1u);
+                            entry = a.med_base + slot; to_long = false; break;
+                        }
+                    }
+                    if (cur == tag) {
+                        const unsigned long long rm = __ldcg(&s->k1);
+                        if (rm == 0) break;                                // representative not published yet: take the per-occurrence path
+                        if ((uint32_t)(rm >> 32) == wlen) {
+                            const uint8_t* __restrict__ rp = a.text + (uint32_t)rm;
+                            bool eq = true;
+                            for (uint32_t j = 0; j < wlen && eq; j++) eq = sh.norm[__ldg(rp + j)] == sh.norm[__ldg(wp + j)];
+                            if (eq) { entry = a.med_base + slot; to_long = false; break; }
+                        }
+                    }
+                    slot = (slot + 1) & a.med_mask;
+                }
+            }
         }
         if (to_long) {
             const uint32_t idx = atomicAdd(a.n_long, 1u);
@@ -235,6 +277,7 @@ __global__ void __launch_bounds__(DT_THREADS) tile_split_dedup_kernel(DevModel m
 
 // ------------------------------------------------------------------ P2: the model on unique words
 struct UniqueArgs {
+    const uint8_t* text; const uint8_t* lut_raw; uint32_t med_base;     // medium words are read from the text at their representative
     DedupSlot* table; const uint32_t* uniq_slots; uint32_t n_uniq;
     unsigned long long* upool; unsigned int* upool_count;      // records: id | start << 32 | end << 40
     unsigned int* work_counter;
@@ -242,7 +285,7 @@ struct UniqueArgs {
 constexpr int UQ_WARPS = 8;
 
 __global__ void __launch_bounds__(UQ_WARPS * 32) bpe_unique_kernel(DevModel m, UniqueArgs a) {
-    __shared__ uint32_t s_id[UQ_WARPS][16], s_s[UQ_WARPS][16], s_e[UQ_WARPS][16], s_rk[UQ_WARPS][16];
+    __shared__ uint32_t s_id[UQ_WARPS][DT_MAX_MED], s_s[UQ_WARPS][DT_MAX_MED], s_e[UQ_WARPS][DT_MAX_MED], s_rk[UQ_WARPS][DT_MAX_MED];
     const uint32_t lane = lane_id(), wid = threadIdx.x >> 5;
     const uint32_t FULL = 0xFFFFFFFFu;
     for (;;) {
@@ -250,27 +293,30 @@ __global__ void __launch_bounds__(UQ_WARPS * 32) bpe_unique_kernel(DevModel m, U
         if (lane == 0) u = atomicAdd(a.work_counter, 1u);
         u = __shfl_sync(FULL, u, 0);
         if (u >= a.n_uniq) break;
-        DedupSlot* s = a.table + a.uniq_slots[u];
-        const uint8_t* key = reinterpret_cast<const uint8_t*>(s);
-        const uint32_t len = (uint32_t)(s->k1 >> 56);
-        const uint32_t n = bpe_encode_word(m, key, len, s_id[wid], s_s[wid], s_e[wid], s_rk[wid]);
+        const uint32_t si = a.uniq_slots[u];
+        DedupSlot* s = a.table + si;
+        const bool med = si >= a.med_base;
+        const uint8_t* key = med ? a.text + (uint32_t)s->k1 : reinterpret_cast<const uint8_t*>(s);
+        const uint32_t len = med ? (uint32_t)(s->k1 >> 32) : (uint32_t)(s->k1 >> 56);
+        DevModel mm = m; if (med) mm.lut = a.lut_raw;
+        const uint32_t n = bpe_encode_word(mm, key, len, s_id[wid], s_s[wid], s_e[wid], s_rk[wid]);
         uint32_t off = 0;
         if (lane == 0) {
             if (n == TKZ_NONE) { s->ntok = TKZ_NONE; s->tok_off = 0; }
             else { off = atomicAdd(a.upool_count, n); s->tok_off = off; s->ntok = n; }
         }
         off = __shfl_sync(FULL, off, 0);
-        if (n != TKZ_NONE && lane < n) {
-            const unsigned long long r = (unsigned long long)s_id[wid][lane] | ((unsigned long long)s_s[wid][lane] << 32) | ((unsigned long long)s_e[wid][lane] << 40);
-            a.upool[off + lane] = r;
-            if (lane == 0) s->rec0 = r;
+        if (n != TKZ_NONE) for (uint32_t k = lane; k < n; k += 32) {
+            const unsigned long long r = (unsigned long long)s_id[wid][k] | ((unsigned long long)s_s[wid][k] << 32) | ((unsigned long long)s_e[wid][k] << 40);
+            a.upool[off + k] = r;
+            if (k == 0) s->rec0 = r;
         }
         __syncwarp();
     }
 }
 
 __global__ void __launch_bounds__(UQ_WARPS * 32) wordpiece_unique_kernel(DevModel m, UniqueArgs a) {
-    __shared__ uint32_t s_id[UQ_WARPS][16], s_s[UQ_WARPS][16], s_e[UQ_WARPS][16];
+    __shared__ uint32_t s_id[UQ_WARPS][DT_MAX_MED], s_s[UQ_WARPS][DT_MAX_MED], s_e[UQ_WARPS][DT_MAX_MED];
     const uint32_t lane = lane_id(), wid = threadIdx.x >> 5;
     const uint32_t FULL = 0xFFFFFFFFu;
     for (;;) {
@@ -278,10 +324,13 @@ __global__ void __launch_bounds__(UQ_WARPS * 32) wordpiece_unique_kernel(DevMode
         if (lane == 0) u = atomicAdd(a.work_counter, 1u);
         u = __shfl_sync(FULL, u, 0);
         if (u >= a.n_uniq) break;
-        DedupSlot* s = a.table + a.uniq_slots[u];
-        const uint8_t* key = reinterpret_cast<const uint8_t*>(s);
-        const uint32_t len = (uint32_t)(s->k1 >> 56);
-        const uint32_t n = wp_encode_word(m, key, len, s_id[wid], s_s[wid], s_e[wid]);
+        const uint32_t si = a.uniq_slots[u];
+        DedupSlot* s = a.table + si;
+        const bool med = si >= a.med_base;
+        const uint8_t* key = med ? a.text + (uint32_t)s->k1 : reinterpret_cast<const uint8_t*>(s);
+        const uint32_t len = med ? (uint32_t)(s->k1 >> 32) : (uint32_t)(s->k1 >> 56);
+        DevModel mm = m; if (med) mm.lut = a.lut_raw;
+        const uint32_t n = wp_encode_word(mm, key, len, s_id[wid], s_s[wid], s_e[wid]);
         __syncwarp();
         uint32_t off = 0;
         if (lane == 0) {
@@ -289,10 +338,10 @@ __global__ void __launch_bounds__(UQ_WARPS * 32) wordpiece_unique_kernel(DevMode
             else { off = atomicAdd(a.upool_count, n); s->tok_off = off; s->ntok = n; }
         }
         off = __shfl_sync(FULL, off, 0);
-        if (n != TKZ_NONE && lane < n) {
-            const unsigned long long r = (unsigned long long)s_id[wid][lane] | ((unsigned long long)s_s[wid][lane] << 32) | ((unsigned long long)s_e[wid][lane] << 40);
-            a.upool[off + lane] = r;
-            if (lane == 0) s->rec0 = r;
+        if (n != TKZ_NONE) for (uint32_t k = lane; k < n; k += 32) {
+            const unsigned long long r = (unsigned long long)s_id[wid][k] | ((unsigned long long)s_s[wid][k] << 32) | ((unsigned long long)s_e[wid][k] << 40);
+            a.upool[off + k] = r;
+            if (k == 0) s->rec0 = r;
         }
         __syncwarp();
     }
@@ -310,6 +359,7 @@ struct TileOutArgs {
     uint32_t* doc_tok_start;           // doc_finish out: global real-token index at the document start (n_docs + 1)
     unsigned long long* doc_tok_off;   // output CSR (n_docs + 1)
     unsigned long long* errw; uint32_t err_code;
+    BigList big;
 };
 
 __device__ __forceinline__ uint32_t entry_ntok(const TileOutArgs& a, uint32_t e) {
@@ -409,7 +459,9 @@ __global__ void __launch_bounds__(DT_THREADS) tile_emit_kernel(TileOutArgs a, Em
                 emit_real(p, o, dst + i, (uint32_t)r, (uint32_t)(r >> 32) & 0xFFu, (uint32_t)(r >> 40) & 0xFFu);
             }
         }
-        // long-list words: tokens sit in the pool at the word's byte position; copied by the whole warp
+        // long-list words: tokens sit in the pool at the word's byte position; copied by the whole warp, or queued for
+        // the grid-wide copy when very long
+        if (is_long && cnt > EMIT_BIG && big_push(a.big, tok_off, cnt, dst)) cnt = 0;
         uint32_t big = __ballot_sync(FULL, cnt && is_long);
         while (big) {
             const int l = __ffs(big) - 1; big &= big - 1;

@@ -37,6 +37,17 @@ __global__ void doc_len_kernel(EmitParams p, const uint32_t* __restrict__ word_t
 
 struct EmitOut { uint32_t* ids; uint32_t* offsets; uint32_t* attention; uint32_t* type_ids; uint32_t* special; };
 
+// words with more than EMIT_BIG tokens (whole documents, MiB-long unbroken words) are not copied by one warp: they are
+// queued here and copied by the whole grid (emit_big_kernel)
+constexpr uint32_t EMIT_BIG = 2048;
+struct BigList { uint4* items; unsigned int* count; uint32_t cap; };     // item = {src pool position, token count, dst lo, dst hi}
+__device__ __forceinline__ bool big_push(const BigList& b, uint32_t src, uint32_t cnt, unsigned long long dst) {
+    const uint32_t i = atomicAdd(b.count, 1u);
+    if (i >= b.cap) return false;
+    b.items[i] = make_uint4(src, cnt, (uint32_t)dst, (uint32_t)(dst >> 32));
+    return true;
+}
+
 __device__ __forceinline__ void emit_real(const EmitParams& p, const EmitOut& o, unsigned long long dst, uint32_t id, uint32_t s, uint32_t e) {
     o.ids[dst] = id;
     if (p.outputs & 2u) reinterpret_cast<uint2*>(o.offsets)[dst] = make_uint2(s, e);
@@ -51,7 +62,7 @@ __global__ void __launch_bounds__(256) emit_words_kernel(EmitParams p, EmitOut o
                                                          const uint32_t* __restrict__ word_tok_off, const uint32_t* __restrict__ doc_word_off,
                                                          const unsigned long long* __restrict__ doc_tok_off,
                                                          const uint32_t* __restrict__ pool_id, const uint32_t* __restrict__ pool_s,
-                                                         const uint32_t* __restrict__ pool_e) {
+                                                         const uint32_t* __restrict__ pool_e, BigList bl) {
     const uint32_t FULL = 0xFFFFFFFFu;
     const uint32_t lane = lane_id();
     const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
@@ -77,6 +88,8 @@ __global__ void __launch_bounds__(256) emit_words_kernel(EmitParams p, EmitOut o
     if (cnt > 0 && cnt <= 4) {
         for (uint32_t k = 0; k < cnt; k++) emit_real(p, o, dst + k, pool_id[src + k], pool_s[src + k], pool_e[src + k]);
     }
+    // very long words: queued for the grid-wide copy
+    if (cnt > EMIT_BIG && big_push(bl, src, cnt, dst)) cnt = 0;
     // long words: warp-cooperative copy
     uint32_t big = __ballot_sync(FULL, cnt > 4);
     while (big) {
@@ -84,6 +97,18 @@ __global__ void __launch_bounds__(256) emit_words_kernel(EmitParams p, EmitOut o
         const uint32_t c = __shfl_sync(FULL, cnt, l), s = __shfl_sync(FULL, src, l);
         const unsigned long long dd = __shfl_sync(FULL, dst, l);
         for (uint32_t k = lane; k < c; k += 32) emit_real(p, o, dd + k, pool_id[s + k], pool_s[s + k], pool_e[s + k]);
+    }
+}
+
+// grid-wide copy of the queued big words: every block takes a strided share of every item
+__global__ void __launch_bounds__(256) emit_big_kernel(EmitParams p, EmitOut o, BigList bl, const uint32_t* __restrict__ pool_id,
+                                                       const uint32_t* __restrict__ pool_s, const uint32_t* __restrict__ pool_e) {
+    uint32_t n = *bl.count; if (n > bl.cap) n = bl.cap;
+    for (uint32_t k = 0; k < n; k++) {
+        const uint4 it = bl.items[k];
+        const unsigned long long dst = (unsigned long long)it.z | ((unsigned long long)it.w << 32);
+        for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < it.y; i += gridDim.x * blockDim.x)
+            emit_real(p, o, dst + i, pool_id[it.x + i], pool_s[it.x + i], pool_e[it.x + i]);
     }
 }
 
