@@ -453,3 +453,39 @@ def test_chunked_host_path_matches_single_shot(monkeypatch, chunk):
         t.encode_batch(docs)
     assert e.value.code == tz.ERR_INVALID_UTF8 and e.value.doc == 3000
     t.close()
+
+
+# ----------------------------------------------------------------------------- fused count+emit (second and later calls of a context)
+def test_fused_emit_path_and_its_overflow_fallback():
+    """The first plain encode of a context takes the counted path and records the token density; later plain encodes take
+    the single-pass fused emit (decoupled look-back) with an estimated output size; a batch that is much denser than any
+    before overflows the estimate and is re-run by the counted path.  Every variant must equal the oracle."""
+    v = {"a": 0, "b": 1, "c": 2, "d": 3, "ab": 4, "abc": 5, "abcd": 6}
+    js = json.dumps({"model": {"type": "BPE", "vocab": v, "merges": ["a b", "ab c", "abc d"]}, "pre_tokenizer": {"type": "Whitespace"}})
+    t, o = pair(js)
+    rng = random.Random(9)
+    sparse = [" ".join(rng.choice(["abcd", "abcd", "abc", "ab"]) for _ in range(rng.randint(0, 60))).encode() for _ in range(3000)]
+    dense = [" ".join("".join(rng.choice("dcba") for _ in range(rng.randint(1, 20))) for _ in range(rng.randint(0, 60))).encode() for _ in range(3000)]
+    mixed = [rng.choice(sparse + dense) for _ in range(4000)] + [b"", b" ", b"d" * 5000, b"abcd" * 3000]
+    for name, docs in (("counted", sparse), ("fused", sparse[::-1]), ("fused-again", sparse[100:2000]), ("overflow", dense), ("fused-dense", mixed),
+                       ("empty", []), ("blank", [b"", b"  "])):
+        assert_same(t.encode_batch(docs), o.encode_batch(docs), name)
+    # errors on the fused path carry the document index too
+    with pytest.raises(tz.TokzigError) as e:
+        t.encode_batch(sparse[:500] + [b"ab \xff ab"] + sparse[:10])
+    assert e.value.code == tz.ERR_INVALID_UTF8 and e.value.doc == 500
+    assert_same(t.encode_batch(sparse), o.encode_batch(sparse), "after error")
+    t.close()
+
+
+def test_fused_emit_switch(monkeypatch):
+    js = tokenizers_io.tokenizer_json("gpt2_whitespace")
+    text, off = corpus.generate("c5", 4 << 20, seed=8)            # includes long unbroken words (long list + big-word copy)
+    o = orc.OracleTokenizer.from_json(js)
+    ref = o.encode_packed(text, off, algo=1, threads=8)
+    for flag in ("0", "1"):
+        monkeypatch.setenv("TKZ_NO_FUSED_EMIT", flag)
+        t = tz.Tokenizer.from_json(js, device=0)
+        for rep in range(3):
+            assert_same(t.encode_packed(text, off), ref, f"TKZ_NO_FUSED_EMIT={flag} call {rep}")
+        t.close()

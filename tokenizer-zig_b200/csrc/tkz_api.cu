@@ -66,8 +66,9 @@ struct tkz_ctx {
     uint64_t chunk_bytes = 64ull << 20;
     // dedup pipeline arenas
     DevBuf a_table, a_uniq, a_long_start, a_long_end, a_long_ntok, a_tile_words, a_tile_nwords, a_tile_ntok, a_doc_word_ref,
-        a_doc_tok_local, a_doc_tok_start, a_doc_real, a_upool, a_tile_doc_lo, a_g_first, a_g_win, a_g_flag, a_big;
-    bool use_dedup = true;
+        a_doc_tok_local, a_doc_tok_start, a_doc_real, a_upool, a_tile_doc_lo, a_g_first, a_g_win, a_g_flag, a_big, a_tile_state;
+    double tok_per_byte_hist = 0.0;       // highest tokens/byte seen by this context: sizes the fused emit's output estimate
+    bool use_dedup = true, use_fused = true;
     HostBuf h_ctrl, h_doc_tok_off, h_ids, h_off, h_attn, h_type, h_special;
     uint64_t arena_bytes = 0;
     tkz_stats stats{};
@@ -210,6 +211,7 @@ extern "C" int tkz_ctx_create(int device, void* stream, uint64_t arena_hint_byte
     }
     (void)arena_hint_bytes;
     if (const char* e = getenv("TKZ_NO_DEDUP")) ctx->use_dedup = !(e[0] == '1');     // A/B switch for the parity tests
+    if (const char* e = getenv("TKZ_NO_FUSED_EMIT")) ctx->use_fused = !(e[0] == '1');
     if (const char* e = getenv("TKZ_CHUNK_BYTES")) { const long long v = atoll(e); if (v > 0) ctx->chunk_bytes = (uint64_t)v; }
     cudaStreamCreateWithFlags(&ctx->s_h2d, cudaStreamNonBlocking);
     cudaStreamCreateWithFlags(&ctx->s_d2h, cudaStreamNonBlocking);
@@ -231,7 +233,7 @@ extern "C" void tkz_ctx_destroy(tkz_ctx* ctx) {
                       &ctx->outs[1].attn, &ctx->outs[1].type, &ctx->outs[1].special, &ctx->in_text[0], &ctx->in_text[1], &ctx->in_doc_off[0],
                       &ctx->in_doc_off[1], &ctx->a_ctrl, &ctx->a_table, &ctx->a_uniq, &ctx->a_long_start, &ctx->a_long_end, &ctx->a_long_ntok,
                       &ctx->a_tile_words, &ctx->a_tile_nwords, &ctx->a_tile_ntok, &ctx->a_doc_word_ref, &ctx->a_doc_tok_local,
-                      &ctx->a_doc_tok_start, &ctx->a_doc_real, &ctx->a_upool, &ctx->a_tile_doc_lo, &ctx->a_g_first, &ctx->a_g_win, &ctx->a_g_flag, &ctx->a_big};
+                      &ctx->a_doc_tok_start, &ctx->a_doc_real, &ctx->a_upool, &ctx->a_tile_doc_lo, &ctx->a_g_first, &ctx->a_g_win, &ctx->a_g_flag, &ctx->a_big, &ctx->a_tile_state};
     for (DevBuf* b : bufs) release(*b);
     HostBuf* hb[] = {&ctx->h_ctrl, &ctx->h_doc_tok_off, &ctx->h_ids, &ctx->h_off, &ctx->h_attn, &ctx->h_type, &ctx->h_special,
                      &ctx->h_doc_stage[0], &ctx->h_doc_stage[1]};
@@ -536,6 +538,72 @@ int encode_dedup(tkz_ctx* ctx, const DevModel& m, const uint8_t* d_text, const u
     ta.tile_ntok = (uint32_t*)ctx->a_tile_ntok.p; ta.doc_tok_local = (uint32_t*)ctx->a_doc_tok_local.p;
     ta.doc_tok_start = (uint32_t*)ctx->a_doc_tok_start.p; ta.doc_tok_off = (unsigned long long*)ctx->O().doc_tok_off.p;
     ta.errw = ctrl; ta.err_code = m.kind == TKZ_MODEL_BPE ? TKZ_ECODE_UTF8 : TKZ_ECODE_UNK;
+    // ---- fused P3 (plain concatenation) when this context already knows the token density of its workload
+    const bool plain = !P.has_truncation && !P.has_padding;
+    if (plain && ctx->use_fused && ctx->tok_per_byte_hist > 0.0) {
+        uint64_t est = (uint64_t)((double)N * ctx->tok_per_byte_hist * 1.25) + 65536;
+        if (est > N + 16) est = N + 16;                                  // tokens <= bytes
+        TRY(ensure(ctx, ctx->O().ids, est * 4));
+        if (P.outputs & TKZ_OUT_OFFSETS) TRY(ensure(ctx, ctx->O().off, est * 8));
+        if (P.outputs & TKZ_OUT_ATTENTION) TRY(ensure(ctx, ctx->O().attn, est * 4));
+        if (P.outputs & TKZ_OUT_TYPE_IDS) TRY(ensure(ctx, ctx->O().type, est * 4));
+        if (P.outputs & TKZ_OUT_SPECIAL) TRY(ensure(ctx, ctx->O().special, est * 4));
+        uint64_t cap = ctx->O().ids.cap / 4;
+        if (P.outputs & TKZ_OUT_OFFSETS) cap = std::min<uint64_t>(cap, ctx->O().off.cap / 8);
+        if (P.outputs & TKZ_OUT_ATTENTION) cap = std::min<uint64_t>(cap, ctx->O().attn.cap / 4);
+        if (P.outputs & TKZ_OUT_TYPE_IDS) cap = std::min<uint64_t>(cap, ctx->O().type.cap / 4);
+        if (P.outputs & TKZ_OUT_SPECIAL) cap = std::min<uint64_t>(cap, ctx->O().special.cap / 4);
+        TRY(ensure(ctx, ctx->a_tile_state, (size_t)n_tiles * 8));
+        CK(cudaMemsetAsync(ctx->a_tile_state.p, 0, (size_t)n_tiles * 8, st));
+        const uint32_t big_cap = (uint32_t)(N / EMIT_BIG + 16);
+        TRY(ensure(ctx, ctx->a_big, (size_t)big_cap * sizeof(uint4)));
+        ta.big = BigList{(uint4*)ctx->a_big.p, (unsigned int*)(ctrl + 9) + 1, big_cap};
+        EmitOut eo{(uint32_t*)ctx->O().ids.p, (uint32_t*)ctx->O().off.p, (uint32_t*)ctx->O().attn.p, (uint32_t*)ctx->O().type.p,
+                   (uint32_t*)ctx->O().special.p};
+        FusedArgs fa{(unsigned long long*)ctx->a_tile_state.p, (unsigned int*)(ctrl + 11) + 1, cap, (unsigned int*)(ctrl + 12) + 1};
+        CK(cudaEventRecord(ctx->ev[3], st));
+        tile_emit_fused_kernel<<<n_tiles, DT_THREADS, 0, st>>>(ta, ep, eo, fa); launches++;
+        if (n_long) { emit_big_kernel<<<ctx->sm_count * 4, 256, 0, st>>>(ep, eo, ta.big, ta.pool_id, ta.pool_s, ta.pool_e); launches++; }
+        tile_words_total_kernel<<<64, 256, 0, st>>>(da.tile_nwords, n_tiles, ctrl); launches++;
+        CK(cudaMemcpyAsync(hctrl, ctrl, 13 * 8, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(hctrl + 32, (unsigned long long*)ctx->a_tile_state.p + (n_tiles - 1), 8, cudaMemcpyDeviceToHost, st));
+        CK(cudaEventRecord(ctx->ev[4], st));
+        CK(cudaStreamSynchronize(st));
+        const bool overflow = (hctrl[12] >> 32) != 0;
+        const unsigned long long errw = hctrl[0];
+        if (!overflow) {
+            const uint64_t T = hctrl[32] & LB_VAL;
+            ctx->stats.n_words = hctrl[10]; ctx->stats.n_unique_words = n_uniq; ctx->stats.n_long_words = n_long;
+            ctx->stats.kernel_launches = launches;
+            if (errw != TKZ_ERRW_NONE) {
+                // document of the first failing word (text order): last document whose first-word reference is <= it
+                std::vector<uint32_t> ref(n_docs + 1);
+                CK(cudaMemcpy(ref.data(), da.doc_word_ref, (n_docs + 1) * 4, cudaMemcpyDeviceToHost));
+                const uint32_t v = (uint32_t)(errw >> 8);
+                const size_t dd = std::upper_bound(ref.begin(), ref.begin() + n_docs, v) - ref.begin();
+                out->err_doc = dd ? (int64_t)dd - 1 : 0;
+                const uint32_t code = (uint32_t)(errw & 0xFF);
+                ctx->err = code == TKZ_ECODE_UTF8 ? "invalid UTF-8 in a BPE pre-token (reference behaviour undefined)" : "MissingUnkToken";
+                return code == TKZ_ECODE_UTF8 ? TKZ_ERR_INVALID_UTF8 : TKZ_ERR_MISSING_UNK;
+            }
+            if (N) ctx->tok_per_byte_hist = std::max(ctx->tok_per_byte_hist, (double)T / (double)N);
+            cudaEventElapsedTime(&ctx->stats.ms_split, ctx->ev[0], ctx->ev[1]);
+            cudaEventElapsedTime(&ctx->stats.ms_model, ctx->ev[1], ctx->ev[2]);
+            ctx->stats.ms_scan = 0.f;
+            cudaEventElapsedTime(&ctx->stats.ms_emit, ctx->ev[3], ctx->ev[4]);
+            cudaEventElapsedTime(&ctx->stats.ms_total, ctx->ev[0], ctx->ev[4]);
+            out->n_docs = n_docs; out->n_tokens = T; out->n_real_tokens = T;
+            out->doc_tok_off = (const uint64_t*)ta.doc_tok_off;
+            out->ids = eo.ids;
+            out->offsets = (P.outputs & TKZ_OUT_OFFSETS) ? eo.offsets : nullptr;
+            out->attention_mask = (P.outputs & TKZ_OUT_ATTENTION) ? eo.attention : nullptr;
+            out->type_ids = (P.outputs & TKZ_OUT_TYPE_IDS) ? eo.type_ids : nullptr;
+            out->special_tokens_mask = (P.outputs & TKZ_OUT_SPECIAL) ? eo.special : nullptr;
+            return TKZ_OK;
+        }
+        // the estimate was too small: counted path below (it re-reads everything, results are unaffected)
+        CK(cudaMemsetAsync(ctrl + 9, 0, 16, st));          // big-list counter (upper half of ctrl[9]) and the word total restart
+    }
     tile_count_kernel<<<n_tiles, DT_THREADS, 0, st>>>(ta); launches++;
     tile_words_total_kernel<<<64, 256, 0, st>>>(da.tile_nwords, n_tiles, ctrl); launches++;
     launches += exclusive_scan<uint32_t>(ta.tile_ntok, n_tiles, ta.tile_ntok, (unsigned long long*)ctx->a_scan_tmp.p, st);
@@ -583,6 +651,7 @@ int encode_dedup(tkz_ctx* ctx, const DevModel& m, const uint8_t* d_text, const u
     cudaEventElapsedTime(&ctx->stats.ms_scan, ctx->ev[2], ctx->ev[3]);
     cudaEventElapsedTime(&ctx->stats.ms_emit, ctx->ev[3], ctx->ev[4]);
     cudaEventElapsedTime(&ctx->stats.ms_total, ctx->ev[0], ctx->ev[4]);
+    if (N && !P.has_truncation && !P.has_padding) ctx->tok_per_byte_hist = std::max(ctx->tok_per_byte_hist, (double)T_real / (double)N);
     out->n_docs = n_docs; out->n_tokens = T; out->n_real_tokens = T_real;
     out->doc_tok_off = (const uint64_t*)ta.doc_tok_off;
     out->ids = eo.ids;
