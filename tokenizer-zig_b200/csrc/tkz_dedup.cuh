@@ -521,25 +521,33 @@ __global__ void __launch_bounds__(DT_THREADS) tile_emit_fused_kernel(TileOutArgs
     }
     uint32_t tile_total;
     block_excl_scan32<DT_THREADS / 32>(mysum, scan, 0, &tile_total);
-    // ---- look-back
-    if (t == 0) {
-        unsigned long long base = 0;
+    // ---- look-back by warp 0: 32 predecessors per round (status words are self-contained: flag + value in one u64)
+    if (t < 32) {
         volatile unsigned long long* st = f.tile_state;
-        if (tile == 0) st[0] = LB_INC | tile_total;
+        unsigned long long base = 0;
+        if (tile == 0) { if (lane == 0) st[0] = LB_INC | tile_total; }
         else {
-            st[tile] = LB_AGG | tile_total;
-            uint32_t j = tile - 1;
+            if (lane == 0) st[tile] = LB_AGG | tile_total;
+            int hi = (int)tile - 1;                                       // closest predecessor not yet accounted for
             for (;;) {
-                const unsigned long long v = st[j];
-                if ((v >> 62) == 0) continue;
-                base += v & LB_VAL;
-                if ((v >> 62) == 2) break;
-                j--;
+                const int j = hi - (int)lane;
+                unsigned long long v = LB_INC;                            // before tile 0: inclusive prefix 0
+                if (j >= 0) { do { v = st[j]; } while ((v >> 62) == 0); }
+                const uint32_t inc_mask = __ballot_sync(FULL, (v >> 62) == 2);
+                // lanes up to (and including) the closest inclusive prefix contribute
+                const int first_inc = inc_mask ? __ffs(inc_mask) - 1 : 32;
+                unsigned long long c = ((int)lane <= first_inc) ? (v & LB_VAL) : 0ULL;
+                for (int d = 16; d > 0; d >>= 1) c += __shfl_xor_sync(FULL, c, d);
+                base += c;
+                if (inc_mask) break;
+                hi -= 32;
             }
-            st[tile] = LB_INC | (base + tile_total);
+            if (lane == 0) st[tile] = LB_INC | (base + tile_total);
         }
-        s_base = base;
-        if (base + tile_total > f.cap) atomicExch(f.overflow, 1u);
+        if (lane == 0) {
+            s_base = base;
+            if (base + tile_total > f.cap) atomicExch(f.overflow, 1u);
+        }
     }
     __syncthreads();
     const unsigned long long base = s_base;
