@@ -456,12 +456,13 @@ def test_chunked_host_path_matches_single_shot(monkeypatch, chunk):
 
 
 # ----------------------------------------------------------------------------- fused count+emit (second and later calls of a context)
-def test_fused_emit_path_and_its_overflow_fallback():
-    """The first plain encode of a context takes the counted path and records the token density; later plain encodes take
+def test_fused_emit_path_and_its_overflow_fallback(monkeypatch):
+    """(opt-in with TKZ_FUSED_EMIT=1: measured slower than count + emit, kept as an experiment)  The first plain encode of a context takes the counted path and records the token density; later plain encodes take
     the single-pass fused emit (decoupled look-back) with an estimated output size; a batch that is much denser than any
     before overflows the estimate and is re-run by the counted path.  Every variant must equal the oracle."""
     v = {"a": 0, "b": 1, "c": 2, "d": 3, "ab": 4, "abc": 5, "abcd": 6}
     js = json.dumps({"model": {"type": "BPE", "vocab": v, "merges": ["a b", "ab c", "abc d"]}, "pre_tokenizer": {"type": "Whitespace"}})
+    monkeypatch.setenv("TKZ_FUSED_EMIT", "1")
     t, o = pair(js)
     rng = random.Random(9)
     sparse = [" ".join(rng.choice(["abcd", "abcd", "abc", "ab"]) for _ in range(rng.randint(0, 60))).encode() for _ in range(3000)]
@@ -484,8 +485,8 @@ def test_fused_emit_switch(monkeypatch):
     o = orc.OracleTokenizer.from_json(js)
     ref = o.encode_packed(text, off, algo=1, threads=8)
     for flag in ("0", "1"):
-        monkeypatch.setenv("TKZ_NO_FUSED_EMIT", flag)
+        monkeypatch.setenv("TKZ_FUSED_EMIT", flag)
         t = tz.Tokenizer.from_json(js, device=0)
         for rep in range(3):
-            assert_same(t.encode_packed(text, off), ref, f"TKZ_NO_FUSED_EMIT={flag} call {rep}")
+            assert_same(t.encode_packed(text, off), ref, f"TKZ_FUSED_EMIT={flag} call {rep}")
         t.close()

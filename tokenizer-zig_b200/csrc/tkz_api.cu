@@ -68,7 +68,7 @@ struct tkz_ctx {
     DevBuf a_table, a_uniq, a_long_start, a_long_end, a_long_ntok, a_tile_words, a_tile_nwords, a_tile_ntok, a_doc_word_ref,
         a_doc_tok_local, a_doc_tok_start, a_doc_real, a_upool, a_tile_doc_lo, a_g_first, a_g_win, a_g_flag, a_big, a_tile_state;
     double tok_per_byte_hist = 0.0;       // highest tokens/byte seen by this context: sizes the fused emit's output estimate
-    bool use_dedup = true, use_fused = true;
+    bool use_dedup = true, use_fused = false;    // fused emit measured slower than count + emit on B200: opt-in
     HostBuf h_ctrl, h_doc_tok_off, h_ids, h_off, h_attn, h_type, h_special;
     uint64_t arena_bytes = 0;
     tkz_stats stats{};
@@ -211,7 +211,7 @@ extern "C" int tkz_ctx_create(int device, void* stream, uint64_t arena_hint_byte
     }
     (void)arena_hint_bytes;
     if (const char* e = getenv("TKZ_NO_DEDUP")) ctx->use_dedup = !(e[0] == '1');     // A/B switch for the parity tests
-    if (const char* e = getenv("TKZ_NO_FUSED_EMIT")) ctx->use_fused = !(e[0] == '1');
+    if (const char* e = getenv("TKZ_FUSED_EMIT")) ctx->use_fused = (e[0] == '1');
     if (const char* e = getenv("TKZ_CHUNK_BYTES")) { const long long v = atoll(e); if (v > 0) ctx->chunk_bytes = (uint64_t)v; }
     cudaStreamCreateWithFlags(&ctx->s_h2d, cudaStreamNonBlocking);
     cudaStreamCreateWithFlags(&ctx->s_d2h, cudaStreamNonBlocking);

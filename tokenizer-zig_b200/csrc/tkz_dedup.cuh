@@ -486,9 +486,9 @@ struct FusedArgs {
     unsigned int* overflow;
 };
 constexpr unsigned long long LB_AGG = 1ULL << 62, LB_INC = 2ULL << 62, LB_VAL = (1ULL << 62) - 1;
-constexpr int FUSED_REG_ITERS = 4;
+constexpr int FUSED_REG_ITERS = 2;
 
-__global__ void __launch_bounds__(DT_THREADS) tile_emit_fused_kernel(TileOutArgs a, EmitParams p, EmitOut o, FusedArgs f) {
+__global__ void __launch_bounds__(DT_THREADS, 8) tile_emit_fused_kernel(TileOutArgs a, EmitParams p, EmitOut o, FusedArgs f) {
     __shared__ uint32_t scan[2 * (DT_THREADS / 32 + 1)];
     __shared__ uint32_t pfx[DT_THREADS];
     __shared__ uint32_t s_tile;
