@@ -68,6 +68,7 @@ struct tkz_ctx {
     DevBuf a_table, a_uniq, a_long_start, a_long_end, a_long_ntok, a_tile_words, a_tile_nwords, a_tile_ntok, a_doc_word_ref,
         a_doc_tok_local, a_doc_tok_start, a_doc_real, a_upool, a_tile_doc_lo, a_g_first, a_g_win, a_g_flag, a_big, a_tile_state;
     double tok_per_byte_hist = 0.0;       // highest tokens/byte seen by this context: sizes the fused emit's output estimate
+    bool has_iso = false;                 // the class table isolates some byte (punctuation split)
     bool use_dedup = true, use_fused = false;    // fused emit measured slower than count + emit on B200: opt-in
     HostBuf h_ctrl, h_doc_tok_off, h_ids, h_off, h_attn, h_type, h_special;
     uint64_t arena_bytes = 0;
@@ -217,6 +218,11 @@ extern "C" int tkz_ctx_create(int device, void* stream, uint64_t arena_hint_byte
     cudaStreamCreateWithFlags(&ctx->s_d2h, cudaStreamNonBlocking);
     for (int i = 0; i < 2; i++) { cudaEventCreateWithFlags(&ctx->ev_h2d[i], cudaEventDisableTiming); cudaEventCreateWithFlags(&ctx->ev_d2h[i], cudaEventDisableTiming); }
     for (auto& ev : ctx->ev) cudaEventCreate(&ev);
+    {
+        unsigned long long pw[DT_MAX_MED]; pw[0] = 1;
+        for (int i = 1; i < DT_MAX_MED; i++) pw[i] = pw[i - 1] * TKZ_MED_HASH_MUL;
+        cudaMemcpyToSymbol(c_med_pw, pw, sizeof pw);
+    }
     *out = ctx;
     return TKZ_OK;
 }
@@ -282,6 +288,8 @@ extern "C" int tkz_model_upload(tkz_ctx* ctx, const tkz_model_desc* d) {
         lut_post[256 + b] = d->class_lut ? d->class_lut[b] : (uint8_t)TKZ_CLS_WORD;
     }
     m.norm_identity = identity; m.norm_has_drop = has_drop;
+    ctx->has_iso = false;
+    for (int b = 0; b < 256; b++) if (lut[256 + b] == TKZ_CLS_ISOLATE || lut_post[256 + b] == TKZ_CLS_ISOLATE) ctx->has_iso = true;
     TRY(upload(ctx, ctx->t_lut, lut.data(), lut.size()));
     TRY(upload(ctx, ctx->t_lut_post, lut_post.data(), lut_post.size()));
     m.lut = (const uint8_t*)ctx->t_lut.p;
@@ -489,7 +497,14 @@ int encode_dedup(tkz_ctx* ctx, const DevModel& m, const uint8_t* d_text, const u
     da.tile_words = (uint32_t*)ctx->a_tile_words.p; da.tile_nwords = (uint32_t*)ctx->a_tile_nwords.p; da.doc_word_ref = (uint32_t*)ctx->a_doc_word_ref.p;
     da.tile_doc_lo = (const uint32_t*)ctx->a_tile_doc_lo.p;
     tile_doc_index_kernel<<<(n_tiles + 1 + 255) / 256, 256, 0, st>>>(d_doc_off, nd, n_tiles, (uint32_t*)ctx->a_tile_doc_lo.p); launches++;
-    tile_split_dedup_kernel<<<n_tiles, DT_THREADS, 0, st>>>(m, da); launches++;
+    {
+        const bool nid = m.norm_identity != 0, iso = ctx->has_iso;
+        if (nid && !iso) tile_split_dedup_kernel<true, false><<<n_tiles, DT_THREADS, 0, st>>>(m, da);
+        else if (nid) tile_split_dedup_kernel<true, true><<<n_tiles, DT_THREADS, 0, st>>>(m, da);
+        else if (!iso) tile_split_dedup_kernel<false, false><<<n_tiles, DT_THREADS, 0, st>>>(m, da);
+        else tile_split_dedup_kernel<false, true><<<n_tiles, DT_THREADS, 0, st>>>(m, da);
+        launches++;
+    }
     if (m.kind == TKZ_MODEL_BPE) { len_class_count_kernel<<<128, 256, 0, st>>>(da.long_start, da.long_end, 0, da.n_long, ctrl + 13); launches++; }
     CK(cudaMemcpyAsync(hctrl + 16, ctrl + 6, 3 * 8, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(hctrl + 24, ctrl + 13, 3 * 8, cudaMemcpyDeviceToHost, st));

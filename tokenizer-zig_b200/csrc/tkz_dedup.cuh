@@ -76,18 +76,23 @@ __global__ void tile_doc_index_kernel(const uint64_t* __restrict__ doc_off, uint
     else if (tile == n_tiles) tile_doc_lo[tile] = n_docs + 1;
 }
 
+// powers of the medium-word hash multiplier (host-initialised, see tkz_api.cu): PW[j] = HASH_MUL^j mod 2^64
+__constant__ unsigned long long c_med_pw[DT_MAX_MED];
+#define TKZ_MED_HASH_MUL 0x9E3779B97F4A7C15ULL
+
 struct DedupShared {
-    uint8_t norm[256];
-    uint8_t cls[256];
+    uint32_t lut[256];                                 // [7:0] normalised byte, bit 8 WORD, bit 9 ISOLATE
     uint32_t text32[(DT_TILE + 2 * DT_SEG) / 4 + 4];   // normalised tile bytes + 2 halo segments
     uint32_t seg[DT_THREADS + 2];                      // per segment: word mask | iso mask << 16 (2 halo segments)
     uint32_t docbits[(DT_TILE + 2 * DT_SEG) / 32 + 2]; // bit p: a document starts at tile_base + p
     uint32_t seg_smask[DT_THREADS];
-    uint32_t seg_sprefix[DT_THREADS];
-    uint32_t scan[2 * (DT_THREADS / 32 + 1)];
+    uint32_t seg_sprefix[DT_THREADS];                  // exclusive count of word starts before the segment, within its WARP
+    uint16_t wlist[DT_THREADS / 32][DT_SEG * 32];      // per warp: tile-local start positions of its words, in order
+    uint32_t wtot[DT_THREADS / 32];
 };
 
 // classify + normalise one 16-byte segment; bytes at or beyond n read as DELIM
+template <bool NORM_ID, bool HAS_ISO>
 __device__ __forceinline__ void dt_load_segment(const uint8_t* __restrict__ text, uint64_t n, uint64_t seg_base, uint32_t seg, DedupShared& sh) {
     uint32_t raw[4] = {0, 0, 0, 0};
     uint32_t valid = 0;                                // bit k: position seg_base + k < n
@@ -103,18 +108,16 @@ __device__ __forceinline__ void dt_load_segment(const uint8_t* __restrict__ text
         uint32_t o = 0;
 #pragma unroll
         for (int j = 0; j < 4; j++) {
-            const uint32_t b = (raw[q] >> (8 * j)) & 0xFF;
-            const uint32_t c = sh.cls[b];
-            word |= (uint32_t)(c == 0) << (q * 4 + j);
-            iso |= (uint32_t)(c == 2) << (q * 4 + j);
-            o |= (uint32_t)sh.norm[b] << (8 * j);
+            const uint32_t e = sh.lut[(raw[q] >> (8 * j)) & 0xFF];
+            word |= ((e >> 8) & 1u) << (q * 4 + j);
+            if (HAS_ISO) iso |= ((e >> 9) & 1u) << (q * 4 + j);
+            if (!NORM_ID) o |= (e & 0xFFu) << (8 * j);
         }
-        nrm[q] = o;
+        nrm[q] = NORM_ID ? raw[q] : o;
     }
     word &= valid; iso &= valid;
     sh.seg[seg] = word | (iso << 16);
-    uint32_t* dst = sh.text32 + seg * 4;
-    dst[0] = nrm[0]; dst[1] = nrm[1]; dst[2] = nrm[2]; dst[3] = nrm[3];
+    *reinterpret_cast<uint4*>(sh.text32 + seg * 4) = make_uint4(nrm[0], nrm[1], nrm[2], nrm[3]);
 }
 
 // 48 consecutive bits of a bit array starting at bit `b0` (b0 multiple of 16)
@@ -125,14 +128,22 @@ __device__ __forceinline__ unsigned long long bits48(const uint32_t* a, uint32_t
     return (lo | (mid << 32)) & 0xFFFFFFFFFFFFULL;
 }
 
-__global__ void __launch_bounds__(DT_THREADS, 8) tile_split_dedup_kernel(DevModel m, DedupArgs a) {
-    __shared__ DedupShared sh;
-    const uint32_t t = threadIdx.x;
+// P1.  Phase 1: one 16-byte segment per thread (classify, normalise into shared memory).  Phase 2: start masks, warp
+// scan, every warp lists the start positions of the words of its 512-byte slice.  Phase 3: the warp walks its list 32
+// words at a time -- one word per lane, so the key build + table probe run with full lane utilisation; words longer than
+// 15 bytes are finished by the whole warp (end search, parallel hash, byte verification).
+template <bool NORM_ID, bool HAS_ISO>
+__global__ void __launch_bounds__(DT_THREADS, 6) tile_split_dedup_kernel(DevModel m, DedupArgs a) {
+    __shared__ __align__(16) DedupShared sh;
+    const uint32_t FULL = 0xFFFFFFFFu;
+    const uint32_t t = threadIdx.x, lane = t & 31, wid = t >> 5;
     const uint32_t tile = blockIdx.x;
     const uint64_t tile_base = (uint64_t)tile * DT_TILE;
-    // ---- prologue: LUTs, document-start bits for [tile_base, tile_base + TILE + 32]
-    sh.norm[t] = m.lut[t];
-    sh.cls[t] = m.lut[256 + t];
+    // ---- prologue: LUT, document-start bits for [tile_base, tile_base + TILE + 32]
+    {
+        const uint32_t c = m.lut[256 + t];
+        sh.lut[t] = (uint32_t)m.lut[t] | ((c == 0) ? 0x100u : 0u) | ((c == 2) ? 0x200u : 0u);
+    }
     if (t < (DT_TILE + 2 * DT_SEG) / 32 + 2) sh.docbits[t] = 0;
     const uint32_t d_lo = __ldg(a.tile_doc_lo + tile);
     __syncthreads();
@@ -142,136 +153,178 @@ __global__ void __launch_bounds__(DT_THREADS, 8) tile_split_dedup_kernel(DevMode
         const uint32_t p = (uint32_t)(off - tile_base);
         atomicOr(&sh.docbits[p >> 5], 1u << (p & 31));
     }
-    dt_load_segment(a.text, a.n, tile_base + (uint64_t)t * DT_SEG, t, sh);
-    if (t < 2) dt_load_segment(a.text, a.n, tile_base + DT_TILE + (uint64_t)t * DT_SEG, DT_THREADS + t, sh);
+    dt_load_segment<NORM_ID, HAS_ISO>(a.text, a.n, tile_base + (uint64_t)t * DT_SEG, t, sh);
+    if (t < 2) dt_load_segment<NORM_ID, HAS_ISO>(a.text, a.n, tile_base + DT_TILE + (uint64_t)t * DT_SEG, DT_THREADS + t, sh);
     __syncthreads();
 
-    // ---- start bits of this segment
+    // ---- phase 2: start bits of this segment, per-warp word list
     const uint32_t sw = sh.seg[t];
     const uint32_t word = sw & 0xFFFFu, iso = sw >> 16;
     uint32_t prev_word;
     if (t > 0) prev_word = (sh.seg[t - 1] >> 15) & 1u;
-    else prev_word = (tile_base > 0 && tile_base - 1 < a.n) ? (uint32_t)(sh.cls[__ldg(a.text + tile_base - 1)] == 0) : 0u;
-    const unsigned long long d48 = bits48(sh.docbits, t * DT_SEG);
-    const uint32_t ds = (uint32_t)d48 & 0xFFFFu;
+    else prev_word = (tile_base > 0 && tile_base - 1 < a.n) ? ((sh.lut[__ldg(a.text + tile_base - 1)] >> 8) & 1u) : 0u;
+    const uint32_t ds = (uint32_t)bits48(sh.docbits, t * DT_SEG) & 0xFFFFu;
     const uint32_t word_prev = ((word << 1) | prev_word) & 0xFFFFu;
-    uint32_t smask = (iso | (word & (~word_prev | ds))) & 0xFFFFu;
-    uint32_t total;
-    const uint32_t ex = block_excl_scan32<DT_THREADS / 32>(__popc(smask), sh.scan, 0, &total);
+    const uint32_t smask = (iso | (word & (~word_prev | ds))) & 0xFFFFu;
+    const uint32_t cnt = __popc(smask);
+    const uint32_t inc = warp_incl_scan(cnt);
+    const uint32_t wex = inc - cnt;                        // word starts of this warp before this segment
     sh.seg_smask[t] = smask;
-    sh.seg_sprefix[t] = ex;
-
-    // ---- every word that starts here: key, insert-or-find, entry
-    const unsigned long long w48 = (unsigned long long)word | ((unsigned long long)(sh.seg[t + 1] & 0xFFFFu) << 16) |
-                                   ((unsigned long long)(sh.seg[t + 2] & 0xFFFFu) << 32);
-    uint32_t* out = a.tile_words + (size_t)tile * DT_WCAP + ex;
-    uint32_t sm = smask;
-    while (sm) {
-        const int k = __ffs(sm) - 1; sm &= sm - 1;
-        const uint32_t p = t * DT_SEG + k;                       // tile-local byte position
-        uint32_t len;
-        if ((iso >> k) & 1u) len = 1;
-        else {
-            const unsigned long long cont = (w48 & ~d48) >> (k + 1);       // bit j: byte p+1+j continues the word
-            len = 1 + (uint32_t)__ffsll((long long)~cont) - 1;            // ~cont has a set bit within 48-(k+1) >= 32 bits
-        }
-        uint32_t entry;
-        bool to_long = len > DT_MAX_SHORT;
-        uint32_t end_abs = 0;
-        if (!to_long) {
-            // 16 bytes at byte offset p of the normalised tile, masked to len, length in the top byte
-            const uint32_t wi = p >> 2, shb = (p & 3) * 8;
-            const uint32_t x0 = sh.text32[wi], x1 = sh.text32[wi + 1], x2 = sh.text32[wi + 2], x3 = sh.text32[wi + 3], x4 = sh.text32[wi + 4];
-            const uint32_t y0 = __funnelshift_r(x0, x1, shb), y1 = __funnelshift_r(x1, x2, shb), y2 = __funnelshift_r(x2, x3, shb),
-                           y3 = __funnelshift_r(x3, x4, shb);
-            unsigned long long k0 = (unsigned long long)y0 | ((unsigned long long)y1 << 32);
-            unsigned long long k1 = (unsigned long long)y2 | ((unsigned long long)y3 << 32);
-            if (len <= 8) { k1 = 0; if (len < 8) k0 &= (1ULL << (8 * len)) - 1ULL; }
-            else k1 &= (1ULL << (8 * (len - 8))) - 1ULL;
-            k1 |= (unsigned long long)len << 56;
-            uint32_t slot = key_hash(k0, k1) & a.table_mask;
-            entry = TKZ_NONE;
-            for (int probe = 0; probe < DT_MAX_PROBE; probe++) {
-                DedupSlot* s = a.table + slot;
-                const ulonglong2 cur = __ldcg(reinterpret_cast<const ulonglong2*>(s));      // one 16-byte load: never torn
-                const unsigned long long c0 = cur.x, c1 = cur.y;
-                if (c0 == k0 && c1 == k1) { entry = slot; break; }
-                if (c0 == 0 && c1 == 0) {
-                    const K128 old = cas128(s, K128{0, 0}, K128{k0, k1});
-                    if (old.lo == 0 && old.hi == 0) {                  // inserted: this thread owns the unique word
-                        const uint32_t u = atomicAdd(a.n_uniq, 1u);
-                        a.uniq_slots[u] = slot;
-                        entry = slot; break;
-                    }
-                    if (old.lo == k0 && old.hi == k1) { entry = slot; break; }
-                }
-                slot = (slot + 1) & a.table_mask;
-            }
-            if (entry == TKZ_NONE) { to_long = true; end_abs = (uint32_t)(tile_base + p + len); }
-        } else {
-            // long word: find its end (first non-WORD byte or next document start)
-            const uint64_t start = tile_base + p;
-            const uint32_t dn = upper_bound_u64(a.doc_off, d_lo > 0 ? d_lo - 1 : 0, a.n_docs + 1, start);
-            uint64_t limit = dn <= a.n_docs ? __ldg(a.doc_off + dn) : a.n;
-            if (limit > a.n) limit = a.n;
-            uint64_t q = start + DT_MAX_SHORT + 1;
-            while (q < limit && sh.cls[__ldg(a.text + q)] == 0) q++;
-            end_abs = (uint32_t)q;
-            const uint32_t wlen = (uint32_t)(q - start);
-            if (wlen <= DT_MAX_MED) {
-                // medium word: 64-bit tag over the normalised bytes, exactness by comparing with the representative
-                const uint8_t* __restrict__ wp = a.text + start;
-                unsigned long long h = TKZ_FNV_OFFSET ^ wlen;
-                for (uint32_t j = 0; j < wlen; j++) h = fnv1a_step(h, sh.norm[__ldg(wp + j)]);
-                h ^= h >> 29; h *= 0xD6E8FEB86659FD93ULL; h ^= h >> 32;
-                const unsigned long long tag = h | 0x8000000000000000ULL;
-                const unsigned long long meta = (unsigned long long)(uint32_t)start | ((unsigned long long)wlen << 32);
-                uint32_t slot = (uint32_t)h & a.med_mask;
-                for (int probe = 0; probe < DT_MAX_PROBE; probe++) {
-                    DedupSlot* s = a.table + a.med_base + slot;
-                    unsigned long long cur = __ldcg(&s->k0);
-                    if (cur == 0) {
-                        cur = atomicCAS(&s->k0, 0ULL, tag);
-                        if (cur == 0) {                                    // owner: publish the representative
-                            __stcg(&s->k1, meta);
-                            __threadfence();
-                            const uint32_t u = atomicAdd(a.n_uniq, 1u);
-                            a.uniq_slots[u] = a.med_base + slot;
-                            atomicAdd(a.n_uniq_med, 1u);
-                            entry = a.med_base + slot; to_long = false; break;
-                        }
-                    }
-                    if (cur == tag) {
-                        const unsigned long long rm = __ldcg(&s->k1);
-                        if (rm == 0) break;                                // representative not published yet: take the per-occurrence path
-                        if ((uint32_t)(rm >> 32) == wlen) {
-                            const uint8_t* __restrict__ rp = a.text + (uint32_t)rm;
-                            bool eq = true;
-                            for (uint32_t j = 0; j < wlen && eq; j++) eq = sh.norm[__ldg(rp + j)] == sh.norm[__ldg(wp + j)];
-                            if (eq) { entry = a.med_base + slot; to_long = false; break; }
-                        }
-                    }
-                    slot = (slot + 1) & a.med_mask;
-                }
-            }
-        }
-        if (to_long) {
-            const uint32_t idx = atomicAdd(a.n_long, 1u);
-            if (idx < a.long_cap) { a.long_start[idx] = (uint32_t)(tile_base + p); a.long_end[idx] = end_abs; }
-            else atomicExch(a.overflow, 1u);
-            entry = DT_LONG | idx;
-        }
-        *out++ = entry;
+    sh.seg_sprefix[t] = wex;
+    {
+        uint32_t sm = smask, k = wex;
+        while (sm) { const int b = __ffs(sm) - 1; sm &= sm - 1; sh.wlist[wid][k++] = (uint16_t)(t * DT_SEG + b); }
     }
-    if (t == 0) a.tile_nwords[tile] = total;
+    const uint32_t nW = __shfl_sync(FULL, inc, 31);        // words of this warp
+    if (lane == 31) sh.wtot[wid] = inc;
     __syncthreads();
+    uint32_t wbase = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < DT_THREADS / 32; w++) { const uint32_t x = sh.wtot[w]; total += x; if ((uint32_t)w < wid) wbase += x; }
+    if (t == 0) a.tile_nwords[tile] = total;
+
+    // ---- phase 3: one word per lane
+    uint32_t* const out = a.tile_words + (size_t)tile * DT_WCAP + wbase;
+    for (uint32_t k0 = 0; k0 < nW; k0 += 32) {
+        const uint32_t k = k0 + lane;
+        const bool have = k < nW;
+        uint32_t p = 0, len = 0, entry = TKZ_NONE;
+        if (have) {
+            p = sh.wlist[wid][k];
+            const uint32_t sg = p >> 4, bit = p & 15u;
+            if (HAS_ISO && ((sh.seg[sg] >> (16 + bit)) & 1u)) len = 1;
+            else {
+                const unsigned long long w48 = (unsigned long long)(sh.seg[sg] & 0xFFFFu) | ((unsigned long long)(sh.seg[sg + 1] & 0xFFFFu) << 16) |
+                                               ((unsigned long long)(sh.seg[sg + 2] & 0xFFFFu) << 32);
+                const unsigned long long d48 = bits48(sh.docbits, sg * DT_SEG);
+                const unsigned long long cont = (w48 & ~d48) >> (bit + 1);       // bit j: byte p+1+j continues the word
+                len = (uint32_t)__ffsll((long long)~cont);                       // 1 + number of continuing bytes
+            }
+            if (len <= DT_MAX_SHORT) {
+                // 16 bytes at byte offset p of the normalised tile, masked to len, length in the top byte
+                const uint32_t wi = p >> 2, shb = (p & 3) * 8;
+                const uint32_t x0 = sh.text32[wi], x1 = sh.text32[wi + 1], x2 = sh.text32[wi + 2], x3 = sh.text32[wi + 3], x4 = sh.text32[wi + 4];
+                unsigned long long kk0 = (unsigned long long)__funnelshift_r(x0, x1, shb) | ((unsigned long long)__funnelshift_r(x1, x2, shb) << 32);
+                unsigned long long kk1 = (unsigned long long)__funnelshift_r(x2, x3, shb) | ((unsigned long long)__funnelshift_r(x3, x4, shb) << 32);
+                if (len <= 8) { kk1 = 0; if (len < 8) kk0 &= (1ULL << (8 * len)) - 1ULL; }
+                else kk1 &= (1ULL << (8 * (len - 8))) - 1ULL;
+                kk1 |= (unsigned long long)len << 56;
+                uint32_t slot = key_hash(kk0, kk1) & a.table_mask;
+                for (int probe = 0; probe < DT_MAX_PROBE; probe++) {
+                    DedupSlot* s = a.table + slot;
+                    const ulonglong2 cur = __ldcg(reinterpret_cast<const ulonglong2*>(s));      // one 16-byte load: never torn
+                    if (cur.x == kk0 && cur.y == kk1) { entry = slot; break; }
+                    if (cur.x == 0 && cur.y == 0) {
+                        const K128 old = cas128(s, K128{0, 0}, K128{kk0, kk1});
+                        if (old.lo == 0 && old.hi == 0) {                  // inserted: this thread owns the unique word
+                            const uint32_t u = atomicAdd(a.n_uniq, 1u);
+                            a.uniq_slots[u] = slot;
+                            entry = slot; break;
+                        }
+                        if (old.lo == kk0 && old.hi == kk1) { entry = slot; break; }
+                    }
+                    slot = (slot + 1) & a.table_mask;
+                }
+            }
+        }
+        // words that did not get an entry: longer than 15 bytes, or no free slot within the probe limit -- whole warp per word
+        uint32_t todo = __ballot_sync(FULL, have && entry == TKZ_NONE);
+        while (todo) {
+            const int l = __ffs(todo) - 1; todo &= todo - 1;
+            const uint32_t wp_ = __shfl_sync(FULL, p, l), wl_ = __shfl_sync(FULL, len, l);
+            const uint64_t start = tile_base + wp_;
+            uint64_t end = start + wl_;
+            uint32_t e = TKZ_NONE;
+            if (wl_ > DT_MAX_SHORT) {
+                // end of the word: first non-WORD byte or the next document start, 32 bytes per step
+                uint64_t limit = 0;
+                if (lane == 0) {
+                    const uint32_t dn = upper_bound_u64(a.doc_off, d_lo > 0 ? d_lo - 1 : 0, a.n_docs + 1, start);
+                    limit = dn <= a.n_docs ? __ldg(a.doc_off + dn) : a.n;
+                    if (limit > a.n) limit = a.n;
+                }
+                limit = __shfl_sync(FULL, limit, 0);
+                uint64_t q = start + DT_MAX_SHORT + 1;
+                for (;;) {
+                    const uint64_t qq = q + lane;
+                    const bool stop = qq >= limit || ((sh.lut[__ldg(a.text + qq)] >> 8) & 1u) == 0;
+                    const uint32_t sm = __ballot_sync(FULL, stop);
+                    if (sm) { q += (uint32_t)__ffs(sm) - 1; break; }
+                    q += 32;
+                }
+                end = q;
+                const uint32_t wlen = (uint32_t)(end - start);
+                if (wlen <= DT_MAX_MED) {
+                    // medium word: 64-bit tag = mixed polynomial hash of the normalised bytes (2 bytes per lane), exactness by
+                    // comparing with the representative occurrence
+                    const uint8_t* __restrict__ wq = a.text + start;
+                    unsigned long long h = 0; uint32_t b0 = 0, b1 = 0;
+                    if (2 * lane < wlen) { b0 = sh.lut[__ldg(wq + 2 * lane)] & 0xFFu; h += (unsigned long long)(b0 + 1) * c_med_pw[2 * lane]; }
+                    if (2 * lane + 1 < wlen) { b1 = sh.lut[__ldg(wq + 2 * lane + 1)] & 0xFFu; h += (unsigned long long)(b1 + 1) * c_med_pw[2 * lane + 1]; }
+                    for (int d = 16; d > 0; d >>= 1) h += __shfl_xor_sync(FULL, h, d);
+                    h ^= wlen; h ^= h >> 29; h *= 0xD6E8FEB86659FD93ULL; h ^= h >> 32;
+                    const unsigned long long tag = h | 0x8000000000000000ULL;
+                    const unsigned long long meta = (unsigned long long)(uint32_t)start | ((unsigned long long)wlen << 32);
+                    uint32_t slot = (uint32_t)h & a.med_mask;
+                    for (int probe = 0; probe < DT_MAX_PROBE; probe++) {
+                        DedupSlot* s = a.table + a.med_base + slot;
+                        unsigned long long cur = 0;
+                        if (lane == 0) {
+                            cur = __ldcg(&s->k0);
+                            if (cur == 0) {
+                                cur = atomicCAS(&s->k0, 0ULL, tag);
+                                if (cur == 0) {                            // owner: publish the representative
+                                    __stcg(&s->k1, meta);
+                                    __threadfence();
+                                    const uint32_t u = atomicAdd(a.n_uniq, 1u);
+                                    a.uniq_slots[u] = a.med_base + slot;
+                                    atomicAdd(a.n_uniq_med, 1u);
+                                    cur = 1;                               // marker: owned
+                                }
+                            }
+                        }
+                        cur = __shfl_sync(FULL, cur, 0);
+                        if (cur == 1) { e = a.med_base + slot; break; }
+                        if (cur == tag) {
+                            unsigned long long rm = 0;
+                            if (lane == 0) rm = __ldcg(&s->k1);
+                            rm = __shfl_sync(FULL, rm, 0);
+                            if (rm == 0) break;                            // representative not published yet: per-occurrence path
+                            bool eq = (uint32_t)(rm >> 32) == wlen;
+                            if (eq) {
+                                const uint8_t* __restrict__ rp = a.text + (uint32_t)rm;
+                                if (2 * lane < wlen) eq = eq && (sh.lut[__ldg(rp + 2 * lane)] & 0xFFu) == b0;
+                                if (2 * lane + 1 < wlen) eq = eq && (sh.lut[__ldg(rp + 2 * lane + 1)] & 0xFFu) == b1;
+                            }
+                            if (__all_sync(FULL, eq)) { e = a.med_base + slot; break; }
+                        }
+                        slot = (slot + 1) & a.med_mask;
+                    }
+                }
+            }
+            if (e == TKZ_NONE) {
+                uint32_t idx = 0;
+                if (lane == 0) {
+                    idx = atomicAdd(a.n_long, 1u);
+                    if (idx < a.long_cap) { a.long_start[idx] = (uint32_t)start; a.long_end[idx] = (uint32_t)end; }
+                    else atomicExch(a.overflow, 1u);
+                }
+                idx = __shfl_sync(FULL, idx, 0);
+                e = DT_LONG | idx;
+            }
+            if ((int)lane == l) entry = e;
+        }
+        if (have) out[k] = entry;
+    }
     // ---- first word (virtual index = tile * WCAP + local index) of every document that starts inside this tile
     for (uint32_t d = d_lo + t; d <= a.n_docs; d += DT_THREADS) {
         const uint64_t off = __ldg(a.doc_off + d);
         if (off >= tile_base + DT_TILE) break;
         const uint32_t p = (uint32_t)(off - tile_base);
         const uint32_t sg = p / DT_SEG;
-        a.doc_word_ref[d] = tile * DT_WCAP + sh.seg_sprefix[sg] + __popc(sh.seg_smask[sg] & ((1u << (p % DT_SEG)) - 1u));
+        uint32_t wb = 0;
+        for (uint32_t w = 0; w < sg / 32; w++) wb += sh.wtot[w];
+        a.doc_word_ref[d] = tile * DT_WCAP + wb + sh.seg_sprefix[sg] + __popc(sh.seg_smask[sg] & ((1u << (p % DT_SEG)) - 1u));
     }
 }
 
