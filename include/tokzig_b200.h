@@ -195,6 +195,10 @@ int tkzh_set_pretokenizer(tkzh_tokenizer* t, const int32_t* kinds, int32_t n);
 int tkzh_encode_batch(tkzh_tokenizer* t, const uint8_t* text, const uint64_t* doc_off, uint64_t n_docs,
                       int add_special_tokens, uint32_t outputs, tkz_batch_result* out);
 
+/* Tokenizer.decode  src/lib.zig:163-189 with the config-path decoders (src/config.zig:459-530): host side only (the
+ * decode direction is outside the GPU hot path).  *out points into the tokenizer and is valid until the next decode. */
+int tkzh_decode(tkzh_tokenizer* t, const uint32_t* ids, uint64_t n, int skip_special_tokens, const uint8_t** out, uint64_t* out_len);
+
 /* lookups  src/lib.zig:203-223 (added vocab first, then the model) */
 uint64_t tkzh_get_vocab_size(tkzh_tokenizer* t);
 int tkzh_token_to_id(tkzh_tokenizer* t, const uint8_t* token, uint64_t len, uint32_t* id);       /* 1 found, 0 not */

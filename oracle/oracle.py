@@ -405,6 +405,43 @@ class OracleTokenizer:
         r = self.encode_batch([b], algo=algo)
         return r.doc(0)
 
+    def decode(self, ids, skip_special_tokens: bool = False) -> bytes:
+        """Tokenizer.decode lib.zig:163-189 + config-path decoders config.zig:488-530 (restated; host logic)."""
+        cfg = self.cfg
+        model_r = {}
+        for k, v in cfg.vocab:
+            model_r[v] = k
+        added, special, next_id = {}, set(), 0            # side Vocab  vocab.zig:39-81
+        seen = set()
+        for a in cfg.added_tokens:
+            if a["content"] in seen:
+                continue
+            seen.add(a["content"])
+            i = a["id"] if a["id"] is not None else next_id
+            if i >= next_id:
+                next_id = i + 1
+            added[i] = a["content"]
+            if a["special"]:
+                special.add(a["content"])
+        r = b""
+        for i in ids:
+            i = int(i)
+            if skip_special_tokens and i in added and added[i] in special:
+                continue
+            if i in model_r:
+                r += model_r[i]
+        if cfg.decoder == "WordPiece":
+            out, j = bytearray(), 0
+            while j < len(r):
+                if j + 1 < len(r) and r[j] == 0x23 and r[j + 1] == 0x23:
+                    j += 2
+                else:
+                    out.append(r[j]); j += 1
+            return bytes(out)
+        if cfg.decoder == "BPE":
+            return r.replace(b"\xc4\xa0", b" ")
+        return r
+
     def count_tokens(self, text: np.ndarray, doc_off: np.ndarray, algo: int = 0, threads: int = 1) -> int:
         """Throughput leg for bench.py's cpu_baseline: same work, result arrays dropped."""
         self._sync()

@@ -105,7 +105,7 @@ EXPORTED_SYMBOLS = [
     "tkz_ctx_create", "tkz_ctx_destroy", "tkz_last_error", "tkz_ctx_get_stats", "tkz_model_upload", "tkz_encode_batch",
     "tkz_encode_batch_device",
     "tkzh_from_json", "tkzh_from_file", "tkzh_free", "tkzh_last_error", "tkzh_ctx", "tkzh_set_truncation", "tkzh_set_padding",
-    "tkzh_set_normalizer", "tkzh_set_pretokenizer", "tkzh_encode_batch", "tkzh_get_vocab_size", "tkzh_token_to_id",
+    "tkzh_set_normalizer", "tkzh_set_pretokenizer", "tkzh_encode_batch", "tkzh_decode", "tkzh_get_vocab_size", "tkzh_token_to_id",
     "tkzh_id_to_token", "tkzh_add_special_tokens", "tkzh_model_vocab_count", "tkzh_merge_count", "tkzh_has_normalizer",
     "tkzh_has_pretokenizer", "tkzh_has_post_processor", "tkzh_added_token_count", "tkzh_added_token", "tkzh_model_desc",
 ]
@@ -143,6 +143,7 @@ def lib():
     L.tkzh_set_normalizer.argtypes = [vp, vp, vp, C.c_int32]
     L.tkzh_set_pretokenizer.argtypes = [vp, vp, C.c_int32]
     L.tkzh_encode_batch.argtypes = [vp, vp, vp, u64, i32, u32, C.POINTER(BatchResult)]
+    L.tkzh_decode.argtypes = [vp, vp, u64, i32, C.POINTER(vp), C.POINTER(u64)]
     L.tkzh_get_vocab_size.argtypes = [vp]
     L.tkzh_get_vocab_size.restype = u64
     L.tkzh_token_to_id.argtypes = [vp, C.c_char_p, u64, C.POINTER(u32)]
@@ -393,6 +394,15 @@ class Tokenizer:
             else:
                 toks.append(self._model_id_to_token(i) or b"")                                    # bpe.zig:258, wordpiece.zig:200-205
         return Encoding(b.ids, b.type_ids, toks, b.offsets, b.special_tokens_mask, b.attention_mask)
+
+    def decode(self, ids, skip_special_tokens: bool = False) -> bytes:
+        """Tokenizer.decode (src/lib.zig:163-189); host side."""
+        a = np.ascontiguousarray(ids, dtype=np.uint32)
+        p, n = C.c_void_p(), C.c_uint64(0)
+        rc = self._L.tkzh_decode(self._h, a.ctypes.data if a.size else None, a.size, 1 if skip_special_tokens else 0, C.byref(p), C.byref(n))
+        if rc != OK:
+            raise TokzigError(rc)
+        return C.string_at(p.value, n.value) if n.value else b""
 
     # -- lookups (src/lib.zig:203-223)
     def get_vocab_size(self) -> int:

@@ -74,6 +74,7 @@ struct tkzh_tokenizer {
     std::vector<uint8_t> vocab_bytes; std::vector<uint64_t> vocab_off;
     uint16_t norm_lut[256]; uint8_t class_lut[256];
     tkz_model_desc desc{};
+    std::string decode_buf;
     // device
     tkz_ctx* ctx = nullptr;
     bool dirty = true;
@@ -342,6 +343,30 @@ extern "C" int tkzh_encode_batch(tkzh_tokenizer* t, const uint8_t* text, const u
     rc = tkz_encode_batch(t->ctx, text, doc_off, n_docs, &p, out);
     if (rc != TKZ_OK) t->err = tkz_last_error(t->ctx);
     return rc;
+}
+
+extern "C" int tkzh_decode(tkzh_tokenizer* t, const uint32_t* ids, uint64_t n, int skip_special_tokens, const uint8_t** out, uint64_t* out_len) {
+    if (!t || !out || !out_len || (n && !ids)) return TKZ_ERR_INVALID_ARG;
+    std::string r;
+    for (uint64_t i = 0; i < n; i++) {                                   // lib.zig:167-179
+        if (skip_special_tokens) {
+            auto a = t->added_vocab.id_to_token.find(ids[i]);
+            if (a != t->added_vocab.id_to_token.end() && t->added_vocab.special.count(a->second)) continue;
+        }
+        auto m = t->vocab_r.find(ids[i]);                                // model_impl.idToToken (not the added vocab)
+        if (m != t->vocab_r.end()) r += m->second;
+    }
+    std::string& o = t->decode_buf;
+    o.clear();
+    if (t->decoder_kind == 1) {                                          // wordPieceDecodeImpl config.zig:488-505: drops every "##"
+        for (size_t i = 0; i < r.size();) { if (i + 1 < r.size() && r[i] == '#' && r[i + 1] == '#') i += 2; else o.push_back(r[i++]); }
+    } else if (t->decoder_kind == 3) {                                   // bpeDecodeImpl config.zig:512-530: U+0120 -> space
+        for (size_t i = 0; i < r.size();) {
+            if (i + 1 < r.size() && (uint8_t)r[i] == 0xC4 && (uint8_t)r[i + 1] == 0xA0) { o.push_back(' '); i += 2; } else o.push_back(r[i++]);
+        }
+    } else o = r;                                                        // ByteLevel copies (config.zig:507-510); none: lib.zig:188
+    *out = (const uint8_t*)o.data(); *out_len = o.size();
+    return TKZ_OK;
 }
 
 extern "C" uint64_t tkzh_get_vocab_size(tkzh_tokenizer* t) { return t->vocab.size() + t->added_vocab.token_to_id.size(); }   // lib.zig:203-205
