@@ -170,10 +170,14 @@ __device__ __forceinline__ uint32_t block_excl_scan32(uint32_t v, uint32_t* sh, 
     const uint32_t inc = warp_incl_scan(v);
     if (lane == 31) s[wid] = inc;
     __syncthreads();
-    uint32_t base = 0, tot = 0;
+    // every warp scans the NW warp totals with shuffles (one shared-memory read per lane)
+    static_assert(NW <= 32, "one lane per warp total");
+    const uint32_t x = lane < NW ? s[lane] : 0u;
+    uint32_t xi = x;
 #pragma unroll
-    for (int w = 0; w < NW; w++) { const uint32_t x = s[w]; tot += x; if ((uint32_t)w < wid) base += x; }
-    *total = tot;
+    for (int d = 1; d < NW; d <<= 1) { const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, xi, d); if (lane >= (uint32_t)d) xi += y; }
+    *total = __shfl_sync(0xFFFFFFFFu, xi, NW - 1);
+    const uint32_t base = __shfl_sync(0xFFFFFFFFu, xi - x, wid);
     return base + inc - v;
 }
 
