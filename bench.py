@@ -233,6 +233,7 @@ def run_ours(args, rank, local_rank, world):
                 L.tkz_ctx_get_stats(ctx_h, C.byref(stats))
                 launches += stats.kernel_launches; words += stats.n_words
                 agg["uniq"] = agg.get("uniq", 0) * 0 + int(stats.n_unique_words); agg["long"] = int(stats.n_long_words)
+                agg["path"] = int(stats.path)
                 for i, k in enumerate(("ms_split", "ms_model", "ms_scan", "ms_emit", "ms_total")):
                     ms[i] += getattr(stats, k)
         return tot_tokens, tot_real, launches, ms, words
@@ -321,6 +322,10 @@ def run_ours(args, rank, local_rank, world):
     # roofline of the dominant kernel stage: algorithmic bytes of one step / that stage's device time in one step
     per_step_ms = [x / args.steps for x in agg["ms"]]
     names = ["split (K0+K1)", "model (K3 bpe | K4 wordpiece)", "scan", "emit (K5)"]
+    path_name = {0: "per-occurrence pipeline", 1: "dedup multi-pass pipeline", 2: "one-pass tile kernel"}.get(agg.get("path"), "?")
+    if agg.get("path") == 2:
+        names[0] = "table reset + tile index"
+        names[3] = "onepass_kernel (split + word-table probe + inline model + look-back + emit in one launch)"
     dom = int(np.argmax(per_step_ms[:4]))
     b_alg = nbytes + 4 * agg["tokens"]                       # input bytes + 4 B x id slots written (one rank)
     b_full = nbytes + (4 + (8 if params.outputs & 2 else 0) + (4 if params.outputs & 4 else 0)) * agg["tokens"]
@@ -339,7 +344,7 @@ def run_ours(args, rank, local_rank, world):
             "data": f"synthetic ({cname} generator, seed 1234+rank, generated in {t_gen:.1f} s)",
             "tokens_per_s": all_real / (ms_step * 1e-3), "slots_per_s": all_slots / (ms_step * 1e-3),
             "config": {"workload": f"{args.workload}: {desc}", "tokenizer": tok_name, "corpus": cname, "bytes_per_gpu": nbytes, "docs_per_gpu": nd,
-                       "words_per_gpu": agg["words"], "unique_words_last_batch": agg.get("uniq"), "long_words_last_batch": agg.get("long"), "tokens_per_gpu": agg["real"], "sub_batches": len(batches), "outputs_mask": int(params.outputs),
+                       "words_per_gpu": agg["words"], "unique_words_last_batch": agg.get("uniq"), "long_words_last_batch": agg.get("long"), "tokens_per_gpu": agg["real"], "sub_batches": len(batches), "outputs_mask": int(params.outputs), "pipeline": path_name,
                        "l2": "inputs (>= 1 GiB per step) larger than the 126 MB L2; no flush needed", "parallelism": f"documents sharded x{world}, no collective"},
             "roofline": roofline, "cpu_baseline": cb, "e2e": e2e, "gpu_launches": int(agg["launches"]), "clocks": sampler.summary(),
             "parity_checked_vs_oracle": parity}

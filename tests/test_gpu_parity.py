@@ -30,15 +30,24 @@ def assert_same(got: tz.BatchEncoding, ref: orc.BatchEncoding, what=""):
     assert np.array_equal(got.special_tokens_mask, ref.special_tokens_mask), f"{what}: special_tokens_mask"
 
 
-def pair(js, dedup=True):
-    """(GPU tokenizer, oracle).  dedup=False forces the per-occurrence pipeline (the context reads TKZ_NO_DEDUP when it
-    is created), so both device pipelines are held to the same oracle."""
+MODES = ("onepass", "multipass", "occurrence")
+
+
+def pair(js, dedup=True, mode=None):
+    """(GPU tokenizer, oracle).  The context reads its pipeline switches when it is created: mode "onepass" = the
+    one-pass tile kernel where it applies (default), "multipass" = the dedup multi-pass pipeline (TKZ_ONEPASS=0, also the
+    fallback of the one-pass kernel), "occurrence" = the per-occurrence pipeline (TKZ_NO_DEDUP=1; dedup=False is the
+    older spelling).  All device pipelines are held to the same oracle."""
     import os
-    os.environ["TKZ_NO_DEDUP"] = "0" if dedup else "1"
+    if mode is None:
+        mode = "onepass" if dedup else "occurrence"
+    os.environ["TKZ_NO_DEDUP"] = "1" if mode == "occurrence" else "0"
+    os.environ["TKZ_ONEPASS"] = "0" if mode == "multipass" else "1"
     try:
         t = tz.Tokenizer.from_json(js, device=0)
     finally:
         os.environ["TKZ_NO_DEDUP"] = "0"
+        os.environ["TKZ_ONEPASS"] = "1"
     return t, orc.OracleTokenizer.from_json(js)
 
 
@@ -83,7 +92,7 @@ def test_bpe_random(seed):
                               improper=[0.0, 0.3, 0.0, 0.5][mode], degenerate=[0.0, 0.0, 0.3, 0.2][mode], alias=[0.0, 0.0, 0.1, 0.2][mode],
                               pretok=[None, "Whitespace", "BertPreTokenizer", "ByteLevel"][(seed // 4) % 4],
                               normalizer=[None, "Lowercase"][(seed // 16) % 2])
-    t, o = pair(js, dedup=seed % 3 != 0)
+    t, o = pair(js, mode=MODES[seed % 3])
     docs = rand_docs(rng, alpha, 400, max_len=90, p_upper=0.2)
     assert_same(t.encode_batch(docs), o.encode_batch(docs), f"seed {seed}")
     t.close()
@@ -95,7 +104,7 @@ def test_wordpiece_random(seed):
     js, alpha = rand_wp_json(rng, n_words=rng.randint(5, 120), prefix=["##", "", "@@@", "#"][seed % 4], max_chars=[None, 4, 7, 100][(seed // 4) % 4],
                              pretok=["BertPreTokenizer", "Whitespace", None, "BertPreTokenizer"][(seed // 2) % 4],
                              normalizer=["BertNormalizer", None][(seed // 8) % 2])
-    t, o = pair(js, dedup=seed % 3 != 0)
+    t, o = pair(js, mode=MODES[seed % 3])
     docs = rand_docs(rng, alpha, 400, max_len=70, p_upper=0.3)
     assert_same(t.encode_batch(docs), o.encode_batch(docs), f"seed {seed}")
     t.close()
@@ -160,20 +169,20 @@ def _fix_utf8(b: bytes) -> bytes:
 
 
 # ----------------------------------------------------------------------------- edge cases
-@pytest.mark.parametrize("dedup", [True, False])
-def test_empty_and_ragged_inputs(dedup):
+@pytest.mark.parametrize("mode", MODES)
+def test_empty_and_ragged_inputs(mode):
     js, alpha = rand_bpe_json(random.Random(1), n_merges=20, pretok="Whitespace")
-    t, o = pair(js, dedup)
+    t, o = pair(js, mode=mode)
     for docs in ([], [b""], [b"", b"", b""], [b" "], [b"  \n\t "], [b"a"], [b"", b"a", b""], [b"ab", b"", b"", b"ba ab"], [b"a" * 5000, b"", b"b"]):
         assert_same(t.encode_batch(docs), o.encode_batch(docs), repr(docs)[:40])
     t.close()
 
 
-@pytest.mark.parametrize("dedup", [True, False])
-def test_document_boundary_splits_words(dedup):
+@pytest.mark.parametrize("mode", MODES)
+def test_document_boundary_splits_words(mode):
     js = json.dumps({"model": {"type": "BPE", "vocab": {"a": 0, "b": 1, "ab": 2, "ba": 3, "abab": 4}, "merges": ["a b", "b a", "ab ab"]},
                      "pre_tokenizer": {"type": "Whitespace"}})
-    t, o = pair(js, dedup)
+    t, o = pair(js, mode=mode)
     docs = [b"abab", b"ab", b"ab", b"a", b"b", b"", b"a b", b"ab"] * 700        # boundaries fall inside tiles and on tile edges
     assert_same(t.encode_batch(docs), o.encode_batch(docs))
     t.close()
@@ -229,7 +238,7 @@ def test_malformed_utf8():
     t.close()
 
 
-@pytest.mark.parametrize("dedup", [True, False])
+@pytest.mark.parametrize("dedup", ["onepass", "multipass", "occurrence"])
 def test_wordpiece_missing_unk_is_an_error(dedup):
     js = json.dumps({"model": {"type": "WordPiece", "vocab": {"hello": 1, "##s": 2}, "unk_token": "[UNK]"}, "pre_tokenizer": {"type": "Whitespace"}})
     t, o = pair(js, dedup)
@@ -302,8 +311,9 @@ def test_batch_split_invariance_and_roundtrip_property():
 
 
 # ----------------------------------------------------------------------------- dedup pipeline specifics
+@pytest.mark.parametrize("mode", ["onepass", "multipass"])
 @pytest.mark.parametrize("model", ["bpe", "wp"])
-def test_dedup_word_lengths_around_the_key_limit(model):
+def test_dedup_word_lengths_around_the_key_limit(model, mode):
     """words of 14 / 15 / 16 / 17 bytes straddle the 128-bit key (15 bytes + length), incl. NUL bytes inside words,
     words crossing 4 KiB tile edges and document boundaries inside a run."""
     rng = random.Random(17)
@@ -311,12 +321,12 @@ def test_dedup_word_lengths_around_the_key_limit(model):
         js, alpha = rand_bpe_json(rng, n_merges=60, alphabet=list("abcde") + ["é"], pretok="Whitespace", dead_merges=0.0)
     else:
         js, alpha = rand_wp_json(rng, n_words=80, alphabet=list("abcde") + ["é"], pretok="Whitespace", normalizer=None)
-    t, o = pair(js)
+    t, o = pair(js, mode=mode)
     docs = []
     for i in range(3000):
         words = []
         for _ in range(rng.randint(0, 12)):
-            L = rng.choice([1, 2, 3, 7, 13, 14, 15, 16, 17, 31, 40])
+            L = rng.choice([1, 2, 3, 7, 13, 14, 15, 16, 17, 31, 40, 63, 64, 65, 66, 100, 101, 255, 256, 257])
             w = "".join(rng.choice(alpha) for _ in range(L)).encode()[:L]
             words.append(w.decode("utf-8", "ignore").encode())
         d = b" ".join(words)
@@ -329,8 +339,8 @@ def test_dedup_word_lengths_around_the_key_limit(model):
 
 def test_dedup_and_per_occurrence_pipelines_agree_on_errors():
     js = json.dumps({"model": {"type": "BPE", "vocab": {"a": 0, "b": 1, "ab": 2}, "merges": ["a b"]}, "pre_tokenizer": {"type": "Whitespace"}})
-    for dedup in (True, False):
-        t, o = pair(js, dedup)
+    for mode in MODES:
+        t, o = pair(js, mode=mode)
         docs = [b"ab ab", b"ab \xffab ab", b"a\x80 ab", b"ab"]            # first failing document in TEXT order is 1
         with pytest.raises(tz.TokzigError) as e:
             t.encode_batch(docs)
@@ -343,13 +353,14 @@ def test_dedup_and_per_occurrence_pipelines_agree_on_errors():
         t.close()
 
 
+@pytest.mark.parametrize("mode", ["onepass", "multipass"])
 @pytest.mark.parametrize("n_words", [60000, 200000])
-def test_dedup_table_pressure_and_overflow(n_words):
+def test_dedup_table_pressure_and_overflow(n_words, mode):
     """more unique words than the batch's table holds: insertions that find no slot fall back to the long list, and when
     the long list overflows as well the batch is re-run by the per-occurrence pipeline -- results stay exact."""
     rng = random.Random(23)
     js, alpha = rand_bpe_json(rng, n_merges=100, alphabet=list("abcdefghijklmnop"), pretok="Whitespace", dead_merges=0.0)
-    t, o = pair(js)
+    t, o = pair(js, mode=mode)
     chars = "abcdefghijklmnopqrstuvwxyzABCDEFGHIJKLMNOPQRSTUVWXYZ0123456789"
     words = ["".join(rng.choice(chars) for _ in range(4)) for _ in range(n_words)]
     docs = [" ".join(words[i:i + 50]).encode() for i in range(0, len(words), 50)]
@@ -490,3 +501,92 @@ def test_fused_emit_switch(monkeypatch):
         for rep in range(3):
             assert_same(t.encode_packed(text, off), ref, f"TKZ_FUSED_EMIT={flag} call {rep}")
         t.close()
+
+
+# ----------------------------------------------------------------------------- one-pass tile kernel (tkz_onepass.cuh)
+@pytest.mark.parametrize("name,cname,mib", [("gpt2_whitespace", "c2", 96), ("llama3_whitespace", "c4", 64), ("bert_wordpiece", "c3", 48)])
+def test_onepass_equals_multipass_at_size(name, cname, mib, monkeypatch):
+    """the one-pass tile kernel against the multi-pass dedup pipeline on the same batch (one device call for the whole
+    batch), every output array compared in full (the multi-pass pipeline is itself held to the oracle at oracle-feasible
+    sizes above)."""
+    monkeypatch.setenv("TKZ_CHUNK_BYTES", str(1 << 31))
+    js = tokenizers_io.tokenizer_json(name)
+    text, off = corpus.generate(cname, mib << 20, seed=31)
+    t1, _ = pair(js, mode="onepass")
+    t0, _ = pair(js, mode="multipass")
+    for rep in range(2):                                  # second call: table sized from history, output estimate from density
+        a = t1.encode_packed(text, off)
+        b = t0.encode_packed(text, off)
+        assert t0.stats().path == 1
+        assert t1.stats().path == 2, "the one-pass kernel gave up on a corpus it is meant to handle"
+        for k in ("doc_tok_off", "ids", "offsets", "attention_mask", "type_ids", "special_tokens_mask"):
+            assert np.array_equal(getattr(a, k), getattr(b, k)), f"{name} call {rep}: {k}"
+    t1.close(); t0.close()
+
+
+def test_onepass_words_between_65_and_256_bytes_and_the_fallback():
+    """65..256-byte words are tokenized inside the one-pass kernel (symbols in global scratch, not deduplicated); a longer
+    word makes the kernel give up and the batch is re-run by the multi-pass pipeline.  Both equal the oracle."""
+    rng = random.Random(41)
+    for model in ("bpe", "wp"):
+        if model == "bpe":
+            js, alpha = rand_bpe_json(rng, n_merges=80, alphabet=list("abcdefgh") + ["é", "語"], pretok="Whitespace", dead_merges=0.0)
+        else:
+            js, alpha = rand_wp_json(rng, n_words=100, alphabet=list("abcdefgh") + ["é"], pretok="BertPreTokenizer", max_chars=300)
+        t, o = pair(js)
+
+        def word(L):
+            return "".join(rng.choice(alpha) for _ in range(L)).encode()[:L].decode("utf-8", "ignore").encode()
+
+        inline = [b" ".join(word(rng.choice([3, 9, 64, 65, 90, 128, 200, 255, 256])) for _ in range(rng.randint(1, 9))) for _ in range(800)]
+        assert_same(t.encode_batch(inline), o.encode_batch(inline, threads=8), model + " inline")
+        assert t.stats().path == 2
+        too_long = inline[:300] + [b"ab " + word(257) + b" cd", word(3000)] + inline[300:500]
+        assert_same(t.encode_batch(too_long), o.encode_batch(too_long, threads=8), model + " fallback")
+        assert t.stats().path == 1
+        assert_same(t.encode_batch(inline), o.encode_batch(inline, threads=8), model + " after fallback")
+        assert t.stats().path == 2
+        t.close()
+
+
+def test_onepass_wordpiece_words_above_max_chars_any_length():
+    """WordPiece only needs the length of a word above max_input_chars_per_word (wordpiece.zig:149-158): one [UNK] with
+    offsets (0, len), whatever the length -- handled inside the one-pass kernel up to 65535 bytes."""
+    js, alpha = rand_wp_json(random.Random(5), n_words=60, pretok="Whitespace", max_chars=100, normalizer=None)
+    t, o = pair(js)
+    docs = [b"x" * n + b" " + b"ab" for n in (99, 100, 101, 255, 256, 257, 1000, 4095, 4096, 4097, 20000, 65535)] * 3
+    assert_same(t.encode_batch(docs), o.encode_batch(docs))
+    assert t.stats().path == 2
+    docs.append(b"y" * 70000)
+    assert_same(t.encode_batch(docs), o.encode_batch(docs))
+    t.close()
+
+
+def test_onepass_dense_isolated_bytes_and_first_wave_contention():
+    """tiles where every byte is its own pre-token (512 words per warp slice), and thousands of tiles that meet the same
+    few new words at the same time (owner / polling protocol)."""
+    js, alpha = rand_wp_json(random.Random(6), n_words=60, pretok="BertPreTokenizer")
+    t, o = pair(js)
+    docs = [b"!" * 9000, b"?!.,;" * 2000, b"a!b?c.d" * 1500, b"...", b""] + [b"hello, world! " * 300] * 400
+    assert_same(t.encode_batch(docs), o.encode_batch(docs, threads=8))
+    assert t.stats().path == 2
+    t.close()
+    js = tokenizers_io.tokenizer_json("gpt2_whitespace")
+    t, o = pair(js)
+    docs = [b"the quick brown fox jumps over the lazy dog " * 100] * 3000
+    for rep in range(3):
+        assert_same(t.encode_batch(docs), o.encode_batch(docs, threads=8), f"contention call {rep}")
+    t.close()
+
+
+def test_onepass_errors_report_the_first_document_in_text_order():
+    js = json.dumps({"model": {"type": "BPE", "vocab": {"a": 0, "b": 1, "ab": 2}, "merges": ["a b"]}, "pre_tokenizer": {"type": "Whitespace"}})
+    t, o = pair(js)
+    filler = [b"ab ab a b"] * 5000
+    for bad_at, bad in ((4000, b"ab \xff"), (1234, b"ab " + b"a" * 30 + b"\xc3"), (0, b"\x80"), (4999, b"a" * 100 + b"\xff")):
+        docs = list(filler); docs[bad_at] = bad; docs[4500] = b"\xfe"
+        with pytest.raises(tz.TokzigError) as e:
+            t.encode_batch(docs)
+        assert e.value.code == tz.ERR_INVALID_UTF8 and e.value.doc == min(bad_at, 4500)
+    assert_same(t.encode_batch(filler), o.encode_batch(filler), "after errors")
+    t.close()

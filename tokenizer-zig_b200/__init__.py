@@ -97,7 +97,7 @@ class Stats(C.Structure):
     _fields_ = [("arena_bytes", C.c_uint64), ("n_words", C.c_uint64), ("n_unique_words", C.c_uint64),
                 ("n_long_words", C.c_uint64), ("kernel_launches", C.c_uint64),
                 ("ms_split", C.c_float), ("ms_model", C.c_float), ("ms_scan", C.c_float), ("ms_emit", C.c_float), ("ms_total", C.c_float),
-                ("model_flags", C.c_uint32)]
+                ("model_flags", C.c_uint32), ("path", C.c_uint32)]
 
 
 # every symbol include/tokzig_b200.h declares (checked by tests/test_cabi_symbols.py)

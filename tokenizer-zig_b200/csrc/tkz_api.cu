@@ -21,6 +21,7 @@
 #include "tkz_common.cuh"
 #include "tkz_dedup.cuh"
 #include "tkz_emit.cuh"
+#include "tkz_onepass.cuh"
 #include "tkz_scan.cuh"
 #include "tkz_split.cuh"
 #include "tkz_wordpiece.cuh"
@@ -70,6 +71,10 @@ struct tkz_ctx {
     double tok_per_byte_hist = 0.0;       // highest tokens/byte seen by this context: sizes the fused emit's output estimate
     bool has_iso = false;                 // the class table isolates some byte (punctuation split)
     bool use_dedup = true, use_fused = false;    // fused emit measured slower than count + emit on B200: opt-in
+    bool use_onepass = true;              // one-pass tile kernel (tkz_onepass.cuh) for plain concatenation
+    DevBuf a_optable, a_lscratch;
+    uint64_t op_uniq_hist = 0;            // most unique words seen in one batch: sizes the next batch's word table
+    uint64_t op_upool_hist = 0;           // most token records used by one batch
     HostBuf h_ctrl, h_doc_tok_off, h_ids, h_off, h_attn, h_type, h_special;
     uint64_t arena_bytes = 0;
     tkz_stats stats{};
@@ -201,6 +206,17 @@ extern "C" int tkz_ctx_create(int device, void* stream, uint64_t arena_hint_byte
         ctx->own_stream = true;
     }
     cudaFuncSetAttribute(bpe_block_kernel<1024, 12288>, cudaFuncAttributeMaxDynamicSharedMemorySize, 12288 * 15);
+    {
+        const int sm = (int)sizeof(OpShared);
+        cudaFuncSetAttribute(onepass_kernel<TKZ_MODEL_BPE, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
+        cudaFuncSetAttribute(onepass_kernel<TKZ_MODEL_BPE, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
+        cudaFuncSetAttribute(onepass_kernel<TKZ_MODEL_BPE, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
+        cudaFuncSetAttribute(onepass_kernel<TKZ_MODEL_BPE, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
+        cudaFuncSetAttribute(onepass_kernel<TKZ_MODEL_WORDPIECE, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
+        cudaFuncSetAttribute(onepass_kernel<TKZ_MODEL_WORDPIECE, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
+        cudaFuncSetAttribute(onepass_kernel<TKZ_MODEL_WORDPIECE, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
+        cudaFuncSetAttribute(onepass_kernel<TKZ_MODEL_WORDPIECE, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
+    }
     e = cudaFuncSetAttribute(bpe_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BPE_SMEM_BYTES);
     if (e != cudaSuccess) {
         g_create_error = std::string("kernel image not usable on this device (built for sm_100a): ") + cudaGetErrorString(e);
@@ -213,6 +229,7 @@ extern "C" int tkz_ctx_create(int device, void* stream, uint64_t arena_hint_byte
     (void)arena_hint_bytes;
     if (const char* e = getenv("TKZ_NO_DEDUP")) ctx->use_dedup = !(e[0] == '1');     // A/B switch for the parity tests
     if (const char* e = getenv("TKZ_FUSED_EMIT")) ctx->use_fused = (e[0] == '1');
+    if (const char* e = getenv("TKZ_ONEPASS")) ctx->use_onepass = !(e[0] == '0');
     if (const char* e = getenv("TKZ_CHUNK_BYTES")) { const long long v = atoll(e); if (v > 0) ctx->chunk_bytes = (uint64_t)v; }
     cudaStreamCreateWithFlags(&ctx->s_h2d, cudaStreamNonBlocking);
     cudaStreamCreateWithFlags(&ctx->s_d2h, cudaStreamNonBlocking);
@@ -239,7 +256,8 @@ extern "C" void tkz_ctx_destroy(tkz_ctx* ctx) {
                       &ctx->outs[1].attn, &ctx->outs[1].type, &ctx->outs[1].special, &ctx->in_text[0], &ctx->in_text[1], &ctx->in_doc_off[0],
                       &ctx->in_doc_off[1], &ctx->a_ctrl, &ctx->a_table, &ctx->a_uniq, &ctx->a_long_start, &ctx->a_long_end, &ctx->a_long_ntok,
                       &ctx->a_tile_words, &ctx->a_tile_nwords, &ctx->a_tile_ntok, &ctx->a_doc_word_ref, &ctx->a_doc_tok_local,
-                      &ctx->a_doc_tok_start, &ctx->a_doc_real, &ctx->a_upool, &ctx->a_tile_doc_lo, &ctx->a_g_first, &ctx->a_g_win, &ctx->a_g_flag, &ctx->a_big, &ctx->a_tile_state};
+                      &ctx->a_doc_tok_start, &ctx->a_doc_real, &ctx->a_upool, &ctx->a_tile_doc_lo, &ctx->a_g_first, &ctx->a_g_win, &ctx->a_g_flag, &ctx->a_big, &ctx->a_tile_state,
+                      &ctx->a_optable, &ctx->a_lscratch};
     for (DevBuf* b : bufs) release(*b);
     HostBuf* hb[] = {&ctx->h_ctrl, &ctx->h_doc_tok_off, &ctx->h_ids, &ctx->h_off, &ctx->h_attn, &ctx->h_type, &ctx->h_special,
                      &ctx->h_doc_stage[0], &ctx->h_doc_stage[1]};
@@ -457,6 +475,117 @@ int launch_bpe(tkz_ctx* ctx, const DevModel& m, const uint8_t* d_text, const uin
         uint64_t g = cls[1]; const uint64_t gc = (uint64_t)ctx->sm_count; if (g > gc) g = gc;
         bpe_block_kernel<1024, BB_BIG_CAP><<<(unsigned)g, 1024, BB_BIG_CAP * 15, st>>>(m, b); launches++;
     }
+    return TKZ_OK;
+}
+
+// The one-pass tile kernel (tkz_onepass.cuh): plain concatenation only.  Returns TKZ_RETRY_MULTIPASS when the kernel
+// gave up (a pre-token longer than OP_MAX_INLINE bytes, a pool ran out, the output estimate was too small): the caller
+// then runs the multi-pass pipeline on the same batch.
+#define TKZ_RETRY_MULTIPASS 2
+template <int MODEL>
+void launch_onepass(const DevModel& m, const OnePassArgs& oa, bool nid, bool iso, uint32_t n_tiles, cudaStream_t st) {
+    const size_t sm = sizeof(OpShared);
+    if (nid && !iso) onepass_kernel<MODEL, true, false><<<n_tiles, OP_THREADS, sm, st>>>(m, oa);
+    else if (nid) onepass_kernel<MODEL, true, true><<<n_tiles, OP_THREADS, sm, st>>>(m, oa);
+    else if (!iso) onepass_kernel<MODEL, false, false><<<n_tiles, OP_THREADS, sm, st>>>(m, oa);
+    else onepass_kernel<MODEL, false, true><<<n_tiles, OP_THREADS, sm, st>>>(m, oa);
+}
+
+int encode_onepass(tkz_ctx* ctx, const DevModel& m, const uint8_t* d_text, const uint64_t* d_doc_off, uint32_t nd, uint64_t N,
+                   const tkz_encode_params& P, tkz_batch_result* out, uint64_t& launches) {
+    cudaStream_t st = ctx->stream;
+    unsigned long long* ctrl = (unsigned long long*)ctx->a_ctrl.p;
+    unsigned long long* hctrl = (unsigned long long*)ctx->h_ctrl.p;
+    const uint64_t n_docs = nd;
+    const uint32_t n_tiles = (uint32_t)(N / OP_TILE + 1);
+    // word table: sized from the text and from what earlier batches of this context needed (load factor <= 1/4)
+    uint64_t want = N / 32; if (want < (1u << 16)) want = 1u << 16; if (want > (1u << 22)) want = 1u << 22;
+    if (want < ctx->op_uniq_hist * 4) want = ctx->op_uniq_hist * 4;
+    if (want > (1u << 26)) want = 1u << 26;
+    const uint32_t tcap = pow2_at_least(want);
+    const uint32_t mcap = tcap >= (1u << 17) ? tcap / 8 : (1u << 14);
+    uint64_t upool_cap = N / 16 + (1u << 16);
+    if (upool_cap < ctx->op_upool_hist * 2) upool_cap = ctx->op_upool_hist * 2;
+    if (upool_cap > 0xFFFFFF00ull) upool_cap = 0xFFFFFF00ull;
+    uint64_t ls_cap = N / 16 + (1u << 22); if (ls_cap > 0xFFFFFF00ull) ls_cap = 0xFFFFFF00ull;
+    // output capacity: tokens <= bytes; with history, the densest batch seen so far plus head-room
+    uint64_t est = N + 16;
+    if (ctx->tok_per_byte_hist > 0.0) { const uint64_t e2 = (uint64_t)((double)N * ctx->tok_per_byte_hist * 1.25) + 65536; if (e2 < est) est = e2; }
+    else if (N > (64ull << 20)) est = N / 2 + 65536;
+    TRY(ensure(ctx, ctx->a_optable, ((size_t)tcap + mcap) * sizeof(OpSlot)));
+    TRY(ensure(ctx, ctx->a_upool, (size_t)upool_cap * 8));
+    TRY(ensure(ctx, ctx->a_lscratch, (size_t)ls_cap * 4));
+    TRY(ensure(ctx, ctx->a_tile_state, (size_t)n_tiles * 8));
+    TRY(ensure(ctx, ctx->a_tile_doc_lo, ((size_t)n_tiles + 2) * 4));
+    TRY(ensure(ctx, ctx->O().doc_tok_off, (n_docs + 1) * 8));
+    TRY(ensure(ctx, ctx->O().ids, est * 4));
+    if (P.outputs & TKZ_OUT_OFFSETS) TRY(ensure(ctx, ctx->O().off, est * 8));
+    if (P.outputs & TKZ_OUT_ATTENTION) TRY(ensure(ctx, ctx->O().attn, est * 4));
+    if (P.outputs & TKZ_OUT_TYPE_IDS) TRY(ensure(ctx, ctx->O().type, est * 4));
+    if (P.outputs & TKZ_OUT_SPECIAL) TRY(ensure(ctx, ctx->O().special, est * 4));
+    uint64_t cap = ctx->O().ids.cap / 4;
+    if (P.outputs & TKZ_OUT_OFFSETS) cap = std::min<uint64_t>(cap, ctx->O().off.cap / 8);
+    if (P.outputs & TKZ_OUT_ATTENTION) cap = std::min<uint64_t>(cap, ctx->O().attn.cap / 4);
+    if (P.outputs & TKZ_OUT_TYPE_IDS) cap = std::min<uint64_t>(cap, ctx->O().type.cap / 4);
+    if (P.outputs & TKZ_OUT_SPECIAL) cap = std::min<uint64_t>(cap, ctx->O().special.cap / 4);
+    CK(cudaMemsetAsync(ctx->a_optable.p, 0, ((size_t)tcap + mcap) * sizeof(OpSlot), st));
+    CK(cudaMemsetAsync(ctx->a_tile_state.p, 0, (size_t)n_tiles * 8, st));
+    tile_doc_index_kernel<<<(n_tiles + 1 + 255) / 256, 256, 0, st>>>(d_doc_off, nd, n_tiles, (uint32_t*)ctx->a_tile_doc_lo.p); launches++;
+    OnePassArgs oa{};
+    oa.text = d_text; oa.n = N; oa.doc_off = d_doc_off; oa.n_docs = nd; oa.tile_doc_lo = (const uint32_t*)ctx->a_tile_doc_lo.p;
+    oa.table = (OpSlot*)ctx->a_optable.p; oa.table_mask = tcap - 1; oa.med_base = tcap; oa.med_mask = mcap - 1;
+    oa.upool = (unsigned long long*)ctx->a_upool.p; oa.upool_cap = (uint32_t)std::min<uint64_t>(upool_cap, ctx->a_upool.cap / 8); oa.upool_count = (unsigned int*)(ctrl + 9);
+    oa.lscratch = (uint32_t*)ctx->a_lscratch.p; oa.lscratch_cap = (uint32_t)ls_cap; oa.lscratch_count = (unsigned int*)(ctrl + 9) + 1;
+    oa.tile_state = (unsigned long long*)ctx->a_tile_state.p;
+    oa.ticket = (unsigned int*)(ctrl + 5); oa.abort_flag = (unsigned int*)(ctrl + 8); oa.errw = ctrl;
+    oa.n_words = ctrl + 10; oa.n_uniq = (unsigned int*)(ctrl + 6); oa.n_uncached = (unsigned int*)(ctrl + 6) + 1;
+    oa.cap = cap; oa.doc_tok_off = (unsigned long long*)ctx->O().doc_tok_off.p;
+    oa.o = EmitOut{(uint32_t*)ctx->O().ids.p, (uint32_t*)ctx->O().off.p, (uint32_t*)ctx->O().attn.p, (uint32_t*)ctx->O().type.p, (uint32_t*)ctx->O().special.p};
+    oa.outputs = P.outputs;
+    CK(cudaEventRecord(ctx->ev[1], st));
+    if (m.kind == TKZ_MODEL_BPE) launch_onepass<TKZ_MODEL_BPE>(m, oa, m.norm_identity != 0, ctx->has_iso, n_tiles, st);
+    else launch_onepass<TKZ_MODEL_WORDPIECE>(m, oa, m.norm_identity != 0, ctx->has_iso, n_tiles, st);
+    launches++;
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(ctx->ev[4], st));
+    CK(cudaMemcpyAsync(hctrl, ctrl, 13 * 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(hctrl + 32, (unsigned long long*)ctx->a_tile_state.p + (n_tiles - 1), 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    const uint32_t n_uniq = (uint32_t)hctrl[6], n_unc = (uint32_t)(hctrl[6] >> 32);
+    ctx->op_uniq_hist = std::max<uint64_t>(ctx->op_uniq_hist, n_uniq);
+    ctx->op_upool_hist = std::max<uint64_t>(ctx->op_upool_hist, (uint32_t)hctrl[9]);
+    if ((uint32_t)hctrl[8] != 0) {
+        // the history still helps the retry of a later batch: densest possible output next time
+        if ((hctrl[32] & OP_LB_VAL) > cap) ctx->tok_per_byte_hist = 1.0;
+        return TKZ_RETRY_MULTIPASS;
+    }
+    const uint64_t T = hctrl[32] & OP_LB_VAL;
+    const unsigned long long errw = hctrl[0];
+    ctx->stats.n_words = hctrl[10]; ctx->stats.n_unique_words = n_uniq; ctx->stats.n_long_words = n_unc;
+    ctx->stats.path = 2;
+    if (errw != TKZ_ERRW_NONE) {
+        op_err_doc_kernel<<<1, 1, 0, st>>>(ctrl, d_doc_off, nd); launches++;
+        CK(cudaMemcpyAsync(hctrl + 4, ctrl + 4, 8, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        out->err_doc = (int64_t)hctrl[4];
+        const uint32_t code = (uint32_t)(errw & 0xFF);
+        ctx->err = code == TKZ_ECODE_UTF8 ? "invalid UTF-8 in a BPE pre-token (reference behaviour undefined)" : "MissingUnkToken";
+        ctx->stats.kernel_launches = launches;
+        return code == TKZ_ECODE_UTF8 ? TKZ_ERR_INVALID_UTF8 : TKZ_ERR_MISSING_UNK;
+    }
+    if (N) ctx->tok_per_byte_hist = std::max(ctx->tok_per_byte_hist, (double)T / (double)N);
+    ctx->stats.kernel_launches = launches;
+    cudaEventElapsedTime(&ctx->stats.ms_split, ctx->ev[0], ctx->ev[1]);
+    ctx->stats.ms_model = 0.f; ctx->stats.ms_scan = 0.f;
+    cudaEventElapsedTime(&ctx->stats.ms_emit, ctx->ev[1], ctx->ev[4]);
+    cudaEventElapsedTime(&ctx->stats.ms_total, ctx->ev[0], ctx->ev[4]);
+    out->n_docs = n_docs; out->n_tokens = T; out->n_real_tokens = T;
+    out->doc_tok_off = (const uint64_t*)oa.doc_tok_off;
+    out->ids = oa.o.ids;
+    out->offsets = (P.outputs & TKZ_OUT_OFFSETS) ? oa.o.offsets : nullptr;
+    out->attention_mask = (P.outputs & TKZ_OUT_ATTENTION) ? oa.o.attention : nullptr;
+    out->type_ids = (P.outputs & TKZ_OUT_TYPE_IDS) ? oa.o.type_ids : nullptr;
+    out->special_tokens_mask = (P.outputs & TKZ_OUT_SPECIAL) ? oa.o.special : nullptr;
     return TKZ_OK;
 }
 
@@ -727,6 +856,13 @@ int encode_device_impl(tkz_ctx* ctx, const uint8_t* d_text, const uint64_t* d_do
 
     // ---- dedup pipeline (tkz_dedup.cuh) whenever there is a pre-tokenizer; falls through to the per-occurrence
     //      pipeline below only if its long list overflowed (pathological: > N/16 long words)
+    ctx->stats.path = m.has_pretok && ctx->use_dedup ? 1 : 0;
+    if (m.has_pretok && ctx->use_dedup && ctx->use_onepass && !P.has_truncation && !P.has_padding) {
+        int rc = encode_onepass(ctx, m, d_text, d_doc_off, nd, N, P, out, launches);
+        if (rc != TKZ_RETRY_MULTIPASS) return rc;
+        ctx->stats.path = 1;
+        ctrl_reset_kernel<<<1, 1, 0, st>>>(ctrl); launches++;
+    }
     if (m.has_pretok && ctx->use_dedup) {
         int rc = encode_dedup(ctx, m, d_text, d_doc_off, nd, N, P, out, launches);
         if (rc != TKZ_RETRY_NO_DEDUP) return rc;

@@ -33,6 +33,16 @@ struct BpeArgs {
     uint32_t max_len;             // words longer than this belong to the block kernels (tkz_bpe_block.cuh); 0xFFFFFFFF = all
 };
 
+// Byte sources for the model kernels: the pre-token's NORMALISED byte at offset p.
+struct GlobalLutSrc {             // raw text in HBM, normalised through the byte map on read
+    const uint8_t* lut; const uint8_t* w;
+    __device__ __forceinline__ uint32_t operator()(uint32_t p) const { return lut[__ldg(w + p)]; }
+};
+struct PlainSrc {                 // already-normalised bytes (shared memory or a table slot)
+    const uint8_t* w;
+    __device__ __forceinline__ uint32_t operator()(uint32_t p) const { return w[p]; }
+};
+
 // exact sequential form of the apply loop (bpe.zig:240-252), used when new_id == first (the re-check at the same index
 // can then match again) -- any table the loader accepts, however odd, keeps reference behaviour.
 __device__ __forceinline__ uint32_t bpe_apply_sequential(uint32_t* ids, uint32_t* ss, uint32_t* ee, uint32_t n, uint32_t A, uint32_t B, uint32_t N) {
@@ -48,15 +58,16 @@ __device__ __forceinline__ uint32_t bpe_apply_sequential(uint32_t* ids, uint32_t
 
 // initial symbols, sequential (one lane): exact Utf8Iterator semantics for malformed-but-in-bounds input.
 // returns symbol count or TKZ_NONE on an invalid lead byte / truncated tail (reference: unreachable).
-__device__ __forceinline__ uint32_t bpe_init_sequential(const DevModel& m, const uint8_t* __restrict__ w, uint32_t len,
+template <class Src>
+__device__ __forceinline__ uint32_t bpe_init_sequential(const DevModel& m, Src src, uint32_t len,
                                                         uint32_t* ids, uint32_t* ss, uint32_t* ee) {
     uint32_t p = 0, k = 0;
     while (p < len) {
-        const uint32_t b0 = m.lut[__ldg(w + p)];
+        const uint32_t b0 = src(p);
         const int L = utf8_seq_len(b0);
         if (L == 0 || p + (uint32_t)L > len) return TKZ_NONE;
         uint32_t key = b0;
-        for (int j = 1; j < L; j++) key |= (uint32_t)m.lut[__ldg(w + p + j)] << (8 * j);
+        for (int j = 1; j < L; j++) key |= src(p + j) << (8 * j);
         uint32_t id = char_lookup(m, key, L);
         if (id == TKZ_NONE && m.has_unk) id = m.unk_id;
         if (id != TKZ_NONE) { ids[k] = id; ss[k] = p; ee[k] = p + (uint32_t)L; k++; }
@@ -65,11 +76,12 @@ __device__ __forceinline__ uint32_t bpe_init_sequential(const DevModel& m, const
     return k;
 }
 
-// One pre-token through BPE.tokenize (bpe.zig:173-263) by one warp.  `wt` = the word's bytes (m.lut is applied on read),
+// One pre-token through BPE.tokenize (bpe.zig:173-263) by one warp.  `src` = the word's normalised bytes,
 // ids/ss/ee/rk = symbol arrays (shared memory or the word's pool slice) with room for `len` entries.
 // Returns the token count, or TKZ_NONE for an invalid lead byte / truncated tail (reference: unreachable).
-__device__ __forceinline__ uint32_t bpe_encode_word(const DevModel& m, const uint8_t* __restrict__ wt, uint32_t len,
-                                                    uint32_t* ids, uint32_t* ss, uint32_t* ee, uint32_t* rk) {
+template <class Src>
+__device__ __forceinline__ uint32_t bpe_encode_word_src(const DevModel& m, Src src, uint32_t len,
+                                                        uint32_t* ids, uint32_t* ss, uint32_t* ee, uint32_t* rk) {
     const uint32_t lane = lane_id();
     const uint32_t FULL = 0xFFFFFFFFu;
     const uint32_t lt_mask = (1u << lane) - 1u;
@@ -79,12 +91,12 @@ __device__ __forceinline__ uint32_t bpe_encode_word(const DevModel& m, const uin
         const uint32_t p = c0 + lane;
         uint32_t b0 = 0x80; int L = 0; bool start = false, bad = false;
         if (p < len) {
-            b0 = m.lut[__ldg(wt + p)];
+            b0 = src(p);
             if ((b0 & 0xC0) == 0x80) {
                 // continuation byte: must be covered by a lead byte at most 3 positions back
                 bool covered = false;
                 for (uint32_t back = 1; back <= 3 && back <= p; back++) {
-                    const uint32_t q = m.lut[__ldg(wt + p - back)];
+                    const uint32_t q = src(p - back);
                     if ((q & 0xC0) != 0x80) { covered = (uint32_t)utf8_seq_len(q) > back; break; }
                 }
                 bad = !covered;
@@ -96,7 +108,7 @@ __device__ __forceinline__ uint32_t bpe_encode_word(const DevModel& m, const uin
         uint32_t key = b0; uint32_t id = TKZ_NONE;
         if (start && !bad) {
             for (int j = 1; j < L; j++) {
-                const uint32_t bj = m.lut[__ldg(wt + p + j)];
+                const uint32_t bj = src(p + j);
                 if ((bj & 0xC0) != 0x80) bad = true;
                 key |= bj << (8 * j);
             }
@@ -109,7 +121,7 @@ __device__ __forceinline__ uint32_t bpe_encode_word(const DevModel& m, const uin
     }
     if (malformed) {
         // rare: re-do the word with the exact sequential iterator; invalid lead / truncated tail is an error
-        if (lane == 0) n = bpe_init_sequential(m, wt, len, ids, ss, ee);
+        if (lane == 0) n = bpe_init_sequential(m, src, len, ids, ss, ee);
         n = __shfl_sync(FULL, n, 0);
         if (n == TKZ_NONE) return TKZ_NONE;
     }
@@ -201,6 +213,12 @@ __device__ __forceinline__ uint32_t bpe_encode_word(const DevModel& m, const uin
     }
 
     return n;
+}
+
+// `wt` = raw text of the word; m.lut is applied on read
+__device__ __forceinline__ uint32_t bpe_encode_word(const DevModel& m, const uint8_t* __restrict__ wt, uint32_t len,
+                                                    uint32_t* ids, uint32_t* ss, uint32_t* ee, uint32_t* rk) {
+    return bpe_encode_word_src(m, GlobalLutSrc{m.lut, wt}, len, ids, ss, ee, rk);
 }
 
 __global__ void __launch_bounds__(BPE_WARPS * 32) bpe_warp_kernel(DevModel m, BpeArgs a) {

@@ -137,7 +137,7 @@ __global__ void __launch_bounds__(NT) bpe_block_kernel(DevModel m, BlockBpeArgs 
         if (s_cnt[0]) {
             // malformed UTF-8: exact sequential iterator by one thread (rare); invalid lead / truncated tail is an error
             if (t == 0) {
-                const uint32_t k = bpe_init_sequential(m, wt, len, ids, ps, pe);
+                const uint32_t k = bpe_init_sequential(m, GlobalLutSrc{m.lut, wt}, len, ids, ps, pe);
                 s_cnt[1] = k;
                 if (k != TKZ_NONE) for (uint32_t i = 0; i < k; i++) first[i] = i;
             }

@@ -12,6 +12,7 @@
 // verifies the key bytes; a ballot picks the longest hit.  Candidates longer than the longest vocabulary key cannot
 // match and are never formed, which removes the reference's O(len^2) probe count without changing any result.
 #pragma once
+#include "tkz_bpe.cuh"
 #include "tkz_common.cuh"
 
 namespace tkz {
@@ -31,7 +32,8 @@ struct WpArgs {
 };
 
 // exact-match probe of (prefix? + word[start .. start+clen)) ; returns id or TKZ_NONE
-__device__ __forceinline__ uint32_t wp_probe(const DevModel& m, const uint8_t* __restrict__ wt, uint32_t start, uint32_t clen,
+template <class Src>
+__device__ __forceinline__ uint32_t wp_probe(const DevModel& m, Src src, uint32_t start, uint32_t clen,
                                              uint64_t hash, bool with_prefix) {
     const uint32_t klen = clen + (with_prefix ? m.prefix_len : 0u);
     uint32_t slot = wp_slot(hash) & m.wp_mask;
@@ -43,7 +45,7 @@ __device__ __forceinline__ uint32_t wp_probe(const DevModel& m, const uint8_t* _
             bool eq = true;
             uint32_t k = 0;
             if (with_prefix) for (; k < m.prefix_len; k++) eq &= (__ldg(key + k) == m.prefix[k]);
-            for (uint32_t j = 0; j < clen && eq; j++) eq &= (__ldg(key + k + j) == m.lut[__ldg(wt + start + j)]);
+            for (uint32_t j = 0; j < clen && eq; j++) eq &= (__ldg(key + k + j) == src(start + j));
             if (eq) return e.id;
         }
         slot = (slot + 1) & m.wp_mask;
@@ -52,8 +54,9 @@ __device__ __forceinline__ uint32_t wp_probe(const DevModel& m, const uint8_t* _
 
 // One pre-token through WordPiece.tokenize (wordpiece.zig:141-222) by one warp.  Lane 0 writes the tokens to
 // oid/os/oe (room for `len` entries).  Returns the token count, or TKZ_NONE when [UNK] is needed but not in the vocabulary.
-__device__ __forceinline__ uint32_t wp_encode_word(const DevModel& m, const uint8_t* __restrict__ wt, uint32_t len,
-                                                   uint32_t* oid, uint32_t* os, uint32_t* oe) {
+template <class Src>
+__device__ __forceinline__ uint32_t wp_encode_word_src(const DevModel& m, Src src, uint32_t len,
+                                                       uint32_t* oid, uint32_t* os, uint32_t* oe) {
     const uint32_t lane = lane_id();
     const uint32_t FULL = 0xFFFFFFFFu;
     bool unk_word = (uint64_t)len > m.max_chars;                         // wordpiece.zig:149
@@ -71,11 +74,11 @@ __device__ __forceinline__ uint32_t wp_encode_word(const DevModel& m, const uint
                 const uint32_t clen = top > lane ? top - lane : 0;       // lane 0 = longest candidate of this step
                 uint64_t h = cont ? m.prefix_state : TKZ_FNV_OFFSET, mine = 0;
                 for (uint32_t j = 0; j < top; j++) {                     // uniform loop, broadcast byte loads
-                    h = fnv1a_step(h, m.lut[__ldg(wt + start + j)]);
+                    h = fnv1a_step(h, src(start + j));
                     if (j + 1 == clen) mine = h;
                 }
                 uint32_t id = TKZ_NONE;
-                if (clen > 0) id = wp_probe(m, wt, start, clen, mine, cont);
+                if (clen > 0) id = wp_probe(m, src, start, clen, mine, cont);
                 const uint32_t hits = __ballot_sync(FULL, id != TKZ_NONE);
                 if (hits) {
                     const int src = __ffs(hits) - 1;
@@ -95,6 +98,11 @@ __device__ __forceinline__ uint32_t wp_encode_word(const DevModel& m, const uint
         ntok = 1;
     }
     return ntok;
+}
+
+__device__ __forceinline__ uint32_t wp_encode_word(const DevModel& m, const uint8_t* __restrict__ wt, uint32_t len,
+                                                   uint32_t* oid, uint32_t* os, uint32_t* oe) {
+    return wp_encode_word_src(m, GlobalLutSrc{m.lut, wt}, len, oid, os, oe);
 }
 
 __global__ void __launch_bounds__(WP_WARPS * 32) wordpiece_warp_kernel(DevModel m, WpArgs a) {
