@@ -322,10 +322,11 @@ def run_ours(args, rank, local_rank, world):
     # roofline of the dominant kernel stage: algorithmic bytes of one step / that stage's device time in one step
     per_step_ms = [x / args.steps for x in agg["ms"]]
     names = ["split (K0+K1)", "model (K3 bpe | K4 wordpiece)", "scan", "emit (K5)"]
-    path_name = {0: "per-occurrence pipeline", 1: "dedup multi-pass pipeline", 2: "one-pass tile kernel"}.get(agg.get("path"), "?")
+    path_name = {0: "per-occurrence pipeline", 1: "dedup multi-pass pipeline", 2: "tile pipeline (2 passes)"}.get(agg.get("path"), "?")
     if agg.get("path") == 2:
-        names[0] = "table reset + tile index"
-        names[3] = "onepass_kernel (split + word-table probe + inline model + look-back + emit in one launch)"
+        names[0] = "tile_words_kernel (pass A: split + word-table probe + inline model)"
+        names[1] = "word-list kernels (pre-tokens > 256 B)"
+        names[3] = "tile_emit_kernel (pass B)"
     dom = int(np.argmax(per_step_ms[:4]))
     b_alg = nbytes + 4 * agg["tokens"]                       # input bytes + 4 B x id slots written (one rank)
     b_full = nbytes + (4 + (8 if params.outputs & 2 else 0) + (4 if params.outputs & 4 else 0)) * agg["tokens"]

@@ -139,8 +139,8 @@ typedef struct tkz_stats {
     float ms_emit;                      /* K5: fused truncate / pad / output write */
     float ms_total;                     /* first kernel to last kernel */
     uint32_t model_flags;               /* bit 0: merge table proven "proper" -> long words use the windowed block kernels */
-    uint32_t path;                      /* pipeline of the last encode: 0 per-occurrence, 1 dedup multi-pass, 2 one-pass tile kernel
-                                           (then ms_emit = the one-pass kernel, ms_split = table reset + tile index) */
+    uint32_t path;                      /* pipeline of the last encode: 0 per-occurrence, 1 dedup multi-pass, 2 tile pipeline
+                                           (then ms_split = pass A, ms_model = word-list kernels, ms_emit = pass B) */
 } tkz_stats;
 
 /* `device` = CUDA ordinal.  `stream` = a cudaStream_t the caller owns (e.g. torch's current stream) or NULL for a

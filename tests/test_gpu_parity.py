@@ -30,24 +30,24 @@ def assert_same(got: tz.BatchEncoding, ref: orc.BatchEncoding, what=""):
     assert np.array_equal(got.special_tokens_mask, ref.special_tokens_mask), f"{what}: special_tokens_mask"
 
 
-MODES = ("onepass", "multipass", "occurrence")
+MODES = ("tiles", "multipass", "occurrence")
 
 
 def pair(js, dedup=True, mode=None):
-    """(GPU tokenizer, oracle).  The context reads its pipeline switches when it is created: mode "onepass" = the
-    one-pass tile kernel where it applies (default), "multipass" = the dedup multi-pass pipeline (TKZ_ONEPASS=0, also the
-    fallback of the one-pass kernel), "occurrence" = the per-occurrence pipeline (TKZ_NO_DEDUP=1; dedup=False is the
-    older spelling).  All device pipelines are held to the same oracle."""
+    """(GPU tokenizer, oracle).  The context reads its pipeline switches when it is created: mode "tiles" = the tile
+    pipeline (tkz_tiles.cuh, default), "multipass" = the older dedup multi-pass pipeline (TKZ_TILES=0, also the fallback
+    when an estimated capacity of the tile pipeline runs out), "occurrence" = the per-occurrence pipeline (TKZ_NO_DEDUP=1;
+    dedup=False is the older spelling).  All device pipelines are held to the same oracle."""
     import os
     if mode is None:
-        mode = "onepass" if dedup else "occurrence"
+        mode = "tiles" if dedup else "occurrence"
     os.environ["TKZ_NO_DEDUP"] = "1" if mode == "occurrence" else "0"
-    os.environ["TKZ_ONEPASS"] = "0" if mode == "multipass" else "1"
+    os.environ["TKZ_TILES"] = "0" if mode == "multipass" else "1"
     try:
         t = tz.Tokenizer.from_json(js, device=0)
     finally:
         os.environ["TKZ_NO_DEDUP"] = "0"
-        os.environ["TKZ_ONEPASS"] = "1"
+        os.environ["TKZ_TILES"] = "1"
     return t, orc.OracleTokenizer.from_json(js)
 
 
@@ -238,7 +238,7 @@ def test_malformed_utf8():
     t.close()
 
 
-@pytest.mark.parametrize("dedup", ["onepass", "multipass", "occurrence"])
+@pytest.mark.parametrize("dedup", ["tiles", "multipass", "occurrence"])
 def test_wordpiece_missing_unk_is_an_error(dedup):
     js = json.dumps({"model": {"type": "WordPiece", "vocab": {"hello": 1, "##s": 2}, "unk_token": "[UNK]"}, "pre_tokenizer": {"type": "Whitespace"}})
     t, o = pair(js, dedup)
@@ -311,7 +311,7 @@ def test_batch_split_invariance_and_roundtrip_property():
 
 
 # ----------------------------------------------------------------------------- dedup pipeline specifics
-@pytest.mark.parametrize("mode", ["onepass", "multipass"])
+@pytest.mark.parametrize("mode", ["tiles", "multipass"])
 @pytest.mark.parametrize("model", ["bpe", "wp"])
 def test_dedup_word_lengths_around_the_key_limit(model, mode):
     """words of 14 / 15 / 16 / 17 bytes straddle the 128-bit key (15 bytes + length), incl. NUL bytes inside words,
@@ -353,7 +353,7 @@ def test_dedup_and_per_occurrence_pipelines_agree_on_errors():
         t.close()
 
 
-@pytest.mark.parametrize("mode", ["onepass", "multipass"])
+@pytest.mark.parametrize("mode", ["tiles", "multipass"])
 @pytest.mark.parametrize("n_words", [60000, 200000])
 def test_dedup_table_pressure_and_overflow(n_words, mode):
     """more unique words than the batch's table holds: insertions that find no slot fall back to the long list, and when
@@ -503,30 +503,29 @@ def test_fused_emit_switch(monkeypatch):
         t.close()
 
 
-# ----------------------------------------------------------------------------- one-pass tile kernel (tkz_onepass.cuh)
+# ----------------------------------------------------------------------------- tile pipeline (tkz_tiles.cuh)
 @pytest.mark.parametrize("name,cname,mib", [("gpt2_whitespace", "c2", 96), ("llama3_whitespace", "c4", 64), ("bert_wordpiece", "c3", 48)])
-def test_onepass_equals_multipass_at_size(name, cname, mib, monkeypatch):
-    """the one-pass tile kernel against the multi-pass dedup pipeline on the same batch (one device call for the whole
-    batch), every output array compared in full (the multi-pass pipeline is itself held to the oracle at oracle-feasible
-    sizes above)."""
+def test_tiles_equal_multipass_at_size(name, cname, mib, monkeypatch):
+    """the tile pipeline against the older multi-pass dedup pipeline on the same batch (one device call for the whole
+    batch), every output array compared in full (both are held to the oracle at oracle-feasible sizes above)."""
     monkeypatch.setenv("TKZ_CHUNK_BYTES", str(1 << 31))
     js = tokenizers_io.tokenizer_json(name)
     text, off = corpus.generate(cname, mib << 20, seed=31)
-    t1, _ = pair(js, mode="onepass")
+    t1, _ = pair(js, mode="tiles")
     t0, _ = pair(js, mode="multipass")
     for rep in range(2):                                  # second call: table sized from history, output estimate from density
         a = t1.encode_packed(text, off)
         b = t0.encode_packed(text, off)
         assert t0.stats().path == 1
-        assert t1.stats().path == 2, "the one-pass kernel gave up on a corpus it is meant to handle"
+        assert t1.stats().path == 2, "the tile pipeline gave up on a corpus it is meant to handle"
         for k in ("doc_tok_off", "ids", "offsets", "attention_mask", "type_ids", "special_tokens_mask"):
             assert np.array_equal(getattr(a, k), getattr(b, k)), f"{name} call {rep}: {k}"
     t1.close(); t0.close()
 
 
-def test_onepass_words_between_65_and_256_bytes_and_the_fallback():
-    """65..256-byte words are tokenized inside the one-pass kernel (symbols in global scratch, not deduplicated); a longer
-    word makes the kernel give up and the batch is re-run by the multi-pass pipeline.  Both equal the oracle."""
+def test_tiles_words_between_65_and_256_bytes_and_the_long_list():
+    """65..256-byte words are tokenized inside pass A (symbols in global scratch, not deduplicated); longer words go to
+    the long list (word-list kernels between the passes, counts folded back per tile and per document start)."""
     rng = random.Random(41)
     for model in ("bpe", "wp"):
         if model == "bpe":
@@ -540,18 +539,21 @@ def test_onepass_words_between_65_and_256_bytes_and_the_fallback():
 
         inline = [b" ".join(word(rng.choice([3, 9, 64, 65, 90, 128, 200, 255, 256])) for _ in range(rng.randint(1, 9))) for _ in range(800)]
         assert_same(t.encode_batch(inline), o.encode_batch(inline, threads=8), model + " inline")
-        assert t.stats().path == 2
-        too_long = inline[:300] + [b"ab " + word(257) + b" cd", word(3000)] + inline[300:500]
-        assert_same(t.encode_batch(too_long), o.encode_batch(too_long, threads=8), model + " fallback")
-        assert t.stats().path == 1
-        assert_same(t.encode_batch(inline), o.encode_batch(inline, threads=8), model + " after fallback")
-        assert t.stats().path == 2
+        assert t.stats().path == 2 and t.stats().n_long_words == 0
+        # long words in front of document starts inside the same tile, at tile edges, back to back
+        longer = inline[:300] + [b"ab " + word(257) + b" cd", word(3000), b"", word(5), word(300) + b" " + word(400), b"x", word(9000)] + inline[300:500]
+        for trunc, pad in ((None, None), (7, {"length": 9, "pad_id": 3})):
+            t.truncation = None if trunc is None else {"max_length": trunc}
+            o.truncation = trunc
+            t.padding = pad; o.padding = pad
+            assert_same(t.encode_batch(longer), o.encode_batch(longer, threads=8), model + f" long list trunc={trunc}")
+            assert t.stats().path == 2 and t.stats().n_long_words >= 5
         t.close()
 
 
-def test_onepass_wordpiece_words_above_max_chars_any_length():
+def test_tiles_wordpiece_words_above_max_chars_any_length():
     """WordPiece only needs the length of a word above max_input_chars_per_word (wordpiece.zig:149-158): one [UNK] with
-    offsets (0, len), whatever the length -- handled inside the one-pass kernel up to 65535 bytes."""
+    offsets (0, len), whatever the length -- handled inside pass A up to 65535 bytes, by the word-list kernel beyond."""
     js, alpha = rand_wp_json(random.Random(5), n_words=60, pretok="Whitespace", max_chars=100, normalizer=None)
     t, o = pair(js)
     docs = [b"x" * n + b" " + b"ab" for n in (99, 100, 101, 255, 256, 257, 1000, 4095, 4096, 4097, 20000, 65535)] * 3
@@ -562,7 +564,7 @@ def test_onepass_wordpiece_words_above_max_chars_any_length():
     t.close()
 
 
-def test_onepass_dense_isolated_bytes_and_first_wave_contention():
+def test_tiles_dense_isolated_bytes_and_first_wave_contention():
     """tiles where every byte is its own pre-token (512 words per warp slice), and thousands of tiles that meet the same
     few new words at the same time (owner / polling protocol)."""
     js, alpha = rand_wp_json(random.Random(6), n_words=60, pretok="BertPreTokenizer")
@@ -579,7 +581,7 @@ def test_onepass_dense_isolated_bytes_and_first_wave_contention():
     t.close()
 
 
-def test_onepass_errors_report_the_first_document_in_text_order():
+def test_tiles_errors_report_the_first_document_in_text_order():
     js = json.dumps({"model": {"type": "BPE", "vocab": {"a": 0, "b": 1, "ab": 2}, "merges": ["a b"]}, "pre_tokenizer": {"type": "Whitespace"}})
     t, o = pair(js)
     filler = [b"ab ab a b"] * 5000

@@ -21,7 +21,7 @@
 #include "tkz_common.cuh"
 #include "tkz_dedup.cuh"
 #include "tkz_emit.cuh"
-#include "tkz_onepass.cuh"
+#include "tkz_tiles.cuh"
 #include "tkz_scan.cuh"
 #include "tkz_split.cuh"
 #include "tkz_wordpiece.cuh"
@@ -71,10 +71,11 @@ struct tkz_ctx {
     double tok_per_byte_hist = 0.0;       // highest tokens/byte seen by this context: sizes the fused emit's output estimate
     bool has_iso = false;                 // the class table isolates some byte (punctuation split)
     bool use_dedup = true, use_fused = false;    // fused emit measured slower than count + emit on B200: opt-in
-    bool use_onepass = true;              // one-pass tile kernel (tkz_onepass.cuh) for plain concatenation
-    DevBuf a_optable, a_lscratch;
-    uint64_t op_uniq_hist = 0;            // most unique words seen in one batch: sizes the next batch's word table
-    uint64_t op_upool_hist = 0;           // most token records used by one batch
+    bool use_tiles = true;                // tile pipeline (tkz_tiles.cuh); TKZ_TILES=0 selects the older multi-pass dedup pipeline
+    DevBuf a_wtable, a_lscratch, a_ent, a_tile_ent_off, a_long_tile;
+    uint64_t tw_uniq_hist = 0;            // most unique words seen in one batch: sizes the next batch's word table
+    uint64_t tw_upool_hist = 0;           // most token records used by one batch
+    double tw_words_per_byte = 0.0;       // densest batch so far: sizes the entry list
     HostBuf h_ctrl, h_doc_tok_off, h_ids, h_off, h_attn, h_type, h_special;
     uint64_t arena_bytes = 0;
     tkz_stats stats{};
@@ -134,8 +135,10 @@ uint32_t pow2_at_least(uint64_t n) { uint32_t c = 2; while (c < n) c <<= 1; retu
 __global__ void ctrl_reset_kernel(unsigned long long* ctrl) {
     // ctrl[0] = error word, ctrl[1] = work counter (u32 view), ctrl[2..4] = read-back scalars,
     // dedup: ctrl[5] second work counter, [6] n_uniq, [7] n_long, [8] overflow, [9] upool_count, [10] n_words
+    // tile pipeline: [5] entry count, [6] n_uniq | n_uncached << 32, [7] n_long, [8] abort, [9] upool | lscratch << 32,
+    //                [10] n_words, [11..12] block-kernel work counters, [13..15] long-word length classes, [16] big-copy list
     ctrl[0] = TKZ_ERRW_NONE;
-    for (int i = 1; i < 16; i++) ctrl[i] = 0;
+    for (int i = 1; i < 32; i++) ctrl[i] = 0;
 }
 #define TKZ_RETRY_NO_DEDUP 1
 __global__ void tile_words_total_kernel(const uint32_t* tile_nwords, uint32_t n_tiles, unsigned long long* ctrl) {
@@ -206,17 +209,6 @@ extern "C" int tkz_ctx_create(int device, void* stream, uint64_t arena_hint_byte
         ctx->own_stream = true;
     }
     cudaFuncSetAttribute(bpe_block_kernel<1024, 12288>, cudaFuncAttributeMaxDynamicSharedMemorySize, 12288 * 15);
-    {
-        const int sm = (int)sizeof(OpShared);
-        cudaFuncSetAttribute(onepass_kernel<TKZ_MODEL_BPE, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
-        cudaFuncSetAttribute(onepass_kernel<TKZ_MODEL_BPE, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
-        cudaFuncSetAttribute(onepass_kernel<TKZ_MODEL_BPE, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
-        cudaFuncSetAttribute(onepass_kernel<TKZ_MODEL_BPE, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
-        cudaFuncSetAttribute(onepass_kernel<TKZ_MODEL_WORDPIECE, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
-        cudaFuncSetAttribute(onepass_kernel<TKZ_MODEL_WORDPIECE, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
-        cudaFuncSetAttribute(onepass_kernel<TKZ_MODEL_WORDPIECE, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
-        cudaFuncSetAttribute(onepass_kernel<TKZ_MODEL_WORDPIECE, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
-    }
     e = cudaFuncSetAttribute(bpe_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BPE_SMEM_BYTES);
     if (e != cudaSuccess) {
         g_create_error = std::string("kernel image not usable on this device (built for sm_100a): ") + cudaGetErrorString(e);
@@ -229,7 +221,7 @@ extern "C" int tkz_ctx_create(int device, void* stream, uint64_t arena_hint_byte
     (void)arena_hint_bytes;
     if (const char* e = getenv("TKZ_NO_DEDUP")) ctx->use_dedup = !(e[0] == '1');     // A/B switch for the parity tests
     if (const char* e = getenv("TKZ_FUSED_EMIT")) ctx->use_fused = (e[0] == '1');
-    if (const char* e = getenv("TKZ_ONEPASS")) ctx->use_onepass = !(e[0] == '0');
+    if (const char* e = getenv("TKZ_TILES")) ctx->use_tiles = !(e[0] == '0');
     if (const char* e = getenv("TKZ_CHUNK_BYTES")) { const long long v = atoll(e); if (v > 0) ctx->chunk_bytes = (uint64_t)v; }
     cudaStreamCreateWithFlags(&ctx->s_h2d, cudaStreamNonBlocking);
     cudaStreamCreateWithFlags(&ctx->s_d2h, cudaStreamNonBlocking);
@@ -257,7 +249,7 @@ extern "C" void tkz_ctx_destroy(tkz_ctx* ctx) {
                       &ctx->in_doc_off[1], &ctx->a_ctrl, &ctx->a_table, &ctx->a_uniq, &ctx->a_long_start, &ctx->a_long_end, &ctx->a_long_ntok,
                       &ctx->a_tile_words, &ctx->a_tile_nwords, &ctx->a_tile_ntok, &ctx->a_doc_word_ref, &ctx->a_doc_tok_local,
                       &ctx->a_doc_tok_start, &ctx->a_doc_real, &ctx->a_upool, &ctx->a_tile_doc_lo, &ctx->a_g_first, &ctx->a_g_win, &ctx->a_g_flag, &ctx->a_big, &ctx->a_tile_state,
-                      &ctx->a_optable, &ctx->a_lscratch};
+                      &ctx->a_wtable, &ctx->a_lscratch, &ctx->a_ent, &ctx->a_tile_ent_off, &ctx->a_long_tile};
     for (DevBuf* b : bufs) release(*b);
     HostBuf* hb[] = {&ctx->h_ctrl, &ctx->h_doc_tok_off, &ctx->h_ids, &ctx->h_off, &ctx->h_attn, &ctx->h_type, &ctx->h_special,
                      &ctx->h_doc_stage[0], &ctx->h_doc_stage[1]};
@@ -478,114 +470,180 @@ int launch_bpe(tkz_ctx* ctx, const DevModel& m, const uint8_t* d_text, const uin
     return TKZ_OK;
 }
 
-// The one-pass tile kernel (tkz_onepass.cuh): plain concatenation only.  Returns TKZ_RETRY_MULTIPASS when the kernel
-// gave up (a pre-token longer than OP_MAX_INLINE bytes, a pool ran out, the output estimate was too small): the caller
-// then runs the multi-pass pipeline on the same batch.
+// The tile pipeline (tkz_tiles.cuh).  Returns TKZ_RETRY_MULTIPASS when pass A ran out of an estimated capacity (entry
+// list, record pool, scratch, long list): the caller then runs the older multi-pass dedup pipeline on the same batch and
+// the next batch of this context gets larger estimates.
 #define TKZ_RETRY_MULTIPASS 2
 template <int MODEL>
-void launch_onepass(const DevModel& m, const OnePassArgs& oa, bool nid, bool iso, uint32_t n_tiles, cudaStream_t st) {
-    const size_t sm = sizeof(OpShared);
-    if (nid && !iso) onepass_kernel<MODEL, true, false><<<n_tiles, OP_THREADS, sm, st>>>(m, oa);
-    else if (nid) onepass_kernel<MODEL, true, true><<<n_tiles, OP_THREADS, sm, st>>>(m, oa);
-    else if (!iso) onepass_kernel<MODEL, false, false><<<n_tiles, OP_THREADS, sm, st>>>(m, oa);
-    else onepass_kernel<MODEL, false, true><<<n_tiles, OP_THREADS, sm, st>>>(m, oa);
+void launch_tile_words(const DevModel& m, const TileArgs& ta, bool nid, bool iso, uint32_t n_tiles, cudaStream_t st) {
+    if (nid && !iso) tile_words_kernel<MODEL, true, false><<<n_tiles, TW_THREADS, 0, st>>>(m, ta);
+    else if (nid) tile_words_kernel<MODEL, true, true><<<n_tiles, TW_THREADS, 0, st>>>(m, ta);
+    else if (!iso) tile_words_kernel<MODEL, false, false><<<n_tiles, TW_THREADS, 0, st>>>(m, ta);
+    else tile_words_kernel<MODEL, false, true><<<n_tiles, TW_THREADS, 0, st>>>(m, ta);
 }
 
-int encode_onepass(tkz_ctx* ctx, const DevModel& m, const uint8_t* d_text, const uint64_t* d_doc_off, uint32_t nd, uint64_t N,
-                   const tkz_encode_params& P, tkz_batch_result* out, uint64_t& launches) {
+int encode_tiles(tkz_ctx* ctx, const DevModel& m, const uint8_t* d_text, const uint64_t* d_doc_off, uint32_t nd, uint64_t N,
+                 const tkz_encode_params& P, tkz_batch_result* out, uint64_t& launches) {
     cudaStream_t st = ctx->stream;
     unsigned long long* ctrl = (unsigned long long*)ctx->a_ctrl.p;
     unsigned long long* hctrl = (unsigned long long*)ctx->h_ctrl.p;
     const uint64_t n_docs = nd;
-    const uint32_t n_tiles = (uint32_t)(N / OP_TILE + 1);
-    // word table: sized from the text and from what earlier batches of this context needed (load factor <= 1/4)
+    const uint32_t n_tiles = (uint32_t)(N / TW_TILE + 1);
+    const bool plain = !P.has_truncation && !P.has_padding;
+    // ---- capacities: from the text size and from what earlier batches of this context needed
     uint64_t want = N / 32; if (want < (1u << 16)) want = 1u << 16; if (want > (1u << 22)) want = 1u << 22;
-    if (want < ctx->op_uniq_hist * 4) want = ctx->op_uniq_hist * 4;
+    if (want < ctx->tw_uniq_hist * 4) want = ctx->tw_uniq_hist * 4;          // load factor <= 1/4
     if (want > (1u << 26)) want = 1u << 26;
     const uint32_t tcap = pow2_at_least(want);
     const uint32_t mcap = tcap >= (1u << 17) ? tcap / 8 : (1u << 14);
-    uint64_t upool_cap = N / 16 + (1u << 16);
-    if (upool_cap < ctx->op_upool_hist * 2) upool_cap = ctx->op_upool_hist * 2;
+    uint64_t upool_cap = N / 8 + (1u << 20);
+    if (upool_cap < ctx->tw_upool_hist * 2) upool_cap = ctx->tw_upool_hist * 2;
     if (upool_cap > 0xFFFFFF00ull) upool_cap = 0xFFFFFF00ull;
     uint64_t ls_cap = N / 16 + (1u << 22); if (ls_cap > 0xFFFFFF00ull) ls_cap = 0xFFFFFF00ull;
-    // output capacity: tokens <= bytes; with history, the densest batch seen so far plus head-room
-    uint64_t est = N + 16;
-    if (ctx->tok_per_byte_hist > 0.0) { const uint64_t e2 = (uint64_t)((double)N * ctx->tok_per_byte_hist * 1.25) + 65536; if (e2 < est) est = e2; }
-    else if (N > (64ull << 20)) est = N / 2 + 65536;
-    TRY(ensure(ctx, ctx->a_optable, ((size_t)tcap + mcap) * sizeof(OpSlot)));
+    uint64_t ent_cap = N + 16;                                               // words <= bytes
+    if (ctx->tw_words_per_byte > 0.0) { const uint64_t e2 = (uint64_t)((double)N * ctx->tw_words_per_byte * 1.25) + 65536; if (e2 < ent_cap) ent_cap = e2; }
+    else if (N > (64ull << 20)) ent_cap = N / 2 + 65536;
+    if (ent_cap > 0xFFFFFF00ull) ent_cap = 0xFFFFFF00ull;
+    const uint32_t long_cap = (uint32_t)(N / 256 + 1024);
+    TRY(ensure(ctx, ctx->a_wtable, ((size_t)tcap + mcap) * sizeof(WordSlot)));
     TRY(ensure(ctx, ctx->a_upool, (size_t)upool_cap * 8));
     TRY(ensure(ctx, ctx->a_lscratch, (size_t)ls_cap * 4));
-    TRY(ensure(ctx, ctx->a_tile_state, (size_t)n_tiles * 8));
+    TRY(ensure(ctx, ctx->a_ent, (size_t)ent_cap * 8));
+    TRY(ensure(ctx, ctx->a_tile_ent_off, ((size_t)n_tiles + 2) * 4));
+    TRY(ensure(ctx, ctx->a_tile_nwords, ((size_t)n_tiles + 2) * 4));
+    TRY(ensure(ctx, ctx->a_tile_ntok, ((size_t)n_tiles + 2) * 4));
     TRY(ensure(ctx, ctx->a_tile_doc_lo, ((size_t)n_tiles + 2) * 4));
+    TRY(ensure(ctx, ctx->a_doc_word_ref, (n_docs + 2) * 4));
+    TRY(ensure(ctx, ctx->a_doc_tok_local, (n_docs + 2) * 4));
+    TRY(ensure(ctx, ctx->a_long_start, (size_t)long_cap * 4));
+    TRY(ensure(ctx, ctx->a_long_end, (size_t)long_cap * 4));
+    TRY(ensure(ctx, ctx->a_long_tile, (size_t)long_cap * 4));
     TRY(ensure(ctx, ctx->O().doc_tok_off, (n_docs + 1) * 8));
-    TRY(ensure(ctx, ctx->O().ids, est * 4));
-    if (P.outputs & TKZ_OUT_OFFSETS) TRY(ensure(ctx, ctx->O().off, est * 8));
-    if (P.outputs & TKZ_OUT_ATTENTION) TRY(ensure(ctx, ctx->O().attn, est * 4));
-    if (P.outputs & TKZ_OUT_TYPE_IDS) TRY(ensure(ctx, ctx->O().type, est * 4));
-    if (P.outputs & TKZ_OUT_SPECIAL) TRY(ensure(ctx, ctx->O().special, est * 4));
-    uint64_t cap = ctx->O().ids.cap / 4;
-    if (P.outputs & TKZ_OUT_OFFSETS) cap = std::min<uint64_t>(cap, ctx->O().off.cap / 8);
-    if (P.outputs & TKZ_OUT_ATTENTION) cap = std::min<uint64_t>(cap, ctx->O().attn.cap / 4);
-    if (P.outputs & TKZ_OUT_TYPE_IDS) cap = std::min<uint64_t>(cap, ctx->O().type.cap / 4);
-    if (P.outputs & TKZ_OUT_SPECIAL) cap = std::min<uint64_t>(cap, ctx->O().special.cap / 4);
-    CK(cudaMemsetAsync(ctx->a_optable.p, 0, ((size_t)tcap + mcap) * sizeof(OpSlot), st));
-    CK(cudaMemsetAsync(ctx->a_tile_state.p, 0, (size_t)n_tiles * 8, st));
+    TRY(ensure(ctx, ctx->a_scan_tmp, (scan_tmp_elems(n_tiles) + scan_tmp_elems(n_docs)) * 8));
+    CK(cudaMemsetAsync(ctx->a_wtable.p, 0, ((size_t)tcap + mcap) * sizeof(WordSlot), st));
     tile_doc_index_kernel<<<(n_tiles + 1 + 255) / 256, 256, 0, st>>>(d_doc_off, nd, n_tiles, (uint32_t*)ctx->a_tile_doc_lo.p); launches++;
-    OnePassArgs oa{};
-    oa.text = d_text; oa.n = N; oa.doc_off = d_doc_off; oa.n_docs = nd; oa.tile_doc_lo = (const uint32_t*)ctx->a_tile_doc_lo.p;
-    oa.table = (OpSlot*)ctx->a_optable.p; oa.table_mask = tcap - 1; oa.med_base = tcap; oa.med_mask = mcap - 1;
-    oa.upool = (unsigned long long*)ctx->a_upool.p; oa.upool_cap = (uint32_t)std::min<uint64_t>(upool_cap, ctx->a_upool.cap / 8); oa.upool_count = (unsigned int*)(ctrl + 9);
-    oa.lscratch = (uint32_t*)ctx->a_lscratch.p; oa.lscratch_cap = (uint32_t)ls_cap; oa.lscratch_count = (unsigned int*)(ctrl + 9) + 1;
-    oa.tile_state = (unsigned long long*)ctx->a_tile_state.p;
-    oa.ticket = (unsigned int*)(ctrl + 5); oa.abort_flag = (unsigned int*)(ctrl + 8); oa.errw = ctrl;
-    oa.n_words = ctrl + 10; oa.n_uniq = (unsigned int*)(ctrl + 6); oa.n_uncached = (unsigned int*)(ctrl + 6) + 1;
-    oa.cap = cap; oa.doc_tok_off = (unsigned long long*)ctx->O().doc_tok_off.p;
-    oa.o = EmitOut{(uint32_t*)ctx->O().ids.p, (uint32_t*)ctx->O().off.p, (uint32_t*)ctx->O().attn.p, (uint32_t*)ctx->O().type.p, (uint32_t*)ctx->O().special.p};
-    oa.outputs = P.outputs;
-    CK(cudaEventRecord(ctx->ev[1], st));
-    if (m.kind == TKZ_MODEL_BPE) launch_onepass<TKZ_MODEL_BPE>(m, oa, m.norm_identity != 0, ctx->has_iso, n_tiles, st);
-    else launch_onepass<TKZ_MODEL_WORDPIECE>(m, oa, m.norm_identity != 0, ctx->has_iso, n_tiles, st);
+    TileArgs ta{};
+    ta.text = d_text; ta.n = N; ta.doc_off = d_doc_off; ta.n_docs = nd; ta.tile_doc_lo = (const uint32_t*)ctx->a_tile_doc_lo.p;
+    ta.table = (WordSlot*)ctx->a_wtable.p; ta.table_mask = tcap - 1; ta.med_base = tcap; ta.med_mask = mcap - 1;
+    ta.upool = (unsigned long long*)ctx->a_upool.p; ta.upool_cap = (uint32_t)upool_cap; ta.upool_count = (unsigned int*)(ctrl + 9);
+    ta.lscratch = (uint32_t*)ctx->a_lscratch.p; ta.lscratch_cap = (uint32_t)ls_cap; ta.lscratch_count = (unsigned int*)(ctrl + 9) + 1;
+    ta.ent = (uint2*)ctx->a_ent.p; ta.ent_cap = (uint32_t)ent_cap; ta.ent_count = (unsigned int*)(ctrl + 5);
+    ta.tile_ent_off = (uint32_t*)ctx->a_tile_ent_off.p; ta.tile_nwords = (uint32_t*)ctx->a_tile_nwords.p; ta.tile_ntok = (uint32_t*)ctx->a_tile_ntok.p;
+    ta.doc_word_ref = (uint32_t*)ctx->a_doc_word_ref.p; ta.doc_tok_local = (uint32_t*)ctx->a_doc_tok_local.p;
+    ta.long_start = (uint32_t*)ctx->a_long_start.p; ta.long_end = (uint32_t*)ctx->a_long_end.p; ta.long_tile = (uint32_t*)ctx->a_long_tile.p;
+    ta.n_long = (unsigned int*)(ctrl + 7); ta.long_cap = long_cap;
+    ta.abort_flag = (unsigned int*)(ctrl + 8); ta.errw = ctrl;
+    ta.n_words = ctrl + 10; ta.n_uniq = (unsigned int*)(ctrl + 6); ta.n_uncached = (unsigned int*)(ctrl + 6) + 1;
+    if (m.kind == TKZ_MODEL_BPE) launch_tile_words<TKZ_MODEL_BPE>(m, ta, m.norm_identity != 0, ctx->has_iso, n_tiles, st);
+    else launch_tile_words<TKZ_MODEL_WORDPIECE>(m, ta, m.norm_identity != 0, ctx->has_iso, n_tiles, st);
     launches++;
-    CK(cudaGetLastError());
-    CK(cudaEventRecord(ctx->ev[4], st));
-    CK(cudaMemcpyAsync(hctrl, ctrl, 13 * 8, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(hctrl + 32, (unsigned long long*)ctx->a_tile_state.p + (n_tiles - 1), 8, cudaMemcpyDeviceToHost, st));
+    if (m.kind == TKZ_MODEL_BPE) { len_class_count_kernel<<<128, 256, 0, st>>>(ta.long_start, ta.long_end, 0, ta.n_long, ctrl + 13); launches++; }
+    CK(cudaMemcpyAsync(hctrl, ctrl, 16 * 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaEventRecord(ctx->ev[1], st));
     CK(cudaStreamSynchronize(st));
-    const uint32_t n_uniq = (uint32_t)hctrl[6], n_unc = (uint32_t)(hctrl[6] >> 32);
-    ctx->op_uniq_hist = std::max<uint64_t>(ctx->op_uniq_hist, n_uniq);
-    ctx->op_upool_hist = std::max<uint64_t>(ctx->op_upool_hist, (uint32_t)hctrl[9]);
+    const uint32_t n_uniq = (uint32_t)hctrl[6], n_unc = (uint32_t)(hctrl[6] >> 32), n_long = (uint32_t)hctrl[7];
+    ctx->tw_uniq_hist = std::max<uint64_t>(ctx->tw_uniq_hist, n_uniq);
+    ctx->tw_upool_hist = std::max<uint64_t>(ctx->tw_upool_hist, (uint32_t)hctrl[9]);
     if ((uint32_t)hctrl[8] != 0) {
-        // the history still helps the retry of a later batch: densest possible output next time
-        if ((hctrl[32] & OP_LB_VAL) > cap) ctx->tok_per_byte_hist = 1.0;
+        ctx->tw_words_per_byte = 1.0;                       // the retry of a later batch gets the worst-case entry list
         return TKZ_RETRY_MULTIPASS;
     }
-    const uint64_t T = hctrl[32] & OP_LB_VAL;
-    const unsigned long long errw = hctrl[0];
-    ctx->stats.n_words = hctrl[10]; ctx->stats.n_unique_words = n_uniq; ctx->stats.n_long_words = n_unc;
+    if (N) ctx->tw_words_per_byte = std::max(ctx->tw_words_per_byte, (double)hctrl[10] / (double)N);
+    ctx->stats.n_words = hctrl[10]; ctx->stats.n_unique_words = n_uniq + n_unc; ctx->stats.n_long_words = n_long;
     ctx->stats.path = 2;
-    if (errw != TKZ_ERRW_NONE) {
-        op_err_doc_kernel<<<1, 1, 0, st>>>(ctrl, d_doc_off, nd); launches++;
-        CK(cudaMemcpyAsync(hctrl + 4, ctrl + 4, 8, cudaMemcpyDeviceToHost, st));
-        CK(cudaStreamSynchronize(st));
+
+    // ---- the few pre-tokens longer than TW_MAX_INLINE bytes: per-occurrence word-list kernels, counts folded back in
+    TRY(ensure(ctx, ctx->a_long_ntok, ((size_t)n_long + 2) * 4));
+    if (n_long) {
+        TRY(ensure(ctx, ctx->a_pool_id, N * 4));
+        TRY(ensure(ctx, ctx->a_pool_s, N * 4));
+        TRY(ensure(ctx, ctx->a_pool_e, N * 4));
+        if (m.kind == TKZ_MODEL_BPE) {
+            TRY(launch_bpe(ctx, m, d_text, ta.long_start, ta.long_end, n_long, (uint32_t*)ctx->a_long_ntok.p, ctrl, 1, 1, hctrl + 13, N, launches));
+        } else {
+            WpArgs a{d_text, ta.long_start, ta.long_end, n_long, (uint32_t*)ctx->a_pool_id.p, (uint32_t*)ctx->a_pool_s.p, (uint32_t*)ctx->a_pool_e.p,
+                     (uint32_t*)ctx->a_long_ntok.p, (unsigned int*)(ctrl + 1), ctrl, 1};
+            uint64_t blocks = ((uint64_t)n_long + WP_WARPS - 1) / WP_WARPS;
+            const uint64_t cap = (uint64_t)ctx->sm_count * 8; if (blocks > cap) blocks = cap;
+            wordpiece_warp_kernel<<<(unsigned)blocks, WP_WARPS * 32, 0, st>>>(m, a); launches++;
+        }
+        long_fix_kernel<<<(n_long + 255) / 256, 256, 0, st>>>(ta.long_start, ta.long_tile, (const uint32_t*)ctx->a_long_ntok.p, n_long, ta.tile_doc_lo,
+                                                               d_doc_off, ta.tile_ntok, ta.doc_tok_local); launches++;
+    }
+    CK(cudaEventRecord(ctx->ev[2], st));
+
+    // ---- tokens per tile -> token base per tile; CSR offsets
+    EmitParams ep{P.has_truncation, P.max_length, P.has_padding, P.pad_length, P.pad_id, P.pad_type_id, P.pad_left, P.outputs};
+    launches += exclusive_scan<uint32_t>(ta.tile_ntok, n_tiles, ta.tile_ntok, (unsigned long long*)ctx->a_scan_tmp.p, st);
+    unsigned long long* doc_tok_off = (unsigned long long*)ctx->O().doc_tok_off.p;
+    if (!plain) {
+        TRY(ensure(ctx, ctx->a_doc_tok_start, (n_docs + 2) * 4));
+        TRY(ensure(ctx, ctx->a_doc_real, (n_docs + 2) * 4));
+        doc_finish2_kernel<<<(nd + 1 + 255) / 256, 256, 0, st>>>(d_doc_off, nd, ta.tile_ntok, ta.doc_tok_local, ep, (uint32_t*)ctx->a_doc_tok_start.p,
+                                                                  (uint32_t*)ctx->a_doc_real.p, doc_tok_off); launches++;
+        launches += exclusive_scan<unsigned long long>(doc_tok_off, n_docs, doc_tok_off, (unsigned long long*)ctx->a_scan_tmp.p, st);
+        CK(cudaMemcpyAsync(hctrl + 3, doc_tok_off + n_docs, 8, cudaMemcpyDeviceToHost, st));
+    }
+    CK(cudaMemcpyAsync(hctrl + 32, ta.tile_ntok + n_tiles, 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(hctrl, ctrl, 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    const uint64_t T_real = (uint32_t)hctrl[32], T = plain ? T_real : hctrl[3];
+    auto fail = [&](unsigned long long errw) -> int {
+        err_doc_kernel<<<1, 1, 0, st>>>(ctrl, d_doc_off, nd); launches++;
+        cudaMemcpyAsync(hctrl + 4, ctrl + 4, 8, cudaMemcpyDeviceToHost, st);
+        cudaStreamSynchronize(st);
         out->err_doc = (int64_t)hctrl[4];
         const uint32_t code = (uint32_t)(errw & 0xFF);
         ctx->err = code == TKZ_ECODE_UTF8 ? "invalid UTF-8 in a BPE pre-token (reference behaviour undefined)" : "MissingUnkToken";
         ctx->stats.kernel_launches = launches;
         return code == TKZ_ECODE_UTF8 ? TKZ_ERR_INVALID_UTF8 : TKZ_ERR_MISSING_UNK;
+    };
+    if (hctrl[0] != TKZ_ERRW_NONE && n_long == 0) return fail(hctrl[0]);   // (errors of long words surface in pass B)
+    CK(cudaEventRecord(ctx->ev[3], st));
+
+    // ---- pass B
+    TRY(ensure(ctx, ctx->O().ids, (T + 4) * 4));
+    if (P.outputs & TKZ_OUT_OFFSETS) TRY(ensure(ctx, ctx->O().off, (T + 4) * 8));
+    if (P.outputs & TKZ_OUT_ATTENTION) TRY(ensure(ctx, ctx->O().attn, (T + 4) * 4));
+    if (P.outputs & TKZ_OUT_TYPE_IDS) TRY(ensure(ctx, ctx->O().type, (T + 4) * 4));
+    if (P.outputs & TKZ_OUT_SPECIAL) TRY(ensure(ctx, ctx->O().special, (T + 4) * 4));
+    EmitOut eo{(uint32_t*)ctx->O().ids.p, (uint32_t*)ctx->O().off.p, (uint32_t*)ctx->O().attn.p, (uint32_t*)ctx->O().type.p,
+               (uint32_t*)ctx->O().special.p};
+    const uint32_t big_cap = (uint32_t)(N / EMIT_BIG + 16);
+    TRY(ensure(ctx, ctx->a_big, (size_t)big_cap * sizeof(uint4)));
+    TileEmitArgs ea{};
+    ea.doc_off = d_doc_off; ea.n_docs = nd; ea.tile_doc_lo = ta.tile_doc_lo;
+    ea.ent = ta.ent; ea.tile_ent_off = ta.tile_ent_off; ea.tile_nwords = ta.tile_nwords; ea.tile_tokbase = ta.tile_ntok;
+    ea.upool = ta.upool; ea.long_start = ta.long_start; ea.long_ntok = (const uint32_t*)ctx->a_long_ntok.p;
+    ea.pool_id = (const uint32_t*)ctx->a_pool_id.p; ea.pool_s = (const uint32_t*)ctx->a_pool_s.p; ea.pool_e = (const uint32_t*)ctx->a_pool_e.p;
+    ea.doc_word_ref = ta.doc_word_ref; ea.doc_tok_local = ta.doc_tok_local; ea.doc_tok_start = (const uint32_t*)ctx->a_doc_tok_start.p;
+    ea.doc_tok_off = doc_tok_off; ea.errw = ctrl; ea.err_code = m.kind == TKZ_MODEL_BPE ? TKZ_ECODE_UTF8 : TKZ_ECODE_UNK;
+    ea.big = BigList{(uint4*)ctx->a_big.p, (unsigned int*)(ctrl + 16), big_cap};
+    if (plain) tile_emit_kernel<true><<<n_tiles, TE_THREADS, 0, st>>>(ea, ep, eo);
+    else tile_emit_kernel<false><<<n_tiles, TE_THREADS, 0, st>>>(ea, ep, eo);
+    launches++;
+    if (n_long) { emit_big_kernel<<<ctx->sm_count * 4, 256, 0, st>>>(ep, eo, ea.big, ea.pool_id, ea.pool_s, ea.pool_e); launches++; }
+    if (P.has_padding && nd) {
+        emit_pad_real_kernel<<<(unsigned)(((uint64_t)nd * 32 + 255) / 256), 256, 0, st>>>(ep, eo, nd, (const uint32_t*)ctx->a_doc_real.p, doc_tok_off); launches++;
     }
-    if (N) ctx->tok_per_byte_hist = std::max(ctx->tok_per_byte_hist, (double)T / (double)N);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(ctx->ev[4], st));
+    if (n_long) CK(cudaMemcpyAsync(hctrl, ctrl, 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (hctrl[0] != TKZ_ERRW_NONE) return fail(hctrl[0]);
     ctx->stats.kernel_launches = launches;
     cudaEventElapsedTime(&ctx->stats.ms_split, ctx->ev[0], ctx->ev[1]);
-    ctx->stats.ms_model = 0.f; ctx->stats.ms_scan = 0.f;
-    cudaEventElapsedTime(&ctx->stats.ms_emit, ctx->ev[1], ctx->ev[4]);
+    cudaEventElapsedTime(&ctx->stats.ms_model, ctx->ev[1], ctx->ev[2]);
+    cudaEventElapsedTime(&ctx->stats.ms_scan, ctx->ev[2], ctx->ev[3]);
+    cudaEventElapsedTime(&ctx->stats.ms_emit, ctx->ev[3], ctx->ev[4]);
     cudaEventElapsedTime(&ctx->stats.ms_total, ctx->ev[0], ctx->ev[4]);
-    out->n_docs = n_docs; out->n_tokens = T; out->n_real_tokens = T;
-    out->doc_tok_off = (const uint64_t*)oa.doc_tok_off;
-    out->ids = oa.o.ids;
-    out->offsets = (P.outputs & TKZ_OUT_OFFSETS) ? oa.o.offsets : nullptr;
-    out->attention_mask = (P.outputs & TKZ_OUT_ATTENTION) ? oa.o.attention : nullptr;
-    out->type_ids = (P.outputs & TKZ_OUT_TYPE_IDS) ? oa.o.type_ids : nullptr;
-    out->special_tokens_mask = (P.outputs & TKZ_OUT_SPECIAL) ? oa.o.special : nullptr;
+    out->n_docs = n_docs; out->n_tokens = T; out->n_real_tokens = T_real;
+    out->doc_tok_off = (const uint64_t*)doc_tok_off;
+    out->ids = eo.ids;
+    out->offsets = (P.outputs & TKZ_OUT_OFFSETS) ? eo.offsets : nullptr;
+    out->attention_mask = (P.outputs & TKZ_OUT_ATTENTION) ? eo.attention : nullptr;
+    out->type_ids = (P.outputs & TKZ_OUT_TYPE_IDS) ? eo.type_ids : nullptr;
+    out->special_tokens_mask = (P.outputs & TKZ_OUT_SPECIAL) ? eo.special : nullptr;
     return TKZ_OK;
 }
 
@@ -857,8 +915,8 @@ int encode_device_impl(tkz_ctx* ctx, const uint8_t* d_text, const uint64_t* d_do
     // ---- dedup pipeline (tkz_dedup.cuh) whenever there is a pre-tokenizer; falls through to the per-occurrence
     //      pipeline below only if its long list overflowed (pathological: > N/16 long words)
     ctx->stats.path = m.has_pretok && ctx->use_dedup ? 1 : 0;
-    if (m.has_pretok && ctx->use_dedup && ctx->use_onepass && !P.has_truncation && !P.has_padding) {
-        int rc = encode_onepass(ctx, m, d_text, d_doc_off, nd, N, P, out, launches);
+    if (m.has_pretok && ctx->use_dedup && ctx->use_tiles) {
+        int rc = encode_tiles(ctx, m, d_text, d_doc_off, nd, N, P, out, launches);
         if (rc != TKZ_RETRY_MULTIPASS) return rc;
         ctx->stats.path = 1;
         ctrl_reset_kernel<<<1, 1, 0, st>>>(ctrl); launches++;

@@ -19,6 +19,7 @@
 #include "tkz_common.cuh"
 #include "tkz_emit.cuh"
 #include "tkz_split.cuh"
+#include "tkz_tiles.cuh"
 #include "tkz_wordpiece.cuh"
 
 namespace tkz {
@@ -67,18 +68,6 @@ struct DedupArgs {
     uint32_t* tile_words; uint32_t* tile_nwords; uint32_t* doc_word_ref;
     const uint32_t* tile_doc_lo;                  // first document with doc_off >= tile start (n_tiles + 1 entries)
 };
-
-// first document that starts at or after each tile start; entry n_tiles = n_docs + 1.  One thread per tile, so the
-// binary searches overlap instead of stalling a whole block behind thread 0.
-__global__ void tile_doc_index_kernel(const uint64_t* __restrict__ doc_off, uint32_t n_docs, uint32_t n_tiles, uint32_t* __restrict__ tile_doc_lo) {
-    const uint32_t tile = blockIdx.x * blockDim.x + threadIdx.x;
-    if (tile < n_tiles) tile_doc_lo[tile] = lower_bound_u64(doc_off, 0, n_docs + 1, (uint64_t)tile * 4096u);
-    else if (tile == n_tiles) tile_doc_lo[tile] = n_docs + 1;
-}
-
-// powers of the medium-word hash multiplier (host-initialised, see tkz_api.cu): PW[j] = HASH_MUL^j mod 2^64
-__constant__ unsigned long long c_med_pw[DT_MAX_MED];
-#define TKZ_MED_HASH_MUL 0x9E3779B97F4A7C15ULL
 
 struct DedupShared {
     uint32_t lut[256];                                 // [7:0] normalised byte, bit 8 WORD, bit 9 ISOLATE
@@ -650,27 +639,6 @@ __global__ void __launch_bounds__(DT_THREADS, 8) tile_emit_fused_kernel(TileOutA
     for (uint32_t d = d_lo + t; d < d_hi; d += DT_THREADS) {
         const uint32_t j = a.doc_word_ref[d] - tile * DT_WCAP;
         if (j >= nw) a.doc_tok_off[d] = base + tile_total;
-    }
-}
-
-// padding slots from per-document real counts (src/encoding.zig:407-414, 418-425), one warp per document
-__global__ void __launch_bounds__(256) emit_pad_real_kernel(EmitParams p, EmitOut o, uint32_t n_docs, const uint32_t* __restrict__ doc_real,
-                                                            const unsigned long long* __restrict__ doc_tok_off) {
-    const uint32_t d = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const uint32_t lane = lane_id();
-    if (d >= n_docs) return;
-    unsigned long long kept;
-    const unsigned long long olen = doc_out_len(p, doc_real[d], &kept);
-    if (olen == kept) return;
-    const unsigned long long base = doc_tok_off[d] + (p.pad_left ? 0 : kept);
-    const unsigned long long npad = olen - kept;
-    for (unsigned long long k = lane; k < npad; k += 32) {
-        const unsigned long long dst = base + k;
-        o.ids[dst] = p.pad_id;
-        if (p.outputs & 2u) reinterpret_cast<uint2*>(o.offsets)[dst] = make_uint2(0u, 0u);
-        if (p.outputs & 4u) o.attention[dst] = 0u;
-        if (p.outputs & 8u) o.type_ids[dst] = p.pad_type_id;
-        if (p.outputs & 16u) o.special[dst] = 1u;
     }
 }
 
