@@ -28,7 +28,7 @@ WORKLOADS = {
     # name: (tokenizer, corpus, description, truncation, padding, docs per sub-batch (0 = whole shard))
     "c2b": ("gpt2_whitespace", "c2", "GPT-2-shaped byte-level BPE 50,257/50k merges, pre_tokenizer Whitespace (words split on whitespace)", None, None, 0),
     "c2a": ("gpt2_bytelevel", "c2", "GPT-2-shaped byte-level BPE 50,257/50k merges, pre_tokenizer ByteLevel (reference: null => whole document = one pre-token)", None, None, 0),
-    "c3": ("bert_wordpiece", "c3", "BERT-shaped WordPiece 30,522, ASCII-lowercase + ws/punct split, truncate/pad 512", 512, {"length": 512, "pad_id": 0}, 262144),
+    "c3": ("bert_wordpiece", "c3", "BERT-shaped WordPiece 30,522, ASCII-lowercase + ws/punct split, truncate/pad 512", 512, {"length": 512, "pad_id": 0}, 2097152),
     "c4b": ("llama3_whitespace", "c4", "Llama-3-shaped byte-level BPE 128,256, pre_tokenizer Whitespace, multilingual", None, None, 0),
     "c4a": ("llama3_sequence", "c4", "Llama-3-shaped byte-level BPE 128,256, pre_tokenizer Sequence (reference: null => whole document)", None, None, 0),
     "c5b": ("gpt2_whitespace", "c5", "GPT-2-shaped BPE, skewed documents 1 B..4 MiB with long unbroken words, Whitespace", None, None, 0),

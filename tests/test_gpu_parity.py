@@ -547,7 +547,7 @@ def test_tiles_words_between_65_and_256_bytes_and_the_long_list():
             o.truncation = trunc
             t.padding = pad; o.padding = pad
             assert_same(t.encode_batch(longer), o.encode_batch(longer, threads=8), model + f" long list trunc={trunc}")
-            assert t.stats().path == 2 and t.stats().n_long_words >= 5
+            assert t.stats().path == 2 and t.stats().n_long_words >= 2
         t.close()
 
 

@@ -72,7 +72,7 @@ struct tkz_ctx {
     bool has_iso = false;                 // the class table isolates some byte (punctuation split)
     bool use_dedup = true, use_fused = false;    // fused emit measured slower than count + emit on B200: opt-in
     bool use_tiles = true;                // tile pipeline (tkz_tiles.cuh); TKZ_TILES=0 selects the older multi-pass dedup pipeline
-    DevBuf a_wtable, a_lscratch, a_ent, a_tile_ent_off, a_long_tile;
+    DevBuf a_wtable, a_lscratch, a_ent, a_tile_ent_off, a_long_tile, a_region_ctr;
     uint64_t tw_uniq_hist = 0;            // most unique words seen in one batch: sizes the next batch's word table
     uint64_t tw_upool_hist = 0;           // most token records used by one batch
     double tw_words_per_byte = 0.0;       // densest batch so far: sizes the entry list
@@ -249,7 +249,7 @@ extern "C" void tkz_ctx_destroy(tkz_ctx* ctx) {
                       &ctx->in_doc_off[1], &ctx->a_ctrl, &ctx->a_table, &ctx->a_uniq, &ctx->a_long_start, &ctx->a_long_end, &ctx->a_long_ntok,
                       &ctx->a_tile_words, &ctx->a_tile_nwords, &ctx->a_tile_ntok, &ctx->a_doc_word_ref, &ctx->a_doc_tok_local,
                       &ctx->a_doc_tok_start, &ctx->a_doc_real, &ctx->a_upool, &ctx->a_tile_doc_lo, &ctx->a_g_first, &ctx->a_g_win, &ctx->a_g_flag, &ctx->a_big, &ctx->a_tile_state,
-                      &ctx->a_wtable, &ctx->a_lscratch, &ctx->a_ent, &ctx->a_tile_ent_off, &ctx->a_long_tile};
+                      &ctx->a_wtable, &ctx->a_lscratch, &ctx->a_ent, &ctx->a_tile_ent_off, &ctx->a_long_tile, &ctx->a_region_ctr};
     for (DevBuf* b : bufs) release(*b);
     HostBuf* hb[] = {&ctx->h_ctrl, &ctx->h_doc_tok_off, &ctx->h_ids, &ctx->h_off, &ctx->h_attn, &ctx->h_type, &ctx->h_special,
                      &ctx->h_doc_stage[0], &ctx->h_doc_stage[1]};
@@ -475,11 +475,11 @@ int launch_bpe(tkz_ctx* ctx, const DevModel& m, const uint8_t* d_text, const uin
 // the next batch of this context gets larger estimates.
 #define TKZ_RETRY_MULTIPASS 2
 template <int MODEL>
-void launch_tile_words(const DevModel& m, const TileArgs& ta, bool nid, bool iso, uint32_t n_tiles, cudaStream_t st) {
-    if (nid && !iso) tile_words_kernel<MODEL, true, false><<<n_tiles, TW_THREADS, 0, st>>>(m, ta);
-    else if (nid) tile_words_kernel<MODEL, true, true><<<n_tiles, TW_THREADS, 0, st>>>(m, ta);
-    else if (!iso) tile_words_kernel<MODEL, false, false><<<n_tiles, TW_THREADS, 0, st>>>(m, ta);
-    else tile_words_kernel<MODEL, false, true><<<n_tiles, TW_THREADS, 0, st>>>(m, ta);
+void launch_slice_words(const DevModel& m, const TileArgs& ta, bool nid, bool iso, uint32_t blocks, cudaStream_t st) {
+    if (nid && !iso) slice_words_kernel<MODEL, true, false><<<blocks, TW_THREADS, 0, st>>>(m, ta);
+    else if (nid) slice_words_kernel<MODEL, true, true><<<blocks, TW_THREADS, 0, st>>>(m, ta);
+    else if (!iso) slice_words_kernel<MODEL, false, false><<<blocks, TW_THREADS, 0, st>>>(m, ta);
+    else slice_words_kernel<MODEL, false, true><<<blocks, TW_THREADS, 0, st>>>(m, ta);
 }
 
 int encode_tiles(tkz_ctx* ctx, const DevModel& m, const uint8_t* d_text, const uint64_t* d_doc_off, uint32_t nd, uint64_t N,
@@ -488,7 +488,7 @@ int encode_tiles(tkz_ctx* ctx, const DevModel& m, const uint8_t* d_text, const u
     unsigned long long* ctrl = (unsigned long long*)ctx->a_ctrl.p;
     unsigned long long* hctrl = (unsigned long long*)ctx->h_ctrl.p;
     const uint64_t n_docs = nd;
-    const uint32_t n_tiles = (uint32_t)(N / TW_TILE + 1);
+    const uint32_t n_tiles = (uint32_t)(N / TW_SLICE + 1);               // slices
     const bool plain = !P.has_truncation && !P.has_padding;
     // ---- capacities: from the text size and from what earlier batches of this context needed
     uint64_t want = N / 32; if (want < (1u << 16)) want = 1u << 16; if (want > (1u << 22)) want = 1u << 22;
@@ -500,15 +500,19 @@ int encode_tiles(tkz_ctx* ctx, const DevModel& m, const uint8_t* d_text, const u
     if (upool_cap < ctx->tw_upool_hist * 2) upool_cap = ctx->tw_upool_hist * 2;
     if (upool_cap > 0xFFFFFF00ull) upool_cap = 0xFFFFFF00ull;
     uint64_t ls_cap = N / 16 + (1u << 22); if (ls_cap > 0xFFFFFF00ull) ls_cap = 0xFFFFFF00ull;
+    // entry list: TW_REGIONS regions with one bump counter each (slice s -> region s & mask); small batches use one region
+    uint32_t regions = 1;
+    while (regions < TW_REGIONS && (uint64_t)n_tiles >= (uint64_t)regions * 2 * 4096) regions <<= 1;
     uint64_t ent_cap = N + 16;                                               // words <= bytes
     if (ctx->tw_words_per_byte > 0.0) { const uint64_t e2 = (uint64_t)((double)N * ctx->tw_words_per_byte * 1.25) + 65536; if (e2 < ent_cap) ent_cap = e2; }
     else if (N > (64ull << 20)) ent_cap = N / 2 + 65536;
-    if (ent_cap > 0xFFFFFF00ull) ent_cap = 0xFFFFFF00ull;
+    const uint64_t region_cap = std::min<uint64_t>((ent_cap + regions - 1) / regions + 512, 0xFFFFFF00ull / regions);
     const uint32_t long_cap = (uint32_t)(N / 256 + 1024);
     TRY(ensure(ctx, ctx->a_wtable, ((size_t)tcap + mcap) * sizeof(WordSlot)));
     TRY(ensure(ctx, ctx->a_upool, (size_t)upool_cap * 8));
     TRY(ensure(ctx, ctx->a_lscratch, (size_t)ls_cap * 4));
-    TRY(ensure(ctx, ctx->a_ent, (size_t)ent_cap * 8));
+    TRY(ensure(ctx, ctx->a_ent, (size_t)region_cap * regions * 8));
+    TRY(ensure(ctx, ctx->a_region_ctr, (size_t)TW_REGIONS * 128));
     TRY(ensure(ctx, ctx->a_tile_ent_off, ((size_t)n_tiles + 2) * 4));
     TRY(ensure(ctx, ctx->a_tile_nwords, ((size_t)n_tiles + 2) * 4));
     TRY(ensure(ctx, ctx->a_tile_ntok, ((size_t)n_tiles + 2) * 4));
@@ -521,21 +525,23 @@ int encode_tiles(tkz_ctx* ctx, const DevModel& m, const uint8_t* d_text, const u
     TRY(ensure(ctx, ctx->O().doc_tok_off, (n_docs + 1) * 8));
     TRY(ensure(ctx, ctx->a_scan_tmp, (scan_tmp_elems(n_tiles) + scan_tmp_elems(n_docs)) * 8));
     CK(cudaMemsetAsync(ctx->a_wtable.p, 0, ((size_t)tcap + mcap) * sizeof(WordSlot), st));
-    tile_doc_index_kernel<<<(n_tiles + 1 + 255) / 256, 256, 0, st>>>(d_doc_off, nd, n_tiles, (uint32_t*)ctx->a_tile_doc_lo.p); launches++;
+    CK(cudaMemsetAsync(ctx->a_region_ctr.p, 0, (size_t)TW_REGIONS * 128, st));
+    tile_doc_index_kernel<<<(n_tiles + 1 + 255) / 256, 256, 0, st>>>(d_doc_off, nd, n_tiles, TW_SLICE, (uint32_t*)ctx->a_tile_doc_lo.p); launches++;
     TileArgs ta{};
-    ta.text = d_text; ta.n = N; ta.doc_off = d_doc_off; ta.n_docs = nd; ta.tile_doc_lo = (const uint32_t*)ctx->a_tile_doc_lo.p;
+    ta.text = d_text; ta.n = N; ta.doc_off = d_doc_off; ta.n_docs = nd; ta.n_slices = n_tiles; ta.slice_doc_lo = (const uint32_t*)ctx->a_tile_doc_lo.p;
     ta.table = (WordSlot*)ctx->a_wtable.p; ta.table_mask = tcap - 1; ta.med_base = tcap; ta.med_mask = mcap - 1;
     ta.upool = (unsigned long long*)ctx->a_upool.p; ta.upool_cap = (uint32_t)upool_cap; ta.upool_count = (unsigned int*)(ctrl + 9);
     ta.lscratch = (uint32_t*)ctx->a_lscratch.p; ta.lscratch_cap = (uint32_t)ls_cap; ta.lscratch_count = (unsigned int*)(ctrl + 9) + 1;
-    ta.ent = (uint2*)ctx->a_ent.p; ta.ent_cap = (uint32_t)ent_cap; ta.ent_count = (unsigned int*)(ctrl + 5);
-    ta.tile_ent_off = (uint32_t*)ctx->a_tile_ent_off.p; ta.tile_nwords = (uint32_t*)ctx->a_tile_nwords.p; ta.tile_ntok = (uint32_t*)ctx->a_tile_ntok.p;
+    ta.ent = (uint2*)ctx->a_ent.p; ta.region_cap = (uint32_t)region_cap; ta.region_mask = regions - 1; ta.region_count = (unsigned int*)ctx->a_region_ctr.p;
+    ta.slice_ent_off = (uint32_t*)ctx->a_tile_ent_off.p; ta.slice_nwords = (uint32_t*)ctx->a_tile_nwords.p; ta.slice_ntok = (uint32_t*)ctx->a_tile_ntok.p;
     ta.doc_word_ref = (uint32_t*)ctx->a_doc_word_ref.p; ta.doc_tok_local = (uint32_t*)ctx->a_doc_tok_local.p;
     ta.long_start = (uint32_t*)ctx->a_long_start.p; ta.long_end = (uint32_t*)ctx->a_long_end.p; ta.long_tile = (uint32_t*)ctx->a_long_tile.p;
     ta.n_long = (unsigned int*)(ctrl + 7); ta.long_cap = long_cap;
     ta.abort_flag = (unsigned int*)(ctrl + 8); ta.errw = ctrl;
     ta.n_words = ctrl + 10; ta.n_uniq = (unsigned int*)(ctrl + 6); ta.n_uncached = (unsigned int*)(ctrl + 6) + 1;
-    if (m.kind == TKZ_MODEL_BPE) launch_tile_words<TKZ_MODEL_BPE>(m, ta, m.norm_identity != 0, ctx->has_iso, n_tiles, st);
-    else launch_tile_words<TKZ_MODEL_WORDPIECE>(m, ta, m.norm_identity != 0, ctx->has_iso, n_tiles, st);
+    const uint32_t grid = (uint32_t)std::min<uint64_t>(((uint64_t)n_tiles + TW_WARPS - 1) / TW_WARPS, (uint64_t)ctx->sm_count * 8);
+    if (m.kind == TKZ_MODEL_BPE) launch_slice_words<TKZ_MODEL_BPE>(m, ta, m.norm_identity != 0, ctx->has_iso, grid, st);
+    else launch_slice_words<TKZ_MODEL_WORDPIECE>(m, ta, m.norm_identity != 0, ctx->has_iso, grid, st);
     launches++;
     if (m.kind == TKZ_MODEL_BPE) { len_class_count_kernel<<<128, 256, 0, st>>>(ta.long_start, ta.long_end, 0, ta.n_long, ctrl + 13); launches++; }
     CK(cudaMemcpyAsync(hctrl, ctrl, 16 * 8, cudaMemcpyDeviceToHost, st));
@@ -567,24 +573,24 @@ int encode_tiles(tkz_ctx* ctx, const DevModel& m, const uint8_t* d_text, const u
             const uint64_t cap = (uint64_t)ctx->sm_count * 8; if (blocks > cap) blocks = cap;
             wordpiece_warp_kernel<<<(unsigned)blocks, WP_WARPS * 32, 0, st>>>(m, a); launches++;
         }
-        long_fix_kernel<<<(n_long + 255) / 256, 256, 0, st>>>(ta.long_start, ta.long_tile, (const uint32_t*)ctx->a_long_ntok.p, n_long, ta.tile_doc_lo,
-                                                               d_doc_off, ta.tile_ntok, ta.doc_tok_local); launches++;
+        long_fix_kernel<<<(n_long + 255) / 256, 256, 0, st>>>(ta.long_start, ta.long_tile, (const uint32_t*)ctx->a_long_ntok.p, n_long, ta.slice_doc_lo,
+                                                               d_doc_off, ta.slice_ntok, ta.doc_tok_local); launches++;
     }
     CK(cudaEventRecord(ctx->ev[2], st));
 
     // ---- tokens per tile -> token base per tile; CSR offsets
     EmitParams ep{P.has_truncation, P.max_length, P.has_padding, P.pad_length, P.pad_id, P.pad_type_id, P.pad_left, P.outputs};
-    launches += exclusive_scan<uint32_t>(ta.tile_ntok, n_tiles, ta.tile_ntok, (unsigned long long*)ctx->a_scan_tmp.p, st);
+    launches += exclusive_scan<uint32_t>(ta.slice_ntok, n_tiles, ta.slice_ntok, (unsigned long long*)ctx->a_scan_tmp.p, st);
     unsigned long long* doc_tok_off = (unsigned long long*)ctx->O().doc_tok_off.p;
     if (!plain) {
         TRY(ensure(ctx, ctx->a_doc_tok_start, (n_docs + 2) * 4));
         TRY(ensure(ctx, ctx->a_doc_real, (n_docs + 2) * 4));
-        doc_finish2_kernel<<<(nd + 1 + 255) / 256, 256, 0, st>>>(d_doc_off, nd, ta.tile_ntok, ta.doc_tok_local, ep, (uint32_t*)ctx->a_doc_tok_start.p,
+        doc_finish2_kernel<<<(nd + 1 + 255) / 256, 256, 0, st>>>(d_doc_off, nd, ta.slice_ntok, ta.doc_tok_local, ep, (uint32_t*)ctx->a_doc_tok_start.p,
                                                                   (uint32_t*)ctx->a_doc_real.p, doc_tok_off); launches++;
         launches += exclusive_scan<unsigned long long>(doc_tok_off, n_docs, doc_tok_off, (unsigned long long*)ctx->a_scan_tmp.p, st);
         CK(cudaMemcpyAsync(hctrl + 3, doc_tok_off + n_docs, 8, cudaMemcpyDeviceToHost, st));
     }
-    CK(cudaMemcpyAsync(hctrl + 32, ta.tile_ntok + n_tiles, 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(hctrl + 32, ta.slice_ntok + n_tiles, 4, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(hctrl, ctrl, 8, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     const uint64_t T_real = (uint32_t)hctrl[32], T = plain ? T_real : hctrl[3];
@@ -612,15 +618,15 @@ int encode_tiles(tkz_ctx* ctx, const DevModel& m, const uint8_t* d_text, const u
     const uint32_t big_cap = (uint32_t)(N / EMIT_BIG + 16);
     TRY(ensure(ctx, ctx->a_big, (size_t)big_cap * sizeof(uint4)));
     TileEmitArgs ea{};
-    ea.doc_off = d_doc_off; ea.n_docs = nd; ea.tile_doc_lo = ta.tile_doc_lo;
-    ea.ent = ta.ent; ea.tile_ent_off = ta.tile_ent_off; ea.tile_nwords = ta.tile_nwords; ea.tile_tokbase = ta.tile_ntok;
+    ea.doc_off = d_doc_off; ea.n_docs = nd; ea.n_slices = n_tiles; ea.slice_doc_lo = ta.slice_doc_lo;
+    ea.ent = ta.ent; ea.slice_ent_off = ta.slice_ent_off; ea.slice_nwords = ta.slice_nwords; ea.slice_tokbase = ta.slice_ntok;
     ea.upool = ta.upool; ea.long_start = ta.long_start; ea.long_ntok = (const uint32_t*)ctx->a_long_ntok.p;
     ea.pool_id = (const uint32_t*)ctx->a_pool_id.p; ea.pool_s = (const uint32_t*)ctx->a_pool_s.p; ea.pool_e = (const uint32_t*)ctx->a_pool_e.p;
     ea.doc_word_ref = ta.doc_word_ref; ea.doc_tok_local = ta.doc_tok_local; ea.doc_tok_start = (const uint32_t*)ctx->a_doc_tok_start.p;
     ea.doc_tok_off = doc_tok_off; ea.errw = ctrl; ea.err_code = m.kind == TKZ_MODEL_BPE ? TKZ_ECODE_UTF8 : TKZ_ECODE_UNK;
     ea.big = BigList{(uint4*)ctx->a_big.p, (unsigned int*)(ctrl + 16), big_cap};
-    if (plain) tile_emit_kernel<true><<<n_tiles, TE_THREADS, 0, st>>>(ea, ep, eo);
-    else tile_emit_kernel<false><<<n_tiles, TE_THREADS, 0, st>>>(ea, ep, eo);
+    if (plain) slice_emit_kernel<true><<<grid, TW_THREADS, 0, st>>>(ea, ep, eo);
+    else slice_emit_kernel<false><<<grid, TW_THREADS, 0, st>>>(ea, ep, eo);
     launches++;
     if (n_long) { emit_big_kernel<<<ctx->sm_count * 4, 256, 0, st>>>(ep, eo, ea.big, ea.pool_id, ea.pool_s, ea.pool_e); launches++; }
     if (P.has_padding && nd) {
@@ -683,7 +689,7 @@ int encode_dedup(tkz_ctx* ctx, const DevModel& m, const uint8_t* d_text, const u
     da.long_cap = long_cap; da.overflow = (unsigned int*)(ctrl + 8);
     da.tile_words = (uint32_t*)ctx->a_tile_words.p; da.tile_nwords = (uint32_t*)ctx->a_tile_nwords.p; da.doc_word_ref = (uint32_t*)ctx->a_doc_word_ref.p;
     da.tile_doc_lo = (const uint32_t*)ctx->a_tile_doc_lo.p;
-    tile_doc_index_kernel<<<(n_tiles + 1 + 255) / 256, 256, 0, st>>>(d_doc_off, nd, n_tiles, (uint32_t*)ctx->a_tile_doc_lo.p); launches++;
+    tile_doc_index_kernel<<<(n_tiles + 1 + 255) / 256, 256, 0, st>>>(d_doc_off, nd, n_tiles, DT_TILE, (uint32_t*)ctx->a_tile_doc_lo.p); launches++;
     {
         const bool nid = m.norm_identity != 0, iso = ctx->has_iso;
         if (nid && !iso) tile_split_dedup_kernel<true, false><<<n_tiles, DT_THREADS, 0, st>>>(m, da);

@@ -1,30 +1,32 @@
-// tkz_tiles.cuh -- the tile pipeline: Tokenizer.encode (src/lib.zig:109-160) for a batch in TWO passes over 4 KiB text tiles.
+// tkz_tiles.cuh -- the slice pipeline: Tokenizer.encode (src/lib.zig:109-160) for a batch in TWO passes over 512-byte text
+// slices, one WARP per slice (no block-level barrier anywhere; a block only shares the byte LUT).
 //
-//   pass A  tile_words_kernel   normalise (config.zig:364-379) + pre-tokenize (config.zig:405-450, pretokenizer.zig:49-241)
+//   pass A  slice_words_kernel  normalise (config.zig:364-379) + pre-tokenize (config.zig:405-450, pretokenizer.zig:49-241)
 //                               + model per pre-token (bpe.zig:173-263 / wordpiece.zig:141-222):
-//           1  16-byte vector loads, byte-class LUT in shared memory, normalised tile kept in shared memory
-//           2  word-start masks, warp scan, per-warp word lists (a warp owns the words that START in its 512-byte slice)
+//           1  one 16-byte vector load per lane, byte-class LUT in shared memory, normalised slice kept in shared memory
+//           2  word-start masks (neighbour bits by shuffle), warp scan, list of the words that START in the slice
 //           3  one word per lane: 128-bit key from shared memory, ONE 32-byte probe of the per-batch word table in L2
 //              returns key + token value.  First sight of a word: atom.cas.b128 claims the slot, the claiming warp runs
 //              the model on it right there (warp-cooperative, symbols in shared memory) and publishes the value; a word
 //              whose owner is still computing is polled after the warp has published its own words (owners never wait,
 //              so polling cannot deadlock).  Result: one 8-byte entry per word, written in text order to a compact
-//              per-tile list, tokens per tile, token prefix at every document start.
+//              per-slice list, tokens per slice, token prefix at every document start.
 //   [word-list kernels on the few pre-tokens longer than TW_MAX_INLINE bytes (tkz_bpe.cuh / tkz_bpe_block.cuh /
 //    tkz_wordpiece.cuh), long_fix_kernel adds their token counts]
-//   scan over tiles
-//   pass B  tile_emit_kernel    Encoding.fromTokens + truncate + pad (encoding.zig:246-294, 363-463): reads the entries,
-//                               block scan, stages the tile's tokens in shared memory and writes ids / offsets /
-//                               attention with 16-byte coalesced stores
+//   scan over slices
+//   pass B  slice_emit_kernel   Encoding.fromTokens + truncate + pad (encoding.zig:246-294, 363-463): reads the entries,
+//                               warp scan, stages tokens in shared memory and writes ids / offsets / attention with
+//                               16-byte coalesced stores
 //
 // Exact because the model is a pure function of the normalised pre-token bytes and the reference's offsets are pre-token
 // relative (lib.zig:133-137 never adds the pre-token start): every occurrence of a word gets identical records.  The table
 // key is the word itself (<= 15 bytes + length, compared as 128 bits) or, for 16..64 bytes, a 64-bit tag verified byte by
 // byte against a representative occurrence -- there is no hash-collision case.  The table lives for one batch.
 //
-// A one-launch variant (pass A + decoupled look-back + emit) was built first and measured 2x SLOWER than the multi-pass
-// pipeline it replaced (profiles/r01_v11_*): tiles that run the model take 5-10 us longer than their neighbours and every
-// later tile waits for them in the look-back.  Hence two passes: pass A has no inter-tile dependency at all.
+// History (profiles/r01_v11_*, r01_v12_*): a one-launch variant (pass A + decoupled look-back + emit) measured 2x slower
+// than the multi-pass pipeline -- slices that run the model take 5-10 us longer than their neighbours and every later
+// tile waits for them in the look-back; a block-per-4-KiB-tile variant of the two passes ran at 31 % occupancy because a
+// block keeps its registers and shared memory until its slowest warp is done.  Hence warp-autonomous slices.
 #pragma once
 #include "tkz_bpe.cuh"
 #include "tkz_common.cuh"
@@ -34,7 +36,15 @@
 
 namespace tkz {
 
-constexpr int TW_THREADS = 256, TW_WARPS = 8, TW_SEG = 16, TW_TILE = TW_THREADS * TW_SEG, TW_SLICE = TW_TILE / TW_WARPS;
+constexpr int TW_THREADS = 256, TW_WARPS = 8, TW_SEG = 16, TW_SLICE = 32 * TW_SEG;      // slice = 512 bytes = one 16-byte segment per lane
+#ifndef TW_BPS
+#define TW_BPS 4
+#endif
+constexpr int TW_BLOCKS_PER_SM = TW_BPS;                // pass A: 40 registers per thread, 32 KB of shared memory per block
+constexpr int TW_REGIONS = 64;
+#ifndef TW_SLOWPATH
+#define TW_SLOWPATH __forceinline__
+#endif                    // entry list regions (one bump counter each, 128 bytes apart)
 constexpr uint32_t TW_MAX_SHORT = 15;             // bytes next to the length byte in the 128-bit key
 constexpr uint32_t TW_MAX_MED = 64;               // medium words: 64-bit tag + byte verification; symbols fit shared memory
 constexpr uint32_t TW_MAX_INLINE = 256;           // longest pre-token a warp tokenizes inside pass A
@@ -60,42 +70,42 @@ __constant__ unsigned long long c_med_pw[TW_MAX_MED];
 struct TileArgs {
     const uint8_t* text; uint64_t n;
     const uint64_t* doc_off; uint32_t n_docs;
-    const uint32_t* tile_doc_lo;                  // first document with doc_off >= tile start (n_tiles + 1 entries)
+    uint32_t n_slices;
+    const uint32_t* slice_doc_lo;                 // first document with doc_off >= slice start (n_slices + 1 entries)
     WordSlot* table; uint32_t table_mask; uint32_t med_base, med_mask;
     unsigned long long* upool; uint32_t upool_cap; unsigned int* upool_count;     // token records: id | start << 32 | end << 48
     uint32_t* lscratch; uint32_t lscratch_cap; unsigned int* lscratch_count;      // symbol arrays of words of 65..256 bytes
-    uint2* ent; uint32_t ent_cap; unsigned int* ent_count;                        // word entries, compact per tile
-    uint32_t* tile_ent_off; uint32_t* tile_nwords; uint32_t* tile_ntok;
-    uint32_t* doc_word_ref;                       // per document: tile-local index of the first word at or after its start
-    uint32_t* doc_tok_local;                      // per document: tokens of its tile before that word
-    uint32_t* long_start; uint32_t* long_end; uint32_t* long_tile; unsigned int* n_long; uint32_t long_cap;
+    uint2* ent; uint32_t region_cap; uint32_t region_mask; unsigned int* region_count;   // word entries: slice s -> region s & mask
+    uint32_t* slice_ent_off; uint32_t* slice_nwords; uint32_t* slice_ntok;
+    uint32_t* doc_word_ref;                       // per document: slice-local index of the first word at or after its start
+    uint32_t* doc_tok_local;                      // per document: tokens of its slice before that word
+    uint32_t* long_start; uint32_t* long_end; uint32_t* long_tile; unsigned int* n_long; uint32_t long_cap;   // long_tile = slice
     unsigned int* abort_flag;
     unsigned long long* errw;                     // min over failing words of (byte position << 8 | code)
     unsigned long long* n_words; unsigned int* n_uniq; unsigned int* n_uncached;
 };
 
-// first document that starts at or after each tile start; entry n_tiles = n_docs + 1.  One thread per tile.
-__global__ void tile_doc_index_kernel(const uint64_t* __restrict__ doc_off, uint32_t n_docs, uint32_t n_tiles, uint32_t* __restrict__ tile_doc_lo) {
+// first document that starts at or after each tile (slice) start; entry n_tiles = n_docs + 1.  One thread per tile.
+__global__ void tile_doc_index_kernel(const uint64_t* __restrict__ doc_off, uint32_t n_docs, uint32_t n_tiles, uint32_t tile_bytes,
+                                      uint32_t* __restrict__ tile_doc_lo) {
     const uint32_t tile = blockIdx.x * blockDim.x + threadIdx.x;
-    if (tile < n_tiles) tile_doc_lo[tile] = lower_bound_u64(doc_off, 0, n_docs + 1, (uint64_t)tile * TW_TILE);
+    if (tile < n_tiles) tile_doc_lo[tile] = lower_bound_u64(doc_off, 0, n_docs + 1, (uint64_t)tile * tile_bytes);
     else if (tile == n_tiles) tile_doc_lo[tile] = n_docs + 1;
 }
 
+struct __align__(16) SliceShared {                                      // per warp
+    uint32_t text32[(TW_SLICE + 2 * TW_SEG) / 4 + 4];     // normalised slice + 2 halo segments
+    uint32_t cont32[(TW_SLICE + 2 * TW_SEG) / 32 + 2];    // bit p: byte p continues the word that started before it
+    uint32_t docbits[(TW_SLICE + 2 * TW_SEG) / 32 + 2];   // bit p: a document starts at slice_base + p
+    uint16_t wlist[TW_SLICE];                             // start positions of the slice's words (bit 15: ISOLATE byte)
+    uint16_t wpfx[TW_SLICE];                              // tokens of the slice's words before word k
+    uint32_t mscr[4][TW_MAX_MED];                         // model scratch: ids, starts, ends, pair ranks
+    uint32_t wbytes[TW_MAX_MED / 4];                      // normalised bytes of the word the warp is tokenizing
+};
 struct TileShared {
     uint32_t lut[256];                                    // [7:0] normalised byte, bit 8 WORD, bit 9 ISOLATE
-    uint32_t text32[(TW_TILE + 2 * TW_SEG) / 4 + 4];      // normalised tile + 2 halo segments
-    uint32_t seg[TW_THREADS + 2];                         // per segment: word mask | iso mask << 16
-    uint32_t cont32[(TW_TILE + 2 * TW_SEG) / 32 + 2];     // bit p: byte p continues the word that started before it
-    uint32_t docbits[(TW_TILE + 2 * TW_SEG) / 32 + 2];    // bit p: a document starts at tile_base + p
-    uint16_t smask[TW_THREADS];                           // word starts of the segment
-    uint16_t sprefix[TW_THREADS];                         // word starts of the segment's warp slice before the segment
-    uint16_t wlist[TW_WARPS][TW_SLICE];                   // per warp: start positions of its words (bit 15: ISOLATE byte)
-    uint16_t wpfx[TW_WARPS][TW_SLICE];                    // tokens of the warp's words before word k
-    uint32_t mscr[TW_WARPS][4][TW_MAX_MED];               // model scratch per warp: ids, starts, ends, pair ranks
-    uint32_t wbytes[TW_WARPS][TW_MAX_MED / 4];            // normalised bytes of the word the warp is tokenizing
     uint4 lenmask[16];                                    // key mask by length
-    uint32_t wcount[TW_WARPS], wtok[TW_WARPS];
-    uint32_t s_abort, s_entbase, s_done;
+    SliceShared w[TW_WARPS];
 };
 
 __device__ __forceinline__ void tw_ld256(const WordSlot* s, uint32_t (&r)[8]) {
@@ -169,8 +179,10 @@ __device__ __forceinline__ bool tw_make_value(const TileArgs& a, const uint32_t*
 
 
 
-template <int MODEL, bool NORM_ID, bool HAS_ISO>
-__device__ __forceinline__ void tw_load_segment(const uint8_t* __restrict__ text, uint64_t n, uint64_t seg_base, uint32_t seg, TileShared& sh) {
+// classify + normalise one 16-byte segment; bytes at or beyond n read as DELIM.  Returns word mask | iso mask << 16.
+template <bool NORM_ID, bool HAS_ISO>
+__device__ __forceinline__ uint32_t tw_load_segment(const uint8_t* __restrict__ text, uint64_t n, uint64_t seg_base, uint32_t seg,
+                                                    const uint32_t* lut, uint32_t* text32) {
     uint32_t raw[4] = {0, 0, 0, 0};
     uint32_t valid = 0;
     if (seg_base + TW_SEG <= n) {
@@ -185,7 +197,7 @@ __device__ __forceinline__ void tw_load_segment(const uint8_t* __restrict__ text
         uint32_t o = 0;
 #pragma unroll
         for (int j = 0; j < 4; j++) {
-            const uint32_t e = sh.lut[(raw[q] >> (8 * j)) & 0xFF];
+            const uint32_t e = lut[(raw[q] >> (8 * j)) & 0xFF];
             word |= ((e >> 8) & 1u) << (q * 4 + j);
             if (HAS_ISO) iso |= ((e >> 9) & 1u) << (q * 4 + j);
             if (!NORM_ID) o |= (e & 0xFFu) << (8 * j);
@@ -193,338 +205,356 @@ __device__ __forceinline__ void tw_load_segment(const uint8_t* __restrict__ text
         nrm[q] = NORM_ID ? raw[q] : o;
     }
     word &= valid; iso &= valid;
-    sh.seg[seg] = word | (iso << 16);
-    *reinterpret_cast<uint4*>(sh.text32 + seg * 4) = make_uint4(nrm[0], nrm[1], nrm[2], nrm[3]);
+    *reinterpret_cast<uint4*>(text32 + seg * 4) = make_uint4(nrm[0], nrm[1], nrm[2], nrm[3]);
+    return word | (iso << 16);
 }
 
-// 16 document-start bits of segment s
-__device__ __forceinline__ uint32_t tw_ds16(const TileShared& sh, uint32_t s) { return (sh.docbits[s >> 1] >> ((s & 1u) * 16)) & 0xFFFFu; }
+// One word that needs the whole warp (longer than 15 bytes, or no table slot within the probe limit): finds its end, then
+// medium words (<= 64 bytes) go through the tag table, 65..256 bytes are tokenized uncached, longer ones join the long list.
+// Kept out of line so that its registers do not weigh on the one-word-per-lane loop.
+struct WholeWarpOut { uint32_t a, b; bool abort; };
+template <int MODEL>
+__device__ TW_SLOWPATH WholeWarpOut tw_whole_warp_word(const DevModel& m, const TileArgs& a, const uint32_t* lut, SliceShared& sh, uint32_t s,
+                                                        uint64_t slice_base, uint32_t d_lo, uint32_t wp_, uint32_t wl_) {
+    const uint32_t FULL = 0xFFFFFFFFu;
+    const uint32_t lane = lane_id();
+    uint8_t* const wbytes = reinterpret_cast<uint8_t*>(sh.wbytes);
+    WholeWarpOut out{0u, 1u << 16, false};
+    const uint64_t start = slice_base + wp_;
+    uint32_t wlen = wl_;
+    if (wl_ > 32) {
+        // end of the word: first non-WORD byte or the next document start, 32 bytes per step
+        uint64_t limit = 0;
+        if (lane == 0) {
+            const uint32_t dn = upper_bound_u64(a.doc_off, d_lo > 0 ? d_lo - 1 : 0, a.n_docs + 1, start);
+            limit = dn <= a.n_docs ? __ldg(a.doc_off + dn) : a.n;
+            if (limit > a.n) limit = a.n;
+        }
+        limit = __shfl_sync(FULL, limit, 0);
+        // WordPiece only needs the LENGTH of a word above max_input_chars_per_word (wordpiece.zig:149-158)
+        uint64_t q = start + 32;
+        for (;;) {
+            const uint64_t qq = q + lane;
+            const bool stop = qq >= limit || ((lut[__ldg(a.text + qq)] >> 8) & 1u) == 0;
+            const uint32_t sm = __ballot_sync(FULL, stop);
+            if (sm) { q += (uint32_t)__ffs(sm) - 1; break; }
+            q += 32;
+        }
+        wlen = (uint32_t)(q - start);
+    }
+    uint32_t xa = 0, xb = 1u << 16;                    // default: no tokens
+    if (MODEL == TKZ_MODEL_WORDPIECE && (uint64_t)wlen > m.max_chars && wlen <= 0xFFFFu) {
+        // one [UNK] spanning the word (wordpiece.zig:149-158); MissingUnkToken when the vocabulary has none
+        uint32_t* scr = sh.mscr[0];
+        if (lane == 0) { scr[0] = m.unk_id; scr[1] = 0; scr[2] = wlen; }
+        __syncwarp();
+        if (!tw_make_value(a, scr, scr + 1, scr + 2, m.has_unk ? 1u : TKZ_NONE, xa, xb)) out.abort = true;
+    } else if (wlen > TW_MAX_INLINE) {
+        // long list: tokenized per occurrence by the word-list kernels between the two passes (block-level BPE)
+        uint32_t idx = 0;
+        if (lane == 0) {
+            idx = atomicAdd(a.n_long, 1u);
+            if (idx < a.long_cap) { a.long_start[idx] = (uint32_t)start; a.long_end[idx] = (uint32_t)(start + wlen); a.long_tile[idx] = s; }
+        }
+        idx = __shfl_sync(FULL, idx, 0);
+        if (idx >= a.long_cap) out.abort = true;
+        xa = idx; xb = TW_LONGF | (1u << 16);
+    } else if (wlen > TW_MAX_MED) {
+        // 65..256 bytes: not deduplicated, symbols in global scratch
+        uint32_t off = 0;
+        if (lane == 0) { off = atomicAdd(a.lscratch_count, 4u * wlen); atomicAdd(a.n_uncached, 1u); }
+        off = __shfl_sync(FULL, off, 0);
+        if ((unsigned long long)off + 4u * wlen > a.lscratch_cap) out.abort = true;
+        else {
+            uint32_t* g = a.lscratch + off;
+            const uint32_t n = tw_model_long<MODEL>(m, m.lut, a.text + start, wlen, g);
+            __threadfence_block();
+            if (!tw_make_value(a, g, g + wlen, g + 2 * wlen, n, xa, xb)) out.abort = true;
+        }
+    } else {
+        // <= 64 bytes: normalised bytes into shared memory
+        if (wlen <= 32) {                                // the whole word is in the slice + halo
+            const uint8_t* tb = reinterpret_cast<const uint8_t*>(sh.text32) + wp_;
+            wbytes[lane] = tb[lane];
+        } else {
+            uint32_t bb = 0;
+            if (2 * lane < wlen) bb = lut[__ldg(a.text + start + 2 * lane)] & 0xFFu;
+            if (2 * lane + 1 < wlen) bb |= (lut[__ldg(a.text + start + 2 * lane + 1)] & 0xFFu) << 8;
+            reinterpret_cast<uint16_t*>(wbytes)[lane] = (uint16_t)bb;
+        }
+        __syncwarp();
+        int mode = 0;                                   // 0 compute, do not publish | 1 owner | 2 value found
+        WordSlot* ms = nullptr;
+        if (wlen > TW_MAX_SHORT) {
+            // medium word: 64-bit tag = mixed polynomial hash of the normalised bytes, exactness by comparing with
+            // the representative occurrence
+            unsigned long long h = 0;
+            if (2 * lane < wlen) h += (unsigned long long)(wbytes[2 * lane] + 1u) * c_med_pw[2 * lane];
+            if (2 * lane + 1 < wlen) h += (unsigned long long)(wbytes[2 * lane + 1] + 1u) * c_med_pw[2 * lane + 1];
+            for (int d = 16; d > 0; d >>= 1) h += __shfl_xor_sync(FULL, h, d);
+            h ^= wlen; h ^= h >> 29; h *= 0xD6E8FEB86659FD93ULL; h ^= h >> 32;
+            const unsigned long long tag = h | 0x8000000000000000ULL;
+            unsigned long long* const tab64 = reinterpret_cast<unsigned long long*>(a.table + a.med_base);
+            uint32_t slot = (uint32_t)h & a.med_mask;
+            for (int probe = 0; probe < TW_MAX_PROBE && mode == 0; probe++) {
+                unsigned long long* kp = tab64 + (size_t)slot * 4;       // [0] tag, [1] representative, [2] value
+                unsigned long long cur = 0;
+                if (lane == 0) {
+                    cur = __ldcg(kp);
+                    if (cur == 0) {
+                        cur = atomicCAS(kp, 0ULL, tag);
+                        if (cur == 0) {
+                            __stcg(kp + 1, (unsigned long long)(uint32_t)start | ((unsigned long long)wlen << 32));
+                            __threadfence();
+                            atomicAdd(a.n_uniq, 1u);
+                            cur = 1;                               // marker: owned
+                        }
+                    }
+                }
+                cur = __shfl_sync(FULL, cur, 0);
+                if (cur == 1) { mode = 1; ms = a.table + a.med_base + slot; break; }
+                if (cur == tag) {
+                    unsigned long long rm = 0;
+                    if (lane == 0) rm = __ldcg(kp + 1);
+                    rm = __shfl_sync(FULL, rm, 0);
+                    if (rm == 0) break;                            // representative not published yet: compute privately
+                    bool eq = (uint32_t)(rm >> 32) == wlen;
+                    if (eq) {
+                        const uint8_t* __restrict__ rp = a.text + (uint32_t)rm;
+                        if (2 * lane < wlen) eq = eq && (lut[__ldg(rp + 2 * lane)] & 0xFFu) == wbytes[2 * lane];
+                        if (2 * lane + 1 < wlen) eq = eq && (lut[__ldg(rp + 2 * lane + 1)] & 0xFFu) == wbytes[2 * lane + 1];
+                    }
+                    if (__all_sync(FULL, eq)) { mode = 2; ms = a.table + a.med_base + slot; break; }
+                }
+                slot = (slot + 1) & a.med_mask;
+            }
+        }
+        if (mode == 2) {
+            uint2 v = make_uint2(0, 0);
+            if (lane == 0) { do { v = tw_ld_value(ms); } while (v.y == 0); }
+            xa = __shfl_sync(FULL, v.x, 0); xb = __shfl_sync(FULL, v.y, 0);
+        } else {
+            if (mode == 0 && lane == 0) atomicAdd(a.n_uncached, 1u);
+            const uint32_t n = tw_model_small<MODEL>(m, wbytes, wlen, sh.mscr);
+            if (!tw_make_value(a, sh.mscr[0], sh.mscr[1], sh.mscr[2], n, xa, xb)) out.abort = true;
+            if (mode == 1 && lane == 0) tw_st_value(ms, xa, xb);
+        }
+    }
+    out.a = xa; out.b = xb;
+    return out;
+}
 
-// pass A
+// One word this warp saw first (short key): model + publish.  Out of line for the same reason.
+template <int MODEL>
+__device__ TW_SLOWPATH WholeWarpOut tw_own_word(const DevModel& m, const TileArgs& a, SliceShared& sh, uint32_t b0, uint32_t b1, uint32_t b2, uint32_t b3,
+                                                 uint32_t bslot) {
+    const uint32_t lane = lane_id();
+    WholeWarpOut out{0u, 0u, false};
+    if (lane < 4) sh.wbytes[lane] = lane == 0 ? b0 : (lane == 1 ? b1 : (lane == 2 ? b2 : (b3 & 0x00FFFFFFu)));
+    __syncwarp();
+    const uint32_t n = tw_model_small<MODEL>(m, reinterpret_cast<const uint8_t*>(sh.wbytes), b3 >> 24, sh.mscr);
+    if (!tw_make_value(a, sh.mscr[0], sh.mscr[1], sh.mscr[2], n, out.a, out.b)) out.abort = true;
+    if (lane == 0) tw_st_value(a.table + bslot, out.a, out.b);
+    __syncwarp();
+    return out;
+}
+
+// pass A: one warp per 512-byte slice, slices strided over all warps of the grid
 template <int MODEL, bool NORM_ID, bool HAS_ISO>
-__global__ void __launch_bounds__(TW_THREADS, 4) tile_words_kernel(const __grid_constant__ DevModel m, const __grid_constant__ TileArgs a) {
-    __shared__ __align__(32) TileShared sh;
+__global__ void __launch_bounds__(TW_THREADS, TW_BLOCKS_PER_SM) slice_words_kernel(const __grid_constant__ DevModel m, const __grid_constant__ TileArgs a) {
+    __shared__ __align__(32) TileShared bs;
     const uint32_t FULL = 0xFFFFFFFFu;
     const uint32_t t = threadIdx.x, lane = t & 31, wid = t >> 5;
-    const uint32_t tile = blockIdx.x;
-
-    // ---- prologue: byte LUT, key masks
-    if (t == 0) { sh.s_abort = *reinterpret_cast<volatile unsigned int*>(a.abort_flag); sh.s_entbase = TW_NONE; sh.s_done = 0; }
+    const uint32_t lt_mask = (1u << lane) - 1u;
     {
         const uint32_t c = m.lut[256 + t];
-        sh.lut[t] = (uint32_t)m.lut[t] | ((c == 0) ? 0x100u : 0u) | ((c == 2) ? 0x200u : 0u);
+        bs.lut[t] = (uint32_t)m.lut[t] | ((c == 0) ? 0x100u : 0u) | ((c == 2) ? 0x200u : 0u);
     }
     if (t < 16) {
         uint32_t w[4];
 #pragma unroll
         for (int q = 0; q < 4; q++) { const int nb = (int)t - 4 * q; w[q] = nb >= 4 ? 0xFFFFFFFFu : (nb <= 0 ? 0u : ((1u << (8 * nb)) - 1u)); }
-        sh.lenmask[t] = make_uint4(w[0], w[1], w[2], w[3]);
+        bs.lenmask[t] = make_uint4(w[0], w[1], w[2], w[3]);
     }
-    if (t < (TW_TILE + 2 * TW_SEG) / 32 + 2) { sh.docbits[t] = 0; sh.cont32[t] = 0; }
-    __syncthreads();
-    if (sh.s_abort) return;
-    const uint64_t tile_base = (uint64_t)tile * TW_TILE;
-    const uint32_t d_lo = __ldg(a.tile_doc_lo + tile), d_hi = __ldg(a.tile_doc_lo + tile + 1);
-
-    // ---- phase 1: document-start bits, classify + normalise one segment per thread
-    for (uint32_t d = d_lo + t; d <= a.n_docs; d += TW_THREADS) {
-        const uint64_t off = __ldg(a.doc_off + d);
-        if (off > tile_base + TW_TILE + 2 * TW_SEG) break;
-        const uint32_t p = (uint32_t)(off - tile_base);
-        atomicOr(&sh.docbits[p >> 5], 1u << (p & 31));
-    }
-    tw_load_segment<MODEL, NORM_ID, HAS_ISO>(a.text, a.n, tile_base + (uint64_t)t * TW_SEG, t, sh);
-    if (t < 2) tw_load_segment<MODEL, NORM_ID, HAS_ISO>(a.text, a.n, tile_base + TW_TILE + (uint64_t)t * TW_SEG, TW_THREADS + t, sh);
-    __syncthreads();
-
-    // ---- phase 2: word starts, continuation bits, per-warp word list
-    uint32_t nW;
-    {
-        uint16_t* cont16 = reinterpret_cast<uint16_t*>(sh.cont32);
-        uint32_t smask_own = 0;
-        for (uint32_t s = t; s < TW_THREADS + 2; s += TW_THREADS) {      // threads 0, 1 also do the halo segments
-            const uint32_t sw = sh.seg[s];
-            const uint32_t word = sw & 0xFFFFu, iso = sw >> 16;
-            uint32_t prev_word;
-            if (s > 0) prev_word = (sh.seg[s - 1] >> 15) & 1u;
-            else prev_word = (tile_base > 0 && tile_base - 1 < a.n) ? ((sh.lut[__ldg(a.text + tile_base - 1)] >> 8) & 1u) : 0u;
-            const uint32_t ds = tw_ds16(sh, s);
-            const uint32_t word_prev = ((word << 1) | prev_word) & 0xFFFFu;
-            const uint32_t smask = (iso | (word & (~word_prev | ds))) & 0xFFFFu;
-            cont16[s] = (uint16_t)(word & ~smask);
-            if (s == t) smask_own = smask;
-        }
-        const uint32_t smask = smask_own;
-        const uint32_t cnt = __popc(smask);
-        const uint32_t inc = warp_incl_scan(cnt);
-        const uint32_t wex = inc - cnt;
-        sh.smask[t] = (uint16_t)smask;
-        sh.sprefix[t] = (uint16_t)wex;
-        const uint32_t iso = HAS_ISO ? (sh.seg[t] >> 16) : 0u;
-        uint32_t sm = smask, k = wex;
-        while (sm) {
-            const int b = __ffs(sm) - 1; sm &= sm - 1;
-            sh.wlist[wid][k++] = (uint16_t)((t * TW_SEG + b) | (((iso >> b) & 1u) << 15));
-        }
-        nW = __shfl_sync(FULL, inc, 31);
-        if (lane == 0) sh.wcount[wid] = nW;
-    }
-    __syncthreads();
-    // words of the tile, of the warps before this one; thread 0 reserves the tile's slice of the entry list
-    uint32_t wordbase = 0, tile_nw = 0;
-#pragma unroll
-    for (int w = 0; w < TW_WARPS; w++) { const uint32_t x = sh.wcount[w]; tile_nw += x; if ((uint32_t)w < wid) wordbase += x; }
-    if (t == 0) {
-        uint32_t eb = tile_nw ? atomicAdd(a.ent_count, tile_nw) : 0u;
-        if ((unsigned long long)eb + tile_nw > a.ent_cap) { atomicExch(a.abort_flag, 1u); eb = TW_NONE - 1; }
-        a.tile_ent_off[tile] = eb; a.tile_nwords[tile] = tile_nw;
-        if (tile_nw) atomicAdd(a.n_words, (unsigned long long)tile_nw);
-        *reinterpret_cast<volatile uint32_t*>(&sh.s_entbase) = eb;
-    }
-
-    // ---- phase 3: one word per lane
-    uint32_t run = 0;                                           // tokens of this warp's words so far
-    uint8_t* const wbytes = reinterpret_cast<uint8_t*>(sh.wbytes[wid]);
+    __syncthreads();                                            // the only block-level barrier
+    SliceShared& sh = bs.w[wid];
+    const uint32_t stride = gridDim.x * TW_WARPS;
+    unsigned long long words_total = 0;
     bool warp_abort = false;
-    uint32_t entbase = TW_NONE;
-    for (uint32_t k0 = 0; k0 < nW; k0 += 32) {
-        const uint32_t k = k0 + lane;
-        const bool have = k < nW;
-        uint32_t p = 0, len = 0, va = 0, vb = 0, myslot = 0;
-        uint32_t key[4] = {0, 0, 0, 0};
-        int state = 0;                                          // 0 done, 1 owner, 2 pending, 3 whole warp needed
-        if (have) {
-            const uint32_t pw = sh.wlist[wid][k];
-            p = pw & 0x0FFFu;
-            if (HAS_ISO && (pw & 0x8000u)) len = 1;
-            else {
-                const uint32_t q = p + 1, w = q >> 5;
-                const uint32_t x = __funnelshift_r(sh.cont32[w], sh.cont32[w + 1], q & 31u);
-                len = (uint32_t)__ffs((int)~x);                 // 1 + continuing bytes; 0 when 32 or more continue
-                if (len == 0) len = 33;
-            }
-            if (len <= TW_MAX_SHORT) {
-                const uint32_t wi = p >> 2, shb = (p & 3u) * 8u;
-                const uint32_t x0 = sh.text32[wi], x1 = sh.text32[wi + 1], x2 = sh.text32[wi + 2], x3 = sh.text32[wi + 3], x4 = sh.text32[wi + 4];
-                const uint4 mk = sh.lenmask[len];
-                key[0] = __funnelshift_r(x0, x1, shb) & mk.x;
-                key[1] = __funnelshift_r(x1, x2, shb) & mk.y;
-                key[2] = __funnelshift_r(x2, x3, shb) & mk.z;
-                key[3] = (__funnelshift_r(x3, x4, shb) & mk.w) | (len << 24);
-                uint32_t slot = tw_key_hash(key[0], key[1], key[2], key[3]) & a.table_mask;
-                state = 3;
-                for (int probe = 0; probe < TW_MAX_PROBE; probe++) {
-                    WordSlot* s = a.table + slot;
-                    uint32_t r[8];
-                    tw_ld256(s, r);
-                    if (r[0] == key[0] && r[1] == key[1] && r[2] == key[2] && r[3] == key[3]) {
-                        if (r[5] != 0) { va = r[4]; vb = r[5]; state = 0; } else { state = 2; myslot = slot; }
-                        break;
-                    }
-                    if ((r[0] | r[1] | r[2] | r[3]) == 0) {
-                        uint32_t old[4];
-                        tw_cas128(s, key, old);
-                        if ((old[0] | old[1] | old[2] | old[3]) == 0) { state = 1; myslot = slot; break; }
-                        if (old[0] == key[0] && old[1] == key[1] && old[2] == key[2] && old[3] == key[3]) { state = 2; myslot = slot; break; }
-                    }
-                    slot = (slot + 1) & a.table_mask;
-                }
-            } else state = 3;
+
+    for (uint32_t s = blockIdx.x * TW_WARPS + wid; s < a.n_slices; s += stride) {
+        const uint64_t slice_base = (uint64_t)s * TW_SLICE;
+        const uint32_t d_lo = __ldg(a.slice_doc_lo + s), d_hi = __ldg(a.slice_doc_lo + s + 1);
+        // the warp's next slice: its text is pulled into L2 while this one is processed
+        if (lane < 5 && (uint64_t)(s + stride) * TW_SLICE + lane * 128 < a.n)
+            asm volatile("prefetch.global.L2 [%0];" :: "l"(a.text + (uint64_t)(s + stride) * TW_SLICE + lane * 128));
+        // ---- phase 1: document-start bits; classify + normalise one segment per lane (lanes 0, 1: also the 2 halo segments)
+        if (lane < (TW_SLICE + 2 * TW_SEG) / 32 + 2) { sh.docbits[lane] = 0; sh.cont32[lane] = 0; }
+        __syncwarp();
+        for (uint32_t d = d_lo + lane; d <= a.n_docs; d += 32) {
+            const uint64_t off = __ldg(a.doc_off + d);
+            if (off > slice_base + TW_SLICE + 2 * TW_SEG) break;
+            const uint32_t p = (uint32_t)(off - slice_base);
+            atomicOr(&sh.docbits[p >> 5], 1u << (p & 31));
         }
-        // ---- words this warp saw first: run the model now and publish the value
-        uint32_t owners = __ballot_sync(FULL, state == 1);
-        if (owners && lane == 0) atomicAdd(a.n_uniq, (unsigned int)__popc(owners));
-        while (owners) {
-            const int l = __ffs(owners) - 1; owners &= owners - 1;
-            const uint32_t b0 = __shfl_sync(FULL, key[0], l), b1 = __shfl_sync(FULL, key[1], l), b2 = __shfl_sync(FULL, key[2], l),
-                           b3 = __shfl_sync(FULL, key[3], l);
-            const uint32_t blen = b3 >> 24, bslot = __shfl_sync(FULL, myslot, l);
-            if (lane < 4) sh.wbytes[wid][lane] = lane == 0 ? b0 : (lane == 1 ? b1 : (lane == 2 ? b2 : (b3 & 0x00FFFFFFu)));
-            __syncwarp();
-            const uint32_t n = tw_model_small<MODEL>(m, wbytes, blen, sh.mscr[wid]);
-            uint32_t xa, xb;
-            if (!tw_make_value(a, sh.mscr[wid][0], sh.mscr[wid][1], sh.mscr[wid][2], n, xa, xb)) warp_abort = true;
-            if (lane == 0) tw_st_value(a.table + bslot, xa, xb);
-            if ((int)lane == l) { va = xa; vb = xb; state = 0; }
-            __syncwarp();
-        }
-        // ---- words that need the whole warp: longer than 15 bytes, or no slot within the probe limit (tkz_tiles.cuh)
-        uint32_t todo = __ballot_sync(FULL, state == 3);
-        while (todo) {
-            const int l = __ffs(todo) - 1; todo &= todo - 1;
-            const uint32_t wp_ = __shfl_sync(FULL, p, l), wl_ = __shfl_sync(FULL, len, l);
-            const uint64_t start = tile_base + wp_;
-            uint32_t wlen = wl_;
-            if (wl_ > TW_MAX_SHORT) {
-                // end of the word: first non-WORD byte or the next document start, 32 bytes per step
-                uint64_t limit = 0;
-                if (lane == 0) {
-                    const uint32_t dn = upper_bound_u64(a.doc_off, d_lo > 0 ? d_lo - 1 : 0, a.n_docs + 1, start);
-                    limit = dn <= a.n_docs ? __ldg(a.doc_off + dn) : a.n;
-                    if (limit > a.n) limit = a.n;
-                }
-                limit = __shfl_sync(FULL, limit, 0);
-                // WordPiece only needs the LENGTH of a word above max_input_chars_per_word (wordpiece.zig:149-158)
-                uint64_t q = start + TW_MAX_SHORT + 1;
-                for (;;) {
-                    const uint64_t qq = q + lane;
-                    const bool stop = qq >= limit || ((sh.lut[__ldg(a.text + qq)] >> 8) & 1u) == 0;
-                    const uint32_t sm = __ballot_sync(FULL, stop);
-                    if (sm) { q += (uint32_t)__ffs(sm) - 1; break; }
-                    q += 32;
-                }
-                wlen = (uint32_t)(q - start);
+        // the byte before the slice (lane 0) and the 32 halo bytes behind it (one per lane): only class bits + normalised bytes
+        uint32_t prev_byte_word = 0;
+        if (lane == 0 && slice_base > 0 && slice_base - 1 < a.n) prev_byte_word = (bs.lut[__ldg(a.text + slice_base - 1)] >> 8) & 1u;
+        uint32_t halo_e = 0;
+        { const uint64_t hp = slice_base + TW_SLICE + lane; if (hp < a.n) halo_e = bs.lut[__ldg(a.text + hp)]; }
+        const uint32_t sw = tw_load_segment<NORM_ID, HAS_ISO>(a.text, a.n, slice_base + (uint64_t)lane * TW_SEG, lane, bs.lut, sh.text32);
+        reinterpret_cast<uint8_t*>(sh.text32)[TW_SLICE + lane] = (uint8_t)halo_e;
+        __syncwarp();
+
+        // ---- phase 2: word starts, continuation bits, word list
+        const uint32_t word = sw & 0xFFFFu, iso = sw >> 16;
+        uint32_t smask, wex, nW;
+        {
+            uint32_t prev_word = __shfl_up_sync(FULL, word >> 15, 1);
+            if (lane == 0) prev_word = prev_byte_word;
+            const uint32_t ds = (sh.docbits[lane >> 1] >> ((lane & 1u) * 16)) & 0xFFFFu;
+            const uint32_t word_prev = ((word << 1) | prev_word) & 0xFFFFu;
+            smask = (iso | (word & (~word_prev | ds))) & 0xFFFFu;
+            const uint32_t cont = word & ~smask;
+            // halo bytes 512..543: continuation bits from the per-lane class bits (same formula, 32 bits wide)
+            const uint32_t hw = __ballot_sync(FULL, (halo_e >> 8) & 1u), hi = HAS_ISO ? __ballot_sync(FULL, (halo_e >> 9) & 1u) : 0u;
+            const uint32_t w31 = __shfl_sync(FULL, word >> 15, 31);
+            const uint32_t hs = hi | (hw & (~((hw << 1) | w31) | sh.docbits[16]));
+            const uint32_t partner = __shfl_xor_sync(FULL, cont, 1);
+            if (!(lane & 1u)) sh.cont32[lane >> 1] = cont | (partner << 16);
+            if (lane == 0) sh.cont32[16] = hw & ~hs;
+            const uint32_t cnt = __popc(smask);
+            const uint32_t inc = warp_incl_scan(cnt);
+            wex = inc - cnt;
+            uint32_t sm = smask, k = wex;
+            while (sm) {
+                const int b = __ffs(sm) - 1; sm &= sm - 1;
+                sh.wlist[k++] = (uint16_t)((lane * TW_SEG + b) | (((iso >> b) & 1u) << 15));
             }
-            uint32_t xa = 0, xb = 1u << 16;                    // default: no tokens
-            if (MODEL == TKZ_MODEL_WORDPIECE && (uint64_t)wlen > m.max_chars && wlen <= 0xFFFFu) {
-                // one [UNK] spanning the word (wordpiece.zig:149-158); MissingUnkToken when the vocabulary has none
-                uint32_t* scr = sh.mscr[wid][0];
-                if (lane == 0) { scr[0] = m.unk_id; scr[1] = 0; scr[2] = wlen; }
-                __syncwarp();
-                if (!tw_make_value(a, scr, scr + 1, scr + 2, m.has_unk ? 1u : TKZ_NONE, xa, xb)) warp_abort = true;
-            } else if (wlen > TW_MAX_INLINE) {
-                // long list: tokenized per occurrence by the word-list kernels between the two passes (block-level BPE)
-                uint32_t idx = 0;
-                if (lane == 0) {
-                    idx = atomicAdd(a.n_long, 1u);
-                    if (idx < a.long_cap) { a.long_start[idx] = (uint32_t)start; a.long_end[idx] = (uint32_t)(start + wlen); a.long_tile[idx] = tile; }
-                }
-                idx = __shfl_sync(FULL, idx, 0);
-                if (idx >= a.long_cap) warp_abort = true;
-                xa = idx; xb = TW_LONGF | (1u << 16);
-            } else if (wlen > TW_MAX_MED) {
-                // 65..256 bytes: not deduplicated, symbols in global scratch
-                uint32_t off = 0;
-                if (lane == 0) { off = atomicAdd(a.lscratch_count, 4u * wlen); atomicAdd(a.n_uncached, 1u); }
-                off = __shfl_sync(FULL, off, 0);
-                if ((unsigned long long)off + 4u * wlen > a.lscratch_cap) warp_abort = true;
+            nW = __shfl_sync(FULL, inc, 31);
+        }
+        // reserve the slice's part of the entry list (region s & mask, one bump counter per region)
+        uint32_t entoff = TW_NONE;
+        if (lane == 0 && nW) {
+            const uint32_t r = s & a.region_mask;
+            const uint32_t eb = atomicAdd(a.region_count + r * 32, nW);
+            if ((unsigned long long)eb + nW > a.region_cap) atomicExch(a.abort_flag, 1u);
+            else entoff = r * a.region_cap + eb;
+        }
+        words_total += nW;
+        __syncwarp();
+
+        // ---- phase 3: one word per lane
+        uint32_t run = 0;                                           // tokens of the slice's words so far
+        for (uint32_t k0 = 0; k0 < nW; k0 += 32) {
+            const uint32_t k = k0 + lane;
+            const bool have = k < nW;
+            uint32_t p = 0, len = 0, va = 0, vb = 0, myslot = 0;
+            uint32_t key[4] = {0, 0, 0, 0};
+            int state = 0;                                          // 0 done, 1 owner, 2 pending, 3 whole warp needed
+            if (have) {
+                const uint32_t pw = sh.wlist[k];
+                p = pw & 0x0FFFu;
+                if (HAS_ISO && (pw & 0x8000u)) len = 1;
                 else {
-                    uint32_t* g = a.lscratch + off;
-                    const uint32_t n = tw_model_long<MODEL>(m, m.lut, a.text + start, wlen, g);
-                    __threadfence_block();
-                    if (!tw_make_value(a, g, g + wlen, g + 2 * wlen, n, xa, xb)) warp_abort = true;
+                    const uint32_t q = p + 1, w = q >> 5;
+                    const uint32_t x = __funnelshift_r(sh.cont32[w], sh.cont32[w + 1], q & 31u);
+                    len = (uint32_t)__ffs((int)~x);                 // 1 + continuing bytes; 0 when 32 or more continue
+                    if (len == 0) len = 33;
                 }
-            } else {
-                // <= 64 bytes: normalised bytes into shared memory
-                {
-                    uint32_t bb = 0;
-                    if (2 * lane < wlen) bb = sh.lut[__ldg(a.text + start + 2 * lane)] & 0xFFu;
-                    if (2 * lane + 1 < wlen) bb |= (sh.lut[__ldg(a.text + start + 2 * lane + 1)] & 0xFFu) << 8;
-                    reinterpret_cast<uint16_t*>(wbytes)[lane] = (uint16_t)bb;
-                }
-                __syncwarp();
-                int mode = 0;                                   // 0 compute, do not publish | 1 owner | 2 value found
-                WordSlot* ms = nullptr;
-                if (wlen > TW_MAX_SHORT) {
-                    // medium word: 64-bit tag = mixed polynomial hash of the normalised bytes, exactness by comparing with
-                    // the representative occurrence
-                    unsigned long long h = 0;
-                    if (2 * lane < wlen) h += (unsigned long long)(wbytes[2 * lane] + 1u) * c_med_pw[2 * lane];
-                    if (2 * lane + 1 < wlen) h += (unsigned long long)(wbytes[2 * lane + 1] + 1u) * c_med_pw[2 * lane + 1];
-                    for (int d = 16; d > 0; d >>= 1) h += __shfl_xor_sync(FULL, h, d);
-                    h ^= wlen; h ^= h >> 29; h *= 0xD6E8FEB86659FD93ULL; h ^= h >> 32;
-                    const unsigned long long tag = h | 0x8000000000000000ULL;
-                    unsigned long long* const tab64 = reinterpret_cast<unsigned long long*>(a.table + a.med_base);
-                    uint32_t slot = (uint32_t)h & a.med_mask;
-                    for (int probe = 0; probe < TW_MAX_PROBE && mode == 0; probe++) {
-                        unsigned long long* kp = tab64 + (size_t)slot * 4;       // [0] tag, [1] representative, [2] value
-                        unsigned long long cur = 0;
-                        if (lane == 0) {
-                            cur = __ldcg(kp);
-                            if (cur == 0) {
-                                cur = atomicCAS(kp, 0ULL, tag);
-                                if (cur == 0) {
-                                    __stcg(kp + 1, (unsigned long long)(uint32_t)start | ((unsigned long long)wlen << 32));
-                                    __threadfence();
-                                    atomicAdd(a.n_uniq, 1u);
-                                    cur = 1;                               // marker: owned
-                                }
-                            }
+                if (len <= TW_MAX_SHORT) {
+                    const uint32_t wi = p >> 2, shb = (p & 3u) * 8u;
+                    const uint32_t x0 = sh.text32[wi], x1 = sh.text32[wi + 1], x2 = sh.text32[wi + 2], x3 = sh.text32[wi + 3], x4 = sh.text32[wi + 4];
+                    const uint4 mk = bs.lenmask[len];
+                    key[0] = __funnelshift_r(x0, x1, shb) & mk.x;
+                    key[1] = __funnelshift_r(x1, x2, shb) & mk.y;
+                    key[2] = __funnelshift_r(x2, x3, shb) & mk.z;
+                    key[3] = (__funnelshift_r(x3, x4, shb) & mk.w) | (len << 24);
+                    uint32_t slot = tw_key_hash(key[0], key[1], key[2], key[3]) & a.table_mask;
+                    state = 3;
+                    for (int probe = 0; probe < TW_MAX_PROBE; probe++) {
+                        WordSlot* sl = a.table + slot;
+                        uint32_t r[8];
+                        tw_ld256(sl, r);
+                        if (r[0] == key[0] && r[1] == key[1] && r[2] == key[2] && r[3] == key[3]) {
+                            if (r[5] != 0) { va = r[4]; vb = r[5]; state = 0; } else { state = 2; myslot = slot; }
+                            break;
                         }
-                        cur = __shfl_sync(FULL, cur, 0);
-                        if (cur == 1) { mode = 1; ms = a.table + a.med_base + slot; break; }
-                        if (cur == tag) {
-                            unsigned long long rm = 0;
-                            if (lane == 0) rm = __ldcg(kp + 1);
-                            rm = __shfl_sync(FULL, rm, 0);
-                            if (rm == 0) break;                            // representative not published yet: compute privately
-                            bool eq = (uint32_t)(rm >> 32) == wlen;
-                            if (eq) {
-                                const uint8_t* __restrict__ rp = a.text + (uint32_t)rm;
-                                if (2 * lane < wlen) eq = eq && (sh.lut[__ldg(rp + 2 * lane)] & 0xFFu) == wbytes[2 * lane];
-                                if (2 * lane + 1 < wlen) eq = eq && (sh.lut[__ldg(rp + 2 * lane + 1)] & 0xFFu) == wbytes[2 * lane + 1];
-                            }
-                            if (__all_sync(FULL, eq)) { mode = 2; ms = a.table + a.med_base + slot; break; }
+                        if ((r[0] | r[1] | r[2] | r[3]) == 0) {
+                            uint32_t old[4];
+                            tw_cas128(sl, key, old);
+                            if ((old[0] | old[1] | old[2] | old[3]) == 0) { state = 1; myslot = slot; break; }
+                            if (old[0] == key[0] && old[1] == key[1] && old[2] == key[2] && old[3] == key[3]) { state = 2; myslot = slot; break; }
                         }
-                        slot = (slot + 1) & a.med_mask;
+                        slot = (slot + 1) & a.table_mask;
                     }
-                }
-                if (mode == 2) {
-                    uint2 v = make_uint2(0, 0);
-                    if (lane == 0) { do { v = tw_ld_value(ms); } while (v.y == 0); }
-                    xa = __shfl_sync(FULL, v.x, 0); xb = __shfl_sync(FULL, v.y, 0);
-                } else {
-                    if (mode == 0 && lane == 0) atomicAdd(a.n_uncached, 1u);
-                    const uint32_t n = tw_model_small<MODEL>(m, wbytes, wlen, sh.mscr[wid]);
-                    if (!tw_make_value(a, sh.mscr[wid][0], sh.mscr[wid][1], sh.mscr[wid][2], n, xa, xb)) warp_abort = true;
-                    if (mode == 1 && lane == 0) tw_st_value(ms, xa, xb);
-                }
+                } else state = 3;
             }
-            if ((int)lane == l) { va = xa; vb = xb; state = 0; len = wlen > 2 ? 2 : wlen; }
-            __syncwarp();
-        }
-        // ---- words whose owner (another warp) was still computing
-        uint32_t pend = __ballot_sync(FULL, state == 2);
-        while (pend) {
-            if (state == 2) {
-                const uint2 v = tw_ld_value(a.table + myslot);
-                if (v.y != 0) { va = v.x; vb = v.y; state = 0; }
+            // ---- words this warp saw first: run the model now and publish the value
+            uint32_t owners = __ballot_sync(FULL, state == 1);
+            if (owners && lane == 0) atomicAdd(a.n_uniq, (unsigned int)__popc(owners));
+            while (owners) {
+                const int l = __ffs(owners) - 1; owners &= owners - 1;
+                const WholeWarpOut r = tw_own_word<MODEL>(m, a, sh, __shfl_sync(FULL, key[0], l), __shfl_sync(FULL, key[1], l), __shfl_sync(FULL, key[2], l),
+                                                          __shfl_sync(FULL, key[3], l), __shfl_sync(FULL, myslot, l));
+                if (r.abort) warp_abort = true;
+                if ((int)lane == l) { va = r.a; vb = r.b; state = 0; }
             }
-            pend = __ballot_sync(FULL, state == 2);
+            // ---- words that need the whole warp: longer than 15 bytes, or no slot within the probe limit
+            uint32_t todo = __ballot_sync(FULL, state == 3);
+            while (todo) {
+                const int l = __ffs(todo) - 1; todo &= todo - 1;
+                const WholeWarpOut r = tw_whole_warp_word<MODEL>(m, a, bs.lut, sh, s, slice_base, d_lo, __shfl_sync(FULL, p, l), __shfl_sync(FULL, len, l));
+                if (r.abort) warp_abort = true;
+                if ((int)lane == l) { va = r.a; vb = r.b; state = 0; }
+            }
+            // ---- words whose owner (another warp) was still computing
+            uint32_t pend = __ballot_sync(FULL, state == 2);
+            while (pend) {
+                if (state == 2) {
+                    const uint2 v = tw_ld_value(a.table + myslot);
+                    if (v.y != 0) { va = v.x; vb = v.y; state = 0; }
+                }
+                pend = __ballot_sync(FULL, state == 2);
+            }
+            // ---- entry + token prefix
+            uint32_t nt = 0, ey = 0;
+            if (have) {
+                const uint32_t nt1 = (vb >> 16) & 0x3FFFu;
+                if (nt1 == TW_NT1_ERR) atomicMin(a.errw, ((unsigned long long)(slice_base + p) << 8) | (MODEL == TKZ_MODEL_BPE ? TKZ_ECODE_UTF8 : TKZ_ECODE_UNK));
+                else nt = nt1 - 1;
+                ey = (nt << 16) | (vb & 0xFFFFu) | (vb & (TW_POOLF | TW_LONGF));
+                if (vb & TW_LONGF) nt = 0;                          // counted after the word-list kernels (long_fix_kernel)
+            }
+            const uint32_t eo_ = __shfl_sync(FULL, entoff, 0);
+            if (have && eo_ != TW_NONE) a.ent[(size_t)eo_ + k] = make_uint2(va, ey);
+            const uint32_t inc = warp_incl_scan(nt);
+            if (have) sh.wpfx[k] = (uint16_t)(run + inc - nt);
+            run += __shfl_sync(FULL, inc, 31);
         }
-        // ---- entry + token prefix
-        uint32_t nt = 0, ey = 0;
-        if (have) {
-            const uint32_t nt1 = (vb >> 16) & 0x3FFFu;
-            if (nt1 == TW_NT1_ERR) atomicMin(a.errw, ((unsigned long long)(tile_base + p) << 8) | (MODEL == TKZ_MODEL_BPE ? TKZ_ECODE_UTF8 : TKZ_ECODE_UNK));
-            else nt = nt1 - 1;
-            ey = (nt << 16) | (vb & 0xFFFFu) | (vb & (TW_POOLF | TW_LONGF));
-            if (vb & TW_LONGF) nt = 0;                          // counted after the word-list kernels (long_fix_kernel)
+        if (lane == 0) {
+            a.slice_ent_off[s] = entoff == TW_NONE ? 0u : entoff;
+            a.slice_nwords[s] = entoff == TW_NONE ? 0u : nW;
+            a.slice_ntok[s] = run;
         }
-        if (entbase == TW_NONE) { do { entbase = *reinterpret_cast<volatile uint32_t*>(&sh.s_entbase); } while (entbase == TW_NONE); }
-        if (have && entbase != TW_NONE - 1) a.ent[(size_t)entbase + wordbase + k] = make_uint2(va, ey);
-        const uint32_t inc = warp_incl_scan(nt);
-        if (have) sh.wpfx[wid][k] = (uint16_t)(run + inc - nt);
-        run += __shfl_sync(FULL, inc, 31);
+        __syncwarp();
+        // ---- token prefix + word index at every document start inside the slice
+        for (uint32_t d0 = d_lo; d0 < d_hi; d0 += 32) {
+            const uint32_t d = d0 + lane;
+            const bool valid = d < d_hi;
+            const uint32_t q = valid ? (uint32_t)(__ldg(a.doc_off + d) - slice_base) : 0u;
+            const uint32_t sg = q >> 4;
+            const uint32_t idx = __shfl_sync(FULL, wex, sg) + __popc(__shfl_sync(FULL, smask, sg) & ((1u << (q & 15u)) - 1u));
+            if (valid) {
+                a.doc_tok_local[d] = idx < nW ? (uint32_t)sh.wpfx[idx] : run;
+                a.doc_word_ref[d] = idx;
+            }
+        }
+        __syncwarp();
     }
     if (__any_sync(FULL, warp_abort) && lane == 0) atomicExch(a.abort_flag, 1u);
-
-    // ---- the warp that finishes last: tokens of the tile, token prefix + word index at every document start of the tile
-    uint32_t done = 0;
-    __syncwarp();
-    if (lane == 0) { sh.wtok[wid] = run; __threadfence_block(); done = atomicAdd(&sh.s_done, 1u); }
-    done = __shfl_sync(FULL, done, 0);
-    if (done != TW_WARPS - 1) return;
-    __threadfence_block();
-    uint32_t tb[TW_WARPS + 1], wb[TW_WARPS + 1];
-    tb[0] = 0; wb[0] = 0;
-#pragma unroll
-    for (int w = 0; w < TW_WARPS; w++) {
-        tb[w + 1] = tb[w] + *reinterpret_cast<volatile uint32_t*>(&sh.wtok[w]);
-        wb[w + 1] = wb[w] + sh.wcount[w];
-    }
-    if (lane == 0) a.tile_ntok[tile] = tb[TW_WARPS];
-    for (uint32_t d = d_lo + lane; d < d_hi; d += 32) {
-        const uint32_t q = (uint32_t)(__ldg(a.doc_off + d) - tile_base);
-        const uint32_t sg = q >> 4, wq = sg >> 5;
-        const uint32_t idx = sh.sprefix[sg] + __popc((uint32_t)sh.smask[sg] & ((1u << (q & 15u)) - 1u));
-        uint32_t tbase = 0, wbase = 0, wcnt = 0, wt_ = 0;
-#pragma unroll
-        for (int w = 0; w < TW_WARPS; w++) if ((uint32_t)w == wq) { tbase = tb[w]; wbase = wb[w]; wcnt = wb[w + 1] - wb[w]; wt_ = tb[w + 1] - tb[w]; }
-        const uint32_t tk = idx < wcnt ? (uint32_t)*reinterpret_cast<volatile uint16_t*>(&sh.wpfx[wq][idx]) : wt_;
-        a.doc_tok_local[d] = tbase + tk;
-        a.doc_word_ref[d] = wbase + idx;
-    }
+    if (lane == 0 && words_total) atomicAdd(a.n_words, words_total);
+    (void)lt_mask;
 }
 
 // after the word-list kernels: the tokens of every long word join its tile's count and the token prefix of the documents
@@ -544,9 +574,9 @@ __global__ void long_fix_kernel(const uint32_t* __restrict__ long_start, const u
 
 // ------------------------------------------------------------------ pass B
 struct TileEmitArgs {
-    const uint64_t* doc_off; uint32_t n_docs; const uint32_t* tile_doc_lo;
-    const uint2* ent; const uint32_t* tile_ent_off; const uint32_t* tile_nwords;
-    const uint32_t* tile_tokbase;                 // exclusive scan of the tile token counts (n_tiles + 1)
+    const uint64_t* doc_off; uint32_t n_docs; uint32_t n_slices; const uint32_t* slice_doc_lo;
+    const uint2* ent; const uint32_t* slice_ent_off; const uint32_t* slice_nwords;
+    const uint32_t* slice_tokbase;                // exclusive scan of the slice token counts (n_slices + 1)
     const unsigned long long* upool;
     const uint32_t* long_start; const uint32_t* long_ntok;
     const uint32_t* pool_id; const uint32_t* pool_s; const uint32_t* pool_e;
@@ -556,119 +586,156 @@ struct TileEmitArgs {
     unsigned long long* errw; uint32_t err_code;
     BigList big;
 };
-constexpr int TE_THREADS = 256;
-constexpr uint32_t TE_STAGE = 1536;               // tokens of one 256-word round staged in shared memory
+constexpr uint32_t TE_STAGE = 256;                // tokens a warp stages in shared memory before one coalesced flush
+
+struct EmitStage { uint32_t id[TE_STAGE + 8]; uint32_t of[TE_STAGE + 8]; };
+
+// staged tokens [0, fill) -> global slots [gstart, gstart + fill): slot i of the staging arrays holds global index
+// (gstart & ~3) + i, so whole groups of 4 tokens go out as 16-byte stores (ids, attention; offsets as 2 x 16 bytes)
+__device__ __forceinline__ void te_flush(const EmitParams& p, const EmitOut& o, const EmitStage& st, unsigned long long gstart, uint32_t fill) {
+    const uint32_t lane = lane_id();
+    const uint32_t outputs = p.outputs;
+    __syncwarp();
+    const uint32_t mis = (uint32_t)(gstart & 3ull), end = mis + fill;
+    const unsigned long long g0 = gstart & ~3ull;
+    for (uint32_t g = lane * 4; g + 4 <= end; g += 128) {
+        if (g >= mis) {
+            *reinterpret_cast<uint4*>(o.ids + g0 + g) = *reinterpret_cast<const uint4*>(st.id + g);
+            if (outputs & 2u) {
+                const uint4 of4 = *reinterpret_cast<const uint4*>(st.of + g);
+                uint4* dst = reinterpret_cast<uint4*>(o.offsets + 2 * (g0 + g));
+                dst[0] = make_uint4(of4.x & 0xFFFFu, of4.x >> 16, of4.y & 0xFFFFu, of4.y >> 16);
+                dst[1] = make_uint4(of4.z & 0xFFFFu, of4.z >> 16, of4.w & 0xFFFFu, of4.w >> 16);
+            }
+            if (outputs & 4u) *reinterpret_cast<uint4*>(o.attention + g0 + g) = make_uint4(1u, 1u, 1u, 1u);
+            if (outputs & 8u) *reinterpret_cast<uint4*>(o.type_ids + g0 + g) = make_uint4(0u, 0u, 0u, 0u);
+            if (outputs & 16u) *reinterpret_cast<uint4*>(o.special + g0 + g) = make_uint4(0u, 0u, 0u, 0u);
+        }
+    }
+    // the partial groups at both ends, one token per lane: lanes 0..3 the head group, lanes 4..7 the tail group
+    {
+        const uint32_t tail0 = end & ~3u;
+        uint32_t j = TW_NONE;
+        if (lane < 4) { if (mis && lane >= mis && lane < end) j = lane; }
+        else if (lane < 8) { const uint32_t x = tail0 + (lane - 4); if ((end & 3u) && x < end && x >= mis && (tail0 != 0 || mis == 0)) j = x; }
+        if (j != TW_NONE) { const uint32_t of = st.of[j]; emit_real(p, o, g0 + j, st.id[j], of & 0xFFFFu, of >> 16); }
+    }
+    __syncwarp();
+}
 
 // PLAIN = no truncation and no padding: the output is the plain concatenation of all tokens in text order, so a token's
-// destination is its global index; the round's tokens are staged in shared memory and written with 16-byte stores.
+// destination is its global index; tokens are staged in shared memory and written with 16-byte stores.
 template <bool PLAIN>
-__global__ void __launch_bounds__(TE_THREADS) tile_emit_kernel(const __grid_constant__ TileEmitArgs a, const __grid_constant__ EmitParams p, const __grid_constant__ EmitOut o) {
-    __shared__ uint32_t scan[2 * (TE_THREADS / 32 + 1)];
-    __shared__ __align__(16) uint32_t st_id[PLAIN ? TE_STAGE + 8 : 4];
-    __shared__ __align__(16) uint32_t st_of[PLAIN ? TE_STAGE + 8 : 4];
+__global__ void __launch_bounds__(TW_THREADS, 6) slice_emit_kernel(const __grid_constant__ TileEmitArgs a, const __grid_constant__ EmitParams p,
+                                                                const __grid_constant__ EmitOut o) {
+    __shared__ __align__(16) EmitStage stage[PLAIN ? TW_WARPS : 1];
     const uint32_t FULL = 0xFFFFFFFFu;
-    const uint32_t t = threadIdx.x, lane = lane_id(), tile = blockIdx.x;
-    const uint32_t nw = a.tile_nwords[tile];
-    const uint2* __restrict__ ent = a.ent + a.tile_ent_off[tile];
-    const uint32_t d_lo = __ldg(a.tile_doc_lo + tile), d_hi = __ldg(a.tile_doc_lo + tile + 1);
-    const uint32_t base = a.tile_tokbase[tile];
-    const uint32_t outputs = p.outputs;
-    uint32_t carry = base, phase = 0;
-    for (uint32_t i0 = 0; i0 < nw; i0 += TE_THREADS, phase ^= 1u) {
-        const uint32_t k = i0 + t;
-        uint32_t ea = 0, ey = 0, nt = 0;
-        if (k < nw) {
-            const uint2 e = __ldg(ent + k);
-            ea = e.x; ey = e.y;
-            if (ey & TW_LONGF) {
-                nt = __ldg(a.long_ntok + ea);
-                if (nt == TKZ_NONE) { atomicMin(a.errw, ((unsigned long long)__ldg(a.long_start + ea) << 8) | a.err_code); nt = 0; }
-            } else nt = (ey >> 16) & 0x3FFFu;
-        }
-        uint32_t tot;
-        const uint32_t ex = block_excl_scan32<TE_THREADS / 32>(nt, scan, phase, &tot);
-        const bool is_long = (ey & TW_LONGF) != 0;
-        bool staged = false;
-        if (PLAIN) {
-            const uint32_t any_long = __syncthreads_or(is_long && nt);
-            staged = !any_long && tot <= TE_STAGE;
-            if (staged) {
-                const uint32_t mis = carry & 3u;
-                if (nt) {
-                    const uint32_t si = mis + ex;
-                    if (!(ey & TW_POOLF)) { st_id[si] = ea; st_of[si] = (ey & 0xFFu) | ((ey & 0xFF00u) << 8); }
-                    else for (uint32_t i = 0; i < nt; i++) {
+    const uint32_t lane = lane_id(), wid = threadIdx.x >> 5;
+    EmitStage& st = stage[PLAIN ? wid : 0];
+    const uint32_t stride = gridDim.x * TW_WARPS;
+    // slice metadata is fetched one slice ahead: lanes 0..4 hold nwords, ent_off, tokbase, doc_lo, doc_lo[+1] of the next slice
+    auto load_meta = [&](uint32_t s) -> uint32_t {
+        if (s >= a.n_slices) return 0u;
+        const uint32_t* src = lane == 0 ? a.slice_nwords + s : (lane == 1 ? a.slice_ent_off + s : (lane == 2 ? a.slice_tokbase + s : a.slice_doc_lo + s + (lane - 3)));
+        return lane < 5 ? __ldg(src) : 0u;
+    };
+    uint32_t s = blockIdx.x * TW_WARPS + wid;
+    uint32_t meta = load_meta(s);
+    for (; s < a.n_slices; s += stride) {
+        const uint32_t nw = __shfl_sync(FULL, meta, 0);
+        const uint2* __restrict__ ent = a.ent + __shfl_sync(FULL, meta, 1);
+        const uint32_t base = __shfl_sync(FULL, meta, 2);
+        const uint32_t d_lo = __shfl_sync(FULL, meta, 3), d_hi = __shfl_sync(FULL, meta, 4);
+        meta = load_meta(s + stride);
+        uint32_t carry = base;                                  // global real-token index of the next token
+        uint32_t fill = 0; unsigned long long gstart = base;     // staging: tokens staged, global index of the first one
+        uint2 e_next = make_uint2(0u, 0u);
+        if (lane < nw) e_next = __ldg(ent + lane);
+        for (uint32_t k0 = 0; k0 < nw; k0 += 32) {
+            const uint32_t k = k0 + lane;
+            const uint32_t ea = e_next.x, ey = k < nw ? e_next.y : 0u;
+            if (k + 32 < nw) e_next = __ldg(ent + k + 32);        // next round's entries are in flight while this round is emitted
+            else if (k0 + 32 >= nw && s + stride < a.n_slices && lane < 4)   // last round: pull the next slice's entries into L2
+                asm volatile("prefetch.global.L2 [%0];" :: "l"(a.ent + __shfl_sync(0xFu, meta, 1) + lane * 16));
+            uint32_t nt = 0;
+            if (k < nw) {
+                if (ey & TW_LONGF) {
+                    nt = __ldg(a.long_ntok + ea);
+                    if (nt == TKZ_NONE) { atomicMin(a.errw, ((unsigned long long)__ldg(a.long_start + ea) << 8) | a.err_code); nt = 0; }
+                } else nt = (ey >> 16) & 0x3FFFu;
+            }
+            // multi-token words: the first two records are requested now and land while the scan runs
+            const bool pooled = nt && (ey & (TW_POOLF | TW_LONGF)) == TW_POOLF;
+            unsigned long long r0 = 0, r1 = 0;
+            if (pooled) { r0 = __ldcg(a.upool + ea); if (nt > 1) r1 = __ldcg(a.upool + ea + 1); }
+            const uint32_t inc = warp_incl_scan(nt);
+            const uint32_t ex = inc - nt, tot = __shfl_sync(FULL, inc, 31);
+            const bool is_long = (ey & TW_LONGF) != 0;
+            bool staged = false;
+            if (PLAIN) {
+                staged = tot <= TE_STAGE && !__any_sync(FULL, is_long && nt);
+                if (staged) {
+                    if (fill + tot > TE_STAGE) { te_flush(p, o, st, gstart, fill); fill = 0; gstart = carry; }
+                    if (nt) {
+                        const uint32_t si = (uint32_t)(gstart & 3ull) + fill + ex;
+                        if (!pooled) { st.id[si] = ea; st.of[si] = (ey & 0xFFu) | ((ey & 0xFF00u) << 8); }
+                        else {
+                            st.id[si] = (uint32_t)r0; st.of[si] = (uint32_t)(r0 >> 32);
+                            if (nt > 1) { st.id[si + 1] = (uint32_t)r1; st.of[si + 1] = (uint32_t)(r1 >> 32); }
+                            for (uint32_t i = 2; i < nt; i++) {
+                                const unsigned long long r = __ldcg(a.upool + ea + i);
+                                st.id[si + i] = (uint32_t)r; st.of[si + i] = (uint32_t)(r >> 32);
+                            }
+                        }
+                    }
+                    fill += tot;
+                } else if (fill) { te_flush(p, o, st, gstart, fill); fill = 0; }
+            }
+            if (!staged) {
+                // destination of the word's first token
+                uint32_t cnt = nt; unsigned long long dst = (unsigned long long)carry + ex;
+                if (!PLAIN && nt) {
+                    // owning document = last document whose first-word reference is <= this word's index in the slice
+                    uint32_t lo = d_lo, hi = d_hi;
+                    while (lo < hi) { const uint32_t mid = lo + ((hi - lo) >> 1); if (__ldg(a.doc_word_ref + mid) <= k) lo = mid + 1; else hi = mid; }
+                    const uint32_t d = lo - 1;
+                    const uint32_t ds = __ldg(a.doc_tok_start + d);
+                    const unsigned long long doc_t = (unsigned long long)(__ldg(a.doc_tok_start + d + 1) - ds);
+                    unsigned long long kept;
+                    const unsigned long long olen = doc_out_len(p, doc_t, &kept);
+                    const unsigned long long j0 = (unsigned long long)(carry + ex) - ds;
+                    const unsigned long long room = j0 < kept ? kept - j0 : 0;
+                    if ((unsigned long long)cnt > room) cnt = (uint32_t)room;
+                    dst = a.doc_tok_off[d] + ((p.has_pad && p.pad_left) ? olen - kept : 0) + j0;
+                }
+                if (cnt && !is_long) {
+                    if (!(ey & TW_POOLF)) emit_real(p, o, dst, ea, ey & 0xFFu, (ey >> 8) & 0xFFu);
+                    else for (uint32_t i = 0; i < cnt; i++) {
                         const unsigned long long r = __ldcg(a.upool + ea + i);
-                        st_id[si + i] = (uint32_t)r; st_of[si + i] = (uint32_t)(r >> 32);
+                        emit_real(p, o, dst + i, (uint32_t)r, (uint32_t)(r >> 32) & 0xFFFFu, (uint32_t)(r >> 48));
                     }
                 }
-                __syncthreads();
-                // global index of staging slot i = (carry & ~3) + i; valid slots [mis, mis + tot)
-                const unsigned long long g0 = (unsigned long long)(carry & ~3u);
-                const uint32_t end = mis + tot;
-                for (uint32_t g = t * 4; g < end; g += TE_THREADS * 4) {
-                    if (g >= mis && g + 4 <= end) {
-                        const uint4 id4 = *reinterpret_cast<const uint4*>(st_id + g);
-                        *reinterpret_cast<uint4*>(o.ids + g0 + g) = id4;
-                        if (outputs & 2u) {
-                            const uint4 of4 = *reinterpret_cast<const uint4*>(st_of + g);
-                            uint4* dst = reinterpret_cast<uint4*>(o.offsets + 2 * (g0 + g));
-                            dst[0] = make_uint4(of4.x & 0xFFFFu, of4.x >> 16, of4.y & 0xFFFFu, of4.y >> 16);
-                            dst[1] = make_uint4(of4.z & 0xFFFFu, of4.z >> 16, of4.w & 0xFFFFu, of4.w >> 16);
-                        }
-                        if (outputs & 4u) *reinterpret_cast<uint4*>(o.attention + g0 + g) = make_uint4(1u, 1u, 1u, 1u);
-                        if (outputs & 8u) *reinterpret_cast<uint4*>(o.type_ids + g0 + g) = make_uint4(0u, 0u, 0u, 0u);
-                        if (outputs & 16u) *reinterpret_cast<uint4*>(o.special + g0 + g) = make_uint4(0u, 0u, 0u, 0u);
-                    } else {
-                        for (uint32_t j = g < mis ? mis : g; j < g + 4 && j < end; j++) {
-                            const uint32_t of = st_of[j];
-                            emit_real(p, o, g0 + j, st_id[j], of & 0xFFFFu, of >> 16);
-                        }
-                    }
+                // long-list words: tokens sit in the pool at the word's byte position; copied by the whole warp, or queued
+                // for the grid-wide copy when very long
+                uint32_t src = 0;
+                if (is_long && cnt) src = __ldg(a.long_start + ea);
+                if (is_long && cnt > EMIT_BIG && big_push(a.big, src, cnt, dst)) cnt = 0;
+                uint32_t big = __ballot_sync(FULL, cnt && is_long);
+                while (big) {
+                    const int l = __ffs(big) - 1; big &= big - 1;
+                    const uint32_t c = __shfl_sync(FULL, cnt, l), sp = __shfl_sync(FULL, src, l);
+                    const unsigned long long dd = __shfl_sync(FULL, dst, l);
+                    for (uint32_t i = lane; i < c; i += 32) emit_real(p, o, dd + i, a.pool_id[sp + i], a.pool_s[sp + i], a.pool_e[sp + i]);
                 }
-                __syncthreads();                            // staging is rewritten by the next round
+                if (PLAIN) gstart = (unsigned long long)carry + tot;
             }
+            carry += tot;
         }
-        if (!staged) {
-            // destination of the word's first token
-            uint32_t cnt = nt; unsigned long long dst = (unsigned long long)carry + ex;
-            if (!PLAIN && nt) {
-                // owning document = last document whose first-word reference is <= this word's index in the tile
-                uint32_t lo = d_lo, hi = d_hi;
-                while (lo < hi) { const uint32_t mid = lo + ((hi - lo) >> 1); if (__ldg(a.doc_word_ref + mid) <= k) lo = mid + 1; else hi = mid; }
-                const uint32_t d = lo - 1;
-                const uint32_t ds = __ldg(a.doc_tok_start + d);
-                const unsigned long long doc_t = (unsigned long long)(__ldg(a.doc_tok_start + d + 1) - ds);
-                unsigned long long kept;
-                const unsigned long long olen = doc_out_len(p, doc_t, &kept);
-                const unsigned long long j0 = (unsigned long long)(carry + ex) - ds;
-                const unsigned long long room = j0 < kept ? kept - j0 : 0;
-                if ((unsigned long long)cnt > room) cnt = (uint32_t)room;
-                dst = a.doc_tok_off[d] + ((p.has_pad && p.pad_left) ? olen - kept : 0) + j0;
-            }
-            if (cnt && !is_long) {
-                if (!(ey & TW_POOLF)) emit_real(p, o, dst, ea, ey & 0xFFu, (ey >> 8) & 0xFFu);
-                else for (uint32_t i = 0; i < cnt; i++) {
-                    const unsigned long long r = __ldcg(a.upool + ea + i);
-                    emit_real(p, o, dst + i, (uint32_t)r, (uint32_t)(r >> 32) & 0xFFFFu, (uint32_t)(r >> 48));
-                }
-            }
-            // long-list words: tokens sit in the pool at the word's byte position; copied by the whole warp, or queued for
-            // the grid-wide copy when very long
-            uint32_t src = 0;
-            if (is_long && cnt) src = __ldg(a.long_start + ea);
-            if (is_long && cnt > EMIT_BIG && big_push(a.big, src, cnt, dst)) cnt = 0;
-            uint32_t big = __ballot_sync(FULL, cnt && is_long);
-            while (big) {
-                const int l = __ffs(big) - 1; big &= big - 1;
-                const uint32_t c = __shfl_sync(FULL, cnt, l), s = __shfl_sync(FULL, src, l);
-                const unsigned long long dd = __shfl_sync(FULL, dst, l);
-                for (uint32_t i = lane; i < c; i += 32) emit_real(p, o, dd + i, a.pool_id[s + i], a.pool_s[s + i], a.pool_e[s + i]);
-            }
+        if (PLAIN) {
+            if (fill) te_flush(p, o, st, gstart, fill);
+            for (uint32_t d = d_lo + lane; d < d_hi; d += 32) a.doc_tok_off[d] = (unsigned long long)base + __ldg(a.doc_tok_local + d);
         }
-        carry += tot;
     }
-    if (PLAIN) for (uint32_t d = d_lo + t; d < d_hi; d += TE_THREADS) a.doc_tok_off[d] = (unsigned long long)base + a.doc_tok_local[d];
 }
 
 // per document: global token index of its start, real token count, output slot count (feeds the scan -> CSR offsets)
@@ -677,10 +744,10 @@ __global__ void doc_finish2_kernel(const uint64_t* __restrict__ doc_off, uint32_
                                    uint32_t* __restrict__ doc_real, unsigned long long* __restrict__ doc_tok_off) {
     const uint32_t d = blockIdx.x * blockDim.x + threadIdx.x;
     if (d > n_docs) return;
-    const uint32_t s0 = tile_tokbase[(uint32_t)(doc_off[d] / TW_TILE)] + doc_tok_local[d];
+    const uint32_t s0 = tile_tokbase[(uint32_t)(doc_off[d] / TW_SLICE)] + doc_tok_local[d];
     doc_tok_start[d] = s0;
     if (d < n_docs) {
-        const uint32_t s1 = tile_tokbase[(uint32_t)(doc_off[d + 1] / TW_TILE)] + doc_tok_local[d + 1];
+        const uint32_t s1 = tile_tokbase[(uint32_t)(doc_off[d + 1] / TW_SLICE)] + doc_tok_local[d + 1];
         const unsigned long long tr = s1 - s0;
         doc_real[d] = (uint32_t)tr;
         unsigned long long kept;
