@@ -209,6 +209,17 @@ extern "C" int tkz_ctx_create(int device, void* stream, uint64_t arena_hint_byte
         ctx->own_stream = true;
     }
     cudaFuncSetAttribute(bpe_block_kernel<1024, 12288>, cudaFuncAttributeMaxDynamicSharedMemorySize, 12288 * 15);
+    {
+        const int sm = (int)sizeof(TileShared);
+        cudaFuncSetAttribute(slice_words_kernel<TKZ_MODEL_BPE, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
+        cudaFuncSetAttribute(slice_words_kernel<TKZ_MODEL_BPE, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
+        cudaFuncSetAttribute(slice_words_kernel<TKZ_MODEL_BPE, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
+        cudaFuncSetAttribute(slice_words_kernel<TKZ_MODEL_BPE, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
+        cudaFuncSetAttribute(slice_words_kernel<TKZ_MODEL_WORDPIECE, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
+        cudaFuncSetAttribute(slice_words_kernel<TKZ_MODEL_WORDPIECE, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
+        cudaFuncSetAttribute(slice_words_kernel<TKZ_MODEL_WORDPIECE, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
+        cudaFuncSetAttribute(slice_words_kernel<TKZ_MODEL_WORDPIECE, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
+    }
     e = cudaFuncSetAttribute(bpe_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BPE_SMEM_BYTES);
     if (e != cudaSuccess) {
         g_create_error = std::string("kernel image not usable on this device (built for sm_100a): ") + cudaGetErrorString(e);
@@ -476,10 +487,11 @@ int launch_bpe(tkz_ctx* ctx, const DevModel& m, const uint8_t* d_text, const uin
 #define TKZ_RETRY_MULTIPASS 2
 template <int MODEL>
 void launch_slice_words(const DevModel& m, const TileArgs& ta, bool nid, bool iso, uint32_t blocks, cudaStream_t st) {
-    if (nid && !iso) slice_words_kernel<MODEL, true, false><<<blocks, TW_THREADS, 0, st>>>(m, ta);
-    else if (nid) slice_words_kernel<MODEL, true, true><<<blocks, TW_THREADS, 0, st>>>(m, ta);
-    else if (!iso) slice_words_kernel<MODEL, false, false><<<blocks, TW_THREADS, 0, st>>>(m, ta);
-    else slice_words_kernel<MODEL, false, true><<<blocks, TW_THREADS, 0, st>>>(m, ta);
+    const size_t sm = sizeof(TileShared);
+    if (nid && !iso) slice_words_kernel<MODEL, true, false><<<blocks, TW_THREADS, sm, st>>>(m, ta);
+    else if (nid) slice_words_kernel<MODEL, true, true><<<blocks, TW_THREADS, sm, st>>>(m, ta);
+    else if (!iso) slice_words_kernel<MODEL, false, false><<<blocks, TW_THREADS, sm, st>>>(m, ta);
+    else slice_words_kernel<MODEL, false, true><<<blocks, TW_THREADS, sm, st>>>(m, ta);
 }
 
 int encode_tiles(tkz_ctx* ctx, const DevModel& m, const uint8_t* d_text, const uint64_t* d_doc_off, uint32_t nd, uint64_t N,
@@ -500,19 +512,18 @@ int encode_tiles(tkz_ctx* ctx, const DevModel& m, const uint8_t* d_text, const u
     if (upool_cap < ctx->tw_upool_hist * 2) upool_cap = ctx->tw_upool_hist * 2;
     if (upool_cap > 0xFFFFFF00ull) upool_cap = 0xFFFFFF00ull;
     uint64_t ls_cap = N / 16 + (1u << 22); if (ls_cap > 0xFFFFFF00ull) ls_cap = 0xFFFFFF00ull;
-    // entry list: TW_REGIONS regions with one bump counter each (slice s -> region s & mask); small batches use one region
-    uint32_t regions = 1;
-    while (regions < TW_REGIONS && (uint64_t)n_tiles >= (uint64_t)regions * 2 * 4096) regions <<= 1;
+    // entry list: warps claim TW_ENT_CHUNK entries at a time (the unused tail of a chunk is lost)
+    const uint32_t grid = (uint32_t)std::min<uint64_t>(((uint64_t)n_tiles + TW_WARPS - 1) / TW_WARPS, (uint64_t)ctx->sm_count * 12);
     uint64_t ent_cap = N + 16;                                               // words <= bytes
     if (ctx->tw_words_per_byte > 0.0) { const uint64_t e2 = (uint64_t)((double)N * ctx->tw_words_per_byte * 1.25) + 65536; if (e2 < ent_cap) ent_cap = e2; }
     else if (N > (64ull << 20)) ent_cap = N / 2 + 65536;
-    const uint64_t region_cap = std::min<uint64_t>((ent_cap + regions - 1) / regions + 512, 0xFFFFFF00ull / regions);
+    ent_cap += ent_cap / 4 + std::min<uint64_t>(n_tiles, (uint64_t)grid * TW_WARPS) * TW_ENT_CHUNK;
+    if (ent_cap > 0xFFFFF000ull) ent_cap = 0xFFFFF000ull;
     const uint32_t long_cap = (uint32_t)(N / 256 + 1024);
     TRY(ensure(ctx, ctx->a_wtable, ((size_t)tcap + mcap) * sizeof(WordSlot)));
     TRY(ensure(ctx, ctx->a_upool, (size_t)upool_cap * 8));
     TRY(ensure(ctx, ctx->a_lscratch, (size_t)ls_cap * 4));
-    TRY(ensure(ctx, ctx->a_ent, (size_t)region_cap * regions * 8));
-    TRY(ensure(ctx, ctx->a_region_ctr, (size_t)TW_REGIONS * 128));
+    TRY(ensure(ctx, ctx->a_ent, (size_t)ent_cap * 8));
     TRY(ensure(ctx, ctx->a_tile_ent_off, ((size_t)n_tiles + 2) * 4));
     TRY(ensure(ctx, ctx->a_tile_nwords, ((size_t)n_tiles + 2) * 4));
     TRY(ensure(ctx, ctx->a_tile_ntok, ((size_t)n_tiles + 2) * 4));
@@ -525,21 +536,19 @@ int encode_tiles(tkz_ctx* ctx, const DevModel& m, const uint8_t* d_text, const u
     TRY(ensure(ctx, ctx->O().doc_tok_off, (n_docs + 1) * 8));
     TRY(ensure(ctx, ctx->a_scan_tmp, (scan_tmp_elems(n_tiles) + scan_tmp_elems(n_docs)) * 8));
     CK(cudaMemsetAsync(ctx->a_wtable.p, 0, ((size_t)tcap + mcap) * sizeof(WordSlot), st));
-    CK(cudaMemsetAsync(ctx->a_region_ctr.p, 0, (size_t)TW_REGIONS * 128, st));
     tile_doc_index_kernel<<<(n_tiles + 1 + 255) / 256, 256, 0, st>>>(d_doc_off, nd, n_tiles, TW_SLICE, (uint32_t*)ctx->a_tile_doc_lo.p); launches++;
     TileArgs ta{};
     ta.text = d_text; ta.n = N; ta.doc_off = d_doc_off; ta.n_docs = nd; ta.n_slices = n_tiles; ta.slice_doc_lo = (const uint32_t*)ctx->a_tile_doc_lo.p;
     ta.table = (WordSlot*)ctx->a_wtable.p; ta.table_mask = tcap - 1; ta.med_base = tcap; ta.med_mask = mcap - 1;
     ta.upool = (unsigned long long*)ctx->a_upool.p; ta.upool_cap = (uint32_t)upool_cap; ta.upool_count = (unsigned int*)(ctrl + 9);
     ta.lscratch = (uint32_t*)ctx->a_lscratch.p; ta.lscratch_cap = (uint32_t)ls_cap; ta.lscratch_count = (unsigned int*)(ctrl + 9) + 1;
-    ta.ent = (uint2*)ctx->a_ent.p; ta.region_cap = (uint32_t)region_cap; ta.region_mask = regions - 1; ta.region_count = (unsigned int*)ctx->a_region_ctr.p;
+    ta.ent = (uint2*)ctx->a_ent.p; ta.ent_cap = (uint32_t)ent_cap; ta.ent_count = (unsigned int*)(ctrl + 5);
     ta.slice_ent_off = (uint32_t*)ctx->a_tile_ent_off.p; ta.slice_nwords = (uint32_t*)ctx->a_tile_nwords.p; ta.slice_ntok = (uint32_t*)ctx->a_tile_ntok.p;
     ta.doc_word_ref = (uint32_t*)ctx->a_doc_word_ref.p; ta.doc_tok_local = (uint32_t*)ctx->a_doc_tok_local.p;
     ta.long_start = (uint32_t*)ctx->a_long_start.p; ta.long_end = (uint32_t*)ctx->a_long_end.p; ta.long_tile = (uint32_t*)ctx->a_long_tile.p;
     ta.n_long = (unsigned int*)(ctrl + 7); ta.long_cap = long_cap;
     ta.abort_flag = (unsigned int*)(ctrl + 8); ta.errw = ctrl;
     ta.n_words = ctrl + 10; ta.n_uniq = (unsigned int*)(ctrl + 6); ta.n_uncached = (unsigned int*)(ctrl + 6) + 1;
-    const uint32_t grid = (uint32_t)std::min<uint64_t>(((uint64_t)n_tiles + TW_WARPS - 1) / TW_WARPS, (uint64_t)ctx->sm_count * 8);
     if (m.kind == TKZ_MODEL_BPE) launch_slice_words<TKZ_MODEL_BPE>(m, ta, m.norm_identity != 0, ctx->has_iso, grid, st);
     else launch_slice_words<TKZ_MODEL_WORDPIECE>(m, ta, m.norm_identity != 0, ctx->has_iso, grid, st);
     launches++;
@@ -554,8 +563,7 @@ int encode_tiles(tkz_ctx* ctx, const DevModel& m, const uint8_t* d_text, const u
         ctx->tw_words_per_byte = 1.0;                       // the retry of a later batch gets the worst-case entry list
         return TKZ_RETRY_MULTIPASS;
     }
-    if (N) ctx->tw_words_per_byte = std::max(ctx->tw_words_per_byte, (double)hctrl[10] / (double)N);
-    ctx->stats.n_words = hctrl[10]; ctx->stats.n_unique_words = n_uniq + n_unc; ctx->stats.n_long_words = n_long;
+    ctx->stats.n_unique_words = n_uniq + n_unc; ctx->stats.n_long_words = n_long;
     ctx->stats.path = 2;
 
     // ---- the few pre-tokens longer than TW_MAX_INLINE bytes: per-occurrence word-list kernels, counts folded back in
@@ -624,6 +632,7 @@ int encode_tiles(tkz_ctx* ctx, const DevModel& m, const uint8_t* d_text, const u
     ea.pool_id = (const uint32_t*)ctx->a_pool_id.p; ea.pool_s = (const uint32_t*)ctx->a_pool_s.p; ea.pool_e = (const uint32_t*)ctx->a_pool_e.p;
     ea.doc_word_ref = ta.doc_word_ref; ea.doc_tok_local = ta.doc_tok_local; ea.doc_tok_start = (const uint32_t*)ctx->a_doc_tok_start.p;
     ea.doc_tok_off = doc_tok_off; ea.errw = ctrl; ea.err_code = m.kind == TKZ_MODEL_BPE ? TKZ_ECODE_UTF8 : TKZ_ECODE_UNK;
+    ea.n_words = ctrl + 10;
     ea.big = BigList{(uint4*)ctx->a_big.p, (unsigned int*)(ctrl + 16), big_cap};
     if (plain) slice_emit_kernel<true><<<grid, TW_THREADS, 0, st>>>(ea, ep, eo);
     else slice_emit_kernel<false><<<grid, TW_THREADS, 0, st>>>(ea, ep, eo);
@@ -634,9 +643,11 @@ int encode_tiles(tkz_ctx* ctx, const DevModel& m, const uint8_t* d_text, const u
     }
     CK(cudaGetLastError());
     CK(cudaEventRecord(ctx->ev[4], st));
-    if (n_long) CK(cudaMemcpyAsync(hctrl, ctrl, 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(hctrl, ctrl, 11 * 8, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     if (hctrl[0] != TKZ_ERRW_NONE) return fail(hctrl[0]);
+    ctx->stats.n_words = hctrl[10];
+    if (N) ctx->tw_words_per_byte = std::max(ctx->tw_words_per_byte, (double)hctrl[10] / (double)N);
     ctx->stats.kernel_launches = launches;
     cudaEventElapsedTime(&ctx->stats.ms_split, ctx->ev[0], ctx->ev[1]);
     cudaEventElapsedTime(&ctx->stats.ms_model, ctx->ev[1], ctx->ev[2]);

@@ -36,12 +36,12 @@
 
 namespace tkz {
 
-constexpr int TW_THREADS = 256, TW_WARPS = 8, TW_SEG = 16, TW_SLICE = 32 * TW_SEG;      // slice = 512 bytes = one 16-byte segment per lane
+constexpr int TW_THREADS = 256, TW_WARPS = 8, TW_SEG = 32, TW_SLICE = 32 * TW_SEG;      // slice = 1 KiB = one 32-byte segment per lane
 #ifndef TW_BPS
 #define TW_BPS 4
 #endif
 constexpr int TW_BLOCKS_PER_SM = TW_BPS;                // pass A: 40 registers per thread, 32 KB of shared memory per block
-constexpr int TW_REGIONS = 64;
+constexpr uint32_t TW_ENT_CHUNK = 4096;            // entries a warp claims from the entry list with one atomic (then sub-allocates)
 #ifndef TW_SLOWPATH
 #define TW_SLOWPATH __forceinline__
 #endif                    // entry list regions (one bump counter each, 128 bytes apart)
@@ -75,7 +75,7 @@ struct TileArgs {
     WordSlot* table; uint32_t table_mask; uint32_t med_base, med_mask;
     unsigned long long* upool; uint32_t upool_cap; unsigned int* upool_count;     // token records: id | start << 32 | end << 48
     uint32_t* lscratch; uint32_t lscratch_cap; unsigned int* lscratch_count;      // symbol arrays of words of 65..256 bytes
-    uint2* ent; uint32_t region_cap; uint32_t region_mask; unsigned int* region_count;   // word entries: slice s -> region s & mask
+    uint2* ent; uint32_t ent_cap; unsigned int* ent_count;                        // word entries: warps claim TW_ENT_CHUNK at a time
     uint32_t* slice_ent_off; uint32_t* slice_nwords; uint32_t* slice_ntok;
     uint32_t* doc_word_ref;                       // per document: slice-local index of the first word at or after its start
     uint32_t* doc_tok_local;                      // per document: tokens of its slice before that word
@@ -94,13 +94,15 @@ __global__ void tile_doc_index_kernel(const uint64_t* __restrict__ doc_off, uint
 }
 
 struct __align__(16) SliceShared {                                      // per warp
-    uint32_t text32[(TW_SLICE + 2 * TW_SEG) / 4 + 4];     // normalised slice + 2 halo segments
-    uint32_t cont32[(TW_SLICE + 2 * TW_SEG) / 32 + 2];    // bit p: byte p continues the word that started before it
-    uint32_t docbits[(TW_SLICE + 2 * TW_SEG) / 32 + 2];   // bit p: a document starts at slice_base + p
+    uint32_t text32[(TW_SLICE + 32) / 4 + 4];             // normalised slice + 32 halo bytes
+    uint32_t cont32[(TW_SLICE + 32) / 32 + 2];            // bit p: byte p continues the word that started before it
+    uint32_t docbits[(TW_SLICE + 32) / 32 + 2];           // bit p: a document starts at slice_base + p
     uint16_t wlist[TW_SLICE];                             // start positions of the slice's words (bit 15: ISOLATE byte)
     uint16_t wpfx[TW_SLICE];                              // tokens of the slice's words before word k
     uint32_t mscr[4][TW_MAX_MED];                         // model scratch: ids, starts, ends, pair ranks
     uint32_t wbytes[TW_MAX_MED / 4];                      // normalised bytes of the word the warp is tokenizing
+    uint32_t seg_smask[32], seg_wex[32];                  // per 32-byte segment: word-start bits, words of the slice before it
+    uint32_t doc_lo_hi[2];                                // documents that start inside the slice: [lo, hi)
 };
 struct TileShared {
     uint32_t lut[256];                                    // [7:0] normalised byte, bit 8 WORD, bit 9 ISOLATE
@@ -109,16 +111,16 @@ struct TileShared {
 };
 
 __device__ __forceinline__ void tw_ld256(const WordSlot* s, uint32_t (&r)[8]) {
-    asm volatile("ld.global.cg.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+    asm volatile("ld.global.ca.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                  : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "l"(s) : "memory");
 }
 __device__ __forceinline__ uint2 tw_ld_value(const WordSlot* s) {
     uint2 v;
-    asm volatile("ld.global.acquire.gpu.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(&s->a) : "memory");
+    asm volatile("ld.global.relaxed.gpu.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(&s->a) : "memory");
     return v;
 }
 __device__ __forceinline__ void tw_st_value(WordSlot* s, uint32_t a, uint32_t b) {
-    asm volatile("st.global.release.gpu.v2.u32 [%0], {%1,%2};" :: "l"(&s->a), "r"(a), "r"(b) : "memory");
+    asm volatile("st.global.relaxed.gpu.v2.u32 [%0], {%1,%2};" :: "l"(&s->a), "r"(a), "r"(b) : "memory");
 }
 // returns the previous 128-bit key
 __device__ __forceinline__ void tw_cas128(WordSlot* s, const uint32_t (&key)[4], uint32_t (&old)[4]) {
@@ -179,34 +181,63 @@ __device__ __forceinline__ bool tw_make_value(const TileArgs& a, const uint32_t*
 
 
 
-// classify + normalise one 16-byte segment; bytes at or beyond n read as DELIM.  Returns word mask | iso mask << 16.
+// classify + normalise one 32-byte segment (two 16-byte vector loads); bytes at or beyond n read as DELIM
 template <bool NORM_ID, bool HAS_ISO>
-__device__ __forceinline__ uint32_t tw_load_segment(const uint8_t* __restrict__ text, uint64_t n, uint64_t seg_base, uint32_t seg,
-                                                    const uint32_t* lut, uint32_t* text32) {
-    uint32_t raw[4] = {0, 0, 0, 0};
-    uint32_t valid = 0;
-    if (seg_base + TW_SEG <= n) {
-        const uint4 v = __ldg(reinterpret_cast<const uint4*>(text + seg_base));
-        raw[0] = v.x; raw[1] = v.y; raw[2] = v.z; raw[3] = v.w; valid = 0xFFFFu;
-    } else {
-        for (int k = 0; k < TW_SEG; k++) if (seg_base + k < n) { raw[k >> 2] |= (uint32_t)__ldg(text + seg_base + k) << ((k & 3) * 8); valid |= 1u << k; }
-    }
-    uint32_t word = 0, iso = 0, nrm[4];
+__device__ __forceinline__ void tw_load_segment(const uint8_t* __restrict__ text, uint64_t n, uint64_t seg_base, uint32_t seg,
+                                                const uint32_t* lut, uint32_t* text32, uint32_t& word_out, uint32_t& iso_out) {
+    uint32_t word = 0, iso = 0;
 #pragma unroll
-    for (int q = 0; q < 4; q++) {
-        uint32_t o = 0;
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-            const uint32_t e = lut[(raw[q] >> (8 * j)) & 0xFF];
-            word |= ((e >> 8) & 1u) << (q * 4 + j);
-            if (HAS_ISO) iso |= ((e >> 9) & 1u) << (q * 4 + j);
-            if (!NORM_ID) o |= (e & 0xFFu) << (8 * j);
+    for (int h = 0; h < 2; h++) {
+        const uint64_t hb = seg_base + 16 * h;
+        uint32_t raw[4] = {0, 0, 0, 0};
+        uint32_t valid = 0;
+        if (hb + 16 <= n) {
+            const uint4 v = __ldg(reinterpret_cast<const uint4*>(text + hb));
+            raw[0] = v.x; raw[1] = v.y; raw[2] = v.z; raw[3] = v.w; valid = 0xFFFFu;
+        } else {
+            for (int k = 0; k < 16; k++) if (hb + k < n) { raw[k >> 2] |= (uint32_t)__ldg(text + hb + k) << ((k & 3) * 8); valid |= 1u << k; }
         }
-        nrm[q] = NORM_ID ? raw[q] : o;
+        uint32_t w16 = 0, i16 = 0, nrm[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            uint32_t o = 0;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const uint32_t e = lut[(raw[q] >> (8 * j)) & 0xFF];
+                w16 |= ((e >> 8) & 1u) << (q * 4 + j);
+                if (HAS_ISO) i16 |= ((e >> 9) & 1u) << (q * 4 + j);
+                if (!NORM_ID) o |= (e & 0xFFu) << (8 * j);
+            }
+            nrm[q] = NORM_ID ? raw[q] : o;
+        }
+        word |= (w16 & valid) << (16 * h); iso |= (i16 & valid) << (16 * h);
+        *reinterpret_cast<uint4*>(text32 + seg * 8 + h * 4) = make_uint4(nrm[0], nrm[1], nrm[2], nrm[3]);
     }
-    word &= valid; iso &= valid;
-    *reinterpret_cast<uint4*>(text32 + seg * 4) = make_uint4(nrm[0], nrm[1], nrm[2], nrm[3]);
-    return word | (iso << 16);
+    word_out = word; iso_out = iso;
+}
+
+// exclusive prefix + total of per-lane values < 2^BITS with BITS ballots (no dependent shuffle chain)
+template <int BITS>
+__device__ __forceinline__ uint32_t tw_ballot_prefix(uint32_t v, uint32_t lt_mask, uint32_t& total) {
+    uint32_t ex = 0, tot = 0;
+#pragma unroll
+    for (int b = 0; b < BITS; b++) {
+        const uint32_t m = __ballot_sync(0xFFFFFFFFu, (v >> b) & 1u);
+        ex += __popc(m & lt_mask) << b; tot += __popc(m) << b;
+    }
+    total = tot;
+    return ex;
+}
+
+// 128-bit key of the word of `len` (<= 15) bytes at slice position p: the normalised bytes, length in the top byte
+__device__ __forceinline__ void tw_build_key(const SliceShared& sh, const uint4* lenmask, uint32_t p, uint32_t len, uint32_t (&key)[4]) {
+    const uint32_t wi = p >> 2, shb = (p & 3u) * 8u;
+    const uint32_t x0 = sh.text32[wi], x1 = sh.text32[wi + 1], x2 = sh.text32[wi + 2], x3 = sh.text32[wi + 3], x4 = sh.text32[wi + 4];
+    const uint4 mk = lenmask[len];
+    key[0] = __funnelshift_r(x0, x1, shb) & mk.x;
+    key[1] = __funnelshift_r(x1, x2, shb) & mk.y;
+    key[2] = __funnelshift_r(x2, x3, shb) & mk.z;
+    key[3] = (__funnelshift_r(x3, x4, shb) & mk.w) | (len << 24);
 }
 
 // One word that needs the whole warp (longer than 15 bytes, or no table slot within the probe limit): finds its end, then
@@ -215,7 +246,9 @@ __device__ __forceinline__ uint32_t tw_load_segment(const uint8_t* __restrict__ 
 struct WholeWarpOut { uint32_t a, b; bool abort; };
 template <int MODEL>
 __device__ TW_SLOWPATH WholeWarpOut tw_whole_warp_word(const DevModel& m, const TileArgs& a, const uint32_t* lut, SliceShared& sh, uint32_t s,
-                                                        uint64_t slice_base, uint32_t d_lo, uint32_t wp_, uint32_t wl_) {
+                                                        uint32_t wp_, uint32_t wl_) {
+    const uint64_t slice_base = (uint64_t)s * TW_SLICE;
+    const uint32_t d_lo = sh.doc_lo_hi[0];
     const uint32_t FULL = 0xFFFFFFFFu;
     const uint32_t lane = lane_id();
     uint8_t* const wbytes = reinterpret_cast<uint8_t*>(sh.wbytes);
@@ -362,7 +395,8 @@ __device__ TW_SLOWPATH WholeWarpOut tw_own_word(const DevModel& m, const TileArg
 // pass A: one warp per 512-byte slice, slices strided over all warps of the grid
 template <int MODEL, bool NORM_ID, bool HAS_ISO>
 __global__ void __launch_bounds__(TW_THREADS, TW_BLOCKS_PER_SM) slice_words_kernel(const __grid_constant__ DevModel m, const __grid_constant__ TileArgs a) {
-    __shared__ __align__(32) TileShared bs;
+    extern __shared__ __align__(32) unsigned char tw_smem_raw[];
+    TileShared& bs = *reinterpret_cast<TileShared*>(tw_smem_raw);
     const uint32_t FULL = 0xFFFFFFFFu;
     const uint32_t t = threadIdx.x, lane = t & 31, wid = t >> 5;
     const uint32_t lt_mask = (1u << lane) - 1u;
@@ -379,21 +413,26 @@ __global__ void __launch_bounds__(TW_THREADS, TW_BLOCKS_PER_SM) slice_words_kern
     __syncthreads();                                            // the only block-level barrier
     SliceShared& sh = bs.w[wid];
     const uint32_t stride = gridDim.x * TW_WARPS;
-    unsigned long long words_total = 0;
     bool warp_abort = false;
 
-    for (uint32_t s = blockIdx.x * TW_WARPS + wid; s < a.n_slices; s += stride) {
+    // first / last document of the warp's next slice are fetched one slice ahead (lanes 0, 1)
+    uint32_t s = blockIdx.x * TW_WARPS + wid;
+    uint32_t meta = (lane < 2 && s < a.n_slices) ? __ldg(a.slice_doc_lo + s + lane) : 0u;
+    uint32_t ecur = 0, eend = 0;                                // the warp's current chunk of the entry list
+    for (; s < a.n_slices; s += stride) {
         const uint64_t slice_base = (uint64_t)s * TW_SLICE;
-        const uint32_t d_lo = __ldg(a.slice_doc_lo + s), d_hi = __ldg(a.slice_doc_lo + s + 1);
+        const uint32_t d_lo = __shfl_sync(FULL, meta, 0);
+        if (lane < 2) sh.doc_lo_hi[lane] = meta;                   // the epilogue reads them back (not kept in registers)
+        meta = (lane < 2 && s + stride < a.n_slices) ? __ldg(a.slice_doc_lo + s + stride + lane) : 0u;
         // the warp's next slice: its text is pulled into L2 while this one is processed
-        if (lane < 5 && (uint64_t)(s + stride) * TW_SLICE + lane * 128 < a.n)
+        if (lane < 9 && (uint64_t)(s + stride) * TW_SLICE + lane * 128 < a.n)
             asm volatile("prefetch.global.L2 [%0];" :: "l"(a.text + (uint64_t)(s + stride) * TW_SLICE + lane * 128));
-        // ---- phase 1: document-start bits; classify + normalise one segment per lane (lanes 0, 1: also the 2 halo segments)
-        if (lane < (TW_SLICE + 2 * TW_SEG) / 32 + 2) { sh.docbits[lane] = 0; sh.cont32[lane] = 0; }
+        // ---- phase 1: document-start bits; classify + normalise one 32-byte segment per lane
+        for (uint32_t i = lane; i < (TW_SLICE + 32) / 32 + 2; i += 32) { sh.docbits[i] = 0; sh.cont32[i] = 0; }
         __syncwarp();
         for (uint32_t d = d_lo + lane; d <= a.n_docs; d += 32) {
             const uint64_t off = __ldg(a.doc_off + d);
-            if (off > slice_base + TW_SLICE + 2 * TW_SEG) break;
+            if (off > slice_base + TW_SLICE + 32) break;
             const uint32_t p = (uint32_t)(off - slice_base);
             atomicOr(&sh.docbits[p >> 5], 1u << (p & 31));
         }
@@ -402,46 +441,43 @@ __global__ void __launch_bounds__(TW_THREADS, TW_BLOCKS_PER_SM) slice_words_kern
         if (lane == 0 && slice_base > 0 && slice_base - 1 < a.n) prev_byte_word = (bs.lut[__ldg(a.text + slice_base - 1)] >> 8) & 1u;
         uint32_t halo_e = 0;
         { const uint64_t hp = slice_base + TW_SLICE + lane; if (hp < a.n) halo_e = bs.lut[__ldg(a.text + hp)]; }
-        const uint32_t sw = tw_load_segment<NORM_ID, HAS_ISO>(a.text, a.n, slice_base + (uint64_t)lane * TW_SEG, lane, bs.lut, sh.text32);
+        uint32_t word, iso;
+        tw_load_segment<NORM_ID, HAS_ISO>(a.text, a.n, slice_base + (uint64_t)lane * TW_SEG, lane, bs.lut, sh.text32, word, iso);
         reinterpret_cast<uint8_t*>(sh.text32)[TW_SLICE + lane] = (uint8_t)halo_e;
         __syncwarp();
 
         // ---- phase 2: word starts, continuation bits, word list
-        const uint32_t word = sw & 0xFFFFu, iso = sw >> 16;
-        uint32_t smask, wex, nW;
+        uint32_t nW;
         {
-            uint32_t prev_word = __shfl_up_sync(FULL, word >> 15, 1);
+            uint32_t smask, wex;
+            uint32_t prev_word = __shfl_up_sync(FULL, word >> 31, 1);
             if (lane == 0) prev_word = prev_byte_word;
-            const uint32_t ds = (sh.docbits[lane >> 1] >> ((lane & 1u) * 16)) & 0xFFFFu;
-            const uint32_t word_prev = ((word << 1) | prev_word) & 0xFFFFu;
-            smask = (iso | (word & (~word_prev | ds))) & 0xFFFFu;
-            const uint32_t cont = word & ~smask;
-            // halo bytes 512..543: continuation bits from the per-lane class bits (same formula, 32 bits wide)
+            const uint32_t ds = sh.docbits[lane];
+            smask = iso | (word & (~((word << 1) | prev_word) | ds));
+            sh.cont32[lane] = word & ~smask;
+            // halo bytes: continuation bits from the per-lane class bits (same formula)
             const uint32_t hw = __ballot_sync(FULL, (halo_e >> 8) & 1u), hi = HAS_ISO ? __ballot_sync(FULL, (halo_e >> 9) & 1u) : 0u;
-            const uint32_t w31 = __shfl_sync(FULL, word >> 15, 31);
-            const uint32_t hs = hi | (hw & (~((hw << 1) | w31) | sh.docbits[16]));
-            const uint32_t partner = __shfl_xor_sync(FULL, cont, 1);
-            if (!(lane & 1u)) sh.cont32[lane >> 1] = cont | (partner << 16);
-            if (lane == 0) sh.cont32[16] = hw & ~hs;
+            const uint32_t w31 = __shfl_sync(FULL, word >> 31, 31);
+            const uint32_t hs = hi | (hw & (~((hw << 1) | w31) | sh.docbits[32]));
+            if (lane == 0) sh.cont32[32] = hw & ~hs;
             const uint32_t cnt = __popc(smask);
-            const uint32_t inc = warp_incl_scan(cnt);
-            wex = inc - cnt;
+            wex = tw_ballot_prefix<6>(cnt, lt_mask, nW);
+            sh.seg_smask[lane] = smask; sh.seg_wex[lane] = wex;
             uint32_t sm = smask, k = wex;
             while (sm) {
                 const int b = __ffs(sm) - 1; sm &= sm - 1;
                 sh.wlist[k++] = (uint16_t)((lane * TW_SEG + b) | (((iso >> b) & 1u) << 15));
             }
-            nW = __shfl_sync(FULL, inc, 31);
         }
-        // reserve the slice's part of the entry list (region s & mask, one bump counter per region)
-        uint32_t entoff = TW_NONE;
-        if (lane == 0 && nW) {
-            const uint32_t r = s & a.region_mask;
-            const uint32_t eb = atomicAdd(a.region_count + r * 32, nW);
-            if ((unsigned long long)eb + nW > a.region_cap) atomicExch(a.abort_flag, 1u);
-            else entoff = r * a.region_cap + eb;
+        // reserve the slice's part of the entry list: the warp sub-allocates from a chunk it claimed with one atomic
+        if (ecur + nW > eend) {
+            uint32_t c = 0;
+            if (lane == 0) c = atomicAdd(a.ent_count, TW_ENT_CHUNK);
+            ecur = __shfl_sync(FULL, c, 0); eend = ecur + TW_ENT_CHUNK;
+            if ((unsigned long long)eend > a.ent_cap) { if (lane == 0) atomicExch(a.abort_flag, 1u); eend = ecur; }
         }
-        words_total += nW;
+        const uint32_t entoff = ecur + nW <= eend ? ecur : TW_NONE;
+        if (entoff != TW_NONE) ecur += nW;
         __syncwarp();
 
         // ---- phase 3: one word per lane
@@ -450,7 +486,6 @@ __global__ void __launch_bounds__(TW_THREADS, TW_BLOCKS_PER_SM) slice_words_kern
             const uint32_t k = k0 + lane;
             const bool have = k < nW;
             uint32_t p = 0, len = 0, va = 0, vb = 0, myslot = 0;
-            uint32_t key[4] = {0, 0, 0, 0};
             int state = 0;                                          // 0 done, 1 owner, 2 pending, 3 whole warp needed
             if (have) {
                 const uint32_t pw = sh.wlist[k];
@@ -463,13 +498,8 @@ __global__ void __launch_bounds__(TW_THREADS, TW_BLOCKS_PER_SM) slice_words_kern
                     if (len == 0) len = 33;
                 }
                 if (len <= TW_MAX_SHORT) {
-                    const uint32_t wi = p >> 2, shb = (p & 3u) * 8u;
-                    const uint32_t x0 = sh.text32[wi], x1 = sh.text32[wi + 1], x2 = sh.text32[wi + 2], x3 = sh.text32[wi + 3], x4 = sh.text32[wi + 4];
-                    const uint4 mk = bs.lenmask[len];
-                    key[0] = __funnelshift_r(x0, x1, shb) & mk.x;
-                    key[1] = __funnelshift_r(x1, x2, shb) & mk.y;
-                    key[2] = __funnelshift_r(x2, x3, shb) & mk.z;
-                    key[3] = (__funnelshift_r(x3, x4, shb) & mk.w) | (len << 24);
+                    uint32_t key[4];
+                    tw_build_key(sh, bs.lenmask, p, len, key);
                     uint32_t slot = tw_key_hash(key[0], key[1], key[2], key[3]) & a.table_mask;
                     state = 3;
                     for (int probe = 0; probe < TW_MAX_PROBE; probe++) {
@@ -495,8 +525,9 @@ __global__ void __launch_bounds__(TW_THREADS, TW_BLOCKS_PER_SM) slice_words_kern
             if (owners && lane == 0) atomicAdd(a.n_uniq, (unsigned int)__popc(owners));
             while (owners) {
                 const int l = __ffs(owners) - 1; owners &= owners - 1;
-                const WholeWarpOut r = tw_own_word<MODEL>(m, a, sh, __shfl_sync(FULL, key[0], l), __shfl_sync(FULL, key[1], l), __shfl_sync(FULL, key[2], l),
-                                                          __shfl_sync(FULL, key[3], l), __shfl_sync(FULL, myslot, l));
+                uint32_t okey[4];                                   // the owner's key again (not kept live across the round)
+                tw_build_key(sh, bs.lenmask, __shfl_sync(FULL, p, l), __shfl_sync(FULL, len, l), okey);
+                const WholeWarpOut r = tw_own_word<MODEL>(m, a, sh, okey[0], okey[1], okey[2], okey[3], __shfl_sync(FULL, myslot, l));
                 if (r.abort) warp_abort = true;
                 if ((int)lane == l) { va = r.a; vb = r.b; state = 0; }
             }
@@ -504,7 +535,7 @@ __global__ void __launch_bounds__(TW_THREADS, TW_BLOCKS_PER_SM) slice_words_kern
             uint32_t todo = __ballot_sync(FULL, state == 3);
             while (todo) {
                 const int l = __ffs(todo) - 1; todo &= todo - 1;
-                const WholeWarpOut r = tw_whole_warp_word<MODEL>(m, a, bs.lut, sh, s, slice_base, d_lo, __shfl_sync(FULL, p, l), __shfl_sync(FULL, len, l));
+                const WholeWarpOut r = tw_whole_warp_word<MODEL>(m, a, bs.lut, sh, s, __shfl_sync(FULL, p, l), __shfl_sync(FULL, len, l));
                 if (r.abort) warp_abort = true;
                 if ((int)lane == l) { va = r.a; vb = r.b; state = 0; }
             }
@@ -526,11 +557,12 @@ __global__ void __launch_bounds__(TW_THREADS, TW_BLOCKS_PER_SM) slice_words_kern
                 ey = (nt << 16) | (vb & 0xFFFFu) | (vb & (TW_POOLF | TW_LONGF));
                 if (vb & TW_LONGF) nt = 0;                          // counted after the word-list kernels (long_fix_kernel)
             }
-            const uint32_t eo_ = __shfl_sync(FULL, entoff, 0);
-            if (have && eo_ != TW_NONE) a.ent[(size_t)eo_ + k] = make_uint2(va, ey);
-            const uint32_t inc = warp_incl_scan(nt);
-            if (have) sh.wpfx[k] = (uint16_t)(run + inc - nt);
-            run += __shfl_sync(FULL, inc, 31);
+            if (have && entoff != TW_NONE) a.ent[(size_t)entoff + k] = make_uint2(va, ey);
+            uint32_t ex, tot;
+            if (!__any_sync(FULL, nt > 3)) ex = tw_ballot_prefix<2>(nt, lt_mask, tot);
+            else { const uint32_t inc = warp_incl_scan(nt); ex = inc - nt; tot = __shfl_sync(FULL, inc, 31); }
+            if (have) sh.wpfx[k] = (uint16_t)(run + ex);
+            run += tot;
         }
         if (lane == 0) {
             a.slice_ent_off[s] = entoff == TW_NONE ? 0u : entoff;
@@ -539,13 +571,12 @@ __global__ void __launch_bounds__(TW_THREADS, TW_BLOCKS_PER_SM) slice_words_kern
         }
         __syncwarp();
         // ---- token prefix + word index at every document start inside the slice
-        for (uint32_t d0 = d_lo; d0 < d_hi; d0 += 32) {
-            const uint32_t d = d0 + lane;
-            const bool valid = d < d_hi;
-            const uint32_t q = valid ? (uint32_t)(__ldg(a.doc_off + d) - slice_base) : 0u;
-            const uint32_t sg = q >> 4;
-            const uint32_t idx = __shfl_sync(FULL, wex, sg) + __popc(__shfl_sync(FULL, smask, sg) & ((1u << (q & 15u)) - 1u));
-            if (valid) {
+        {
+            const uint32_t dlo = sh.doc_lo_hi[0], dhi = sh.doc_lo_hi[1];
+            for (uint32_t d = dlo + lane; d < dhi; d += 32) {
+                const uint32_t q = (uint32_t)(__ldg(a.doc_off + d) - (uint64_t)s * TW_SLICE);
+                const uint32_t sg = q >> 5;
+                const uint32_t idx = sh.seg_wex[sg] + __popc(sh.seg_smask[sg] & ((1u << (q & 31u)) - 1u));
                 a.doc_tok_local[d] = idx < nW ? (uint32_t)sh.wpfx[idx] : run;
                 a.doc_word_ref[d] = idx;
             }
@@ -553,8 +584,6 @@ __global__ void __launch_bounds__(TW_THREADS, TW_BLOCKS_PER_SM) slice_words_kern
         __syncwarp();
     }
     if (__any_sync(FULL, warp_abort) && lane == 0) atomicExch(a.abort_flag, 1u);
-    if (lane == 0 && words_total) atomicAdd(a.n_words, words_total);
-    (void)lt_mask;
 }
 
 // after the word-list kernels: the tokens of every long word join its tile's count and the token prefix of the documents
@@ -584,6 +613,7 @@ struct TileEmitArgs {
     const uint32_t* doc_tok_start;                // !PLAIN: global real-token index at each document start (n_docs + 1)
     unsigned long long* doc_tok_off;              // PLAIN: written here; !PLAIN: read (CSR after truncate / pad)
     unsigned long long* errw; uint32_t err_code;
+    unsigned long long* n_words;                  // statistics: pre-tokens of the batch
     BigList big;
 };
 constexpr uint32_t TE_STAGE = 256;                // tokens a warp stages in shared memory before one coalesced flush
@@ -641,8 +671,10 @@ __global__ void __launch_bounds__(TW_THREADS, 6) slice_emit_kernel(const __grid_
     };
     uint32_t s = blockIdx.x * TW_WARPS + wid;
     uint32_t meta = load_meta(s);
+    uint32_t words_total = 0;
     for (; s < a.n_slices; s += stride) {
         const uint32_t nw = __shfl_sync(FULL, meta, 0);
+        words_total += nw;
         const uint2* __restrict__ ent = a.ent + __shfl_sync(FULL, meta, 1);
         const uint32_t base = __shfl_sync(FULL, meta, 2);
         const uint32_t d_lo = __shfl_sync(FULL, meta, 3), d_hi = __shfl_sync(FULL, meta, 4);
@@ -736,6 +768,7 @@ __global__ void __launch_bounds__(TW_THREADS, 6) slice_emit_kernel(const __grid_
             for (uint32_t d = d_lo + lane; d < d_hi; d += 32) a.doc_tok_off[d] = (unsigned long long)base + __ldg(a.doc_tok_local + d);
         }
     }
+    if (lane == 0 && words_total) atomicAdd(a.n_words, (unsigned long long)words_total);
 }
 
 // per document: global token index of its start, real token count, output slot count (feeds the scan -> CSR offsets)
