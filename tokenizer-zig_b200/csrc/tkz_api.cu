@@ -77,6 +77,8 @@ struct tkz_ctx {
     uint64_t tw_upool_hist = 0;           // most token records used by one batch
     double tw_words_per_byte = 0.0;       // densest batch so far: sizes the entry list
     HostBuf h_ctrl, h_doc_tok_off, h_ids, h_off, h_attn, h_type, h_special;
+    unsigned long long* h_ctrl_dev = nullptr;   // device alias of h_ctrl (mapped pinned memory): scalars are read back by a tiny
+                                                // kernel, not by a D2H memcpy that would queue behind the result copies
     uint64_t arena_bytes = 0;
     tkz_stats stats{};
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // stage boundaries of the last encode
@@ -139,6 +141,18 @@ __global__ void ctrl_reset_kernel(unsigned long long* ctrl) {
     //                [10] n_words, [11..12] block-kernel work counters, [13..15] long-word length classes, [16] big-copy list
     ctrl[0] = TKZ_ERRW_NONE;
     for (int i = 1; i < 32; i++) ctrl[i] = 0;
+}
+// scalars -> mapped host memory, in stream order (replaces small D2H memcpys: those share the copy engine's queue with the
+// multi-megabyte result copies of the previous chunk and would stall the kernels of this one behind them)
+__global__ void publish_kernel(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, uint32_t n) {
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i];
+    __threadfence_system();
+}
+int readback(tkz_ctx* ctx, unsigned long long* h_dst, const void* d_src, size_t bytes) {
+    unsigned long long* hbase = (unsigned long long*)ctx->h_ctrl.p;
+    uint32_t* dst = (uint32_t*)(ctx->h_ctrl_dev + (h_dst - hbase));
+    publish_kernel<<<1, 32, 0, ctx->stream>>>((const uint32_t*)d_src, dst, (uint32_t)(bytes / 4));
+    return TKZ_OK;
 }
 #define TKZ_RETRY_NO_DEDUP 1
 __global__ void tile_words_total_kernel(const uint32_t* tile_nwords, uint32_t n_tiles, unsigned long long* ctrl) {
@@ -226,9 +240,13 @@ extern "C" int tkz_ctx_create(int device, void* stream, uint64_t arena_hint_byte
         if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
         delete ctx; return TKZ_ERR_CUDA;
     }
-    if (ensure(ctx, ctx->a_ctrl, 64 * sizeof(unsigned long long)) != TKZ_OK || ensure_host(ctx, ctx->h_ctrl, 64 * sizeof(unsigned long long)) != TKZ_OK) {
-        g_create_error = ctx->err; if (ctx->own_stream) cudaStreamDestroy(ctx->stream); delete ctx; return TKZ_ERR_OOM;
+    if (ensure(ctx, ctx->a_ctrl, 64 * sizeof(unsigned long long)) != TKZ_OK ||
+        cudaHostAlloc(&ctx->h_ctrl.p, 64 * sizeof(unsigned long long), cudaHostAllocMapped) != cudaSuccess ||
+        cudaHostGetDevicePointer((void**)&ctx->h_ctrl_dev, ctx->h_ctrl.p, 0) != cudaSuccess) {
+        g_create_error = ctx->err.empty() ? "cudaHostAlloc (mapped control block) failed" : ctx->err;
+        if (ctx->own_stream) cudaStreamDestroy(ctx->stream); delete ctx; return TKZ_ERR_OOM;
     }
+    ctx->h_ctrl.cap = 64 * sizeof(unsigned long long);
     (void)arena_hint_bytes;
     if (const char* e = getenv("TKZ_NO_DEDUP")) ctx->use_dedup = !(e[0] == '1');     // A/B switch for the parity tests
     if (const char* e = getenv("TKZ_FUSED_EMIT")) ctx->use_fused = (e[0] == '1');
@@ -553,7 +571,7 @@ int encode_tiles(tkz_ctx* ctx, const DevModel& m, const uint8_t* d_text, const u
     else launch_slice_words<TKZ_MODEL_WORDPIECE>(m, ta, m.norm_identity != 0, ctx->has_iso, grid, st);
     launches++;
     if (m.kind == TKZ_MODEL_BPE) { len_class_count_kernel<<<128, 256, 0, st>>>(ta.long_start, ta.long_end, 0, ta.n_long, ctrl + 13); launches++; }
-    CK(cudaMemcpyAsync(hctrl, ctrl, 16 * 8, cudaMemcpyDeviceToHost, st));
+    TRY(readback(ctx, hctrl, ctrl, 16 * 8));
     CK(cudaEventRecord(ctx->ev[1], st));
     CK(cudaStreamSynchronize(st));
     const uint32_t n_uniq = (uint32_t)hctrl[6], n_unc = (uint32_t)(hctrl[6] >> 32), n_long = (uint32_t)hctrl[7];
@@ -596,15 +614,15 @@ int encode_tiles(tkz_ctx* ctx, const DevModel& m, const uint8_t* d_text, const u
         doc_finish2_kernel<<<(nd + 1 + 255) / 256, 256, 0, st>>>(d_doc_off, nd, ta.slice_ntok, ta.doc_tok_local, ep, (uint32_t*)ctx->a_doc_tok_start.p,
                                                                   (uint32_t*)ctx->a_doc_real.p, doc_tok_off); launches++;
         launches += exclusive_scan<unsigned long long>(doc_tok_off, n_docs, doc_tok_off, (unsigned long long*)ctx->a_scan_tmp.p, st);
-        CK(cudaMemcpyAsync(hctrl + 3, doc_tok_off + n_docs, 8, cudaMemcpyDeviceToHost, st));
+        TRY(readback(ctx, hctrl + 3, doc_tok_off + n_docs, 8));
     }
-    CK(cudaMemcpyAsync(hctrl + 32, ta.slice_ntok + n_tiles, 4, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(hctrl, ctrl, 8, cudaMemcpyDeviceToHost, st));
+    TRY(readback(ctx, hctrl + 32, ta.slice_ntok + n_tiles, 4));
+    TRY(readback(ctx, hctrl, ctrl, 8));
     CK(cudaStreamSynchronize(st));
     const uint64_t T_real = (uint32_t)hctrl[32], T = plain ? T_real : hctrl[3];
     auto fail = [&](unsigned long long errw) -> int {
         err_doc_kernel<<<1, 1, 0, st>>>(ctrl, d_doc_off, nd); launches++;
-        cudaMemcpyAsync(hctrl + 4, ctrl + 4, 8, cudaMemcpyDeviceToHost, st);
+        readback(ctx, hctrl + 4, ctrl + 4, 8);
         cudaStreamSynchronize(st);
         out->err_doc = (int64_t)hctrl[4];
         const uint32_t code = (uint32_t)(errw & 0xFF);
@@ -643,7 +661,7 @@ int encode_tiles(tkz_ctx* ctx, const DevModel& m, const uint8_t* d_text, const u
     }
     CK(cudaGetLastError());
     CK(cudaEventRecord(ctx->ev[4], st));
-    CK(cudaMemcpyAsync(hctrl, ctrl, 11 * 8, cudaMemcpyDeviceToHost, st));
+    TRY(readback(ctx, hctrl, ctrl, 11 * 8));
     CK(cudaStreamSynchronize(st));
     if (hctrl[0] != TKZ_ERRW_NONE) return fail(hctrl[0]);
     ctx->stats.n_words = hctrl[10];
@@ -710,8 +728,8 @@ int encode_dedup(tkz_ctx* ctx, const DevModel& m, const uint8_t* d_text, const u
         launches++;
     }
     if (m.kind == TKZ_MODEL_BPE) { len_class_count_kernel<<<128, 256, 0, st>>>(da.long_start, da.long_end, 0, da.n_long, ctrl + 13); launches++; }
-    CK(cudaMemcpyAsync(hctrl + 16, ctrl + 6, 3 * 8, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(hctrl + 24, ctrl + 13, 3 * 8, cudaMemcpyDeviceToHost, st));
+    TRY(readback(ctx, hctrl + 16, ctrl + 6, 3 * 8));
+    TRY(readback(ctx, hctrl + 24, ctrl + 13, 3 * 8));
     CK(cudaEventRecord(ctx->ev[1], st));
     CK(cudaStreamSynchronize(st));
     const uint32_t n_uniq = (uint32_t)hctrl[16], n_uniq_med = (uint32_t)(hctrl[16] >> 32), n_long = (uint32_t)hctrl[17];
@@ -784,8 +802,8 @@ int encode_dedup(tkz_ctx* ctx, const DevModel& m, const uint8_t* d_text, const u
         tile_emit_fused_kernel<<<n_tiles, DT_THREADS, 0, st>>>(ta, ep, eo, fa); launches++;
         if (n_long) { emit_big_kernel<<<ctx->sm_count * 4, 256, 0, st>>>(ep, eo, ta.big, ta.pool_id, ta.pool_s, ta.pool_e); launches++; }
         tile_words_total_kernel<<<64, 256, 0, st>>>(da.tile_nwords, n_tiles, ctrl); launches++;
-        CK(cudaMemcpyAsync(hctrl, ctrl, 13 * 8, cudaMemcpyDeviceToHost, st));
-        CK(cudaMemcpyAsync(hctrl + 32, (unsigned long long*)ctx->a_tile_state.p + (n_tiles - 1), 8, cudaMemcpyDeviceToHost, st));
+        TRY(readback(ctx, hctrl, ctrl, 13 * 8));
+        TRY(readback(ctx, hctrl + 32, (unsigned long long*)ctx->a_tile_state.p + (n_tiles - 1), 8));
         CK(cudaEventRecord(ctx->ev[4], st));
         CK(cudaStreamSynchronize(st));
         const bool overflow = (hctrl[12] >> 32) != 0;
@@ -829,7 +847,7 @@ int encode_dedup(tkz_ctx* ctx, const DevModel& m, const uint8_t* d_text, const u
     doc_finish_kernel<<<(nd + 1 + 255) / 256, 256, 0, st>>>(ta, ep, (uint32_t*)ctx->a_doc_real.p); launches++;
     launches += exclusive_scan<unsigned long long>(ta.doc_tok_off, n_docs, ta.doc_tok_off, (unsigned long long*)ctx->a_scan_tmp.p, st);
     gather_scalars_dedup_kernel<<<1, 1, 0, st>>>(ctrl, ta.tile_ntok, n_tiles, ta.doc_tok_off, nd, da.doc_word_ref); launches++;
-    CK(cudaMemcpyAsync(hctrl, ctrl, 11 * 8, cudaMemcpyDeviceToHost, st));
+    TRY(readback(ctx, hctrl, ctrl, 11 * 8));
     CK(cudaStreamSynchronize(st));
     const unsigned long long errw = hctrl[0];
     const uint64_t T_real = hctrl[2], T = hctrl[3];
@@ -921,7 +939,7 @@ int encode_device_impl(tkz_ctx* ctx, const uint8_t* d_text, const uint64_t* d_do
         launches += exclusive_scan<uint32_t>(chunk, n_chunks, chunk, (unsigned long long*)ctx->a_scan_tmp.p, st);
         norm_write_kernel<<<(unsigned)n_chunks, 256, 0, st>>>(m, d_text, N, chunk, (uint8_t*)ctx->a_norm_text.p); launches++;
         norm_docoff_kernel<<<(unsigned)((n_docs + 1 + 255) / 256), 256, 0, st>>>(m, d_text, N, chunk, d_doc_off, nd, (uint64_t*)ctx->a_norm_doc_off.p); launches++;
-        CK(cudaMemcpyAsync(hctrl + 8, chunk + n_chunks, 4, cudaMemcpyDeviceToHost, st));
+        TRY(readback(ctx, hctrl + 8, chunk + n_chunks, 4));
         CK(cudaStreamSynchronize(st));
         N = *(uint32_t*)(hctrl + 8);
         d_text = (const uint8_t*)ctx->a_norm_text.p;
@@ -955,7 +973,7 @@ int encode_device_impl(tkz_ctx* ctx, const uint8_t* d_text, const uint64_t* d_do
         unsigned long long* tiles = (unsigned long long*)ctx->a_tiles.p;
         split_count_kernel<<<(unsigned)n_tiles, SPLIT_THREADS, 0, st>>>(m, d_text, N, d_doc_off, nd, tiles); launches++;
         launches += exclusive_scan<unsigned long long>(tiles, n_tiles, tiles, (unsigned long long*)ctx->a_scan_tmp.p, st);
-        CK(cudaMemcpyAsync(hctrl + 8, tiles + n_tiles, 8, cudaMemcpyDeviceToHost, st));
+        TRY(readback(ctx, hctrl + 8, tiles + n_tiles, 8));
         CK(cudaStreamSynchronize(st));
         const unsigned long long tot = hctrl[8];
         W = tot >> 32;
@@ -989,7 +1007,7 @@ int encode_device_impl(tkz_ctx* ctx, const uint8_t* d_text, const uint64_t* d_do
     if (nw) {
         if (m.kind == TKZ_MODEL_BPE) {
             len_class_count_kernel<<<128, 256, 0, st>>>(word_start, word_end, nw, nullptr, ctrl + 13); launches++;
-            CK(cudaMemcpyAsync(hctrl + 24, ctrl + 13, 3 * 8, cudaMemcpyDeviceToHost, st));
+            TRY(readback(ctx, hctrl + 24, ctrl + 13, 3 * 8));
             CK(cudaStreamSynchronize(st));
             TRY(launch_bpe(ctx, m, d_text, word_start, word_end, nw, word_ntok, ctrl, 1, 0, hctrl + 24, N, launches));
         } else {
@@ -1013,7 +1031,7 @@ int encode_device_impl(tkz_ctx* ctx, const uint8_t* d_text, const uint64_t* d_do
     if (nd) { doc_len_kernel<<<(nd + 255) / 256, 256, 0, st>>>(ep, word_tok_off, doc_word_off, nd, doc_tok_off); launches++; }
     launches += exclusive_scan<unsigned long long>(doc_tok_off, n_docs, doc_tok_off, (unsigned long long*)ctx->a_scan_tmp.p, st);
     gather_scalars_kernel<<<1, 1, 0, st>>>(ctrl, word_tok_off, nw, doc_tok_off, nd, word_doc); launches++;
-    CK(cudaMemcpyAsync(hctrl, ctrl, 5 * 8, cudaMemcpyDeviceToHost, st));
+    TRY(readback(ctx, hctrl, ctrl, 5 * 8));
     CK(cudaStreamSynchronize(st));
     const unsigned long long errw = hctrl[0];
     const uint64_t T_real = hctrl[2], T = hctrl[3];
