@@ -322,17 +322,24 @@ def run_ours(args, rank, local_rank, world):
     # roofline of the dominant kernel stage: algorithmic bytes of one step / that stage's device time in one step
     per_step_ms = [x / args.steps for x in agg["ms"]]
     names = ["split (K0+K1)", "model (K3 bpe | K4 wordpiece)", "scan", "emit (K5)"]
-    path_name = {0: "per-occurrence pipeline", 1: "dedup multi-pass pipeline", 2: "tile pipeline (2 passes)"}.get(agg.get("path"), "?")
+    path_name = {0: "per-occurrence pipeline", 1: "dedup multi-pass pipeline", 2: "slice pipeline (2 passes)"}.get(agg.get("path"), "?")
     if agg.get("path") == 2:
-        names[0] = "tile_words_kernel (pass A: split + word-table probe + inline model)"
+        names[0] = "slice_words_kernel (pass A: normalise + split + word-table probe + inline model)"
         names[1] = "word-list kernels (pre-tokens > 256 B)"
-        names[3] = "tile_emit_kernel (pass B)"
+        names[3] = "slice_emit_kernel (pass B: fromTokens + truncate + pad)"
     dom = int(np.argmax(per_step_ms[:4]))
     b_alg = nbytes + 4 * agg["tokens"]                       # input bytes + 4 B x id slots written (one rank)
     b_full = nbytes + (4 + (8 if params.outputs & 2 else 0) + (4 if params.outputs & 4 else 0)) * agg["tokens"]
     ach_dom = b_alg / (per_step_ms[dom] * 1e-3) / 1e9 if per_step_ms[dom] > 0 else 0.0
     ach_pipe = b_alg / (ms_step * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": names[dom], "achieved": ach_dom, "peak": peak, "unit": "GB/s", "frac": ach_dom / peak, "traffic": None,
+    traffic = None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(f"{args.workload}:{args.size_mib}")
+        if tj and agg.get("path") == 2:
+            traffic = tj.get("slice_words_kernel" if dom == 0 else ("slice_emit_kernel" if dom == 3 else ""))
+    except Exception:
+        pass
+    roofline = {"bound": "hbm", "kernel": names[dom], "achieved": ach_dom, "peak": peak, "unit": "GB/s", "frac": ach_dom / peak, "traffic": traffic,
                 "peak_source": peak_src, "algorithmic_bytes_per_step": b_alg,
                 "pipeline": {"achieved": ach_pipe, "frac": ach_pipe / peak, "note": "all kernels of a step: input bytes + 4 B per id slot over the whole device time"},
                 "stage_ms_per_step": dict(zip(["split", "model", "scan", "emit", "total_kernels"], [round(x, 4) for x in per_step_ms])),
