@@ -176,7 +176,7 @@ __global__ void gather_scalars_dedup_kernel(unsigned long long* ctrl, const uint
     ctrl[4] = d;
 }
 // word-length classes of the BPE kernels: [0] 65..2048 bytes, [1] > 2048, [2] > 12288 (needs global state arrays)
-constexpr uint32_t BB_WARP_MAX = 64, BB_SMALL_MAX = 2048, BB_BIG_CAP = 12288;
+constexpr uint32_t BB_WARP_MAX = 64, BB_TINY_MAX = 1024, BB_SMALL_MAX = 2048, BB_BIG_CAP = 12288;
 __global__ void len_class_count_kernel(const uint32_t* word_start, const uint32_t* word_end, uint32_t n_fixed, const unsigned int* n_dev,
                                        unsigned long long* counts) {
     const uint32_t n = n_dev ? *n_dev : n_fixed;
@@ -487,8 +487,12 @@ int launch_bpe(tkz_ctx* ctx, const DevModel& m, const uint8_t* d_text, const uin
     b.g_first = (uint32_t*)ctx->a_g_first.p; b.g_win = (uint16_t*)ctx->a_g_win.p; b.g_flag = (uint8_t*)ctx->a_g_flag.p;
     b.word_ntok = word_ntok; b.errw = ctrl; b.sentinel_errors = sentinel;
     if (cls[0]) {
-        b.min_len = BB_WARP_MAX + 1; b.max_len = BB_SMALL_MAX; b.work_counter = (unsigned int*)(ctrl + 11);
-        uint64_t g = cls[0]; const uint64_t gc = (uint64_t)ctx->sm_count * 6; if (g > gc) g = gc;
+        // 65..1024 bytes: two warps per word (cheap barriers, 14 words in flight per SM); 1025..2048: eight warps
+        b.min_len = BB_WARP_MAX + 1; b.max_len = BB_TINY_MAX; b.work_counter = (unsigned int*)(ctrl + 17);
+        uint64_t g = cls[0]; uint64_t gc = (uint64_t)ctx->sm_count * 14; if (g > gc) g = gc;
+        bpe_block_kernel<64, BB_TINY_MAX><<<(unsigned)g, 64, BB_TINY_MAX * 15, st>>>(m, b); launches++;
+        b.min_len = BB_TINY_MAX + 1; b.max_len = BB_SMALL_MAX; b.work_counter = (unsigned int*)(ctrl + 11);
+        g = cls[0]; gc = (uint64_t)ctx->sm_count * 6; if (g > gc) g = gc;
         bpe_block_kernel<256, BB_SMALL_MAX><<<(unsigned)g, 256, BB_SMALL_MAX * 15, st>>>(m, b); launches++;
     }
     if (cls[1]) {
