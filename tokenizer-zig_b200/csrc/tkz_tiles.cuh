@@ -266,12 +266,40 @@ __device__ TW_SLOWPATH WholeWarpOut tw_whole_warp_word(const DevModel& m, const 
         limit = __shfl_sync(FULL, limit, 0);
         // WordPiece only needs the LENGTH of a word above max_input_chars_per_word (wordpiece.zig:149-158)
         uint64_t q = start + 32;
-        for (;;) {
+        bool found = false;
+        for (int round = 0; round < 3 && !found; round++) {       // the first 96 bytes one per lane (most words end here)
             const uint64_t qq = q + lane;
             const bool stop = qq >= limit || ((lut[__ldg(a.text + qq)] >> 8) & 1u) == 0;
             const uint32_t sm = __ballot_sync(FULL, stop);
-            if (sm) { q += (uint32_t)__ffs(sm) - 1; break; }
-            q += 32;
+            if (sm) { q += (uint32_t)__ffs(sm) - 1; found = true; } else q += 32;
+        }
+        if (!found) {
+            // long unbroken run (up to MiBs): 512 bytes per step, one aligned 16-byte load per lane
+            const uint32_t pre = (uint32_t)((16u - (uint32_t)(q & 15u)) & 15u);
+            {
+                const uint64_t qq = q + lane;
+                const bool stop = lane < pre && (qq >= limit || ((lut[__ldg(a.text + qq)] >> 8) & 1u) == 0);
+                const uint32_t sm = __ballot_sync(FULL, stop);
+                if (sm) { q += (uint32_t)__ffs(sm) - 1; found = true; } else q += pre;
+            }
+            while (!found) {
+                const uint64_t qq = q + 16u * lane;
+                uint32_t mask = 0;                                  // bit j: the word stops at byte qq + j
+                if (qq + 16 <= limit) {
+                    const uint4 v = __ldg(reinterpret_cast<const uint4*>(a.text + qq));
+                    const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                    for (int j = 0; j < 16; j++) mask |= ((((lut[(w4[j >> 2] >> (8 * (j & 3))) & 0xFFu] >> 8) & 1u) ^ 1u) << j);
+                } else {
+                    for (int j = 0; j < 16; j++) if (qq + j >= limit || ((lut[__ldg(a.text + qq + j)] >> 8) & 1u) == 0) { mask |= 1u << j; break; }
+                }
+                const uint32_t sm = __ballot_sync(FULL, mask != 0);
+                if (sm) {
+                    const int l0 = __ffs(sm) - 1;
+                    q += 16u * (uint32_t)l0 + (uint32_t)(__ffs(__shfl_sync(FULL, mask, l0)) - 1);
+                    found = true;
+                } else q += 512;
+            }
         }
         wlen = (uint32_t)(q - start);
     }
@@ -788,25 +816,34 @@ __global__ void doc_finish2_kernel(const uint64_t* __restrict__ doc_off, uint32_
     }
 }
 
+// warp-wide fill of n u32 slots at p with v: scalar head up to 16-byte alignment, 16-byte stores, scalar tail
+__device__ __forceinline__ void warp_fill_u32(uint32_t* p, unsigned long long n, uint32_t v) {
+    const uint32_t lane = lane_id();
+    const uint32_t head = (uint32_t)((4u - (uint32_t)(((uintptr_t)p >> 2) & 3u)) & 3u);
+    const unsigned long long h = head < n ? head : n;
+    if (lane < h) p[lane] = v;
+    const unsigned long long n4 = (n - h) >> 2;
+    uint4* p4 = reinterpret_cast<uint4*>(p + h);
+    for (unsigned long long i = lane; i < n4; i += 32) p4[i] = make_uint4(v, v, v, v);
+    const unsigned long long done = h + (n4 << 2);
+    if (done + lane < n) p[done + lane] = v;
+}
+
 // padding slots from per-document real counts (src/encoding.zig:407-414, 418-425), one warp per document
 __global__ void __launch_bounds__(256) emit_pad_real_kernel(EmitParams p, EmitOut o, uint32_t n_docs, const uint32_t* __restrict__ doc_real,
                                                             const unsigned long long* __restrict__ doc_tok_off) {
     const uint32_t d = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const uint32_t lane = lane_id();
     if (d >= n_docs) return;
     unsigned long long kept;
     const unsigned long long olen = doc_out_len(p, doc_real[d], &kept);
     if (olen == kept) return;
     const unsigned long long base = doc_tok_off[d] + (p.pad_left ? 0 : kept);
     const unsigned long long npad = olen - kept;
-    for (unsigned long long k = lane; k < npad; k += 32) {
-        const unsigned long long dst = base + k;
-        o.ids[dst] = p.pad_id;
-        if (p.outputs & 2u) reinterpret_cast<uint2*>(o.offsets)[dst] = make_uint2(0u, 0u);
-        if (p.outputs & 4u) o.attention[dst] = 0u;
-        if (p.outputs & 8u) o.type_ids[dst] = p.pad_type_id;
-        if (p.outputs & 16u) o.special[dst] = 1u;
-    }
+    warp_fill_u32(o.ids + base, npad, p.pad_id);
+    if (p.outputs & 2u) warp_fill_u32(o.offsets + 2 * base, 2 * npad, 0u);
+    if (p.outputs & 4u) warp_fill_u32(o.attention + base, npad, 0u);
+    if (p.outputs & 8u) warp_fill_u32(o.type_ids + base, npad, p.pad_type_id);
+    if (p.outputs & 16u) warp_fill_u32(o.special + base, npad, 1u);
 }
 
 // document of the first failing word (byte position in the error word) -> ctrl[4]

@@ -83,6 +83,7 @@ pub const Stats = extern struct {
     ms_emit: f32,
     ms_total: f32,
     model_flags: u32,
+    path: u32, // pipeline of the last encode: 0 per-occurrence, 1 dedup multi-pass, 2 slice pipeline
 };
 
 pub extern fn tkz_ctx_create(device: c_int, stream: ?*anyopaque, arena_hint_bytes: u64, out: *?*Ctx) c_int;
