@@ -592,3 +592,43 @@ def test_tiles_errors_report_the_first_document_in_text_order():
         assert e.value.code == tz.ERR_INVALID_UTF8 and e.value.doc == min(bad_at, 4500)
     assert_same(t.encode_batch(filler), o.encode_batch(filler), "after errors")
     t.close()
+
+
+def test_full_size_properties_1gib():
+    """BASELINE.json configs[1] at its full size (1 GiB of the c2 corpus, GPT-2-shaped tokenizer), through properties that
+    need no oracle run: (1) batch-split invariance -- the encoding of the whole batch equals the concatenation of the
+    encodings of its halves (different slice / chunk / table-occupancy layout); (2) the slice pipeline equals the older
+    multi-pass pipeline on all 235 M tokens; (3) token strings of sampled documents concatenate to the document minus
+    the characters the vocabulary lacks; (4) CSR offsets are monotone and end at the token count."""
+    js = tokenizers_io.tokenizer_json("gpt2_whitespace")
+    text, off = corpus.generate("c2", 1 << 30, seed=1234)
+    nd = len(off) - 1
+    t = tz.Tokenizer.from_json(js, device=0)
+    full = t.encode_packed(text, off, outputs=3)
+    assert t.stats().path == 2
+    assert int(full.doc_tok_off[-1]) == len(full.ids) and np.all(np.diff(full.doc_tok_off.astype(np.int64)) >= 0)
+    h = nd // 2
+    a = t.encode_packed(text[: int(off[h])], off[: h + 1], outputs=3)
+    b = t.encode_packed(text[int(off[h]):], off[h:] - off[h], outputs=3)
+    na = len(a.ids)
+    assert na + len(b.ids) == len(full.ids)
+    assert np.array_equal(full.ids[:na], a.ids) and np.array_equal(full.ids[na:], b.ids)
+    assert np.array_equal(full.offsets[:na], a.offsets) and np.array_equal(full.offsets[na:], b.offsets)
+    assert np.array_equal(full.doc_tok_off[: h + 1], a.doc_tok_off) and np.array_equal(full.doc_tok_off[h:], b.doc_tok_off + a.doc_tok_off[-1])
+    del a, b
+    t0, _ = pair(js, mode="multipass")
+    old = t0.encode_packed(text, off, outputs=3)
+    assert t0.stats().path == 1
+    assert np.array_equal(old.ids, full.ids) and np.array_equal(old.offsets, full.offsets) and np.array_equal(old.doc_tok_off, full.doc_tok_off)
+    del old
+    t0.close()
+    d = t.model_desc()
+    id2tok = {int(i): k for k, i in zip(d["keys"], d["ids"])}
+    single = {k for k in d["keys"] if len(k.decode("utf-8", "ignore")) == 1}
+    rng = random.Random(5)
+    for i in rng.sample(range(nd), 300):
+        doc = text[int(off[i]):int(off[i + 1])].tobytes()
+        kept = b"".join(ch.encode() for w in doc.split() for ch in w.decode("utf-8") if ch.encode() in single)
+        sl = full.doc_slice(i)
+        assert b"".join(id2tok[int(x)] for x in full.ids[sl]) == kept
+    t.close()

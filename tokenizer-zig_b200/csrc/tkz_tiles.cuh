@@ -513,23 +513,36 @@ __global__ void __launch_bounds__(TW_THREADS, TW_BLOCKS_PER_SM) slice_words_kern
         for (uint32_t k0 = 0; k0 < nW; k0 += 32) {
             const uint32_t k = k0 + lane;
             const bool have = k < nW;
-            uint32_t p = 0, len = 0, va = 0, vb = 0, myslot = 0;
-            int state = 0;                                          // 0 done, 1 owner, 2 pending, 3 whole warp needed
-            if (have) {
-                const uint32_t pw = sh.wlist[k];
-                p = pw & 0x0FFFu;
+            // straight-line first probe for every lane (lanes past the end repeat the round's first word, result ignored)
+            const uint32_t pw = sh.wlist[have ? k : k0];
+            const uint32_t p = pw & 0x0FFFu;
+            uint32_t len;
+            {
+                const uint32_t q = p + 1, w = q >> 5;
+                const uint32_t x = __funnelshift_r(sh.cont32[w], sh.cont32[w + 1], q & 31u);
+                len = (uint32_t)__ffs((int)~x);                     // 1 + continuing bytes; 0 when 32 or more continue
+                if (len == 0) len = 33;
                 if (HAS_ISO && (pw & 0x8000u)) len = 1;
-                else {
-                    const uint32_t q = p + 1, w = q >> 5;
-                    const uint32_t x = __funnelshift_r(sh.cont32[w], sh.cont32[w + 1], q & 31u);
-                    len = (uint32_t)__ffs((int)~x);                 // 1 + continuing bytes; 0 when 32 or more continue
-                    if (len == 0) len = 33;
-                }
-                if (len <= TW_MAX_SHORT) {
-                    uint32_t key[4];
-                    tw_build_key(sh, bs.lenmask, p, len, key);
-                    uint32_t slot = tw_key_hash(key[0], key[1], key[2], key[3]) & a.table_mask;
+            }
+            const bool is_short = len <= TW_MAX_SHORT;
+            uint32_t key[4];
+            tw_build_key(sh, bs.lenmask, p, is_short ? len : TW_MAX_SHORT, key);
+            uint32_t myslot = tw_key_hash(key[0], key[1], key[2], key[3]) & a.table_mask;
+            uint32_t va, vb;
+            int state;                                              // 0 done, 1 owner, 2 pending, 3 whole warp needed, 4 keep probing
+            {
+                uint32_t r[8];
+                tw_ld256(a.table + myslot, r);
+                va = r[4]; vb = r[5];
+                const bool hit = is_short && r[0] == key[0] && r[1] == key[1] && r[2] == key[2] && r[3] == key[3] && r[5] != 0;
+                state = (!have || hit) ? 0 : (is_short ? 4 : 3);
+            }
+            if (__any_sync(FULL, state != 0)) {
+                // ---- rare: first sight of a word, a collision, a word whose owner is still computing, a long word
+                if (state == 4) {
+                    uint32_t slot = myslot;
                     state = 3;
+#pragma unroll 1
                     for (int probe = 0; probe < TW_MAX_PROBE; probe++) {
                         WordSlot* sl = a.table + slot;
                         uint32_t r[8];
@@ -546,35 +559,34 @@ __global__ void __launch_bounds__(TW_THREADS, TW_BLOCKS_PER_SM) slice_words_kern
                         }
                         slot = (slot + 1) & a.table_mask;
                     }
-                } else state = 3;
-            }
-            // ---- words this warp saw first: run the model now and publish the value
-            uint32_t owners = __ballot_sync(FULL, state == 1);
-            if (owners && lane == 0) atomicAdd(a.n_uniq, (unsigned int)__popc(owners));
-            while (owners) {
-                const int l = __ffs(owners) - 1; owners &= owners - 1;
-                uint32_t okey[4];                                   // the owner's key again (not kept live across the round)
-                tw_build_key(sh, bs.lenmask, __shfl_sync(FULL, p, l), __shfl_sync(FULL, len, l), okey);
-                const WholeWarpOut r = tw_own_word<MODEL>(m, a, sh, okey[0], okey[1], okey[2], okey[3], __shfl_sync(FULL, myslot, l));
-                if (r.abort) warp_abort = true;
-                if ((int)lane == l) { va = r.a; vb = r.b; state = 0; }
-            }
-            // ---- words that need the whole warp: longer than 15 bytes, or no slot within the probe limit
-            uint32_t todo = __ballot_sync(FULL, state == 3);
-            while (todo) {
-                const int l = __ffs(todo) - 1; todo &= todo - 1;
-                const WholeWarpOut r = tw_whole_warp_word<MODEL>(m, a, bs.lut, sh, s, __shfl_sync(FULL, p, l), __shfl_sync(FULL, len, l));
-                if (r.abort) warp_abort = true;
-                if ((int)lane == l) { va = r.a; vb = r.b; state = 0; }
-            }
-            // ---- words whose owner (another warp) was still computing
-            uint32_t pend = __ballot_sync(FULL, state == 2);
-            while (pend) {
-                if (state == 2) {
-                    const uint2 v = tw_ld_value(a.table + myslot);
-                    if (v.y != 0) { va = v.x; vb = v.y; state = 0; }
                 }
-                pend = __ballot_sync(FULL, state == 2);
+                // words this warp saw first: run the model now and publish the value
+                uint32_t owners = __ballot_sync(FULL, state == 1);
+                if (owners && lane == 0) atomicAdd(a.n_uniq, (unsigned int)__popc(owners));
+                while (owners) {
+                    const int l = __ffs(owners) - 1; owners &= owners - 1;
+                    const WholeWarpOut r = tw_own_word<MODEL>(m, a, sh, __shfl_sync(FULL, key[0], l), __shfl_sync(FULL, key[1], l),
+                                                              __shfl_sync(FULL, key[2], l), __shfl_sync(FULL, key[3], l), __shfl_sync(FULL, myslot, l));
+                    if (r.abort) warp_abort = true;
+                    if ((int)lane == l) { va = r.a; vb = r.b; state = 0; }
+                }
+                // words that need the whole warp: longer than 15 bytes, or no slot within the probe limit
+                uint32_t todo = __ballot_sync(FULL, state == 3);
+                while (todo) {
+                    const int l = __ffs(todo) - 1; todo &= todo - 1;
+                    const WholeWarpOut r = tw_whole_warp_word<MODEL>(m, a, bs.lut, sh, s, __shfl_sync(FULL, p, l), __shfl_sync(FULL, len, l));
+                    if (r.abort) warp_abort = true;
+                    if ((int)lane == l) { va = r.a; vb = r.b; state = 0; }
+                }
+                // words whose owner (another warp) was still computing
+                uint32_t pend = __ballot_sync(FULL, state == 2);
+                while (pend) {
+                    if (state == 2) {
+                        const uint2 v = tw_ld_value(a.table + myslot);
+                        if (v.y != 0) { va = v.x; vb = v.y; state = 0; }
+                    }
+                    pend = __ballot_sync(FULL, state == 2);
+                }
             }
             // ---- entry + token prefix
             uint32_t nt = 0, ey = 0;
