@@ -184,7 +184,8 @@ __device__ __forceinline__ bool tw_make_value(const TileArgs& a, const uint32_t*
 // classify + normalise one 32-byte segment (two 16-byte vector loads); bytes at or beyond n read as DELIM
 template <bool NORM_ID, bool HAS_ISO>
 __device__ __forceinline__ void tw_load_segment(const uint8_t* __restrict__ text, uint64_t n, uint64_t seg_base, uint32_t seg,
-                                                const uint32_t* lut, uint32_t* text32, uint32_t& word_out, uint32_t& iso_out) {
+                                                const uint32_t* lut, uint32_t cw_word, uint32_t cw_iso, uint32_t* text32,
+                                                uint32_t& word_out, uint32_t& iso_out) {
     uint32_t word = 0, iso = 0;
 #pragma unroll
     for (int h = 0; h < 2; h++) {
@@ -203,10 +204,18 @@ __device__ __forceinline__ void tw_load_segment(const uint8_t* __restrict__ text
             uint32_t o = 0;
 #pragma unroll
             for (int j = 0; j < 4; j++) {
-                const uint32_t e = lut[(raw[q] >> (8 * j)) & 0xFF];
-                w16 |= ((e >> 8) & 1u) << (q * 4 + j);
-                if (HAS_ISO) i16 |= ((e >> 9) & 1u) << (q * 4 + j);
-                if (!NORM_ID) o |= (e & 0xFFu) << (8 * j);
+                const uint32_t b = (raw[q] >> (8 * j)) & 0xFFu;
+                if (NORM_ID) {
+                    // identity byte map: only the class bits are needed -> 256-bit tables held by lanes 0..7, read by shuffle
+                    // (the shared-memory LUT serialises on bank conflicts: 32 lanes x arbitrary bytes)
+                    w16 |= ((__shfl_sync(0xFFFFFFFFu, cw_word, b >> 5) >> (b & 31u)) & 1u) << (q * 4 + j);
+                    if (HAS_ISO) i16 |= ((__shfl_sync(0xFFFFFFFFu, cw_iso, b >> 5) >> (b & 31u)) & 1u) << (q * 4 + j);
+                } else {
+                    const uint32_t e = lut[b];
+                    w16 |= ((e >> 8) & 1u) << (q * 4 + j);
+                    if (HAS_ISO) i16 |= ((e >> 9) & 1u) << (q * 4 + j);
+                    o |= (e & 0xFFu) << (8 * j);
+                }
             }
             nrm[q] = NORM_ID ? raw[q] : o;
         }
@@ -440,6 +449,9 @@ __global__ void __launch_bounds__(TW_THREADS, TW_BLOCKS_PER_SM) slice_words_kern
     }
     __syncthreads();                                            // the only block-level barrier
     SliceShared& sh = bs.w[wid];
+    // class bits of byte values 32 * lane .. 32 * lane + 31 (lanes 0..7), for the shuffle look-up of tw_load_segment
+    uint32_t cw_word = 0, cw_iso = 0;
+    if (NORM_ID && lane < 8) for (int j = 0; j < 32; j++) { const uint32_t e = bs.lut[32 * lane + j]; cw_word |= ((e >> 8) & 1u) << j; cw_iso |= ((e >> 9) & 1u) << j; }
     const uint32_t stride = gridDim.x * TW_WARPS;
     bool warp_abort = false;
 
@@ -470,7 +482,7 @@ __global__ void __launch_bounds__(TW_THREADS, TW_BLOCKS_PER_SM) slice_words_kern
         uint32_t halo_e = 0;
         { const uint64_t hp = slice_base + TW_SLICE + lane; if (hp < a.n) halo_e = bs.lut[__ldg(a.text + hp)]; }
         uint32_t word, iso;
-        tw_load_segment<NORM_ID, HAS_ISO>(a.text, a.n, slice_base + (uint64_t)lane * TW_SEG, lane, bs.lut, sh.text32, word, iso);
+        tw_load_segment<NORM_ID, HAS_ISO>(a.text, a.n, slice_base + (uint64_t)lane * TW_SEG, lane, bs.lut, cw_word, cw_iso, sh.text32, word, iso);
         reinterpret_cast<uint8_t*>(sh.text32)[TW_SLICE + lane] = (uint8_t)halo_e;
         __syncwarp();
 
