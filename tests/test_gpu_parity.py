@@ -632,3 +632,28 @@ def test_full_size_properties_1gib():
         sl = full.doc_slice(i)
         assert b"".join(id2tok[int(x)] for x in full.ids[sl]) == kept
     t.close()
+
+
+@pytest.mark.parametrize("model", ["bpe", "wp"])
+def test_tiles_words_of_16_to_31_bytes_share_prefixes(model):
+    """words of 16..31 bytes take the lane-parallel 64-byte slots: the first half of the key ([length, bytes 0..14]) is
+    claimed by CAS, the second half compared afterwards -- so words that share their first 15 bytes (and length), words
+    with NUL bytes in either half, and the neighbours 15 / 32 bytes long must all stay distinct."""
+    rng = random.Random(77)
+    if model == "bpe":
+        js, alpha = rand_bpe_json(rng, n_merges=60, alphabet=list("abcd") + ["é"], pretok="Whitespace", dead_merges=0.0)
+    else:
+        js, alpha = rand_wp_json(rng, n_words=80, alphabet=list("abcd") + ["é"], pretok="Whitespace", normalizer=None, max_chars=40)
+    t, o = pair(js)
+    stems = ["".join(rng.choice("abcd") for _ in range(15)) for _ in range(6)] + ["a" * 15, "\x00" * 15 if model == "wp" else "b" * 15]
+    words = []
+    for st in stems:
+        for L in (15, 16, 17, 20, 30, 31, 32, 33):
+            for _ in range(6):
+                tail = "".join(rng.choice("abcd" + ("\x00" if model == "wp" else "")) for _ in range(L - 15))
+                words.append((st + tail).encode())
+    docs = [b" ".join(rng.choice(words) for _ in range(rng.randint(1, 40))) for _ in range(6000)]
+    for rep in range(2):
+        assert_same(t.encode_batch(docs), o.encode_batch(docs, threads=8), f"{model} call {rep}")
+    assert t.stats().path == 2
+    t.close()

@@ -530,6 +530,7 @@ int encode_tiles(tkz_ctx* ctx, const DevModel& m, const uint8_t* d_text, const u
     if (want > (1u << 26)) want = 1u << 26;
     const uint32_t tcap = pow2_at_least(want);
     const uint32_t mcap = tcap >= (1u << 17) ? tcap / 8 : (1u << 14);
+    const uint32_t m32cap = tcap >= (1u << 16) ? tcap / 4 : (1u << 14);        // 64-byte slots for words of 16..31 bytes
     uint64_t upool_cap = N / 8 + (1u << 20);
     if (upool_cap < ctx->tw_upool_hist * 2) upool_cap = ctx->tw_upool_hist * 2;
     if (upool_cap > 0xFFFFFF00ull) upool_cap = 0xFFFFFF00ull;
@@ -542,7 +543,7 @@ int encode_tiles(tkz_ctx* ctx, const DevModel& m, const uint8_t* d_text, const u
     ent_cap += ent_cap / 4 + std::min<uint64_t>(n_tiles, (uint64_t)grid * TW_WARPS) * TW_ENT_CHUNK;
     if (ent_cap > 0xFFFFF000ull) ent_cap = 0xFFFFF000ull;
     const uint32_t long_cap = (uint32_t)(N / 256 + 1024);
-    TRY(ensure(ctx, ctx->a_wtable, ((size_t)tcap + mcap) * sizeof(WordSlot)));
+    TRY(ensure(ctx, ctx->a_wtable, ((size_t)tcap + mcap) * sizeof(WordSlot) + (size_t)m32cap * sizeof(WordSlot32)));
     TRY(ensure(ctx, ctx->a_upool, (size_t)upool_cap * 8));
     TRY(ensure(ctx, ctx->a_lscratch, (size_t)ls_cap * 4));
     TRY(ensure(ctx, ctx->a_ent, (size_t)ent_cap * 8));
@@ -557,11 +558,12 @@ int encode_tiles(tkz_ctx* ctx, const DevModel& m, const uint8_t* d_text, const u
     TRY(ensure(ctx, ctx->a_long_tile, (size_t)long_cap * 4));
     TRY(ensure(ctx, ctx->O().doc_tok_off, (n_docs + 1) * 8));
     TRY(ensure(ctx, ctx->a_scan_tmp, (scan_tmp_elems(n_tiles) + scan_tmp_elems(n_docs)) * 8));
-    CK(cudaMemsetAsync(ctx->a_wtable.p, 0, ((size_t)tcap + mcap) * sizeof(WordSlot), st));
+    CK(cudaMemsetAsync(ctx->a_wtable.p, 0, ((size_t)tcap + mcap) * sizeof(WordSlot) + (size_t)m32cap * sizeof(WordSlot32), st));
     tile_doc_index_kernel<<<(n_tiles + 1 + 255) / 256, 256, 0, st>>>(d_doc_off, nd, n_tiles, TW_SLICE, (uint32_t*)ctx->a_tile_doc_lo.p); launches++;
     TileArgs ta{};
     ta.text = d_text; ta.n = N; ta.doc_off = d_doc_off; ta.n_docs = nd; ta.n_slices = n_tiles; ta.slice_doc_lo = (const uint32_t*)ctx->a_tile_doc_lo.p;
     ta.table = (WordSlot*)ctx->a_wtable.p; ta.table_mask = tcap - 1; ta.med_base = tcap; ta.med_mask = mcap - 1;
+    ta.table32 = (WordSlot32*)((WordSlot*)ctx->a_wtable.p + tcap + mcap); ta.table32_mask = m32cap - 1;
     ta.upool = (unsigned long long*)ctx->a_upool.p; ta.upool_cap = (uint32_t)upool_cap; ta.upool_count = (unsigned int*)(ctrl + 9);
     ta.lscratch = (uint32_t*)ctx->a_lscratch.p; ta.lscratch_cap = (uint32_t)ls_cap; ta.lscratch_count = (unsigned int*)(ctrl + 9) + 1;
     ta.ent = (uint2*)ctx->a_ent.p; ta.ent_cap = (uint32_t)ent_cap; ta.ent_count = (unsigned int*)(ctrl + 5);

@@ -67,12 +67,19 @@ static_assert(sizeof(WordSlot) == 32, "one sector");
 __constant__ unsigned long long c_med_pw[TW_MAX_MED];
 #define TKZ_MED_HASH_MUL 0x9E3779B97F4A7C15ULL
 
+// 64-byte slot for words of 16..31 bytes (one per lane, like short words): k = [length, bytes 0..14], k2 = bytes 15..30.
+// The first half is claimed with atom.cas.b128 (length >= 16 keeps it non-zero), the owner then stores k2 and sets c;
+// a, b = the value as in WordSlot.
+struct __align__(64) WordSlot32 { uint32_t k[4]; uint32_t a, b, c, d; uint32_t k2[4]; uint32_t pad[4]; };
+static_assert(sizeof(WordSlot32) == 64, "two sectors");
+
 struct TileArgs {
     const uint8_t* text; uint64_t n;
     const uint64_t* doc_off; uint32_t n_docs;
     uint32_t n_slices;
     const uint32_t* slice_doc_lo;                 // first document with doc_off >= slice start (n_slices + 1 entries)
     WordSlot* table; uint32_t table_mask; uint32_t med_base, med_mask;
+    WordSlot32* table32; uint32_t table32_mask;
     unsigned long long* upool; uint32_t upool_cap; unsigned int* upool_count;     // token records: id | start << 32 | end << 48
     uint32_t* lscratch; uint32_t lscratch_cap; unsigned int* lscratch_count;      // symbol arrays of words of 65..256 bytes
     uint2* ent; uint32_t ent_cap; unsigned int* ent_count;                        // word entries: warps claim TW_ENT_CHUNK at a time
@@ -112,6 +119,11 @@ struct TileShared {
 
 __device__ __forceinline__ void tw_ld256(const WordSlot* s, uint32_t (&r)[8]) {
     asm volatile("ld.global.ca.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "l"(s) : "memory");
+}
+// same, straight from L2 (a slot that is looked at again must not be served from a stale L1 line)
+__device__ __forceinline__ void tw_ld256_cg(const void* s, uint32_t (&r)[8]) {
+    asm volatile("ld.global.cg.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                  : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "l"(s) : "memory");
 }
 __device__ __forceinline__ uint2 tw_ld_value(const WordSlot* s) {
@@ -249,10 +261,47 @@ __device__ __forceinline__ void tw_build_key(const SliceShared& sh, const uint4*
     key[3] = (__funnelshift_r(x3, x4, shb) & mk.w) | (len << 24);
 }
 
+struct WholeWarpOut { uint32_t a, b; bool abort; };     // result of the out-of-line word handlers
+
+// 256-bit key of the word of `len` (16..31) bytes at slice position p: key[0..3] = [len, bytes 0..14], key[4..7] = bytes 15..30
+__device__ __forceinline__ void tw_build_key32(const SliceShared& sh, const uint4* lenmask, uint32_t p, uint32_t len, uint32_t (&key)[8]) {
+    const uint32_t wi = p >> 2, shb = (p & 3u) * 8u;
+    uint32_t w[8];
+    uint32_t x = sh.text32[wi];
+#pragma unroll
+    for (int i = 0; i < 8; i++) { const uint32_t y = sh.text32[wi + 1 + i]; w[i] = __funnelshift_r(x, y, shb); x = y; }
+    const uint4 mk = lenmask[len - 16];                            // bytes 16.. of the word: keep len - 16 of them
+    w[4] &= mk.x; w[5] &= mk.y; w[6] &= mk.z; w[7] &= mk.w;
+    key[0] = len | (w[0] << 8);
+#pragma unroll
+    for (int i = 1; i < 8; i++) key[i] = (w[i - 1] >> 24) | (w[i] << 8);
+}
+__device__ __forceinline__ uint32_t tw_key_hash32(const uint32_t (&k)[8]) {
+    uint32_t h = k[0] * 0x9E3779B1u;
+#pragma unroll
+    for (int i = 1; i < 8; i++) h = (h ^ k[i] ^ (h >> 15)) * (0x85EBCA77u + 2u * (uint32_t)i * 0x9E3779B1u);
+    h ^= h >> 15; h *= 0x2C1B3C6Du; h ^= h >> 13;
+    return h;
+}
+
+// One word of 16..31 bytes this warp saw first: model + publish into its WordSlot32.  Out of line.
+template <int MODEL>
+__device__ TW_SLOWPATH WholeWarpOut tw_own_word32(const DevModel& m, const TileArgs& a, SliceShared& sh, uint32_t wp_, uint32_t wlen, uint32_t bslot) {
+    const uint32_t lane = lane_id();
+    WholeWarpOut out{0u, 0u, false};
+    uint8_t* const wbytes = reinterpret_cast<uint8_t*>(sh.wbytes);
+    wbytes[lane] = (reinterpret_cast<const uint8_t*>(sh.text32) + wp_)[lane];     // the whole word is in the slice + halo
+    __syncwarp();
+    const uint32_t n = tw_model_small<MODEL>(m, wbytes, wlen, sh.mscr);
+    if (!tw_make_value(a, sh.mscr[0], sh.mscr[1], sh.mscr[2], n, out.a, out.b)) out.abort = true;
+    if (lane == 0) asm volatile("st.global.relaxed.gpu.v2.u32 [%0], {%1,%2};" :: "l"(&a.table32[bslot].a), "r"(out.a), "r"(out.b) : "memory");
+    __syncwarp();
+    return out;
+}
+
 // One word that needs the whole warp (longer than 15 bytes, or no table slot within the probe limit): finds its end, then
 // medium words (<= 64 bytes) go through the tag table, 65..256 bytes are tokenized uncached, longer ones join the long list.
 // Kept out of line so that its registers do not weigh on the one-word-per-lane loop.
-struct WholeWarpOut { uint32_t a, b; bool abort; };
 template <int MODEL>
 __device__ TW_SLOWPATH WholeWarpOut tw_whole_warp_word(const DevModel& m, const TileArgs& a, const uint32_t* lut, SliceShared& sh, uint32_t s,
                                                         uint32_t wp_, uint32_t wl_) {
@@ -582,7 +631,64 @@ __global__ void __launch_bounds__(TW_THREADS, TW_BLOCKS_PER_SM) slice_words_kern
                     if (r.abort) warp_abort = true;
                     if ((int)lane == l) { va = r.a; vb = r.b; state = 0; }
                 }
-                // words that need the whole warp: longer than 15 bytes, or no slot within the probe limit
+                // words of 16..31 bytes: one per lane through the 64-byte slots (state 5 probing, 6 pending, 7 owner)
+                if (state == 3 && len >= 16 && len <= 31) state = 5;
+                if (__any_sync(FULL, state == 5)) {
+                    uint32_t k32[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+                    uint32_t slot = 0;
+                    if (state == 5) { tw_build_key32(sh, bs.lenmask, p, len, k32); slot = tw_key_hash32(k32) & a.table32_mask; }
+                    // warp-uniform probe rounds: a lane that meets a half-published key simply looks again next round
+#pragma unroll 1
+                    for (int it = 0; it < 4 * TW_MAX_PROBE && __any_sync(FULL, state == 5); it++) {
+                        if (state == 5) {
+                            WordSlot32* sl = a.table32 + slot;
+                            uint32_t r[8];
+                            tw_ld256_cg(sl, r);
+                            bool same1 = r[0] == k32[0] && r[1] == k32[1] && r[2] == k32[2] && r[3] == k32[3];
+                            if (!same1 && (r[0] | r[1] | r[2] | r[3]) == 0) {
+                                const uint32_t k1[4] = {k32[0], k32[1], k32[2], k32[3]};
+                                uint32_t old[4];
+                                tw_cas128(reinterpret_cast<WordSlot*>(sl), k1, old);
+                                if ((old[0] | old[1] | old[2] | old[3]) == 0) {
+                                    // owner: second half, then the flag
+                                    asm volatile("st.global.relaxed.gpu.v4.u32 [%0], {%1,%2,%3,%4};" :: "l"(sl->k2), "r"(k32[4]), "r"(k32[5]), "r"(k32[6]), "r"(k32[7]) : "memory");
+                                    __threadfence();
+                                    asm volatile("st.global.relaxed.gpu.u32 [%0], %1;" :: "l"(&sl->c), "r"(1u) : "memory");
+                                    state = 7; myslot = slot;
+                                } else if (old[0] != k1[0] || old[1] != k1[1] || old[2] != k1[2] || old[3] != k1[3]) slot = (slot + 1) & a.table32_mask;
+                                // (same first half inserted by somebody else meanwhile: look at this slot again next round)
+                            } else if (same1) {
+                                if (r[6] != 0) {                       // second half is there: compare it
+                                    uint32_t q0, q1, q2, q3;
+                                    asm volatile("ld.global.relaxed.gpu.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(q0), "=r"(q1), "=r"(q2), "=r"(q3) : "l"(sl->k2) : "memory");
+                                    if (q0 == k32[4] && q1 == k32[5] && q2 == k32[6] && q3 == k32[7]) {
+                                        myslot = slot;
+                                        if (r[5] != 0) { va = r[4]; vb = r[5]; state = 0; } else state = 6;
+                                    } else slot = (slot + 1) & a.table32_mask;
+                                }
+                            } else slot = (slot + 1) & a.table32_mask;
+                        }
+                    }
+                    if (state == 5) state = 3;                      // no slot within the limit: whole-warp path, uncached
+                    uint32_t own32 = __ballot_sync(FULL, state == 7);
+                    if (own32 && lane == 0) atomicAdd(a.n_uniq, (unsigned int)__popc(own32));
+                    while (own32) {
+                        const int l = __ffs(own32) - 1; own32 &= own32 - 1;
+                        const WholeWarpOut r = tw_own_word32<MODEL>(m, a, sh, __shfl_sync(FULL, p, l), __shfl_sync(FULL, len, l), __shfl_sync(FULL, myslot, l));
+                        if (r.abort) warp_abort = true;
+                        if ((int)lane == l) { va = r.a; vb = r.b; state = 0; }
+                    }
+                    uint32_t pend32 = __ballot_sync(FULL, state == 6);
+                    while (pend32) {
+                        if (state == 6) {
+                            uint32_t x, y;
+                            asm volatile("ld.global.relaxed.gpu.v2.u32 {%0,%1}, [%2];" : "=r"(x), "=r"(y) : "l"(&a.table32[myslot].a) : "memory");
+                            if (y != 0) { va = x; vb = y; state = 0; }
+                        }
+                        pend32 = __ballot_sync(FULL, state == 6);
+                    }
+                }
+                // words that need the whole warp: longer than 31 bytes, or no slot within the probe limit
                 uint32_t todo = __ballot_sync(FULL, state == 3);
                 while (todo) {
                     const int l = __ffs(todo) - 1; todo &= todo - 1;
