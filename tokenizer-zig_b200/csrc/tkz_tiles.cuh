@@ -306,7 +306,6 @@ template <int MODEL>
 __device__ TW_SLOWPATH WholeWarpOut tw_whole_warp_word(const DevModel& m, const TileArgs& a, const uint32_t* lut, SliceShared& sh, uint32_t s,
                                                         uint32_t wp_, uint32_t wl_) {
     const uint64_t slice_base = (uint64_t)s * TW_SLICE;
-    const uint32_t d_lo = sh.doc_lo_hi[0];
     const uint32_t FULL = 0xFFFFFFFFu;
     const uint32_t lane = lane_id();
     uint8_t* const wbytes = reinterpret_cast<uint8_t*>(sh.wbytes);
@@ -315,13 +314,24 @@ __device__ TW_SLOWPATH WholeWarpOut tw_whole_warp_word(const DevModel& m, const 
     uint32_t wlen = wl_;
     if (wl_ > 32) {
         // end of the word: first non-WORD byte or the next document start, 32 bytes per step
-        uint64_t limit = 0;
-        if (lane == 0) {
-            const uint32_t dn = upper_bound_u64(a.doc_off, d_lo > 0 ? d_lo - 1 : 0, a.n_docs + 1, start);
-            limit = dn <= a.n_docs ? __ldg(a.doc_off + dn) : a.n;
+        // next document start behind the word's first byte: inside the slice from the document-start bits (one 32-bit
+        // word per lane), else the first document of the following slices (no binary search)
+        uint64_t limit;
+        {
+            uint32_t wd = sh.docbits[lane];
+            const uint32_t q1 = wp_ + 1;                        // first candidate position
+            if (lane < (q1 >> 5)) wd = 0;
+            else if (lane == (q1 >> 5)) wd &= 0xFFFFFFFFu << (q1 & 31u);
+            const uint32_t any = __ballot_sync(FULL, wd != 0);
+            if (any) {
+                const int l0 = __ffs(any) - 1;
+                limit = slice_base + 32u * (uint32_t)l0 + (uint32_t)(__ffs(__shfl_sync(FULL, wd, l0)) - 1);
+            } else {
+                const uint32_t dn = sh.doc_lo_hi[1];             // first document that starts at or after the next slice
+                limit = dn <= a.n_docs ? __ldg(a.doc_off + dn) : a.n;
+            }
             if (limit > a.n) limit = a.n;
         }
-        limit = __shfl_sync(FULL, limit, 0);
         // WordPiece only needs the LENGTH of a word above max_input_chars_per_word (wordpiece.zig:149-158)
         uint64_t q = start + 32;
         bool found = false;
