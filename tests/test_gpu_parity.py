@@ -657,3 +657,23 @@ def test_tiles_words_of_16_to_31_bytes_share_prefixes(model):
         assert_same(t.encode_batch(docs), o.encode_batch(docs, threads=8), f"{model} call {rep}")
     assert t.stats().path == 2
     t.close()
+
+
+def test_tiles_capacity_estimate_exceeded_falls_back_then_adapts():
+    """a batch that needs more token records than the slice pipeline reserved (millions of distinct multi-token words in
+    a few MiB) is re-run by the multi-pass pipeline -- same result -- and the context sizes the next batch from what
+    this one needed, so the same batch then stays on the slice pipeline."""
+    rng = random.Random(99)
+    v = {c: i for i, c in enumerate("abcdefghijklmnopqrstuvwxyz")}
+    js = json.dumps({"model": {"type": "BPE", "vocab": v, "merges": []}, "pre_tokenizer": {"type": "Whitespace"}})
+    t, o = pair(js)
+    n_words = 300000                                   # 15 one-character tokens each: 4.5 M records > N / 8 + 2^20
+    raw = rng.randbytes(n_words * 15)
+    letters = bytes(97 + (b % 26) for b in raw)
+    docs = [b" ".join(letters[i * 15:(i + 1) * 15] for i in range(j, min(j + 40, n_words))) for j in range(0, n_words, 40)]
+    ref = o.encode_batch(docs, threads=8)
+    assert_same(t.encode_batch(docs), ref, "first call")
+    assert t.stats().path == 1, "expected the capacity fallback on the first call"
+    assert_same(t.encode_batch(docs), ref, "second call")
+    assert t.stats().path == 2, "the second call should fit the adapted capacities"
+    t.close()
