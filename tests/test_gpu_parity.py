@@ -30,24 +30,24 @@ def assert_same(got: tz.BatchEncoding, ref: orc.BatchEncoding, what=""):
     assert np.array_equal(got.special_tokens_mask, ref.special_tokens_mask), f"{what}: special_tokens_mask"
 
 
-MODES = ("tiles", "multipass", "occurrence")
+MODES = ("slices", "multipass", "occurrence")
 
 
 def pair(js, dedup=True, mode=None):
-    """(GPU tokenizer, oracle).  The context reads its pipeline switches when it is created: mode "tiles" = the tile
-    pipeline (tkz_tiles.cuh, default), "multipass" = the older dedup multi-pass pipeline (TKZ_TILES=0, also the fallback
-    when an estimated capacity of the tile pipeline runs out), "occurrence" = the per-occurrence pipeline (TKZ_NO_DEDUP=1;
+    """(GPU tokenizer, oracle).  The context reads its pipeline switches when it is created: mode "slices" = the slice
+    pipeline (tkz_slices.cuh, default), "multipass" = the older dedup multi-pass pipeline (TKZ_SLICES=0, also the fallback
+    when an estimated capacity of the slice pipeline runs out), "occurrence" = the per-occurrence pipeline (TKZ_NO_DEDUP=1;
     dedup=False is the older spelling).  All device pipelines are held to the same oracle."""
     import os
     if mode is None:
-        mode = "tiles" if dedup else "occurrence"
+        mode = "slices" if dedup else "occurrence"
     os.environ["TKZ_NO_DEDUP"] = "1" if mode == "occurrence" else "0"
-    os.environ["TKZ_TILES"] = "0" if mode == "multipass" else "1"
+    os.environ["TKZ_SLICES"] = "0" if mode == "multipass" else "1"
     try:
         t = tz.Tokenizer.from_json(js, device=0)
     finally:
         os.environ["TKZ_NO_DEDUP"] = "0"
-        os.environ["TKZ_TILES"] = "1"
+        os.environ["TKZ_SLICES"] = "1"
     return t, orc.OracleTokenizer.from_json(js)
 
 
@@ -238,7 +238,7 @@ def test_malformed_utf8():
     t.close()
 
 
-@pytest.mark.parametrize("dedup", ["tiles", "multipass", "occurrence"])
+@pytest.mark.parametrize("dedup", ["slices", "multipass", "occurrence"])
 def test_wordpiece_missing_unk_is_an_error(dedup):
     js = json.dumps({"model": {"type": "WordPiece", "vocab": {"hello": 1, "##s": 2}, "unk_token": "[UNK]"}, "pre_tokenizer": {"type": "Whitespace"}})
     t, o = pair(js, dedup)
@@ -311,7 +311,7 @@ def test_batch_split_invariance_and_roundtrip_property():
 
 
 # ----------------------------------------------------------------------------- dedup pipeline specifics
-@pytest.mark.parametrize("mode", ["tiles", "multipass"])
+@pytest.mark.parametrize("mode", ["slices", "multipass"])
 @pytest.mark.parametrize("model", ["bpe", "wp"])
 def test_dedup_word_lengths_around_the_key_limit(model, mode):
     """words of 14 / 15 / 16 / 17 bytes straddle the 128-bit key (15 bytes + length), incl. NUL bytes inside words,
@@ -353,7 +353,7 @@ def test_dedup_and_per_occurrence_pipelines_agree_on_errors():
         t.close()
 
 
-@pytest.mark.parametrize("mode", ["tiles", "multipass"])
+@pytest.mark.parametrize("mode", ["slices", "multipass"])
 @pytest.mark.parametrize("n_words", [60000, 200000])
 def test_dedup_table_pressure_and_overflow(n_words, mode):
     """more unique words than the batch's table holds: insertions that find no slot fall back to the long list, and when
@@ -466,58 +466,21 @@ def test_chunked_host_path_matches_single_shot(monkeypatch, chunk):
     t.close()
 
 
-# ----------------------------------------------------------------------------- fused count+emit (second and later calls of a context)
-def test_fused_emit_path_and_its_overflow_fallback(monkeypatch):
-    """(opt-in with TKZ_FUSED_EMIT=1: measured slower than count + emit, kept as an experiment)  The first plain encode of a context takes the counted path and records the token density; later plain encodes take
-    the single-pass fused emit (decoupled look-back) with an estimated output size; a batch that is much denser than any
-    before overflows the estimate and is re-run by the counted path.  Every variant must equal the oracle."""
-    v = {"a": 0, "b": 1, "c": 2, "d": 3, "ab": 4, "abc": 5, "abcd": 6}
-    js = json.dumps({"model": {"type": "BPE", "vocab": v, "merges": ["a b", "ab c", "abc d"]}, "pre_tokenizer": {"type": "Whitespace"}})
-    monkeypatch.setenv("TKZ_FUSED_EMIT", "1")
-    t, o = pair(js)
-    rng = random.Random(9)
-    sparse = [" ".join(rng.choice(["abcd", "abcd", "abc", "ab"]) for _ in range(rng.randint(0, 60))).encode() for _ in range(3000)]
-    dense = [" ".join("".join(rng.choice("dcba") for _ in range(rng.randint(1, 20))) for _ in range(rng.randint(0, 60))).encode() for _ in range(3000)]
-    mixed = [rng.choice(sparse + dense) for _ in range(4000)] + [b"", b" ", b"d" * 5000, b"abcd" * 3000]
-    for name, docs in (("counted", sparse), ("fused", sparse[::-1]), ("fused-again", sparse[100:2000]), ("overflow", dense), ("fused-dense", mixed),
-                       ("empty", []), ("blank", [b"", b"  "])):
-        assert_same(t.encode_batch(docs), o.encode_batch(docs), name)
-    # errors on the fused path carry the document index too
-    with pytest.raises(tz.TokzigError) as e:
-        t.encode_batch(sparse[:500] + [b"ab \xff ab"] + sparse[:10])
-    assert e.value.code == tz.ERR_INVALID_UTF8 and e.value.doc == 500
-    assert_same(t.encode_batch(sparse), o.encode_batch(sparse), "after error")
-    t.close()
-
-
-def test_fused_emit_switch(monkeypatch):
-    js = tokenizers_io.tokenizer_json("gpt2_whitespace")
-    text, off = corpus.generate("c5", 4 << 20, seed=8)            # includes long unbroken words (long list + big-word copy)
-    o = orc.OracleTokenizer.from_json(js)
-    ref = o.encode_packed(text, off, algo=1, threads=8)
-    for flag in ("0", "1"):
-        monkeypatch.setenv("TKZ_FUSED_EMIT", flag)
-        t = tz.Tokenizer.from_json(js, device=0)
-        for rep in range(3):
-            assert_same(t.encode_packed(text, off), ref, f"TKZ_FUSED_EMIT={flag} call {rep}")
-        t.close()
-
-
-# ----------------------------------------------------------------------------- tile pipeline (tkz_tiles.cuh)
+# ----------------------------------------------------------------------------- slice pipeline (tkz_slices.cuh)
 @pytest.mark.parametrize("name,cname,mib", [("gpt2_whitespace", "c2", 96), ("llama3_whitespace", "c4", 64), ("bert_wordpiece", "c3", 48)])
 def test_tiles_equal_multipass_at_size(name, cname, mib, monkeypatch):
-    """the tile pipeline against the older multi-pass dedup pipeline on the same batch (one device call for the whole
+    """the slice pipeline against the older multi-pass dedup pipeline on the same batch (one device call for the whole
     batch), every output array compared in full (both are held to the oracle at oracle-feasible sizes above)."""
     monkeypatch.setenv("TKZ_CHUNK_BYTES", str(1 << 31))
     js = tokenizers_io.tokenizer_json(name)
     text, off = corpus.generate(cname, mib << 20, seed=31)
-    t1, _ = pair(js, mode="tiles")
+    t1, _ = pair(js, mode="slices")
     t0, _ = pair(js, mode="multipass")
     for rep in range(2):                                  # second call: table sized from history, output estimate from density
         a = t1.encode_packed(text, off)
         b = t0.encode_packed(text, off)
         assert t0.stats().path == 1
-        assert t1.stats().path == 2, "the tile pipeline gave up on a corpus it is meant to handle"
+        assert t1.stats().path == 2, "the slice pipeline gave up on a corpus it is meant to handle"
         for k in ("doc_tok_off", "ids", "offsets", "attention_mask", "type_ids", "special_tokens_mask"):
             assert np.array_equal(getattr(a, k), getattr(b, k)), f"{name} call {rep}: {k}"
     t1.close(); t0.close()

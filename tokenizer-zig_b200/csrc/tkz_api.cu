@@ -21,7 +21,7 @@
 #include "tkz_common.cuh"
 #include "tkz_dedup.cuh"
 #include "tkz_emit.cuh"
-#include "tkz_tiles.cuh"
+#include "tkz_slices.cuh"
 #include "tkz_scan.cuh"
 #include "tkz_split.cuh"
 #include "tkz_wordpiece.cuh"
@@ -67,12 +67,11 @@ struct tkz_ctx {
     uint64_t chunk_bytes = 64ull << 20;
     // dedup pipeline arenas
     DevBuf a_table, a_uniq, a_long_start, a_long_end, a_long_ntok, a_tile_words, a_tile_nwords, a_tile_ntok, a_doc_word_ref,
-        a_doc_tok_local, a_doc_tok_start, a_doc_real, a_upool, a_tile_doc_lo, a_g_first, a_g_win, a_g_flag, a_big, a_tile_state;
-    double tok_per_byte_hist = 0.0;       // highest tokens/byte seen by this context: sizes the fused emit's output estimate
+        a_doc_tok_local, a_doc_tok_start, a_doc_real, a_upool, a_tile_doc_lo, a_g_first, a_g_win, a_g_flag, a_big;
     bool has_iso = false;                 // the class table isolates some byte (punctuation split)
-    bool use_dedup = true, use_fused = false;    // fused emit measured slower than count + emit on B200: opt-in
-    bool use_tiles = true;                // tile pipeline (tkz_tiles.cuh); TKZ_TILES=0 selects the older multi-pass dedup pipeline
-    DevBuf a_wtable, a_lscratch, a_ent, a_tile_ent_off, a_long_tile, a_region_ctr;
+    bool use_dedup = true;                // TKZ_NO_DEDUP=1: per-occurrence pipeline even with a pre-tokenizer (A/B switch of the parity tests)
+    bool use_slices = true;               // slice pipeline (tkz_slices.cuh); TKZ_SLICES=0 selects the older multi-pass dedup pipeline
+    DevBuf a_wtable, a_lscratch, a_ent, a_tile_ent_off, a_long_slice, a_region_ctr;
     uint64_t tw_uniq_hist = 0;            // most unique words seen in one batch: sizes the next batch's word table
     uint64_t tw_upool_hist = 0;           // most token records used by one batch
     double tw_words_per_byte = 0.0;       // densest batch so far: sizes the entry list
@@ -137,7 +136,7 @@ uint32_t pow2_at_least(uint64_t n) { uint32_t c = 2; while (c < n) c <<= 1; retu
 __global__ void ctrl_reset_kernel(unsigned long long* ctrl) {
     // ctrl[0] = error word, ctrl[1] = work counter (u32 view), ctrl[2..4] = read-back scalars,
     // dedup: ctrl[5] second work counter, [6] n_uniq, [7] n_long, [8] overflow, [9] upool_count, [10] n_words
-    // tile pipeline: [5] entry count, [6] n_uniq | n_uncached << 32, [7] n_long, [8] abort, [9] upool | lscratch << 32,
+    // slice pipeline: [5] entry count, [6] n_uniq | n_uncached << 32, [7] n_long, [8] abort, [9] upool | lscratch << 32,
     //                [10] n_words, [11..12] block-kernel work counters, [13..15] long-word length classes, [16] big-copy list
     ctrl[0] = TKZ_ERRW_NONE;
     for (int i = 1; i < 32; i++) ctrl[i] = 0;
@@ -224,7 +223,7 @@ extern "C" int tkz_ctx_create(int device, void* stream, uint64_t arena_hint_byte
     }
     cudaFuncSetAttribute(bpe_block_kernel<1024, 12288>, cudaFuncAttributeMaxDynamicSharedMemorySize, 12288 * 15);
     {
-        const int sm = (int)sizeof(TileShared);
+        const int sm = (int)sizeof(BlockShared);
         cudaFuncSetAttribute(slice_words_kernel<TKZ_MODEL_BPE, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
         cudaFuncSetAttribute(slice_words_kernel<TKZ_MODEL_BPE, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
         cudaFuncSetAttribute(slice_words_kernel<TKZ_MODEL_BPE, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
@@ -249,8 +248,7 @@ extern "C" int tkz_ctx_create(int device, void* stream, uint64_t arena_hint_byte
     ctx->h_ctrl.cap = 64 * sizeof(unsigned long long);
     (void)arena_hint_bytes;
     if (const char* e = getenv("TKZ_NO_DEDUP")) ctx->use_dedup = !(e[0] == '1');     // A/B switch for the parity tests
-    if (const char* e = getenv("TKZ_FUSED_EMIT")) ctx->use_fused = (e[0] == '1');
-    if (const char* e = getenv("TKZ_TILES")) ctx->use_tiles = !(e[0] == '0');
+    if (const char* e = getenv("TKZ_SLICES")) ctx->use_slices = !(e[0] == '0');
     if (const char* e = getenv("TKZ_CHUNK_BYTES")) { const long long v = atoll(e); if (v > 0) ctx->chunk_bytes = (uint64_t)v; }
     cudaStreamCreateWithFlags(&ctx->s_h2d, cudaStreamNonBlocking);
     cudaStreamCreateWithFlags(&ctx->s_d2h, cudaStreamNonBlocking);
@@ -277,8 +275,8 @@ extern "C" void tkz_ctx_destroy(tkz_ctx* ctx) {
                       &ctx->outs[1].attn, &ctx->outs[1].type, &ctx->outs[1].special, &ctx->in_text[0], &ctx->in_text[1], &ctx->in_doc_off[0],
                       &ctx->in_doc_off[1], &ctx->a_ctrl, &ctx->a_table, &ctx->a_uniq, &ctx->a_long_start, &ctx->a_long_end, &ctx->a_long_ntok,
                       &ctx->a_tile_words, &ctx->a_tile_nwords, &ctx->a_tile_ntok, &ctx->a_doc_word_ref, &ctx->a_doc_tok_local,
-                      &ctx->a_doc_tok_start, &ctx->a_doc_real, &ctx->a_upool, &ctx->a_tile_doc_lo, &ctx->a_g_first, &ctx->a_g_win, &ctx->a_g_flag, &ctx->a_big, &ctx->a_tile_state,
-                      &ctx->a_wtable, &ctx->a_lscratch, &ctx->a_ent, &ctx->a_tile_ent_off, &ctx->a_long_tile, &ctx->a_region_ctr};
+                      &ctx->a_doc_tok_start, &ctx->a_doc_real, &ctx->a_upool, &ctx->a_tile_doc_lo, &ctx->a_g_first, &ctx->a_g_win, &ctx->a_g_flag, &ctx->a_big,
+                      &ctx->a_wtable, &ctx->a_lscratch, &ctx->a_ent, &ctx->a_tile_ent_off, &ctx->a_long_slice, &ctx->a_region_ctr};
     for (DevBuf* b : bufs) release(*b);
     HostBuf* hb[] = {&ctx->h_ctrl, &ctx->h_doc_tok_off, &ctx->h_ids, &ctx->h_off, &ctx->h_attn, &ctx->h_type, &ctx->h_special,
                      &ctx->h_doc_stage[0], &ctx->h_doc_stage[1]};
@@ -503,26 +501,26 @@ int launch_bpe(tkz_ctx* ctx, const DevModel& m, const uint8_t* d_text, const uin
     return TKZ_OK;
 }
 
-// The tile pipeline (tkz_tiles.cuh).  Returns TKZ_RETRY_MULTIPASS when pass A ran out of an estimated capacity (entry
+// The slice pipeline (tkz_slices.cuh).  Returns TKZ_RETRY_MULTIPASS when pass A ran out of an estimated capacity (entry
 // list, record pool, scratch, long list): the caller then runs the older multi-pass dedup pipeline on the same batch and
 // the next batch of this context gets larger estimates.
 #define TKZ_RETRY_MULTIPASS 2
 template <int MODEL>
-void launch_slice_words(const DevModel& m, const TileArgs& ta, bool nid, bool iso, uint32_t blocks, cudaStream_t st) {
-    const size_t sm = sizeof(TileShared);
+void launch_slice_words(const DevModel& m, const SliceArgs& ta, bool nid, bool iso, uint32_t blocks, cudaStream_t st) {
+    const size_t sm = sizeof(BlockShared);
     if (nid && !iso) slice_words_kernel<MODEL, true, false><<<blocks, TW_THREADS, sm, st>>>(m, ta);
     else if (nid) slice_words_kernel<MODEL, true, true><<<blocks, TW_THREADS, sm, st>>>(m, ta);
     else if (!iso) slice_words_kernel<MODEL, false, false><<<blocks, TW_THREADS, sm, st>>>(m, ta);
     else slice_words_kernel<MODEL, false, true><<<blocks, TW_THREADS, sm, st>>>(m, ta);
 }
 
-int encode_tiles(tkz_ctx* ctx, const DevModel& m, const uint8_t* d_text, const uint64_t* d_doc_off, uint32_t nd, uint64_t N,
+int encode_slices(tkz_ctx* ctx, const DevModel& m, const uint8_t* d_text, const uint64_t* d_doc_off, uint32_t nd, uint64_t N,
                  const tkz_encode_params& P, tkz_batch_result* out, uint64_t& launches) {
     cudaStream_t st = ctx->stream;
     unsigned long long* ctrl = (unsigned long long*)ctx->a_ctrl.p;
     unsigned long long* hctrl = (unsigned long long*)ctx->h_ctrl.p;
     const uint64_t n_docs = nd;
-    const uint32_t n_tiles = (uint32_t)(N / TW_SLICE + 1);               // slices
+    const uint32_t n_slices = (uint32_t)(N / TW_SLICE + 1);
     const bool plain = !P.has_truncation && !P.has_padding;
     // ---- capacities: from the text size and from what earlier batches of this context needed
     uint64_t want = N / 32; if (want < (1u << 16)) want = 1u << 16; if (want > (1u << 22)) want = 1u << 22;
@@ -536,32 +534,32 @@ int encode_tiles(tkz_ctx* ctx, const DevModel& m, const uint8_t* d_text, const u
     if (upool_cap > 0xFFFFFF00ull) upool_cap = 0xFFFFFF00ull;
     uint64_t ls_cap = N / 16 + (1u << 22); if (ls_cap > 0xFFFFFF00ull) ls_cap = 0xFFFFFF00ull;
     // entry list: warps claim TW_ENT_CHUNK entries at a time (the unused tail of a chunk is lost)
-    const uint32_t grid = (uint32_t)std::min<uint64_t>(((uint64_t)n_tiles + TW_WARPS - 1) / TW_WARPS, (uint64_t)ctx->sm_count * 12);
+    const uint32_t grid = (uint32_t)std::min<uint64_t>(((uint64_t)n_slices + TW_WARPS - 1) / TW_WARPS, (uint64_t)ctx->sm_count * 12);
     uint64_t ent_cap = N + 16;                                               // words <= bytes
     if (ctx->tw_words_per_byte > 0.0) { const uint64_t e2 = (uint64_t)((double)N * ctx->tw_words_per_byte * 1.25) + 65536; if (e2 < ent_cap) ent_cap = e2; }
     else if (N > (64ull << 20)) ent_cap = N / 2 + 65536;
-    ent_cap += ent_cap / 4 + std::min<uint64_t>(n_tiles, (uint64_t)grid * TW_WARPS) * TW_ENT_CHUNK;
+    ent_cap += ent_cap / 4 + std::min<uint64_t>(n_slices, (uint64_t)grid * TW_WARPS) * TW_ENT_CHUNK;
     if (ent_cap > 0xFFFFF000ull) ent_cap = 0xFFFFF000ull;
     const uint32_t long_cap = (uint32_t)(N / 256 + 1024);
     TRY(ensure(ctx, ctx->a_wtable, ((size_t)tcap + mcap) * sizeof(WordSlot) + (size_t)m32cap * sizeof(WordSlot32)));
     TRY(ensure(ctx, ctx->a_upool, (size_t)upool_cap * 8));
     TRY(ensure(ctx, ctx->a_lscratch, (size_t)ls_cap * 4));
     TRY(ensure(ctx, ctx->a_ent, (size_t)ent_cap * 8));
-    TRY(ensure(ctx, ctx->a_tile_ent_off, ((size_t)n_tiles + 2) * 4));
-    TRY(ensure(ctx, ctx->a_tile_nwords, ((size_t)n_tiles + 2) * 4));
-    TRY(ensure(ctx, ctx->a_tile_ntok, ((size_t)n_tiles + 2) * 4));
-    TRY(ensure(ctx, ctx->a_tile_doc_lo, ((size_t)n_tiles + 2) * 4));
+    TRY(ensure(ctx, ctx->a_tile_ent_off, ((size_t)n_slices + 2) * 4));
+    TRY(ensure(ctx, ctx->a_tile_nwords, ((size_t)n_slices + 2) * 4));
+    TRY(ensure(ctx, ctx->a_tile_ntok, ((size_t)n_slices + 2) * 4));
+    TRY(ensure(ctx, ctx->a_tile_doc_lo, ((size_t)n_slices + 2) * 4));
     TRY(ensure(ctx, ctx->a_doc_word_ref, (n_docs + 2) * 4));
     TRY(ensure(ctx, ctx->a_doc_tok_local, (n_docs + 2) * 4));
     TRY(ensure(ctx, ctx->a_long_start, (size_t)long_cap * 4));
     TRY(ensure(ctx, ctx->a_long_end, (size_t)long_cap * 4));
-    TRY(ensure(ctx, ctx->a_long_tile, (size_t)long_cap * 4));
+    TRY(ensure(ctx, ctx->a_long_slice, (size_t)long_cap * 4));
     TRY(ensure(ctx, ctx->O().doc_tok_off, (n_docs + 1) * 8));
-    TRY(ensure(ctx, ctx->a_scan_tmp, (scan_tmp_elems(n_tiles) + scan_tmp_elems(n_docs)) * 8));
+    TRY(ensure(ctx, ctx->a_scan_tmp, (scan_tmp_elems(n_slices) + scan_tmp_elems(n_docs)) * 8));
     CK(cudaMemsetAsync(ctx->a_wtable.p, 0, ((size_t)tcap + mcap) * sizeof(WordSlot) + (size_t)m32cap * sizeof(WordSlot32), st));
-    tile_doc_index_kernel<<<(n_tiles + 1 + 255) / 256, 256, 0, st>>>(d_doc_off, nd, n_tiles, TW_SLICE, (uint32_t*)ctx->a_tile_doc_lo.p); launches++;
-    TileArgs ta{};
-    ta.text = d_text; ta.n = N; ta.doc_off = d_doc_off; ta.n_docs = nd; ta.n_slices = n_tiles; ta.slice_doc_lo = (const uint32_t*)ctx->a_tile_doc_lo.p;
+    tile_doc_index_kernel<<<(n_slices + 1 + 255) / 256, 256, 0, st>>>(d_doc_off, nd, n_slices, TW_SLICE, (uint32_t*)ctx->a_tile_doc_lo.p); launches++;
+    SliceArgs ta{};
+    ta.text = d_text; ta.n = N; ta.doc_off = d_doc_off; ta.n_docs = nd; ta.n_slices = n_slices; ta.slice_doc_lo = (const uint32_t*)ctx->a_tile_doc_lo.p;
     ta.table = (WordSlot*)ctx->a_wtable.p; ta.table_mask = tcap - 1; ta.med_base = tcap; ta.med_mask = mcap - 1;
     ta.table32 = (WordSlot32*)((WordSlot*)ctx->a_wtable.p + tcap + mcap); ta.table32_mask = m32cap - 1;
     ta.upool = (unsigned long long*)ctx->a_upool.p; ta.upool_cap = (uint32_t)upool_cap; ta.upool_count = (unsigned int*)(ctrl + 9);
@@ -569,7 +567,7 @@ int encode_tiles(tkz_ctx* ctx, const DevModel& m, const uint8_t* d_text, const u
     ta.ent = (uint2*)ctx->a_ent.p; ta.ent_cap = (uint32_t)ent_cap; ta.ent_count = (unsigned int*)(ctrl + 5);
     ta.slice_ent_off = (uint32_t*)ctx->a_tile_ent_off.p; ta.slice_nwords = (uint32_t*)ctx->a_tile_nwords.p; ta.slice_ntok = (uint32_t*)ctx->a_tile_ntok.p;
     ta.doc_word_ref = (uint32_t*)ctx->a_doc_word_ref.p; ta.doc_tok_local = (uint32_t*)ctx->a_doc_tok_local.p;
-    ta.long_start = (uint32_t*)ctx->a_long_start.p; ta.long_end = (uint32_t*)ctx->a_long_end.p; ta.long_tile = (uint32_t*)ctx->a_long_tile.p;
+    ta.long_start = (uint32_t*)ctx->a_long_start.p; ta.long_end = (uint32_t*)ctx->a_long_end.p; ta.long_slice = (uint32_t*)ctx->a_long_slice.p;
     ta.n_long = (unsigned int*)(ctrl + 7); ta.long_cap = long_cap;
     ta.abort_flag = (unsigned int*)(ctrl + 8); ta.errw = ctrl;
     ta.n_words = ctrl + 10; ta.n_uniq = (unsigned int*)(ctrl + 6); ta.n_uncached = (unsigned int*)(ctrl + 6) + 1;
@@ -605,14 +603,14 @@ int encode_tiles(tkz_ctx* ctx, const DevModel& m, const uint8_t* d_text, const u
             const uint64_t cap = (uint64_t)ctx->sm_count * 8; if (blocks > cap) blocks = cap;
             wordpiece_warp_kernel<<<(unsigned)blocks, WP_WARPS * 32, 0, st>>>(m, a); launches++;
         }
-        long_fix_kernel<<<(n_long + 255) / 256, 256, 0, st>>>(ta.long_start, ta.long_tile, (const uint32_t*)ctx->a_long_ntok.p, n_long, ta.slice_doc_lo,
+        long_fix_kernel<<<(n_long + 255) / 256, 256, 0, st>>>(ta.long_start, ta.long_slice, (const uint32_t*)ctx->a_long_ntok.p, n_long, ta.slice_doc_lo,
                                                                d_doc_off, ta.slice_ntok, ta.doc_tok_local); launches++;
     }
     CK(cudaEventRecord(ctx->ev[2], st));
 
     // ---- tokens per tile -> token base per tile; CSR offsets
     EmitParams ep{P.has_truncation, P.max_length, P.has_padding, P.pad_length, P.pad_id, P.pad_type_id, P.pad_left, P.outputs};
-    launches += exclusive_scan<uint32_t>(ta.slice_ntok, n_tiles, ta.slice_ntok, (unsigned long long*)ctx->a_scan_tmp.p, st);
+    launches += exclusive_scan<uint32_t>(ta.slice_ntok, n_slices, ta.slice_ntok, (unsigned long long*)ctx->a_scan_tmp.p, st);
     unsigned long long* doc_tok_off = (unsigned long long*)ctx->O().doc_tok_off.p;
     if (!plain) {
         TRY(ensure(ctx, ctx->a_doc_tok_start, (n_docs + 2) * 4));
@@ -622,7 +620,7 @@ int encode_tiles(tkz_ctx* ctx, const DevModel& m, const uint8_t* d_text, const u
         launches += exclusive_scan<unsigned long long>(doc_tok_off, n_docs, doc_tok_off, (unsigned long long*)ctx->a_scan_tmp.p, st);
         TRY(readback(ctx, hctrl + 3, doc_tok_off + n_docs, 8));
     }
-    TRY(readback(ctx, hctrl + 32, ta.slice_ntok + n_tiles, 4));
+    TRY(readback(ctx, hctrl + 32, ta.slice_ntok + n_slices, 4));
     TRY(readback(ctx, hctrl, ctrl, 8));
     CK(cudaStreamSynchronize(st));
     const uint64_t T_real = (uint32_t)hctrl[32], T = plain ? T_real : hctrl[3];
@@ -649,8 +647,8 @@ int encode_tiles(tkz_ctx* ctx, const DevModel& m, const uint8_t* d_text, const u
                (uint32_t*)ctx->O().special.p};
     const uint32_t big_cap = (uint32_t)(N / EMIT_BIG + 16);
     TRY(ensure(ctx, ctx->a_big, (size_t)big_cap * sizeof(uint4)));
-    TileEmitArgs ea{};
-    ea.doc_off = d_doc_off; ea.n_docs = nd; ea.n_slices = n_tiles; ea.slice_doc_lo = ta.slice_doc_lo;
+    SliceEmitArgs ea{};
+    ea.doc_off = d_doc_off; ea.n_docs = nd; ea.n_slices = n_slices; ea.slice_doc_lo = ta.slice_doc_lo;
     ea.ent = ta.ent; ea.slice_ent_off = ta.slice_ent_off; ea.slice_nwords = ta.slice_nwords; ea.slice_tokbase = ta.slice_ntok;
     ea.upool = ta.upool; ea.long_start = ta.long_start; ea.long_ntok = (const uint32_t*)ctx->a_long_ntok.p;
     ea.pool_id = (const uint32_t*)ctx->a_pool_id.p; ea.pool_s = (const uint32_t*)ctx->a_pool_s.p; ea.pool_e = (const uint32_t*)ctx->a_pool_e.p;
@@ -781,72 +779,6 @@ int encode_dedup(tkz_ctx* ctx, const DevModel& m, const uint8_t* d_text, const u
     ta.tile_ntok = (uint32_t*)ctx->a_tile_ntok.p; ta.doc_tok_local = (uint32_t*)ctx->a_doc_tok_local.p;
     ta.doc_tok_start = (uint32_t*)ctx->a_doc_tok_start.p; ta.doc_tok_off = (unsigned long long*)ctx->O().doc_tok_off.p;
     ta.errw = ctrl; ta.err_code = m.kind == TKZ_MODEL_BPE ? TKZ_ECODE_UTF8 : TKZ_ECODE_UNK;
-    // ---- fused P3 (plain concatenation) when this context already knows the token density of its workload
-    const bool plain = !P.has_truncation && !P.has_padding;
-    if (plain && ctx->use_fused && ctx->tok_per_byte_hist > 0.0) {
-        uint64_t est = (uint64_t)((double)N * ctx->tok_per_byte_hist * 1.25) + 65536;
-        if (est > N + 16) est = N + 16;                                  // tokens <= bytes
-        TRY(ensure(ctx, ctx->O().ids, est * 4));
-        if (P.outputs & TKZ_OUT_OFFSETS) TRY(ensure(ctx, ctx->O().off, est * 8));
-        if (P.outputs & TKZ_OUT_ATTENTION) TRY(ensure(ctx, ctx->O().attn, est * 4));
-        if (P.outputs & TKZ_OUT_TYPE_IDS) TRY(ensure(ctx, ctx->O().type, est * 4));
-        if (P.outputs & TKZ_OUT_SPECIAL) TRY(ensure(ctx, ctx->O().special, est * 4));
-        uint64_t cap = ctx->O().ids.cap / 4;
-        if (P.outputs & TKZ_OUT_OFFSETS) cap = std::min<uint64_t>(cap, ctx->O().off.cap / 8);
-        if (P.outputs & TKZ_OUT_ATTENTION) cap = std::min<uint64_t>(cap, ctx->O().attn.cap / 4);
-        if (P.outputs & TKZ_OUT_TYPE_IDS) cap = std::min<uint64_t>(cap, ctx->O().type.cap / 4);
-        if (P.outputs & TKZ_OUT_SPECIAL) cap = std::min<uint64_t>(cap, ctx->O().special.cap / 4);
-        TRY(ensure(ctx, ctx->a_tile_state, (size_t)n_tiles * 8));
-        CK(cudaMemsetAsync(ctx->a_tile_state.p, 0, (size_t)n_tiles * 8, st));
-        const uint32_t big_cap = (uint32_t)(N / EMIT_BIG + 16);
-        TRY(ensure(ctx, ctx->a_big, (size_t)big_cap * sizeof(uint4)));
-        ta.big = BigList{(uint4*)ctx->a_big.p, (unsigned int*)(ctrl + 9) + 1, big_cap};
-        EmitOut eo{(uint32_t*)ctx->O().ids.p, (uint32_t*)ctx->O().off.p, (uint32_t*)ctx->O().attn.p, (uint32_t*)ctx->O().type.p,
-                   (uint32_t*)ctx->O().special.p};
-        FusedArgs fa{(unsigned long long*)ctx->a_tile_state.p, (unsigned int*)(ctrl + 11) + 1, cap, (unsigned int*)(ctrl + 12) + 1};
-        CK(cudaEventRecord(ctx->ev[3], st));
-        tile_emit_fused_kernel<<<n_tiles, DT_THREADS, 0, st>>>(ta, ep, eo, fa); launches++;
-        if (n_long) { emit_big_kernel<<<ctx->sm_count * 4, 256, 0, st>>>(ep, eo, ta.big, ta.pool_id, ta.pool_s, ta.pool_e); launches++; }
-        tile_words_total_kernel<<<64, 256, 0, st>>>(da.tile_nwords, n_tiles, ctrl); launches++;
-        TRY(readback(ctx, hctrl, ctrl, 13 * 8));
-        TRY(readback(ctx, hctrl + 32, (unsigned long long*)ctx->a_tile_state.p + (n_tiles - 1), 8));
-        CK(cudaEventRecord(ctx->ev[4], st));
-        CK(cudaStreamSynchronize(st));
-        const bool overflow = (hctrl[12] >> 32) != 0;
-        const unsigned long long errw = hctrl[0];
-        if (!overflow) {
-            const uint64_t T = hctrl[32] & LB_VAL;
-            ctx->stats.n_words = hctrl[10]; ctx->stats.n_unique_words = n_uniq; ctx->stats.n_long_words = n_long;
-            ctx->stats.kernel_launches = launches;
-            if (errw != TKZ_ERRW_NONE) {
-                // document of the first failing word (text order): last document whose first-word reference is <= it
-                std::vector<uint32_t> ref(n_docs + 1);
-                CK(cudaMemcpy(ref.data(), da.doc_word_ref, (n_docs + 1) * 4, cudaMemcpyDeviceToHost));
-                const uint32_t v = (uint32_t)(errw >> 8);
-                const size_t dd = std::upper_bound(ref.begin(), ref.begin() + n_docs, v) - ref.begin();
-                out->err_doc = dd ? (int64_t)dd - 1 : 0;
-                const uint32_t code = (uint32_t)(errw & 0xFF);
-                ctx->err = code == TKZ_ECODE_UTF8 ? "invalid UTF-8 in a BPE pre-token (reference behaviour undefined)" : "MissingUnkToken";
-                return code == TKZ_ECODE_UTF8 ? TKZ_ERR_INVALID_UTF8 : TKZ_ERR_MISSING_UNK;
-            }
-            if (N) ctx->tok_per_byte_hist = std::max(ctx->tok_per_byte_hist, (double)T / (double)N);
-            cudaEventElapsedTime(&ctx->stats.ms_split, ctx->ev[0], ctx->ev[1]);
-            cudaEventElapsedTime(&ctx->stats.ms_model, ctx->ev[1], ctx->ev[2]);
-            ctx->stats.ms_scan = 0.f;
-            cudaEventElapsedTime(&ctx->stats.ms_emit, ctx->ev[3], ctx->ev[4]);
-            cudaEventElapsedTime(&ctx->stats.ms_total, ctx->ev[0], ctx->ev[4]);
-            out->n_docs = n_docs; out->n_tokens = T; out->n_real_tokens = T;
-            out->doc_tok_off = (const uint64_t*)ta.doc_tok_off;
-            out->ids = eo.ids;
-            out->offsets = (P.outputs & TKZ_OUT_OFFSETS) ? eo.offsets : nullptr;
-            out->attention_mask = (P.outputs & TKZ_OUT_ATTENTION) ? eo.attention : nullptr;
-            out->type_ids = (P.outputs & TKZ_OUT_TYPE_IDS) ? eo.type_ids : nullptr;
-            out->special_tokens_mask = (P.outputs & TKZ_OUT_SPECIAL) ? eo.special : nullptr;
-            return TKZ_OK;
-        }
-        // the estimate was too small: counted path below (it re-reads everything, results are unaffected)
-        CK(cudaMemsetAsync(ctrl + 9, 0, 16, st));          // big-list counter (upper half of ctrl[9]) and the word total restart
-    }
     tile_count_kernel<<<n_tiles, DT_THREADS, 0, st>>>(ta); launches++;
     tile_words_total_kernel<<<64, 256, 0, st>>>(da.tile_nwords, n_tiles, ctrl); launches++;
     launches += exclusive_scan<uint32_t>(ta.tile_ntok, n_tiles, ta.tile_ntok, (unsigned long long*)ctx->a_scan_tmp.p, st);
@@ -894,7 +826,6 @@ int encode_dedup(tkz_ctx* ctx, const DevModel& m, const uint8_t* d_text, const u
     cudaEventElapsedTime(&ctx->stats.ms_scan, ctx->ev[2], ctx->ev[3]);
     cudaEventElapsedTime(&ctx->stats.ms_emit, ctx->ev[3], ctx->ev[4]);
     cudaEventElapsedTime(&ctx->stats.ms_total, ctx->ev[0], ctx->ev[4]);
-    if (N && !P.has_truncation && !P.has_padding) ctx->tok_per_byte_hist = std::max(ctx->tok_per_byte_hist, (double)T_real / (double)N);
     out->n_docs = n_docs; out->n_tokens = T; out->n_real_tokens = T_real;
     out->doc_tok_off = (const uint64_t*)ta.doc_tok_off;
     out->ids = eo.ids;
@@ -956,8 +887,8 @@ int encode_device_impl(tkz_ctx* ctx, const uint8_t* d_text, const uint64_t* d_do
     // ---- dedup pipeline (tkz_dedup.cuh) whenever there is a pre-tokenizer; falls through to the per-occurrence
     //      pipeline below only if its long list overflowed (pathological: > N/16 long words)
     ctx->stats.path = m.has_pretok && ctx->use_dedup ? 1 : 0;
-    if (m.has_pretok && ctx->use_dedup && ctx->use_tiles) {
-        int rc = encode_tiles(ctx, m, d_text, d_doc_off, nd, N, P, out, launches);
+    if (m.has_pretok && ctx->use_dedup && ctx->use_slices) {
+        int rc = encode_slices(ctx, m, d_text, d_doc_off, nd, N, P, out, launches);
         if (rc != TKZ_RETRY_MULTIPASS) return rc;
         ctx->stats.path = 1;
         ctrl_reset_kernel<<<1, 1, 0, st>>>(ctrl); launches++;

@@ -19,7 +19,7 @@
 #include "tkz_common.cuh"
 #include "tkz_emit.cuh"
 #include "tkz_split.cuh"
-#include "tkz_tiles.cuh"
+#include "tkz_slices.cuh"
 #include "tkz_wordpiece.cuh"
 
 namespace tkz {
@@ -511,134 +511,6 @@ __global__ void __launch_bounds__(DT_THREADS) tile_emit_kernel(TileOutArgs a, Em
             const unsigned long long dd = __shfl_sync(FULL, dst, l);
             for (uint32_t i = lane; i < c; i += 32) emit_real(p, o, dd + i, a.pool_id[s + i], a.pool_s[s + i], a.pool_e[s + i]);
         }
-    }
-}
-
-// ------------------------------------------------------------------ P3 fused (plain concatenation): ONE pass over the tile lists.
-// Without truncation / padding the destination of a token is its global index, so counting (P3a), the scan over tiles and
-// the emit (P3b) collapse into one kernel: each tile sums its token counts, obtains its base from the tiles before it by
-// decoupled look-back (tile ids are handed out by an atomic ticket, so every predecessor is running or finished), and
-// writes its tokens.  The slot look-ups of the first 1024 words of a tile are kept in registers between the two phases.
-// The output capacity is an estimate (the exact total is only known afterwards): a tile that would write past `cap`
-// raises `overflow` and the host re-runs the batch through the counted path.
-struct FusedArgs {
-    unsigned long long* tile_state;      // [n_tiles] 0 = not ready | 1<<62 + aggregate | 2<<62 + inclusive prefix
-    unsigned int* ticket;
-    unsigned long long cap;              // slots available in the output arrays
-    unsigned int* overflow;
-};
-constexpr unsigned long long LB_AGG = 1ULL << 62, LB_INC = 2ULL << 62, LB_VAL = (1ULL << 62) - 1;
-constexpr int FUSED_REG_ITERS = 2;
-
-__global__ void __launch_bounds__(DT_THREADS, 8) tile_emit_fused_kernel(TileOutArgs a, EmitParams p, EmitOut o, FusedArgs f) {
-    __shared__ uint32_t scan[2 * (DT_THREADS / 32 + 1)];
-    __shared__ uint32_t pfx[DT_THREADS];
-    __shared__ uint32_t s_tile;
-    __shared__ unsigned long long s_base;
-    const uint32_t FULL = 0xFFFFFFFFu;
-    const uint32_t t = threadIdx.x, lane = lane_id();
-    if (t == 0) s_tile = atomicAdd(f.ticket, 1u);
-    __syncthreads();
-    const uint32_t tile = s_tile;
-    const uint32_t nw = a.tile_nwords[tile];
-    const uint32_t* words = a.tile_words + (size_t)tile * DT_WCAP;
-    const uint32_t d_lo = __ldg(a.tile_doc_lo + tile), d_hi = __ldg(a.tile_doc_lo + tile + 1);
-
-    // ---- phase A: look up every word once, sum the token counts
-    uint32_t r_e[FUSED_REG_ITERS], r_nt[FUSED_REG_ITERS], r_off[FUSED_REG_ITERS]; unsigned long long r_rec[FUSED_REG_ITERS];
-    uint32_t mysum = 0;
-    auto lookup = [&](uint32_t k, uint32_t& e, uint32_t& nt, uint32_t& tok_off, unsigned long long& rec0) {
-        e = 0; nt = 0; tok_off = 0; rec0 = 0;
-        if (k < nw) {
-            e = words[k];
-            if (e & DT_LONG) { nt = __ldg(a.long_ntok + (e & ~DT_LONG)); tok_off = __ldg(a.long_start + (e & ~DT_LONG)); }
-            else { const uint4 v = __ldg(reinterpret_cast<const uint4*>(&a.table[e].tok_off)); tok_off = v.x; nt = v.y; rec0 = (unsigned long long)v.z | ((unsigned long long)v.w << 32); }
-            if (nt == TKZ_NONE) { atomicMin(a.errw, ((unsigned long long)(tile * (uint32_t)DT_WCAP + k) << 8) | a.err_code); nt = 0; }
-        }
-    };
-#pragma unroll
-    for (int it = 0; it < FUSED_REG_ITERS; it++) { lookup(it * DT_THREADS + t, r_e[it], r_nt[it], r_off[it], r_rec[it]); mysum += r_nt[it]; }
-    for (uint32_t i0 = FUSED_REG_ITERS * DT_THREADS; i0 < nw; i0 += DT_THREADS) {
-        uint32_t e, nt, off; unsigned long long rec; lookup(i0 + t, e, nt, off, rec); mysum += nt;
-    }
-    uint32_t tile_total;
-    block_excl_scan32<DT_THREADS / 32>(mysum, scan, 0, &tile_total);
-    // ---- look-back by warp 0: 32 predecessors per round (status words are self-contained: flag + value in one u64)
-    if (t < 32) {
-        volatile unsigned long long* st = f.tile_state;
-        unsigned long long base = 0;
-        if (tile == 0) { if (lane == 0) st[0] = LB_INC | tile_total; }
-        else {
-            if (lane == 0) st[tile] = LB_AGG | tile_total;
-            int hi = (int)tile - 1;                                       // closest predecessor not yet accounted for
-            for (;;) {
-                const int j = hi - (int)lane;
-                unsigned long long v = LB_INC;                            // before tile 0: inclusive prefix 0
-                if (j >= 0) { do { v = st[j]; } while ((v >> 62) == 0); }
-                const uint32_t inc_mask = __ballot_sync(FULL, (v >> 62) == 2);
-                // lanes up to (and including) the closest inclusive prefix contribute
-                const int first_inc = inc_mask ? __ffs(inc_mask) - 1 : 32;
-                unsigned long long c = ((int)lane <= first_inc) ? (v & LB_VAL) : 0ULL;
-                for (int d = 16; d > 0; d >>= 1) c += __shfl_xor_sync(FULL, c, d);
-                base += c;
-                if (inc_mask) break;
-                hi -= 32;
-            }
-            if (lane == 0) st[tile] = LB_INC | (base + tile_total);
-        }
-        if (lane == 0) {
-            s_base = base;
-            if (base + tile_total > f.cap) atomicExch(f.overflow, 1u);
-        }
-    }
-    __syncthreads();
-    const unsigned long long base = s_base;
-    const bool fits = base + tile_total <= f.cap;
-    // ---- phase B: per-word destination = base + prefix; emit
-    uint32_t carry = 0, phase = 1;
-    const uint32_t n_it = (nw + DT_THREADS - 1) / DT_THREADS;
-    for (uint32_t it = 0; it < n_it; it++, phase ^= 1u) {
-        const uint32_t k = it * DT_THREADS + t;
-        uint32_t e, nt, tok_off; unsigned long long rec0;
-        if (it < FUSED_REG_ITERS) {
-            e = r_e[0]; nt = r_nt[0]; tok_off = r_off[0]; rec0 = r_rec[0];
-#pragma unroll
-            for (int q = 1; q < FUSED_REG_ITERS; q++) if (it == (uint32_t)q) { e = r_e[q]; nt = r_nt[q]; tok_off = r_off[q]; rec0 = r_rec[q]; }
-        } else lookup(k, e, nt, tok_off, rec0);
-        uint32_t tot;
-        const uint32_t ex = carry + block_excl_scan32<DT_THREADS / 32>(nt, scan, phase, &tot);
-        carry += tot;
-        const unsigned long long dst = base + ex;
-        // CSR offsets of the documents whose first word falls in this iteration
-        pfx[t] = ex;
-        __syncthreads();
-        for (uint32_t d = d_lo + t; d < d_hi; d += DT_THREADS) {
-            const uint32_t j = a.doc_word_ref[d] - tile * DT_WCAP;
-            if (j >= it * DT_THREADS && j < (it + 1) * DT_THREADS && j < nw) a.doc_tok_off[d] = base + pfx[j - it * DT_THREADS];
-        }
-        const bool is_long = (e & DT_LONG) != 0;
-        uint32_t cnt = fits ? nt : 0;
-        if (cnt && !is_long) {
-            emit_real(p, o, dst, (uint32_t)rec0, (uint32_t)(rec0 >> 32) & 0xFFu, (uint32_t)(rec0 >> 40) & 0xFFu);
-            for (uint32_t i = 1; i < cnt; i++) {
-                const unsigned long long r = __ldg(a.upool + tok_off + i);
-                emit_real(p, o, dst + i, (uint32_t)r, (uint32_t)(r >> 32) & 0xFFu, (uint32_t)(r >> 40) & 0xFFu);
-            }
-        }
-        if (is_long && cnt > EMIT_BIG && big_push(a.big, tok_off, cnt, dst)) cnt = 0;
-        uint32_t big = __ballot_sync(FULL, cnt && is_long);
-        while (big) {
-            const int l = __ffs(big) - 1; big &= big - 1;
-            const uint32_t c = __shfl_sync(FULL, cnt, l), s = __shfl_sync(FULL, tok_off, l);
-            const unsigned long long dd = __shfl_sync(FULL, dst, l);
-            for (uint32_t i = lane; i < c; i += 32) emit_real(p, o, dd + i, a.pool_id[s + i], a.pool_s[s + i], a.pool_e[s + i]);
-        }
-        __syncthreads();                                    // pfx is rewritten by the next iteration
-    }
-    // documents that start in this tile after its last word (or tiles without words): offset = end of the tile
-    for (uint32_t d = d_lo + t; d < d_hi; d += DT_THREADS) {
-        const uint32_t j = a.doc_word_ref[d] - tile * DT_WCAP;
-        if (j >= nw) a.doc_tok_off[d] = base + tile_total;
     }
 }
 

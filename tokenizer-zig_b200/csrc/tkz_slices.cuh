@@ -1,4 +1,4 @@
-// tkz_tiles.cuh -- the slice pipeline: Tokenizer.encode (src/lib.zig:109-160) for a batch in TWO passes over 512-byte text
+// tkz_slices.cuh -- the slice pipeline: Tokenizer.encode (src/lib.zig:109-160) for a batch in TWO passes over 512-byte text
 // slices, one WARP per slice (no block-level barrier anywhere; a block only shares the byte LUT).
 //
 //   pass A  slice_words_kernel  normalise (config.zig:364-379) + pre-tokenize (config.zig:405-450, pretokenizer.zig:49-241)
@@ -37,14 +37,8 @@
 namespace tkz {
 
 constexpr int TW_THREADS = 256, TW_WARPS = 8, TW_SEG = 32, TW_SLICE = 32 * TW_SEG;      // slice = 1 KiB = one 32-byte segment per lane
-#ifndef TW_BPS
-#define TW_BPS 4
-#endif
-constexpr int TW_BLOCKS_PER_SM = TW_BPS;                // pass A: 40 registers per thread, 32 KB of shared memory per block
-constexpr uint32_t TW_ENT_CHUNK = 4096;            // entries a warp claims from the entry list with one atomic (then sub-allocates)
-#ifndef TW_SLOWPATH
-#define TW_SLOWPATH __forceinline__
-#endif                    // entry list regions (one bump counter each, 128 bytes apart)
+constexpr int TW_BLOCKS_PER_SM = 4;                // pass A: 64 registers per thread, 53 KB of shared memory per block (5 / 6 blocks spill: slower)
+constexpr uint32_t TW_ENT_CHUNK = 4096;            // entries a warp claims from the entry list with one atomic (then sub-allocates)                    // entry list regions (one bump counter each, 128 bytes apart)
 constexpr uint32_t TW_MAX_SHORT = 15;             // bytes next to the length byte in the 128-bit key
 constexpr uint32_t TW_MAX_MED = 64;               // medium words: 64-bit tag + byte verification; symbols fit shared memory
 constexpr uint32_t TW_MAX_INLINE = 256;           // longest pre-token a warp tokenizes inside pass A
@@ -73,7 +67,7 @@ __constant__ unsigned long long c_med_pw[TW_MAX_MED];
 struct __align__(64) WordSlot32 { uint32_t k[4]; uint32_t a, b, c, d; uint32_t k2[4]; uint32_t pad[4]; };
 static_assert(sizeof(WordSlot32) == 64, "two sectors");
 
-struct TileArgs {
+struct SliceArgs {
     const uint8_t* text; uint64_t n;
     const uint64_t* doc_off; uint32_t n_docs;
     uint32_t n_slices;
@@ -86,7 +80,7 @@ struct TileArgs {
     uint32_t* slice_ent_off; uint32_t* slice_nwords; uint32_t* slice_ntok;
     uint32_t* doc_word_ref;                       // per document: slice-local index of the first word at or after its start
     uint32_t* doc_tok_local;                      // per document: tokens of its slice before that word
-    uint32_t* long_start; uint32_t* long_end; uint32_t* long_tile; unsigned int* n_long; uint32_t long_cap;   // long_tile = slice
+    uint32_t* long_start; uint32_t* long_end; uint32_t* long_slice; unsigned int* n_long; uint32_t long_cap;   // long_slice = slice
     unsigned int* abort_flag;
     unsigned long long* errw;                     // min over failing words of (byte position << 8 | code)
     unsigned long long* n_words; unsigned int* n_uniq; unsigned int* n_uncached;
@@ -111,7 +105,7 @@ struct __align__(16) SliceShared {                                      // per w
     uint32_t seg_smask[32], seg_wex[32];                  // per 32-byte segment: word-start bits, words of the slice before it
     uint32_t doc_lo_hi[2];                                // documents that start inside the slice: [lo, hi)
 };
-struct TileShared {
+struct BlockShared {
     uint32_t lut[256];                                    // [7:0] normalised byte, bit 8 WORD, bit 9 ISOLATE
     uint4 lenmask[16];                                    // key mask by length
     SliceShared w[TW_WARPS];
@@ -173,7 +167,7 @@ __device__ __noinline__ uint32_t tw_model_long(const DevModel& m, const uint8_t*
 
 // tokens (ids/ss/ee, n of them; n == TKZ_NONE: rejected) -> value (va, vb) in slot encoding; multi-token words and tokens
 // with offsets beyond a byte go to the record pool.  Warp-collective; false = pool exhausted.
-__device__ __forceinline__ bool tw_make_value(const TileArgs& a, const uint32_t* ids, const uint32_t* ss, const uint32_t* ee, uint32_t n,
+__device__ __forceinline__ bool tw_make_value(const SliceArgs& a, const uint32_t* ids, const uint32_t* ss, const uint32_t* ee, uint32_t n,
                                               uint32_t& va, uint32_t& vb) {
     const uint32_t lane = lane_id();
     if (n == TKZ_NONE) { va = 0; vb = TW_NT1_ERR << 16; return true; }
@@ -286,7 +280,7 @@ __device__ __forceinline__ uint32_t tw_key_hash32(const uint32_t (&k)[8]) {
 
 // One word of 16..31 bytes this warp saw first: model + publish into its WordSlot32.  Out of line.
 template <int MODEL>
-__device__ TW_SLOWPATH WholeWarpOut tw_own_word32(const DevModel& m, const TileArgs& a, SliceShared& sh, uint32_t wp_, uint32_t wlen, uint32_t bslot) {
+__device__ __forceinline__ WholeWarpOut tw_own_word32(const DevModel& m, const SliceArgs& a, SliceShared& sh, uint32_t wp_, uint32_t wlen, uint32_t bslot) {
     const uint32_t lane = lane_id();
     WholeWarpOut out{0u, 0u, false};
     uint8_t* const wbytes = reinterpret_cast<uint8_t*>(sh.wbytes);
@@ -303,7 +297,7 @@ __device__ TW_SLOWPATH WholeWarpOut tw_own_word32(const DevModel& m, const TileA
 // medium words (<= 64 bytes) go through the tag table, 65..256 bytes are tokenized uncached, longer ones join the long list.
 // Kept out of line so that its registers do not weigh on the one-word-per-lane loop.
 template <int MODEL>
-__device__ TW_SLOWPATH WholeWarpOut tw_whole_warp_word(const DevModel& m, const TileArgs& a, const uint32_t* lut, SliceShared& sh, uint32_t s,
+__device__ __forceinline__ WholeWarpOut tw_whole_warp_word(const DevModel& m, const SliceArgs& a, const uint32_t* lut, SliceShared& sh, uint32_t s,
                                                         uint32_t wp_, uint32_t wl_) {
     const uint64_t slice_base = (uint64_t)s * TW_SLICE;
     const uint32_t FULL = 0xFFFFFFFFu;
@@ -383,7 +377,7 @@ __device__ TW_SLOWPATH WholeWarpOut tw_whole_warp_word(const DevModel& m, const 
         uint32_t idx = 0;
         if (lane == 0) {
             idx = atomicAdd(a.n_long, 1u);
-            if (idx < a.long_cap) { a.long_start[idx] = (uint32_t)start; a.long_end[idx] = (uint32_t)(start + wlen); a.long_tile[idx] = s; }
+            if (idx < a.long_cap) { a.long_start[idx] = (uint32_t)start; a.long_end[idx] = (uint32_t)(start + wlen); a.long_slice[idx] = s; }
         }
         idx = __shfl_sync(FULL, idx, 0);
         if (idx >= a.long_cap) out.abort = true;
@@ -475,7 +469,7 @@ __device__ TW_SLOWPATH WholeWarpOut tw_whole_warp_word(const DevModel& m, const 
 
 // One word this warp saw first (short key): model + publish.  Out of line for the same reason.
 template <int MODEL>
-__device__ TW_SLOWPATH WholeWarpOut tw_own_word(const DevModel& m, const TileArgs& a, SliceShared& sh, uint32_t b0, uint32_t b1, uint32_t b2, uint32_t b3,
+__device__ __forceinline__ WholeWarpOut tw_own_word(const DevModel& m, const SliceArgs& a, SliceShared& sh, uint32_t b0, uint32_t b1, uint32_t b2, uint32_t b3,
                                                  uint32_t bslot) {
     const uint32_t lane = lane_id();
     WholeWarpOut out{0u, 0u, false};
@@ -490,9 +484,9 @@ __device__ TW_SLOWPATH WholeWarpOut tw_own_word(const DevModel& m, const TileArg
 
 // pass A: one warp per 512-byte slice, slices strided over all warps of the grid
 template <int MODEL, bool NORM_ID, bool HAS_ISO>
-__global__ void __launch_bounds__(TW_THREADS, TW_BLOCKS_PER_SM) slice_words_kernel(const __grid_constant__ DevModel m, const __grid_constant__ TileArgs a) {
+__global__ void __launch_bounds__(TW_THREADS, TW_BLOCKS_PER_SM) slice_words_kernel(const __grid_constant__ DevModel m, const __grid_constant__ SliceArgs a) {
     extern __shared__ __align__(32) unsigned char tw_smem_raw[];
-    TileShared& bs = *reinterpret_cast<TileShared*>(tw_smem_raw);
+    BlockShared& bs = *reinterpret_cast<BlockShared*>(tw_smem_raw);
     const uint32_t FULL = 0xFFFFFFFFu;
     const uint32_t t = threadIdx.x, lane = t & 31, wid = t >> 5;
     const uint32_t lt_mask = (1u << lane) - 1u;
@@ -756,21 +750,21 @@ __global__ void __launch_bounds__(TW_THREADS, TW_BLOCKS_PER_SM) slice_words_kern
 
 // after the word-list kernels: the tokens of every long word join its tile's count and the token prefix of the documents
 // that start behind it in the same tile
-__global__ void long_fix_kernel(const uint32_t* __restrict__ long_start, const uint32_t* __restrict__ long_tile, const uint32_t* __restrict__ long_ntok,
+__global__ void long_fix_kernel(const uint32_t* __restrict__ long_start, const uint32_t* __restrict__ long_slice, const uint32_t* __restrict__ long_ntok,
                                 uint32_t n_long, const uint32_t* __restrict__ tile_doc_lo, const uint64_t* __restrict__ doc_off,
                                 uint32_t* tile_ntok, uint32_t* doc_tok_local) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_long) return;
     const uint32_t n = long_ntok[i];
     if (n == TKZ_NONE || n == 0) return;
-    const uint32_t tile = long_tile[i];
+    const uint32_t tile = long_slice[i];
     atomicAdd(tile_ntok + tile, n);
     const uint64_t pos = long_start[i];
     for (uint32_t d = tile_doc_lo[tile]; d < tile_doc_lo[tile + 1]; d++) if (doc_off[d] > pos) atomicAdd(doc_tok_local + d, n);
 }
 
 // ------------------------------------------------------------------ pass B
-struct TileEmitArgs {
+struct SliceEmitArgs {
     const uint64_t* doc_off; uint32_t n_docs; uint32_t n_slices; const uint32_t* slice_doc_lo;
     const uint2* ent; const uint32_t* slice_ent_off; const uint32_t* slice_nwords;
     const uint32_t* slice_tokbase;                // exclusive scan of the slice token counts (n_slices + 1)
@@ -824,7 +818,7 @@ __device__ __forceinline__ void te_flush(const EmitParams& p, const EmitOut& o, 
 // PLAIN = no truncation and no padding: the output is the plain concatenation of all tokens in text order, so a token's
 // destination is its global index; tokens are staged in shared memory and written with 16-byte stores.
 template <bool PLAIN>
-__global__ void __launch_bounds__(TW_THREADS, 6) slice_emit_kernel(const __grid_constant__ TileEmitArgs a, const __grid_constant__ EmitParams p,
+__global__ void __launch_bounds__(TW_THREADS, 6) slice_emit_kernel(const __grid_constant__ SliceEmitArgs a, const __grid_constant__ EmitParams p,
                                                                 const __grid_constant__ EmitOut o) {
     __shared__ __align__(16) EmitStage stage[PLAIN ? TW_WARPS : 1];
     const uint32_t FULL = 0xFFFFFFFFu;
