@@ -164,6 +164,31 @@ int tkz_encode_batch(tkz_ctx* ctx, const uint8_t* text, const uint64_t* doc_off,
 int tkz_encode_batch_device(tkz_ctx* ctx, const void* d_text, const void* d_doc_off, uint64_t n_docs,
                             uint64_t text_bytes, const tkz_encode_params* params, tkz_batch_result* out);
 
+/* ------------------------------------------------------------------ decode (the inverse direction) */
+/* Tables of Tokenizer.decode (src/lib.zig:163-189): token strings come from the MODEL vocabulary by id
+ * (model_impl.idToToken); special_ids = ids flagged special in the ADDED vocabulary (skipped when skip_special_tokens,
+ * src/lib.zig:169-177); decoder_kind as the config loader selects it (src/config.zig:459-530): 0 none, 1 "WordPiece"
+ * (drops every "##" pair), 2 "ByteLevel" (copy), 3 "BPE" (U+0120 -> space). */
+typedef struct tkz_decode_desc {
+    const uint8_t* tok_bytes;
+    const uint64_t* tok_off;            /* n_ids + 1; ids without a token have an empty range */
+    uint32_t n_ids;
+    const uint32_t* special_ids;
+    uint32_t n_special;
+    int32_t decoder_kind;
+} tkz_decode_desc;
+typedef struct tkz_decode_result {
+    uint64_t n_seqs;
+    uint64_t n_bytes;
+    const uint64_t* byte_off;           /* n_seqs + 1: sequence s decodes to bytes[byte_off[s] .. byte_off[s+1]) */
+    const uint8_t* bytes;
+} tkz_decode_result;
+int tkz_decode_upload(tkz_ctx* ctx, const tkz_decode_desc* desc);
+/* Replaces the caller loop over Tokenizer.decode: ids = all sequences back to back, seq_off[n_seqs+1].  HOST pointers;
+ * the result arrays are HOST pointers owned by the context (valid until the next decode on it). */
+int tkz_decode_batch(tkz_ctx* ctx, const uint32_t* ids, const uint64_t* seq_off, uint64_t n_seqs, int skip_special_tokens,
+                     tkz_decode_result* out);
+
 /* ------------------------------------------------------------------ host mirror of src/lib.zig (C++ behind a C ABI) */
 typedef struct tkzh_tokenizer tkzh_tokenizer;
 
@@ -200,6 +225,9 @@ int tkzh_encode_batch(tkzh_tokenizer* t, const uint8_t* text, const uint64_t* do
 /* Tokenizer.decode  src/lib.zig:163-189 with the config-path decoders (src/config.zig:459-530): host side only (the
  * decode direction is outside the GPU hot path).  *out points into the tokenizer and is valid until the next decode. */
 int tkzh_decode(tkzh_tokenizer* t, const uint32_t* ids, uint64_t n, int skip_special_tokens, const uint8_t** out, uint64_t* out_len);
+/* the same for a batch of sequences on the GPU (tkz_decode_batch with this tokenizer's tables) */
+int tkzh_decode_batch(tkzh_tokenizer* t, const uint32_t* ids, const uint64_t* seq_off, uint64_t n_seqs, int skip_special_tokens,
+                      tkz_decode_result* out);
 
 /* lookups  src/lib.zig:203-223 (added vocab first, then the model) */
 uint64_t tkzh_get_vocab_size(tkzh_tokenizer* t);

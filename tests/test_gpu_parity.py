@@ -640,3 +640,53 @@ def test_tiles_capacity_estimate_exceeded_falls_back_then_adapts():
     assert_same(t.encode_batch(docs), ref, "second call")
     assert t.stats().path == 2, "the second call should fit the adapted capacities"
     t.close()
+
+
+# ----------------------------------------------------------------------------- decode on the GPU (tkz_decode.cuh)
+def test_decode_batch_on_gpu_matches_host_decode_and_oracle():
+    """Tokenizer.decode (src/lib.zig:163-189) for a batch: the reference's known answers, then random id sequences with
+    every decoder kind, ids outside the vocabulary, special ids, '#' runs and C4 A0 pairs that only form ACROSS token
+    boundaries, sequences longer than one 32-byte step, empty sequences -- against the host decode and the oracle."""
+    js = json.dumps({"model": {"type": "WordPiece", "vocab": {"[PAD]": 0, "[CLS]": 1, "[SEP]": 2, "hello": 3}},
+                     "added_tokens": [{"id": 1, "content": "[CLS]", "special": True}, {"id": 2, "content": "[SEP]", "special": True}]})
+    t, o = pair(js)
+    assert t.decode_batch([[1, 3, 2], [], [3]], False) == [b"[CLS]hello[SEP]", b"", b"hello"]          # src/lib.zig:652-686
+    assert t.decode_batch([[1, 3, 2], [], [3]], True) == [b"hello", b"", b"hello"]
+    t.close()
+    rng = random.Random(11)
+    for dec in (None, "WordPiece", "BPE", "ByteLevel"):
+        vocab = {"[UNK]": 0, "a": 1, "##b": 2, "#": 3, "\u0120c": 4, "d##": 5, "[X]": 6, "\u00c4": 7, "###": 8, "x" * 40: 9, "": 10}
+        root = {"model": {"type": "WordPiece", "vocab": vocab},
+                "added_tokens": [{"id": 6, "content": "[X]", "special": True}, {"id": 1, "content": "a", "special": False}, {"id": 40, "content": "[Y]", "special": True}]}
+        if dec:
+            root["decoder"] = {"type": dec}
+        t, o = pair(json.dumps(root, ensure_ascii=False))
+        seqs = [[rng.randrange(0, 13) for _ in range(rng.choice([0, 1, 2, 5, 12, 40, 200]))] for _ in range(300)]
+        seqs += [[3] * n for n in (1, 2, 3, 31, 32, 33, 64, 65, 1000)] + [[5, 2] * 20, [7, 4] * 30, [], [10, 10], [99, 40]]
+        for skip in (False, True):
+            got = t.decode_batch(seqs, skip)
+            for ids, g in zip(seqs, got):
+                assert g == t.decode(ids, skip) == o.decode(ids, skip), (dec, skip, ids[:20])
+        t.close()
+
+
+def test_decode_round_trip_at_size():
+    """encode a corpus sample on the GPU, decode every document's ids on the GPU: with a vocabulary whose single-codepoint
+    keys cover the text and no decoder rewriting, the decoded bytes are the document without its separators."""
+    js = tokenizers_io.tokenizer_json("gpt2_whitespace")
+    t = tz.Tokenizer.from_json(js, device=0)
+    text, off = corpus.generate("c2", 24 << 20, seed=3)
+    enc = t.encode_packed(text, off, outputs=1)
+    nd = len(off) - 1
+    seqs = [enc.ids[enc.doc_slice(i)] for i in range(nd)]
+    dec = t.decode_batch(seqs)
+    d = t.model_desc()
+    single = {k for k in d["keys"] if len(k.decode("utf-8", "ignore")) == 1}
+    rng = random.Random(4)
+    for i in rng.sample(range(nd), 300):
+        doc = text[int(off[i]):int(off[i + 1])].tobytes()
+        kept = b"".join(ch.encode() for w in doc.split() for ch in w.decode("utf-8") if ch.encode() in single)
+        assert t.decode(seqs[i]) == dec[i]
+        if b"\xc4\xa0" not in kept and b"##" not in kept:               # whatever decoder the JSON names leaves these documents alone
+            assert dec[i] == kept
+    t.close()

@@ -93,6 +93,10 @@ class BatchResult(C.Structure):
     ]
 
 
+class DecodeResult(C.Structure):
+    _fields_ = [("n_seqs", C.c_uint64), ("n_bytes", C.c_uint64), ("byte_off", C.c_void_p), ("bytes", C.c_void_p)]
+
+
 class Stats(C.Structure):
     _fields_ = [("arena_bytes", C.c_uint64), ("n_words", C.c_uint64), ("n_unique_words", C.c_uint64),
                 ("n_long_words", C.c_uint64), ("kernel_launches", C.c_uint64),
@@ -103,9 +107,9 @@ class Stats(C.Structure):
 # every symbol include/tokzig_b200.h declares (checked by tests/test_cabi_symbols.py)
 EXPORTED_SYMBOLS = [
     "tkz_ctx_create", "tkz_ctx_destroy", "tkz_last_error", "tkz_ctx_get_stats", "tkz_model_upload", "tkz_encode_batch",
-    "tkz_encode_batch_device",
+    "tkz_encode_batch_device", "tkz_decode_upload", "tkz_decode_batch",
     "tkzh_from_json", "tkzh_from_file", "tkzh_free", "tkzh_last_error", "tkzh_ctx", "tkzh_set_truncation", "tkzh_set_padding",
-    "tkzh_set_normalizer", "tkzh_set_pretokenizer", "tkzh_encode_batch", "tkzh_decode", "tkzh_get_vocab_size", "tkzh_token_to_id",
+    "tkzh_set_normalizer", "tkzh_set_pretokenizer", "tkzh_encode_batch", "tkzh_decode", "tkzh_decode_batch", "tkzh_get_vocab_size", "tkzh_token_to_id",
     "tkzh_id_to_token", "tkzh_add_special_tokens", "tkzh_model_vocab_count", "tkzh_merge_count", "tkzh_has_normalizer",
     "tkzh_has_pretokenizer", "tkzh_has_post_processor", "tkzh_added_token_count", "tkzh_added_token", "tkzh_model_desc",
 ]
@@ -144,6 +148,9 @@ def lib():
     L.tkzh_set_pretokenizer.argtypes = [vp, vp, C.c_int32]
     L.tkzh_encode_batch.argtypes = [vp, vp, vp, u64, i32, u32, C.POINTER(BatchResult)]
     L.tkzh_decode.argtypes = [vp, vp, u64, i32, C.POINTER(vp), C.POINTER(u64)]
+    L.tkzh_decode_batch.argtypes = [vp, vp, vp, u64, i32, C.POINTER(DecodeResult)]
+    L.tkz_decode_upload.argtypes = [vp, vp]
+    L.tkz_decode_batch.argtypes = [vp, vp, vp, u64, i32, C.POINTER(DecodeResult)]
     L.tkzh_get_vocab_size.argtypes = [vp]
     L.tkzh_get_vocab_size.restype = u64
     L.tkzh_token_to_id.argtypes = [vp, C.c_char_p, u64, C.POINTER(u32)]
@@ -403,6 +410,20 @@ class Tokenizer:
         if rc != OK:
             raise TokzigError(rc)
         return C.string_at(p.value, n.value) if n.value else b""
+
+    def decode_batch(self, seqs: Sequence, skip_special_tokens: bool = False) -> list:
+        """Tokenizer.decode for a batch of id sequences on the GPU (tkz_decode_batch); returns one bytes object per sequence."""
+        lens = np.fromiter((len(x) for x in seqs), dtype=np.uint64, count=len(seqs))
+        off = np.zeros(len(seqs) + 1, dtype=np.uint64)
+        np.cumsum(lens, out=off[1:])
+        ids = np.ascontiguousarray(np.concatenate([np.asarray(x, dtype=np.uint32) for x in seqs]) if len(seqs) and off[-1] else np.zeros(0, np.uint32), dtype=np.uint32)
+        r = DecodeResult()
+        rc = self._L.tkzh_decode_batch(self._h, ids.ctypes.data if ids.size else None, off.ctypes.data, len(seqs), 1 if skip_special_tokens else 0, C.byref(r))
+        if rc != OK:
+            raise TokzigError(rc, (self._L.tkzh_last_error(self._h) or b"").decode())
+        boff = _copy(r.byte_off, len(seqs) + 1, np.uint64)
+        data = C.string_at(r.bytes, int(r.n_bytes)) if r.n_bytes else b""
+        return [data[int(boff[i]):int(boff[i + 1])] for i in range(len(seqs))]
 
     # -- lookups (src/lib.zig:203-223)
     def get_vocab_size(self) -> int:

@@ -19,6 +19,7 @@
 #include "tkz_bpe.cuh"
 #include "tkz_bpe_block.cuh"
 #include "tkz_common.cuh"
+#include "tkz_decode.cuh"
 #include "tkz_dedup.cuh"
 #include "tkz_emit.cuh"
 #include "tkz_slices.cuh"
@@ -76,6 +77,11 @@ struct tkz_ctx {
     uint64_t tw_upool_hist = 0;           // most token records used by one batch
     double tw_words_per_byte = 0.0;       // densest batch so far: sizes the entry list
     HostBuf h_ctrl, h_doc_tok_off, h_ids, h_off, h_attn, h_type, h_special;
+    // decode direction (tkz_decode.cuh)
+    bool has_decode = false;
+    DecodeTables dt{};
+    DevBuf t_dec_bytes, t_dec_off, t_dec_special, a_dec_ids, a_dec_seq_off, a_dec_len, a_dec_raw, a_dec_out, a_dec_olen, a_dec_boff;
+    HostBuf h_dec_bytes, h_dec_off;
     unsigned long long* h_ctrl_dev = nullptr;   // device alias of h_ctrl (mapped pinned memory): scalars are read back by a tiny
                                                 // kernel, not by a D2H memcpy that would queue behind the result copies
     uint64_t arena_bytes = 0;
@@ -276,10 +282,12 @@ extern "C" void tkz_ctx_destroy(tkz_ctx* ctx) {
                       &ctx->in_doc_off[1], &ctx->a_ctrl, &ctx->a_table, &ctx->a_uniq, &ctx->a_long_start, &ctx->a_long_end, &ctx->a_long_ntok,
                       &ctx->a_tile_words, &ctx->a_tile_nwords, &ctx->a_tile_ntok, &ctx->a_doc_word_ref, &ctx->a_doc_tok_local,
                       &ctx->a_doc_tok_start, &ctx->a_doc_real, &ctx->a_upool, &ctx->a_tile_doc_lo, &ctx->a_g_first, &ctx->a_g_win, &ctx->a_g_flag, &ctx->a_big,
-                      &ctx->a_wtable, &ctx->a_lscratch, &ctx->a_ent, &ctx->a_tile_ent_off, &ctx->a_long_slice, &ctx->a_region_ctr};
+                      &ctx->a_wtable, &ctx->a_lscratch, &ctx->a_ent, &ctx->a_tile_ent_off, &ctx->a_long_slice, &ctx->a_region_ctr,
+                      &ctx->t_dec_bytes, &ctx->t_dec_off, &ctx->t_dec_special, &ctx->a_dec_ids, &ctx->a_dec_seq_off, &ctx->a_dec_len, &ctx->a_dec_raw,
+                      &ctx->a_dec_out, &ctx->a_dec_olen, &ctx->a_dec_boff};
     for (DevBuf* b : bufs) release(*b);
     HostBuf* hb[] = {&ctx->h_ctrl, &ctx->h_doc_tok_off, &ctx->h_ids, &ctx->h_off, &ctx->h_attn, &ctx->h_type, &ctx->h_special,
-                     &ctx->h_doc_stage[0], &ctx->h_doc_stage[1]};
+                     &ctx->h_doc_stage[0], &ctx->h_doc_stage[1], &ctx->h_dec_bytes, &ctx->h_dec_off};
     for (HostBuf* b : hb) release_host(*b);
     if (ctx->s_h2d) cudaStreamDestroy(ctx->s_h2d);
     if (ctx->s_d2h) cudaStreamDestroy(ctx->s_d2h);
@@ -1180,4 +1188,94 @@ extern "C" int tkz_encode_batch(tkz_ctx* ctx, const uint8_t* text, const uint64_
     CK(cudaSetDevice(ctx->device));
     if (n_docs >= 2 && N > ctx->chunk_bytes + ctx->chunk_bytes / 2) return encode_host_chunked(ctx, text, doc_off, n_docs, N, params, out);
     return encode_host_single(ctx, text, doc_off, n_docs, N, params, out);
+}
+
+// ------------------------------------------------------------------------------------------------ decode
+extern "C" int tkz_decode_upload(tkz_ctx* ctx, const tkz_decode_desc* d) {
+    if (!ctx || !d || (d->n_ids && (!d->tok_off || (!d->tok_bytes && d->tok_off[d->n_ids])))) return TKZ_ERR_INVALID_ARG;
+    if (d->decoder_kind < 0 || d->decoder_kind > 3) { ctx->err = "unknown decoder_kind"; return TKZ_ERR_INVALID_ARG; }
+    CK(cudaSetDevice(ctx->device));
+    const uint64_t nb = d->n_ids ? d->tok_off[d->n_ids] : 0;
+    TRY(upload(ctx, ctx->t_dec_bytes, d->tok_bytes, (size_t)nb));
+    std::vector<unsigned long long> off(d->n_ids + 1, 0);
+    for (uint32_t i = 0; i <= d->n_ids; i++) off[i] = d->n_ids ? d->tok_off[i] : 0;
+    TRY(upload(ctx, ctx->t_dec_off, off.data(), off.size() * 8));
+    uint32_t max_sp = 0;
+    for (uint32_t i = 0; i < d->n_special; i++) max_sp = std::max(max_sp, d->special_ids[i]);
+    std::vector<uint32_t> bits(d->n_special ? (size_t)(max_sp >> 5) + 1 : 1, 0);
+    for (uint32_t i = 0; i < d->n_special; i++) bits[d->special_ids[i] >> 5] |= 1u << (d->special_ids[i] & 31u);
+    TRY(upload(ctx, ctx->t_dec_special, bits.data(), bits.size() * 4));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->dt = DecodeTables{(const uint8_t*)ctx->t_dec_bytes.p, (const unsigned long long*)ctx->t_dec_off.p, d->n_ids,
+                           (const uint32_t*)ctx->t_dec_special.p, d->n_special ? (uint32_t)bits.size() : 0u, d->decoder_kind};
+    ctx->has_decode = true;
+    return TKZ_OK;
+}
+
+extern "C" int tkz_decode_batch(tkz_ctx* ctx, const uint32_t* ids, const uint64_t* seq_off, uint64_t n_seqs, int skip_special_tokens,
+                                tkz_decode_result* out) {
+    if (!ctx || !out || !seq_off) return TKZ_ERR_INVALID_ARG;
+    memset(out, 0, sizeof *out);
+    if (!ctx->has_decode) { ctx->err = "no decode tables uploaded"; return TKZ_ERR_INVALID_ARG; }
+    if (seq_off[0] != 0) { ctx->err = "seq_off[0] must be 0"; return TKZ_ERR_INVALID_ARG; }
+    const uint64_t n_tok = seq_off[n_seqs];
+    if (n_tok && !ids) return TKZ_ERR_INVALID_ARG;
+    if (n_tok >= 0xFFFFFFF0ull || n_seqs >= 0xFFFFFFF0ull) { ctx->err = "too many ids in one decode batch"; return TKZ_ERR_INVALID_ARG; }
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    unsigned long long* hctrl = (unsigned long long*)ctx->h_ctrl.p;
+    const DecodeTables& t = ctx->dt;
+    TRY(ensure(ctx, ctx->a_dec_ids, n_tok * 4));
+    TRY(ensure(ctx, ctx->a_dec_seq_off, (n_seqs + 1) * 8));
+    TRY(ensure(ctx, ctx->a_dec_len, (n_tok + 2) * 4));
+    TRY(ensure(ctx, ctx->a_dec_olen, (n_seqs + 2) * 4));
+    TRY(ensure(ctx, ctx->a_dec_boff, (n_seqs + 2) * 8));
+    TRY(ensure(ctx, ctx->a_scan_tmp, (scan_tmp_elems(n_tok) + scan_tmp_elems(n_seqs)) * 8));
+    if (n_tok) CK(cudaMemcpyAsync(ctx->a_dec_ids.p, ids, n_tok * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->a_dec_seq_off.p, seq_off, (n_seqs + 1) * 8, cudaMemcpyHostToDevice, st));
+    uint32_t* tok_len = (uint32_t*)ctx->a_dec_len.p;
+    const uint32_t* d_ids = (const uint32_t*)ctx->a_dec_ids.p;
+    const unsigned long long* d_seq = (const unsigned long long*)ctx->a_dec_seq_off.p;
+    if (n_tok) dec_len_kernel<<<(unsigned)((n_tok + 255) / 256), 256, 0, st>>>(t, d_ids, n_tok, skip_special_tokens, tok_len);
+    exclusive_scan<uint32_t>(tok_len, n_tok, tok_len, (unsigned long long*)ctx->a_scan_tmp.p, st);      // tok_len[n_tok] = raw bytes
+    TRY(readback(ctx, hctrl + 40, tok_len + n_tok, 4));
+    CK(cudaStreamSynchronize(st));
+    const uint64_t raw_bytes = (uint32_t)hctrl[40];
+    TRY(ensure(ctx, ctx->a_dec_raw, raw_bytes));
+    uint8_t* raw = (uint8_t*)ctx->a_dec_raw.p;
+    if (n_tok) dec_gather_kernel<<<(unsigned)((n_tok + 255) / 256), 256, 0, st>>>(t, d_ids, n_tok, tok_len, raw);
+    unsigned long long* byte_off = (unsigned long long*)ctx->a_dec_boff.p;
+    const uint8_t* d_bytes = raw;
+    uint64_t out_bytes = raw_bytes;
+    const unsigned seq_blocks = (unsigned)((n_seqs + 1 + 255) / 256), warp_blocks = (unsigned)((n_seqs * 32 + 255) / 256);
+    if (t.decoder_kind == 1 || t.decoder_kind == 3) {
+        uint32_t* olen = (uint32_t*)ctx->a_dec_olen.p;
+        if (n_seqs) {
+            if (t.decoder_kind == 1) dec_filter_kernel<1, false><<<warp_blocks, 256, 0, st>>>(raw, d_seq, tok_len, n_seqs, olen, nullptr, nullptr);
+            else dec_filter_kernel<3, false><<<warp_blocks, 256, 0, st>>>(raw, d_seq, tok_len, n_seqs, olen, nullptr, nullptr);
+        }
+        exclusive_scan<uint32_t>(olen, n_seqs, olen, (unsigned long long*)ctx->a_scan_tmp.p, st);
+        TRY(readback(ctx, hctrl + 41, olen + n_seqs, 4));
+        CK(cudaStreamSynchronize(st));
+        out_bytes = (uint32_t)hctrl[41];
+        TRY(ensure(ctx, ctx->a_dec_out, out_bytes));
+        uint8_t* ob = (uint8_t*)ctx->a_dec_out.p;
+        if (n_seqs) {
+            if (t.decoder_kind == 1) dec_filter_kernel<1, true><<<warp_blocks, 256, 0, st>>>(raw, d_seq, tok_len, n_seqs, nullptr, olen, ob);
+            else dec_filter_kernel<3, true><<<warp_blocks, 256, 0, st>>>(raw, d_seq, tok_len, n_seqs, nullptr, olen, ob);
+        }
+        dec_widen_kernel<<<seq_blocks, 256, 0, st>>>(olen, n_seqs + 1, byte_off);
+        d_bytes = ob;
+    } else {
+        dec_seq_off_kernel<<<seq_blocks, 256, 0, st>>>(d_seq, n_seqs, tok_len, byte_off);
+    }
+    CK(cudaGetLastError());
+    TRY(ensure_host(ctx, ctx->h_dec_bytes, out_bytes));
+    TRY(ensure_host(ctx, ctx->h_dec_off, (n_seqs + 1) * 8));
+    if (out_bytes) CK(cudaMemcpyAsync(ctx->h_dec_bytes.p, d_bytes, out_bytes, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(ctx->h_dec_off.p, byte_off, (n_seqs + 1) * 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    out->n_seqs = n_seqs; out->n_bytes = out_bytes;
+    out->byte_off = (const uint64_t*)ctx->h_dec_off.p; out->bytes = (const uint8_t*)ctx->h_dec_bytes.p;
+    return TKZ_OK;
 }

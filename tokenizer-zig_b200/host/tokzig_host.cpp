@@ -11,6 +11,7 @@
 #include <cerrno>
 #include <cstdio>
 #include <cstring>
+#include <algorithm>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -78,6 +79,7 @@ struct tkzh_tokenizer {
     // device
     tkz_ctx* ctx = nullptr;
     bool dirty = true;
+    bool decode_dirty = true;             // decode tables not uploaded yet / special set changed
 };
 
 namespace {
@@ -369,6 +371,32 @@ extern "C" int tkzh_decode(tkzh_tokenizer* t, const uint32_t* ids, uint64_t n, i
     return TKZ_OK;
 }
 
+// Tokenizer.decode for a batch on the GPU: same tables as tkzh_decode (model vocabulary by id, special ids of the added
+// vocabulary, decoder kind), flattened once and re-uploaded when addSpecialTokens changed the special set.
+extern "C" int tkzh_decode_batch(tkzh_tokenizer* t, const uint32_t* ids, const uint64_t* seq_off, uint64_t n_seqs, int skip_special_tokens,
+                                 tkz_decode_result* out) {
+    if (!t || !out || !seq_off) return TKZ_ERR_INVALID_ARG;
+    if (!t->ctx) { t->err = "tokenizer was loaded without a device (tokzig_b200 has no CPU fallback)"; return TKZ_ERR_CUDA; }
+    if (t->decode_dirty) {
+        uint32_t n_ids = 0;
+        for (auto& kv : t->vocab_r) n_ids = std::max(n_ids, kv.first + 1);
+        std::vector<uint64_t> off((size_t)n_ids + 1, 0);
+        for (auto& kv : t->vocab_r) off[kv.first + 1] = kv.second.size();
+        for (uint32_t i = 0; i < n_ids; i++) off[i + 1] += off[i];
+        std::vector<uint8_t> bytes((size_t)off[n_ids]);
+        for (auto& kv : t->vocab_r) if (!kv.second.empty()) memcpy(bytes.data() + off[kv.first], kv.second.data(), kv.second.size());
+        std::vector<uint32_t> special;
+        for (auto& kv : t->added_vocab.id_to_token) if (t->added_vocab.special.count(kv.second)) special.push_back(kv.first);
+        tkz_decode_desc d{bytes.data(), off.data(), n_ids, special.data(), (uint32_t)special.size(), t->decoder_kind};
+        int rc = tkz_decode_upload(t->ctx, &d);
+        if (rc != TKZ_OK) { t->err = tkz_last_error(t->ctx); return rc; }
+        t->decode_dirty = false;
+    }
+    int rc = tkz_decode_batch(t->ctx, ids, seq_off, n_seqs, skip_special_tokens, out);
+    if (rc != TKZ_OK) t->err = tkz_last_error(t->ctx);
+    return rc;
+}
+
 extern "C" uint64_t tkzh_get_vocab_size(tkzh_tokenizer* t) { return t->vocab.size() + t->added_vocab.token_to_id.size(); }   // lib.zig:203-205
 extern "C" int tkzh_token_to_id(tkzh_tokenizer* t, const uint8_t* token, uint64_t len, uint32_t* id) {                         // lib.zig:208-214
     std::string k((const char*)token, (size_t)len);
@@ -392,6 +420,7 @@ extern "C" int tkzh_add_special_tokens(tkzh_tokenizer* t, const uint8_t* content
         if (t->added_vocab.add(a, true)) c++;
     }
     if (added) *added = c;
+    if (c) t->decode_dirty = true;
     return TKZ_OK;
 }
 extern "C" uint64_t tkzh_model_vocab_count(tkzh_tokenizer* t) { return t->vocab.size(); }

@@ -86,6 +86,21 @@ pub const Stats = extern struct {
     path: u32, // pipeline of the last encode: 0 per-occurrence, 1 dedup multi-pass, 2 slice pipeline
 };
 
+pub const DecodeDesc = extern struct {
+    tok_bytes: ?[*]const u8,
+    tok_off: [*]const u64, // n_ids + 1
+    n_ids: u32,
+    special_ids: ?[*]const u32,
+    n_special: u32,
+    decoder_kind: i32, // 0 none, 1 WordPiece, 2 ByteLevel, 3 BPE (src/config.zig:459-530)
+};
+pub const DecodeResult = extern struct {
+    n_seqs: u64,
+    n_bytes: u64,
+    byte_off: ?[*]const u64,
+    bytes: ?[*]const u8,
+};
+
 pub extern fn tkz_ctx_create(device: c_int, stream: ?*anyopaque, arena_hint_bytes: u64, out: *?*Ctx) c_int;
 pub extern fn tkz_ctx_destroy(ctx: ?*Ctx) void;
 pub extern fn tkz_last_error(ctx: ?*Ctx) [*:0]const u8;
@@ -93,3 +108,5 @@ pub extern fn tkz_ctx_get_stats(ctx: *Ctx, out: *Stats) c_int;
 pub extern fn tkz_model_upload(ctx: *Ctx, desc: *const ModelDesc) c_int;
 pub extern fn tkz_encode_batch(ctx: *Ctx, text: ?[*]const u8, doc_off: [*]const u64, n_docs: u64, params: *const EncodeParams, out: *BatchResult) c_int;
 pub extern fn tkz_encode_batch_device(ctx: *Ctx, d_text: ?*const anyopaque, d_doc_off: *const anyopaque, n_docs: u64, text_bytes: u64, params: *const EncodeParams, out: *BatchResult) c_int;
+pub extern fn tkz_decode_upload(ctx: *Ctx, desc: *const DecodeDesc) c_int;
+pub extern fn tkz_decode_batch(ctx: *Ctx, ids: ?[*]const u32, seq_off: [*]const u64, n_seqs: u64, skip_special_tokens: c_int, out: *DecodeResult) c_int;
