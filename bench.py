@@ -312,6 +312,20 @@ def run_ours(args, rank, local_rank, world):
         e2e = {"value": all_bytes / float(td.item()) / 1e9, "unit": "GB/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                "ms_per_step": float(td.item()) * 1e3, "steps": e2e_steps, "tokens_per_s": all_real / float(td.item()),
                "api": "tkz_encode_batch (host pointers; pinned text H2D + result D2H inside the timed region)"}
+        if params.outputs != 1 and pad is None:
+            # the same call asking for the ids only (what the metric's "output ids" names): shows how much of e2e is the D2H of
+            # offsets + attention mask
+            full_mask = params.outputs
+            params.outputs = 1
+            host_step()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(2):
+                h2d1, d2h1 = host_step()
+            torch.cuda.synchronize()
+            dt1 = (time.perf_counter() - t0) / 2
+            params.outputs = full_mask
+            e2e["ids_only"] = {"value": nbytes / dt1 / 1e9, "unit": "GB/s", "ms_per_step": dt1 * 1e3, "d2h_bytes_per_step": d2h1, "note": "rank-local"}
 
     if rank != 0:
         if world > 1:
