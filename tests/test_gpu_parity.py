@@ -562,7 +562,7 @@ def test_full_size_properties_1gib():
     need no oracle run: (1) batch-split invariance -- the encoding of the whole batch equals the concatenation of the
     encodings of its halves (different slice / chunk / table-occupancy layout); (2) the slice pipeline equals the older
     multi-pass pipeline on all 235 M tokens; (3) token strings of sampled documents concatenate to the document minus
-    the characters the vocabulary lacks; (4) CSR offsets are monotone and end at the token count."""
+    the characters the vocabulary lacks; (4) CSR offsets are monotone and end at the token count; (5) the oracle on the same GiB, every id and offset."""
     js = tokenizers_io.tokenizer_json("gpt2_whitespace")
     text, off = corpus.generate("c2", 1 << 30, seed=1234)
     nd = len(off) - 1
@@ -585,6 +585,12 @@ def test_full_size_properties_1gib():
     assert np.array_equal(old.ids, full.ids) and np.array_equal(old.offsets, full.offsets) and np.array_equal(old.doc_tok_off, full.doc_tok_off)
     del old
     t0.close()
+    # (5) and the oracle itself on the whole GiB (literal BPE.tokenize on all host cores: a few seconds per GiB here)
+    import os
+    o = orc.OracleTokenizer.from_json(js)
+    ref = o.encode_packed(text, off, algo=0, threads=os.cpu_count() or 1)
+    assert np.array_equal(ref.ids, full.ids) and np.array_equal(ref.offsets, full.offsets) and np.array_equal(ref.doc_tok_off, full.doc_tok_off)
+    del ref
     d = t.model_desc()
     id2tok = {int(i): k for k, i in zip(d["keys"], d["ids"])}
     single = {k for k in d["keys"] if len(k.decode("utf-8", "ignore")) == 1}
