@@ -1,15 +1,17 @@
-// tkz_slices.cuh -- the slice pipeline: Tokenizer.encode (src/lib.zig:109-160) for a batch in TWO passes over 512-byte text
+// tkz_slices.cuh -- the slice pipeline: Tokenizer.encode (src/lib.zig:109-160) for a batch in TWO passes over 1 KiB text
 // slices, one WARP per slice (no block-level barrier anywhere; a block only shares the byte LUT).
 //
 //   pass A  slice_words_kernel  normalise (config.zig:364-379) + pre-tokenize (config.zig:405-450, pretokenizer.zig:49-241)
 //                               + model per pre-token (bpe.zig:173-263 / wordpiece.zig:141-222):
-//           1  one 16-byte vector load per lane, byte-class LUT in shared memory, normalised slice kept in shared memory
-//           2  word-start masks (neighbour bits by shuffle), warp scan, list of the words that START in the slice
-//           3  one word per lane: 128-bit key from shared memory, ONE 32-byte probe of the per-batch word table in L2
-//              returns key + token value.  First sight of a word: atom.cas.b128 claims the slot, the claiming warp runs
+//           1  two 16-byte vector loads per lane (32 bytes), byte classes from a shared-memory LUT (or, when the byte map
+//              is the identity, from 256-bit class tables held in registers and read by shuffle), normalised slice kept
+//              in shared memory
+//           2  word-start masks (neighbour bits by shuffle), ballot prefix, list of the words that START in the slice
+//           3  32 words per round, one per lane: 128-bit key from shared memory, ONE 32-byte probe of the per-batch word
+//              table in L2 returns key + token value (straight-line; everything else sits behind one warp vote).  First sight of a word: atom.cas.b128 claims the slot, the claiming warp runs
 //              the model on it right there (warp-cooperative, symbols in shared memory) and publishes the value; a word
 //              whose owner is still computing is polled after the warp has published its own words (owners never wait,
-//              so polling cannot deadlock).  Result: one 8-byte entry per word, written in text order to a compact
+//              so polling cannot deadlock).  Words of 16..31 bytes go the same way through 64-byte slots.  Result: one 8-byte entry per word, written in text order to a compact
 //              per-slice list, tokens per slice, token prefix at every document start.
 //   [word-list kernels on the few pre-tokens longer than TW_MAX_INLINE bytes (tkz_bpe.cuh / tkz_bpe_block.cuh /
 //    tkz_wordpiece.cuh), long_fix_kernel adds their token counts]
@@ -20,8 +22,8 @@
 //
 // Exact because the model is a pure function of the normalised pre-token bytes and the reference's offsets are pre-token
 // relative (lib.zig:133-137 never adds the pre-token start): every occurrence of a word gets identical records.  The table
-// key is the word itself (<= 15 bytes + length, compared as 128 bits) or, for 16..64 bytes, a 64-bit tag verified byte by
-// byte against a representative occurrence -- there is no hash-collision case.  The table lives for one batch.
+// key is the word itself (<= 15 bytes + length compared as 128 bits, 16..31 bytes as 256 bits) or, for 32..64 bytes, a 64-bit
+// tag verified byte by byte against a representative occurrence -- there is no hash-collision case.  The table lives for one batch.
 //
 // History (profiles/r01_v11_*, r01_v12_*): a one-launch variant (pass A + decoupled look-back + emit) measured 2x slower
 // than the multi-pass pipeline -- slices that run the model take 5-10 us longer than their neighbours and every later
@@ -38,9 +40,9 @@ namespace tkz {
 
 constexpr int TW_THREADS = 256, TW_WARPS = 8, TW_SEG = 32, TW_SLICE = 32 * TW_SEG;      // slice = 1 KiB = one 32-byte segment per lane
 constexpr int TW_BLOCKS_PER_SM = 4;                // pass A: 64 registers per thread, 53 KB of shared memory per block (5 / 6 blocks spill: slower)
-constexpr uint32_t TW_ENT_CHUNK = 4096;            // entries a warp claims from the entry list with one atomic (then sub-allocates)                    // entry list regions (one bump counter each, 128 bytes apart)
+constexpr uint32_t TW_ENT_CHUNK = 4096;            // entries a warp claims from the entry list with one atomic (then sub-allocates)
 constexpr uint32_t TW_MAX_SHORT = 15;             // bytes next to the length byte in the 128-bit key
-constexpr uint32_t TW_MAX_MED = 64;               // medium words: 64-bit tag + byte verification; symbols fit shared memory
+constexpr uint32_t TW_MAX_MED = 64;               // words of 32..64 bytes: 64-bit tag + byte verification; symbols fit shared memory
 constexpr uint32_t TW_MAX_INLINE = 256;           // longest pre-token a warp tokenizes inside pass A
 constexpr int TW_MAX_PROBE = 32;
 constexpr uint32_t TW_POOLF = 0x80000000u;        // value / entry flag: token records are in upool[a .. a + ntok)
