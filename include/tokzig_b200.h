@@ -138,7 +138,7 @@ typedef struct tkz_stats {
     float ms_scan;                      /* prefix sums: tokens per word -> per document -> CSR */
     float ms_emit;                      /* K5: fused truncate / pad / output write */
     float ms_total;                     /* first kernel to last kernel */
-    uint32_t model_flags;               /* bit 0: merge table proven "proper" -> long words use the windowed block kernels */
+    uint32_t model_flags;               /* bit 0: merge table proven "proper" -> long words use the windowed block kernels; bit 1: the last encode ran the grid-wide kernel on huge words */
     uint32_t path;                      /* pipeline of the last encode: 0 per-occurrence, 1 dedup multi-pass, 2 tile pipeline
                                            (then ms_split = pass A, ms_model = word-list kernels, ms_emit = pass B) */
 } tkz_stats;

@@ -426,6 +426,86 @@ def test_windowed_cascades_and_runs_at_length():
     t.close()
 
 
+# ----------------------------------------------------------------------------- grid-wide kernel (huge words, tkz_bpe_grid.cuh)
+def _huge_docs(rng, alpha, lengths, p_run=0.08, drop=("z", "語")):
+    """Unbroken words (no white space): random symbols, equal-symbol runs of 2..90 (longer than the kernel's walk limit of
+    32), characters that are not in the vocabulary (dropped, or <unk>)."""
+    docs = []
+    for n in lengths:
+        out = []
+        while len(out) < n:
+            x = rng.random()
+            if x < p_run:
+                out.extend([rng.choice(alpha)] * rng.randint(2, 90))
+            elif x < p_run + 0.02:
+                out.append(rng.choice(drop))
+            else:
+                out.append(rng.choice(alpha))
+        docs.append("".join(out[:n]).encode())
+    return docs
+
+
+@pytest.mark.parametrize("seed", range(10))
+def test_grid_kernel_random_proper_tables(seed):
+    """Several words above the shared-memory capacity (12288 bytes) in one batch go through bpe_grid_kernel together; as
+    whole documents (no pre-tokenizer, per-occurrence pipeline) and as words of the slice pipeline's long list."""
+    rng = random.Random(7000 + seed)
+    alpha = list("abcdefgh")[: rng.randint(2, 8)] + (["é", "中"] if seed % 2 else [])
+    js, alpha = rand_bpe_json(rng, n_merges=rng.randint(5, 400), alphabet=alpha, unk="<unk>" if seed % 4 == 0 else None,
+                              dead_merges=0.0, unique_products=True, pretok=[None, "Whitespace"][(seed // 2) % 2])
+    t, o = pair(js)
+    lengths = [12289, 13000, 40000, 3, 150000, 12288, 0, 20000, 65, 70001, 2500]
+    docs = _huge_docs(rng, alpha, lengths)
+    docs.append(b" ".join(_huge_docs(rng, alpha, [15000, 100, 30000, 14000])))      # several huge words in one document
+    got = t.encode_batch(docs)
+    st = t.stats()
+    assert st.model_flags & 1, "the generated table must be recognised as proper"
+    assert st.model_flags & 2, "the huge words must have taken the grid-wide kernel"
+    assert_same(got, o.encode_batch(docs, algo=1, threads=8), f"seed {seed}")
+    t.close()
+
+
+def test_grid_kernel_runs_empty_words_and_malformed_words(monkeypatch):
+    v = {"a": 0, "b": 1, "aa": 2, "aaaa": 3, "ab": 4, "aab": 5, "Ã(": 6}
+    js = json.dumps({"model": {"type": "BPE", "vocab": v, "merges": ["a a", "aa aa", "a b", "aa b"]}}, ensure_ascii=False)
+    t, o = pair(js)
+    docs = [b"a" * 20001, b"a" * 300000, (b"a" * 9 + b"b") * 5000, b"b" + b"a" * 70000 + b"b" * 5, (b"aab" * 5 + b"aaaab") * 3000,
+            "語".encode() * 10000,                          # 30000 bytes, no symbol at all
+            b"a" * 13001 + "語".encode() * 5 + b"a" * 13000, b"ab" * 40000,
+            b"ab" * 7000 + b"\xc3(" + b"ab" * 7000,         # malformed but in bounds: left to the block kernel (sequential re-decode)
+            b"", b"ab"]
+    got = t.encode_batch(docs)
+    assert t.stats().model_flags & 2
+    assert_same(got, o.encode_batch(docs, algo=1, threads=8))
+    # invalid lead byte inside a huge word: still an error with the document index
+    bad = [b"ab" * 9000, b"ab" * 9000 + b"\xff" + b"ab" * 10]
+    with pytest.raises(tz.TokzigError) as e:
+        t.encode_batch(bad)
+    assert e.value.code == tz.ERR_INVALID_UTF8 and e.value.doc == 1
+    t.close()
+    # A/B: the same batch with one block per huge word
+    monkeypatch.setenv("TKZ_NO_GRID", "1")
+    t2 = tz.Tokenizer.from_json(js, device=0)
+    got2 = t2.encode_batch(docs)
+    assert not (t2.stats().model_flags & 2)
+    assert_same(got2, got)
+    t2.close()
+
+
+def test_grid_kernel_on_the_skewed_corpus():
+    """c5 generator (documents 1 B .. 4 MiB with long unbroken words) through the GPT-2-shaped tokenizers: Whitespace
+    (slice pipeline + long list) and ByteLevel JSON (whole documents)."""
+    text, off = corpus.generate("c5", 24 << 20, seed=77)
+    for name in ("gpt2_whitespace", "gpt2_bytelevel"):
+        js = tokenizers_io.tokenizer_json(name)
+        t = tz.Tokenizer.from_json(js, device=0)
+        o = orc.OracleTokenizer.from_json(js)
+        got = t.encode_packed(text, off)
+        assert t.stats().model_flags & 2, name
+        assert_same(got, o.encode_packed(text, off, algo=1, threads=8), name)
+        t.close()
+
+
 def test_windowed_vs_literal_switch(monkeypatch):
     """TKZ_NO_WINDOWED=1 forces the literal round kernel for long words: both schedules must give the oracle's answer."""
     js = tokenizers_io.tokenizer_json("gpt2_bytelevel")

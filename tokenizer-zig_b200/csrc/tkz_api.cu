@@ -18,6 +18,7 @@
 #include "../../include/tokzig_b200.h"
 #include "tkz_bpe.cuh"
 #include "tkz_bpe_block.cuh"
+#include "tkz_bpe_grid.cuh"
 #include "tkz_common.cuh"
 #include "tkz_decode.cuh"
 #include "tkz_dedup.cuh"
@@ -73,6 +74,10 @@ struct tkz_ctx {
     bool use_dedup = true;                // TKZ_NO_DEDUP=1: per-occurrence pipeline even with a pre-tokenizer (A/B switch of the parity tests)
     bool use_slices = true;               // slice pipeline (tkz_slices.cuh); TKZ_SLICES=0 selects the older multi-pass dedup pipeline
     DevBuf a_wtable, a_lscratch, a_ent, a_tile_ent_off, a_long_slice, a_region_ctr;
+    DevBuf a_huge_w, a_huge_base, a_huge_done, a_grid_state, a_grid_words;   // bpe_grid_kernel (tkz_bpe_grid.cuh)
+    bool use_grid = true;                 // TKZ_NO_GRID=1: huge words stay with one block each (A/B switch of the parity tests)
+    bool grid_used = false;               // the last encode ran bpe_grid_kernel
+    int grid_blocks = 0;                  // co-resident blocks of bpe_grid_kernel (0: cooperative launch not available)
     uint64_t tw_uniq_hist = 0;            // most unique words seen in one batch: sizes the next batch's word table
     uint64_t tw_upool_hist = 0;           // most token records used by one batch
     double tw_words_per_byte = 0.0;       // densest batch so far: sizes the entry list
@@ -255,6 +260,13 @@ extern "C" int tkz_ctx_create(int device, void* stream, uint64_t arena_hint_byte
     (void)arena_hint_bytes;
     if (const char* e = getenv("TKZ_NO_DEDUP")) ctx->use_dedup = !(e[0] == '1');     // A/B switch for the parity tests
     if (const char* e = getenv("TKZ_SLICES")) ctx->use_slices = !(e[0] == '0');
+    if (const char* e = getenv("TKZ_NO_GRID")) ctx->use_grid = !(e[0] == '1');
+    {
+        int coop = 0, per_sm = 0;
+        cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device);
+        if (coop && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bpe_grid_kernel, BG_NT, 0) == cudaSuccess && per_sm > 0)
+            ctx->grid_blocks = ctx->sm_count * per_sm;
+    }
     if (const char* e = getenv("TKZ_CHUNK_BYTES")) { const long long v = atoll(e); if (v > 0) ctx->chunk_bytes = (uint64_t)v; }
     cudaStreamCreateWithFlags(&ctx->s_h2d, cudaStreamNonBlocking);
     cudaStreamCreateWithFlags(&ctx->s_d2h, cudaStreamNonBlocking);
@@ -283,6 +295,7 @@ extern "C" void tkz_ctx_destroy(tkz_ctx* ctx) {
                       &ctx->a_tile_words, &ctx->a_tile_nwords, &ctx->a_tile_ntok, &ctx->a_doc_word_ref, &ctx->a_doc_tok_local,
                       &ctx->a_doc_tok_start, &ctx->a_doc_real, &ctx->a_upool, &ctx->a_tile_doc_lo, &ctx->a_g_first, &ctx->a_g_win, &ctx->a_g_flag, &ctx->a_big,
                       &ctx->a_wtable, &ctx->a_lscratch, &ctx->a_ent, &ctx->a_tile_ent_off, &ctx->a_long_slice, &ctx->a_region_ctr,
+                      &ctx->a_huge_w, &ctx->a_huge_base, &ctx->a_huge_done, &ctx->a_grid_state, &ctx->a_grid_words,
                       &ctx->t_dec_bytes, &ctx->t_dec_off, &ctx->t_dec_special, &ctx->a_dec_ids, &ctx->a_dec_seq_off, &ctx->a_dec_len, &ctx->a_dec_raw,
                       &ctx->a_dec_out, &ctx->a_dec_olen, &ctx->a_dec_boff};
     for (DevBuf* b : bufs) release(*b);
@@ -302,7 +315,7 @@ extern "C" const char* tkz_last_error(tkz_ctx* ctx) { return ctx ? ctx->err.c_st
 extern "C" int tkz_ctx_get_stats(tkz_ctx* ctx, tkz_stats* out) {
     if (!ctx || !out) return TKZ_ERR_INVALID_ARG;
     *out = ctx->stats; out->arena_bytes = ctx->arena_bytes;
-    out->model_flags = (ctx->has_model && ctx->dm.windowed_ok) ? 1u : 0u;
+    out->model_flags = ((ctx->has_model && ctx->dm.windowed_ok) ? 1u : 0u) | (ctx->grid_used ? 2u : 0u);
     return TKZ_OK;
 }
 
@@ -394,6 +407,8 @@ extern "C" int tkz_model_upload(tkz_ctx* ctx, const tkz_model_desc* d) {
             std::sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) { return mtab[x].rank < mtab[y].rank; });
             bool proper = true;
             for (size_t i = 1; i < order.size() && proper; i++) if (mtab[order[i]].rank == mtab[order[i - 1]].rank) proper = false;
+            // (ranks / ids in the reserved range of TKZ_BOUNDARY, TKZ_DIRTY, BG_PENDING keep the literal kernel)
+            for (uint32_t sl : order) if (mtab[sl].rank >= TKZ_BOUNDARY || mtab[sl].new_id >= BG_PENDING) proper = false;
             std::unordered_map<uint32_t, uint32_t> max_prod, min_cons, nsym;    // per symbol id
             for (uint32_t sl : order) {
                 const MergeEnt& e = mtab[sl];
@@ -500,6 +515,55 @@ int launch_bpe(tkz_ctx* ctx, const DevModel& m, const uint8_t* d_text, const uin
         b.min_len = BB_TINY_MAX + 1; b.max_len = BB_SMALL_MAX; b.work_counter = (unsigned int*)(ctrl + 11);
         g = cls[0]; gc = (uint64_t)ctx->sm_count * 6; if (g > gc) g = gc;
         bpe_block_kernel<256, BB_SMALL_MAX><<<(unsigned)g, 256, BB_SMALL_MAX * 15, st>>>(m, b); launches++;
+    }
+    if (cls[2] && ctx->use_grid && ctx->grid_blocks > 0) {
+        // words above the shared-memory capacity: all of them together on one cooperative grid (tkz_bpe_grid.cuh); a word
+        // it leaves alone (malformed UTF-8) and everything when its state does not fit falls through to the block kernel
+        const uint32_t hcap = (uint32_t)cls[2];
+        unsigned long long* hctrl = (unsigned long long*)ctx->h_ctrl.p;
+        TRY(ensure(ctx, ctx->a_huge_w, ((size_t)hcap + 2) * 4));
+        TRY(ensure(ctx, ctx->a_huge_base, ((size_t)hcap + 2) * 4));
+        TRY(ensure(ctx, ctx->a_huge_done, (size_t)nw + 16));
+        CK(cudaMemsetAsync(ctx->a_huge_done.p, 0, (size_t)nw, st));
+        huge_list_kernel<<<1, 1024, 0, st>>>(word_start, word_end, nw, BB_BIG_CAP + 1, hcap, (uint32_t*)ctx->a_huge_w.p, (uint32_t*)ctx->a_huge_base.p, ctrl + 18);
+        launches++;
+        TRY(readback(ctx, hctrl + 40, ctrl + 18, 16));
+        CK(cudaStreamSynchronize(st));
+        const uint64_t n_huge = hctrl[40], M = hctrl[41];
+        auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+        const size_t per4 = al((size_t)M * 4 + 16), per2 = al((size_t)M * 2 + 16);
+        const size_t state_bytes = 11 * per4 + 2 * per2;                    // (id, s, e, rk, wid) x 2 + hn, win x 2
+        const size_t words_bytes = 4 * al(((size_t)n_huge + 2) * 4) + al((size_t)n_huge + 16) + al((size_t)ctx->grid_blocks * 8 + 64) + 256;
+        bool ok = n_huge > 0 && n_huge <= hcap && M < 0xFFFFF000ull;
+        if (ok && (ensure(ctx, ctx->a_grid_state, state_bytes) != TKZ_OK || ensure(ctx, ctx->a_grid_words, words_bytes) != TKZ_OK)) {
+            ok = false; ctx->err.clear(); cudaGetLastError();                // no room for the grid state: one block per word
+        }
+        if (ok) {
+            GridBpeArgs ga{};
+            ga.text = d_text; ga.word_start = word_start; ga.word_end = word_end;
+            ga.hw = (const uint32_t*)ctx->a_huge_w.p; ga.hbase = (const uint32_t*)ctx->a_huge_base.p; ga.n_huge = (uint32_t)n_huge; ga.M = (uint32_t)M;
+            uint8_t* p = (uint8_t*)ctx->a_grid_state.p;
+            auto take = [&](size_t bytes) { uint8_t* r = p; p += bytes; return r; };
+            for (int k = 0; k < 2; k++) {
+                ga.id[k] = (uint32_t*)take(per4); ga.s[k] = (uint32_t*)take(per4); ga.e[k] = (uint32_t*)take(per4);
+                ga.rk[k] = (uint32_t*)take(per4); ga.wid[k] = (uint32_t*)take(per4); ga.win[k] = (uint16_t*)take(per2);
+            }
+            ga.hn = (uint32_t*)take(per4);
+            p = (uint8_t*)ctx->a_grid_words.p;
+            const size_t pw = al(((size_t)n_huge + 2) * 4);
+            ga.wmin[0] = (uint32_t*)take(pw); ga.wmin[1] = (uint32_t*)take(pw); ga.wstart = (uint32_t*)take(pw); take(pw);
+            ga.wbad = take(al((size_t)n_huge + 16));
+            ga.blk = (uint32_t*)take(al((size_t)ctx->grid_blocks * 8 + 64));
+            ga.gs = (uint32_t*)take(256);
+            ga.pool_id = (uint32_t*)ctx->a_pool_id.p; ga.pool_s = (uint32_t*)ctx->a_pool_s.p; ga.pool_e = (uint32_t*)ctx->a_pool_e.p;
+            ga.word_ntok = word_ntok; ga.done = (uint8_t*)ctx->a_huge_done.p;
+            DevModel mm = m;
+            void* args[] = {(void*)&mm, (void*)&ga};
+            CK(cudaLaunchCooperativeKernel((void*)bpe_grid_kernel, dim3((unsigned)ctx->grid_blocks), dim3(BG_NT), args, 0, st));
+            launches++;
+            b.skip = (const uint8_t*)ctx->a_huge_done.p;
+            ctx->grid_used = true;
+        }
     }
     if (cls[1]) {
         b.min_len = BB_SMALL_MAX + 1; b.max_len = 0xFFFFFFFFu; b.work_counter = (unsigned int*)(ctrl + 12);
@@ -849,6 +913,7 @@ int encode_device_impl(tkz_ctx* ctx, const uint8_t* d_text, const uint64_t* d_do
     memset(out, 0, sizeof *out);
     out->err_doc = -1;
     if (!ctx->has_model) { ctx->err = "no model uploaded"; return TKZ_ERR_INVALID_ARG; }
+    ctx->grid_used = false;
     if (N >= 0xFFFFF000ull) { ctx->err = "batch text must be < 4 GiB (u32 offsets, types.zig:4-6): split the batch"; return TKZ_ERR_INVALID_ARG; }
     if (n_docs >= 0xFFFFFFF0ull) { ctx->err = "too many documents in one batch"; return TKZ_ERR_INVALID_ARG; }
     CK(cudaSetDevice(ctx->device));

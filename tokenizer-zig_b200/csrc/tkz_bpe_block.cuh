@@ -40,6 +40,7 @@ struct BlockBpeArgs {
     unsigned int* work_counter;
     unsigned long long* errw;
     int sentinel_errors;
+    const uint8_t* skip;                  // optional, per word: already tokenized by bpe_grid_kernel (tkz_bpe_grid.cuh)
 };
 
 template <int NT>
@@ -88,6 +89,7 @@ __global__ void __launch_bounds__(NT) bpe_block_kernel(DevModel m, BlockBpeArgs 
         if (w >= a.n_words) break;
         const uint32_t ws = a.word_start[w], len = a.word_end[w] - ws;
         if (len < a.min_len || len > a.max_len) continue;
+        if (a.skip && a.skip[w]) continue;
         const uint8_t* __restrict__ wt = a.text + ws;
         const bool in_smem = len <= (uint32_t)CAP;
         uint32_t* ids = in_smem ? s_id : a.pool_id + ws;
