@@ -533,7 +533,7 @@ int launch_bpe(tkz_ctx* ctx, const DevModel& m, const uint8_t* d_text, const uin
         auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
         const size_t per4 = al((size_t)M * 4 + 16), per2 = al((size_t)M * 2 + 16);
         const size_t state_bytes = 11 * per4 + 2 * per2;                    // (id, s, e, rk, wid) x 2 + hn, win x 2
-        const size_t words_bytes = 4 * al(((size_t)n_huge + 2) * 4) + al((size_t)n_huge + 16) + al((size_t)ctx->grid_blocks * 8 + 64) + 256;
+        const size_t words_bytes = 4 * al(((size_t)n_huge + 2) * 4) + al((size_t)n_huge + 16) + al((size_t)ctx->grid_blocks * 33 * 4 + 64) + 256 + 4096;
         bool ok = n_huge > 0 && n_huge <= hcap && M < 0xFFFFF000ull;
         if (ok && (ensure(ctx, ctx->a_grid_state, state_bytes) != TKZ_OK || ensure(ctx, ctx->a_grid_words, words_bytes) != TKZ_OK)) {
             ok = false; ctx->err.clear(); cudaGetLastError();                // no room for the grid state: one block per word
@@ -553,14 +553,29 @@ int launch_bpe(tkz_ctx* ctx, const DevModel& m, const uint8_t* d_text, const uin
             const size_t pw = al(((size_t)n_huge + 2) * 4);
             ga.wmin[0] = (uint32_t*)take(pw); ga.wmin[1] = (uint32_t*)take(pw); ga.wstart = (uint32_t*)take(pw); take(pw);
             ga.wbad = take(al((size_t)n_huge + 16));
-            ga.blk = (uint32_t*)take(al((size_t)ctx->grid_blocks * 8 + 64));
+            ga.blk = (uint32_t*)take(al((size_t)ctx->grid_blocks * 33 * 4 + 64));
             ga.gs = (uint32_t*)take(256);
+            ga.dbg = (uint32_t*)take(4096);
             ga.pool_id = (uint32_t*)ctx->a_pool_id.p; ga.pool_s = (uint32_t*)ctx->a_pool_s.p; ga.pool_e = (uint32_t*)ctx->a_pool_e.p;
             ga.word_ntok = word_ntok; ga.done = (uint8_t*)ctx->a_huge_done.p;
             DevModel mm = m;
             void* args[] = {(void*)&mm, (void*)&ga};
             CK(cudaLaunchCooperativeKernel((void*)bpe_grid_kernel, dim3((unsigned)ctx->grid_blocks), dim3(BG_NT), args, 0, st));
             launches++;
+            if (getenv("TKZ_GRID_DEBUG")) {
+                uint32_t gsh[16];
+                cudaStreamSynchronize(st);
+                cudaMemcpy(gsh, ga.gs, sizeof gsh, cudaMemcpyDeviceToHost);
+                const unsigned long long* g64 = (const unsigned long long*)(gsh + 8);
+                fprintf(stderr, "[tkz grid] words %u bytes %u symbols %u steps %u run-scans %u  ms: heads %.2f compact+ranks %.2f\n", ga.n_huge, ga.M,
+                        gsh[7], gsh[5], gsh[6], g64[1] * 1e-6, g64[2] * 1e-6);
+                if (getenv("TKZ_GRID_DEBUG")[0] == '2') {
+                    uint32_t d[1024];
+                    cudaMemcpy(d, ga.dbg, sizeof d, cudaMemcpyDeviceToHost);
+                    for (uint32_t k = 0; k < gsh[5] && k < 256; k++)
+                        fprintf(stderr, "[tkz grid]   step %3u  n %10u  heads %9u  H %7.3f ms  K %7.3f ms\n", k, d[4 * k], d[4 * k + 1], d[4 * k + 2] * 1e-6, d[4 * k + 3] * 1e-6);
+                }
+            }
             b.skip = (const uint8_t*)ctx->a_huge_done.p;
             ctx->grid_used = true;
         }

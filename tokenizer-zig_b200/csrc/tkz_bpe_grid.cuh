@@ -45,7 +45,8 @@ struct GridBpeArgs {
     uint32_t* wmin[2];                    // per huge word: smallest pair rank (double-buffered by step parity)
     uint32_t* wstart;                     // per huge word: first symbol in the final array (n_huge + 1)
     uint8_t* wbad;                        // per huge word: malformed UTF-8 seen
-    uint32_t* blk;                        // per block: [0, G) head counts, [G, 2G) last run boundary
+    uint32_t* blk;                        // [0, 32 G) heads per warp part (init: [0, G) symbols per block), [32 G, 33 G) last run boundary per block
+    uint32_t* dbg;                        // TKZ_GRID_DEBUG: per step (first 256) n, heads, ns in H, ns in K
     uint32_t* gs;                         // scalars: [1 + parity] a mergeable pair exists, [3 + parity] run scan needed
     uint32_t* pool_id; uint32_t* pool_s; uint32_t* pool_e;      // results, indexed by the word's byte position
     uint32_t* word_ntok; uint8_t* done;   // per word of the list
@@ -100,11 +101,12 @@ __global__ void __launch_bounds__(BG_NT, 1) bpe_grid_kernel(const __grid_constan
     const uint32_t gt = b * BG_NT + t, gstride = G * BG_NT;
     const uint32_t FULL = 0xFFFFFFFFu;
     uint32_t phase = 0;
-    // contiguous range of block b over n elements, a multiple of BG_NT long
+    // contiguous range of block b over n elements, a multiple of 4 * BG_NT long (so that a warp's 1/32 of it is a multiple of 128)
     auto range = [&](uint32_t n, uint32_t& lo, uint32_t& hi) {
-        const unsigned long long per = ((((unsigned long long)n + G - 1) / G + BG_NT - 1) / BG_NT) * BG_NT;
+        const unsigned long long per = ((((unsigned long long)n + G - 1) / G + 4 * BG_NT - 1) / (4 * BG_NT)) * (4 * BG_NT);
         const unsigned long long l = per * b, h = l + per;
         lo = (uint32_t)(l < n ? l : n); hi = (uint32_t)(h < n ? h : n);
+        return per;
     };
 
     // ---------------- per-word state; initial symbols at their byte positions in buffer 0 (bpe.zig:185-211)
@@ -182,80 +184,108 @@ __global__ void __launch_bounds__(BG_NT, 1) bpe_grid_kernel(const __grid_constan
     uint32_t cur = 1;
     grid.sync();
 
-    // ---------------- merge steps
-    for (uint32_t step = 0;; step++) {
-        const uint32_t par = step & 1u;
-        uint32_t* const ids = a.id[cur]; uint32_t* const rk = a.rk[cur]; uint32_t* const wd = a.wid[cur]; uint16_t* const win = a.win[cur];
-        range(n, lo, hi);
-        // C. ranks of the pairs the last step touched; smallest rank per word; does any word still have a mergeable pair?
-        {
-            bool any = false;
-            for (uint32_t c0 = lo; c0 < hi; c0 += BG_NT) {
-                const uint32_t i = c0 + t;
-                uint32_t r = TKZ_NONE, w = TKZ_NONE;
-                if (i < hi) {
-                    r = rk[i]; w = wd[i];
-                    if (r == TKZ_DIRTY) {
-                        if (i + 1 < n && wd[i + 1] == w) {
-                            r = TKZ_NONE;
-                            if (!a.wbad[w]) { uint32_t nid, wv = 0; r = merge_lookup_win(m, ids[i], ids[i + 1], &nid, &wv); win[i] = (uint16_t)wv; }
-                        } else r = TKZ_BOUNDARY;
-                        rk[i] = r;
-                    }
-                }
-                const bool finite = r < TKZ_BOUNDARY;
-                const uint32_t fm = __ballot_sync(FULL, finite);
-                if (fm) {
-                    // one atomic per warp when all its mergeable pairs belong to the same word (the usual case)
-                    const uint32_t w0 = __shfl_sync(FULL, w, __ffs(fm) - 1);
-                    if (__all_sync(FULL, !finite || w == w0)) {
-                        uint32_t mn = finite ? r : TKZ_NONE;
-                        for (int d = 16; d > 0; d >>= 1) { const uint32_t y = __shfl_xor_sync(FULL, mn, d); mn = y < mn ? y : mn; }
-                        if ((t & 31) == 0) atomicMin(&a.wmin[par][w0], mn);
-                    } else if (finite) atomicMin(&a.wmin[par][w], r);
-                    any = true;
-                }
+    // ---------------- ranks + windows of all pairs, smallest rank per word (once; afterwards pass K keeps them current)
+    range(n, lo, hi);
+    {
+        uint32_t* const ids = a.id[1]; uint32_t* const rk = a.rk[1]; uint32_t* const wd = a.wid[1]; uint16_t* const win = a.win[1];
+        bool any = false;
+        for (uint32_t c0 = lo; c0 < hi; c0 += BG_NT) {
+            const uint32_t i = c0 + t;
+            uint32_t r = TKZ_NONE, w = TKZ_NONE;
+            if (i < hi) {
+                w = wd[i];
+                if (i + 1 < n && wd[i + 1] == w) {
+                    if (!a.wbad[w]) { uint32_t nid, wv = 0; r = merge_lookup_win(m, ids[i], ids[i + 1], &nid, &wv); win[i] = (uint16_t)wv; }
+                } else r = TKZ_BOUNDARY;
+                rk[i] = r;
             }
-            if (__syncthreads_or(any ? 1 : 0) && t == 0) *(volatile uint32_t*)(a.gs + 1 + par) = 1u;
+            const bool finite = r < TKZ_BOUNDARY;
+            const uint32_t fm = __ballot_sync(FULL, finite);
+            if (fm) {
+                // one atomic per warp when all its mergeable pairs belong to the same word (the usual case)
+                const uint32_t w0 = __shfl_sync(FULL, w, __ffs(fm) - 1);
+                if (__all_sync(FULL, !finite || w == w0)) {
+                    uint32_t mn = finite ? r : TKZ_NONE;
+                    for (int d = 16; d > 0; d >>= 1) { const uint32_t y = __shfl_xor_sync(FULL, mn, d); mn = y < mn ? y : mn; }
+                    if ((t & 31) == 0) atomicMin(&a.wmin[0][w0], mn);
+                } else if (finite) atomicMin(&a.wmin[0][w], r);
+                any = true;
+            }
         }
-        grid.sync();
+        if (__syncthreads_or(any ? 1 : 0) && t == 0) *(volatile uint32_t*)(a.gs + 1) = 1u;
+    }
+    grid.sync();
+
+    // ---------------- merge steps: two passes (H heads, K compaction + new ranks), each warp streaming its own contiguous
+    // part of the array, four consecutive symbols per lane (16-byte loads), no block barrier inside a pass.
+    // (block 0 keeps counters for TKZ_GRID_DEBUG: gs[5] steps, gs[6] run scans, gs[7] initial symbols, gs[8..] ns in H / K)
+    unsigned long long th = 0, tk = 0, t0 = 0;
+    uint32_t n_scans = 0;
+    auto now = [] { unsigned long long x; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(x)); return x; };
+    if (gt == 0) a.gs[7] = n;
+    const uint32_t lane = t & 31, wq = t >> 5;
+    uint32_t* const cnt = a.blk;                                 // heads per warp part: G * 32 entries; then G run boundaries
+    uint32_t step = 0;
+    for (;; step++) {
+        const uint32_t par = step & 1u;
         if (*(volatile uint32_t*)(a.gs + 1 + par) == 0u) break;                   // bpe.zig:232-234 for every word
+        if (gt == 0) t0 = now();
+        uint32_t* const ids = a.id[cur]; uint32_t* const rk = a.rk[cur]; uint32_t* const wd = a.wid[cur]; uint16_t* const win = a.win[cur];
+        const unsigned long long per = range(n, lo, hi);
+        const uint32_t per_w = (uint32_t)(per / 32);                              // a multiple of 128
+        const unsigned long long wl64 = per * b + (unsigned long long)per_w * wq;
+        const uint32_t wlo = (uint32_t)(wl64 < n ? wl64 : n), whi = (uint32_t)(wl64 + per_w < n ? wl64 + per_w : n);
 
         // H. heads of this step and their new ids
         {
+            for (uint32_t w = gt; w < a.n_huge; w += gstride) a.wmin[par ^ 1u][w] = TKZ_NONE;
+            if (gt == 0) { a.gs[1 + (par ^ 1u)] = 0; a.gs[3 + (par ^ 1u)] = 0; }
             uint32_t heads = 0; bool pend = false;
-            for (uint32_t c0 = lo; c0 < hi; c0 += BG_NT) {
-                const uint32_t i = c0 + t;
-                if (i >= hi) continue;
-                uint32_t hv = TKZ_NONE;
-                const uint32_t r = rk[i];
-                if (r < TKZ_BOUNDARY) {
-                    const uint32_t x = ids[i], y = ids[i + 1];
-                    bool head = false;
-                    if (x != y) {
-                        const uint32_t wv = win[i], wl = wv & 0xFFu, wr = wv >> 8;
-                        const uint32_t wlo = i > wl ? i - wl : 0;
-                        uint32_t whi = i + wr; if (whi > n - 2) whi = n - 2;
-                        head = true;
-                        for (uint32_t j = i; j > wlo && head;) { --j; const uint32_t rj = rk[j]; if (rj == TKZ_BOUNDARY) break; head = rj >= r; }
-                        for (uint32_t j = i + 1; j <= whi && head; j++) { const uint32_t rj = rk[j]; if (rj == TKZ_BOUNDARY) break; head = rj >= r; }
-                    } else if (r == a.wmin[par][wd[i]]) {
-                        // the reference round of this word: runs of x pair up from their start
-                        uint32_t j = i, k = 0;
-                        while (k < BG_WALK && j > 0 && rk[j - 1] != TKZ_BOUNDARY && ids[j - 1] == x) { j--; k++; }
-                        if (k == BG_WALK && j > 0 && rk[j - 1] != TKZ_BOUNDARY && ids[j - 1] == x) { hv = BG_PENDING; pend = true; }
-                        else head = ((i - j) & 1u) == 0;
+            for (uint32_t c0 = wlo; c0 < whi; c0 += 128) {
+                const uint32_t i0 = c0 + 4 * lane;
+                uint32_t rr[4] = {TKZ_NONE, TKZ_NONE, TKZ_NONE, TKZ_NONE};
+                if (i0 < whi) { const uint4 v = *reinterpret_cast<const uint4*>(rk + i0); rr[0] = v.x; rr[1] = v.y; rr[2] = v.z; rr[3] = v.w; }
+                bool fin = false;
+#pragma unroll
+                for (int k = 0; k < 4; k++) { if (i0 + k >= n) rr[k] = TKZ_NONE; fin |= rr[k] < TKZ_BOUNDARY; }
+                uint32_t hv[4] = {TKZ_NONE, TKZ_NONE, TKZ_NONE, TKZ_NONE};
+                if (fin) {
+                    uint32_t idv[5];
+                    { const uint4 v = *reinterpret_cast<const uint4*>(ids + i0); idv[0] = v.x; idv[1] = v.y; idv[2] = v.z; idv[3] = v.w; }
+                    idv[4] = i0 + 4 < n ? ids[i0 + 4] : TKZ_NONE;
+                    const uint2 w2 = *reinterpret_cast<const uint2*>(win + i0);
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        const uint32_t r = rr[k];
+                        if (r >= TKZ_BOUNDARY) continue;
+                        const uint32_t i = i0 + k, x = idv[k], y = idv[k + 1];
+                        bool head = false;
+                        if (x != y) {
+                            const uint32_t wv = ((k < 2 ? w2.x : w2.y) >> ((k & 1) * 16)) & 0xFFFFu, wl = wv & 0xFFu, wr = wv >> 8;
+                            const uint32_t jlo = i > wl ? i - wl : 0;
+                            uint32_t jhi = i + wr; if (jhi > n - 2) jhi = n - 2;
+                            head = true;
+                            for (uint32_t j = i; j > jlo && head;) { --j; const uint32_t rj = rk[j]; if (rj == TKZ_BOUNDARY) break; head = rj >= r; }
+                            for (uint32_t j = i + 1; j <= jhi && head; j++) { const uint32_t rj = rk[j]; if (rj == TKZ_BOUNDARY) break; head = rj >= r; }
+                        } else if (r == a.wmin[par][wd[i]]) {
+                            // the reference round of this word: runs of x pair up from their start
+                            uint32_t j = i, c = 0;
+                            while (c < BG_WALK && j > 0 && rk[j - 1] != TKZ_BOUNDARY && ids[j - 1] == x) { j--; c++; }
+                            if (c == BG_WALK && j > 0 && rk[j - 1] != TKZ_BOUNDARY && ids[j - 1] == x) { hv[k] = BG_PENDING; pend = true; }
+                            else head = ((i - j) & 1u) == 0;
+                        }
+                        if (head) { uint32_t nid = 0; merge_rank_lookup(m, x, y, &nid); hv[k] = nid; heads++; }
                     }
-                    if (head) { uint32_t nid = 0; merge_rank_lookup(m, x, y, &nid); hv = nid; heads++; }
                 }
-                a.hn[i] = hv;
+                if (i0 < whi) *reinterpret_cast<uint4*>(a.hn + i0) = make_uint4(hv[0], hv[1], hv[2], hv[3]);
             }
-            const uint32_t tot = bg_block_sum(heads, red);
-            if (t == 0) a.blk[b] = tot;
+            for (int d = 16; d > 0; d >>= 1) heads += __shfl_xor_sync(FULL, heads, d);
+            if (lane == 0) cnt[b * 32 + wq] = heads;
             if (__syncthreads_or(pend ? 1 : 0) && t == 0) *(volatile uint32_t*)(a.gs + 3 + par) = 1u;
         }
         grid.sync();
         if (*(volatile uint32_t*)(a.gs + 3 + par) != 0u) {
+            n_scans++;
             // long equal-symbol runs: start of the run of every symbol = max-scan over the run boundaries before it
             {
                 uint32_t last = 0;
@@ -267,12 +297,11 @@ __global__ void __launch_bounds__(BG_NT, 1) bpe_grid_kernel(const __grid_constan
                 __syncthreads();
                 if ((t & 31) == 0) red[t >> 5] = last;
                 __syncthreads();
-                if (t == 0) { uint32_t mx = 0; for (int w = 0; w < BG_NT / 32; w++) mx = red[w] > mx ? red[w] : mx; a.blk[G + b] = mx; }
+                if (t == 0) { uint32_t mx = 0; for (int w = 0; w < BG_NT / 32; w++) mx = red[w] > mx ? red[w] : mx; cnt[G * 32 + b] = mx; }
             }
             grid.sync();
             {
-                uint32_t carry = bg_prefix_max(a.blk + G, b, red);
-                uint32_t extra = 0;
+                uint32_t carry = bg_prefix_max(cnt + G * 32, b, red);
                 for (uint32_t c0 = lo; c0 < hi; c0 += BG_NT) {
                     const uint32_t i = c0 + t;
                     uint32_t v = 0;
@@ -280,7 +309,10 @@ __global__ void __launch_bounds__(BG_NT, 1) bpe_grid_kernel(const __grid_constan
                     const uint32_t rs = block_incl_maxscan<BG_NT>(v, red, carry);
                     if (i < hi && a.hn[i] == BG_PENDING) {
                         uint32_t hv = TKZ_NONE;
-                        if (((i - rs) & 1u) == 0) { uint32_t nid = 0; merge_rank_lookup(m, ids[i], ids[i + 1], &nid); hv = nid; extra++; }
+                        if (((i - rs) & 1u) == 0) {
+                            uint32_t nid = 0; merge_rank_lookup(m, ids[i], ids[i + 1], &nid); hv = nid;
+                            atomicAdd(&cnt[b * 32 + (uint32_t)((i - per * b) / per_w)], 1u);
+                        }
                         a.hn[i] = hv;
                     }
                     __syncthreads();
@@ -288,46 +320,115 @@ __global__ void __launch_bounds__(BG_NT, 1) bpe_grid_kernel(const __grid_constan
                     __syncthreads();
                     carry = s_x;
                 }
-                const uint32_t tot = bg_block_sum(extra, red);
-                if (t == 0 && tot) a.blk[b] += tot;
             }
             grid.sync();
         }
+        unsigned long long dth = 0;
+        if (gt == 0) { const unsigned long long x = now(); dth = x - t0; th += dth; t0 = x; }
 
-        // K. compaction into the other buffer: symbol i moves to i - (heads before i - 1)
+        // K. compaction into the other buffer (symbol i moves to i - #heads before i - 1) + ranks of the pairs a merge touched
         {
             const uint32_t nxt = cur ^ 1u;
-            for (uint32_t w = gt; w < a.n_huge; w += gstride) a.wmin[par ^ 1u][w] = TKZ_NONE;
-            if (gt == 0) { a.gs[1 + (par ^ 1u)] = 0; a.gs[3 + (par ^ 1u)] = 0; }
             uint32_t before, total;
-            bg_prefix_total(a.blk, G, b, red, before, total);
-            uint32_t run = before;
-            for (uint32_t c0 = lo; c0 < hi; c0 += BG_NT, phase ^= 1u) {
-                const uint32_t i = c0 + t;
-                uint32_t h = TKZ_NONE; bool pv = false, nx = false;
-                if (i < hi) {
-                    h = a.hn[i];
-                    pv = i > 0 && a.hn[i - 1] != TKZ_NONE;
-                    nx = i + 1 < n && a.hn[i + 1] != TKZ_NONE;
-                }
-                const bool hd = h != TKZ_NONE;
-                uint32_t tot;
-                const uint32_t ex = block_excl_scan32<BG_NT / 32>(hd ? 1u : 0u, sc, phase, &tot);
-                if (i < hi && !pv) {
-                    const uint32_t q = i - (run + ex);
-                    a.id[nxt][q] = hd ? h : ids[i];
-                    a.s[nxt][q] = a.s[cur][i];
-                    a.e[nxt][q] = hd ? a.e[cur][i + 1] : a.e[cur][i];
-                    a.wid[nxt][q] = wd[i];
-                    a.rk[nxt][q] = (hd || nx) ? TKZ_DIRTY : rk[i];
-                    a.win[nxt][q] = win[i];
-                }
-                run += tot;
+            bg_prefix_total(cnt, G * 32, b * 32, red, before, total);
+            {
+                const uint32_t own = __ldcg(cnt + b * 32 + lane);
+                uint32_t inc = own;
+                for (int d = 1; d < 32; d <<= 1) { const uint32_t y = __shfl_up_sync(FULL, inc, d); if (lane >= (uint32_t)d) inc += y; }
+                before += __shfl_sync(FULL, inc - own, wq);
             }
+            uint32_t run = before;
+            uint32_t lmin = TKZ_NONE, lw = TKZ_NONE;                 // smallest new rank seen by this lane, and its word
+            for (uint32_t c0 = wlo; c0 < whi; c0 += 128) {
+                const uint32_t i0 = c0 + 4 * lane;
+                const bool in = i0 < whi;
+                uint32_t hh[6], idv[6], wv[6], sv[4], ev[5], rr[4], wn[4];
+                {
+                    uint4 v = make_uint4(TKZ_NONE, TKZ_NONE, TKZ_NONE, TKZ_NONE);
+                    if (in) v = *reinterpret_cast<const uint4*>(a.hn + i0);
+                    hh[0] = v.x; hh[1] = v.y; hh[2] = v.z; hh[3] = v.w;
+#pragma unroll
+                    for (int k = 0; k < 4; k++) if (i0 + k >= n) hh[k] = TKZ_NONE;
+                }
+                uint32_t hprev = __shfl_up_sync(FULL, hh[3], 1);
+                hh[4] = __shfl_down_sync(FULL, hh[0], 1); hh[5] = __shfl_down_sync(FULL, hh[1], 1);
+                if (lane == 0) hprev = (in && i0 > 0) ? a.hn[i0 - 1] : TKZ_NONE;
+                if (lane == 31) { hh[4] = i0 + 4 < n ? a.hn[i0 + 4] : TKZ_NONE; hh[5] = i0 + 5 < n ? a.hn[i0 + 5] : TKZ_NONE; }
+                uint32_t c = 0;
+#pragma unroll
+                for (int k = 0; k < 4; k++) c += hh[k] != TKZ_NONE;
+                uint32_t inc = c;
+                for (int d = 1; d < 32; d <<= 1) { const uint32_t y = __shfl_up_sync(FULL, inc, d); if (lane >= (uint32_t)d) inc += y; }
+                const uint32_t tot = __shfl_sync(FULL, inc, 31);
+                uint32_t E = run + inc - c;                          // heads at positions < i0
+                run += tot;
+                {
+                    uint4 v = make_uint4(0, 0, 0, 0), u = v, x = v, y = v, z = v; uint2 w2 = make_uint2(0, 0);
+                    if (in) {
+                        v = *reinterpret_cast<const uint4*>(ids + i0); u = *reinterpret_cast<const uint4*>(wd + i0);
+                        x = *reinterpret_cast<const uint4*>(a.s[cur] + i0); y = *reinterpret_cast<const uint4*>(a.e[cur] + i0);
+                        z = *reinterpret_cast<const uint4*>(rk + i0); w2 = *reinterpret_cast<const uint2*>(win + i0);
+                    }
+                    idv[0] = v.x; idv[1] = v.y; idv[2] = v.z; idv[3] = v.w; wv[0] = u.x; wv[1] = u.y; wv[2] = u.z; wv[3] = u.w;
+                    sv[0] = x.x; sv[1] = x.y; sv[2] = x.z; sv[3] = x.w; ev[0] = y.x; ev[1] = y.y; ev[2] = y.z; ev[3] = y.w;
+                    rr[0] = z.x; rr[1] = z.y; rr[2] = z.z; rr[3] = z.w;
+                    wn[0] = w2.x & 0xFFFFu; wn[1] = w2.x >> 16; wn[2] = w2.y & 0xFFFFu; wn[3] = w2.y >> 16;
+                }
+                idv[4] = __shfl_down_sync(FULL, idv[0], 1); idv[5] = __shfl_down_sync(FULL, idv[1], 1);
+                wv[4] = __shfl_down_sync(FULL, wv[0], 1); wv[5] = __shfl_down_sync(FULL, wv[1], 1);
+                ev[4] = __shfl_down_sync(FULL, ev[0], 1);
+                if (lane == 31) {
+                    idv[4] = i0 + 4 < n ? ids[i0 + 4] : TKZ_NONE; idv[5] = i0 + 5 < n ? ids[i0 + 5] : TKZ_NONE;
+                    wv[4] = i0 + 4 < n ? wd[i0 + 4] : TKZ_NONE; wv[5] = i0 + 5 < n ? wd[i0 + 5] : TKZ_NONE;
+                    ev[4] = i0 + 4 < n ? a.e[cur][i0 + 4] : 0u;
+                }
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const uint32_t i = i0 + k;
+                    const bool hd = hh[k] != TKZ_NONE;
+                    const bool pv = (k ? hh[k - 1] : hprev) != TKZ_NONE;
+                    if (i < n && in && !pv) {
+                        const uint32_t q = i - E;
+                        const uint32_t nid = hd ? hh[k] : idv[k];
+                        uint32_t r = rr[k], wnew = wn[k];
+                        if (hd || hh[k + 1] != TKZ_NONE) {
+                            // the pair with the next surviving symbol changed: it is i + 2 behind a head, else i + 1 (itself a head?)
+                            const uint32_t nbh = hd ? hh[k + 2] : hh[k + 1], nbid = hd ? idv[k + 2] : idv[k + 1], nbw = hd ? wv[k + 2] : wv[k + 1];
+                            if (i + (hd ? 2u : 1u) >= n || nbw != wv[k]) r = TKZ_BOUNDARY;
+                            else if (a.wbad[wv[k]]) r = TKZ_NONE;
+                            else { uint32_t tmp, w_ = 0; r = merge_lookup_win(m, nid, nbh != TKZ_NONE ? nbh : nbid, &tmp, &w_); wnew = w_; }
+                        }
+                        a.id[nxt][q] = nid; a.s[nxt][q] = sv[k]; a.e[nxt][q] = hd ? ev[k + 1] : ev[k];
+                        a.wid[nxt][q] = wv[k]; a.rk[nxt][q] = r; a.win[nxt][q] = (uint16_t)wnew;
+                        if (r < TKZ_BOUNDARY) {
+                            if (lw == TKZ_NONE) lw = wv[k];
+                            if (wv[k] == lw) lmin = r < lmin ? r : lmin; else atomicMin(&a.wmin[par ^ 1u][wv[k]], r);
+                        }
+                    }
+                    E += hd ? 1u : 0u;
+                }
+            }
+            // smallest rank per word: one atomic per warp when all its lanes met the same word (the usual case)
+            const uint32_t fm = __ballot_sync(FULL, lw != TKZ_NONE);
+            if (fm) {
+                const uint32_t w0 = __shfl_sync(FULL, lw, __ffs(fm) - 1);
+                if (__all_sync(FULL, lw == TKZ_NONE || lw == w0)) {
+                    for (int d = 16; d > 0; d >>= 1) { const uint32_t y = __shfl_xor_sync(FULL, lmin, d); lmin = y < lmin ? y : lmin; }
+                    if (lane == 0) atomicMin(&a.wmin[par ^ 1u][w0], lmin);
+                } else if (lw != TKZ_NONE) atomicMin(&a.wmin[par ^ 1u][lw], lmin);
+            }
+            if (__syncthreads_or(fm ? 1 : 0) && t == 0) *(volatile uint32_t*)(a.gs + 1 + (par ^ 1u)) = 1u;
+            if (gt == 0 && step < 256) { a.dbg[4 * step] = n; a.dbg[4 * step + 1] = total; a.dbg[4 * step + 2] = (uint32_t)dth; }
             n -= total;
             cur = nxt;
         }
         grid.sync();
+        if (gt == 0) { const unsigned long long d = now() - t0; tk += d; if (step < 256) a.dbg[4 * step + 3] = (uint32_t)d; }
+    }
+    if (gt == 0) {
+        a.gs[5] = step; a.gs[6] = n_scans;
+        unsigned long long* g64 = reinterpret_cast<unsigned long long*>(a.gs + 8);
+        g64[0] = 0; g64[1] = th; g64[2] = tk;
     }
 
     // ---------------- tokens (bpe.zig:256-260): first symbol of every word in the final array, then the copy to the pool
