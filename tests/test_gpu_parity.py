@@ -492,6 +492,34 @@ def test_grid_kernel_runs_empty_words_and_malformed_words(monkeypatch):
     t2.close()
 
 
+def test_grid_kernel_sparse_phase_falls_back_for_a_long_late_run():
+    """(a, a) has the highest rank: its runs wait until every other pair of the word is done, i.e. until the kernel is in its
+    sparse in-place phase; a run longer than the sparse walk limit must send it back to the dense steps (run scan)."""
+    rng = random.Random(99)
+    toks = list("bcdefgh")
+    vocab = {c: i for i, c in enumerate("abcdefgh")}
+    merges = []
+    while len(merges) < 150:
+        x, y = rng.choice(toks), rng.choice(toks)
+        if x + y in vocab or len(x + y) > 12:
+            continue
+        vocab[x + y] = len(vocab)
+        toks.append(x + y)
+        merges.append(f"{x} {y}")
+    vocab["aa"] = len(vocab)
+    vocab["aaaa"] = len(vocab)
+    merges += ["a a", "aa aa"]
+    js = json.dumps({"model": {"type": "BPE", "vocab": vocab, "merges": merges}})
+    t, o = pair(js)
+    rnd = lambda n: "".join(rng.choice("bcdefgh") for _ in range(n))
+    docs = [(rnd(60000) + "a" * 3001 + rnd(9000) + "a" * 700 + rnd(50) + "a" * 5000).encode(), (rnd(20000) + "a" * 40 + rnd(100)).encode(),
+            ("a" * 2100 + rnd(30000)).encode()]
+    got = t.encode_batch(docs)
+    assert t.stats().model_flags & 3 == 3
+    assert_same(got, o.encode_batch(docs, algo=1, threads=8))
+    t.close()
+
+
 def test_grid_kernel_on_the_skewed_corpus():
     """c5 generator (documents 1 B .. 4 MiB with long unbroken words) through the GPT-2-shaped tokenizers: Whitespace
     (slice pipeline + long list) and ByteLevel JSON (whole documents)."""

@@ -563,12 +563,12 @@ int launch_bpe(tkz_ctx* ctx, const DevModel& m, const uint8_t* d_text, const uin
             CK(cudaLaunchCooperativeKernel((void*)bpe_grid_kernel, dim3((unsigned)ctx->grid_blocks), dim3(BG_NT), args, 0, st));
             launches++;
             if (getenv("TKZ_GRID_DEBUG")) {
-                uint32_t gsh[16];
+                uint32_t gsh[32];
                 cudaStreamSynchronize(st);
                 cudaMemcpy(gsh, ga.gs, sizeof gsh, cudaMemcpyDeviceToHost);
                 const unsigned long long* g64 = (const unsigned long long*)(gsh + 8);
-                fprintf(stderr, "[tkz grid] words %u bytes %u symbols %u steps %u run-scans %u  ms: heads %.2f compact+ranks %.2f\n", ga.n_huge, ga.M,
-                        gsh[7], gsh[5], gsh[6], g64[1] * 1e-6, g64[2] * 1e-6);
+                fprintf(stderr, "[tkz grid] words %u bytes %u symbols %u dense steps %u run-scans %u sparse steps %u (%u phases)  ms: heads %.2f compact+ranks %.2f sparse %.2f\n", ga.n_huge, ga.M,
+                        gsh[7], gsh[5], gsh[6], gsh[20], gsh[21], g64[1] * 1e-6, g64[2] * 1e-6, g64[0] * 1e-6);
                 if (getenv("TKZ_GRID_DEBUG")[0] == '2') {
                     uint32_t d[1024];
                     cudaMemcpy(d, ga.dbg, sizeof d, cudaMemcpyDeviceToHost);

@@ -32,6 +32,7 @@ namespace cg = cooperative_groups;
 #define TKZ_BOUNDARY 0xFFFFFFFDu          // cached "rank" of the position behind a word's last symbol
 constexpr int BG_NT = 1024;
 constexpr uint32_t BG_WALK = 32;          // equal-symbol runs up to this length find their start by walking left
+constexpr uint32_t BG_SPARSE_WALK = 1024;  // same in the sparse phase (walks skip dead symbols); longer runs go back to the dense steps
 constexpr uint32_t BG_PENDING = 0xFFFFFFFEu;   // head mark of an (A, A) pair that waits for the run scan
 
 struct GridBpeArgs {
@@ -111,7 +112,7 @@ __global__ void __launch_bounds__(BG_NT, 1) bpe_grid_kernel(const __grid_constan
 
     // ---------------- per-word state; initial symbols at their byte positions in buffer 0 (bpe.zig:185-211)
     for (uint32_t w = gt; w < a.n_huge; w += gstride) { a.wmin[0][w] = TKZ_NONE; a.wmin[1][w] = TKZ_NONE; a.wbad[w] = 0; }
-    if (gt < 8) a.gs[gt] = 0;
+    if (gt < 32) a.gs[gt] = 0;
     uint32_t lo, hi;
     range(a.M, lo, hi);
     {
@@ -219,8 +220,8 @@ __global__ void __launch_bounds__(BG_NT, 1) bpe_grid_kernel(const __grid_constan
     // ---------------- merge steps: two passes (H heads, K compaction + new ranks), each warp streaming its own contiguous
     // part of the array, four consecutive symbols per lane (16-byte loads), no block barrier inside a pass.
     // (block 0 keeps counters for TKZ_GRID_DEBUG: gs[5] steps, gs[6] run scans, gs[7] initial symbols, gs[8..] ns in H / K)
-    unsigned long long th = 0, tk = 0, t0 = 0;
-    uint32_t n_scans = 0;
+    unsigned long long th = 0, tk = 0, ts = 0, t0 = 0;
+    uint32_t n_scans = 0, n_sparse = 0, n_phases = 0;
     auto now = [] { unsigned long long x; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(x)); return x; };
     if (gt == 0) a.gs[7] = n;
     const uint32_t lane = t & 31, wq = t >> 5;
@@ -228,6 +229,7 @@ __global__ void __launch_bounds__(BG_NT, 1) bpe_grid_kernel(const __grid_constan
     uint32_t step = 0;
     for (;; step++) {
         const uint32_t par = step & 1u;
+        uint32_t total_heads = 0;
         if (*(volatile uint32_t*)(a.gs + 1 + par) == 0u) break;                   // bpe.zig:232-234 for every word
         if (gt == 0) t0 = now();
         uint32_t* const ids = a.id[cur]; uint32_t* const rk = a.rk[cur]; uint32_t* const wd = a.wid[cur]; uint16_t* const win = a.win[cur];
@@ -420,15 +422,180 @@ __global__ void __launch_bounds__(BG_NT, 1) bpe_grid_kernel(const __grid_constan
             if (__syncthreads_or(fm ? 1 : 0) && t == 0) *(volatile uint32_t*)(a.gs + 1 + (par ^ 1u)) = 1u;
             if (gt == 0 && step < 256) { a.dbg[4 * step] = n; a.dbg[4 * step + 1] = total; a.dbg[4 * step + 2] = (uint32_t)dth; }
             n -= total;
+            total_heads = total;
             cur = nxt;
         }
         grid.sync();
-        if (gt == 0) { const unsigned long long d = now() - t0; tk += d; if (step < 256) a.dbg[4 * step + 3] = (uint32_t)d; }
+        if (gt == 0) { const unsigned long long d = now() - t0; tk += d; if (step < 256) a.dbg[4 * step + 3] = (uint32_t)d; t0 = now(); }
+
+        // ---------------- sparse phase.  Once a step merges less than 1/128 of the symbols, copying the whole array per step
+        // is the cost (long dependency chains resolve one link per step: dozens of steps with a handful of merges each).
+        // The few pairs that still have a rank are kept in a list; merges are applied IN PLACE: the right symbol of a merged
+        // pair is marked dead (dstep = the step it died in; a step sees the deaths of earlier steps only) and skipped when
+        // neighbours / windows are walked.  Same head rule as pass H.  One compaction at the end.  An (A, A) run longer than
+        // BG_SPARSE_WALK returns to the dense steps (run scan) after that compaction.
+        // Scratch = the arrays of the other buffer: pair lists, dstep, hstep (step in which hn[i] was written).
+        if ((unsigned long long)total_heads * 128u < (unsigned long long)n + total_heads && *(volatile uint32_t*)(a.gs + 1 + (par ^ 1u)) != 0u) {
+            const uint32_t nxt = cur ^ 1u;
+            uint32_t* const ids2 = a.id[cur]; uint32_t* const rk2 = a.rk[cur]; uint32_t* const wd2 = a.wid[cur]; uint16_t* const win2 = a.win[cur];
+            uint32_t* const ev2 = a.e[cur];
+            uint32_t* lst[2] = {a.id[nxt], a.s[nxt]};
+            uint32_t* const dstep = a.rk[nxt]; uint32_t* const hstep = a.wid[nxt];
+            range(n, lo, hi);
+            for (uint32_t c0 = lo; c0 < hi; c0 += BG_NT) {
+                const uint32_t i = c0 + t;
+                bool fin = false;
+                if (i < hi) { dstep[i] = 0; hstep[i] = 0; fin = rk2[i] < TKZ_BOUNDARY; }
+                const uint32_t fm = __ballot_sync(FULL, fin);
+                if (fm) {
+                    uint32_t base = 0;
+                    if (lane == 0) base = atomicAdd(a.gs + 18, (uint32_t)__popc(fm));
+                    base = __shfl_sync(FULL, base, 0);
+                    if (fin) lst[0][base + __popc(fm & ((1u << lane) - 1u))] = i;
+                }
+            }
+            grid.sync();
+            uint32_t gstep = 0, li = 0, sp = par ^ 1u;
+            bool need_dense = false;
+            auto dead = [&](uint32_t i) { const uint32_t d = dstep[i]; return d != 0u && d < gstep; };
+            auto next_live = [&](uint32_t i) { do { i++; } while (i < n && dead(i)); return i; };                // n: none
+            auto prev_live = [&](uint32_t i) { while (i > 0) { i--; if (!dead(i)) return i; } return (uint32_t)TKZ_NONE; };
+            auto head_id = [&](uint32_t i) { return hstep[i] == gstep ? a.hn[i] : (uint32_t)TKZ_NONE; };       // TKZ_NONE: not a head this step
+            for (;;) {
+                const uint32_t len = *(volatile uint32_t*)(a.gs + 18 + li);
+                if (len == 0) break;
+                gstep++;
+                const uint32_t* const L = lst[li]; uint32_t* const Ln = lst[li ^ 1u];
+                // W. smallest rank per word
+                for (uint32_t idx = gt; idx < len; idx += gstride) { const uint32_t i = L[idx]; atomicMin(&a.wmin[sp][wd2[i]], rk2[i]); }
+                if (gt == 0) { a.gs[18 + (li ^ 1u)] = 0; a.gs[16 + ((gstep & 1u) ^ 1u)] = 0; }
+                grid.sync();
+                // H. heads
+                for (uint32_t w = gt; w < a.n_huge; w += gstride) a.wmin[sp ^ 1u][w] = TKZ_NONE;
+                for (uint32_t idx = gt; idx < len; idx += gstride) {
+                    const uint32_t i = L[idx], r = rk2[i], j = next_live(i), x = ids2[i], y = ids2[j];
+                    bool head = false;
+                    if (x != y) {
+                        const uint32_t wv = win2[i], wl = wv & 0xFFu, wr = wv >> 8;
+                        head = true;
+                        uint32_t q = i;
+                        for (uint32_t c = 0; c < wl && head; c++) { q = prev_live(q); if (q == TKZ_NONE) break; const uint32_t rq = rk2[q]; if (rq == TKZ_BOUNDARY) break; head = rq >= r; }
+                        q = i;
+                        for (uint32_t c = 0; c < wr && head; c++) { q = next_live(q); if (q >= n) break; const uint32_t rq = rk2[q]; if (rq == TKZ_BOUNDARY) break; head = rq >= r; }
+                    } else if (r == a.wmin[sp][wd2[i]]) {
+                        uint32_t q = i, c = 0;
+                        for (;;) {
+                            const uint32_t pq = prev_live(q);
+                            if (pq == TKZ_NONE || rk2[pq] == TKZ_BOUNDARY || ids2[pq] != x) break;
+                            q = pq;
+                            if (++c > BG_SPARSE_WALK) { *(volatile uint32_t*)(a.gs + 16 + (gstep & 1u)) = 1u; break; }
+                        }
+                        head = (c & 1u) == 0;
+                    }
+                    uint32_t hv = TKZ_NONE;
+                    if (head) merge_rank_lookup(m, x, y, &hv);
+                    a.hn[i] = hv; hstep[i] = gstep;
+                }
+                grid.sync();
+                if (*(volatile uint32_t*)(a.gs + 16 + (gstep & 1u)) != 0u) { need_dense = true; break; }
+                // A. apply the merges in place, ranks of the pairs they touch, next list
+                for (uint32_t c0 = 0; c0 < len; c0 += gstride) {
+                    const uint32_t idx = c0 + gt;
+                    uint32_t add0 = TKZ_NONE, add1 = TKZ_NONE;                   // pairs with a rank for the next list
+                    if (idx < len) {
+                        const uint32_t i = L[idx];
+                        const uint32_t nid = head_id(i);
+                        if (nid != TKZ_NONE) {
+                            const uint32_t j = next_live(i), k2 = next_live(j);
+                            uint32_t r1 = TKZ_BOUNDARY, w1 = 0;
+                            if (k2 < n && wd2[k2] == wd2[i]) { const uint32_t hk = head_id(k2); uint32_t tmp; r1 = merge_lookup_win(m, nid, hk != TKZ_NONE ? hk : ids2[k2], &tmp, &w1); }
+                            const uint32_t pl = prev_live(i);
+                            if (pl != TKZ_NONE && wd2[pl] == wd2[i]) {
+                                const uint32_t pp = prev_live(pl);
+                                if (!(pp != TKZ_NONE && head_id(pp) != TKZ_NONE)) {              // pl itself survives this step
+                                    uint32_t tmp, w0 = 0;
+                                    const uint32_t r0 = merge_lookup_win(m, ids2[pl], nid, &tmp, &w0);
+                                    rk2[pl] = r0; win2[pl] = (uint16_t)w0;
+                                    if (r0 < TKZ_BOUNDARY) add1 = pl;
+                                }
+                            }
+                            ids2[i] = nid; ev2[i] = ev2[j]; rk2[i] = r1; win2[i] = (uint16_t)w1; dstep[j] = gstep;
+                            if (r1 < TKZ_BOUNDARY) add0 = i;
+                        } else {
+                            const uint32_t pl = prev_live(i);
+                            const bool removed = pl != TKZ_NONE && head_id(pl) != TKZ_NONE;
+                            if (!removed && head_id(next_live(i)) == TKZ_NONE) add0 = i;       // (a head to the right re-ranks and lists this pair)
+                        }
+                    }
+                    const uint32_t m0 = __ballot_sync(FULL, add0 != TKZ_NONE), m1 = __ballot_sync(FULL, add1 != TKZ_NONE);
+                    if (m0 | m1) {
+                        uint32_t base = 0;
+                        if (lane == 0) base = atomicAdd(a.gs + 18 + (li ^ 1u), (uint32_t)(__popc(m0) + __popc(m1)));
+                        base = __shfl_sync(FULL, base, 0);
+                        const uint32_t lt = (1u << lane) - 1u;
+                        if (add0 != TKZ_NONE) Ln[base + __popc(m0 & lt)] = add0;
+                        if (add1 != TKZ_NONE) Ln[base + __popc(m0) + __popc(m1 & lt)] = add1;
+                    }
+                }
+                grid.sync();
+                li ^= 1u; sp ^= 1u;
+                n_sparse++;
+            }
+            // compaction: the dead symbols leave; the other buffer becomes the array again
+            {
+                const unsigned long long per2 = range(n, lo, hi);
+                const uint32_t pw2 = (uint32_t)(per2 / 32);
+                const unsigned long long wl64 = per2 * b + (unsigned long long)pw2 * wq;
+                const uint32_t wlo = (uint32_t)(wl64 < n ? wl64 : n), whi = (uint32_t)(wl64 + pw2 < n ? wl64 + pw2 : n);
+                uint32_t nd = 0;
+                for (uint32_t c0 = wlo; c0 < whi; c0 += 32) {
+                    const uint32_t i = c0 + lane;
+                    if (i < whi) { const bool d = dstep[i] != 0u; a.hn[i] = d ? 1u : 0u; nd += d; }
+                }
+                for (int d = 16; d > 0; d >>= 1) nd += __shfl_xor_sync(FULL, nd, d);
+                if (lane == 0) cnt[b * 32 + wq] = nd;
+                for (uint32_t w = gt; w < a.n_huge; w += gstride) { a.wmin[0][w] = TKZ_NONE; a.wmin[1][w] = TKZ_NONE; }
+                if (gt == 0) { a.gs[16] = 0; a.gs[17] = 0; a.gs[18] = 0; a.gs[19] = 0; a.gs[1] = 0; a.gs[2] = 0; }
+                grid.sync();
+                uint32_t before, total;
+                bg_prefix_total(cnt, G * 32, b * 32, red, before, total);
+                {
+                    const uint32_t own = __ldcg(cnt + b * 32 + lane);
+                    uint32_t inc = own;
+                    for (int d = 1; d < 32; d <<= 1) { const uint32_t y = __shfl_up_sync(FULL, inc, d); if (lane >= (uint32_t)d) inc += y; }
+                    before += __shfl_sync(FULL, inc - own, wq);
+                }
+                uint32_t run = before;
+                bool any = false;
+                uint32_t* const sv2 = a.s[cur];
+                for (uint32_t c0 = wlo; c0 < whi; c0 += 32) {
+                    const uint32_t i = c0 + lane;
+                    const bool live = i < whi && a.hn[i] == 0u;
+                    uint32_t xi = 0, xs = 0, xe = 0, xw = 0, xr = TKZ_NONE, xn = 0;
+                    if (live) { xi = ids2[i]; xs = sv2[i]; xe = ev2[i]; xw = wd2[i]; xr = rk2[i]; xn = win2[i]; }
+                    const uint32_t lm = __ballot_sync(FULL, live), valid = __ballot_sync(FULL, i < whi);
+                    const uint32_t q = i - (run + (uint32_t)__popc(valid & ~lm & ((1u << lane) - 1u)));
+                    run += (uint32_t)__popc(valid & ~lm);
+                    if (live) {
+                        // (the words of this buffer were scratch: all six arrays are written)
+                        a.id[nxt][q] = xi; a.s[nxt][q] = xs; a.e[nxt][q] = xe; a.wid[nxt][q] = xw; a.rk[nxt][q] = xr; a.win[nxt][q] = (uint16_t)xn;
+                        if (xr < TKZ_BOUNDARY) { atomicMin(&a.wmin[par ^ 1u][xw], xr); any = true; }
+                    }
+                }
+                if (__syncthreads_or(any ? 1 : 0) && t == 0) *(volatile uint32_t*)(a.gs + 1 + (par ^ 1u)) = 1u;
+                n -= total;
+                cur = nxt;
+                n_phases++;
+                (void)need_dense;
+            }
+            grid.sync();
+            if (gt == 0) ts += now() - t0;
+        }
     }
     if (gt == 0) {
-        a.gs[5] = step; a.gs[6] = n_scans;
+        a.gs[5] = step; a.gs[6] = n_scans; a.gs[20] = n_sparse; a.gs[21] = n_phases;
         unsigned long long* g64 = reinterpret_cast<unsigned long long*>(a.gs + 8);
-        g64[0] = 0; g64[1] = th; g64[2] = tk;
+        g64[0] = ts; g64[1] = th; g64[2] = tk;
     }
 
     // ---------------- tokens (bpe.zig:256-260): first symbol of every word in the final array, then the copy to the pool
