@@ -76,6 +76,7 @@ struct tkz_ctx {
     DevBuf a_wtable, a_lscratch, a_ent, a_tile_ent_off, a_long_slice, a_region_ctr;
     DevBuf a_huge_w, a_huge_base, a_huge_done, a_grid_state, a_grid_words;   // bpe_grid_kernel (tkz_bpe_grid.cuh)
     bool use_grid = true;                 // TKZ_NO_GRID=1: huge words stay with one block each (A/B switch of the parity tests)
+    uint32_t grid_min_len = 12289;        // shortest word (bytes) that goes to bpe_grid_kernel (TKZ_GRID_MIN_LEN)
     bool grid_used = false;               // the last encode ran bpe_grid_kernel
     int grid_blocks = 0;                  // co-resident blocks of bpe_grid_kernel (0: cooperative launch not available)
     uint64_t tw_uniq_hist = 0;            // most unique words seen in one batch: sizes the next batch's word table
@@ -261,6 +262,7 @@ extern "C" int tkz_ctx_create(int device, void* stream, uint64_t arena_hint_byte
     if (const char* e = getenv("TKZ_NO_DEDUP")) ctx->use_dedup = !(e[0] == '1');     // A/B switch for the parity tests
     if (const char* e = getenv("TKZ_SLICES")) ctx->use_slices = !(e[0] == '0');
     if (const char* e = getenv("TKZ_NO_GRID")) ctx->use_grid = !(e[0] == '1');
+    if (const char* e = getenv("TKZ_GRID_MIN_LEN")) { const long long v = atoll(e); if (v > (long long)BB_WARP_MAX) ctx->grid_min_len = (uint32_t)v; }
     {
         int coop = 0, per_sm = 0;
         cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device);
@@ -507,25 +509,17 @@ int launch_bpe(tkz_ctx* ctx, const DevModel& m, const uint8_t* d_text, const uin
     b.pool_id = (uint32_t*)ctx->a_pool_id.p; b.pool_s = (uint32_t*)ctx->a_pool_s.p; b.pool_e = (uint32_t*)ctx->a_pool_e.p; b.pool_rk = (uint32_t*)ctx->a_pool_rk.p;
     b.g_first = (uint32_t*)ctx->a_g_first.p; b.g_win = (uint16_t*)ctx->a_g_win.p; b.g_flag = (uint8_t*)ctx->a_g_flag.p;
     b.word_ntok = word_ntok; b.errw = ctrl; b.sentinel_errors = sentinel;
-    if (cls[0]) {
-        // 65..1024 bytes: two warps per word (cheap barriers, 14 words in flight per SM); 1025..2048: eight warps
-        b.min_len = BB_WARP_MAX + 1; b.max_len = BB_TINY_MAX; b.work_counter = (unsigned int*)(ctrl + 17);
-        uint64_t g = cls[0]; uint64_t gc = (uint64_t)ctx->sm_count * 14; if (g > gc) g = gc;
-        bpe_block_kernel<64, BB_TINY_MAX><<<(unsigned)g, 64, BB_TINY_MAX * 15, st>>>(m, b); launches++;
-        b.min_len = BB_TINY_MAX + 1; b.max_len = BB_SMALL_MAX; b.work_counter = (unsigned int*)(ctrl + 11);
-        g = cls[0]; gc = (uint64_t)ctx->sm_count * 6; if (g > gc) g = gc;
-        bpe_block_kernel<256, BB_SMALL_MAX><<<(unsigned)g, 256, BB_SMALL_MAX * 15, st>>>(m, b); launches++;
-    }
-    if (cls[2] && ctx->use_grid && ctx->grid_blocks > 0) {
+    const uint32_t grid_min = ctx->grid_min_len;
+    if ((grid_min > BB_BIG_CAP ? cls[2] != 0 : (cls[0] || cls[1])) && ctx->use_grid && ctx->grid_blocks > 0) {
         // words above the shared-memory capacity: all of them together on one cooperative grid (tkz_bpe_grid.cuh); a word
         // it leaves alone (malformed UTF-8) and everything when its state does not fit falls through to the block kernel
-        const uint32_t hcap = (uint32_t)cls[2];
+        const uint32_t hcap = grid_min == BB_BIG_CAP + 1 ? (uint32_t)cls[2] : nw;
         unsigned long long* hctrl = (unsigned long long*)ctx->h_ctrl.p;
         TRY(ensure(ctx, ctx->a_huge_w, ((size_t)hcap + 2) * 4));
         TRY(ensure(ctx, ctx->a_huge_base, ((size_t)hcap + 2) * 4));
         TRY(ensure(ctx, ctx->a_huge_done, (size_t)nw + 16));
         CK(cudaMemsetAsync(ctx->a_huge_done.p, 0, (size_t)nw, st));
-        huge_list_kernel<<<1, 1024, 0, st>>>(word_start, word_end, nw, BB_BIG_CAP + 1, hcap, (uint32_t*)ctx->a_huge_w.p, (uint32_t*)ctx->a_huge_base.p, ctrl + 18);
+        huge_list_kernel<<<1, 1024, 0, st>>>(word_start, word_end, nw, grid_min, hcap, (uint32_t*)ctx->a_huge_w.p, (uint32_t*)ctx->a_huge_base.p, ctrl + 18);
         launches++;
         TRY(readback(ctx, hctrl + 40, ctrl + 18, 16));
         CK(cudaStreamSynchronize(st));
@@ -533,7 +527,7 @@ int launch_bpe(tkz_ctx* ctx, const DevModel& m, const uint8_t* d_text, const uin
         auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
         const size_t per4 = al((size_t)M * 4 + 16), per2 = al((size_t)M * 2 + 16);
         const size_t state_bytes = 11 * per4 + 2 * per2;                    // (id, s, e, rk, wid) x 2 + hn, win x 2
-        const size_t words_bytes = 4 * al(((size_t)n_huge + 2) * 4) + al((size_t)n_huge + 16) + al((size_t)ctx->grid_blocks * 33 * 4 + 64) + 256 + 4096;
+        const size_t words_bytes = 4 * al(((size_t)n_huge + 2) * 4) + al((size_t)n_huge + 16) + al((size_t)ctx->grid_blocks * 33 * 4 + 64) + 256 + 5120;
         bool ok = n_huge > 0 && n_huge <= hcap && M < 0xFFFFF000ull;
         if (ok && (ensure(ctx, ctx->a_grid_state, state_bytes) != TKZ_OK || ensure(ctx, ctx->a_grid_words, words_bytes) != TKZ_OK)) {
             ok = false; ctx->err.clear(); cudaGetLastError();                // no room for the grid state: one block per word
@@ -555,7 +549,7 @@ int launch_bpe(tkz_ctx* ctx, const DevModel& m, const uint8_t* d_text, const uin
             ga.wbad = take(al((size_t)n_huge + 16));
             ga.blk = (uint32_t*)take(al((size_t)ctx->grid_blocks * 33 * 4 + 64));
             ga.gs = (uint32_t*)take(256);
-            ga.dbg = (uint32_t*)take(4096);
+            ga.dbg = (uint32_t*)take(5120);
             ga.pool_id = (uint32_t*)ctx->a_pool_id.p; ga.pool_s = (uint32_t*)ctx->a_pool_s.p; ga.pool_e = (uint32_t*)ctx->a_pool_e.p;
             ga.word_ntok = word_ntok; ga.done = (uint8_t*)ctx->a_huge_done.p;
             DevModel mm = m;
@@ -570,15 +564,24 @@ int launch_bpe(tkz_ctx* ctx, const DevModel& m, const uint8_t* d_text, const uin
                 fprintf(stderr, "[tkz grid] words %u bytes %u symbols %u dense steps %u run-scans %u sparse steps %u (%u phases)  ms: heads %.2f compact+ranks %.2f sparse %.2f\n", ga.n_huge, ga.M,
                         gsh[7], gsh[5], gsh[6], gsh[20], gsh[21], g64[1] * 1e-6, g64[2] * 1e-6, g64[0] * 1e-6);
                 if (getenv("TKZ_GRID_DEBUG")[0] == '2') {
-                    uint32_t d[1024];
+                    uint32_t d[1280];
                     cudaMemcpy(d, ga.dbg, sizeof d, cudaMemcpyDeviceToHost);
                     for (uint32_t k = 0; k < gsh[5] && k < 256; k++)
-                        fprintf(stderr, "[tkz grid]   step %3u  n %10u  heads %9u  H %7.3f ms  K %7.3f ms\n", k, d[4 * k], d[4 * k + 1], d[4 * k + 2] * 1e-6, d[4 * k + 3] * 1e-6);
+                        fprintf(stderr, "[tkz grid]   step %3u  n %10u  heads %9u  ranked pairs after %9u  H %7.3f ms  K %7.3f ms\n", k, d[4 * k], d[4 * k + 1], d[1024 + k], d[4 * k + 2] * 1e-6, d[4 * k + 3] * 1e-6);
                 }
             }
             b.skip = (const uint8_t*)ctx->a_huge_done.p;
             ctx->grid_used = true;
         }
+    }
+    if (cls[0]) {
+        // 65..1024 bytes: two warps per word (cheap barriers, 14 words in flight per SM); 1025..2048: eight warps
+        b.min_len = BB_WARP_MAX + 1; b.max_len = BB_TINY_MAX; b.work_counter = (unsigned int*)(ctrl + 17);
+        uint64_t g = cls[0]; uint64_t gc = (uint64_t)ctx->sm_count * 14; if (g > gc) g = gc;
+        bpe_block_kernel<64, BB_TINY_MAX><<<(unsigned)g, 64, BB_TINY_MAX * 15, st>>>(m, b); launches++;
+        b.min_len = BB_TINY_MAX + 1; b.max_len = BB_SMALL_MAX; b.work_counter = (unsigned int*)(ctrl + 11);
+        g = cls[0]; gc = (uint64_t)ctx->sm_count * 6; if (g > gc) g = gc;
+        bpe_block_kernel<256, BB_SMALL_MAX><<<(unsigned)g, 256, BB_SMALL_MAX * 15, st>>>(m, b); launches++;
     }
     if (cls[1]) {
         b.min_len = BB_SMALL_MAX + 1; b.max_len = 0xFFFFFFFFu; b.work_counter = (unsigned int*)(ctrl + 12);

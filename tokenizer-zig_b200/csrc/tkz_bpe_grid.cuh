@@ -32,6 +32,7 @@ namespace cg = cooperative_groups;
 #define TKZ_BOUNDARY 0xFFFFFFFDu          // cached "rank" of the position behind a word's last symbol
 constexpr int BG_NT = 1024;
 constexpr uint32_t BG_WALK = 32;          // equal-symbol runs up to this length find their start by walking left
+constexpr uint32_t BG_SPARSE_DIV = 16;     // the sparse phase starts when fewer than n / 16 pairs still have a rank (a listed pair costs ~10x a streamed symbol)
 constexpr uint32_t BG_SPARSE_WALK = 1024;  // same in the sparse phase (walks skip dead symbols); longer runs go back to the dense steps
 constexpr uint32_t BG_PENDING = 0xFFFFFFFEu;   // head mark of an (A, A) pair that waits for the run scan
 
@@ -241,7 +242,7 @@ __global__ void __launch_bounds__(BG_NT, 1) bpe_grid_kernel(const __grid_constan
         // H. heads of this step and their new ids
         {
             for (uint32_t w = gt; w < a.n_huge; w += gstride) a.wmin[par ^ 1u][w] = TKZ_NONE;
-            if (gt == 0) { a.gs[1 + (par ^ 1u)] = 0; a.gs[3 + (par ^ 1u)] = 0; }
+            if (gt == 0) { a.gs[1 + (par ^ 1u)] = 0; a.gs[3 + (par ^ 1u)] = 0; a.gs[22 + (par ^ 1u)] = 0; }
             uint32_t heads = 0; bool pend = false;
             for (uint32_t c0 = wlo; c0 < whi; c0 += 128) {
                 const uint32_t i0 = c0 + 4 * lane;
@@ -341,6 +342,7 @@ __global__ void __launch_bounds__(BG_NT, 1) bpe_grid_kernel(const __grid_constan
             }
             uint32_t run = before;
             uint32_t lmin = TKZ_NONE, lw = TKZ_NONE;                 // smallest new rank seen by this lane, and its word
+            uint32_t nfin = 0;                                       // pairs with a rank among the symbols this lane wrote
             for (uint32_t c0 = wlo; c0 < whi; c0 += 128) {
                 const uint32_t i0 = c0 + 4 * lane;
                 const bool in = i0 < whi;
@@ -403,6 +405,7 @@ __global__ void __launch_bounds__(BG_NT, 1) bpe_grid_kernel(const __grid_constan
                         a.id[nxt][q] = nid; a.s[nxt][q] = sv[k]; a.e[nxt][q] = hd ? ev[k + 1] : ev[k];
                         a.wid[nxt][q] = wv[k]; a.rk[nxt][q] = r; a.win[nxt][q] = (uint16_t)wnew;
                         if (r < TKZ_BOUNDARY) {
+                            nfin++;
                             if (lw == TKZ_NONE) lw = wv[k];
                             if (wv[k] == lw) lmin = r < lmin ? r : lmin; else atomicMin(&a.wmin[par ^ 1u][wv[k]], r);
                         }
@@ -420,6 +423,8 @@ __global__ void __launch_bounds__(BG_NT, 1) bpe_grid_kernel(const __grid_constan
                 } else if (lw != TKZ_NONE) atomicMin(&a.wmin[par ^ 1u][lw], lmin);
             }
             if (__syncthreads_or(fm ? 1 : 0) && t == 0) *(volatile uint32_t*)(a.gs + 1 + (par ^ 1u)) = 1u;
+            for (int d = 16; d > 0; d >>= 1) nfin += __shfl_xor_sync(FULL, nfin, d);
+            if (lane == 0 && nfin) atomicAdd(a.gs + 22 + (par ^ 1u), nfin);
             if (gt == 0 && step < 256) { a.dbg[4 * step] = n; a.dbg[4 * step + 1] = total; a.dbg[4 * step + 2] = (uint32_t)dth; }
             n -= total;
             total_heads = total;
@@ -428,14 +433,17 @@ __global__ void __launch_bounds__(BG_NT, 1) bpe_grid_kernel(const __grid_constan
         grid.sync();
         if (gt == 0) { const unsigned long long d = now() - t0; tk += d; if (step < 256) a.dbg[4 * step + 3] = (uint32_t)d; t0 = now(); }
 
-        // ---------------- sparse phase.  Once a step merges less than 1/128 of the symbols, copying the whole array per step
-        // is the cost (long dependency chains resolve one link per step: dozens of steps with a handful of merges each).
+        // ---------------- sparse phase.  Once less than 1/BG_SPARSE_DIV of the pairs still have a rank, copying the whole array
+        // per step is the cost (long dependency chains resolve one link per step: dozens of steps with a handful of merges each).
         // The few pairs that still have a rank are kept in a list; merges are applied IN PLACE: the right symbol of a merged
         // pair is marked dead (dstep = the step it died in; a step sees the deaths of earlier steps only) and skipped when
         // neighbours / windows are walked.  Same head rule as pass H.  One compaction at the end.  An (A, A) run longer than
         // BG_SPARSE_WALK returns to the dense steps (run scan) after that compaction.
         // Scratch = the arrays of the other buffer: pair lists, dstep, hstep (step in which hn[i] was written).
-        if ((unsigned long long)total_heads * 128u < (unsigned long long)n + total_heads && *(volatile uint32_t*)(a.gs + 1 + (par ^ 1u)) != 0u) {
+        const uint32_t n_live = *(volatile uint32_t*)(a.gs + 22 + (par ^ 1u));
+        if (gt == 0 && step < 256) a.dbg[1024 + step] = n_live;
+        (void)total_heads;
+        if ((unsigned long long)n_live * BG_SPARSE_DIV < n && n_live != 0u) {
             const uint32_t nxt = cur ^ 1u;
             uint32_t* const ids2 = a.id[cur]; uint32_t* const rk2 = a.rk[cur]; uint32_t* const wd2 = a.wid[cur]; uint16_t* const win2 = a.win[cur];
             uint32_t* const ev2 = a.e[cur];
@@ -467,7 +475,19 @@ __global__ void __launch_bounds__(BG_NT, 1) bpe_grid_kernel(const __grid_constan
                 gstep++;
                 const uint32_t* const L = lst[li]; uint32_t* const Ln = lst[li ^ 1u];
                 // W. smallest rank per word
-                for (uint32_t idx = gt; idx < len; idx += gstride) { const uint32_t i = L[idx]; atomicMin(&a.wmin[sp][wd2[i]], rk2[i]); }
+                for (uint32_t c0 = 0; c0 < len; c0 += gstride) {
+                    const uint32_t idx = c0 + gt;
+                    uint32_t r = TKZ_NONE, w = TKZ_NONE;
+                    if (idx < len) { const uint32_t i = L[idx]; r = rk2[i]; w = wd2[i]; }
+                    const uint32_t vm = __ballot_sync(FULL, idx < len);
+                    if (vm) {
+                        const uint32_t w0 = __shfl_sync(FULL, w, __ffs(vm) - 1);
+                        if (__all_sync(FULL, idx >= len || w == w0)) {
+                            for (int d = 16; d > 0; d >>= 1) { const uint32_t y = __shfl_xor_sync(FULL, r, d); r = y < r ? y : r; }
+                            if (lane == 0) atomicMin(&a.wmin[sp][w0], r);
+                        } else if (idx < len) atomicMin(&a.wmin[sp][w], r);
+                    }
+                }
                 if (gt == 0) { a.gs[18 + (li ^ 1u)] = 0; a.gs[16 + ((gstep & 1u) ^ 1u)] = 0; }
                 grid.sync();
                 // H. heads
