@@ -437,7 +437,8 @@ __global__ void __launch_bounds__(BG_NT, 1) bpe_grid_kernel(const __grid_constan
         // per step is the cost (long dependency chains resolve one link per step: dozens of steps with a handful of merges each).
         // The few pairs that still have a rank are kept in a list; merges are applied IN PLACE: the right symbol of a merged
         // pair is marked dead (dstep = the step it died in; a step sees the deaths of earlier steps only) and skipped when
-        // neighbours / windows are walked.  Same head rule as pass H.  One compaction at the end.  An (A, A) run longer than
+        // neighbours / windows are walked.  Same head rule as pass H; two passes and two grid barriers per step.  One compaction
+        // at the end.  An (A, A) run longer than
         // BG_SPARSE_WALK returns to the dense steps (run scan) after that compaction.
         // Scratch = the arrays of the other buffer: pair lists, dstep, hstep (step in which hn[i] was written).
         const uint32_t n_live = *(volatile uint32_t*)(a.gs + 22 + (par ^ 1u));
@@ -474,24 +475,9 @@ __global__ void __launch_bounds__(BG_NT, 1) bpe_grid_kernel(const __grid_constan
                 if (len == 0) break;
                 gstep++;
                 const uint32_t* const L = lst[li]; uint32_t* const Ln = lst[li ^ 1u];
-                // W. smallest rank per word
-                for (uint32_t c0 = 0; c0 < len; c0 += gstride) {
-                    const uint32_t idx = c0 + gt;
-                    uint32_t r = TKZ_NONE, w = TKZ_NONE;
-                    if (idx < len) { const uint32_t i = L[idx]; r = rk2[i]; w = wd2[i]; }
-                    const uint32_t vm = __ballot_sync(FULL, idx < len);
-                    if (vm) {
-                        const uint32_t w0 = __shfl_sync(FULL, w, __ffs(vm) - 1);
-                        if (__all_sync(FULL, idx >= len || w == w0)) {
-                            for (int d = 16; d > 0; d >>= 1) { const uint32_t y = __shfl_xor_sync(FULL, r, d); r = y < r ? y : r; }
-                            if (lane == 0) atomicMin(&a.wmin[sp][w0], r);
-                        } else if (idx < len) atomicMin(&a.wmin[sp][w], r);
-                    }
-                }
-                if (gt == 0) { a.gs[18 + (li ^ 1u)] = 0; a.gs[16 + ((gstep & 1u) ^ 1u)] = 0; }
-                grid.sync();
-                // H. heads
+                // H. heads (wmin[sp] = smallest rank per word: from pass K at the start, then from pass A of the step before)
                 for (uint32_t w = gt; w < a.n_huge; w += gstride) a.wmin[sp ^ 1u][w] = TKZ_NONE;
+                if (gt == 0) { a.gs[18 + (li ^ 1u)] = 0; a.gs[16 + ((gstep & 1u) ^ 1u)] = 0; }
                 for (uint32_t idx = gt; idx < len; idx += gstride) {
                     const uint32_t i = L[idx], r = rk2[i], j = next_live(i), x = ids2[i], y = ids2[j];
                     bool head = false;
@@ -518,33 +504,35 @@ __global__ void __launch_bounds__(BG_NT, 1) bpe_grid_kernel(const __grid_constan
                 }
                 grid.sync();
                 if (*(volatile uint32_t*)(a.gs + 16 + (gstep & 1u)) != 0u) { need_dense = true; break; }
-                // A. apply the merges in place, ranks of the pairs they touch, next list
+                // A. apply the merges in place, ranks of the pairs they touch, next list + the word minima of the next step
                 for (uint32_t c0 = 0; c0 < len; c0 += gstride) {
                     const uint32_t idx = c0 + gt;
                     uint32_t add0 = TKZ_NONE, add1 = TKZ_NONE;                   // pairs with a rank for the next list
+                    uint32_t rmin = TKZ_NONE, w = TKZ_NONE;                      // smallest rank among them, their word
                     if (idx < len) {
                         const uint32_t i = L[idx];
                         const uint32_t nid = head_id(i);
+                        w = wd2[i];
                         if (nid != TKZ_NONE) {
                             const uint32_t j = next_live(i), k2 = next_live(j);
                             uint32_t r1 = TKZ_BOUNDARY, w1 = 0;
-                            if (k2 < n && wd2[k2] == wd2[i]) { const uint32_t hk = head_id(k2); uint32_t tmp; r1 = merge_lookup_win(m, nid, hk != TKZ_NONE ? hk : ids2[k2], &tmp, &w1); }
+                            if (k2 < n && wd2[k2] == w) { const uint32_t hk = head_id(k2); uint32_t tmp; r1 = merge_lookup_win(m, nid, hk != TKZ_NONE ? hk : ids2[k2], &tmp, &w1); }
                             const uint32_t pl = prev_live(i);
-                            if (pl != TKZ_NONE && wd2[pl] == wd2[i]) {
+                            if (pl != TKZ_NONE && wd2[pl] == w) {
                                 const uint32_t pp = prev_live(pl);
                                 if (!(pp != TKZ_NONE && head_id(pp) != TKZ_NONE)) {              // pl itself survives this step
                                     uint32_t tmp, w0 = 0;
                                     const uint32_t r0 = merge_lookup_win(m, ids2[pl], nid, &tmp, &w0);
                                     rk2[pl] = r0; win2[pl] = (uint16_t)w0;
-                                    if (r0 < TKZ_BOUNDARY) add1 = pl;
+                                    if (r0 < TKZ_BOUNDARY) { add1 = pl; rmin = r0; }
                                 }
                             }
                             ids2[i] = nid; ev2[i] = ev2[j]; rk2[i] = r1; win2[i] = (uint16_t)w1; dstep[j] = gstep;
-                            if (r1 < TKZ_BOUNDARY) add0 = i;
+                            if (r1 < TKZ_BOUNDARY) { add0 = i; rmin = r1 < rmin ? r1 : rmin; }
                         } else {
                             const uint32_t pl = prev_live(i);
                             const bool removed = pl != TKZ_NONE && head_id(pl) != TKZ_NONE;
-                            if (!removed && head_id(next_live(i)) == TKZ_NONE) add0 = i;       // (a head to the right re-ranks and lists this pair)
+                            if (!removed && head_id(next_live(i)) == TKZ_NONE) { add0 = i; rmin = rk2[i]; }   // (a head to the right re-ranks and lists this pair)
                         }
                     }
                     const uint32_t m0 = __ballot_sync(FULL, add0 != TKZ_NONE), m1 = __ballot_sync(FULL, add1 != TKZ_NONE);
@@ -555,6 +543,12 @@ __global__ void __launch_bounds__(BG_NT, 1) bpe_grid_kernel(const __grid_constan
                         const uint32_t lt = (1u << lane) - 1u;
                         if (add0 != TKZ_NONE) Ln[base + __popc(m0 & lt)] = add0;
                         if (add1 != TKZ_NONE) Ln[base + __popc(m0) + __popc(m1 & lt)] = add1;
+                        // one atomic per warp when all its listed pairs belong to the same word (the usual case)
+                        const uint32_t w0 = __shfl_sync(FULL, w, __ffs(m0 | m1) - 1);
+                        if (__all_sync(FULL, rmin == TKZ_NONE || w == w0)) {
+                            for (int d = 16; d > 0; d >>= 1) { const uint32_t y = __shfl_xor_sync(FULL, rmin, d); rmin = y < rmin ? y : rmin; }
+                            if (lane == 0) atomicMin(&a.wmin[sp ^ 1u][w0], rmin);
+                        } else if (rmin != TKZ_NONE) atomicMin(&a.wmin[sp ^ 1u][w], rmin);
                     }
                 }
                 grid.sync();
