@@ -149,7 +149,8 @@ __global__ void ctrl_reset_kernel(unsigned long long* ctrl) {
     // ctrl[0] = error word, ctrl[1] = work counter (u32 view), ctrl[2..4] = read-back scalars,
     // dedup: ctrl[5] second work counter, [6] n_uniq, [7] n_long, [8] overflow, [9] upool_count, [10] n_words
     // slice pipeline: [5] entry count, [6] n_uniq | n_uncached << 32, [7] n_long, [8] abort, [9] upool | lscratch << 32,
-    //                [10] n_words, [11..12] block-kernel work counters, [13..15] long-word length classes, [16] big-copy list
+    //                [10] n_words, [11..12], [17], [20..21] block-kernel work counters, [13..15] long-word length classes,
+    //                [16] big-copy list, [18..19] huge-word list (count, bytes)
     ctrl[0] = TKZ_ERRW_NONE;
     for (int i = 1; i < 32; i++) ctrl[i] = 0;
 }
@@ -187,7 +188,7 @@ __global__ void gather_scalars_dedup_kernel(unsigned long long* ctrl, const uint
     ctrl[4] = d;
 }
 // word-length classes of the BPE kernels: [0] 65..2048 bytes, [1] > 2048, [2] > 12288 (needs global state arrays)
-constexpr uint32_t BB_WARP_MAX = 64, BB_TINY_MAX = 1024, BB_SMALL_MAX = 2048, BB_BIG_CAP = 12288;
+constexpr uint32_t BB_WARP_MAX = 64, BB_MINI_MAX = 512, BB_TINY_MAX = 1024, BB_SMALL_MAX = 2048, BB_MID_MAX = 4096, BB_BIG_CAP = 12288;
 __global__ void len_class_count_kernel(const uint32_t* word_start, const uint32_t* word_end, uint32_t n_fixed, const unsigned int* n_dev,
                                        unsigned long long* counts) {
     const uint32_t n = n_dev ? *n_dev : n_fixed;
@@ -234,6 +235,7 @@ extern "C" int tkz_ctx_create(int device, void* stream, uint64_t arena_hint_byte
         ctx->own_stream = true;
     }
     cudaFuncSetAttribute(bpe_block_kernel<1024, 12288>, cudaFuncAttributeMaxDynamicSharedMemorySize, 12288 * 15);
+    cudaFuncSetAttribute(bpe_block_kernel<512, 4096, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4096 * 15);
     {
         const int sm = (int)sizeof(BlockShared);
         cudaFuncSetAttribute(slice_words_kernel<TKZ_MODEL_BPE, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
@@ -574,18 +576,28 @@ int launch_bpe(tkz_ctx* ctx, const DevModel& m, const uint8_t* d_text, const uin
             ctx->grid_used = true;
         }
     }
+    // One class per shared-memory footprint (15 B per symbol of capacity): an SM holds ~14 k symbols of state whatever the
+    // class, so a word in a class far above its length wastes the SM (c2a: 73 % of the words above 2048 bytes are below
+    // 4096; 59 % of those up to 1024 are below 512).
     if (cls[0]) {
-        // 65..1024 bytes: two warps per word (cheap barriers, 14 words in flight per SM); 1025..2048: eight warps
-        b.min_len = BB_WARP_MAX + 1; b.max_len = BB_TINY_MAX; b.work_counter = (unsigned int*)(ctrl + 17);
-        uint64_t g = cls[0]; uint64_t gc = (uint64_t)ctx->sm_count * 14; if (g > gc) g = gc;
-        bpe_block_kernel<64, BB_TINY_MAX><<<(unsigned)g, 64, BB_TINY_MAX * 15, st>>>(m, b); launches++;
+        // 65..512 bytes: one warp per word, 28 words in flight per SM; ..1024: two warps, 14 words; ..2048: eight warps, 6 words
+        b.min_len = BB_WARP_MAX + 1; b.max_len = BB_MINI_MAX; b.work_counter = (unsigned int*)(ctrl + 20);
+        uint64_t g = cls[0]; uint64_t gc = (uint64_t)ctx->sm_count * 28; if (g > gc) g = gc;
+        bpe_block_kernel<32, BB_MINI_MAX, 28><<<(unsigned)g, 32, BB_MINI_MAX * 15, st>>>(m, b); launches++;
+        b.min_len = BB_MINI_MAX + 1; b.max_len = BB_TINY_MAX; b.work_counter = (unsigned int*)(ctrl + 17);
+        g = cls[0]; gc = (uint64_t)ctx->sm_count * 14; if (g > gc) g = gc;
+        bpe_block_kernel<64, BB_TINY_MAX, 14><<<(unsigned)g, 64, BB_TINY_MAX * 15, st>>>(m, b); launches++;
         b.min_len = BB_TINY_MAX + 1; b.max_len = BB_SMALL_MAX; b.work_counter = (unsigned int*)(ctrl + 11);
         g = cls[0]; gc = (uint64_t)ctx->sm_count * 6; if (g > gc) g = gc;
-        bpe_block_kernel<256, BB_SMALL_MAX><<<(unsigned)g, 256, BB_SMALL_MAX * 15, st>>>(m, b); launches++;
+        bpe_block_kernel<256, BB_SMALL_MAX, 6><<<(unsigned)g, 256, BB_SMALL_MAX * 15, st>>>(m, b); launches++;
     }
     if (cls[1]) {
-        b.min_len = BB_SMALL_MAX + 1; b.max_len = 0xFFFFFFFFu; b.work_counter = (unsigned int*)(ctrl + 12);
-        uint64_t g = cls[1]; const uint64_t gc = (uint64_t)ctx->sm_count; if (g > gc) g = gc;
+        // 2049..4096 bytes: sixteen warps, 3 words in flight per SM; longer: 32 warps, one word per SM (global state above 12288)
+        b.min_len = BB_SMALL_MAX + 1; b.max_len = BB_MID_MAX; b.work_counter = (unsigned int*)(ctrl + 21);
+        uint64_t g = cls[1]; uint64_t gc = (uint64_t)ctx->sm_count * 3; if (g > gc) g = gc;
+        bpe_block_kernel<512, BB_MID_MAX, 3><<<(unsigned)g, 512, BB_MID_MAX * 15, st>>>(m, b); launches++;
+        b.min_len = BB_MID_MAX + 1; b.max_len = 0xFFFFFFFFu; b.work_counter = (unsigned int*)(ctrl + 12);
+        g = cls[1]; gc = (uint64_t)ctx->sm_count; if (g > gc) g = gc;
         bpe_block_kernel<1024, BB_BIG_CAP><<<(unsigned)g, 1024, BB_BIG_CAP * 15, st>>>(m, b); launches++;
     }
     return TKZ_OK;

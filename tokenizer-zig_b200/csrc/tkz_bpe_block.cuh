@@ -68,8 +68,8 @@ __device__ __forceinline__ uint32_t block_incl_maxscan(uint32_t v, uint32_t* sh 
 }
 
 // NT threads, CAP symbols of shared-memory state (15 bytes each)
-template <int NT, int CAP>
-__global__ void __launch_bounds__(NT) bpe_block_kernel(DevModel m, BlockBpeArgs a) {
+template <int NT, int CAP, int MINB = 1>
+__global__ void __launch_bounds__(NT, MINB) bpe_block_kernel(DevModel m, BlockBpeArgs a) {
     extern __shared__ __align__(16) uint8_t bb_smem[];
     uint32_t* const s_id = reinterpret_cast<uint32_t*>(bb_smem);
     uint32_t* const s_first = s_id + CAP;
