@@ -430,17 +430,29 @@ extern "C" int tkz_model_upload(tkz_ctx* ctx, const tkz_model_desc* d) {
                     auto it = nsym.find(e.new_id);
                     if (it == nsym.end() || it->second < v) nsym[e.new_id] = v;
                 }
-                std::unordered_map<uint32_t, uint32_t> WL, WR;  // WL[a] = max nsym(X) over merges (X, a); WR[b] = max nsym(Z) over (b, Z)
+                // Threats to an occurrence (a, b) of rank r: merges that consume a from the left or b from the right BEFORE round
+                // r, i.e. entries (X, a) / (b, Z) with a rank below r (X, Z are then built by merges of even lower rank).  Window
+                // of the entry: wl = max nsym(X) over (X, a) with rank < r, wr = max nsym(Z) over (b, Z) with rank < r.  Early
+                // merges involve short symbols, so the pairs that merge in the first, populous steps get windows of 1-3 symbols
+                // (a rank-blind window is as wide as the longest token that ever joins the symbol: TKZ_WINDOWS=blind).
+                const bool blind = [] { const char* e = getenv("TKZ_WINDOWS"); return e && e[0] == 'b'; }();
+                std::unordered_map<uint32_t, uint32_t> WL, WR;  // running max while the entries are visited in rank order
                 for (uint32_t sl : order) {
                     const MergeEnt& e = mtab[sl];
-                    uint32_t& l = WL[e.second]; l = std::max(l, ns(e.first));
-                    uint32_t& r = WR[e.first]; r = std::max(r, ns(e.second));
+                    if (blind) { uint32_t& l = WL[e.second]; l = std::max(l, ns(e.first)); uint32_t& r = WR[e.first]; r = std::max(r, ns(e.second)); }
                 }
-                for (uint32_t sl : order) {
+                for (uint32_t sl : order) {                    // ascending rank: WL / WR hold exactly the entries of lower rank
                     const MergeEnt& e = mtab[sl];
-                    const uint32_t wl = WL[e.first], wr = WR[e.second];     // threats to `first` from its left, to `second` from its right
+                    auto get = [](std::unordered_map<uint32_t, uint32_t>& mp, uint32_t k) { auto it = mp.find(k); return it == mp.end() ? 0u : it->second; };
+                    const uint32_t wl = get(WL, e.first), wr = get(WR, e.second);     // threats to `first` from its left, to `second` from its right
                     if (wl > 250 || wr > 250) { proper = false; break; }
                     win[sl] = (uint16_t)(wl | (wr << 8));
+                    if (!blind) { uint32_t& l = WL[e.second]; l = std::max(l, ns(e.first)); uint32_t& r = WR[e.first]; r = std::max(r, ns(e.second)); }
+                }
+                if (getenv("TKZ_GRID_DEBUG") && !order.empty()) {
+                    double sl_ = 0, sr_ = 0; uint32_t ml = 0, mr = 0;
+                    for (uint32_t sl : order) { sl_ += win[sl] & 0xFF; sr_ += win[sl] >> 8; ml = std::max<uint32_t>(ml, win[sl] & 0xFF); mr = std::max<uint32_t>(mr, win[sl] >> 8); }
+                    fprintf(stderr, "[tkz upload] %zu merges, windows: mean left %.2f right %.2f, max left %u right %u (%s)\n", order.size(), sl_ / order.size(), sr_ / order.size(), ml, mr, blind ? "rank-blind" : "rank-aware");
                 }
             }
             TRY(upload(ctx, ctx->t_merge_win, win.data(), win.size() * 2));

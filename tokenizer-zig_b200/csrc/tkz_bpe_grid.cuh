@@ -230,7 +230,6 @@ __global__ void __launch_bounds__(BG_NT, 1) bpe_grid_kernel(const __grid_constan
     uint32_t step = 0;
     for (;; step++) {
         const uint32_t par = step & 1u;
-        uint32_t total_heads = 0;
         if (*(volatile uint32_t*)(a.gs + 1 + par) == 0u) break;                   // bpe.zig:232-234 for every word
         if (gt == 0) t0 = now();
         uint32_t* const ids = a.id[cur]; uint32_t* const rk = a.rk[cur]; uint32_t* const wd = a.wid[cur]; uint16_t* const win = a.win[cur];
@@ -427,7 +426,6 @@ __global__ void __launch_bounds__(BG_NT, 1) bpe_grid_kernel(const __grid_constan
             if (lane == 0 && nfin) atomicAdd(a.gs + 22 + (par ^ 1u), nfin);
             if (gt == 0 && step < 256) { a.dbg[4 * step] = n; a.dbg[4 * step + 1] = total; a.dbg[4 * step + 2] = (uint32_t)dth; }
             n -= total;
-            total_heads = total;
             cur = nxt;
         }
         grid.sync();
@@ -443,7 +441,6 @@ __global__ void __launch_bounds__(BG_NT, 1) bpe_grid_kernel(const __grid_constan
         // Scratch = the arrays of the other buffer: pair lists, dstep, hstep (step in which hn[i] was written).
         const uint32_t n_live = *(volatile uint32_t*)(a.gs + 22 + (par ^ 1u));
         if (gt == 0 && step < 256) a.dbg[1024 + step] = n_live;
-        (void)total_heads;
         if ((unsigned long long)n_live * BG_SPARSE_DIV < n && n_live != 0u) {
             const uint32_t nxt = cur ^ 1u;
             uint32_t* const ids2 = a.id[cur]; uint32_t* const rk2 = a.rk[cur]; uint32_t* const wd2 = a.wid[cur]; uint16_t* const win2 = a.win[cur];
@@ -465,7 +462,6 @@ __global__ void __launch_bounds__(BG_NT, 1) bpe_grid_kernel(const __grid_constan
             }
             grid.sync();
             uint32_t gstep = 0, li = 0, sp = par ^ 1u;
-            bool need_dense = false;
             auto dead = [&](uint32_t i) { const uint32_t d = dstep[i]; return d != 0u && d < gstep; };
             auto next_live = [&](uint32_t i) { do { i++; } while (i < n && dead(i)); return i; };                // n: none
             auto prev_live = [&](uint32_t i) { while (i > 0) { i--; if (!dead(i)) return i; } return (uint32_t)TKZ_NONE; };
@@ -503,7 +499,7 @@ __global__ void __launch_bounds__(BG_NT, 1) bpe_grid_kernel(const __grid_constan
                     a.hn[i] = hv; hstep[i] = gstep;
                 }
                 grid.sync();
-                if (*(volatile uint32_t*)(a.gs + 16 + (gstep & 1u)) != 0u) { need_dense = true; break; }
+                if (*(volatile uint32_t*)(a.gs + 16 + (gstep & 1u)) != 0u) break;
                 // A. apply the merges in place, ranks of the pairs they touch, next list + the word minima of the next step
                 for (uint32_t c0 = 0; c0 < len; c0 += gstride) {
                     const uint32_t idx = c0 + gt;
@@ -600,7 +596,6 @@ __global__ void __launch_bounds__(BG_NT, 1) bpe_grid_kernel(const __grid_constan
                 n -= total;
                 cur = nxt;
                 n_phases++;
-                (void)need_dense;
             }
             grid.sync();
             if (gt == 0) ts += now() - t0;

@@ -2,7 +2,7 @@
 """Per-SOURCE-LINE view of an ncu report: joins the SASS rows of `ncu --page source --csv` (samples, executed
 instructions, active threads) with the line table of the shipped library (`nvdisasm -g`), here on the CPU box.
 
-usage: python tools/ncu_lines.py gpurun_out/x.ncu-rep [--kernel REGEX] [--top N] [--lib path/to/lib.so]
+usage: python tools/ncu_lines.py gpurun_out/x.ncu-rep [--kernel REGEX] [--index N] [--top N] [--lib path/to/lib.so]
 
 The library must be the build that was profiled (the SASS rows are matched to the disassembly by position and opcode).
 """
@@ -59,6 +59,11 @@ def main():
     kre = arg("--kernel", "onepass_kernel")
     cmd = ["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name", f"regex:{kre}"]
     rows = list(csv.reader(subprocess.run(cmd, capture_output=True, text=True).stdout.splitlines()))
+    # several captured launches match: --index N picks the N-th (0-based) of them
+    starts = [k for k, r in enumerate(rows) if r and r[0] == "Kernel Name"]
+    if not starts:
+        sys.exit("no captured kernel matches --kernel")
+    rows = rows[starts[min(int(arg("--index", "0")), len(starts) - 1)]:]
     name = rows[0][1]
     hdr = rows[1]
     ci = {n: i for i, n in enumerate(hdr)}
