@@ -492,7 +492,7 @@ def test_grid_kernel_runs_empty_words_and_malformed_words(monkeypatch):
     t2.close()
 
 
-def test_grid_kernel_sparse_phase_falls_back_for_a_long_late_run():
+def test_grid_kernel_sparse_phase_falls_back_for_a_long_late_run(monkeypatch):
     """(a, a) has the highest rank: its runs wait until every other pair of the word is done, i.e. until the kernel is in its
     sparse in-place phase; a run longer than the sparse walk limit must send it back to the dense steps (run scan)."""
     rng = random.Random(99)
@@ -516,8 +516,16 @@ def test_grid_kernel_sparse_phase_falls_back_for_a_long_late_run():
             ("a" * 2100 + rnd(30000)).encode()]
     got = t.encode_batch(docs)
     assert t.stats().model_flags & 3 == 3
-    assert_same(got, o.encode_batch(docs, algo=1, threads=8))
+    ref = o.encode_batch(docs, algo=1, threads=8)
+    assert_same(got, ref)
     t.close()
+    # the same with a walk limit of 2: the phase changes (sparse -> compaction -> dense run scan -> sparse ...) happen dozens
+    # of times per launch (regression: a flag reset that raced with slower blocks still reading the flag)
+    monkeypatch.setenv("TKZ_GRID_SPARSE_WALK", "2")
+    for rep in range(3):
+        t2 = tz.Tokenizer.from_json(js, device=0)
+        assert_same(t2.encode_batch(docs + _huge_docs(rng, list("bcdefgha"), [15000, 40000], p_run=0.3)[:0]), ref, f"walk limit 2, repetition {rep}")
+        t2.close()
 
 
 def test_grid_kernel_on_the_skewed_corpus():

@@ -549,6 +549,9 @@ int launch_bpe(tkz_ctx* ctx, const DevModel& m, const uint8_t* d_text, const uin
         if (ok) {
             GridBpeArgs ga{};
             ga.text = d_text; ga.word_start = word_start; ga.word_end = word_end;
+            ga.sparse_div = BG_SPARSE_DIV; ga.sparse_walk = BG_SPARSE_WALK;
+            if (const char* e = getenv("TKZ_GRID_SPARSE_WALK")) ga.sparse_walk = (uint32_t)atoll(e);
+            if (const char* e = getenv("TKZ_GRID_SPARSE_DIV")) ga.sparse_div = (uint32_t)atoll(e);
             ga.hw = (const uint32_t*)ctx->a_huge_w.p; ga.hbase = (const uint32_t*)ctx->a_huge_base.p; ga.n_huge = (uint32_t)n_huge; ga.M = (uint32_t)M;
             uint8_t* p = (uint8_t*)ctx->a_grid_state.p;
             auto take = [&](size_t bytes) { uint8_t* r = p; p += bytes; return r; };

@@ -42,6 +42,8 @@ struct GridBpeArgs {
     const uint32_t* hw;                   // huge word h -> index in the word list            (n_huge)
     const uint32_t* hbase;                // huge word h -> first byte in the concatenation   (n_huge + 1, last = M)
     uint32_t n_huge, M;
+    uint32_t sparse_walk;                 // longest run walk of the sparse phase (TKZ_GRID_SPARSE_WALK)
+    uint32_t sparse_div;                  // sparse phase below n / sparse_div ranked pairs (0: dense steps only; TKZ_GRID_SPARSE_DIV)
     uint32_t* id[2]; uint32_t* s[2]; uint32_t* e[2]; uint32_t* rk[2]; uint32_t* wid[2]; uint16_t* win[2];
     uint32_t* hn;                         // per symbol: TKZ_NONE, BG_PENDING, or the new id of the pair it heads
     uint32_t* wmin[2];                    // per huge word: smallest pair rank (double-buffered by step parity)
@@ -441,7 +443,7 @@ __global__ void __launch_bounds__(BG_NT, 1) bpe_grid_kernel(const __grid_constan
         // Scratch = the arrays of the other buffer: pair lists, dstep, hstep (step in which hn[i] was written).
         const uint32_t n_live = *(volatile uint32_t*)(a.gs + 22 + (par ^ 1u));
         if (gt == 0 && step < 256) a.dbg[1024 + step] = n_live;
-        if ((unsigned long long)n_live * BG_SPARSE_DIV < n && n_live != 0u) {
+        if (a.sparse_div != 0u && (unsigned long long)n_live * a.sparse_div < n && n_live != 0u) {
             const uint32_t nxt = cur ^ 1u;
             uint32_t* const ids2 = a.id[cur]; uint32_t* const rk2 = a.rk[cur]; uint32_t* const wd2 = a.wid[cur]; uint16_t* const win2 = a.win[cur];
             uint32_t* const ev2 = a.e[cur];
@@ -490,7 +492,7 @@ __global__ void __launch_bounds__(BG_NT, 1) bpe_grid_kernel(const __grid_constan
                             const uint32_t pq = prev_live(q);
                             if (pq == TKZ_NONE || rk2[pq] == TKZ_BOUNDARY || ids2[pq] != x) break;
                             q = pq;
-                            if (++c > BG_SPARSE_WALK) { *(volatile uint32_t*)(a.gs + 16 + (gstep & 1u)) = 1u; break; }
+                            if (++c > a.sparse_walk) { *(volatile uint32_t*)(a.gs + 16 + (gstep & 1u)) = 1u; break; }
                         }
                         head = (c & 1u) == 0;
                     }
@@ -565,8 +567,10 @@ __global__ void __launch_bounds__(BG_NT, 1) bpe_grid_kernel(const __grid_constan
                 for (int d = 16; d > 0; d >>= 1) nd += __shfl_xor_sync(FULL, nd, d);
                 if (lane == 0) cnt[b * 32 + wq] = nd;
                 for (uint32_t w = gt; w < a.n_huge; w += gstride) { a.wmin[0][w] = TKZ_NONE; a.wmin[1][w] = TKZ_NONE; }
-                if (gt == 0) { a.gs[16] = 0; a.gs[17] = 0; a.gs[18] = 0; a.gs[19] = 0; a.gs[1] = 0; a.gs[2] = 0; }
+                if (gt == 0) { a.gs[1] = 0; a.gs[2] = 0; }
                 grid.sync();
+                // (only now: a block may still have been reading the run-scan flag / list length when block 0 got here)
+                if (gt == 0) { a.gs[16] = 0; a.gs[17] = 0; a.gs[18] = 0; a.gs[19] = 0; }
                 uint32_t before, total;
                 bg_prefix_total(cnt, G * 32, b * 32, red, before, total);
                 {

@@ -17,10 +17,15 @@ from tools import corpus, tokenizers_io                           # noqa: E402
 
 def main():
     mib = int(sys.argv[1]) if len(sys.argv) > 1 else 256
-    cases = [("gpt2_whitespace", "c2", None, None), ("llama3_whitespace", "c4", None, None),
-             ("bert_wordpiece", "c3", 512, {"length": 512, "pad_id": 0}), ("bert_wordpiece", "c3", None, None)]
-    for name, cname, trunc, pad in cases:
-        size = (mib << 20) if pad is None else min(mib, 64) << 20        # padded output is 8 KB per sentence
+    # (tokenizer, corpus, truncation, padding, oracle BPE variant, size cap in MiB): algo 0 = literal BPE.tokenize; the
+    # long-word workloads (whole documents, MiB-long words: block + grid kernels) need the fast-exact variant (algo 1,
+    # proven equal to algo 0 by tests/test_oracle_fast_exact.py) -- the literal one is O(n^2) per word
+    cases = [("gpt2_whitespace", "c2", None, None, 0, 1 << 20), ("llama3_whitespace", "c4", None, None, 0, 1 << 20),
+             ("bert_wordpiece", "c3", 512, {"length": 512, "pad_id": 0}, 0, 64), ("bert_wordpiece", "c3", None, None, 0, 1 << 20),
+             ("gpt2_bytelevel", "c2", None, None, 1, 512), ("gpt2_whitespace", "c5", None, None, 1, 512), ("gpt2_bytelevel", "c5", None, None, 1, 256),
+             ("llama3_sequence", "c4", None, None, 1, 256)]
+    for name, cname, trunc, pad, algo, cap in cases:
+        size = min(mib, cap) << 20                                       # (padded output is 8 KB per sentence)
         js = tokenizers_io.tokenizer_json(name)
         text, off = corpus.generate(cname, size, seed=4242)
         t = tz.Tokenizer.from_json(js, device=0)
@@ -30,10 +35,10 @@ def main():
         t.padding = pad
         o.padding = pad
         t0 = time.time(); got = t.encode_packed(text, off); t1 = time.time()
-        ref = o.encode_packed(text, off, algo=0, threads=os.cpu_count() or 1); t2 = time.time()
+        ref = o.encode_packed(text, off, algo=algo, threads=os.cpu_count() or 1); t2 = time.time()
         ok = all(np.array_equal(getattr(got, k), getattr(ref, k)) for k in ("doc_tok_off", "ids", "offsets", "attention_mask", "type_ids", "special_tokens_mask"))
         print(f"{name:20s} {cname} {size >> 20:5d} MiB trunc={trunc} pad={'yes' if pad else 'no'}: {len(ref.ids)} slots, gpu {t1 - t0:.2f} s, oracle {t2 - t1:.1f} s, "
-              f"path {t.stats().path}: {'EQUAL' if ok else 'MISMATCH'}", flush=True)
+              f"path {t.stats().path} flags {t.stats().model_flags} oracle algo {algo}: {'EQUAL' if ok else 'MISMATCH'}", flush=True)
         if not ok:
             sys.exit(1)
         t.close()

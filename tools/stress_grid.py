@@ -59,7 +59,10 @@ def main():
         for min_len in ("12289", "65"):
             os.environ["TKZ_GRID_MIN_LEN"] = min_len
             t = tz.Tokenizer.from_json(js, device=0)
-            got = t.encode_batch(docs)
+            try:
+                got = t.encode_batch(docs)
+            except tz.TokzigError as e:
+                print(f"seed {seed} TKZ_GRID_MIN_LEN={min_len}: GPU raised {e}; document lengths {[len(d) for d in docs]}"); sys.exit(1)
             flags = t.stats().model_flags
             t.close()
             if not (flags & 1):
