@@ -436,6 +436,8 @@ extern "C" int tkz_model_upload(tkz_ctx* ctx, const tkz_model_desc* d) {
                 // merges involve short symbols, so the pairs that merge in the first, populous steps get windows of 1-3 symbols
                 // (a rank-blind window is as wide as the longest token that ever joins the symbol: TKZ_WINDOWS=blind).
                 const bool blind = [] { const char* e = getenv("TKZ_WINDOWS"); return e && e[0] == 'b'; }();
+                const bool no_local_aa = [] { const char* e = getenv("TKZ_LOCAL_AA"); return e && e[0] == '0'; }();
+                m.local_aa = no_local_aa ? 0 : 1;
                 std::unordered_map<uint32_t, uint32_t> WL, WR;  // running max while the entries are visited in rank order
                 for (uint32_t sl : order) {
                     const MergeEnt& e = mtab[sl];
@@ -444,7 +446,10 @@ extern "C" int tkz_model_upload(tkz_ctx* ctx, const tkz_model_desc* d) {
                 for (uint32_t sl : order) {                    // ascending rank: WL / WR hold exactly the entries of lower rank
                     const MergeEnt& e = mtab[sl];
                     auto get = [](std::unordered_map<uint32_t, uint32_t>& mp, uint32_t k) { auto it = mp.find(k); return it == mp.end() ? 0u : it->second; };
-                    const uint32_t wl = get(WL, e.first), wr = get(WR, e.second);     // threats to `first` from its left, to `second` from its right
+                    uint32_t wl = get(WL, e.first), wr = get(WR, e.second);     // threats to `first` from its left, to `second` from its right
+                    // (A, A): the window is laid around the whole RUN of A and must also see an A that could still appear next
+                    // to the run (it would change which A pairs with which): such an A is built from at most nsym(A) symbols
+                    if (e.first == e.second && !no_local_aa) { wl = std::max(wl, ns(e.first)); wr = std::max(wr, ns(e.first)); }
                     if (wl > 250 || wr > 250) { proper = false; break; }
                     win[sl] = (uint16_t)(wl | (wr << 8));
                     if (!blind) { uint32_t& l = WL[e.second]; l = std::max(l, ns(e.first)); uint32_t& r = WR[e.first]; r = std::max(r, ns(e.second)); }

@@ -28,6 +28,8 @@
 
 namespace tkz {
 
+constexpr uint32_t BB_RUN_WALK = 32;        // equal-symbol runs up to this length are handled by the run-window rule
+
 struct BlockBpeArgs {
     const uint8_t* text;
     const uint32_t* word_start;
@@ -186,6 +188,25 @@ __global__ void __launch_bounds__(NT, MINB) bpe_block_kernel(DevModel m, BlockBp
                             for (uint32_t j = lo; j < i && head; j++) head = rk[j] >= r;
                             for (uint32_t j = i + 1; j <= hi && head; j++) head = rk[j] >= r;
                             // an equal rank inside the window is another occurrence of the same pair: it cannot overlap (a != b)
+                        } else if (r != TKZ_NONE && m.local_aa) {
+                            // (A, A): the window goes around the whole run of A (its extent is part of the decision: the run
+                            // pairs up from its start).  Nothing of lower rank left of the run within wl pairs, nor from the pair
+                            // of its last A on within wr pairs => no A of the run is consumed and no A joins it before round r
+                            // (the entry's window also covers nsym(A), see tkz_api.cu), so the run pairs up NOW as it will then.
+                            // Runs longer than BB_RUN_WALK wait for the round in which (A, A) is the word's minimum (below).
+                            const uint32_t x = ids[i];
+                            uint32_t s0 = i, e0 = i + 2, c = 0;
+                            while (c < BB_RUN_WALK && s0 > 0 && ids[s0 - 1] == x) { s0--; c++; }
+                            c = 0;
+                            while (c < BB_RUN_WALK && e0 < n && ids[e0] == x) { e0++; c++; }
+                            if (!(s0 > 0 && ids[s0 - 1] == x) && !(e0 < n && ids[e0] == x) && ((i - s0) & 1u) == 0) {
+                                const uint32_t wv = win[i], wl = wv & 0xFFu, wr = wv >> 8;
+                                const uint32_t lo = s0 > wl ? s0 - wl : 0;
+                                uint32_t hi = e0 - 2 + wr; if (hi > n - 2) hi = n - 2;
+                                head = true;
+                                for (uint32_t j = s0; j > lo && head;) { --j; head = rk[j] >= r; }
+                                for (uint32_t j = e0 - 1; j <= hi && head; j++) head = rk[j] >= r;
+                            }
                         }
                     }
                     flag[i] = head ? 1 : 0;

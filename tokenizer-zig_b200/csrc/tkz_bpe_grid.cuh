@@ -271,12 +271,29 @@ __global__ void __launch_bounds__(BG_NT, 1) bpe_grid_kernel(const __grid_constan
                             head = true;
                             for (uint32_t j = i; j > jlo && head;) { --j; const uint32_t rj = rk[j]; if (rj == TKZ_BOUNDARY) break; head = rj >= r; }
                             for (uint32_t j = i + 1; j <= jhi && head; j++) { const uint32_t rj = rk[j]; if (rj == TKZ_BOUNDARY) break; head = rj >= r; }
-                        } else if (r == a.wmin[par][wd[i]]) {
-                            // the reference round of this word: runs of x pair up from their start
-                            uint32_t j = i, c = 0;
-                            while (c < BG_WALK && j > 0 && rk[j - 1] != TKZ_BOUNDARY && ids[j - 1] == x) { j--; c++; }
-                            if (c == BG_WALK && j > 0 && rk[j - 1] != TKZ_BOUNDARY && ids[j - 1] == x) { hv[k] = BG_PENDING; pend = true; }
-                            else head = ((i - j) & 1u) == 0;
+                        } else {
+                            // (A, A).  A run that ends within BG_WALK symbols on both sides: the run-window rule of
+                            // tkz_bpe_block.cuh decides.  Longer runs wait for the reference round of their word.
+                            uint32_t s0 = i, e0 = i + 2, c = 0;
+                            while (c < BG_WALK && s0 > 0 && rk[s0 - 1] != TKZ_BOUNDARY && ids[s0 - 1] == x) { s0--; c++; }
+                            const bool lopen = s0 > 0 && rk[s0 - 1] != TKZ_BOUNDARY && ids[s0 - 1] == x;
+                            c = 0;
+                            while (c < BG_WALK && e0 < n && rk[e0 - 1] != TKZ_BOUNDARY && ids[e0] == x) { e0++; c++; }
+                            const bool ropen = e0 < n && rk[e0 - 1] != TKZ_BOUNDARY && ids[e0] == x;
+                            if (m.local_aa && !lopen && !ropen) {
+                                if (((i - s0) & 1u) == 0) {
+                                    const uint32_t wv = ((k < 2 ? w2.x : w2.y) >> ((k & 1) * 16)) & 0xFFFFu, wl = wv & 0xFFu, wr = wv >> 8;
+                                    const uint32_t jlo = s0 > wl ? s0 - wl : 0;
+                                    uint32_t jhi = e0 - 2 + wr; if (jhi > n - 2) jhi = n - 2;
+                                    head = true;
+                                    for (uint32_t j = s0; j > jlo && head;) { --j; const uint32_t rj = rk[j]; if (rj == TKZ_BOUNDARY) break; head = rj >= r; }
+                                    for (uint32_t j = e0 - 1; j <= jhi && head; j++) { const uint32_t rj = rk[j]; if (rj == TKZ_BOUNDARY) break; head = rj >= r; }
+                                }
+                            } else if (r == a.wmin[par][wd[i]]) {
+                                // the reference round of this word: runs of x pair up from their start
+                                if (lopen) { hv[k] = BG_PENDING; pend = true; }
+                                else head = ((i - s0) & 1u) == 0;
+                            }
                         }
                         if (head) { uint32_t nid = 0; merge_rank_lookup(m, x, y, &nid); hv[k] = nid; heads++; }
                     }
@@ -486,15 +503,43 @@ __global__ void __launch_bounds__(BG_NT, 1) bpe_grid_kernel(const __grid_constan
                         for (uint32_t c = 0; c < wl && head; c++) { q = prev_live(q); if (q == TKZ_NONE) break; const uint32_t rq = rk2[q]; if (rq == TKZ_BOUNDARY) break; head = rq >= r; }
                         q = i;
                         for (uint32_t c = 0; c < wr && head; c++) { q = next_live(q); if (q >= n) break; const uint32_t rq = rk2[q]; if (rq == TKZ_BOUNDARY) break; head = rq >= r; }
-                    } else if (r == a.wmin[sp][wd2[i]]) {
-                        uint32_t q = i, c = 0;
+                    } else {
+                        // (A, A): run-window rule for runs that end within BG_WALK symbols on both sides, else the word's round
+                        uint32_t s0 = i, last = j, c = 0, c2 = 0;
+                        bool lopen = false, ropen = false;
                         for (;;) {
-                            const uint32_t pq = prev_live(q);
+                            const uint32_t pq = prev_live(s0);
                             if (pq == TKZ_NONE || rk2[pq] == TKZ_BOUNDARY || ids2[pq] != x) break;
-                            q = pq;
-                            if (++c > a.sparse_walk) { *(volatile uint32_t*)(a.gs + 16 + (gstep & 1u)) = 1u; break; }
+                            if (c == BG_WALK) { lopen = true; break; }
+                            s0 = pq; c++;
                         }
-                        head = (c & 1u) == 0;
+                        for (;;) {
+                            if (rk2[last] == TKZ_BOUNDARY) break;
+                            const uint32_t nq = next_live(last);
+                            if (nq >= n || ids2[nq] != x) break;
+                            if (c2 == BG_WALK) { ropen = true; break; }
+                            last = nq; c2++;
+                        }
+                        if (m.local_aa && !lopen && !ropen) {
+                            if ((c & 1u) == 0) {
+                                const uint32_t wv = win2[i], wl = wv & 0xFFu, wr = wv >> 8;
+                                head = true;
+                                uint32_t q = s0;
+                                for (uint32_t d = 0; d < wl && head; d++) { q = prev_live(q); if (q == TKZ_NONE) break; const uint32_t rq = rk2[q]; if (rq == TKZ_BOUNDARY) break; head = rq >= r; }
+                                q = last;
+                                for (uint32_t d = 0; d < wr && head; d++) { const uint32_t rq = rk2[q]; if (rq == TKZ_BOUNDARY) break; head = rq >= r; q = next_live(q); if (q >= n) break; }
+                            }
+                        } else if (r == a.wmin[sp][wd2[i]]) {
+                            // the reference round of this word; the parity of a long run needs the whole distance to its start
+                            uint32_t q = s0;
+                            for (;;) {
+                                const uint32_t pq = prev_live(q);
+                                if (pq == TKZ_NONE || rk2[pq] == TKZ_BOUNDARY || ids2[pq] != x) break;
+                                q = pq;
+                                if (++c > a.sparse_walk) { *(volatile uint32_t*)(a.gs + 16 + (gstep & 1u)) = 1u; break; }
+                            }
+                            head = (c & 1u) == 0;
+                        }
                     }
                     uint32_t hv = TKZ_NONE;
                     if (head) merge_rank_lookup(m, x, y, &hv);
