@@ -9,14 +9,21 @@
 // lower rank than every merge that CONSUMES it.  Then
 //   (1) a pair created by the merge of rank r has a rank > r, so the round order equals strict rank order: an occurrence
 //       (a,b) of rank r gets merged unless a or b is consumed earlier by a merge of rank < r;
-//   (2) a can only be consumed from the left by a merge (X,a) whose X is built, by merges of rank < r, from the symbols
-//       directly left of a; X spans at most WL[a] = max nsym(X) over all table entries (X,a) current symbols, and the FIRST
-//       merge of that chain is a pair that is present NOW, inside that span, with rank < r.  Symmetrically for b (WR[b]).
-// So an occurrence at position i with rank r may merge immediately when no present pair in [i-WL[a], i+WR[b]] has a smaller
+//   (2) a can only be consumed from the left, BEFORE round r, by a merge (X,a) of rank < r whose X is built, by merges of
+//       even lower rank, from the symbols directly left of a; X spans at most wl = max nsym(X) over the table entries (X,a)
+//       of rank < r current symbols, and the FIRST merge of that chain is a pair that is present NOW, inside that span, with
+//       rank < r.  Symmetrically for b (wr over the entries (b,Z) of rank < r).  The windows are stored per table entry
+//       (merge_win, built in tkz_api.cu); early merges join short symbols, so low ranks have windows of 1-3 symbols.
+// So an occurrence at position i with rank r may merge immediately when no present pair in [i-wl, i+wr] has a smaller
 // rank ("windowed local minimum") -- every such occurrence of the whole word merges in the same step.  The global minimum
-// always qualifies, so every step makes progress; typical text needs a few dozen steps independent of the word length.
-// Pairs of two equal symbols (runs: aaaaa -> aa aa a pairs up from the run start) only merge when their rank is the word's
-// global minimum, by run parity, exactly like a reference round.
+// always qualifies, so every step makes progress; typical text needs one or two dozen steps independent of the word length.
+// Pairs of two equal symbols (A,A) are decided per RUN of A, because a run pairs up from its start (aaaaa -> aa aa a):
+//   * run-window rule (runs up to BB_RUN_WALK symbols): nothing of lower rank within wl pairs left of the run's first A, nor
+//     within wr pairs from the pair of its last A on, where the entry's wl / wr also cover nsym(A) -- the span from which an A
+//     that would join the run and shift the pairing could still be built.  Then the run is the same run in round r and is
+//     paired up now, every second pair from its start;
+//   * longer runs wait for the step in which (A,A) is the minimum rank of the whole word: exactly the reference round (run
+//     starts by a block-wide max-scan; every other pair waits that step).
 // Tables that are not proper (or have windows > 250) never reach this kernel: bpe_warp_kernel keeps the literal rounds.
 //
 // State per current symbol: id, index of its first initial symbol, cached rank + window of the pair with its right

@@ -9,14 +9,19 @@
 //
 // Reference semantics: src/model/bpe.zig:185-211 (initial symbols), :214-253 (merge rounds), :256-260 (tokens).  The
 // schedule is exact for PROPER merge tables (see tkz_bpe_block.cuh for the argument; improper tables never get here):
-//   * a pair (a, b), a != b, of rank r merges as soon as no present pair inside its window [i - WL[a], i + WR[b]] has a
-//     smaller rank; windows never reach into a neighbouring word (the pair behind a word's last symbol carries the
+//   * a pair (a, b), a != b, of rank r merges as soon as no present pair inside its (rank-aware) window [i - wl, i + wr]
+//     has a smaller rank; windows never reach into a neighbouring word (the pair behind a word's last symbol carries the
 //     reserved rank TKZ_BOUNDARY and stops the scan);
-//   * a pair of two equal symbols (A, A) merges only when its rank is the minimum over its whole word -- exactly the
-//     reference's current round for that word -- and then every run of A pairs up from its start (bpe.zig:236-251:
-//     "do not advance i after a merge" never re-matches because new_id != A in a proper table).  Run starts: a bounded
-//     walk to the left; runs longer than BG_WALK symbols are resolved by a grid-wide max-scan of run boundaries.
-//     Other windowed heads of the same word merge in the same step: none of them has the (A, A) pair in its window.
+//   * a pair of two equal symbols (A, A) in a run of up to BG_WALK symbols follows the run-window rule of
+//     tkz_bpe_block.cuh; in a longer run it merges only when its rank is the minimum over its whole word -- exactly the
+//     reference's current round for that word -- and then the run pairs up from its start (bpe.zig:236-251: "do not
+//     advance i after a merge" never re-matches because new_id != A in a proper table); starts of long runs come from a
+//     grid-wide max-scan of run boundaries.  Other heads of the same word merge in the same step: none of them has the
+//     (A, A) pair in its window.
+// Steps: DENSE (two streaming passes H / K over the whole array, K compacts into the other buffer and re-ranks the pairs
+// a merge touched) while many pairs still have a rank, then SPARSE (pair list, merges in place, dead marks) -- see the
+// comments at the two loops.  Flags that steer all blocks are double-buffered by step parity and reset only a full grid
+// barrier after their last reader.
 //
 // State per live symbol, ping-ponged between two buffers by the compaction of every step: id, byte offsets (start, end)
 // inside the word, cached rank + window of the pair with the right neighbour, index of the word.  Words with malformed
