@@ -39,7 +39,7 @@
 namespace tkz {
 
 constexpr int TW_THREADS = 256, TW_WARPS = 8, TW_SEG = 32, TW_SLICE = 32 * TW_SEG;      // slice = 1 KiB = one 32-byte segment per lane
-constexpr int TW_BLOCKS_PER_SM = 4;                // pass A: 64 registers per thread, 53 KB of shared memory per block (5 / 6 blocks spill: slower)
+constexpr int TW_BLOCKS_PER_SM = 4;                // pass A: 64 registers per thread, 38 KB of shared memory per block (5 / 6 blocks spill: slower)
 constexpr uint32_t TW_ENT_CHUNK = 4096;            // entries a warp claims from the entry list with one atomic (then sub-allocates)
 constexpr uint32_t TW_MAX_SHORT = 15;             // bytes next to the length byte in the 128-bit key
 constexpr uint32_t TW_MAX_MED = 64;               // words of 32..64 bytes: 64-bit tag + byte verification; symbols fit shared memory
@@ -100,8 +100,9 @@ struct __align__(16) SliceShared {                                      // per w
     uint32_t text32[(TW_SLICE + 32) / 4 + 4];             // normalised slice + 32 halo bytes
     uint32_t cont32[(TW_SLICE + 32) / 32 + 2];            // bit p: byte p continues the word that started before it
     uint32_t docbits[(TW_SLICE + 32) / 32 + 2];           // bit p: a document starts at slice_base + p
-    uint16_t wlist[TW_SLICE];                             // start positions of the slice's words (bit 15: ISOLATE byte)
-    uint16_t wpfx[TW_SLICE];                              // tokens of the slice's words before word k
+    uint16_t wlist[TW_SLICE];                             // start positions of the slice's words (bit 15: ISOLATE byte); a round
+                                                          // replaces the entries it has read by the token prefix of its words
+                                                          // (tokens of the slice's words before word k, read by the epilogue)
     uint32_t mscr[4][TW_MAX_MED];                         // model scratch: ids, starts, ends, pair ranks
     uint32_t wbytes[TW_MAX_MED / 4];                      // normalised bytes of the word the warp is tokenizing
     uint32_t seg_smask[32], seg_wex[32];                  // per 32-byte segment: word-start bits, words of the slice before it
@@ -121,6 +122,13 @@ __device__ __forceinline__ void tw_ld256(const WordSlot* s, uint32_t (&r)[8]) {
 __device__ __forceinline__ void tw_ld256_cg(const void* s, uint32_t (&r)[8]) {
     asm volatile("ld.global.cg.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                  : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "l"(s) : "memory");
+}
+// text is read once: 16-byte loads that do not allocate in L1, which the 212 KB of shared memory leave small and which
+// the word-table probes need (ncu, r01_v40: 22 % L1 hit rate of the global loads with allocating text loads)
+__device__ __forceinline__ uint4 tw_ld_text16(const uint8_t* p) {
+    uint4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
 }
 __device__ __forceinline__ uint2 tw_ld_value(const WordSlot* s) {
     uint2 v;
@@ -201,7 +209,7 @@ __device__ __forceinline__ void tw_load_segment(const uint8_t* __restrict__ text
         uint32_t raw[4] = {0, 0, 0, 0};
         uint32_t valid = 0;
         if (hb + 16 <= n) {
-            const uint4 v = __ldg(reinterpret_cast<const uint4*>(text + hb));
+            const uint4 v = tw_ld_text16(text + hb);
             raw[0] = v.x; raw[1] = v.y; raw[2] = v.z; raw[3] = v.w; valid = 0xFFFFu;
         } else {
             for (int k = 0; k < 16; k++) if (hb + k < n) { raw[k >> 2] |= (uint32_t)__ldg(text + hb + k) << ((k & 3) * 8); valid |= 1u << k; }
@@ -725,7 +733,7 @@ __global__ void __launch_bounds__(TW_THREADS, TW_BLOCKS_PER_SM) slice_words_kern
             uint32_t ex, tot;
             if (!__any_sync(FULL, nt > 3)) ex = tw_ballot_prefix<2>(nt, lt_mask, tot);
             else { const uint32_t inc = warp_incl_scan(nt); ex = inc - nt; tot = __shfl_sync(FULL, inc, 31); }
-            if (have) sh.wpfx[k] = (uint16_t)(run + ex);
+            if (have) sh.wlist[k] = (uint16_t)(run + ex);      // (the round's wlist entries were read at its top, before the votes)
             run += tot;
         }
         if (lane == 0) {
@@ -741,7 +749,7 @@ __global__ void __launch_bounds__(TW_THREADS, TW_BLOCKS_PER_SM) slice_words_kern
                 const uint32_t q = (uint32_t)(__ldg(a.doc_off + d) - (uint64_t)s * TW_SLICE);
                 const uint32_t sg = q >> 5;
                 const uint32_t idx = sh.seg_wex[sg] + __popc(sh.seg_smask[sg] & ((1u << (q & 31u)) - 1u));
-                a.doc_tok_local[d] = idx < nW ? (uint32_t)sh.wpfx[idx] : run;
+                a.doc_tok_local[d] = idx < nW ? (uint32_t)sh.wlist[idx] : run;
                 a.doc_word_ref[d] = idx;
             }
         }
