@@ -130,6 +130,13 @@ __device__ __forceinline__ uint4 tw_ld_text16(const uint8_t* p) {
     asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
     return v;
 }
+// entries are read once by pass B: no L1 allocation, the L1 is kept for the token records of frequent multi-token words
+// (measured neutral on c2b: pass B is issue / DRAM-write bound, 1.61 ms either way)
+__device__ __forceinline__ uint2 tw_ld_entry(const uint2* p) {
+    uint2 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
+    return v;
+}
 __device__ __forceinline__ uint2 tw_ld_value(const WordSlot* s) {
     uint2 v;
     asm volatile("ld.global.relaxed.gpu.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(&s->a) : "memory");
@@ -854,11 +861,11 @@ __global__ void __launch_bounds__(TW_THREADS, 6) slice_emit_kernel(const __grid_
         uint32_t carry = base;                                  // global real-token index of the next token
         uint32_t fill = 0; unsigned long long gstart = base;     // staging: tokens staged, global index of the first one
         uint2 e_next = make_uint2(0u, 0u);
-        if (lane < nw) e_next = __ldg(ent + lane);
+        if (lane < nw) e_next = tw_ld_entry(ent + lane);
         for (uint32_t k0 = 0; k0 < nw; k0 += 32) {
             const uint32_t k = k0 + lane;
             const uint32_t ea = e_next.x, ey = k < nw ? e_next.y : 0u;
-            if (k + 32 < nw) e_next = __ldg(ent + k + 32);        // next round's entries are in flight while this round is emitted
+            if (k + 32 < nw) e_next = tw_ld_entry(ent + k + 32);  // next round's entries are in flight while this round is emitted
             else if (k0 + 32 >= nw && s + stride < a.n_slices && lane < 4)   // last round: pull the next slice's entries into L2
                 asm volatile("prefetch.global.L2 [%0];" :: "l"(a.ent + __shfl_sync(0xFu, meta, 1) + lane * 16));
             uint32_t nt = 0;
@@ -871,7 +878,7 @@ __global__ void __launch_bounds__(TW_THREADS, 6) slice_emit_kernel(const __grid_
             // multi-token words: the first two records are requested now and land while the scan runs
             const bool pooled = nt && (ey & (TW_POOLF | TW_LONGF)) == TW_POOLF;
             unsigned long long r0 = 0, r1 = 0;
-            if (pooled) { r0 = __ldcg(a.upool + ea); if (nt > 1) r1 = __ldcg(a.upool + ea + 1); }
+            if (pooled) { r0 = __ldg(a.upool + ea); if (nt > 1) r1 = __ldg(a.upool + ea + 1); }
             const uint32_t inc = warp_incl_scan(nt);
             const uint32_t ex = inc - nt, tot = __shfl_sync(FULL, inc, 31);
             const bool is_long = (ey & TW_LONGF) != 0;
@@ -887,7 +894,7 @@ __global__ void __launch_bounds__(TW_THREADS, 6) slice_emit_kernel(const __grid_
                             st.id[si] = (uint32_t)r0; st.of[si] = (uint32_t)(r0 >> 32);
                             if (nt > 1) { st.id[si + 1] = (uint32_t)r1; st.of[si + 1] = (uint32_t)(r1 >> 32); }
                             for (uint32_t i = 2; i < nt; i++) {
-                                const unsigned long long r = __ldcg(a.upool + ea + i);
+                                const unsigned long long r = __ldg(a.upool + ea + i);
                                 st.id[si + i] = (uint32_t)r; st.of[si + i] = (uint32_t)(r >> 32);
                             }
                         }
@@ -915,7 +922,7 @@ __global__ void __launch_bounds__(TW_THREADS, 6) slice_emit_kernel(const __grid_
                 if (cnt && !is_long) {
                     if (!(ey & TW_POOLF)) emit_real(p, o, dst, ea, ey & 0xFFu, (ey >> 8) & 0xFFu);
                     else for (uint32_t i = 0; i < cnt; i++) {
-                        const unsigned long long r = __ldcg(a.upool + ea + i);
+                        const unsigned long long r = __ldg(a.upool + ea + i);
                         emit_real(p, o, dst + i, (uint32_t)r, (uint32_t)(r >> 32) & 0xFFFFu, (uint32_t)(r >> 48));
                     }
                 }
