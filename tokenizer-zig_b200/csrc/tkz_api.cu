@@ -576,9 +576,12 @@ int launch_bpe(tkz_ctx* ctx, const DevModel& m, const uint8_t* d_text, const uin
             ga.word_ntok = word_ntok; ga.done = (uint8_t*)ctx->a_huge_done.p;
             DevModel mm = m;
             void* args[] = {(void*)&mm, (void*)&ga};
-            CK(cudaLaunchCooperativeKernel((void*)bpe_grid_kernel, dim3((unsigned)ctx->grid_blocks), dim3(BG_NT), args, 0, st));
-            launches++;
-            if (getenv("TKZ_GRID_DEBUG")) {
+            // (a refused cooperative launch -- e.g. not all blocks can be co-resident on a partitioned device -- is not an
+            // error: the block kernel below then takes every word, as with TKZ_NO_GRID=1)
+            const cudaError_t le = cudaLaunchCooperativeKernel((void*)bpe_grid_kernel, dim3((unsigned)ctx->grid_blocks), dim3(BG_NT), args, 0, st);
+            if (le != cudaSuccess) { cudaGetLastError(); ok = false; }
+            else launches++;
+            if (ok && getenv("TKZ_GRID_DEBUG")) {
                 uint32_t gsh[32];
                 cudaStreamSynchronize(st);
                 cudaMemcpy(gsh, ga.gs, sizeof gsh, cudaMemcpyDeviceToHost);
@@ -592,8 +595,7 @@ int launch_bpe(tkz_ctx* ctx, const DevModel& m, const uint8_t* d_text, const uin
                         fprintf(stderr, "[tkz grid]   step %3u  n %10u  heads %9u  ranked pairs after %9u  H %7.3f ms  K %7.3f ms\n", k, d[4 * k], d[4 * k + 1], d[1024 + k], d[4 * k + 2] * 1e-6, d[4 * k + 3] * 1e-6);
                 }
             }
-            b.skip = (const uint8_t*)ctx->a_huge_done.p;
-            ctx->grid_used = true;
+            if (ok) { b.skip = (const uint8_t*)ctx->a_huge_done.p; ctx->grid_used = true; }
         }
     }
     // One class per shared-memory footprint (15 B per symbol of capacity): an SM holds ~14 k symbols of state whatever the
