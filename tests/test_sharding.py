@@ -37,6 +37,41 @@ def test_skewed_corpus_balance():
     assert sizes.max() / sizes.mean() < 1.05
 
 
+def test_document_costs_match_a_brute_force_and_balance_the_skewed_corpus():
+    """bytes are not equally expensive on the c5 corpus (unbroken words of KiBs..MiBs go through the block / grid
+    kernels at 20-36x the time per byte): the shard cut by modelled cost is never worse than the cut by bytes."""
+    import re
+    text, off = corpus.generate("c5", 64 << 20, 11)
+    cost = tz.document_costs(text, off)
+    b = text.tobytes()
+    for d in list(range(0, len(off) - 1, 7))[:120]:
+        doc = b[int(off[d]):int(off[d + 1])]
+        want = float(len(doc))
+        for m in re.finditer(rb"[^ \t\n\r]+", doc):
+            n = len(m.group(0))
+            want += (tz.COST_HUGE_WORD - 1) * n if n > 12288 else ((tz.COST_LONG_WORD - 1) * n if n > 64 else 0.0)
+        assert abs(cost[d] - want) < 1e-6 * max(want, 1.0), d
+    whole = tz.document_costs(text, off, b"")                      # no pre-tokenizer: the document is the word
+    lens = np.diff(off.astype(np.int64))
+    assert np.allclose(whole, lens * np.where(lens > 12288, tz.COST_HUGE_WORD, np.where(lens > 64, tz.COST_LONG_WORD, 1.0)))
+    acc = np.concatenate([[0.0], np.cumsum(cost)])
+    imb = {}
+    for world in (2, 4, 8):
+        for name, c in (("bytes", None), ("cost", cost)):
+            bb = tz.shard_bounds(off, world, c)
+            assert bb[0] == 0 and bb[-1] == len(off) - 1 and np.all(np.diff(bb) >= 0)
+            per = acc[bb[1:]] - acc[bb[:-1]]
+            imb[name, world] = per.max() / per.mean()             # slowest shard over the mean, in modelled time
+    # (contiguous cuts at document boundaries: a single 4 MiB word is a floor neither cut can go below)
+    assert imb["cost", 4] < 0.9 * imb["bytes", 4] and imb["cost", 8] < 0.8 * imb["bytes", 8], imb
+    assert imb["cost", 2] <= imb["bytes", 2] + 0.01, imb
+    # an ordinary corpus: cost == bytes up to the rare long word, the cuts barely move
+    text2, off2 = corpus.generate("c2", 8 << 20, 5)
+    c2 = tz.document_costs(text2, off2)
+    assert c2.sum() < 1.05 * int(off2[-1])
+    assert np.abs(tz.shard_bounds(off2, 8, c2) - tz.shard_bounds(off2, 8)).max() <= max(8, (len(off2) - 1) // 50)
+
+
 def _worker(rank, world, port, q):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     import torch

@@ -508,26 +508,74 @@ class Tokenizer:
 
 
 # --------------------------------------------------------------------------- multi-GPU sharding (host logic, no collective)
-def shard_bounds(doc_off: np.ndarray, n_shards: int) -> np.ndarray:
-    """Byte-balanced contiguous document ranges (north star: "sharded ... by byte-balanced ranges with no collective"):
-    shard k takes documents [b[k], b[k+1]), cut at the document boundary nearest to k * total / n_shards."""
+# Modelled device time per input byte, relative to ordinary text (B200, round 1: c2b 5.2 ms / GiB; pre-tokens of 65 B .. 12 KiB
+# in the windowed block kernels 104 ms / GiB (c2a); longer ones on the cooperative grid 43 ms per 245 MB (c5b)).
+COST_LONG_WORD = 20.0
+COST_HUGE_WORD = 36.0
+
+
+def document_costs(text: np.ndarray, doc_off: np.ndarray, delimiters: bytes = b" \t\n\r") -> np.ndarray:
+    """Modelled encode cost per document, in units of "one byte of ordinary text" ("cost model (bytes x per-bucket
+    factor)" for skewed corpora): bytes + (COST_LONG_WORD - 1) x bytes in pre-tokens of 65..12288 bytes + (COST_HUGE_WORD - 1)
+    x bytes in longer ones.  `delimiters` = the bytes the pre-tokenizer drops (b"" = no pre-tokenizer: a document is one
+    pre-token).  Host-side helper for cutting shards; plain numpy over the text, nothing is encoded."""
+    text = np.asarray(text, dtype=np.uint8)
+    doc_off = np.asarray(doc_off, dtype=np.int64)
+    nd = len(doc_off) - 1
+    lens = np.diff(doc_off).astype(np.float64)
+    if nd == 0:
+        return lens
+    if len(delimiters) == 0:
+        wlen, wdoc = np.diff(doc_off), np.arange(nd)
+    else:
+        base, end_ = int(doc_off[0]), int(doc_off[-1])
+        is_delim = np.zeros(256, dtype=bool)
+        is_delim[np.frombuffer(delimiters, dtype=np.uint8)] = True
+        nb = ~is_delim[text[base:end_]]                                       # byte belongs to a word
+        n = len(nb)
+        first = np.zeros(n, dtype=bool); last = np.zeros(n, dtype=bool)     # first / last byte of a document
+        nonempty = doc_off[1:] > doc_off[:-1]
+        first[doc_off[:-1][nonempty] - base] = True
+        last[doc_off[1:][nonempty] - 1 - base] = True
+        prev = np.zeros(n, dtype=bool); prev[1:] = nb[:-1]
+        nxt = np.zeros(n, dtype=bool); nxt[:-1] = nb[1:]
+        s_idx = np.flatnonzero(nb & (~prev | first))                          # a word starts behind a delimiter or a document start
+        e_idx = np.flatnonzero(nb & (~nxt | last))
+        wlen = e_idx - s_idx + 1
+        sel = wlen > 64                                                       # only long words change the cost
+        wlen = wlen[sel]
+        wdoc = np.searchsorted(doc_off, s_idx[sel] + base, side="right") - 1
+    extra = np.where(wlen > 12288, COST_HUGE_WORD - 1.0, np.where(wlen > 64, COST_LONG_WORD - 1.0, 0.0)) * wlen
+    keep = (extra > 0) & (wdoc >= 0) & (wdoc < nd)
+    return lens + np.bincount(wdoc[keep], weights=extra[keep], minlength=nd)[:nd]
+
+
+def shard_bounds(doc_off: np.ndarray, n_shards: int, cost: np.ndarray = None) -> np.ndarray:
+    """Balanced contiguous document ranges (north star: "sharded ... by byte-balanced ranges with no collective"):
+    shard k takes documents [b[k], b[k+1]), cut at the document boundary nearest to k * total / n_shards.  The measure is
+    bytes, or `cost` (one value per document, e.g. `document_costs`) for corpora whose bytes are not equally expensive."""
     doc_off = np.asarray(doc_off, dtype=np.uint64)
     nd = len(doc_off) - 1
-    total = int(doc_off[-1]) - int(doc_off[0])
+    if cost is not None:
+        acc = np.zeros(nd + 1, dtype=np.float64)
+        np.cumsum(np.asarray(cost, dtype=np.float64), out=acc[1:])
+    else:
+        acc = doc_off.astype(np.float64) - float(doc_off[0])
+    total = float(acc[-1])
     b = np.zeros(n_shards + 1, dtype=np.int64)
     for k in range(1, n_shards):
-        target = int(doc_off[0]) + (total * k) // n_shards
-        i = int(np.searchsorted(doc_off, target, side="left"))
-        if i > 0 and i <= nd and (target - int(doc_off[i - 1])) < (int(doc_off[min(i, nd)]) - target):
+        target = total * k / n_shards
+        i = int(np.searchsorted(acc, target, side="left"))
+        if i > 0 and i <= nd and (target - acc[i - 1]) < (acc[min(i, nd)] - target):
             i -= 1
         b[k] = max(b[k - 1], min(i, nd))
     b[n_shards] = nd
     return b
 
 
-def shard(text: np.ndarray, doc_off: np.ndarray, rank: int, world: int):
+def shard(text: np.ndarray, doc_off: np.ndarray, rank: int, world: int, cost: np.ndarray = None):
     """The (text, doc_off) slice rank `rank` of `world` encodes; offsets rebased to 0."""
-    b = shard_bounds(doc_off, world)
+    b = shard_bounds(doc_off, world, cost)
     lo, hi = int(b[rank]), int(b[rank + 1])
     base = int(doc_off[lo])
     return text[base:int(doc_off[hi])], (np.asarray(doc_off[lo:hi + 1], dtype=np.uint64) - np.uint64(base)), (lo, hi)
