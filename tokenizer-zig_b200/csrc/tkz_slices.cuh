@@ -499,7 +499,8 @@ __device__ __forceinline__ WholeWarpOut tw_own_word(const DevModel& m, const Sli
     return out;
 }
 
-// pass A: one warp per 512-byte slice, slices strided over all warps of the grid
+// pass A: one warp per 1 KiB slice, slices strided over all warps of the grid (4 blocks of 8 warps per SM: 64 registers, 38 KB of
+// shared memory per block, which leaves ~90 KB of L1 for the word-table probes)
 template <int MODEL, bool NORM_ID, bool HAS_ISO>
 __global__ void __launch_bounds__(TW_THREADS, TW_BLOCKS_PER_SM) slice_words_kernel(const __grid_constant__ DevModel m, const __grid_constant__ SliceArgs a) {
     extern __shared__ __align__(32) unsigned char tw_smem_raw[];
