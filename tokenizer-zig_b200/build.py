@@ -49,7 +49,8 @@ def build(force=False, verbose=False):
         obj = os.path.join(LIB_DIR, os.path.basename(src) + ".o")
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-Wall", "-c", src, "-o", obj])
         objs.append(obj)
-    subprocess.check_call([NVCC, *ARCH, "-shared", "-o", SO, *objs, "-cudart", "static"])
+    # the CUDA runtime is linked dynamically (the image and torch both ship libcudart.so.12): nothing of the runtime is embedded in the artefact
+    subprocess.check_call([NVCC, *ARCH, "-shared", "-o", SO, *objs, "-cudart", "shared", "-Xlinker", "-rpath=/usr/local/cuda/lib64"])
     if os.path.exists(AR):
         os.remove(AR)
     subprocess.check_call(["ar", "rcs", AR, *objs])
