@@ -94,6 +94,11 @@ typedef struct tkz_model_desc {
 #define TKZ_OUT_TYPE_IDS 8u
 #define TKZ_OUT_SPECIAL 16u
 #define TKZ_OUT_ALL 31u
+/* Offsets as ONE u16 per token (start | end << 8) in tkz_batch_result.offsets_packed instead of two u32: possible because
+ * the reference's offsets are relative to the pre-token (src/lib.zig:133-137), delivered when every pre-token of the batch
+ * is shorter than 256 bytes.  A batch with a longer pre-token (or a tokenizer without pre-tokenizer) falls back to
+ * TKZ_OUT_OFFSETS for the whole call: exactly one of offsets / offsets_packed is then non-NULL. */
+#define TKZ_OUT_OFFSETS_PACKED 32u
 
 /* Per-call knobs = the public fields Tokenizer.truncation / Tokenizer.padding (src/lib.zig:41-42,149-157;
  * src/types.zig:39-45,55-59).  stride / strategy / pad_token are ignored by the reference's encode. */
@@ -123,6 +128,7 @@ typedef struct tkz_batch_result {
     const uint32_t* type_ids;
     const uint32_t* special_tokens_mask;
     int64_t err_doc;                    /* document index of the first error, -1 if none */
+    const uint16_t* offsets_packed;     /* n_tokens x (start | end << 8), see TKZ_OUT_OFFSETS_PACKED; padding slots are 0 */
 } tkz_batch_result;
 
 /* counters of the last encode (FastTokenizer.arenaMemoryUsage analogue, src/lib.zig:451-453) */
@@ -138,8 +144,8 @@ typedef struct tkz_stats {
     float ms_scan;                      /* prefix sums: tokens per word -> per document -> CSR */
     float ms_emit;                      /* K5: fused truncate / pad / output write */
     float ms_total;                     /* first kernel to last kernel */
-    uint32_t model_flags;               /* bit 0: merge table proven "proper" -> long words use the windowed block kernels; bit 1: the last encode ran the grid-wide kernel on huge words */
-    uint32_t path;                      /* pipeline of the last encode: 0 per-occurrence, 1 dedup multi-pass, 2 tile pipeline
+    uint32_t model_flags;               /* bit 0: merge table proven "proper" -> long words use the windowed block kernels; bit 1: the last encode ran the grid-wide kernel on huge words; bit 2: it re-ran the slice pipeline with worst-case capacities */
+    uint32_t path;                      /* pipeline of the last encode: 0 per-occurrence, 2 slice pipeline
                                            (then ms_split = pass A, ms_model = word-list kernels, ms_emit = pass B) */
 } tkz_stats;
 

@@ -30,24 +30,24 @@ def assert_same(got: tz.BatchEncoding, ref: orc.BatchEncoding, what=""):
     assert np.array_equal(got.special_tokens_mask, ref.special_tokens_mask), f"{what}: special_tokens_mask"
 
 
-MODES = ("slices", "multipass", "occurrence")
+MODES = ("slices", "lut", "occurrence")
 
 
 def pair(js, dedup=True, mode=None):
     """(GPU tokenizer, oracle).  The context reads its pipeline switches when it is created: mode "slices" = the slice
-    pipeline (tkz_slices.cuh, default), "multipass" = the older dedup multi-pass pipeline (TKZ_SLICES=0, also the fallback
-    when an estimated capacity of the slice pipeline runs out), "occurrence" = the per-occurrence pipeline (TKZ_NO_DEDUP=1;
-    dedup=False is the older spelling).  All device pipelines are held to the same oracle."""
+    pipeline (tkz_slices.cuh, default: byte classes by packed range compares when the class table allows it), "lut" = the
+    same pipeline with the per-byte class look-up forced (TKZ_CLASSIFY=lut), "occurrence" = the per-occurrence pipeline
+    (TKZ_NO_DEDUP=1; dedup=False is the older spelling).  All device pipelines are held to the same oracle."""
     import os
     if mode is None:
         mode = "slices" if dedup else "occurrence"
     os.environ["TKZ_NO_DEDUP"] = "1" if mode == "occurrence" else "0"
-    os.environ["TKZ_SLICES"] = "0" if mode == "multipass" else "1"
+    os.environ["TKZ_CLASSIFY"] = "lut" if mode == "lut" else "auto"
     try:
         t = tz.Tokenizer.from_json(js, device=0)
     finally:
         os.environ["TKZ_NO_DEDUP"] = "0"
-        os.environ["TKZ_SLICES"] = "1"
+        os.environ["TKZ_CLASSIFY"] = "auto"
     return t, orc.OracleTokenizer.from_json(js)
 
 
@@ -238,10 +238,10 @@ def test_malformed_utf8():
     t.close()
 
 
-@pytest.mark.parametrize("dedup", ["slices", "multipass", "occurrence"])
+@pytest.mark.parametrize("dedup", ["slices", "lut", "occurrence"])
 def test_wordpiece_missing_unk_is_an_error(dedup):
     js = json.dumps({"model": {"type": "WordPiece", "vocab": {"hello": 1, "##s": 2}, "unk_token": "[UNK]"}, "pre_tokenizer": {"type": "Whitespace"}})
-    t, o = pair(js, dedup)
+    t, o = pair(js, mode=dedup)
     assert_same(t.encode_batch([b"hello hellos"]), o.encode_batch([b"hello hellos"]))
     with pytest.raises(tz.TokzigError) as e:
         t.encode_batch([b"hello", b"hello xyz", b"q"])
@@ -311,7 +311,7 @@ def test_batch_split_invariance_and_roundtrip_property():
 
 
 # ----------------------------------------------------------------------------- dedup pipeline specifics
-@pytest.mark.parametrize("mode", ["slices", "multipass"])
+@pytest.mark.parametrize("mode", ["slices", "lut"])
 @pytest.mark.parametrize("model", ["bpe", "wp"])
 def test_dedup_word_lengths_around_the_key_limit(model, mode):
     """words of 14 / 15 / 16 / 17 bytes straddle the 128-bit key (15 bytes + length), incl. NUL bytes inside words,
@@ -353,7 +353,7 @@ def test_dedup_and_per_occurrence_pipelines_agree_on_errors():
         t.close()
 
 
-@pytest.mark.parametrize("mode", ["slices", "multipass"])
+@pytest.mark.parametrize("mode", ["slices", "lut"])
 @pytest.mark.parametrize("n_words", [60000, 200000])
 def test_dedup_table_pressure_and_overflow(n_words, mode):
     """more unique words than the batch's table holds: insertions that find no slot fall back to the long list, and when
@@ -584,26 +584,27 @@ def test_chunked_host_path_matches_single_shot(monkeypatch, chunk):
 
 # ----------------------------------------------------------------------------- slice pipeline (tkz_slices.cuh)
 @pytest.mark.parametrize("name,cname,mib", [("gpt2_whitespace", "c2", 96), ("llama3_whitespace", "c4", 64), ("bert_wordpiece", "c3", 48)])
-def test_tiles_equal_multipass_at_size(name, cname, mib, monkeypatch):
-    """the slice pipeline against the older multi-pass dedup pipeline on the same batch (one device call for the whole
-    batch), every output array compared in full (both are held to the oracle at oracle-feasible sizes above)."""
+def test_tiles_equal_per_occurrence_at_size(name, cname, mib, monkeypatch):
+    """the slice pipeline against the per-occurrence pipeline (one warp per pre-token, no word table) on the same batch
+    (one device call for the whole batch), every output array compared in full (both are held to the oracle at
+    oracle-feasible sizes above)."""
     monkeypatch.setenv("TKZ_CHUNK_BYTES", str(1 << 31))
     js = tokenizers_io.tokenizer_json(name)
     text, off = corpus.generate(cname, mib << 20, seed=31)
     t1, _ = pair(js, mode="slices")
-    t0, _ = pair(js, mode="multipass")
+    t0, _ = pair(js, mode="occurrence")
     for rep in range(2):                                  # second call: table sized from history, output estimate from density
         a = t1.encode_packed(text, off)
         b = t0.encode_packed(text, off)
-        assert t0.stats().path == 1
+        assert t0.stats().path == 0
         assert t1.stats().path == 2, "the slice pipeline gave up on a corpus it is meant to handle"
         for k in ("doc_tok_off", "ids", "offsets", "attention_mask", "type_ids", "special_tokens_mask"):
             assert np.array_equal(getattr(a, k), getattr(b, k)), f"{name} call {rep}: {k}"
     t1.close(); t0.close()
 
 
-def test_tiles_words_between_65_and_256_bytes_and_the_long_list():
-    """65..256-byte words are tokenized inside pass A (symbols in global scratch, not deduplicated); longer words go to
+def test_tiles_words_between_65_and_255_bytes_and_the_long_list():
+    """65..255-byte words are tokenized inside pass A (symbols in global scratch, not deduplicated); longer words go to
     the long list (word-list kernels between the passes, counts folded back per tile and per document start)."""
     rng = random.Random(41)
     for model in ("bpe", "wp"):
@@ -616,11 +617,11 @@ def test_tiles_words_between_65_and_256_bytes_and_the_long_list():
         def word(L):
             return "".join(rng.choice(alpha) for _ in range(L)).encode()[:L].decode("utf-8", "ignore").encode()
 
-        inline = [b" ".join(word(rng.choice([3, 9, 64, 65, 90, 128, 200, 255, 256])) for _ in range(rng.randint(1, 9))) for _ in range(800)]
+        inline = [b" ".join(word(rng.choice([3, 9, 64, 65, 90, 128, 200, 254, 255])) for _ in range(rng.randint(1, 9))) for _ in range(800)]
         assert_same(t.encode_batch(inline), o.encode_batch(inline, threads=8), model + " inline")
         assert t.stats().path == 2 and t.stats().n_long_words == 0
         # long words in front of document starts inside the same tile, at tile edges, back to back
-        longer = inline[:300] + [b"ab " + word(257) + b" cd", word(3000), b"", word(5), word(300) + b" " + word(400), b"x", word(9000)] + inline[300:500]
+        longer = inline[:300] + [b"ab " + word(256) + b" cd", word(257) + b" " + word(256) + b" " + word(256) + b" " + word(256), word(3000), b"", word(5), word(300) + b" " + word(400), b"x", word(9000)] + inline[300:500]
         for trunc, pad in ((None, None), (7, {"length": 9, "pad_id": 3})):
             t.truncation = None if trunc is None else {"max_length": trunc}
             o.truncation = trunc
@@ -632,7 +633,7 @@ def test_tiles_words_between_65_and_256_bytes_and_the_long_list():
 
 def test_tiles_wordpiece_words_above_max_chars_any_length():
     """WordPiece only needs the length of a word above max_input_chars_per_word (wordpiece.zig:149-158): one [UNK] with
-    offsets (0, len), whatever the length -- handled inside pass A up to 65535 bytes, by the word-list kernel beyond."""
+    offsets (0, len), whatever the length -- handled inside pass A up to 255 bytes, by the word-list kernel beyond."""
     js, alpha = rand_wp_json(random.Random(5), n_words=60, pretok="Whitespace", max_chars=100, normalizer=None)
     t, o = pair(js)
     docs = [b"x" * n + b" " + b"ab" for n in (99, 100, 101, 255, 256, 257, 1000, 4095, 4096, 4097, 20000, 65535)] * 3
@@ -676,8 +677,8 @@ def test_tiles_errors_report_the_first_document_in_text_order():
 def test_full_size_properties_1gib():
     """BASELINE.json configs[1] at its full size (1 GiB of the c2 corpus, GPT-2-shaped tokenizer), through properties that
     need no oracle run: (1) batch-split invariance -- the encoding of the whole batch equals the concatenation of the
-    encodings of its halves (different slice / chunk / table-occupancy layout); (2) the slice pipeline equals the older
-    multi-pass pipeline on all 235 M tokens; (3) token strings of sampled documents concatenate to the document minus
+    encodings of its halves (different slice / chunk / table-occupancy layout); (2) the slice pipeline equals the
+    per-occurrence pipeline on all 235 M tokens; (3) token strings of sampled documents concatenate to the document minus
     the characters the vocabulary lacks; (4) CSR offsets are monotone and end at the token count; (5) the oracle on the same GiB, every id and offset."""
     js = tokenizers_io.tokenizer_json("gpt2_whitespace")
     text, off = corpus.generate("c2", 1 << 30, seed=1234)
@@ -695,9 +696,9 @@ def test_full_size_properties_1gib():
     assert np.array_equal(full.offsets[:na], a.offsets) and np.array_equal(full.offsets[na:], b.offsets)
     assert np.array_equal(full.doc_tok_off[: h + 1], a.doc_tok_off) and np.array_equal(full.doc_tok_off[h:], b.doc_tok_off + a.doc_tok_off[-1])
     del a, b
-    t0, _ = pair(js, mode="multipass")
+    t0, _ = pair(js, mode="occurrence")
     old = t0.encode_packed(text, off, outputs=3)
-    assert t0.stats().path == 1
+    assert t0.stats().path == 0
     assert np.array_equal(old.ids, full.ids) and np.array_equal(old.offsets, full.offsets) and np.array_equal(old.doc_tok_off, full.doc_tok_off)
     del old
     t0.close()
@@ -746,8 +747,8 @@ def test_tiles_words_of_16_to_31_bytes_share_prefixes(model):
 
 def test_tiles_capacity_estimate_exceeded_falls_back_then_adapts():
     """a batch that needs more token records than the slice pipeline reserved (millions of distinct multi-token words in
-    a few MiB) is re-run by the multi-pass pipeline -- same result -- and the context sizes the next batch from what
-    this one needed, so the same batch then stays on the slice pipeline."""
+    a few MiB) is run again with worst-case capacities -- same result -- and the context sizes the next batch from what
+    this one needed, so the same batch then needs no second run."""
     rng = random.Random(99)
     v = {c: i for i, c in enumerate("abcdefghijklmnopqrstuvwxyz")}
     js = json.dumps({"model": {"type": "BPE", "vocab": v, "merges": []}, "pre_tokenizer": {"type": "Whitespace"}})
@@ -758,9 +759,9 @@ def test_tiles_capacity_estimate_exceeded_falls_back_then_adapts():
     docs = [b" ".join(letters[i * 15:(i + 1) * 15] for i in range(j, min(j + 40, n_words))) for j in range(0, n_words, 40)]
     ref = o.encode_batch(docs, threads=8)
     assert_same(t.encode_batch(docs), ref, "first call")
-    assert t.stats().path == 1, "expected the capacity fallback on the first call"
+    assert t.stats().path == 2 and t.stats().model_flags & 4, "expected the worst-case re-run on the first call"
     assert_same(t.encode_batch(docs), ref, "second call")
-    assert t.stats().path == 2, "the second call should fit the adapted capacities"
+    assert t.stats().path == 2 and not (t.stats().model_flags & 4), "the second call should fit the adapted capacities"
     t.close()
 
 

@@ -30,6 +30,7 @@ _ERR_NAMES = {ERR_OOM: "OutOfMemory", ERR_MISSING_UNK: "MissingUnkToken", ERR_IN
               ERR_INVALID_VOCAB_ENTRY: "InvalidVocabEntry", ERR_IO: "IoError"}
 
 OUT_IDS, OUT_OFFSETS, OUT_ATTENTION, OUT_TYPE_IDS, OUT_SPECIAL, OUT_ALL = 1, 2, 4, 8, 16, 31
+OUT_OFFSETS_PACKED = 32          # one u16 per token (start | end << 8); falls back to OUT_OFFSETS when a pre-token has >= 256 bytes
 NORM_CFG_LOWER, NORM_BERT_STRUCT, NORM_LOWER_STRUCT = 1, 2, 3
 PT_WS_CFG, PT_BERT_CFG, PT_WS_STRUCT, PT_BERT_STRUCT, PT_BYTELEVEL_STRUCT = 1, 2, 3, 4, 5
 MODEL_BPE, MODEL_WORDPIECE = 0, 1
@@ -90,6 +91,7 @@ class BatchResult(C.Structure):
         ("type_ids", C.c_void_p),
         ("special_tokens_mask", C.c_void_p),
         ("err_doc", C.c_int64),
+        ("offsets_packed", C.c_void_p),
     ]
 
 
@@ -211,9 +213,16 @@ class BatchEncoding:
     type_ids: Optional[np.ndarray]
     special_tokens_mask: Optional[np.ndarray]
     n_real_tokens: int = 0
+    offsets_packed: Optional[np.ndarray] = None     # u16 per token: start | end << 8 (OUT_OFFSETS_PACKED)
 
     def __len__(self):
         return len(self.doc_tok_off) - 1
+
+    def unpacked_offsets(self) -> Optional[np.ndarray]:
+        """(n, 2) u32 offsets whichever form the call delivered."""
+        if self.offsets is not None or self.offsets_packed is None:
+            return self.offsets
+        return np.stack([self.offsets_packed & 0xFF, self.offsets_packed >> 8], axis=1).astype(np.uint32)
 
     def doc_slice(self, i):
         return slice(int(self.doc_tok_off[i]), int(self.doc_tok_off[i + 1]))
@@ -230,6 +239,7 @@ def _result_to_batch(r: BatchResult) -> BatchEncoding:
         type_ids=_copy(r.type_ids, T, np.uint32) if r.type_ids else None,
         special_tokens_mask=_copy(r.special_tokens_mask, T, np.uint32) if r.special_tokens_mask else None,
         n_real_tokens=int(r.n_real_tokens),
+        offsets_packed=_copy(r.offsets_packed, T, np.uint16) if r.offsets_packed else None,
     )
 
 

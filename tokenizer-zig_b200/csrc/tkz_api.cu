@@ -21,7 +21,6 @@
 #include "tkz_bpe_grid.cuh"
 #include "tkz_common.cuh"
 #include "tkz_decode.cuh"
-#include "tkz_dedup.cuh"
 #include "tkz_emit.cuh"
 #include "tkz_slices.cuh"
 #include "tkz_scan.cuh"
@@ -59,7 +58,7 @@ struct tkz_ctx {
     DevBuf a_text, a_doc_off, a_norm_text, a_norm_doc_off, a_chunk, a_tiles, a_word_start, a_word_end, a_word_doc, a_doc_word_off,
         a_word_ntok, a_pool_id, a_pool_s, a_pool_e, a_pool_rk, a_scan_tmp, a_ctrl;
     // output arrays, double-buffered so that the D2H copy of one chunk overlaps the kernels of the next (tkz_encode_batch)
-    struct OutSet { DevBuf doc_tok_off, ids, off, attn, type, special; } outs[2];
+    struct OutSet { DevBuf doc_tok_off, ids, off, attn, type, special, off16; } outs[2];
     int out_sel = 0;
     OutSet& O() { return outs[out_sel]; }
     DevBuf in_text[2], in_doc_off[2];
@@ -67,22 +66,25 @@ struct tkz_ctx {
     cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
     cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_d2h[2] = {nullptr, nullptr};
     uint64_t chunk_bytes = 64ull << 20;
-    // dedup pipeline arenas
-    DevBuf a_table, a_uniq, a_long_start, a_long_end, a_long_ntok, a_tile_words, a_tile_nwords, a_tile_ntok, a_doc_word_ref,
+    // slice pipeline arenas (tkz_slices.cuh)
+    DevBuf a_long_start, a_long_end, a_long_ntok, a_long_slice, a_long_ins, a_tile_ntok, a_tile_ntok_inline, a_tile_tok_off, a_tile_long,
         a_doc_tok_local, a_doc_tok_start, a_doc_real, a_upool, a_tile_doc_lo, a_g_first, a_g_win, a_g_flag, a_big;
-    bool has_iso = false;                 // the class table isolates some byte (punctuation split)
     bool use_dedup = true;                // TKZ_NO_DEDUP=1: per-occurrence pipeline even with a pre-tokenizer (A/B switch of the parity tests)
-    bool use_slices = true;               // slice pipeline (tkz_slices.cuh); TKZ_SLICES=0 selects the older multi-pass dedup pipeline
-    DevBuf a_wtable, a_lscratch, a_ent, a_tile_ent_off, a_long_slice, a_region_ctr;
+    DevBuf a_wtable, a_lscratch, a_tok_id, a_tok_of;
+    bool has_iso = false;                 // the class table isolates some byte (punctuation split)
+    ClassRanges cr{}, cr_post{};          // byte classes as ranges (raw bytes / bytes already normalised by K0)
+    bool stage_bulk = true;               // TKZ_STAGE=ldg: pass A stages its slices with plain loads instead of bulk copies (A/B switch)
+    bool force_lut = false;               // TKZ_CLASSIFY=lut: per-byte look-up even when the class table fits ranges (A/B switch)
     DevBuf a_huge_w, a_huge_base, a_huge_done, a_grid_state, a_grid_words;   // bpe_grid_kernel (tkz_bpe_grid.cuh)
     bool use_grid = true;                 // TKZ_NO_GRID=1: huge words stay with one block each (A/B switch of the parity tests)
     uint32_t grid_min_len = 12289;        // shortest word (bytes) that goes to bpe_grid_kernel (TKZ_GRID_MIN_LEN)
     bool grid_used = false;               // the last encode ran bpe_grid_kernel
+    bool retried = false;                 // the last encode re-ran the slice pipeline with worst-case capacities
     int grid_blocks = 0;                  // co-resident blocks of bpe_grid_kernel (0: cooperative launch not available)
     uint64_t tw_uniq_hist = 0;            // most unique words seen in one batch: sizes the next batch's word table
     uint64_t tw_upool_hist = 0;           // most token records used by one batch
-    double tw_words_per_byte = 0.0;       // densest batch so far: sizes the entry list
-    HostBuf h_ctrl, h_doc_tok_off, h_ids, h_off, h_attn, h_type, h_special;
+    double tw_tok_per_byte = 0.0;         // densest batch so far: sizes the token stream
+    HostBuf h_ctrl, h_doc_tok_off, h_ids, h_off, h_attn, h_type, h_special, h_off16;
     // decode direction (tkz_decode.cuh)
     bool has_decode = false;
     DecodeTables dt{};
@@ -166,27 +168,6 @@ int readback(tkz_ctx* ctx, unsigned long long* h_dst, const void* d_src, size_t 
     publish_kernel<<<1, 32, 0, ctx->stream>>>((const uint32_t*)d_src, dst, (uint32_t)(bytes / 4));
     return TKZ_OK;
 }
-#define TKZ_RETRY_NO_DEDUP 1
-__global__ void tile_words_total_kernel(const uint32_t* tile_nwords, uint32_t n_tiles, unsigned long long* ctrl) {
-    unsigned long long s = 0;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_tiles; i += gridDim.x * blockDim.x) s += tile_nwords[i];
-    for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(0xFFFFFFFFu, s, d);
-    if ((threadIdx.x & 31) == 0 && s) atomicAdd(ctrl + 10, s);
-}
-__global__ void gather_scalars_dedup_kernel(unsigned long long* ctrl, const uint32_t* tile_tok_base, uint32_t n_tiles,
-                                            const unsigned long long* doc_tok_off, uint32_t n_docs, const uint32_t* doc_word_ref) {
-    ctrl[2] = tile_tok_base[n_tiles];
-    ctrl[3] = doc_tok_off[n_docs];
-    const unsigned long long ew = ctrl[0];
-    unsigned long long d = 0;
-    if (ew != TKZ_ERRW_NONE) {
-        const uint32_t v = (uint32_t)(ew >> 8);            // virtual word index of the first failing word (text order)
-        uint32_t lo = 0, hi = n_docs;                      // last document with doc_word_ref <= v
-        while (lo < hi) { const uint32_t mid = lo + ((hi - lo) >> 1); if (doc_word_ref[mid] <= v) lo = mid + 1; else hi = mid; }
-        d = lo ? lo - 1 : 0;
-    }
-    ctrl[4] = d;
-}
 // word-length classes of the BPE kernels: [0] 65..2048 bytes, [1] > 2048, [2] > 12288 (needs global state arrays)
 constexpr uint32_t BB_WARP_MAX = 64, BB_MINI_MAX = 512, BB_TINY_MAX = 1024, BB_SMALL_MAX = 2048, BB_MID_MAX = 4096, BB_BIG_CAP = 12288;
 __global__ void len_class_count_kernel(const uint32_t* word_start, const uint32_t* word_end, uint32_t n_fixed, const unsigned int* n_dev,
@@ -238,14 +219,14 @@ extern "C" int tkz_ctx_create(int device, void* stream, uint64_t arena_hint_byte
     cudaFuncSetAttribute(bpe_block_kernel<512, 4096, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4096 * 15);
     {
         const int sm = (int)sizeof(BlockShared);
-        cudaFuncSetAttribute(slice_words_kernel<TKZ_MODEL_BPE, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
-        cudaFuncSetAttribute(slice_words_kernel<TKZ_MODEL_BPE, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
-        cudaFuncSetAttribute(slice_words_kernel<TKZ_MODEL_BPE, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
-        cudaFuncSetAttribute(slice_words_kernel<TKZ_MODEL_BPE, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
-        cudaFuncSetAttribute(slice_words_kernel<TKZ_MODEL_WORDPIECE, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
-        cudaFuncSetAttribute(slice_words_kernel<TKZ_MODEL_WORDPIECE, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
-        cudaFuncSetAttribute(slice_words_kernel<TKZ_MODEL_WORDPIECE, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
-        cudaFuncSetAttribute(slice_words_kernel<TKZ_MODEL_WORDPIECE, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
+        cudaFuncSetAttribute(slice_words_kernel<TKZ_MODEL_BPE, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
+        cudaFuncSetAttribute(slice_words_kernel<TKZ_MODEL_BPE, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
+        cudaFuncSetAttribute(slice_words_kernel<TKZ_MODEL_BPE, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
+        cudaFuncSetAttribute(slice_words_kernel<TKZ_MODEL_BPE, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
+        cudaFuncSetAttribute(slice_words_kernel<TKZ_MODEL_WORDPIECE, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
+        cudaFuncSetAttribute(slice_words_kernel<TKZ_MODEL_WORDPIECE, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
+        cudaFuncSetAttribute(slice_words_kernel<TKZ_MODEL_WORDPIECE, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
+        cudaFuncSetAttribute(slice_words_kernel<TKZ_MODEL_WORDPIECE, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
     }
     e = cudaFuncSetAttribute(bpe_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BPE_SMEM_BYTES);
     if (e != cudaSuccess) {
@@ -262,7 +243,8 @@ extern "C" int tkz_ctx_create(int device, void* stream, uint64_t arena_hint_byte
     ctx->h_ctrl.cap = 64 * sizeof(unsigned long long);
     (void)arena_hint_bytes;
     if (const char* e = getenv("TKZ_NO_DEDUP")) ctx->use_dedup = !(e[0] == '1');     // A/B switch for the parity tests
-    if (const char* e = getenv("TKZ_SLICES")) ctx->use_slices = !(e[0] == '0');
+    if (const char* e = getenv("TKZ_CLASSIFY")) ctx->force_lut = (e[0] == 'l');
+    if (const char* e = getenv("TKZ_STAGE")) ctx->stage_bulk = !(e[0] == 'l');
     if (const char* e = getenv("TKZ_NO_GRID")) ctx->use_grid = !(e[0] == '1');
     if (const char* e = getenv("TKZ_GRID_MIN_LEN")) { const long long v = atoll(e); if (v > (long long)BB_WARP_MAX) ctx->grid_min_len = (uint32_t)v; }
     {
@@ -277,8 +259,8 @@ extern "C" int tkz_ctx_create(int device, void* stream, uint64_t arena_hint_byte
     for (int i = 0; i < 2; i++) { cudaEventCreateWithFlags(&ctx->ev_h2d[i], cudaEventDisableTiming); cudaEventCreateWithFlags(&ctx->ev_d2h[i], cudaEventDisableTiming); }
     for (auto& ev : ctx->ev) cudaEventCreate(&ev);
     {
-        unsigned long long pw[DT_MAX_MED]; pw[0] = 1;
-        for (int i = 1; i < DT_MAX_MED; i++) pw[i] = pw[i - 1] * TKZ_MED_HASH_MUL;
+        unsigned long long pw[TW_MAX_MED]; pw[0] = 1;
+        for (int i = 1; i < (int)TW_MAX_MED; i++) pw[i] = pw[i - 1] * TKZ_MED_HASH_MUL;
         cudaMemcpyToSymbol(c_med_pw, pw, sizeof pw);
     }
     *out = ctx;
@@ -292,18 +274,17 @@ extern "C" void tkz_ctx_destroy(tkz_ctx* ctx) {
     DevBuf* bufs[] = {&ctx->t_lut, &ctx->t_lut_post, &ctx->t_char_ascii, &ctx->t_char_tab, &ctx->t_merges, &ctx->t_merge_win, &ctx->t_wp_tab, &ctx->t_wp_pool,
                       &ctx->a_text, &ctx->a_doc_off, &ctx->a_norm_text, &ctx->a_norm_doc_off, &ctx->a_chunk, &ctx->a_tiles, &ctx->a_word_start,
                       &ctx->a_word_end, &ctx->a_word_doc, &ctx->a_doc_word_off, &ctx->a_word_ntok, &ctx->a_pool_id, &ctx->a_pool_s, &ctx->a_pool_e,
-                      &ctx->a_pool_rk, &ctx->a_scan_tmp, &ctx->outs[0].doc_tok_off, &ctx->outs[0].ids, &ctx->outs[0].off, &ctx->outs[0].attn,
-                      &ctx->outs[0].type, &ctx->outs[0].special, &ctx->outs[1].doc_tok_off, &ctx->outs[1].ids, &ctx->outs[1].off,
-                      &ctx->outs[1].attn, &ctx->outs[1].type, &ctx->outs[1].special, &ctx->in_text[0], &ctx->in_text[1], &ctx->in_doc_off[0],
-                      &ctx->in_doc_off[1], &ctx->a_ctrl, &ctx->a_table, &ctx->a_uniq, &ctx->a_long_start, &ctx->a_long_end, &ctx->a_long_ntok,
-                      &ctx->a_tile_words, &ctx->a_tile_nwords, &ctx->a_tile_ntok, &ctx->a_doc_word_ref, &ctx->a_doc_tok_local,
+                      &ctx->a_pool_rk, &ctx->a_scan_tmp, &ctx->in_text[0], &ctx->in_text[1], &ctx->in_doc_off[0],
+                      &ctx->in_doc_off[1], &ctx->a_ctrl, &ctx->a_long_start, &ctx->a_long_end, &ctx->a_long_ntok, &ctx->a_long_slice, &ctx->a_long_ins,
+                      &ctx->a_tile_ntok, &ctx->a_tile_ntok_inline, &ctx->a_tile_tok_off, &ctx->a_tile_long, &ctx->a_doc_tok_local,
                       &ctx->a_doc_tok_start, &ctx->a_doc_real, &ctx->a_upool, &ctx->a_tile_doc_lo, &ctx->a_g_first, &ctx->a_g_win, &ctx->a_g_flag, &ctx->a_big,
-                      &ctx->a_wtable, &ctx->a_lscratch, &ctx->a_ent, &ctx->a_tile_ent_off, &ctx->a_long_slice, &ctx->a_region_ctr,
+                      &ctx->a_wtable, &ctx->a_lscratch, &ctx->a_tok_id, &ctx->a_tok_of,
                       &ctx->a_huge_w, &ctx->a_huge_base, &ctx->a_huge_done, &ctx->a_grid_state, &ctx->a_grid_words,
                       &ctx->t_dec_bytes, &ctx->t_dec_off, &ctx->t_dec_special, &ctx->a_dec_ids, &ctx->a_dec_seq_off, &ctx->a_dec_len, &ctx->a_dec_raw,
                       &ctx->a_dec_out, &ctx->a_dec_olen, &ctx->a_dec_boff};
+    for (auto& os : ctx->outs) for (DevBuf* b : {&os.doc_tok_off, &os.ids, &os.off, &os.attn, &os.type, &os.special, &os.off16}) release(*b);
     for (DevBuf* b : bufs) release(*b);
-    HostBuf* hb[] = {&ctx->h_ctrl, &ctx->h_doc_tok_off, &ctx->h_ids, &ctx->h_off, &ctx->h_attn, &ctx->h_type, &ctx->h_special,
+    HostBuf* hb[] = {&ctx->h_ctrl, &ctx->h_doc_tok_off, &ctx->h_ids, &ctx->h_off, &ctx->h_attn, &ctx->h_type, &ctx->h_special, &ctx->h_off16,
                      &ctx->h_doc_stage[0], &ctx->h_doc_stage[1], &ctx->h_dec_bytes, &ctx->h_dec_off};
     for (HostBuf* b : hb) release_host(*b);
     if (ctx->s_h2d) cudaStreamDestroy(ctx->s_h2d);
@@ -319,7 +300,7 @@ extern "C" const char* tkz_last_error(tkz_ctx* ctx) { return ctx ? ctx->err.c_st
 extern "C" int tkz_ctx_get_stats(tkz_ctx* ctx, tkz_stats* out) {
     if (!ctx || !out) return TKZ_ERR_INVALID_ARG;
     *out = ctx->stats; out->arena_bytes = ctx->arena_bytes;
-    out->model_flags = ((ctx->has_model && ctx->dm.windowed_ok) ? 1u : 0u) | (ctx->grid_used ? 2u : 0u);
+    out->model_flags = ((ctx->has_model && ctx->dm.windowed_ok) ? 1u : 0u) | (ctx->grid_used ? 2u : 0u) | (ctx->retried ? 4u : 0u);
     return TKZ_OK;
 }
 
@@ -350,8 +331,38 @@ extern "C" int tkz_model_upload(tkz_ctx* ctx, const tkz_model_desc* d) {
         lut_post[256 + b] = d->class_lut ? d->class_lut[b] : (uint8_t)TKZ_CLS_WORD;
     }
     m.norm_identity = identity; m.norm_has_drop = has_drop;
+    // byte classes as ranges (tkz_slices.cuh, four bytes per instruction) when the tables allow it: the byte map is the
+    // identity or exactly A-Z -> a-z, bytes >= 0x80 are WORD, and DELIM / ISOLATE are a few runs of byte values each
+    auto make_ranges = [](const uint8_t* nrm, const uint8_t* cls, bool drops) -> ClassRanges {
+        ClassRanges r{};
+        if (drops) return r;
+        bool ident = true, lower = true;
+        for (int b = 0; b < 256; b++) {
+            if (nrm[b] != b) ident = false;
+            if (nrm[b] != ((b >= 'A' && b <= 'Z') ? b + 32 : b)) lower = false;
+        }
+        if (!ident && !lower) return r;
+        for (int b = 128; b < 256; b++) if (cls[b] != TKZ_CLS_WORD) return r;
+        for (int c = TKZ_CLS_DELIM; c <= TKZ_CLS_ISOLATE; c++) {
+            int n = 0;
+            for (int b = 0; b < 128;) {
+                if (cls[b] != c) { b++; continue; }
+                int e = b; while (e + 1 < 128 && cls[e + 1] == c) e++;
+                if (n == TW_MAX_RANGES) return r;
+                const uint32_t lo = (uint32_t)(0x80 - b) * 0x01010101u, hi = (uint32_t)(0x7F - e) * 0x01010101u;
+                if (c == TKZ_CLS_DELIM) { r.d_lo[n] = lo; r.d_hi[n] = hi; } else { r.i_lo[n] = lo; r.i_hi[n] = hi; }
+                n++; b = e + 1;
+            }
+            if (c == TKZ_CLS_DELIM) r.n_delim = n; else r.n_iso = n;
+        }
+        r.norm_lower = (lower && !ident) ? 1 : 0;
+        r.usable = tw_ranges_supported(r.n_delim, r.n_iso) ? 1 : 0;
+        return r;
+    };
     ctx->has_iso = false;
     for (int b = 0; b < 256; b++) if (lut[256 + b] == TKZ_CLS_ISOLATE || lut_post[256 + b] == TKZ_CLS_ISOLATE) ctx->has_iso = true;
+    ctx->cr = make_ranges(lut.data(), lut.data() + 256, has_drop);
+    ctx->cr_post = make_ranges(lut_post.data(), lut_post.data() + 256, false);
     TRY(upload(ctx, ctx->t_lut, lut.data(), lut.size()));
     TRY(upload(ctx, ctx->t_lut_post, lut_post.data(), lut_post.size()));
     m.lut = (const uint8_t*)ctx->t_lut.p;
@@ -625,21 +636,29 @@ int launch_bpe(tkz_ctx* ctx, const DevModel& m, const uint8_t* d_text, const uin
     return TKZ_OK;
 }
 
-// The slice pipeline (tkz_slices.cuh).  Returns TKZ_RETRY_MULTIPASS when pass A ran out of an estimated capacity (entry
-// list, record pool, scratch, long list): the caller then runs the older multi-pass dedup pipeline on the same batch and
-// the next batch of this context gets larger estimates.
-#define TKZ_RETRY_MULTIPASS 2
+// The slice pipeline (tkz_slices.cuh).  Capacities that depend on the text (token stream, record pool, word table) are
+// estimated from the batch and from what earlier batches of the context needed; when pass A runs out of one of them the
+// call returns TKZ_RETRY_WORST and the caller runs it again with worst-case capacities (tokens <= bytes), never truncated.
+#define TKZ_RETRY_WORST 2
 template <int MODEL>
-void launch_slice_words(const DevModel& m, const SliceArgs& ta, bool nid, bool iso, uint32_t blocks, cudaStream_t st) {
+void launch_slice_words(const DevModel& m, const SliceArgs& ta, int cls, uint32_t blocks, cudaStream_t st) {
     const size_t sm = sizeof(BlockShared);
-    if (nid && !iso) slice_words_kernel<MODEL, true, false><<<blocks, TW_THREADS, sm, st>>>(m, ta);
-    else if (nid) slice_words_kernel<MODEL, true, true><<<blocks, TW_THREADS, sm, st>>>(m, ta);
-    else if (!iso) slice_words_kernel<MODEL, false, false><<<blocks, TW_THREADS, sm, st>>>(m, ta);
-    else slice_words_kernel<MODEL, false, true><<<blocks, TW_THREADS, sm, st>>>(m, ta);
+    if (cls == 0) slice_words_kernel<MODEL, 0><<<blocks, TW_THREADS, sm, st>>>(m, ta);
+    else if (cls == 1) slice_words_kernel<MODEL, 1><<<blocks, TW_THREADS, sm, st>>>(m, ta);
+    else if (cls == 2) slice_words_kernel<MODEL, 2><<<blocks, TW_THREADS, sm, st>>>(m, ta);
+    else slice_words_kernel<MODEL, 3><<<blocks, TW_THREADS, sm, st>>>(m, ta);
+}
+template <bool PLAIN>
+void launch_slice_emit(const SliceEmitArgs& ea, const EmitParams& ep, const EmitOut& eo, uint32_t blocks, cudaStream_t st) {
+    const uint32_t o = ep.outputs;
+    if (o == TKZ_OUT_IDS) slice_emit_kernel<PLAIN, 1u><<<blocks, TW_THREADS, 0, st>>>(ea, ep, eo);
+    else if (o == (TKZ_OUT_IDS | TKZ_OUT_OFFSETS | TKZ_OUT_ATTENTION)) slice_emit_kernel<PLAIN, 7u><<<blocks, TW_THREADS, 0, st>>>(ea, ep, eo);
+    else if (o == (TKZ_OUT_IDS | TKZ_OUT_OFFSETS_PACKED)) slice_emit_kernel<PLAIN, 33u><<<blocks, TW_THREADS, 0, st>>>(ea, ep, eo);
+    else slice_emit_kernel<PLAIN, 0u><<<blocks, TW_THREADS, 0, st>>>(ea, ep, eo);
 }
 
-int encode_slices(tkz_ctx* ctx, const DevModel& m, const uint8_t* d_text, const uint64_t* d_doc_off, uint32_t nd, uint64_t N,
-                 const tkz_encode_params& P, tkz_batch_result* out, uint64_t& launches) {
+int encode_slices(tkz_ctx* ctx, const DevModel& m, const ClassRanges& cr, const uint8_t* d_text, const uint64_t* d_doc_off, uint32_t nd, uint64_t N,
+                  tkz_encode_params P, bool worst, tkz_batch_result* out, uint64_t& launches) {
     cudaStream_t st = ctx->stream;
     unsigned long long* ctrl = (unsigned long long*)ctx->a_ctrl.p;
     unsigned long long* hctrl = (unsigned long long*)ctx->h_ctrl.p;
@@ -651,52 +670,62 @@ int encode_slices(tkz_ctx* ctx, const DevModel& m, const uint8_t* d_text, const 
     if (want < ctx->tw_uniq_hist * 4) want = ctx->tw_uniq_hist * 4;          // load factor <= 1/4
     if (want > (1u << 26)) want = 1u << 26;
     const uint32_t tcap = pow2_at_least(want);
+    uint32_t tbits = 0; while ((1u << tbits) < tcap) tbits++;
     const uint32_t mcap = tcap >= (1u << 17) ? tcap / 8 : (1u << 14);
     const uint32_t m32cap = tcap >= (1u << 16) ? tcap / 4 : (1u << 14);        // 64-byte slots for words of 16..31 bytes
-    uint64_t upool_cap = N / 8 + (1u << 20);
+    uint64_t upool_cap = worst ? N + (1u << 16) : N / 8 + (1u << 20);
     if (upool_cap < ctx->tw_upool_hist * 2) upool_cap = ctx->tw_upool_hist * 2;
     if (upool_cap > 0xFFFFFF00ull) upool_cap = 0xFFFFFF00ull;
-    uint64_t ls_cap = N / 16 + (1u << 22); if (ls_cap > 0xFFFFFF00ull) ls_cap = 0xFFFFFF00ull;
-    // entry list: warps claim TW_ENT_CHUNK entries at a time (the unused tail of a chunk is lost)
-    const uint32_t grid = (uint32_t)std::min<uint64_t>(((uint64_t)n_slices + TW_WARPS - 1) / TW_WARPS, (uint64_t)ctx->sm_count * 12);
-    uint64_t ent_cap = N + 16;                                               // words <= bytes
-    if (ctx->tw_words_per_byte > 0.0) { const uint64_t e2 = (uint64_t)((double)N * ctx->tw_words_per_byte * 1.25) + 65536; if (e2 < ent_cap) ent_cap = e2; }
-    else if (N > (64ull << 20)) ent_cap = N / 2 + 65536;
-    ent_cap += ent_cap / 4 + std::min<uint64_t>(n_slices, (uint64_t)grid * TW_WARPS) * TW_ENT_CHUNK;
-    if (ent_cap > 0xFFFFF000ull) ent_cap = 0xFFFFF000ull;
-    const uint32_t long_cap = (uint32_t)(N / 256 + 1024);
+    // persistent grid: every warp keeps a private chunk of the token stream and a private model scratch
+    const uint32_t grid = (uint32_t)std::min<uint64_t>(((uint64_t)n_slices + TW_WARPS - 1) / TW_WARPS, (uint64_t)ctx->sm_count * TW_BLOCKS_PER_SM);
+    const uint64_t warps = (uint64_t)grid * TW_WARPS;
+    // token stream: a warp claims TW_TOK_CHUNK tokens at a time and starts a slice only with TW_SLICE_TOK_MAX of them left
+    double tpb = worst ? 1.0 : (ctx->tw_tok_per_byte > 0.0 ? std::min(1.0, ctx->tw_tok_per_byte * 1.25) : 0.5);
+    uint64_t tok_cap = (uint64_t)((double)N * tpb) + 4096;
+    tok_cap = tok_cap + tok_cap / 8 + (tok_cap * TW_SLICE_TOK_MAX) / (TW_TOK_CHUNK - TW_SLICE_TOK_MAX) + warps * TW_TOK_CHUNK;
+    if (tok_cap > 0xFFFFF000ull) tok_cap = 0xFFFFF000ull;
+    const uint32_t long_cap = (uint32_t)(N / 256 + 16);                        // a long word has more than 255 bytes: always enough
+    const bool want_of = (P.outputs & (TKZ_OUT_OFFSETS | TKZ_OUT_OFFSETS_PACKED)) != 0;
     TRY(ensure(ctx, ctx->a_wtable, ((size_t)tcap + mcap) * sizeof(WordSlot) + (size_t)m32cap * sizeof(WordSlot32)));
     TRY(ensure(ctx, ctx->a_upool, (size_t)upool_cap * 8));
-    TRY(ensure(ctx, ctx->a_lscratch, (size_t)ls_cap * 4));
-    TRY(ensure(ctx, ctx->a_ent, (size_t)ent_cap * 8));
-    TRY(ensure(ctx, ctx->a_tile_ent_off, ((size_t)n_slices + 2) * 4));
-    TRY(ensure(ctx, ctx->a_tile_nwords, ((size_t)n_slices + 2) * 4));
+    TRY(ensure(ctx, ctx->a_lscratch, (size_t)warps * 4 * 256 * 4));
+    TRY(ensure(ctx, ctx->a_tok_id, (size_t)tok_cap * 4));
+    if (want_of) TRY(ensure(ctx, ctx->a_tok_of, (size_t)tok_cap * 2));
+    TRY(ensure(ctx, ctx->a_tile_tok_off, ((size_t)n_slices + 2) * 4));
+    TRY(ensure(ctx, ctx->a_tile_ntok_inline, ((size_t)n_slices + 2) * 4));
     TRY(ensure(ctx, ctx->a_tile_ntok, ((size_t)n_slices + 2) * 4));
+    TRY(ensure(ctx, ctx->a_tile_long, ((size_t)n_slices + 2) * 4));
     TRY(ensure(ctx, ctx->a_tile_doc_lo, ((size_t)n_slices + 2) * 4));
-    TRY(ensure(ctx, ctx->a_doc_word_ref, (n_docs + 2) * 4));
     TRY(ensure(ctx, ctx->a_doc_tok_local, (n_docs + 2) * 4));
     TRY(ensure(ctx, ctx->a_long_start, (size_t)long_cap * 4));
     TRY(ensure(ctx, ctx->a_long_end, (size_t)long_cap * 4));
     TRY(ensure(ctx, ctx->a_long_slice, (size_t)long_cap * 4));
+    TRY(ensure(ctx, ctx->a_long_ins, (size_t)long_cap * 4));
     TRY(ensure(ctx, ctx->O().doc_tok_off, (n_docs + 1) * 8));
     TRY(ensure(ctx, ctx->a_scan_tmp, (scan_tmp_elems(n_slices) + scan_tmp_elems(n_docs)) * 8));
     CK(cudaMemsetAsync(ctx->a_wtable.p, 0, ((size_t)tcap + mcap) * sizeof(WordSlot) + (size_t)m32cap * sizeof(WordSlot32), st));
     tile_doc_index_kernel<<<(n_slices + 1 + 255) / 256, 256, 0, st>>>(d_doc_off, nd, n_slices, TW_SLICE, (uint32_t*)ctx->a_tile_doc_lo.p); launches++;
     SliceArgs ta{};
     ta.text = d_text; ta.n = N; ta.doc_off = d_doc_off; ta.n_docs = nd; ta.n_slices = n_slices; ta.slice_doc_lo = (const uint32_t*)ctx->a_tile_doc_lo.p;
-    ta.table = (WordSlot*)ctx->a_wtable.p; ta.table_mask = tcap - 1; ta.med_base = tcap; ta.med_mask = mcap - 1;
+    ta.table = (WordSlot*)ctx->a_wtable.p; ta.table_shift = 32 - tbits; ta.med_base = tcap; ta.med_mask = mcap - 1;
     ta.table32 = (WordSlot32*)((WordSlot*)ctx->a_wtable.p + tcap + mcap); ta.table32_mask = m32cap - 1;
     ta.upool = (unsigned long long*)ctx->a_upool.p; ta.upool_cap = (uint32_t)upool_cap; ta.upool_count = (unsigned int*)(ctrl + 9);
-    ta.lscratch = (uint32_t*)ctx->a_lscratch.p; ta.lscratch_cap = (uint32_t)ls_cap; ta.lscratch_count = (unsigned int*)(ctrl + 9) + 1;
-    ta.ent = (uint2*)ctx->a_ent.p; ta.ent_cap = (uint32_t)ent_cap; ta.ent_count = (unsigned int*)(ctrl + 5);
-    ta.slice_ent_off = (uint32_t*)ctx->a_tile_ent_off.p; ta.slice_nwords = (uint32_t*)ctx->a_tile_nwords.p; ta.slice_ntok = (uint32_t*)ctx->a_tile_ntok.p;
-    ta.doc_word_ref = (uint32_t*)ctx->a_doc_word_ref.p; ta.doc_tok_local = (uint32_t*)ctx->a_doc_tok_local.p;
+    ta.lscratch = (uint32_t*)ctx->a_lscratch.p;
+    ta.tok_id = (uint32_t*)ctx->a_tok_id.p; ta.tok_of = want_of ? (uint16_t*)ctx->a_tok_of.p : nullptr;
+    ta.tok_cap = (uint32_t)tok_cap; ta.tok_count = (unsigned int*)(ctrl + 5);
+    ta.slice_tok_off = (uint32_t*)ctx->a_tile_tok_off.p; ta.slice_ntok_inline = (uint32_t*)ctx->a_tile_ntok_inline.p;
+    ta.slice_ntok = (uint32_t*)ctx->a_tile_ntok.p; ta.slice_long = (uint32_t*)ctx->a_tile_long.p;
+    ta.doc_tok_local = (uint32_t*)ctx->a_doc_tok_local.p;
     ta.long_start = (uint32_t*)ctx->a_long_start.p; ta.long_end = (uint32_t*)ctx->a_long_end.p; ta.long_slice = (uint32_t*)ctx->a_long_slice.p;
-    ta.n_long = (unsigned int*)(ctrl + 7); ta.long_cap = long_cap;
+    ta.long_ins = (uint32_t*)ctx->a_long_ins.p; ta.n_long = (unsigned int*)(ctrl + 7); ta.long_cap = long_cap;
     ta.abort_flag = (unsigned int*)(ctrl + 8); ta.errw = ctrl;
     ta.n_words = ctrl + 10; ta.n_uniq = (unsigned int*)(ctrl + 6); ta.n_uncached = (unsigned int*)(ctrl + 6) + 1;
-    if (m.kind == TKZ_MODEL_BPE) launch_slice_words<TKZ_MODEL_BPE>(m, ta, m.norm_identity != 0, ctx->has_iso, grid, st);
-    else launch_slice_words<TKZ_MODEL_WORDPIECE>(m, ta, m.norm_identity != 0, ctx->has_iso, grid, st);
+    ta.cr = cr;
+    ta.stage_bulk = ctx->stage_bulk ? 1 : 0;
+    ta.has_iso = ctx->has_iso ? 1 : 0;
+    const int cls = (cr.usable && !ctx->force_lut) ? (cr.norm_lower ? 1 : 0) : (m.norm_identity ? 2 : 3);
+    if (m.kind == TKZ_MODEL_BPE) launch_slice_words<TKZ_MODEL_BPE>(m, ta, cls, grid, st);
+    else launch_slice_words<TKZ_MODEL_WORDPIECE>(m, ta, cls, grid, st);
     launches++;
     if (m.kind == TKZ_MODEL_BPE) { len_class_count_kernel<<<128, 256, 0, st>>>(ta.long_start, ta.long_end, 0, ta.n_long, ctrl + 13); launches++; }
     TRY(readback(ctx, hctrl, ctrl, 16 * 8));
@@ -706,11 +735,14 @@ int encode_slices(tkz_ctx* ctx, const DevModel& m, const uint8_t* d_text, const 
     ctx->tw_uniq_hist = std::max<uint64_t>(ctx->tw_uniq_hist, n_uniq);
     ctx->tw_upool_hist = std::max<uint64_t>(ctx->tw_upool_hist, (uint32_t)hctrl[9]);
     if ((uint32_t)hctrl[8] != 0) {
-        ctx->tw_words_per_byte = 1.0;                       // the retry of a later batch gets the worst-case entry list
-        return TKZ_RETRY_MULTIPASS;
+        if (worst) { ctx->err = "internal: slice pipeline ran out of a worst-case capacity"; return TKZ_ERR_CUDA; }
+        ctx->tw_tok_per_byte = 1.0;                         // later batches of this context get the worst-case token stream at once
+        return TKZ_RETRY_WORST;
     }
     ctx->stats.n_unique_words = n_uniq + n_unc; ctx->stats.n_long_words = n_long;
     ctx->stats.path = 2;
+    // packed (one byte each) offsets exist only when no pre-token reaches 256 bytes: otherwise the call delivers 32-bit pairs
+    if ((P.outputs & TKZ_OUT_OFFSETS_PACKED) && n_long) P.outputs = (P.outputs & ~TKZ_OUT_OFFSETS_PACKED) | TKZ_OUT_OFFSETS;
 
     // ---- the few pre-tokens longer than TW_MAX_INLINE bytes: per-occurrence word-list kernels, counts folded back in
     TRY(ensure(ctx, ctx->a_long_ntok, ((size_t)n_long + 2) * 4));
@@ -767,21 +799,23 @@ int encode_slices(tkz_ctx* ctx, const DevModel& m, const uint8_t* d_text, const 
     if (P.outputs & TKZ_OUT_ATTENTION) TRY(ensure(ctx, ctx->O().attn, (T + 4) * 4));
     if (P.outputs & TKZ_OUT_TYPE_IDS) TRY(ensure(ctx, ctx->O().type, (T + 4) * 4));
     if (P.outputs & TKZ_OUT_SPECIAL) TRY(ensure(ctx, ctx->O().special, (T + 4) * 4));
+    if (P.outputs & TKZ_OUT_OFFSETS_PACKED) TRY(ensure(ctx, ctx->O().off16, (T + 4) * 2));
     EmitOut eo{(uint32_t*)ctx->O().ids.p, (uint32_t*)ctx->O().off.p, (uint32_t*)ctx->O().attn.p, (uint32_t*)ctx->O().type.p,
-               (uint32_t*)ctx->O().special.p};
+               (uint32_t*)ctx->O().special.p, (uint16_t*)ctx->O().off16.p};
     const uint32_t big_cap = (uint32_t)(N / EMIT_BIG + 16);
     TRY(ensure(ctx, ctx->a_big, (size_t)big_cap * sizeof(uint4)));
     SliceEmitArgs ea{};
     ea.doc_off = d_doc_off; ea.n_docs = nd; ea.n_slices = n_slices; ea.slice_doc_lo = ta.slice_doc_lo;
-    ea.ent = ta.ent; ea.slice_ent_off = ta.slice_ent_off; ea.slice_nwords = ta.slice_nwords; ea.slice_tokbase = ta.slice_ntok;
-    ea.upool = ta.upool; ea.long_start = ta.long_start; ea.long_ntok = (const uint32_t*)ctx->a_long_ntok.p;
+    ea.tok_id = ta.tok_id; ea.tok_of = ta.tok_of;
+    ea.slice_tok_off = ta.slice_tok_off; ea.slice_ntok_inline = ta.slice_ntok_inline; ea.slice_long = ta.slice_long; ea.slice_tokbase = ta.slice_ntok;
+    ea.long_start = ta.long_start; ea.long_ins = ta.long_ins; ea.long_ntok = (const uint32_t*)ctx->a_long_ntok.p;
     ea.pool_id = (const uint32_t*)ctx->a_pool_id.p; ea.pool_s = (const uint32_t*)ctx->a_pool_s.p; ea.pool_e = (const uint32_t*)ctx->a_pool_e.p;
-    ea.doc_word_ref = ta.doc_word_ref; ea.doc_tok_local = ta.doc_tok_local; ea.doc_tok_start = (const uint32_t*)ctx->a_doc_tok_start.p;
+    ea.doc_tok_local = ta.doc_tok_local; ea.doc_tok_start = (const uint32_t*)ctx->a_doc_tok_start.p;
     ea.doc_tok_off = doc_tok_off; ea.errw = ctrl; ea.err_code = m.kind == TKZ_MODEL_BPE ? TKZ_ECODE_UTF8 : TKZ_ECODE_UNK;
-    ea.n_words = ctrl + 10;
     ea.big = BigList{(uint4*)ctx->a_big.p, (unsigned int*)(ctrl + 16), big_cap};
-    if (plain) slice_emit_kernel<true><<<grid, TW_THREADS, 0, st>>>(ea, ep, eo);
-    else slice_emit_kernel<false><<<grid, TW_THREADS, 0, st>>>(ea, ep, eo);
+    const uint32_t egrid = (uint32_t)std::min<uint64_t>(((uint64_t)n_slices + TW_WARPS - 1) / TW_WARPS, (uint64_t)ctx->sm_count * 16);
+    if (plain) launch_slice_emit<true>(ea, ep, eo, egrid, st);
+    else launch_slice_emit<false>(ea, ep, eo, egrid, st);
     launches++;
     if (n_long) { emit_big_kernel<<<ctx->sm_count * 4, 256, 0, st>>>(ep, eo, ea.big, ea.pool_id, ea.pool_s, ea.pool_e); launches++; }
     if (P.has_padding && nd) {
@@ -793,7 +827,7 @@ int encode_slices(tkz_ctx* ctx, const DevModel& m, const uint8_t* d_text, const 
     CK(cudaStreamSynchronize(st));
     if (hctrl[0] != TKZ_ERRW_NONE) return fail(hctrl[0]);
     ctx->stats.n_words = hctrl[10];
-    if (N) ctx->tw_words_per_byte = std::max(ctx->tw_words_per_byte, (double)hctrl[10] / (double)N);
+    if (N) ctx->tw_tok_per_byte = std::max(ctx->tw_tok_per_byte, (double)T_real / (double)N);
     ctx->stats.kernel_launches = launches;
     cudaEventElapsedTime(&ctx->stats.ms_split, ctx->ev[0], ctx->ev[1]);
     cudaEventElapsedTime(&ctx->stats.ms_model, ctx->ev[1], ctx->ev[2]);
@@ -807,156 +841,7 @@ int encode_slices(tkz_ctx* ctx, const DevModel& m, const uint8_t* d_text, const 
     out->attention_mask = (P.outputs & TKZ_OUT_ATTENTION) ? eo.attention : nullptr;
     out->type_ids = (P.outputs & TKZ_OUT_TYPE_IDS) ? eo.type_ids : nullptr;
     out->special_tokens_mask = (P.outputs & TKZ_OUT_SPECIAL) ? eo.special : nullptr;
-    return TKZ_OK;
-}
-
-// The dedup pipeline (tkz_dedup.cuh).  Returns TKZ_RETRY_NO_DEDUP when the long list overflowed.
-int encode_dedup(tkz_ctx* ctx, const DevModel& m, const uint8_t* d_text, const uint64_t* d_doc_off, uint32_t nd, uint64_t N,
-                 const tkz_encode_params& P, tkz_batch_result* out, uint64_t& launches) {
-    cudaStream_t st = ctx->stream;
-    unsigned long long* ctrl = (unsigned long long*)ctx->a_ctrl.p;
-    unsigned long long* hctrl = (unsigned long long*)ctx->h_ctrl.p;
-    const uint64_t n_docs = nd;
-    const uint32_t n_tiles = (uint32_t)(N / DT_TILE + 1);
-    uint64_t want = N / 8; if (want < (1u << 16)) want = 1u << 16; if (want > (1u << 24)) want = 1u << 24;
-    const uint32_t tcap = pow2_at_least(want);
-    const uint32_t long_cap = (uint32_t)(N / 16 + 1024);
-    const uint32_t mcap = tcap >= (1u << 17) ? tcap / 8 : (1u << 14);          // medium-word slots behind the short-word slots
-    TRY(ensure(ctx, ctx->a_table, ((size_t)tcap + mcap) * sizeof(DedupSlot)));
-    TRY(ensure(ctx, ctx->a_uniq, ((size_t)tcap + mcap) * 4));
-    TRY(ensure(ctx, ctx->a_long_start, (size_t)long_cap * 4));
-    TRY(ensure(ctx, ctx->a_long_end, (size_t)long_cap * 4));
-    TRY(ensure(ctx, ctx->a_tile_words, (size_t)n_tiles * DT_WCAP * 4));
-    TRY(ensure(ctx, ctx->a_tile_nwords, ((size_t)n_tiles + 2) * 4));
-    TRY(ensure(ctx, ctx->a_tile_ntok, ((size_t)n_tiles + 2) * 4));
-    TRY(ensure(ctx, ctx->a_doc_word_ref, (n_docs + 2) * 4));
-    TRY(ensure(ctx, ctx->a_doc_tok_local, (n_docs + 2) * 4));
-    TRY(ensure(ctx, ctx->a_doc_tok_start, (n_docs + 2) * 4));
-    TRY(ensure(ctx, ctx->a_doc_real, (n_docs + 2) * 4));
-    TRY(ensure(ctx, ctx->a_tile_doc_lo, ((size_t)n_tiles + 2) * 4));
-    TRY(ensure(ctx, ctx->O().doc_tok_off, (n_docs + 1) * 8));
-    TRY(ensure(ctx, ctx->a_scan_tmp, (scan_tmp_elems(n_tiles) + scan_tmp_elems(n_docs)) * 8));
-    CK(cudaMemsetAsync(ctx->a_table.p, 0, ((size_t)tcap + mcap) * sizeof(DedupSlot), st));
-    DedupArgs da{};
-    da.text = d_text; da.n = N; da.doc_off = d_doc_off; da.n_docs = nd;
-    da.table = (DedupSlot*)ctx->a_table.p; da.table_mask = tcap - 1;
-    da.med_base = tcap; da.med_mask = mcap - 1; da.n_uniq_med = (unsigned int*)(ctrl + 6) + 1;
-    da.uniq_slots = (uint32_t*)ctx->a_uniq.p; da.n_uniq = (unsigned int*)(ctrl + 6);
-    da.long_start = (uint32_t*)ctx->a_long_start.p; da.long_end = (uint32_t*)ctx->a_long_end.p; da.n_long = (unsigned int*)(ctrl + 7);
-    da.long_cap = long_cap; da.overflow = (unsigned int*)(ctrl + 8);
-    da.tile_words = (uint32_t*)ctx->a_tile_words.p; da.tile_nwords = (uint32_t*)ctx->a_tile_nwords.p; da.doc_word_ref = (uint32_t*)ctx->a_doc_word_ref.p;
-    da.tile_doc_lo = (const uint32_t*)ctx->a_tile_doc_lo.p;
-    tile_doc_index_kernel<<<(n_tiles + 1 + 255) / 256, 256, 0, st>>>(d_doc_off, nd, n_tiles, DT_TILE, (uint32_t*)ctx->a_tile_doc_lo.p); launches++;
-    {
-        const bool nid = m.norm_identity != 0, iso = ctx->has_iso;
-        if (nid && !iso) tile_split_dedup_kernel<true, false><<<n_tiles, DT_THREADS, 0, st>>>(m, da);
-        else if (nid) tile_split_dedup_kernel<true, true><<<n_tiles, DT_THREADS, 0, st>>>(m, da);
-        else if (!iso) tile_split_dedup_kernel<false, false><<<n_tiles, DT_THREADS, 0, st>>>(m, da);
-        else tile_split_dedup_kernel<false, true><<<n_tiles, DT_THREADS, 0, st>>>(m, da);
-        launches++;
-    }
-    if (m.kind == TKZ_MODEL_BPE) { len_class_count_kernel<<<128, 256, 0, st>>>(da.long_start, da.long_end, 0, da.n_long, ctrl + 13); launches++; }
-    TRY(readback(ctx, hctrl + 16, ctrl + 6, 3 * 8));
-    TRY(readback(ctx, hctrl + 24, ctrl + 13, 3 * 8));
-    CK(cudaEventRecord(ctx->ev[1], st));
-    CK(cudaStreamSynchronize(st));
-    const uint32_t n_uniq = (uint32_t)hctrl[16], n_uniq_med = (uint32_t)(hctrl[16] >> 32), n_long = (uint32_t)hctrl[17];
-    if (hctrl[18] != 0) return TKZ_RETRY_NO_DEDUP;
-
-    // ---- P2: the model on unique words (identity byte map: keys are stored normalised) and on the long list
-    DevModel mu = m; mu.lut = (const uint8_t*)ctx->t_lut_post.p;
-    TRY(ensure(ctx, ctx->a_upool, ((size_t)(n_uniq - n_uniq_med) * DT_MAX_SHORT + (size_t)n_uniq_med * DT_MAX_MED + 16) * 8));
-    TRY(ensure(ctx, ctx->a_long_ntok, ((size_t)n_long + 2) * 4));
-    if (n_uniq) {
-        UniqueArgs ua{d_text, m.lut, tcap, (DedupSlot*)ctx->a_table.p, (const uint32_t*)ctx->a_uniq.p, n_uniq, (unsigned long long*)ctx->a_upool.p,
-                      (unsigned int*)(ctrl + 9), (unsigned int*)(ctrl + 1)};
-        uint64_t blocks = ((uint64_t)n_uniq + UQ_WARPS - 1) / UQ_WARPS;
-        const uint64_t cap = (uint64_t)ctx->sm_count * 8; if (blocks > cap) blocks = cap;
-        if (m.kind == TKZ_MODEL_BPE) bpe_unique_kernel<<<(unsigned)blocks, UQ_WARPS * 32, 0, st>>>(mu, ua);
-        else wordpiece_unique_kernel<<<(unsigned)blocks, UQ_WARPS * 32, 0, st>>>(mu, ua);
-        launches++;
-    }
-    if (n_long) {
-        TRY(ensure(ctx, ctx->a_pool_id, N * 4));
-        TRY(ensure(ctx, ctx->a_pool_s, N * 4));
-        TRY(ensure(ctx, ctx->a_pool_e, N * 4));
-        if (m.kind == TKZ_MODEL_BPE) {
-            TRY(launch_bpe(ctx, m, d_text, da.long_start, da.long_end, n_long, (uint32_t*)ctx->a_long_ntok.p, ctrl, 5, 1, hctrl + 24, N, launches));
-        } else {
-            WpArgs a{d_text, da.long_start, da.long_end, n_long, (uint32_t*)ctx->a_pool_id.p, (uint32_t*)ctx->a_pool_s.p, (uint32_t*)ctx->a_pool_e.p,
-                     (uint32_t*)ctx->a_long_ntok.p, (unsigned int*)(ctrl + 5), ctrl, 1};
-            uint64_t blocks = ((uint64_t)n_long + WP_WARPS - 1) / WP_WARPS;
-            const uint64_t cap = (uint64_t)ctx->sm_count * 8; if (blocks > cap) blocks = cap;
-            wordpiece_warp_kernel<<<(unsigned)blocks, WP_WARPS * 32, 0, st>>>(m, a); launches++;
-        }
-    }
-    CK(cudaEventRecord(ctx->ev[2], st));
-
-    // ---- P3a: tokens per tile, per document; CSR offsets
-    EmitParams ep{P.has_truncation, P.max_length, P.has_padding, P.pad_length, P.pad_id, P.pad_type_id, P.pad_left, P.outputs};
-    TileOutArgs ta{};
-    ta.doc_off = d_doc_off; ta.n_docs = nd; ta.n = N;
-    ta.table = (const DedupSlot*)ctx->a_table.p; ta.upool = (const unsigned long long*)ctx->a_upool.p;
-    ta.long_start = da.long_start; ta.long_ntok = (const uint32_t*)ctx->a_long_ntok.p;
-    ta.pool_id = (const uint32_t*)ctx->a_pool_id.p; ta.pool_s = (const uint32_t*)ctx->a_pool_s.p; ta.pool_e = (const uint32_t*)ctx->a_pool_e.p;
-    ta.tile_words = da.tile_words; ta.tile_nwords = da.tile_nwords; ta.doc_word_ref = da.doc_word_ref; ta.tile_doc_lo = da.tile_doc_lo;
-    ta.tile_ntok = (uint32_t*)ctx->a_tile_ntok.p; ta.doc_tok_local = (uint32_t*)ctx->a_doc_tok_local.p;
-    ta.doc_tok_start = (uint32_t*)ctx->a_doc_tok_start.p; ta.doc_tok_off = (unsigned long long*)ctx->O().doc_tok_off.p;
-    ta.errw = ctrl; ta.err_code = m.kind == TKZ_MODEL_BPE ? TKZ_ECODE_UTF8 : TKZ_ECODE_UNK;
-    tile_count_kernel<<<n_tiles, DT_THREADS, 0, st>>>(ta); launches++;
-    tile_words_total_kernel<<<64, 256, 0, st>>>(da.tile_nwords, n_tiles, ctrl); launches++;
-    launches += exclusive_scan<uint32_t>(ta.tile_ntok, n_tiles, ta.tile_ntok, (unsigned long long*)ctx->a_scan_tmp.p, st);
-    doc_finish_kernel<<<(nd + 1 + 255) / 256, 256, 0, st>>>(ta, ep, (uint32_t*)ctx->a_doc_real.p); launches++;
-    launches += exclusive_scan<unsigned long long>(ta.doc_tok_off, n_docs, ta.doc_tok_off, (unsigned long long*)ctx->a_scan_tmp.p, st);
-    gather_scalars_dedup_kernel<<<1, 1, 0, st>>>(ctrl, ta.tile_ntok, n_tiles, ta.doc_tok_off, nd, da.doc_word_ref); launches++;
-    TRY(readback(ctx, hctrl, ctrl, 11 * 8));
-    CK(cudaStreamSynchronize(st));
-    const unsigned long long errw = hctrl[0];
-    const uint64_t T_real = hctrl[2], T = hctrl[3];
-    ctx->stats.n_words = hctrl[10]; ctx->stats.n_unique_words = n_uniq; ctx->stats.n_long_words = n_long;
-    if (errw != TKZ_ERRW_NONE) {
-        out->err_doc = (int64_t)hctrl[4];
-        const uint32_t code = (uint32_t)(errw & 0xFF);
-        ctx->err = code == TKZ_ECODE_UTF8 ? "invalid UTF-8 in a BPE pre-token (reference behaviour undefined)" : "MissingUnkToken";
-        ctx->stats.kernel_launches = launches;
-        return code == TKZ_ECODE_UTF8 ? TKZ_ERR_INVALID_UTF8 : TKZ_ERR_MISSING_UNK;
-    }
-    CK(cudaEventRecord(ctx->ev[3], st));
-
-    // ---- P3b: emit
-    TRY(ensure(ctx, ctx->O().ids, T * 4));
-    if (P.outputs & TKZ_OUT_OFFSETS) TRY(ensure(ctx, ctx->O().off, T * 8));
-    if (P.outputs & TKZ_OUT_ATTENTION) TRY(ensure(ctx, ctx->O().attn, T * 4));
-    if (P.outputs & TKZ_OUT_TYPE_IDS) TRY(ensure(ctx, ctx->O().type, T * 4));
-    if (P.outputs & TKZ_OUT_SPECIAL) TRY(ensure(ctx, ctx->O().special, T * 4));
-    EmitOut eo{(uint32_t*)ctx->O().ids.p, (uint32_t*)ctx->O().off.p, (uint32_t*)ctx->O().attn.p, (uint32_t*)ctx->O().type.p,
-               (uint32_t*)ctx->O().special.p};
-    const uint32_t big_cap = (uint32_t)(N / EMIT_BIG + 16);
-    TRY(ensure(ctx, ctx->a_big, (size_t)big_cap * sizeof(uint4)));
-    ta.big = BigList{(uint4*)ctx->a_big.p, (unsigned int*)(ctrl + 9) + 1, big_cap};       // upper half of ctrl[9] (zeroed by ctrl_reset)
-    if (!P.has_truncation && !P.has_padding) tile_emit_kernel<true><<<n_tiles, DT_THREADS, 0, st>>>(ta, ep, eo);
-    else tile_emit_kernel<false><<<n_tiles, DT_THREADS, 0, st>>>(ta, ep, eo);
-    launches++;
-    if (n_long) { emit_big_kernel<<<ctx->sm_count * 4, 256, 0, st>>>(ep, eo, ta.big, ta.pool_id, ta.pool_s, ta.pool_e); launches++; }
-    if (P.has_padding && nd) {
-        emit_pad_real_kernel<<<(unsigned)(((uint64_t)nd * 32 + 255) / 256), 256, 0, st>>>(ep, eo, nd, (const uint32_t*)ctx->a_doc_real.p, ta.doc_tok_off); launches++;
-    }
-    CK(cudaGetLastError());
-    CK(cudaEventRecord(ctx->ev[4], st));
-    CK(cudaStreamSynchronize(st));
-    ctx->stats.kernel_launches = launches;
-    cudaEventElapsedTime(&ctx->stats.ms_split, ctx->ev[0], ctx->ev[1]);
-    cudaEventElapsedTime(&ctx->stats.ms_model, ctx->ev[1], ctx->ev[2]);
-    cudaEventElapsedTime(&ctx->stats.ms_scan, ctx->ev[2], ctx->ev[3]);
-    cudaEventElapsedTime(&ctx->stats.ms_emit, ctx->ev[3], ctx->ev[4]);
-    cudaEventElapsedTime(&ctx->stats.ms_total, ctx->ev[0], ctx->ev[4]);
-    out->n_docs = n_docs; out->n_tokens = T; out->n_real_tokens = T_real;
-    out->doc_tok_off = (const uint64_t*)ta.doc_tok_off;
-    out->ids = eo.ids;
-    out->offsets = (P.outputs & TKZ_OUT_OFFSETS) ? eo.offsets : nullptr;
-    out->attention_mask = (P.outputs & TKZ_OUT_ATTENTION) ? eo.attention : nullptr;
-    out->type_ids = (P.outputs & TKZ_OUT_TYPE_IDS) ? eo.type_ids : nullptr;
-    out->special_tokens_mask = (P.outputs & TKZ_OUT_SPECIAL) ? eo.special : nullptr;
+    out->offsets_packed = (P.outputs & TKZ_OUT_OFFSETS_PACKED) ? eo.offsets16 : nullptr;
     return TKZ_OK;
 }
 
@@ -965,7 +850,7 @@ int encode_device_impl(tkz_ctx* ctx, const uint8_t* d_text, const uint64_t* d_do
     memset(out, 0, sizeof *out);
     out->err_doc = -1;
     if (!ctx->has_model) { ctx->err = "no model uploaded"; return TKZ_ERR_INVALID_ARG; }
-    ctx->grid_used = false;
+    ctx->grid_used = false; ctx->retried = false;
     if (N >= 0xFFFFF000ull) { ctx->err = "batch text must be < 4 GiB (u32 offsets, types.zig:4-6): split the batch"; return TKZ_ERR_INVALID_ARG; }
     if (n_docs >= 0xFFFFFFF0ull) { ctx->err = "too many documents in one batch"; return TKZ_ERR_INVALID_ARG; }
     CK(cudaSetDevice(ctx->device));
@@ -1009,20 +894,19 @@ int encode_device_impl(tkz_ctx* ctx, const uint8_t* d_text, const uint64_t* d_do
         m = ctx->dm_post;
     }
 
-    // ---- dedup pipeline (tkz_dedup.cuh) whenever there is a pre-tokenizer; falls through to the per-occurrence
-    //      pipeline below only if its long list overflowed (pathological: > N/16 long words)
-    ctx->stats.path = m.has_pretok && ctx->use_dedup ? 1 : 0;
-    if (m.has_pretok && ctx->use_dedup && ctx->use_slices) {
-        int rc = encode_slices(ctx, m, d_text, d_doc_off, nd, N, P, out, launches);
-        if (rc != TKZ_RETRY_MULTIPASS) return rc;
-        ctx->stats.path = 1;
-        ctrl_reset_kernel<<<1, 1, 0, st>>>(ctrl); launches++;
-    }
+    // ---- slice pipeline (tkz_slices.cuh) whenever there is a pre-tokenizer; TKZ_NO_DEDUP=1 keeps the per-occurrence
+    //      pipeline below for A/B tests
+    ctx->stats.path = 0;
     if (m.has_pretok && ctx->use_dedup) {
-        int rc = encode_dedup(ctx, m, d_text, d_doc_off, nd, N, P, out, launches);
-        if (rc != TKZ_RETRY_NO_DEDUP) return rc;
+        const ClassRanges& cr = ctx->dm.norm_has_drop ? ctx->cr_post : ctx->cr;      // (K0 ran: the text is already normalised)
+        int rc = encode_slices(ctx, m, cr, d_text, d_doc_off, nd, N, P, false, out, launches);
+        if (rc != TKZ_RETRY_WORST) return rc;
+        ctx->retried = true;
         ctrl_reset_kernel<<<1, 1, 0, st>>>(ctrl); launches++;
+        return encode_slices(ctx, m, cr, d_text, d_doc_off, nd, N, P, true, out, launches);
     }
+    // no pre-tokenizer: a pre-token can have any length, offsets are delivered as 32-bit pairs
+    if (P.outputs & TKZ_OUT_OFFSETS_PACKED) P.outputs = (P.outputs & ~TKZ_OUT_OFFSETS_PACKED) | TKZ_OUT_OFFSETS;
 
     // ---- K1: pre-token spans
     uint64_t W = 0;
@@ -1114,7 +998,7 @@ int encode_device_impl(tkz_ctx* ctx, const uint8_t* d_text, const uint64_t* d_do
     if (P.outputs & TKZ_OUT_TYPE_IDS) TRY(ensure(ctx, ctx->O().type, T * 4));
     if (P.outputs & TKZ_OUT_SPECIAL) TRY(ensure(ctx, ctx->O().special, T * 4));
     EmitOut eo{(uint32_t*)ctx->O().ids.p, (uint32_t*)ctx->O().off.p, (uint32_t*)ctx->O().attn.p, (uint32_t*)ctx->O().type.p,
-               (uint32_t*)ctx->O().special.p};
+               (uint32_t*)ctx->O().special.p, nullptr};
     if (nw) {
         const uint32_t big_cap = (uint32_t)(N / EMIT_BIG + 16);
         TRY(ensure(ctx, ctx->a_big, (size_t)big_cap * sizeof(uint4)));
@@ -1144,6 +1028,7 @@ int encode_device_impl(tkz_ctx* ctx, const uint8_t* d_text, const uint64_t* d_do
     out->attention_mask = (P.outputs & TKZ_OUT_ATTENTION) ? eo.attention : nullptr;
     out->type_ids = (P.outputs & TKZ_OUT_TYPE_IDS) ? eo.type_ids : nullptr;
     out->special_tokens_mask = (P.outputs & TKZ_OUT_SPECIAL) ? eo.special : nullptr;
+    out->offsets_packed = nullptr;
     return TKZ_OK;
 }
 
@@ -1183,22 +1068,23 @@ int encode_host_single(tkz_ctx* ctx, const uint8_t* text, const uint64_t* doc_of
     int rc = encode_device_impl(ctx, (const uint8_t*)ctx->a_text.p, (const uint64_t*)ctx->a_doc_off.p, n_docs, N, params, &dev);
     *out = dev;
     out->doc_tok_off = nullptr; out->ids = nullptr; out->offsets = nullptr; out->attention_mask = nullptr; out->type_ids = nullptr;
-    out->special_tokens_mask = nullptr;
+    out->special_tokens_mask = nullptr; out->offsets_packed = nullptr;
     if (rc != TKZ_OK) return rc;
     const uint64_t T = dev.n_tokens;
     cudaStream_t st = ctx->stream;
     TRY(ensure_host(ctx, ctx->h_doc_tok_off, (n_docs + 1) * 8));
     CK(cudaMemcpyAsync(ctx->h_doc_tok_off.p, dev.doc_tok_off, (n_docs + 1) * 8, cudaMemcpyDeviceToHost, st));
     out->doc_tok_off = (const uint64_t*)ctx->h_doc_tok_off.p;
-    struct { const uint32_t* src; HostBuf* hb; const uint32_t** dst; size_t elem; } cp[] = {
-        {dev.ids, &ctx->h_ids, &out->ids, 4}, {dev.offsets, &ctx->h_off, &out->offsets, 8},
-        {dev.attention_mask, &ctx->h_attn, &out->attention_mask, 4}, {dev.type_ids, &ctx->h_type, &out->type_ids, 4},
-        {dev.special_tokens_mask, &ctx->h_special, &out->special_tokens_mask, 4}};
+    struct { const void* src; HostBuf* hb; const void** dst; size_t elem; } cp[] = {
+        {dev.ids, &ctx->h_ids, (const void**)&out->ids, 4}, {dev.offsets, &ctx->h_off, (const void**)&out->offsets, 8},
+        {dev.attention_mask, &ctx->h_attn, (const void**)&out->attention_mask, 4}, {dev.type_ids, &ctx->h_type, (const void**)&out->type_ids, 4},
+        {dev.special_tokens_mask, &ctx->h_special, (const void**)&out->special_tokens_mask, 4},
+        {dev.offsets_packed, &ctx->h_off16, (const void**)&out->offsets_packed, 2}};
     for (auto& c : cp) {
         if (!c.src) continue;
         TRY(ensure_host(ctx, *c.hb, T * c.elem));
         if (T) CK(cudaMemcpyAsync(c.hb->p, c.src, T * c.elem, cudaMemcpyDeviceToHost, st));
-        *c.dst = (const uint32_t*)c.hb->p;
+        *c.dst = c.hb->p;
     }
     CK(cudaStreamSynchronize(st));
     return TKZ_OK;
@@ -1208,7 +1094,7 @@ int encode_host_single(tkz_ctx* ctx, const uint8_t* text, const uint64_t* doc_of
 // their own streams while the kernels of chunk i run (PCIe is full duplex).  Input and output device buffers are
 // double-buffered; results land in one set of pinned host arrays at their final positions.
 int encode_host_chunked(tkz_ctx* ctx, const uint8_t* text, const uint64_t* doc_off, uint64_t n_docs, uint64_t N,
-                        const tkz_encode_params* params, tkz_batch_result* out) {
+                        const tkz_encode_params* params_in, tkz_batch_result* out) {
     memset(out, 0, sizeof *out);
     out->err_doc = -1;
     // chunk boundaries (document indices)
@@ -1220,7 +1106,10 @@ int encode_host_chunked(tkz_ctx* ctx, const uint8_t* text, const uint64_t* doc_o
         cb.push_back(lo);
     }
     const size_t nc = cb.size() - 1;
-    uint32_t outputs = params ? params->outputs : 0; if (outputs == 0) outputs = TKZ_OUT_ALL; outputs |= TKZ_OUT_IDS;
+    tkz_encode_params P{};
+    if (params_in) P = *params_in;
+    if (P.outputs == 0) P.outputs = TKZ_OUT_ALL;
+    P.outputs |= TKZ_OUT_IDS;
     TRY(ensure_host(ctx, ctx->h_doc_tok_off, (n_docs + 1) * 8));
     uint64_t* h_dto = (uint64_t*)ctx->h_doc_tok_off.p;
     std::vector<uint64_t> tok_base(nc + 1, 0);
@@ -1237,6 +1126,7 @@ int encode_host_chunked(tkz_ctx* ctx, const uint8_t* text, const uint64_t* doc_o
         CK(cudaEventRecord(ctx->ev_h2d[b], ctx->s_h2d));
         return TKZ_OK;
     };
+restart:
     TRY(stage_in(0));
     uint64_t T_total = 0, T_real = 0;
     for (size_t i = 0; i < nc; i++) {
@@ -1252,12 +1142,18 @@ int encode_host_chunked(tkz_ctx* ctx, const uint8_t* text, const uint64_t* doc_o
         CK(cudaEventSynchronize(ctx->ev_d2h[b]));              // output set b is free once chunk i-2 has been copied out
         ctx->out_sel = b;
         tkz_batch_result dev{};
-        int rc = encode_device_impl(ctx, (const uint8_t*)ctx->in_text[b].p, (const uint64_t*)ctx->in_doc_off[b].p, nd, nb, params, &dev);
+        int rc = encode_device_impl(ctx, (const uint8_t*)ctx->in_text[b].p, (const uint64_t*)ctx->in_doc_off[b].p, nd, nb, &P, &dev);
         if (rc != TKZ_OK) {
             cudaStreamSynchronize(ctx->s_h2d); cudaStreamSynchronize(ctx->s_d2h);
             out->err_doc = dev.err_doc >= 0 ? (int64_t)d0 + dev.err_doc : -1;
             ctx->out_sel = 0;
             return rc;
+        }
+        if ((P.outputs & TKZ_OUT_OFFSETS_PACKED) && !dev.offsets_packed) {
+            // a pre-token of 256 bytes or more in this chunk: the whole call delivers 32-bit offsets, start again
+            CK(cudaStreamSynchronize(ctx->s_h2d)); CK(cudaStreamSynchronize(ctx->s_d2h));
+            P.outputs = (P.outputs & ~TKZ_OUT_OFFSETS_PACKED) | TKZ_OUT_OFFSETS;
+            goto restart;
         }
         const uint64_t T = dev.n_tokens;
         tok_base[i] = T_total;
@@ -1265,9 +1161,9 @@ int encode_host_chunked(tkz_ctx* ctx, const uint8_t* text, const uint64_t* doc_o
         uint64_t est = T_total + T;
         if (i == 0 && nb) est = (uint64_t)((double)T * ((double)N / (double)nb) * 1.03) + 4096;
         if (est < T_total + T) est = T_total + T;
-        struct { const uint32_t* src; HostBuf* hb; size_t elem; } cp[] = {
+        struct { const void* src; HostBuf* hb; size_t elem; } cp[] = {
             {dev.ids, &ctx->h_ids, 4}, {dev.offsets, &ctx->h_off, 8}, {dev.attention_mask, &ctx->h_attn, 4},
-            {dev.type_ids, &ctx->h_type, 4}, {dev.special_tokens_mask, &ctx->h_special, 4}};
+            {dev.type_ids, &ctx->h_type, 4}, {dev.special_tokens_mask, &ctx->h_special, 4}, {dev.offsets_packed, &ctx->h_off16, 2}};
         for (auto& c : cp) {
             if (!c.src) continue;
             TRY(ensure_host_keep(ctx, *c.hb, est * c.elem, T_total * c.elem));
@@ -1284,6 +1180,7 @@ int encode_host_chunked(tkz_ctx* ctx, const uint8_t* text, const uint64_t* doc_o
     for (size_t i = 1; i < nc; i++) { const uint64_t base = tok_base[i]; for (uint64_t d = cb[i]; d < cb[i + 1]; d++) h_dto[d] += base; }
     h_dto[n_docs] = T_total;
     ctx->out_sel = 0;
+    const uint32_t outputs = P.outputs;
     out->n_docs = n_docs; out->n_tokens = T_total; out->n_real_tokens = T_real;
     out->doc_tok_off = h_dto;
     out->ids = (const uint32_t*)ctx->h_ids.p;
@@ -1291,6 +1188,7 @@ int encode_host_chunked(tkz_ctx* ctx, const uint8_t* text, const uint64_t* doc_o
     out->attention_mask = (outputs & TKZ_OUT_ATTENTION) ? (const uint32_t*)ctx->h_attn.p : nullptr;
     out->type_ids = (outputs & TKZ_OUT_TYPE_IDS) ? (const uint32_t*)ctx->h_type.p : nullptr;
     out->special_tokens_mask = (outputs & TKZ_OUT_SPECIAL) ? (const uint32_t*)ctx->h_special.p : nullptr;
+    out->offsets_packed = (outputs & TKZ_OUT_OFFSETS_PACKED) ? (const uint16_t*)ctx->h_off16.p : nullptr;
     return TKZ_OK;
 }
 

@@ -35,7 +35,8 @@ __global__ void doc_len_kernel(EmitParams p, const uint32_t* __restrict__ word_t
     doc_len[d] = doc_out_len(p, t, &kept);
 }
 
-struct EmitOut { uint32_t* ids; uint32_t* offsets; uint32_t* attention; uint32_t* type_ids; uint32_t* special; };
+struct EmitOut { uint32_t* ids; uint32_t* offsets; uint32_t* attention; uint32_t* type_ids; uint32_t* special;
+                 uint16_t* offsets16; };     // offsets16: one u16 per token (start | end << 8), only when every pre-token is < 256 bytes
 
 // words with more than EMIT_BIG tokens (whole documents, MiB-long unbroken words) are not copied by one warp: they are
 // queued here and copied by the whole grid (emit_big_kernel)

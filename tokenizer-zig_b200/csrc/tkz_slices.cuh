@@ -3,32 +3,35 @@
 //
 //   pass A  slice_words_kernel  normalise (config.zig:364-379) + pre-tokenize (config.zig:405-450, pretokenizer.zig:49-241)
 //                               + model per pre-token (bpe.zig:173-263 / wordpiece.zig:141-222):
-//           1  two 16-byte vector loads per lane (32 bytes), byte classes from a shared-memory LUT (or, when the byte map
-//              is the identity, from 256-bit class tables held in registers and read by shuffle), normalised slice kept
-//              in shared memory
-//           2  word-start masks (neighbour bits by shuffle), ballot prefix, list of the words that START in the slice
+//           0  the slice (+ 16 bytes before, 48 behind) arrives in shared memory by ONE bulk copy (cp.async.bulk +
+//              mbarrier, double-buffered per warp: slice i+1 is in flight while slice i is processed)
+//           1  byte classes: 4 bytes per instruction (range compares on packed bytes, class sets given as byte ranges at
+//              upload) or, for arbitrary tables, a per-byte look-up; the byte map is applied in place
+//           2  word-start masks (neighbour bits by shuffle), prefix over lanes, list of the words that START in the slice
 //           3  32 words per round, one per lane: 128-bit key from shared memory, ONE 32-byte probe of the per-batch word
-//              table in L2 returns key + token value (straight-line; everything else sits behind one warp vote).  First sight of a word: atom.cas.b128 claims the slot, the claiming warp runs
-//              the model on it right there (warp-cooperative, symbols in shared memory) and publishes the value; a word
-//              whose owner is still computing is polled after the warp has published its own words (owners never wait,
-//              so polling cannot deadlock).  Words of 16..31 bytes go the same way through 64-byte slots.  Result: one 8-byte entry per word, written in text order to a compact
-//              per-slice list, tokens per slice, token prefix at every document start.
+//              table in L2 returns key + tokens (words of one or two tokens carry them in the slot).  First sight of a
+//              word: atom.cas.b128 claims the slot, the claiming warp runs the model on it right there (warp-cooperative,
+//              symbols in shared memory) and publishes the value; a word whose owner is still computing is polled after
+//              the warp has published its own words (owners never wait, so polling cannot deadlock).  Words of 16..31
+//              bytes go the same way through 64-byte slots.  Result: the TOKENS of the slice's words, in text order, in
+//              a compact per-slice run of the token stream (id u32 + offsets u8,u8), the token count of the slice and the
+//              token prefix at every document start.
 //   [word-list kernels on the few pre-tokens longer than TW_MAX_INLINE bytes (tkz_bpe.cuh / tkz_bpe_block.cuh /
 //    tkz_wordpiece.cuh), long_fix_kernel adds their token counts]
 //   scan over slices
-//   pass B  slice_emit_kernel   Encoding.fromTokens + truncate + pad (encoding.zig:246-294, 363-463): reads the entries,
-//                               warp scan, stages tokens in shared memory and writes ids / offsets / attention with
-//                               16-byte coalesced stores
+//   pass B  slice_emit_kernel   Encoding.fromTokens + truncate + pad (encoding.zig:246-294, 363-463): a streaming copy of
+//                               the token stream to its final position, widened to the arrays the call asked for
 //
 // Exact because the model is a pure function of the normalised pre-token bytes and the reference's offsets are pre-token
 // relative (lib.zig:133-137 never adds the pre-token start): every occurrence of a word gets identical records.  The table
 // key is the word itself (<= 15 bytes + length compared as 128 bits, 16..31 bytes as 256 bits) or, for 32..64 bytes, a 64-bit
 // tag verified byte by byte against a representative occurrence -- there is no hash-collision case.  The table lives for one batch.
 //
-// History (profiles/r01_v11_*, r01_v12_*): a one-launch variant (pass A + decoupled look-back + emit) measured 2x slower
-// than the multi-pass pipeline -- slices that run the model take 5-10 us longer than their neighbours and every later
-// tile waits for them in the look-back; a block-per-4-KiB-tile variant of the two passes ran at 31 % occupancy because a
-// block keeps its registers and shared memory until its slowest warp is done.  Hence warp-autonomous slices.
+// History (profiles/r01_*): a one-launch variant (pass A + decoupled look-back + emit) measured 2x slower -- slices that
+// run the model take 5-10 us longer than their neighbours and every later tile waits for them; a block-per-4-KiB-tile
+// variant ran at 31 % occupancy because a block keeps its registers and shared memory until its slowest warp is done.
+// Hence warp-autonomous slices.  Round 1 handed 8-byte word entries from A to B and let B expand them (1.37 G warp
+// instructions for 235 M tokens); now A writes tokens and B only moves them.
 #pragma once
 #include "tkz_bpe.cuh"
 #include "tkz_common.cuh"
@@ -39,23 +42,26 @@
 namespace tkz {
 
 constexpr int TW_THREADS = 256, TW_WARPS = 8, TW_SEG = 32, TW_SLICE = 32 * TW_SEG;      // slice = 1 KiB = one 32-byte segment per lane
-constexpr int TW_BLOCKS_PER_SM = 4;                // pass A: 64 registers per thread, 38 KB of shared memory per block (5 / 6 blocks spill: slower)
-constexpr uint32_t TW_ENT_CHUNK = 4096;            // entries a warp claims from the entry list with one atomic (then sub-allocates)
+constexpr int TW_PRE = 16, TW_POST = 48, TW_STAGE = TW_PRE + TW_SLICE + TW_POST;         // staged window: 16 B before, 48 B behind the slice
+constexpr int TW_BLOCKS_PER_SM = 4;                // pass A: 64 registers per thread
+constexpr uint32_t TW_TOK_CHUNK = 16384;           // tokens a warp claims from the token stream with one atomic (then sub-allocates)
+constexpr uint32_t TW_SLICE_TOK_MAX = TW_SLICE + 256;   // tokens the words that start in one slice can have (<= their bytes)
 constexpr uint32_t TW_MAX_SHORT = 15;             // bytes next to the length byte in the 128-bit key
 constexpr uint32_t TW_MAX_MED = 64;               // words of 32..64 bytes: 64-bit tag + byte verification; symbols fit shared memory
-constexpr uint32_t TW_MAX_INLINE = 256;           // longest pre-token a warp tokenizes inside pass A
+constexpr uint32_t TW_MAX_INLINE = 255;           // longest pre-token a warp tokenizes inside pass A (offsets fit a byte)
 constexpr int TW_MAX_PROBE = 32;
-constexpr uint32_t TW_POOLF = 0x80000000u;        // value / entry flag: token records are in upool[a .. a + ntok)
-constexpr uint32_t TW_LONGF = 0x40000000u;        // entry flag: a = index into the long list
-constexpr uint32_t TW_NT1_ERR = 0x3FFFu;          // (ntok + 1) field of a word the model rejected
+constexpr uint32_t TW_POOLF = 0x80000000u;        // value flag: token records are in upool[a .. a + ntok)
+constexpr uint32_t TW_ERRF = 0x40000000u;         // value flag: the model rejected the word
+constexpr uint32_t TW_LONGF = 0x20000000u;        // in registers only: the word joins the long list (a = its length)
 constexpr uint32_t TW_NONE = 0xFFFFFFFFu;
+constexpr uint32_t TW_MAX_SLICE_LONG = 4;         // long words (> 255 bytes) that can START in one 1 KiB slice
 
 // 32-byte slot = one L2 sector.  Short words (<= 15 bytes): k0..k3 = the normalised bytes, length in the top byte of k3
 // (so a used key is never all zero).  Medium words live in their own slot range: k0,k1 = 64-bit tag (top bit set),
 // k2,k3 = representative occurrence (text position, length), published after the tag.
-// Value, one 8-byte store by the owner: b = (ntok + 1) << 16 | end << 8 | start [| TW_POOLF]; b == 0: not computed yet.
-// ntok == 1 without TW_POOLF: a = the token id, offsets (start, end) in b.  With TW_POOLF: a = first record in upool.
-// Entry of a word occurrence (pass A -> pass B): x = a, y = ntok << 16 | end << 8 | start | flags.
+// Value: b = flags | (ntok + 1) << 16 | end0 << 8 | start0; b == 0: not computed yet (the owner stores (a, b) with one
+// 8-byte store, after (c, d)).  Without TW_POOLF (0, 1 or 2 tokens): a = id of token 0, c = id of token 1,
+// d = end1 << 8 | start1.  With TW_POOLF: a = first record in upool, ntok of them.
 struct __align__(32) WordSlot { uint32_t k0, k1, k2, k3, a, b, c, d; };
 static_assert(sizeof(WordSlot) == 32, "one sector");
 
@@ -65,27 +71,40 @@ __constant__ unsigned long long c_med_pw[TW_MAX_MED];
 
 // 64-byte slot for words of 16..31 bytes (one per lane, like short words): k = [length, bytes 0..14], k2 = bytes 15..30.
 // The first half is claimed with atom.cas.b128 (length >= 16 keeps it non-zero), the owner then stores k2 and sets c;
-// a, b = the value as in WordSlot.
+// a, b = the value as in WordSlot (two-token words go to the record pool here: c is taken).
 struct __align__(64) WordSlot32 { uint32_t k[4]; uint32_t a, b, c, d; uint32_t k2[4]; uint32_t pad[4]; };
 static_assert(sizeof(WordSlot32) == 64, "two sectors");
+
+// byte classes as ranges (filled at upload when the class table allows it): non-WORD bytes are all < 0x80 and form at
+// most TW_MAX_RANGES runs per class.  add_lo / add_hi are the packed-byte addends of the range test (see tw_classify4).
+constexpr int TW_MAX_RANGES = 6;
+struct ClassRanges {
+    int usable;                                    // 0: the kernel must use the byte LUT
+    int n_delim, n_iso;
+    int norm_lower;                                // the byte map is exactly A-Z -> a-z (else identity when usable)
+    uint32_t d_lo[TW_MAX_RANGES], d_hi[TW_MAX_RANGES], i_lo[TW_MAX_RANGES], i_hi[TW_MAX_RANGES];
+};
 
 struct SliceArgs {
     const uint8_t* text; uint64_t n;
     const uint64_t* doc_off; uint32_t n_docs;
     uint32_t n_slices;
     const uint32_t* slice_doc_lo;                 // first document with doc_off >= slice start (n_slices + 1 entries)
-    WordSlot* table; uint32_t table_mask; uint32_t med_base, med_mask;
+    WordSlot* table; uint32_t table_shift; uint32_t med_base, med_mask;          // slot = hash >> table_shift
     WordSlot32* table32; uint32_t table32_mask;
     unsigned long long* upool; uint32_t upool_cap; unsigned int* upool_count;     // token records: id | start << 32 | end << 48
-    uint32_t* lscratch; uint32_t lscratch_cap; unsigned int* lscratch_count;      // symbol arrays of words of 65..256 bytes
-    uint2* ent; uint32_t ent_cap; unsigned int* ent_count;                        // word entries: warps claim TW_ENT_CHUNK at a time
-    uint32_t* slice_ent_off; uint32_t* slice_nwords; uint32_t* slice_ntok;
-    uint32_t* doc_word_ref;                       // per document: slice-local index of the first word at or after its start
-    uint32_t* doc_tok_local;                      // per document: tokens of its slice before that word
-    uint32_t* long_start; uint32_t* long_end; uint32_t* long_slice; unsigned int* n_long; uint32_t long_cap;   // long_slice = slice
+    uint32_t* lscratch;                           // per warp of the grid: 4 * 256 u32, symbol arrays of words of 65..255 bytes
+    uint32_t* tok_id; uint16_t* tok_of; uint32_t tok_cap; unsigned int* tok_count; // token stream; tok_of == nullptr: offsets not wanted
+    uint32_t* slice_tok_off; uint32_t* slice_ntok_inline; uint32_t* slice_ntok;   // slice_ntok (+ long words) is scanned -> token base
+    uint32_t* slice_long;                         // first long-list index << 3 | count of the long words that start in the slice
+    uint32_t* doc_tok_local;                      // per document: tokens of its slice before its first word
+    uint32_t* long_start; uint32_t* long_end; uint32_t* long_slice; uint32_t* long_ins; unsigned int* n_long; uint32_t long_cap;
     unsigned int* abort_flag;
     unsigned long long* errw;                     // min over failing words of (byte position << 8 | code)
     unsigned long long* n_words; unsigned int* n_uniq; unsigned int* n_uncached;
+    ClassRanges cr;
+    int has_iso;                                  // some byte is its own pre-token (punctuation split)
+    int stage_bulk;                               // 1: slices arrive by cp.async.bulk (default); 0: 16-byte loads per lane (TKZ_STAGE=ldg, A/B switch)
 };
 
 // first document that starts at or after each tile (slice) start; entry n_tiles = n_docs + 1.  One thread per tile.
@@ -97,7 +116,8 @@ __global__ void tile_doc_index_kernel(const uint64_t* __restrict__ doc_off, uint
 }
 
 struct __align__(16) SliceShared {                                      // per warp
-    uint32_t text32[(TW_SLICE + 32) / 4 + 4];             // normalised slice + 32 halo bytes
+    uint32_t raw[2][TW_STAGE / 4];                        // staged text windows (bulk copy destination), normalised in place
+    unsigned long long bar[2];                            // mbarriers of the two windows
     uint32_t cont32[(TW_SLICE + 32) / 32 + 2];            // bit p: byte p continues the word that started before it
     uint32_t docbits[(TW_SLICE + 32) / 32 + 2];           // bit p: a document starts at slice_base + p
     uint16_t wlist[TW_SLICE];                             // start positions of the slice's words (bit 15: ISOLATE byte); a round
@@ -107,12 +127,28 @@ struct __align__(16) SliceShared {                                      // per w
     uint32_t wbytes[TW_MAX_MED / 4];                      // normalised bytes of the word the warp is tokenizing
     uint32_t seg_smask[32], seg_wex[32];                  // per 32-byte segment: word-start bits, words of the slice before it
     uint32_t doc_lo_hi[2];                                // documents that start inside the slice: [lo, hi)
+    uint32_t lbuf[TW_MAX_SLICE_LONG][3];                  // long words of the slice: position, length, token index of insertion
 };
 struct BlockShared {
     uint32_t lut[256];                                    // [7:0] normalised byte, bit 8 WORD, bit 9 ISOLATE
     uint4 lenmask[16];                                    // key mask by length
     SliceShared w[TW_WARPS];
 };
+
+// ---------------------------------------------------------------- bulk copy + mbarrier (sm_90+: UBLKCP / SYNCS in SASS)
+__device__ __forceinline__ uint32_t tw_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void tw_mbar_init(unsigned long long* bar) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(tw_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tw_bulk_load(void* dst, const void* src, uint32_t bytes, unsigned long long* bar) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(tw_smem_u32(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(tw_smem_u32(dst)), "l"(src), "r"(bytes), "r"(tw_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tw_mbar_wait(unsigned long long* bar, uint32_t parity) {
+    asm volatile("{\n\t.reg .pred p;\n\tTW_WAIT_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra TW_DONE_%=;\n\tbra TW_WAIT_%=;\n\tTW_DONE_%=:\n\t}"
+                 :: "r"(tw_smem_u32(bar)), "r"(parity) : "memory");
+}
 
 __device__ __forceinline__ void tw_ld256(const WordSlot* s, uint32_t (&r)[8]) {
     asm volatile("ld.global.ca.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
@@ -123,26 +159,23 @@ __device__ __forceinline__ void tw_ld256_cg(const void* s, uint32_t (&r)[8]) {
     asm volatile("ld.global.cg.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                  : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "l"(s) : "memory");
 }
-// text is read once: 16-byte loads that do not allocate in L1, which the 212 KB of shared memory leave small and which
-// the word-table probes need (ncu, r01_v40: 22 % L1 hit rate of the global loads with allocating text loads)
-__device__ __forceinline__ uint4 tw_ld_text16(const uint8_t* p) {
+// text read by plain loads (A/B path, tails): 16 bytes that do not allocate in L1
+__device__ __forceinline__ uint4 tw_ld_text16(const uint4* p) {
     uint4 v;
     asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
     return v;
 }
-// entries are read once by pass B: no L1 allocation, the L1 is kept for the token records of frequent multi-token words
-// (measured neutral on c2b: pass B is issue / DRAM-write bound, 1.61 ms either way)
-__device__ __forceinline__ uint2 tw_ld_entry(const uint2* p) {
-    uint2 v;
-    asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
+__device__ __forceinline__ uint4 tw_ld_value(const WordSlot* s) {
+    uint4 v;
+    asm volatile("ld.global.relaxed.gpu.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(&s->a) : "memory");
     return v;
 }
-__device__ __forceinline__ uint2 tw_ld_value(const WordSlot* s) {
-    uint2 v;
-    asm volatile("ld.global.relaxed.gpu.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(&s->a) : "memory");
-    return v;
-}
-__device__ __forceinline__ void tw_st_value(WordSlot* s, uint32_t a, uint32_t b) {
+// (c, d) first, then (a, b): a reader that sees b != 0 sees the second token too
+__device__ __forceinline__ void tw_st_value(WordSlot* s, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    if (c | d) {
+        asm volatile("st.global.relaxed.gpu.v2.u32 [%0], {%1,%2};" :: "l"(&s->c), "r"(c), "r"(d) : "memory");
+        __threadfence();
+    }
     asm volatile("st.global.relaxed.gpu.v2.u32 [%0], {%1,%2};" :: "l"(&s->a), "r"(a), "r"(b) : "memory");
 }
 // returns the previous 128-bit key
@@ -154,13 +187,12 @@ __device__ __forceinline__ void tw_cas128(WordSlot* s, const uint32_t (&key)[4],
                  : "=l"(o0), "=l"(o1) : "l"(0ULL), "l"(0ULL), "l"(v0), "l"(v1), "l"(s) : "memory");
     old[0] = (uint32_t)o0; old[1] = (uint32_t)(o0 >> 32); old[2] = (uint32_t)o1; old[3] = (uint32_t)(o1 >> 32);
 }
+// multiply-add mix of the four key words, folded once; the slot is taken from the TOP bits of the last product
 __device__ __forceinline__ uint32_t tw_key_hash(uint32_t k0, uint32_t k1, uint32_t k2, uint32_t k3) {
-    uint32_t h = k0 * 0x9E3779B1u;
-    h = (h ^ k1) * 0x85EBCA77u;
-    h = (h ^ k2 ^ (h >> 15)) * 0xC2B2AE3Du;
-    h = (h ^ k3) * 0x27D4EB2Fu;
-    h ^= h >> 15; h *= 0x2C1B3C6Du; h ^= h >> 13;
-    return h;
+    uint32_t h = k0 * 0x9E3779B1u + k1 * 0x85EBCA77u;
+    h += k2 * 0xC2B2AE3Du + k3 * 0x27D4EB2Fu;
+    h ^= h >> 15;
+    return h * 0x2C1B3C6Du;
 }
 
 // model on a word of <= TW_MAX_MED normalised bytes held in shared memory; tokens in scr[0] ids, scr[1] starts, scr[2] ends
@@ -182,68 +214,134 @@ __device__ __noinline__ uint32_t tw_model_long(const DevModel& m, const uint8_t*
     return n;
 }
 
-// tokens (ids/ss/ee, n of them; n == TKZ_NONE: rejected) -> value (va, vb) in slot encoding; multi-token words and tokens
-// with offsets beyond a byte go to the record pool.  Warp-collective; false = pool exhausted.
+struct WordVal { uint32_t a, b, c, d; };                 // value of a word in slot encoding
+struct WholeWarpOut { WordVal v; bool abort; };          // result of the out-of-line word handlers
+
+// tokens (ids/ss/ee, n of them; n == TKZ_NONE: rejected) -> value; words of more than two tokens (more than one when
+// !two_inline) go to the record pool.  Warp-collective; false = pool exhausted.
 __device__ __forceinline__ bool tw_make_value(const SliceArgs& a, const uint32_t* ids, const uint32_t* ss, const uint32_t* ee, uint32_t n,
-                                              uint32_t& va, uint32_t& vb) {
+                                              bool two_inline, WordVal& v) {
     const uint32_t lane = lane_id();
-    if (n == TKZ_NONE) { va = 0; vb = TW_NT1_ERR << 16; return true; }
-    if (n == 0) { va = 0; vb = 1u << 16; return true; }
-    if (n == 1 && ee[0] < 256u) { va = ids[0]; vb = (2u << 16) | (ee[0] << 8) | ss[0]; return true; }
+    v.a = 0; v.c = 0; v.d = 0;
+    if (n == TKZ_NONE) { v.b = TW_ERRF | (1u << 16); return true; }
+    if (n == 0) { v.b = 1u << 16; return true; }
+    if (n == 1) { v.a = ids[0]; v.b = (2u << 16) | (ee[0] << 8) | ss[0]; return true; }
+    if (n == 2 && two_inline) { v.a = ids[0]; v.b = (3u << 16) | (ee[0] << 8) | ss[0]; v.c = ids[1]; v.d = (ee[1] << 8) | ss[1]; return true; }
     uint32_t off = 0;
     if (lane == 0) off = atomicAdd(a.upool_count, n);
     off = __shfl_sync(0xFFFFFFFFu, off, 0);
-    if ((unsigned long long)off + n > a.upool_cap) { va = 0; vb = 1u << 16; return false; }
+    if ((unsigned long long)off + n > a.upool_cap) { v.b = 1u << 16; return false; }
     for (uint32_t k = lane; k < n; k += 32)
         __stcg(a.upool + off + k, (unsigned long long)ids[k] | ((unsigned long long)ss[k] << 32) | ((unsigned long long)ee[k] << 48));
     __threadfence();
     __syncwarp();
-    va = off; vb = ((n + 1) << 16) | TW_POOLF;
+    v.a = off; v.b = ((n + 1) << 16) | TW_POOLF;
     return true;
 }
 
+// ---------------------------------------------------------------- byte classes, four bytes per instruction
+// x = 4 packed bytes.  A byte b < 0x80 lies in [lo, hi] iff bit 7 of (b + 0x80 - lo) is set and bit 7 of (b + 0x7F - hi) is
+// not; with b taken as b & 0x7F no carry crosses a byte.  Returns the masks in bit 7 of each byte.  N is a compile-time
+// count: the addends are then read straight from the kernel parameters as instruction operands.
+template <int N>
+__device__ __forceinline__ uint32_t tw_in_ranges4(uint32_t x7, const uint32_t* lo, const uint32_t* hi) {
+    uint32_t acc = 0;
+#pragma unroll
+    for (int k = 0; k < N; k++) acc |= (x7 + lo[k]) & ~(x7 + hi[k]);
+    return acc;
+}
+// bits 7, 15, 23, 31 -> a nibble in the TOP four bits (no two partial products share a bit)
+__device__ __forceinline__ uint32_t tw_gather4(uint32_t hi_bits) { return hi_bits * 0x00204081u; }
 
+// the class sets the range form is compiled for: ND runs of DELIM bytes (1..3), NI runs of ISOLATE bytes (0 or 4):
+// whitespace splits (config.zig:440-450) and the BERT splits (config.zig:405-438, pretokenizer.zig:81-133); any other table
+// takes the per-byte look-up
+__host__ __device__ __forceinline__ bool tw_ranges_supported(int nd, int ni) { return nd >= 1 && nd <= 3 && (ni == 0 || ni == 4); }
 
-// classify + normalise one 32-byte segment (two 16-byte vector loads); bytes at or beyond n read as DELIM
-template <bool NORM_ID, bool HAS_ISO>
-__device__ __forceinline__ void tw_load_segment(const uint8_t* __restrict__ text, uint64_t n, uint64_t seg_base, uint32_t seg,
-                                                const uint32_t* lut, uint32_t cw_word, uint32_t cw_iso, uint32_t* text32,
-                                                uint32_t& word_out, uint32_t& iso_out) {
+// classify (+ normalise in place) the 8 words of a lane's 32-byte segment held in shared memory
+template <int NORM, int ND, int NI>          // NORM: 0 identity, 1 A-Z -> a-z
+__device__ __forceinline__ void tw_classify_segment_ranges(const ClassRanges& cr, uint32_t* seg, uint32_t& word_out, uint32_t& iso_out) {
+    const uint4 v0 = *reinterpret_cast<const uint4*>(seg), v1 = *reinterpret_cast<const uint4*>(seg + 4);
+    uint32_t x[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
     uint32_t word = 0, iso = 0;
 #pragma unroll
-    for (int h = 0; h < 2; h++) {
-        const uint64_t hb = seg_base + 16 * h;
-        uint32_t raw[4] = {0, 0, 0, 0};
-        uint32_t valid = 0;
-        if (hb + 16 <= n) {
-            const uint4 v = tw_ld_text16(text + hb);
-            raw[0] = v.x; raw[1] = v.y; raw[2] = v.z; raw[3] = v.w; valid = 0xFFFFu;
-        } else {
-            for (int k = 0; k < 16; k++) if (hb + k < n) { raw[k >> 2] |= (uint32_t)__ldg(text + hb + k) << ((k & 3) * 8); valid |= 1u << k; }
+    for (int q = 7; q >= 0; q--) {
+        const uint32_t x7 = x[q] & 0x7F7F7F7Fu;
+        const uint32_t nh = ~x[q] & 0x80808080u;                                  // bytes below 0x80
+        const uint32_t dl = tw_in_ranges4<ND>(x7, cr.d_lo, cr.d_hi);
+        uint32_t is = 0;
+        if (NI) is = tw_in_ranges4<NI>(x7, cr.i_lo, cr.i_hi) & nh;
+        const uint32_t wd = ~(dl & nh) & ~is & 0x80808080u;                       // WORD: neither (bytes >= 0x80 are WORD)
+        word = __funnelshift_l(tw_gather4(wd), word, 4);
+        if (NI) iso = __funnelshift_l(tw_gather4(is), iso, 4);
+        if (NORM == 1) {
+            const uint32_t up = (x7 + 0x3F3F3F3Fu) & ~(x7 + 0x25252525u) & nh;   // 'A' (0x41) .. 'Z' (0x5A)
+            x[q] |= up >> 2;                                                      // + 0x20
         }
-        uint32_t w16 = 0, i16 = 0, nrm[4];
+    }
+    if (NORM == 1) {
+        *reinterpret_cast<uint4*>(seg) = make_uint4(x[0], x[1], x[2], x[3]);
+        *reinterpret_cast<uint4*>(seg + 4) = make_uint4(x[4], x[5], x[6], x[7]);
+    }
+    word_out = word; iso_out = iso;
+}
+// one word (4 bytes) the same way: returns nibbles in the low 4 bits
+template <int NORM, int ND, int NI>
+__device__ __forceinline__ void tw_classify_word_ranges(const ClassRanges& cr, uint32_t* wp, uint32_t& word_nib, uint32_t& iso_nib) {
+    uint32_t x = *wp;
+    const uint32_t x7 = x & 0x7F7F7F7Fu, nh = ~x & 0x80808080u;
+    const uint32_t dl = tw_in_ranges4<ND>(x7, cr.d_lo, cr.d_hi);
+    uint32_t is = 0;
+    if (NI) is = tw_in_ranges4<NI>(x7, cr.i_lo, cr.i_hi) & nh;
+    const uint32_t wd = ~(dl & nh) & ~is & 0x80808080u;
+    word_nib = tw_gather4(wd) >> 28; iso_nib = tw_gather4(is) >> 28;
+    if (NORM == 1) {
+        const uint32_t up = (x7 + 0x3F3F3F3Fu) & ~(x7 + 0x25252525u) & nh;
+        *wp = x | (up >> 2);
+    }
+}
+// phase 1 in range form: the lane's segment, the 32 bytes behind the slice (lanes 0..7: class nibbles, lanes 8..11 only
+// normalise), the byte before it (lane 12)
+template <int NORM, int ND, int NI>
+__device__ __forceinline__ void tw_phase1_ranges(const ClassRanges& cr, uint32_t* tw, uint32_t& word, uint32_t& iso, uint32_t& hw, uint32_t& hi, uint32_t& prev_byte_word) {
+    const uint32_t FULL = 0xFFFFFFFFu, lane = lane_id();
+    tw_classify_segment_ranges<NORM, ND, NI>(cr, tw + lane * 8, word, iso);
+    uint32_t wn = 0, in_ = 0;
+    if (lane < 12) tw_classify_word_ranges<NORM, ND, NI>(cr, tw + TW_SLICE / 4 + lane, wn, in_);
+    else if (lane == 12) { uint32_t tmp = tw[-1]; tw_classify_word_ranges<0, ND, NI>(cr, &tmp, wn, in_); }
+    prev_byte_word = __shfl_sync(FULL, wn, 12) >> 3;
+    const uint32_t sh4 = (lane & 7u) * 4u;
+    hw = __reduce_or_sync(FULL, lane < 8 ? wn << sh4 : 0u);
+    hi = NI ? __reduce_or_sync(FULL, lane < 8 ? in_ << sh4 : 0u) : 0u;
+}
+// arbitrary tables: one look-up per byte (identity byte map: 256-bit class tables held by lanes 0..7 and read by shuffle,
+// because 32 lanes x arbitrary bytes serialise on the banks of a shared-memory LUT)
+template <bool NORM_ID, bool HAS_ISO>
+__device__ __forceinline__ void tw_classify_segment_lut(const uint32_t* lut, uint32_t cw_word, uint32_t cw_iso, uint32_t* seg, uint32_t& word_out, uint32_t& iso_out) {
+    const uint4 v0 = *reinterpret_cast<const uint4*>(seg), v1 = *reinterpret_cast<const uint4*>(seg + 4);
+    const uint32_t x[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+    uint32_t word = 0, iso = 0, nrm[8];
 #pragma unroll
-        for (int q = 0; q < 4; q++) {
-            uint32_t o = 0;
+    for (int q = 0; q < 8; q++) {
+        uint32_t o = 0;
 #pragma unroll
-            for (int j = 0; j < 4; j++) {
-                const uint32_t b = (raw[q] >> (8 * j)) & 0xFFu;
-                if (NORM_ID) {
-                    // identity byte map: only the class bits are needed -> 256-bit tables held by lanes 0..7, read by shuffle
-                    // (the shared-memory LUT serialises on bank conflicts: 32 lanes x arbitrary bytes)
-                    w16 |= ((__shfl_sync(0xFFFFFFFFu, cw_word, b >> 5) >> (b & 31u)) & 1u) << (q * 4 + j);
-                    if (HAS_ISO) i16 |= ((__shfl_sync(0xFFFFFFFFu, cw_iso, b >> 5) >> (b & 31u)) & 1u) << (q * 4 + j);
-                } else {
-                    const uint32_t e = lut[b];
-                    w16 |= ((e >> 8) & 1u) << (q * 4 + j);
-                    if (HAS_ISO) i16 |= ((e >> 9) & 1u) << (q * 4 + j);
-                    o |= (e & 0xFFu) << (8 * j);
-                }
+        for (int j = 0; j < 4; j++) {
+            const uint32_t b = (x[q] >> (8 * j)) & 0xFFu;
+            if (NORM_ID) {
+                word |= ((__shfl_sync(0xFFFFFFFFu, cw_word, b >> 5) >> (b & 31u)) & 1u) << (q * 4 + j);
+                if (HAS_ISO) iso |= ((__shfl_sync(0xFFFFFFFFu, cw_iso, b >> 5) >> (b & 31u)) & 1u) << (q * 4 + j);
+            } else {
+                const uint32_t e = lut[b];
+                word |= ((e >> 8) & 1u) << (q * 4 + j);
+                if (HAS_ISO) iso |= ((e >> 9) & 1u) << (q * 4 + j);
+                o |= (e & 0xFFu) << (8 * j);
             }
-            nrm[q] = NORM_ID ? raw[q] : o;
         }
-        word |= (w16 & valid) << (16 * h); iso |= (i16 & valid) << (16 * h);
-        *reinterpret_cast<uint4*>(text32 + seg * 8 + h * 4) = make_uint4(nrm[0], nrm[1], nrm[2], nrm[3]);
+        nrm[q] = o;
+    }
+    if (!NORM_ID) {
+        *reinterpret_cast<uint4*>(seg) = make_uint4(nrm[0], nrm[1], nrm[2], nrm[3]);
+        *reinterpret_cast<uint4*>(seg + 4) = make_uint4(nrm[4], nrm[5], nrm[6], nrm[7]);
     }
     word_out = word; iso_out = iso;
 }
@@ -262,9 +360,9 @@ __device__ __forceinline__ uint32_t tw_ballot_prefix(uint32_t v, uint32_t lt_mas
 }
 
 // 128-bit key of the word of `len` (<= 15) bytes at slice position p: the normalised bytes, length in the top byte
-__device__ __forceinline__ void tw_build_key(const SliceShared& sh, const uint4* lenmask, uint32_t p, uint32_t len, uint32_t (&key)[4]) {
+__device__ __forceinline__ void tw_build_key(const uint32_t* tw, const uint4* lenmask, uint32_t p, uint32_t len, uint32_t (&key)[4]) {
     const uint32_t wi = p >> 2, shb = (p & 3u) * 8u;
-    const uint32_t x0 = sh.text32[wi], x1 = sh.text32[wi + 1], x2 = sh.text32[wi + 2], x3 = sh.text32[wi + 3], x4 = sh.text32[wi + 4];
+    const uint32_t x0 = tw[wi], x1 = tw[wi + 1], x2 = tw[wi + 2], x3 = tw[wi + 3], x4 = tw[wi + 4];
     const uint4 mk = lenmask[len];
     key[0] = __funnelshift_r(x0, x1, shb) & mk.x;
     key[1] = __funnelshift_r(x1, x2, shb) & mk.y;
@@ -272,15 +370,13 @@ __device__ __forceinline__ void tw_build_key(const SliceShared& sh, const uint4*
     key[3] = (__funnelshift_r(x3, x4, shb) & mk.w) | (len << 24);
 }
 
-struct WholeWarpOut { uint32_t a, b; bool abort; };     // result of the out-of-line word handlers
-
 // 256-bit key of the word of `len` (16..31) bytes at slice position p: key[0..3] = [len, bytes 0..14], key[4..7] = bytes 15..30
-__device__ __forceinline__ void tw_build_key32(const SliceShared& sh, const uint4* lenmask, uint32_t p, uint32_t len, uint32_t (&key)[8]) {
+__device__ __forceinline__ void tw_build_key32(const uint32_t* tw, const uint4* lenmask, uint32_t p, uint32_t len, uint32_t (&key)[8]) {
     const uint32_t wi = p >> 2, shb = (p & 3u) * 8u;
     uint32_t w[8];
-    uint32_t x = sh.text32[wi];
+    uint32_t x = tw[wi];
 #pragma unroll
-    for (int i = 0; i < 8; i++) { const uint32_t y = sh.text32[wi + 1 + i]; w[i] = __funnelshift_r(x, y, shb); x = y; }
+    for (int i = 0; i < 8; i++) { const uint32_t y = tw[wi + 1 + i]; w[i] = __funnelshift_r(x, y, shb); x = y; }
     const uint4 mk = lenmask[len - 16];                            // bytes 16.. of the word: keep len - 16 of them
     w[4] &= mk.x; w[5] &= mk.y; w[6] &= mk.z; w[7] &= mk.w;
     key[0] = len | (w[0] << 8);
@@ -297,30 +393,30 @@ __device__ __forceinline__ uint32_t tw_key_hash32(const uint32_t (&k)[8]) {
 
 // One word of 16..31 bytes this warp saw first: model + publish into its WordSlot32.  Out of line.
 template <int MODEL>
-__device__ __forceinline__ WholeWarpOut tw_own_word32(const DevModel& m, const SliceArgs& a, SliceShared& sh, uint32_t wp_, uint32_t wlen, uint32_t bslot) {
+__device__ __forceinline__ WholeWarpOut tw_own_word32(const DevModel& m, const SliceArgs& a, SliceShared& sh, const uint32_t* tw, uint32_t wp_, uint32_t wlen, uint32_t bslot) {
     const uint32_t lane = lane_id();
-    WholeWarpOut out{0u, 0u, false};
+    WholeWarpOut out{{0u, 0u, 0u, 0u}, false};
     uint8_t* const wbytes = reinterpret_cast<uint8_t*>(sh.wbytes);
-    wbytes[lane] = (reinterpret_cast<const uint8_t*>(sh.text32) + wp_)[lane];     // the whole word is in the slice + halo
+    wbytes[lane] = (reinterpret_cast<const uint8_t*>(tw) + wp_)[lane];     // the whole word is in the slice + halo
     __syncwarp();
     const uint32_t n = tw_model_small<MODEL>(m, wbytes, wlen, sh.mscr);
-    if (!tw_make_value(a, sh.mscr[0], sh.mscr[1], sh.mscr[2], n, out.a, out.b)) out.abort = true;
-    if (lane == 0) asm volatile("st.global.relaxed.gpu.v2.u32 [%0], {%1,%2};" :: "l"(&a.table32[bslot].a), "r"(out.a), "r"(out.b) : "memory");
+    if (!tw_make_value(a, sh.mscr[0], sh.mscr[1], sh.mscr[2], n, false, out.v)) out.abort = true;
+    if (lane == 0) asm volatile("st.global.relaxed.gpu.v2.u32 [%0], {%1,%2};" :: "l"(&a.table32[bslot].a), "r"(out.v.a), "r"(out.v.b) : "memory");
     __syncwarp();
     return out;
 }
 
-// One word that needs the whole warp (longer than 15 bytes, or no table slot within the probe limit): finds its end, then
-// medium words (<= 64 bytes) go through the tag table, 65..256 bytes are tokenized uncached, longer ones join the long list.
-// Kept out of line so that its registers do not weigh on the one-word-per-lane loop.
+// One word that needs the whole warp (longer than 31 bytes, or no table slot within the probe limit): finds its end, then
+// medium words (<= 64 bytes) go through the tag table, 65..255 bytes are tokenized uncached, longer ones are returned with
+// TW_LONGF (a = length) and join the long list.  Kept out of line so that its registers do not weigh on the round loop.
 template <int MODEL>
-__device__ __forceinline__ WholeWarpOut tw_whole_warp_word(const DevModel& m, const SliceArgs& a, const uint32_t* lut, SliceShared& sh, uint32_t s,
-                                                        uint32_t wp_, uint32_t wl_) {
+__device__ __forceinline__ WholeWarpOut tw_whole_warp_word(const DevModel& m, const SliceArgs& a, const uint32_t* lut, SliceShared& sh, const uint32_t* tw,
+                                                        uint32_t s, uint32_t wp_, uint32_t wl_, uint32_t* lscr) {
     const uint64_t slice_base = (uint64_t)s * TW_SLICE;
     const uint32_t FULL = 0xFFFFFFFFu;
     const uint32_t lane = lane_id();
     uint8_t* const wbytes = reinterpret_cast<uint8_t*>(sh.wbytes);
-    WholeWarpOut out{0u, 1u << 16, false};
+    WholeWarpOut out{{0u, 1u << 16, 0u, 0u}, false};
     const uint64_t start = slice_base + wp_;
     uint32_t wlen = wl_;
     if (wl_ > 32) {
@@ -382,39 +478,28 @@ __device__ __forceinline__ WholeWarpOut tw_whole_warp_word(const DevModel& m, co
         }
         wlen = (uint32_t)(q - start);
     }
-    uint32_t xa = 0, xb = 1u << 16;                    // default: no tokens
-    if (MODEL == TKZ_MODEL_WORDPIECE && (uint64_t)wlen > m.max_chars && wlen <= 0xFFFFu) {
-        // one [UNK] spanning the word (wordpiece.zig:149-158); MissingUnkToken when the vocabulary has none
+    WordVal xv{0u, 1u << 16, 0u, 0u};                    // default: no tokens
+    if (MODEL == TKZ_MODEL_WORDPIECE && (uint64_t)wlen > m.max_chars && wlen <= TW_MAX_INLINE) {
+        // one [UNK] spanning the word (wordpiece.zig:149-158); MissingUnkToken when the vocabulary has none.  (Longer words
+        // take the long list: wordpiece_warp_kernel applies the same rule with 32-bit offsets.)
         uint32_t* scr = sh.mscr[0];
         if (lane == 0) { scr[0] = m.unk_id; scr[1] = 0; scr[2] = wlen; }
         __syncwarp();
-        if (!tw_make_value(a, scr, scr + 1, scr + 2, m.has_unk ? 1u : TKZ_NONE, xa, xb)) out.abort = true;
+        if (!tw_make_value(a, scr, scr + 1, scr + 2, m.has_unk ? 1u : TKZ_NONE, false, xv)) out.abort = true;
     } else if (wlen > TW_MAX_INLINE) {
         // long list: tokenized per occurrence by the word-list kernels between the two passes (block-level BPE)
-        uint32_t idx = 0;
-        if (lane == 0) {
-            idx = atomicAdd(a.n_long, 1u);
-            if (idx < a.long_cap) { a.long_start[idx] = (uint32_t)start; a.long_end[idx] = (uint32_t)(start + wlen); a.long_slice[idx] = s; }
-        }
-        idx = __shfl_sync(FULL, idx, 0);
-        if (idx >= a.long_cap) out.abort = true;
-        xa = idx; xb = TW_LONGF | (1u << 16);
+        xv.a = wlen; xv.b = TW_LONGF | (1u << 16);
     } else if (wlen > TW_MAX_MED) {
-        // 65..256 bytes: not deduplicated, symbols in global scratch
-        uint32_t off = 0;
-        if (lane == 0) { off = atomicAdd(a.lscratch_count, 4u * wlen); atomicAdd(a.n_uncached, 1u); }
-        off = __shfl_sync(FULL, off, 0);
-        if ((unsigned long long)off + 4u * wlen > a.lscratch_cap) out.abort = true;
-        else {
-            uint32_t* g = a.lscratch + off;
-            const uint32_t n = tw_model_long<MODEL>(m, m.lut, a.text + start, wlen, g);
-            __threadfence_block();
-            if (!tw_make_value(a, g, g + wlen, g + 2 * wlen, n, xa, xb)) out.abort = true;
-        }
+        // 65..255 bytes: not deduplicated, symbols in the warp's global scratch
+        if (lane == 0) atomicAdd(a.n_uncached, 1u);
+        const uint32_t n = tw_model_long<MODEL>(m, m.lut, a.text + start, wlen, lscr);
+        __threadfence_block();
+        if (!tw_make_value(a, lscr, lscr + wlen, lscr + 2 * wlen, n, false, xv)) out.abort = true;
+        __syncwarp();
     } else {
         // <= 64 bytes: normalised bytes into shared memory
         if (wlen <= 32) {                                // the whole word is in the slice + halo
-            const uint8_t* tb = reinterpret_cast<const uint8_t*>(sh.text32) + wp_;
+            const uint8_t* tb = reinterpret_cast<const uint8_t*>(tw) + wp_;
             wbytes[lane] = tb[lane];
         } else {
             uint32_t bb = 0;
@@ -470,17 +555,17 @@ __device__ __forceinline__ WholeWarpOut tw_whole_warp_word(const DevModel& m, co
             }
         }
         if (mode == 2) {
-            uint2 v = make_uint2(0, 0);
+            uint4 v = make_uint4(0, 0, 0, 0);
             if (lane == 0) { do { v = tw_ld_value(ms); } while (v.y == 0); }
-            xa = __shfl_sync(FULL, v.x, 0); xb = __shfl_sync(FULL, v.y, 0);
+            xv.a = __shfl_sync(FULL, v.x, 0); xv.b = __shfl_sync(FULL, v.y, 0);
         } else {
             if (mode == 0 && lane == 0) atomicAdd(a.n_uncached, 1u);
             const uint32_t n = tw_model_small<MODEL>(m, wbytes, wlen, sh.mscr);
-            if (!tw_make_value(a, sh.mscr[0], sh.mscr[1], sh.mscr[2], n, xa, xb)) out.abort = true;
-            if (mode == 1 && lane == 0) tw_st_value(ms, xa, xb);
+            if (!tw_make_value(a, sh.mscr[0], sh.mscr[1], sh.mscr[2], n, false, xv)) out.abort = true;
+            if (mode == 1 && lane == 0) tw_st_value(ms, xv.a, xv.b, 0u, 0u);
         }
     }
-    out.a = xa; out.b = xb;
+    out.v = xv;
     return out;
 }
 
@@ -489,22 +574,24 @@ template <int MODEL>
 __device__ __forceinline__ WholeWarpOut tw_own_word(const DevModel& m, const SliceArgs& a, SliceShared& sh, uint32_t b0, uint32_t b1, uint32_t b2, uint32_t b3,
                                                  uint32_t bslot) {
     const uint32_t lane = lane_id();
-    WholeWarpOut out{0u, 0u, false};
+    WholeWarpOut out{{0u, 0u, 0u, 0u}, false};
     if (lane < 4) sh.wbytes[lane] = lane == 0 ? b0 : (lane == 1 ? b1 : (lane == 2 ? b2 : (b3 & 0x00FFFFFFu)));
     __syncwarp();
     const uint32_t n = tw_model_small<MODEL>(m, reinterpret_cast<const uint8_t*>(sh.wbytes), b3 >> 24, sh.mscr);
-    if (!tw_make_value(a, sh.mscr[0], sh.mscr[1], sh.mscr[2], n, out.a, out.b)) out.abort = true;
-    if (lane == 0) tw_st_value(a.table + bslot, out.a, out.b);
+    if (!tw_make_value(a, sh.mscr[0], sh.mscr[1], sh.mscr[2], n, true, out.v)) out.abort = true;
+    if (lane == 0) tw_st_value(a.table + bslot, out.v.a, out.v.b, out.v.c, out.v.d);
     __syncwarp();
     return out;
 }
 
-// pass A: one warp per 1 KiB slice, slices strided over all warps of the grid (4 blocks of 8 warps per SM: 64 registers, 38 KB of
-// shared memory per block, which leaves ~90 KB of L1 for the word-table probes)
-template <int MODEL, bool NORM_ID, bool HAS_ISO>
+// CLS: 0 byte ranges + identity byte map, 1 byte ranges + ASCII lower-case, 2 LUT + identity, 3 LUT + arbitrary byte map
+// pass A: one warp per 1 KiB slice, slices strided over all warps of the grid (4 blocks of 8 warps per SM)
+template <int MODEL, int CLS>
 __global__ void __launch_bounds__(TW_THREADS, TW_BLOCKS_PER_SM) slice_words_kernel(const __grid_constant__ DevModel m, const __grid_constant__ SliceArgs a) {
-    extern __shared__ __align__(32) unsigned char tw_smem_raw[];
+    extern __shared__ __align__(128) unsigned char tw_smem_raw[];
     BlockShared& bs = *reinterpret_cast<BlockShared*>(tw_smem_raw);
+    constexpr bool RANGES = CLS < 2;
+    constexpr bool NORM_ID = CLS == 0 || CLS == 2;
     const uint32_t FULL = 0xFFFFFFFFu;
     const uint32_t t = threadIdx.x, lane = t & 31, wid = t >> 5;
     const uint32_t lt_mask = (1u << lane) - 1u;
@@ -518,26 +605,45 @@ __global__ void __launch_bounds__(TW_THREADS, TW_BLOCKS_PER_SM) slice_words_kern
         for (int q = 0; q < 4; q++) { const int nb = (int)t - 4 * q; w[q] = nb >= 4 ? 0xFFFFFFFFu : (nb <= 0 ? 0u : ((1u << (8 * nb)) - 1u)); }
         bs.lenmask[t] = make_uint4(w[0], w[1], w[2], w[3]);
     }
-    __syncthreads();                                            // the only block-level barrier
     SliceShared& sh = bs.w[wid];
-    // class bits of byte values 32 * lane .. 32 * lane + 31 (lanes 0..7), for the shuffle look-up of tw_load_segment
+    if (lane == 0) { tw_mbar_init(&sh.bar[0]); tw_mbar_init(&sh.bar[1]); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    __syncthreads();                                            // the only block-level barrier
+    // class bits of byte values 32 * lane .. 32 * lane + 31 (lanes 0..7), for the shuffle look-up of the LUT + identity mode
     uint32_t cw_word = 0, cw_iso = 0;
-    if (NORM_ID && lane < 8) for (int j = 0; j < 32; j++) { const uint32_t e = bs.lut[32 * lane + j]; cw_word |= ((e >> 8) & 1u) << j; cw_iso |= ((e >> 9) & 1u) << j; }
+    if (CLS == 2 && lane < 8) for (int j = 0; j < 32; j++) { const uint32_t e = bs.lut[32 * lane + j]; cw_word |= ((e >> 8) & 1u) << j; cw_iso |= ((e >> 9) & 1u) << j; }
     const uint32_t stride = gridDim.x * TW_WARPS;
+    const uint32_t gwarp = blockIdx.x * TW_WARPS + wid;
+    uint32_t* const lscr = a.lscratch + (size_t)gwarp * (4 * 256);
     bool warp_abort = false;
 
-    // first / last document of the warp's next slice are fetched one slice ahead (lanes 0, 1)
-    uint32_t s = blockIdx.x * TW_WARPS + wid;
+    // a slice whose whole staged window lies inside the text is fetched by a bulk copy; the last one or two slices of the
+    // batch are loaded byte by byte with bounds checks
+    auto bulk_ok = [&](uint32_t sl) -> bool { return sl < a.n_slices && (uint64_t)sl * TW_SLICE + TW_SLICE + TW_POST <= a.n; };
+    auto issue = [&](uint32_t sl, uint32_t buf) {
+        const uint64_t base = (uint64_t)sl * TW_SLICE;
+        if (sl == 0) tw_bulk_load(reinterpret_cast<uint8_t*>(sh.raw[buf]) + TW_PRE, a.text, TW_SLICE + TW_POST, &sh.bar[buf]);
+        else tw_bulk_load(sh.raw[buf], a.text + base - TW_PRE, TW_STAGE, &sh.bar[buf]);
+    };
+
+    uint32_t s = gwarp;
     uint32_t meta = (lane < 2 && s < a.n_slices) ? __ldg(a.slice_doc_lo + s + lane) : 0u;
-    uint32_t ecur = 0, eend = 0;                                // the warp's current chunk of the entry list
-    for (; s < a.n_slices; s += stride) {
+    uint32_t tcur = 0, tend = 0;                                // the warp's current chunk of the token stream
+    uint32_t buf = 0, phase = 0;                                // staging window in use, parity bits of the two mbarriers
+    unsigned long long words_total = 0;
+    if (lane == 0 && a.stage_bulk && bulk_ok(s)) issue(s, 0);
+    for (; s < a.n_slices; s += stride, buf ^= 1u) {
         const uint64_t slice_base = (uint64_t)s * TW_SLICE;
         const uint32_t d_lo = __shfl_sync(FULL, meta, 0);
         if (lane < 2) sh.doc_lo_hi[lane] = meta;                   // the epilogue reads them back (not kept in registers)
         meta = (lane < 2 && s + stride < a.n_slices) ? __ldg(a.slice_doc_lo + s + stride + lane) : 0u;
-        // the warp's next slice: its text is pulled into L2 while this one is processed
-        if (lane < 9 && (uint64_t)(s + stride) * TW_SLICE + lane * 128 < a.n)
-            asm volatile("prefetch.global.L2 [%0];" :: "l"(a.text + (uint64_t)(s + stride) * TW_SLICE + lane * 128));
+        uint32_t* const rawb = sh.raw[buf];
+        uint32_t* const tw = rawb + TW_PRE / 4;                    // word 0 = bytes 0..3 of the slice
+        uint8_t* const tb = reinterpret_cast<uint8_t*>(tw);
+        // the warp's next slice goes into the other window now (its readers finished at the end of the previous iteration)
+        if (lane == 0 && a.stage_bulk && bulk_ok(s + stride)) {
+            if (!NORM_ID) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the window was normalised in place
+            issue(s + stride, buf ^ 1u);
+        }
         // ---- phase 1: document-start bits; classify + normalise one 32-byte segment per lane
         for (uint32_t i = lane; i < (TW_SLICE + 32) / 32 + 2; i += 32) { sh.docbits[i] = 0; sh.cont32[i] = 0; }
         __syncwarp();
@@ -547,14 +653,59 @@ __global__ void __launch_bounds__(TW_THREADS, TW_BLOCKS_PER_SM) slice_words_kern
             const uint32_t p = (uint32_t)(off - slice_base);
             atomicOr(&sh.docbits[p >> 5], 1u << (p & 31));
         }
-        // the byte before the slice (lane 0) and the 32 halo bytes behind it (one per lane): only class bits + normalised bytes
-        uint32_t prev_byte_word = 0;
-        if (lane == 0 && slice_base > 0 && slice_base - 1 < a.n) prev_byte_word = (bs.lut[__ldg(a.text + slice_base - 1)] >> 8) & 1u;
-        uint32_t halo_e = 0;
-        { const uint64_t hp = slice_base + TW_SLICE + lane; if (hp < a.n) halo_e = bs.lut[__ldg(a.text + hp)]; }
-        uint32_t word, iso;
-        tw_load_segment<NORM_ID, HAS_ISO>(a.text, a.n, slice_base + (uint64_t)lane * TW_SEG, lane, bs.lut, cw_word, cw_iso, sh.text32, word, iso);
-        reinterpret_cast<uint8_t*>(sh.text32)[TW_SLICE + lane] = (uint8_t)halo_e;
+        const bool tail = !bulk_ok(s);
+        if (!tail && a.stage_bulk) { tw_mbar_wait(&sh.bar[buf], (phase >> buf) & 1u); phase ^= 1u << buf; }
+        else if (!tail) {
+            // A/B path: the window by 16-byte loads (two per lane for the slice, lanes 0..3 the 16 bytes before and 48 behind)
+            const uint4* g = reinterpret_cast<const uint4*>(a.text + slice_base);
+            uint4* d4 = reinterpret_cast<uint4*>(tw);
+            const uint4 v0 = tw_ld_text16(g + 2 * lane), v1 = tw_ld_text16(g + 2 * lane + 1);
+            uint4 hv = make_uint4(0, 0, 0, 0);
+            if (lane < 4 && (lane > 0 || slice_base > 0)) hv = tw_ld_text16(lane == 0 ? g - 1 : g + 63 + lane);
+            d4[2 * lane] = v0; d4[2 * lane + 1] = v1;
+            if (lane < 4) d4[lane == 0 ? -1 : 63 + (int)lane] = hv;
+            __syncwarp();
+        } else {
+            // bytes at or beyond n read as 0 and are masked out of the class bits below
+            for (uint32_t i = lane; i < TW_STAGE / 4; i += 32) {
+                uint32_t v = 0;
+                for (int j = 0; j < 4; j++) {
+                    const long long q = (long long)slice_base - TW_PRE + 4 * i + j;
+                    if (q >= 0 && (uint64_t)q < a.n) v |= (uint32_t)__ldg(a.text + q) << (8 * j);
+                }
+                rawb[i] = v;
+            }
+            __syncwarp();
+        }
+        uint32_t word, iso, hw, hi, prev_byte_word;
+        if (RANGES) {
+            constexpr int NRM = CLS == 1 ? 1 : 0;
+            switch (a.cr.n_delim * 2 + (a.cr.n_iso ? 1 : 0)) {
+                case 2: tw_phase1_ranges<NRM, 1, 0>(a.cr, tw, word, iso, hw, hi, prev_byte_word); break;
+                case 3: tw_phase1_ranges<NRM, 1, 4>(a.cr, tw, word, iso, hw, hi, prev_byte_word); break;
+                case 4: tw_phase1_ranges<NRM, 2, 0>(a.cr, tw, word, iso, hw, hi, prev_byte_word); break;
+                case 5: tw_phase1_ranges<NRM, 2, 4>(a.cr, tw, word, iso, hw, hi, prev_byte_word); break;
+                case 6: tw_phase1_ranges<NRM, 3, 0>(a.cr, tw, word, iso, hw, hi, prev_byte_word); break;
+                default: tw_phase1_ranges<NRM, 3, 4>(a.cr, tw, word, iso, hw, hi, prev_byte_word); break;
+            }
+        } else {
+            if (a.has_iso) tw_classify_segment_lut<NORM_ID, true>(bs.lut, cw_word, cw_iso, tw + lane * 8, word, iso);
+            else tw_classify_segment_lut<NORM_ID, false>(bs.lut, cw_word, cw_iso, tw + lane * 8, word, iso);
+            const uint32_t he = bs.lut[tb[TW_SLICE + lane]];
+            if (!NORM_ID) { tb[TW_SLICE + lane] = (uint8_t)he; if (lane < 16) tb[TW_SLICE + 32 + lane] = (uint8_t)bs.lut[tb[TW_SLICE + 32 + lane]]; }
+            hw = __ballot_sync(FULL, (he >> 8) & 1u); hi = __ballot_sync(FULL, (he >> 9) & 1u);
+            prev_byte_word = (bs.lut[tb[-1]] >> 8) & 1u;
+        }
+        if (slice_base == 0) prev_byte_word = 0;
+        if (tail) {
+            // validity: bytes of the lane's segment / of the halo that lie inside the text
+            const long long rem = (long long)a.n - (long long)(slice_base + (uint64_t)lane * TW_SEG);
+            const uint32_t valid = rem >= 32 ? FULL : (rem <= 0 ? 0u : ((1u << rem) - 1u));
+            word &= valid; iso &= valid;
+            const long long hrem = (long long)a.n - (long long)(slice_base + TW_SLICE);
+            const uint32_t hvalid = hrem >= 32 ? FULL : (hrem <= 0 ? 0u : ((1u << hrem) - 1u));
+            hw &= hvalid; hi &= hvalid;
+        }
         __syncwarp();
 
         // ---- phase 2: word starts, continuation bits, word list
@@ -566,13 +717,13 @@ __global__ void __launch_bounds__(TW_THREADS, TW_BLOCKS_PER_SM) slice_words_kern
             const uint32_t ds = sh.docbits[lane];
             smask = iso | (word & (~((word << 1) | prev_word) | ds));
             sh.cont32[lane] = word & ~smask;
-            // halo bytes: continuation bits from the per-lane class bits (same formula)
-            const uint32_t hw = __ballot_sync(FULL, (halo_e >> 8) & 1u), hi = HAS_ISO ? __ballot_sync(FULL, (halo_e >> 9) & 1u) : 0u;
+            // halo bytes: continuation bits (same formula)
             const uint32_t w31 = __shfl_sync(FULL, word >> 31, 31);
             const uint32_t hs = hi | (hw & (~((hw << 1) | w31) | sh.docbits[32]));
             if (lane == 0) sh.cont32[32] = hw & ~hs;
             const uint32_t cnt = __popc(smask);
-            wex = tw_ballot_prefix<6>(cnt, lt_mask, nW);
+            const uint32_t inc = warp_incl_scan(cnt);
+            wex = inc - cnt; nW = __shfl_sync(FULL, inc, 31);
             sh.seg_smask[lane] = smask; sh.seg_wex[lane] = wex;
             uint32_t sm = smask, k = wex;
             while (sm) {
@@ -580,24 +731,26 @@ __global__ void __launch_bounds__(TW_THREADS, TW_BLOCKS_PER_SM) slice_words_kern
                 sh.wlist[k++] = (uint16_t)((lane * TW_SEG + b) | (((iso >> b) & 1u) << 15));
             }
         }
-        // reserve the slice's part of the entry list: the warp sub-allocates from a chunk it claimed with one atomic
-        if (ecur + nW > eend) {
+        words_total += nW;
+        // reserve the slice's run of the token stream: the warp sub-allocates from a chunk it claimed with one atomic
+        if (tcur + TW_SLICE_TOK_MAX > tend) {
             uint32_t c = 0;
-            if (lane == 0) c = atomicAdd(a.ent_count, TW_ENT_CHUNK);
-            ecur = __shfl_sync(FULL, c, 0); eend = ecur + TW_ENT_CHUNK;
-            if ((unsigned long long)eend > a.ent_cap) { if (lane == 0) atomicExch(a.abort_flag, 1u); eend = ecur; }
+            if (lane == 0) c = atomicAdd(a.tok_count, TW_TOK_CHUNK);
+            tcur = __shfl_sync(FULL, c, 0); tend = tcur + TW_TOK_CHUNK;
+            if ((unsigned long long)tend > a.tok_cap) { warp_abort = true; tend = tcur; }
         }
-        const uint32_t entoff = ecur + nW <= eend ? ecur : TW_NONE;
-        if (entoff != TW_NONE) ecur += nW;
+        const bool can_store = tcur + TW_SLICE_TOK_MAX <= tend;
+        const uint32_t tbase = tcur;
         __syncwarp();
 
         // ---- phase 3: one word per lane
         uint32_t run = 0;                                           // tokens of the slice's words so far
+        uint32_t n_long_here = 0;
         for (uint32_t k0 = 0; k0 < nW; k0 += 32) {
             const uint32_t k = k0 + lane;
             const bool have = k < nW;
-            // straight-line first probe for every lane (lanes past the end repeat the round's first word, result ignored)
-            const uint32_t pw = sh.wlist[have ? k : k0];
+            // straight-line first probe for every lane (lanes past the end repeat the slice's last word, result ignored)
+            const uint32_t pw = sh.wlist[have ? k : nW - 1];
             const uint32_t p = pw & 0x0FFFu;
             uint32_t len;
             {
@@ -605,23 +758,24 @@ __global__ void __launch_bounds__(TW_THREADS, TW_BLOCKS_PER_SM) slice_words_kern
                 const uint32_t x = __funnelshift_r(sh.cont32[w], sh.cont32[w + 1], q & 31u);
                 len = (uint32_t)__ffs((int)~x);                     // 1 + continuing bytes; 0 when 32 or more continue
                 if (len == 0) len = 33;
-                if (HAS_ISO && (pw & 0x8000u)) len = 1;
+                if (pw & 0x8000u) len = 1;
             }
             const bool is_short = len <= TW_MAX_SHORT;
             uint32_t key[4];
-            tw_build_key(sh, bs.lenmask, p, is_short ? len : TW_MAX_SHORT, key);
-            uint32_t myslot = tw_key_hash(key[0], key[1], key[2], key[3]) & a.table_mask;
-            uint32_t va, vb;
+            tw_build_key(tw, bs.lenmask, p, is_short ? len : TW_MAX_SHORT, key);
+            uint32_t myslot = tw_key_hash(key[0], key[1], key[2], key[3]) >> a.table_shift;
+            WordVal v;
             int state;                                              // 0 done, 1 owner, 2 pending, 3 whole warp needed, 4 keep probing
             {
                 uint32_t r[8];
                 tw_ld256(a.table + myslot, r);
-                va = r[4]; vb = r[5];
+                v.a = r[4]; v.b = r[5]; v.c = r[6]; v.d = r[7];
                 const bool hit = is_short && r[0] == key[0] && r[1] == key[1] && r[2] == key[2] && r[3] == key[3] && r[5] != 0;
                 state = (!have || hit) ? 0 : (is_short ? 4 : 3);
             }
             if (__any_sync(FULL, state != 0)) {
                 // ---- rare: first sight of a word, a collision, a word whose owner is still computing, a long word
+                const uint32_t tmask = (0xFFFFFFFFu >> a.table_shift);
                 if (state == 4) {
                     uint32_t slot = myslot;
                     state = 3;
@@ -631,7 +785,7 @@ __global__ void __launch_bounds__(TW_THREADS, TW_BLOCKS_PER_SM) slice_words_kern
                         uint32_t r[8];
                         tw_ld256(sl, r);
                         if (r[0] == key[0] && r[1] == key[1] && r[2] == key[2] && r[3] == key[3]) {
-                            if (r[5] != 0) { va = r[4]; vb = r[5]; state = 0; } else { state = 2; myslot = slot; }
+                            if (r[5] != 0) { v.a = r[4]; v.b = r[5]; v.c = r[6]; v.d = r[7]; state = 0; } else { state = 2; myslot = slot; }
                             break;
                         }
                         if ((r[0] | r[1] | r[2] | r[3]) == 0) {
@@ -640,7 +794,7 @@ __global__ void __launch_bounds__(TW_THREADS, TW_BLOCKS_PER_SM) slice_words_kern
                             if ((old[0] | old[1] | old[2] | old[3]) == 0) { state = 1; myslot = slot; break; }
                             if (old[0] == key[0] && old[1] == key[1] && old[2] == key[2] && old[3] == key[3]) { state = 2; myslot = slot; break; }
                         }
-                        slot = (slot + 1) & a.table_mask;
+                        slot = (slot + 1) & tmask;
                     }
                 }
                 // words this warp saw first: run the model now and publish the value
@@ -651,14 +805,14 @@ __global__ void __launch_bounds__(TW_THREADS, TW_BLOCKS_PER_SM) slice_words_kern
                     const WholeWarpOut r = tw_own_word<MODEL>(m, a, sh, __shfl_sync(FULL, key[0], l), __shfl_sync(FULL, key[1], l),
                                                               __shfl_sync(FULL, key[2], l), __shfl_sync(FULL, key[3], l), __shfl_sync(FULL, myslot, l));
                     if (r.abort) warp_abort = true;
-                    if ((int)lane == l) { va = r.a; vb = r.b; state = 0; }
+                    if ((int)lane == l) { v = r.v; state = 0; }
                 }
                 // words of 16..31 bytes: one per lane through the 64-byte slots (state 5 probing, 6 pending, 7 owner)
                 if (state == 3 && len >= 16 && len <= 31) state = 5;
                 if (__any_sync(FULL, state == 5)) {
                     uint32_t k32[8] = {0, 0, 0, 0, 0, 0, 0, 0};
                     uint32_t slot = 0;
-                    if (state == 5) { tw_build_key32(sh, bs.lenmask, p, len, k32); slot = tw_key_hash32(k32) & a.table32_mask; }
+                    if (state == 5) { tw_build_key32(tw, bs.lenmask, p, len, k32); slot = tw_key_hash32(k32) & a.table32_mask; }
                     // warp-uniform probe rounds: a lane that meets a half-published key simply looks again next round
 #pragma unroll 1
                     for (int it = 0; it < 4 * TW_MAX_PROBE && __any_sync(FULL, state == 5); it++) {
@@ -685,7 +839,7 @@ __global__ void __launch_bounds__(TW_THREADS, TW_BLOCKS_PER_SM) slice_words_kern
                                     asm volatile("ld.global.relaxed.gpu.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(q0), "=r"(q1), "=r"(q2), "=r"(q3) : "l"(sl->k2) : "memory");
                                     if (q0 == k32[4] && q1 == k32[5] && q2 == k32[6] && q3 == k32[7]) {
                                         myslot = slot;
-                                        if (r[5] != 0) { va = r[4]; vb = r[5]; state = 0; } else state = 6;
+                                        if (r[5] != 0) { v.a = r[4]; v.b = r[5]; v.c = 0; v.d = 0; state = 0; } else state = 6;
                                     } else slot = (slot + 1) & a.table32_mask;
                                 }
                             } else slot = (slot + 1) & a.table32_mask;
@@ -696,16 +850,16 @@ __global__ void __launch_bounds__(TW_THREADS, TW_BLOCKS_PER_SM) slice_words_kern
                     if (own32 && lane == 0) atomicAdd(a.n_uniq, (unsigned int)__popc(own32));
                     while (own32) {
                         const int l = __ffs(own32) - 1; own32 &= own32 - 1;
-                        const WholeWarpOut r = tw_own_word32<MODEL>(m, a, sh, __shfl_sync(FULL, p, l), __shfl_sync(FULL, len, l), __shfl_sync(FULL, myslot, l));
+                        const WholeWarpOut r = tw_own_word32<MODEL>(m, a, sh, tw, __shfl_sync(FULL, p, l), __shfl_sync(FULL, len, l), __shfl_sync(FULL, myslot, l));
                         if (r.abort) warp_abort = true;
-                        if ((int)lane == l) { va = r.a; vb = r.b; state = 0; }
+                        if ((int)lane == l) { v = r.v; state = 0; }
                     }
                     uint32_t pend32 = __ballot_sync(FULL, state == 6);
                     while (pend32) {
                         if (state == 6) {
                             uint32_t x, y;
                             asm volatile("ld.global.relaxed.gpu.v2.u32 {%0,%1}, [%2];" : "=r"(x), "=r"(y) : "l"(&a.table32[myslot].a) : "memory");
-                            if (y != 0) { va = x; vb = y; state = 0; }
+                            if (y != 0) { v.a = x; v.b = y; v.c = 0; v.d = 0; state = 0; }
                         }
                         pend32 = __ballot_sync(FULL, state == 6);
                     }
@@ -714,43 +868,81 @@ __global__ void __launch_bounds__(TW_THREADS, TW_BLOCKS_PER_SM) slice_words_kern
                 uint32_t todo = __ballot_sync(FULL, state == 3);
                 while (todo) {
                     const int l = __ffs(todo) - 1; todo &= todo - 1;
-                    const WholeWarpOut r = tw_whole_warp_word<MODEL>(m, a, bs.lut, sh, s, __shfl_sync(FULL, p, l), __shfl_sync(FULL, len, l));
+                    const WholeWarpOut r = tw_whole_warp_word<MODEL>(m, a, bs.lut, sh, tw, s, __shfl_sync(FULL, p, l), __shfl_sync(FULL, len, l), lscr);
                     if (r.abort) warp_abort = true;
-                    if ((int)lane == l) { va = r.a; vb = r.b; state = 0; }
+                    if ((int)lane == l) { v = r.v; state = 0; }
                 }
                 // words whose owner (another warp) was still computing
                 uint32_t pend = __ballot_sync(FULL, state == 2);
                 while (pend) {
                     if (state == 2) {
-                        const uint2 v = tw_ld_value(a.table + myslot);
-                        if (v.y != 0) { va = v.x; vb = v.y; state = 0; }
+                        const uint4 q = tw_ld_value(a.table + myslot);
+                        if (q.y != 0) { v.a = q.x; v.b = q.y; v.c = q.z; v.d = q.w; state = 0; }
                     }
                     pend = __ballot_sync(FULL, state == 2);
                 }
             }
-            // ---- entry + token prefix
-            uint32_t nt = 0, ey = 0;
-            if (have) {
-                const uint32_t nt1 = (vb >> 16) & 0x3FFFu;
-                if (nt1 == TW_NT1_ERR) atomicMin(a.errw, ((unsigned long long)(slice_base + p) << 8) | (MODEL == TKZ_MODEL_BPE ? TKZ_ECODE_UTF8 : TKZ_ECODE_UNK));
-                else nt = nt1 - 1;
-                ey = (nt << 16) | (vb & 0xFFFFu) | (vb & (TW_POOLF | TW_LONGF));
-                if (vb & TW_LONGF) nt = 0;                          // counted after the word-list kernels (long_fix_kernel)
-            }
-            if (have && entoff != TW_NONE) a.ent[(size_t)entoff + k] = make_uint2(va, ey);
+            // ---- tokens + token prefix
+            uint32_t nt = 0;
+            const uint32_t flags = have ? (v.b & 0xE0000000u) : 0u;
+            if (have) nt = ((v.b >> 16) & 0x1FFFu) - 1u;
+            if (flags & (TW_ERRF | TW_LONGF)) nt = 0;
             uint32_t ex, tot;
             if (!__any_sync(FULL, nt > 3)) ex = tw_ballot_prefix<2>(nt, lt_mask, tot);
             else { const uint32_t inc = warp_incl_scan(nt); ex = inc - nt; tot = __shfl_sync(FULL, inc, 31); }
+            const uint32_t dst = tbase + run + ex;                  // stream position of the word's first token
+            if (can_store && nt && !(flags & TW_POOLF)) {
+                a.tok_id[dst] = v.a;
+                if (nt == 2) a.tok_id[dst + 1] = v.c;
+                if (a.tok_of) { a.tok_of[dst] = (uint16_t)v.b; if (nt == 2) a.tok_of[dst + 1] = (uint16_t)v.d; }
+            }
+            // words with three or more tokens: their records are copied from the pool by the whole warp, one word at a time
+            uint32_t pooled = __ballot_sync(FULL, can_store && nt && (flags & TW_POOLF));
+            while (pooled) {
+                const int l = __ffs(pooled) - 1; pooled &= pooled - 1;
+                const uint32_t pa = __shfl_sync(FULL, v.a, l), pn = __shfl_sync(FULL, nt, l), pd = __shfl_sync(FULL, dst, l);
+                for (uint32_t i = lane; i < pn; i += 32) {
+                    const unsigned long long r = __ldcg(a.upool + pa + i);       // written in THIS launch by the word's owner: L2, not the read-only path
+                    a.tok_id[pd + i] = (uint32_t)r;
+                    if (a.tok_of) a.tok_of[pd + i] = (uint16_t)(((uint32_t)(r >> 32) & 0xFFu) | ((uint32_t)(r >> 48) << 8));
+                }
+            }
+            if (__any_sync(FULL, flags & (TW_ERRF | TW_LONGF))) {
+                if (flags & TW_ERRF) atomicMin(a.errw, ((unsigned long long)(slice_base + p) << 8) | (MODEL == TKZ_MODEL_BPE ? TKZ_ECODE_UTF8 : TKZ_ECODE_UNK));
+                // long words of the slice, in text order: position, length, index of insertion in the slice's token run
+                const uint32_t lm = __ballot_sync(FULL, (flags & TW_LONGF) != 0);
+                if (flags & TW_LONGF) {
+                    const uint32_t j = n_long_here + __popc(lm & lt_mask);
+                    if (j < TW_MAX_SLICE_LONG) { sh.lbuf[j][0] = p; sh.lbuf[j][1] = v.a; sh.lbuf[j][2] = run + ex; }
+                }
+                n_long_here += __popc(lm);
+            }
             if (have) sh.wlist[k] = (uint16_t)(run + ex);      // (the round's wlist entries were read at its top, before the votes)
             run += tot;
         }
+        if (can_store) tcur += run;
+        // long words -> one contiguous run of the long list
+        uint32_t lfirst = 0;
+        if (n_long_here) {
+            if (n_long_here > TW_MAX_SLICE_LONG) { n_long_here = TW_MAX_SLICE_LONG; warp_abort = true; }   // cannot happen (each is > 255 bytes)
+            if (lane == 0) lfirst = atomicAdd(a.n_long, n_long_here);
+            lfirst = __shfl_sync(FULL, lfirst, 0);
+            __syncwarp();
+            if (lfirst + n_long_here > a.long_cap) { warp_abort = true; n_long_here = 0; }
+            else if (lane < n_long_here) {
+                const uint32_t st = (uint32_t)(slice_base + sh.lbuf[lane][0]);
+                a.long_start[lfirst + lane] = st; a.long_end[lfirst + lane] = st + sh.lbuf[lane][1];
+                a.long_slice[lfirst + lane] = s; a.long_ins[lfirst + lane] = sh.lbuf[lane][2];
+            }
+        }
         if (lane == 0) {
-            a.slice_ent_off[s] = entoff == TW_NONE ? 0u : entoff;
-            a.slice_nwords[s] = entoff == TW_NONE ? 0u : nW;
+            a.slice_tok_off[s] = tbase;
+            a.slice_ntok_inline[s] = can_store ? run : 0u;
             a.slice_ntok[s] = run;
+            a.slice_long[s] = (lfirst << 3) | n_long_here;
         }
         __syncwarp();
-        // ---- token prefix + word index at every document start inside the slice
+        // ---- token prefix at every document start inside the slice
         {
             const uint32_t dlo = sh.doc_lo_hi[0], dhi = sh.doc_lo_hi[1];
             for (uint32_t d = dlo + lane; d < dhi; d += 32) {
@@ -758,11 +950,11 @@ __global__ void __launch_bounds__(TW_THREADS, TW_BLOCKS_PER_SM) slice_words_kern
                 const uint32_t sg = q >> 5;
                 const uint32_t idx = sh.seg_wex[sg] + __popc(sh.seg_smask[sg] & ((1u << (q & 31u)) - 1u));
                 a.doc_tok_local[d] = idx < nW ? (uint32_t)sh.wlist[idx] : run;
-                a.doc_word_ref[d] = idx;
             }
         }
         __syncwarp();
     }
+    if (lane == 0 && words_total) atomicAdd(a.n_words, words_total);
     if (__any_sync(FULL, warp_abort) && lane == 0) atomicExch(a.abort_flag, 1u);
 }
 
@@ -784,171 +976,146 @@ __global__ void long_fix_kernel(const uint32_t* __restrict__ long_start, const u
 // ------------------------------------------------------------------ pass B
 struct SliceEmitArgs {
     const uint64_t* doc_off; uint32_t n_docs; uint32_t n_slices; const uint32_t* slice_doc_lo;
-    const uint2* ent; const uint32_t* slice_ent_off; const uint32_t* slice_nwords;
+    const uint32_t* tok_id; const uint16_t* tok_of;
+    const uint32_t* slice_tok_off; const uint32_t* slice_ntok_inline; const uint32_t* slice_long;
     const uint32_t* slice_tokbase;                // exclusive scan of the slice token counts (n_slices + 1)
-    const unsigned long long* upool;
-    const uint32_t* long_start; const uint32_t* long_ntok;
+    const uint32_t* long_start; const uint32_t* long_ins; const uint32_t* long_ntok;
     const uint32_t* pool_id; const uint32_t* pool_s; const uint32_t* pool_e;
-    const uint32_t* doc_word_ref; const uint32_t* doc_tok_local;
+    const uint32_t* doc_tok_local;
     const uint32_t* doc_tok_start;                // !PLAIN: global real-token index at each document start (n_docs + 1)
     unsigned long long* doc_tok_off;              // PLAIN: written here; !PLAIN: read (CSR after truncate / pad)
     unsigned long long* errw; uint32_t err_code;
-    unsigned long long* n_words;                  // statistics: pre-tokens of the batch
     BigList big;
 };
-constexpr uint32_t TE_STAGE = 256;                // tokens a warp stages in shared memory before one coalesced flush
 
-struct EmitStage { uint32_t id[TE_STAGE + 8]; uint32_t of[TE_STAGE + 8]; };
+// one token of the stream -> the arrays the call asked for.  OUTS = the TKZ_OUT_* mask when known at compile time
+// (ids only / ids + offsets + attention), 0 = read it from the parameters.
+template <uint32_t OUTS>
+__device__ __forceinline__ void te_put(const EmitParams& p, const EmitOut& o, unsigned long long dst, uint32_t id, uint32_t of) {
+    const uint32_t outputs = OUTS ? OUTS : p.outputs;
+    o.ids[dst] = id;
+    if (outputs & 2u) reinterpret_cast<uint2*>(o.offsets)[dst] = make_uint2(of & 0xFFu, of >> 8);
+    if (outputs & 4u) o.attention[dst] = 1u;
+    if (outputs & 8u) o.type_ids[dst] = 0u;
+    if (outputs & 16u) o.special[dst] = 0u;
+    if (outputs & 32u) o.offsets16[dst] = (uint16_t)of;
+}
 
-// staged tokens [0, fill) -> global slots [gstart, gstart + fill): slot i of the staging arrays holds global index
-// (gstart & ~3) + i, so whole groups of 4 tokens go out as 16-byte stores (ids, attention; offsets as 2 x 16 bytes)
-__device__ __forceinline__ void te_flush(const EmitParams& p, const EmitOut& o, const EmitStage& st, unsigned long long gstart, uint32_t fill) {
+// copies the stream tokens [j0, j1) of a slice (stream position src + j) to dst0 + (j - j0); 4 loads in flight per lane
+template <uint32_t OUTS>
+__device__ __forceinline__ void te_copy(const SliceEmitArgs& a, const EmitParams& p, const EmitOut& o, size_t src, uint32_t j0, uint32_t j1,
+                                        unsigned long long dst0) {
     const uint32_t lane = lane_id();
-    const uint32_t outputs = p.outputs;
-    __syncwarp();
-    const uint32_t mis = (uint32_t)(gstart & 3ull), end = mis + fill;
-    const unsigned long long g0 = gstart & ~3ull;
-    for (uint32_t g = lane * 4; g + 4 <= end; g += 128) {
-        if (g >= mis) {
-            *reinterpret_cast<uint4*>(o.ids + g0 + g) = *reinterpret_cast<const uint4*>(st.id + g);
-            if (outputs & 2u) {
-                const uint4 of4 = *reinterpret_cast<const uint4*>(st.of + g);
-                uint4* dst = reinterpret_cast<uint4*>(o.offsets + 2 * (g0 + g));
-                dst[0] = make_uint4(of4.x & 0xFFFFu, of4.x >> 16, of4.y & 0xFFFFu, of4.y >> 16);
-                dst[1] = make_uint4(of4.z & 0xFFFFu, of4.z >> 16, of4.w & 0xFFFFu, of4.w >> 16);
-            }
-            if (outputs & 4u) *reinterpret_cast<uint4*>(o.attention + g0 + g) = make_uint4(1u, 1u, 1u, 1u);
-            if (outputs & 8u) *reinterpret_cast<uint4*>(o.type_ids + g0 + g) = make_uint4(0u, 0u, 0u, 0u);
-            if (outputs & 16u) *reinterpret_cast<uint4*>(o.special + g0 + g) = make_uint4(0u, 0u, 0u, 0u);
-        }
+    const uint32_t outputs = OUTS ? OUTS : p.outputs;
+    const bool want_of = (outputs & (2u | 32u)) != 0;
+    for (uint32_t j = j0 + lane; j < j1; j += 128) {
+        uint32_t id[4], of[4] = {0, 0, 0, 0};
+#pragma unroll
+        for (int u = 0; u < 4; u++) if (j + 32 * u < j1) { id[u] = __ldg(a.tok_id + src + j + 32 * u); if (want_of) of[u] = __ldg(a.tok_of + src + j + 32 * u); }
+#pragma unroll
+        for (int u = 0; u < 4; u++) if (j + 32 * u < j1) te_put<OUTS>(p, o, dst0 + (j + 32 * u - j0), id[u], of[u]);
     }
-    // the partial groups at both ends, one token per lane: lanes 0..3 the head group, lanes 4..7 the tail group
-    {
-        const uint32_t tail0 = end & ~3u;
-        uint32_t j = TW_NONE;
-        if (lane < 4) { if (mis && lane >= mis && lane < end) j = lane; }
-        else if (lane < 8) { const uint32_t x = tail0 + (lane - 4); if ((end & 3u) && x < end && x >= mis && (tail0 != 0 || mis == 0)) j = x; }
-        if (j != TW_NONE) { const uint32_t of = st.of[j]; emit_real(p, o, g0 + j, st.id[j], of & 0xFFFFu, of >> 16); }
-    }
-    __syncwarp();
 }
 
 // PLAIN = no truncation and no padding: the output is the plain concatenation of all tokens in text order, so a token's
-// destination is its global index; tokens are staged in shared memory and written with 16-byte stores.
-template <bool PLAIN>
-__global__ void __launch_bounds__(TW_THREADS, 6) slice_emit_kernel(const __grid_constant__ SliceEmitArgs a, const __grid_constant__ EmitParams p,
+// destination is its global index.  Otherwise the tokens of the slice are cut by the documents that meet the slice.
+template <bool PLAIN, uint32_t OUTS>
+__global__ void __launch_bounds__(TW_THREADS, PLAIN ? 8 : 5) slice_emit_kernel(const __grid_constant__ SliceEmitArgs a, const __grid_constant__ EmitParams p,
                                                                 const __grid_constant__ EmitOut o) {
-    __shared__ __align__(16) EmitStage stage[PLAIN ? TW_WARPS : 1];
     const uint32_t FULL = 0xFFFFFFFFu;
     const uint32_t lane = lane_id(), wid = threadIdx.x >> 5;
-    EmitStage& st = stage[PLAIN ? wid : 0];
     const uint32_t stride = gridDim.x * TW_WARPS;
-    // slice metadata is fetched one slice ahead: lanes 0..4 hold nwords, ent_off, tokbase, doc_lo, doc_lo[+1] of the next slice
+    // slice metadata is fetched one slice ahead: lanes 0..6 hold ntok_inline, tok_off, tokbase, tokbase[+1], long, doc_lo, doc_lo[+1]
     auto load_meta = [&](uint32_t s) -> uint32_t {
-        if (s >= a.n_slices) return 0u;
-        const uint32_t* src = lane == 0 ? a.slice_nwords + s : (lane == 1 ? a.slice_ent_off + s : (lane == 2 ? a.slice_tokbase + s : a.slice_doc_lo + s + (lane - 3)));
-        return lane < 5 ? __ldg(src) : 0u;
+        if (s >= a.n_slices || lane >= 7) return 0u;
+        const uint32_t* src = lane == 0 ? a.slice_ntok_inline + s : (lane == 1 ? a.slice_tok_off + s : (lane < 4 ? a.slice_tokbase + s + (lane - 2)
+                              : (lane == 4 ? a.slice_long + s : a.slice_doc_lo + s + (lane - 5))));
+        return __ldg(src);
     };
     uint32_t s = blockIdx.x * TW_WARPS + wid;
     uint32_t meta = load_meta(s);
-    uint32_t words_total = 0;
     for (; s < a.n_slices; s += stride) {
-        const uint32_t nw = __shfl_sync(FULL, meta, 0);
-        words_total += nw;
-        const uint2* __restrict__ ent = a.ent + __shfl_sync(FULL, meta, 1);
-        const uint32_t base = __shfl_sync(FULL, meta, 2);
-        const uint32_t d_lo = __shfl_sync(FULL, meta, 3), d_hi = __shfl_sync(FULL, meta, 4);
+        const uint32_t ntok = __shfl_sync(FULL, meta, 0);
+        const size_t src = __shfl_sync(FULL, meta, 1);
+        const uint32_t base = __shfl_sync(FULL, meta, 2), base_next = __shfl_sync(FULL, meta, 3);
+        const uint32_t lg = __shfl_sync(FULL, meta, 4);
+        const uint32_t d_lo = __shfl_sync(FULL, meta, 5), d_hi = __shfl_sync(FULL, meta, 6);
         meta = load_meta(s + stride);
-        uint32_t carry = base;                                  // global real-token index of the next token
-        uint32_t fill = 0; unsigned long long gstart = base;     // staging: tokens staged, global index of the first one
-        uint2 e_next = make_uint2(0u, 0u);
-        if (lane < nw) e_next = tw_ld_entry(ent + lane);
-        for (uint32_t k0 = 0; k0 < nw; k0 += 32) {
-            const uint32_t k = k0 + lane;
-            const uint32_t ea = e_next.x, ey = k < nw ? e_next.y : 0u;
-            if (k + 32 < nw) e_next = tw_ld_entry(ent + k + 32);  // next round's entries are in flight while this round is emitted
-            else if (k0 + 32 >= nw && s + stride < a.n_slices && lane < 4)   // last round: pull the next slice's entries into L2
-                asm volatile("prefetch.global.L2 [%0];" :: "l"(a.ent + __shfl_sync(0xFu, meta, 1) + lane * 16));
-            uint32_t nt = 0;
-            if (k < nw) {
-                if (ey & TW_LONGF) {
-                    nt = __ldg(a.long_ntok + ea);
-                    if (nt == TKZ_NONE) { atomicMin(a.errw, ((unsigned long long)__ldg(a.long_start + ea) << 8) | a.err_code); nt = 0; }
-                } else nt = (ey >> 16) & 0x3FFFu;
+        if (PLAIN) {
+            if (lg == 0) te_copy<OUTS>(a, p, o, src, 0, ntok, base);
+            else {
+                // pieces: inline tokens up to the next long word's insertion index, then the long word (from the pool)
+                uint32_t j = 0; unsigned long long g = base;
+                const uint32_t lf = lg >> 3, ln = lg & 7u;
+                for (uint32_t i = 0; i <= ln; i++) {
+                    const uint32_t jn = i < ln ? __ldg(a.long_ins + lf + i) : ntok;
+                    te_copy<OUTS>(a, p, o, src, j, jn, g);
+                    g += jn - j; j = jn;
+                    if (i < ln) {
+                        uint32_t cnt = __ldg(a.long_ntok + lf + i);
+                        const uint32_t sp = __ldg(a.long_start + lf + i);
+                        if (cnt == TKZ_NONE) { if (lane == 0) atomicMin(a.errw, ((unsigned long long)sp << 8) | a.err_code); cnt = 0; }
+                        bool queued = false;
+                        if (cnt > EMIT_BIG) { if (lane == 0) queued = big_push(a.big, sp, cnt, g); queued = __shfl_sync(FULL, queued, 0); }
+                        if (!queued) for (uint32_t q = lane; q < cnt; q += 32) emit_real(p, o, g + q, a.pool_id[sp + q], a.pool_s[sp + q], a.pool_e[sp + q]);
+                        g += cnt;
+                    }
+                }
             }
-            // multi-token words: the first two records are requested now and land while the scan runs
-            const bool pooled = nt && (ey & (TW_POOLF | TW_LONGF)) == TW_POOLF;
-            unsigned long long r0 = 0, r1 = 0;
-            if (pooled) { r0 = __ldg(a.upool + ea); if (nt > 1) r1 = __ldg(a.upool + ea + 1); }
-            const uint32_t inc = warp_incl_scan(nt);
-            const uint32_t ex = inc - nt, tot = __shfl_sync(FULL, inc, 31);
-            const bool is_long = (ey & TW_LONGF) != 0;
-            bool staged = false;
-            if (PLAIN) {
-                staged = tot <= TE_STAGE && !__any_sync(FULL, is_long && nt);
-                if (staged) {
-                    if (fill + tot > TE_STAGE) { te_flush(p, o, st, gstart, fill); fill = 0; gstart = carry; }
-                    if (nt) {
-                        const uint32_t si = (uint32_t)(gstart & 3ull) + fill + ex;
-                        if (!pooled) { st.id[si] = ea; st.of[si] = (ey & 0xFFu) | ((ey & 0xFF00u) << 8); }
-                        else {
-                            st.id[si] = (uint32_t)r0; st.of[si] = (uint32_t)(r0 >> 32);
-                            if (nt > 1) { st.id[si + 1] = (uint32_t)r1; st.of[si + 1] = (uint32_t)(r1 >> 32); }
-                            for (uint32_t i = 2; i < nt; i++) {
-                                const unsigned long long r = __ldg(a.upool + ea + i);
-                                st.id[si + i] = (uint32_t)r; st.of[si + i] = (uint32_t)(r >> 32);
+            for (uint32_t d = d_lo + lane; d < d_hi; d += 32) a.doc_tok_off[d] = (unsigned long long)base + __ldg(a.doc_tok_local + d);
+        } else {
+            // documents that own tokens of this slice: d_lo - 1 (continuing from an earlier slice) and those starting here
+            if (base_next == base) continue;
+            const uint32_t lf = lg >> 3, ln = lg & 7u;
+            const uint32_t d_first = d_lo ? d_lo - 1 : 0;
+            for (uint32_t dc = d_first; dc < d_hi && dc < a.n_docs; dc += 31) {
+                // lane l holds the token start of document dc + l (32 values: 31 documents and the end of the last one)
+                const uint32_t dl = dc + lane;
+                const uint32_t my_ds = dl <= a.n_docs ? __ldg(a.doc_tok_start + dl) : 0xFFFFFFFFu;
+                const unsigned long long my_dto = dl < a.n_docs ? a.doc_tok_off[dl] : 0ull;
+                const uint32_t nd_here = min(31u, min(d_hi, a.n_docs) - dc);
+                for (uint32_t e = 0; e < nd_here; e++) {
+                    const uint32_t ds = __shfl_sync(FULL, my_ds, e), dn = __shfl_sync(FULL, my_ds, e + 1);
+                    const unsigned long long dto = __shfl_sync(FULL, my_dto, e);
+                    uint32_t g0 = max(ds, base), g1 = min(dn, base_next);      // real-token range of the document inside this slice
+                    if (g0 >= g1) continue;
+                    unsigned long long kept;
+                    const unsigned long long olen = doc_out_len(p, (unsigned long long)(dn - ds), &kept);
+                    const unsigned long long shift = (p.has_pad && p.pad_left) ? olen - kept : 0;
+                    if ((unsigned long long)(g1 - ds) > kept) g1 = ds + (uint32_t)kept;             // truncation
+                    if (g0 >= g1) continue;
+                    const unsigned long long dbase = dto + shift;                                    // destination of the document's token 0
+                    if (ln == 0) te_copy<OUTS>(a, p, o, src, g0 - base, g1 - base, dbase + (g0 - ds));
+                    else {
+                        // slice-local real index r = g - base; pieces as in the PLAIN case, cut to [g0, g1)
+                        uint32_t j = 0, r = 0;
+                        for (uint32_t i = 0; i <= ln; i++) {
+                            const uint32_t jn = i < ln ? __ldg(a.long_ins + lf + i) : ntok;
+                            {   // inline piece: stream tokens [j, jn) = real indices [r, r + jn - j)
+                                const uint32_t lo = max(g0 - base, r), hi2 = min(g1 - base, r + (jn - j));
+                                if (lo < hi2) te_copy<OUTS>(a, p, o, src, j + (lo - r), j + (hi2 - r), dbase + (base + lo - ds));
+                            }
+                            r += jn - j; j = jn;
+                            if (i < ln) {
+                                uint32_t cnt = __ldg(a.long_ntok + lf + i);
+                                const uint32_t sp = __ldg(a.long_start + lf + i);
+                                if (cnt == TKZ_NONE) { if (lane == 0) atomicMin(a.errw, ((unsigned long long)sp << 8) | a.err_code); cnt = 0; }
+                                const uint32_t lo = max(g0 - base, r), hi2 = min(g1 - base, r + cnt);
+                                if (lo < hi2) {
+                                    const uint32_t c2 = hi2 - lo, sp2 = sp + (lo - r);
+                                    const unsigned long long dd = dbase + (base + lo - ds);
+                                    bool queued = false;
+                                    if (c2 > EMIT_BIG) { if (lane == 0) queued = big_push(a.big, sp2, c2, dd); queued = __shfl_sync(FULL, queued, 0); }
+                                    if (!queued) for (uint32_t q = lane; q < c2; q += 32) emit_real(p, o, dd + q, a.pool_id[sp2 + q], a.pool_s[sp2 + q], a.pool_e[sp2 + q]);
+                                }
+                                r += cnt;
                             }
                         }
                     }
-                    fill += tot;
-                } else if (fill) { te_flush(p, o, st, gstart, fill); fill = 0; }
+                }
             }
-            if (!staged) {
-                // destination of the word's first token
-                uint32_t cnt = nt; unsigned long long dst = (unsigned long long)carry + ex;
-                if (!PLAIN && nt) {
-                    // owning document = last document whose first-word reference is <= this word's index in the slice
-                    uint32_t lo = d_lo, hi = d_hi;
-                    while (lo < hi) { const uint32_t mid = lo + ((hi - lo) >> 1); if (__ldg(a.doc_word_ref + mid) <= k) lo = mid + 1; else hi = mid; }
-                    const uint32_t d = lo - 1;
-                    const uint32_t ds = __ldg(a.doc_tok_start + d);
-                    const unsigned long long doc_t = (unsigned long long)(__ldg(a.doc_tok_start + d + 1) - ds);
-                    unsigned long long kept;
-                    const unsigned long long olen = doc_out_len(p, doc_t, &kept);
-                    const unsigned long long j0 = (unsigned long long)(carry + ex) - ds;
-                    const unsigned long long room = j0 < kept ? kept - j0 : 0;
-                    if ((unsigned long long)cnt > room) cnt = (uint32_t)room;
-                    dst = a.doc_tok_off[d] + ((p.has_pad && p.pad_left) ? olen - kept : 0) + j0;
-                }
-                if (cnt && !is_long) {
-                    if (!(ey & TW_POOLF)) emit_real(p, o, dst, ea, ey & 0xFFu, (ey >> 8) & 0xFFu);
-                    else for (uint32_t i = 0; i < cnt; i++) {
-                        const unsigned long long r = __ldg(a.upool + ea + i);
-                        emit_real(p, o, dst + i, (uint32_t)r, (uint32_t)(r >> 32) & 0xFFFFu, (uint32_t)(r >> 48));
-                    }
-                }
-                // long-list words: tokens sit in the pool at the word's byte position; copied by the whole warp, or queued
-                // for the grid-wide copy when very long
-                uint32_t src = 0;
-                if (is_long && cnt) src = __ldg(a.long_start + ea);
-                if (is_long && cnt > EMIT_BIG && big_push(a.big, src, cnt, dst)) cnt = 0;
-                uint32_t big = __ballot_sync(FULL, cnt && is_long);
-                while (big) {
-                    const int l = __ffs(big) - 1; big &= big - 1;
-                    const uint32_t c = __shfl_sync(FULL, cnt, l), sp = __shfl_sync(FULL, src, l);
-                    const unsigned long long dd = __shfl_sync(FULL, dst, l);
-                    for (uint32_t i = lane; i < c; i += 32) emit_real(p, o, dd + i, a.pool_id[sp + i], a.pool_s[sp + i], a.pool_e[sp + i]);
-                }
-                if (PLAIN) gstart = (unsigned long long)carry + tot;
-            }
-            carry += tot;
-        }
-        if (PLAIN) {
-            if (fill) te_flush(p, o, st, gstart, fill);
-            for (uint32_t d = d_lo + lane; d < d_hi; d += 32) a.doc_tok_off[d] = (unsigned long long)base + __ldg(a.doc_tok_local + d);
         }
     }
-    if (lane == 0 && words_total) atomicAdd(a.n_words, (unsigned long long)words_total);
 }
 
 // per document: global token index of its start, real token count, output slot count (feeds the scan -> CSR offsets)
@@ -996,6 +1163,7 @@ __global__ void __launch_bounds__(256) emit_pad_real_kernel(EmitParams p, EmitOu
     if (p.outputs & 4u) warp_fill_u32(o.attention + base, npad, 0u);
     if (p.outputs & 8u) warp_fill_u32(o.type_ids + base, npad, p.pad_type_id);
     if (p.outputs & 16u) warp_fill_u32(o.special + base, npad, 1u);
+    if (p.outputs & 32u) { uint16_t* q = o.offsets16 + base; for (unsigned long long i = lane_id(); i < npad; i += 32) q[i] = 0; }
 }
 
 // document of the first failing word (byte position in the error word) -> ctrl[4]
