@@ -40,7 +40,7 @@ def build(force=False, verbose=False):
     objs = []
     for src in CU_SRCS:
         obj = os.path.join(LIB_DIR, os.path.basename(src) + ".o")
-        cmd = [NVCC, *ARCH, "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC", "-c", src, "-o", obj]
+        cmd = [NVCC, *ARCH, "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC", *os.environ.get("TKZ_NVCC_FLAGS", "").split(), "-c", src, "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         subprocess.check_call(cmd)

@@ -43,7 +43,12 @@ namespace tkz {
 
 constexpr int TW_THREADS = 256, TW_WARPS = 8, TW_SEG = 32, TW_SLICE = 32 * TW_SEG;      // slice = 1 KiB = one 32-byte segment per lane
 constexpr int TW_PRE = 16, TW_POST = 48, TW_STAGE = TW_PRE + TW_SLICE + TW_POST;         // staged window: 16 B before, 48 B behind the slice
-constexpr int TW_BLOCKS_PER_SM = 4;                // pass A: 64 registers per thread
+#ifndef TKZ_BPS
+#define TKZ_BPS 3
+#endif
+constexpr int TW_BLOCKS_PER_SM = TKZ_BPS;          // pass A: 3 blocks of 8 warps -> 80 registers per thread and ~150 KB of shared memory per SM, which leaves
+                                                   // ~90 KB of L1 for the table probes; 4 blocks -> 64 registers: the round loop spills (B200, c2b 1 GiB: 4.93 ms
+                                                   // against 4.25; build-time A/B: TKZ_NVCC_FLAGS=-DTKZ_BPS=4)
 constexpr uint32_t TW_TOK_CHUNK = 16384;           // tokens a warp claims from the token stream with one atomic (then sub-allocates)
 constexpr uint32_t TW_SLICE_TOK_MAX = TW_SLICE + 256;   // tokens the words that start in one slice can have (<= their bytes)
 constexpr uint32_t TW_MAX_SHORT = 15;             // bytes next to the length byte in the 128-bit key
@@ -89,12 +94,13 @@ struct SliceArgs {
     const uint8_t* text; uint64_t n;
     const uint64_t* doc_off; uint32_t n_docs;
     uint32_t n_slices;
+    uint32_t n_bulk;                              // slices [0, n_bulk) have their whole staged window inside the text
     const uint32_t* slice_doc_lo;                 // first document with doc_off >= slice start (n_slices + 1 entries)
     WordSlot* table; uint32_t table_shift; uint32_t med_base, med_mask;          // slot = hash >> table_shift
     WordSlot32* table32; uint32_t table32_mask;
     unsigned long long* upool; uint32_t upool_cap; unsigned int* upool_count;     // token records: id | start << 32 | end << 48
     uint32_t* lscratch;                           // per warp of the grid: 4 * 256 u32, symbol arrays of words of 65..255 bytes
-    uint32_t* tok_id; uint16_t* tok_of; uint32_t tok_cap; unsigned int* tok_count; // token stream; tok_of == nullptr: offsets not wanted
+    uint32_t* tok_id; uint2* tok2; uint32_t tok_cap; unsigned int* tok_count;     // token stream: ids only, or {id, start | end << 8} records (tok2) when the call wants offsets
     uint32_t* slice_tok_off; uint32_t* slice_ntok_inline; uint32_t* slice_ntok;   // slice_ntok (+ long words) is scanned -> token base
     uint32_t* slice_long;                         // first long-list index << 3 | count of the long words that start in the slice
     uint32_t* doc_tok_local;                      // per document: tokens of its slice before its first word
@@ -128,6 +134,7 @@ struct __align__(16) SliceShared {                                      // per w
     uint32_t seg_smask[32], seg_wex[32];                  // per 32-byte segment: word-start bits, words of the slice before it
     uint32_t doc_lo_hi[2];                                // documents that start inside the slice: [lo, hi)
     uint32_t lbuf[TW_MAX_SLICE_LONG][3];                  // long words of the slice: position, length, token index of insertion
+    uint4 plist[32];                                      // words of 3+ tokens whose records wait to be copied from the pool: {first record, count, stream position}
 };
 struct BlockShared {
     uint32_t lut[256];                                    // [7:0] normalised byte, bit 8 WORD, bit 9 ISOLATE
@@ -584,6 +591,24 @@ __device__ __forceinline__ WholeWarpOut tw_own_word(const DevModel& m, const Sli
     return out;
 }
 
+// copies the token records of the listed words (three or more tokens each) from the pool into the token stream: four lanes
+// per word, eight words per step, so that the L2 round trips of a whole slice overlap (one at a time they were 17 % of the
+// kernel's stall samples)
+__device__ __forceinline__ void tw_flush_pooled(const SliceArgs& a, const uint4* plist, uint32_t n) {
+    const uint32_t lane = lane_id();
+    __syncwarp();
+    for (uint32_t e = lane >> 2; e < n; e += 8) {
+        const uint4 q = plist[e];
+        for (uint32_t i = lane & 3u; i < q.y; i += 4) {
+            const unsigned long long r = __ldcg(a.upool + q.x + i);       // written in THIS launch by the word's owner: L2, not the read-only path
+            const uint32_t of = ((uint32_t)(r >> 32) & 0xFFu) | ((uint32_t)(r >> 48) << 8);
+            if (a.tok2) a.tok2[q.z + i] = make_uint2((uint32_t)r, of);
+            else a.tok_id[q.z + i] = (uint32_t)r;
+        }
+    }
+    __syncwarp();
+}
+
 // CLS: 0 byte ranges + identity byte map, 1 byte ranges + ASCII lower-case, 2 LUT + identity, 3 LUT + arbitrary byte map
 // pass A: one warp per 1 KiB slice, slices strided over all warps of the grid (4 blocks of 8 warps per SM)
 template <int MODEL, int CLS>
@@ -613,12 +638,11 @@ __global__ void __launch_bounds__(TW_THREADS, TW_BLOCKS_PER_SM) slice_words_kern
     if (CLS == 2 && lane < 8) for (int j = 0; j < 32; j++) { const uint32_t e = bs.lut[32 * lane + j]; cw_word |= ((e >> 8) & 1u) << j; cw_iso |= ((e >> 9) & 1u) << j; }
     const uint32_t stride = gridDim.x * TW_WARPS;
     const uint32_t gwarp = blockIdx.x * TW_WARPS + wid;
-    uint32_t* const lscr = a.lscratch + (size_t)gwarp * (4 * 256);
     bool warp_abort = false;
 
     // a slice whose whole staged window lies inside the text is fetched by a bulk copy; the last one or two slices of the
     // batch are loaded byte by byte with bounds checks
-    auto bulk_ok = [&](uint32_t sl) -> bool { return sl < a.n_slices && (uint64_t)sl * TW_SLICE + TW_SLICE + TW_POST <= a.n; };
+    auto bulk_ok = [&](uint32_t sl) -> bool { return sl < a.n_bulk; };
     auto issue = [&](uint32_t sl, uint32_t buf) {
         const uint64_t base = (uint64_t)sl * TW_SLICE;
         if (sl == 0) tw_bulk_load(reinterpret_cast<uint8_t*>(sh.raw[buf]) + TW_PRE, a.text, TW_SLICE + TW_POST, &sh.bar[buf]);
@@ -629,7 +653,7 @@ __global__ void __launch_bounds__(TW_THREADS, TW_BLOCKS_PER_SM) slice_words_kern
     uint32_t meta = (lane < 2 && s < a.n_slices) ? __ldg(a.slice_doc_lo + s + lane) : 0u;
     uint32_t tcur = 0, tend = 0;                                // the warp's current chunk of the token stream
     uint32_t buf = 0, phase = 0;                                // staging window in use, parity bits of the two mbarriers
-    unsigned long long words_total = 0;
+    uint32_t words_total = 0;
     if (lane == 0 && a.stage_bulk && bulk_ok(s)) issue(s, 0);
     for (; s < a.n_slices; s += stride, buf ^= 1u) {
         const uint64_t slice_base = (uint64_t)s * TW_SLICE;
@@ -745,7 +769,7 @@ __global__ void __launch_bounds__(TW_THREADS, TW_BLOCKS_PER_SM) slice_words_kern
 
         // ---- phase 3: one word per lane
         uint32_t run = 0;                                           // tokens of the slice's words so far
-        uint32_t n_long_here = 0;
+        uint32_t n_long_here = 0, n_pl = 0;
         for (uint32_t k0 = 0; k0 < nW; k0 += 32) {
             const uint32_t k = k0 + lane;
             const bool have = k < nW;
@@ -862,13 +886,14 @@ __global__ void __launch_bounds__(TW_THREADS, TW_BLOCKS_PER_SM) slice_words_kern
                             if (y != 0) { v.a = x; v.b = y; v.c = 0; v.d = 0; state = 0; }
                         }
                         pend32 = __ballot_sync(FULL, state == 6);
+                        if (pend32) __nanosleep(64);              // the owner is running the model: leave it the issue slots
                     }
                 }
                 // words that need the whole warp: longer than 31 bytes, or no slot within the probe limit
                 uint32_t todo = __ballot_sync(FULL, state == 3);
                 while (todo) {
                     const int l = __ffs(todo) - 1; todo &= todo - 1;
-                    const WholeWarpOut r = tw_whole_warp_word<MODEL>(m, a, bs.lut, sh, tw, s, __shfl_sync(FULL, p, l), __shfl_sync(FULL, len, l), lscr);
+                    const WholeWarpOut r = tw_whole_warp_word<MODEL>(m, a, bs.lut, sh, tw, s, __shfl_sync(FULL, p, l), __shfl_sync(FULL, len, l), a.lscratch + (size_t)(blockIdx.x * TW_WARPS + wid) * (4 * 256));
                     if (r.abort) warp_abort = true;
                     if ((int)lane == l) { v = r.v; state = 0; }
                 }
@@ -880,6 +905,7 @@ __global__ void __launch_bounds__(TW_THREADS, TW_BLOCKS_PER_SM) slice_words_kern
                         if (q.y != 0) { v.a = q.x; v.b = q.y; v.c = q.z; v.d = q.w; state = 0; }
                     }
                     pend = __ballot_sync(FULL, state == 2);
+                    if (pend) __nanosleep(64);
                 }
             }
             // ---- tokens + token prefix
@@ -892,20 +918,16 @@ __global__ void __launch_bounds__(TW_THREADS, TW_BLOCKS_PER_SM) slice_words_kern
             else { const uint32_t inc = warp_incl_scan(nt); ex = inc - nt; tot = __shfl_sync(FULL, inc, 31); }
             const uint32_t dst = tbase + run + ex;                  // stream position of the word's first token
             if (can_store && nt && !(flags & TW_POOLF)) {
-                a.tok_id[dst] = v.a;
-                if (nt == 2) a.tok_id[dst + 1] = v.c;
-                if (a.tok_of) { a.tok_of[dst] = (uint16_t)v.b; if (nt == 2) a.tok_of[dst + 1] = (uint16_t)v.d; }
+                if (a.tok2) { a.tok2[dst] = make_uint2(v.a, v.b & 0xFFFFu); if (nt == 2) a.tok2[dst + 1] = make_uint2(v.c, v.d & 0xFFFFu); }
+                else { a.tok_id[dst] = v.a; if (nt == 2) a.tok_id[dst + 1] = v.c; }
             }
-            // words with three or more tokens: their records are copied from the pool by the whole warp, one word at a time
-            uint32_t pooled = __ballot_sync(FULL, can_store && nt && (flags & TW_POOLF));
-            while (pooled) {
-                const int l = __ffs(pooled) - 1; pooled &= pooled - 1;
-                const uint32_t pa = __shfl_sync(FULL, v.a, l), pn = __shfl_sync(FULL, nt, l), pd = __shfl_sync(FULL, dst, l);
-                for (uint32_t i = lane; i < pn; i += 32) {
-                    const unsigned long long r = __ldcg(a.upool + pa + i);       // written in THIS launch by the word's owner: L2, not the read-only path
-                    a.tok_id[pd + i] = (uint32_t)r;
-                    if (a.tok_of) a.tok_of[pd + i] = (uint16_t)(((uint32_t)(r >> 32) & 0xFFu) | ((uint32_t)(r >> 48) << 8));
-                }
+            // words with three or more tokens: listed now, copied from the pool at the end of the slice
+            const uint32_t pooled = __ballot_sync(FULL, can_store && nt && (flags & TW_POOLF));
+            if (pooled) {
+                const uint32_t np = __popc(pooled);
+                if (n_pl + np > 32) { tw_flush_pooled(a, sh.plist, n_pl); n_pl = 0; }
+                if ((pooled >> lane) & 1u) sh.plist[n_pl + __popc(pooled & lt_mask)] = make_uint4(v.a, nt, dst, 0u);
+                n_pl += np;
             }
             if (__any_sync(FULL, flags & (TW_ERRF | TW_LONGF))) {
                 if (flags & TW_ERRF) atomicMin(a.errw, ((unsigned long long)(slice_base + p) << 8) | (MODEL == TKZ_MODEL_BPE ? TKZ_ECODE_UTF8 : TKZ_ECODE_UNK));
@@ -920,6 +942,7 @@ __global__ void __launch_bounds__(TW_THREADS, TW_BLOCKS_PER_SM) slice_words_kern
             if (have) sh.wlist[k] = (uint16_t)(run + ex);      // (the round's wlist entries were read at its top, before the votes)
             run += tot;
         }
+        if (n_pl) tw_flush_pooled(a, sh.plist, n_pl);
         if (can_store) tcur += run;
         // long words -> one contiguous run of the long list
         uint32_t lfirst = 0;
@@ -954,7 +977,7 @@ __global__ void __launch_bounds__(TW_THREADS, TW_BLOCKS_PER_SM) slice_words_kern
         }
         __syncwarp();
     }
-    if (lane == 0 && words_total) atomicAdd(a.n_words, words_total);
+    if (lane == 0 && words_total) atomicAdd(a.n_words, (unsigned long long)words_total);
     if (__any_sync(FULL, warp_abort) && lane == 0) atomicExch(a.abort_flag, 1u);
 }
 
@@ -976,7 +999,7 @@ __global__ void long_fix_kernel(const uint32_t* __restrict__ long_start, const u
 // ------------------------------------------------------------------ pass B
 struct SliceEmitArgs {
     const uint64_t* doc_off; uint32_t n_docs; uint32_t n_slices; const uint32_t* slice_doc_lo;
-    const uint32_t* tok_id; const uint16_t* tok_of;
+    const uint32_t* tok_id; const uint2* tok2;     // ids only, or {id, start | end << 8} records
     const uint32_t* slice_tok_off; const uint32_t* slice_ntok_inline; const uint32_t* slice_long;
     const uint32_t* slice_tokbase;                // exclusive scan of the slice token counts (n_slices + 1)
     const uint32_t* long_start; const uint32_t* long_ins; const uint32_t* long_ntok;
@@ -1011,7 +1034,10 @@ __device__ __forceinline__ void te_copy(const SliceEmitArgs& a, const EmitParams
     for (uint32_t j = j0 + lane; j < j1; j += 128) {
         uint32_t id[4], of[4] = {0, 0, 0, 0};
 #pragma unroll
-        for (int u = 0; u < 4; u++) if (j + 32 * u < j1) { id[u] = __ldg(a.tok_id + src + j + 32 * u); if (want_of) of[u] = __ldg(a.tok_of + src + j + 32 * u); }
+        for (int u = 0; u < 4; u++) if (j + 32 * u < j1) {
+            if (want_of) { const uint2 r = __ldg(a.tok2 + src + j + 32 * u); id[u] = r.x; of[u] = r.y; }
+            else id[u] = __ldg(a.tok_id + src + j + 32 * u);
+        }
 #pragma unroll
         for (int u = 0; u < 4; u++) if (j + 32 * u < j1) te_put<OUTS>(p, o, dst0 + (j + 32 * u - j0), id[u], of[u]);
     }
