@@ -99,6 +99,9 @@ typedef struct tkz_model_desc {
  * is shorter than 256 bytes.  A batch with a longer pre-token (or a tokenizer without pre-tokenizer) falls back to
  * TKZ_OUT_OFFSETS for the whole call: exactly one of offsets / offsets_packed is then non-NULL. */
 #define TKZ_OUT_OFFSETS_PACKED 32u
+/* Ids as u16 in tkz_batch_result.ids16 instead of u32 in ids: honoured when every id of the uploaded vocabulary is below
+ * 65536 (GPT-2- and BERT-sized vocabularies), ignored otherwise: exactly one of ids / ids16 is non-NULL. */
+#define TKZ_OUT_IDS_U16 64u
 
 /* Per-call knobs = the public fields Tokenizer.truncation / Tokenizer.padding (src/lib.zig:41-42,149-157;
  * src/types.zig:39-45,55-59).  stride / strategy / pad_token are ignored by the reference's encode. */
@@ -129,6 +132,7 @@ typedef struct tkz_batch_result {
     const uint32_t* special_tokens_mask;
     int64_t err_doc;                    /* document index of the first error, -1 if none */
     const uint16_t* offsets_packed;     /* n_tokens x (start | end << 8), see TKZ_OUT_OFFSETS_PACKED; padding slots are 0 */
+    const uint16_t* ids16;              /* n_tokens, see TKZ_OUT_IDS_U16 */
 } tkz_batch_result;
 
 /* counters of the last encode (FastTokenizer.arenaMemoryUsage analogue, src/lib.zig:451-453) */
@@ -164,6 +168,32 @@ int tkz_model_upload(tkz_ctx* ctx, const tkz_model_desc* desc);
  * by the context.  Total text must be < 4 GiB per call (offsets are u32, src/types.zig:4-6). */
 int tkz_encode_batch(tkz_ctx* ctx, const uint8_t* text, const uint64_t* doc_off, uint64_t n_docs,
                      const tkz_encode_params* params, tkz_batch_result* out);
+
+/* Compact batch encoding: ONLY what has to cross PCIe.  Everything in an Encoding that is a constant of (kept token count,
+ * padding parameters) -- attention_mask, type_ids, special_tokens_mask, every padding slot (src/encoding.zig:246-294,
+ * 385-463) -- is rebuilt on the host by tkz_compact_expand when and where the caller wants it; ids travel as u16 when the
+ * vocabulary allows, offsets as one u16 per token (TKZ_OUT_OFFSETS_PACKED).  Truncation is applied on the device.
+ * Arrays are HOST pointers owned by the context (valid until the next encode on it). */
+typedef struct tkz_compact_result {
+    uint64_t n_docs;
+    uint64_t n_kept;                    /* real tokens after truncation, all documents */
+    uint64_t n_real_tokens;             /* before truncation */
+    const uint64_t* doc_kept_off;       /* n_docs + 1: document d keeps tokens [doc_kept_off[d], doc_kept_off[d+1]) */
+    const uint32_t* ids;                /* n_kept, or NULL when ids16 is delivered */
+    const uint16_t* ids16;
+    const uint16_t* offsets_packed;     /* n_kept x (start | end << 8), or NULL (a pre-token of 256+ bytes: see offsets) */
+    const uint32_t* offsets;            /* 2 * n_kept, or NULL */
+    tkz_encode_params params;           /* truncation / padding the expanded Encodings have */
+    int64_t err_doc;
+} tkz_compact_result;
+int tkz_encode_batch_compact(tkz_ctx* ctx, const uint8_t* text, const uint64_t* doc_off, uint64_t n_docs,
+                             const tkz_encode_params* params, int want_offsets, tkz_compact_result* out);
+/* slots documents [d0, d1) occupy after padding (the sizes tkz_compact_expand needs) */
+uint64_t tkz_compact_slots(const tkz_compact_result* r, uint64_t d0, uint64_t d1);
+/* Encoding.fromTokens + Encoding.pad for documents [d0, d1) on the host: fills the arrays that are not NULL (offsets: 2 u32
+ * per slot; doc_tok_off: d1 - d0 + 1 entries relative to d0).  Plain CPU code: nothing is tokenized here. */
+int tkz_compact_expand(const tkz_compact_result* r, uint64_t d0, uint64_t d1, uint64_t* doc_tok_off, uint32_t* ids,
+                       uint32_t* offsets, uint32_t* attention_mask, uint32_t* type_ids, uint32_t* special_tokens_mask);
 
 /* Same, text and doc_off already DEVICE resident; result arrays are DEVICE pointers (scalars in *out are host
  * values).  All work is enqueued on the context's stream; the call returns after the stream has drained. */

@@ -813,3 +813,88 @@ def test_decode_round_trip_at_size():
         if b"\xc4\xa0" not in kept and b"##" not in kept:               # whatever decoder the JSON names leaves these documents alone
             assert dec[i] == kept
     t.close()
+
+
+# ----------------------------------------------------------------------------- compact result / packed formats
+@pytest.mark.parametrize("seed", range(12))
+def test_compact_result_expands_to_the_reference_encoding(seed):
+    """tkz_encode_batch_compact ships kept ids (u16 when the vocabulary allows) + one u16 of offsets per token and nothing that is a
+    constant of the parameters; tkz_compact_expand must rebuild the reference's six arrays bit-exactly (truncation, left and
+    right padding, documents without tokens), for the whole batch and for any document range."""
+    rng = random.Random(4200 + seed)
+    if seed % 2:
+        js, alpha = rand_wp_json(rng)
+    else:
+        js, alpha = rand_bpe_json(rng, n_merges=30, pretok="Whitespace")
+    t, o = pair(js, mode=MODES[seed % 3])
+    docs = rand_docs(rng, alpha, 300, max_len=60) + [b"", b"   "]
+    trunc = [None, 0, 1, 5, 8, 64][seed % 6]
+    pad = [None, {"length": 8, "pad_id": 7, "pad_type_id": 3, "direction": "right"}, {"length": 5, "pad_id": 0, "direction": "left"},
+           {"length": None, "pad_id": 9}][(seed // 2) % 4]
+    t.truncation = None if trunc is None else {"max_length": trunc}
+    o.truncation = trunc
+    t.padding = pad
+    o.padding = pad
+    ref = o.encode_batch(docs)
+    text, off = tz.pack_docs(docs)
+    r = t.encode_compact(text, off)
+    assert r.ids16 and not r.ids, "small vocabulary: ids must travel as u16"
+    if MODES[seed % 3] != "occurrence":
+        assert r.offsets_packed and not r.offsets
+    assert_same(tz.expand_compact(r), ref, f"seed {seed} trunc {trunc} pad {pad}")
+    lo, hi = 17, 203
+    part = tz.expand_compact(r, lo, hi)
+    a, b = int(ref.doc_tok_off[lo]), int(ref.doc_tok_off[hi])
+    assert np.array_equal(part.doc_tok_off, ref.doc_tok_off[lo:hi + 1] - ref.doc_tok_off[lo])
+    assert np.array_equal(part.ids, ref.ids[a:b]) and np.array_equal(part.offsets, ref.offsets[a:b])
+    assert np.array_equal(part.attention_mask, ref.attention_mask[a:b]) and np.array_equal(part.type_ids, ref.type_ids[a:b])
+    assert np.array_equal(part.special_tokens_mask, ref.special_tokens_mask[a:b])
+    # ids only
+    r2 = t.encode_compact(text, off, want_offsets=False)
+    assert not r2.offsets_packed and not r2.offsets
+    assert np.array_equal(tz.expand_compact(r2).ids, ref.ids)
+    t.close()
+
+
+def test_packed_formats_fall_back_when_they_cannot_hold_the_values(monkeypatch):
+    """offsets_packed needs every pre-token below 256 bytes (else the whole call -- every chunk of the host path -- delivers
+    32-bit offsets); ids16 needs every vocabulary id below 65536."""
+    rng = random.Random(77)
+    js, alpha = rand_bpe_json(rng, n_merges=40, alphabet=list("abcdefg"), pretok="Whitespace", dead_merges=0.0)
+    t, o = pair(js)
+    short = [b" ".join(bytes(rng.choice(b"abcdefg") for _ in range(rng.randint(1, 40))) for _ in range(rng.randint(1, 30))) for _ in range(2000)]
+    long_doc = b"ab " + bytes(rng.choice(b"abcdefg") for _ in range(300)) + b" cd"
+    for docs, packed in ((short, True), (short[:1000] + [long_doc] + short[1000:], False)):
+        for chunk in (1 << 31, 16384):
+            monkeypatch.setenv("TKZ_CHUNK_BYTES", str(chunk))
+            t2 = tz.Tokenizer.from_json(js, device=0)
+            text, off = tz.pack_docs(docs)
+            got = t2.encode_packed(text, off, outputs=tz.OUT_IDS | tz.OUT_OFFSETS_PACKED | tz.OUT_IDS_U16)
+            ref = o.encode_batch(docs, threads=4)
+            assert (got.offsets_packed is not None) == packed and (got.offsets is not None) == (not packed)
+            assert np.array_equal(got.ids, ref.ids) and np.array_equal(got.unpacked_offsets(), ref.offsets) and np.array_equal(got.doc_tok_off, ref.doc_tok_off)
+            r = t2.encode_compact(text, off)
+            assert bool(r.offsets_packed) == packed
+            assert_same(tz.expand_compact(r), ref, f"packed={packed} chunk={chunk}")
+            t2.close()
+    t.close()
+    # vocabulary ids above 65535: ids stay u32
+    v = {c: 70000 + i for i, c in enumerate("abcd")}
+    v["ab"] = 70010
+    js2 = json.dumps({"model": {"type": "BPE", "vocab": v, "merges": ["a b"]}, "pre_tokenizer": {"type": "Whitespace"}})
+    t3, o3 = pair(js2)
+    docs = [b"ab abcd", b"", b"dcba ab"]
+    text, off = tz.pack_docs(docs)
+    r = t3.encode_compact(text, off)
+    assert r.ids and not r.ids16
+    assert_same(tz.expand_compact(r), o3.encode_batch(docs))
+    t3.close()
+    # no pre-tokenizer: a pre-token can have any length, offsets are always 32-bit
+    js3 = json.dumps({"model": {"type": "BPE", "vocab": {"a": 0, "b": 1, "ab": 2}, "merges": ["a b"]}})
+    t4, o4 = pair(js3)
+    docs = [b"abab" * 100, b"ba"]
+    text, off = tz.pack_docs(docs)
+    r = t4.encode_compact(text, off)
+    assert r.offsets and not r.offsets_packed
+    assert_same(tz.expand_compact(r), o4.encode_batch(docs))
+    t4.close()

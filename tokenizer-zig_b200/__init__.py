@@ -30,6 +30,7 @@ _ERR_NAMES = {ERR_OOM: "OutOfMemory", ERR_MISSING_UNK: "MissingUnkToken", ERR_IN
               ERR_INVALID_VOCAB_ENTRY: "InvalidVocabEntry", ERR_IO: "IoError"}
 
 OUT_IDS, OUT_OFFSETS, OUT_ATTENTION, OUT_TYPE_IDS, OUT_SPECIAL, OUT_ALL = 1, 2, 4, 8, 16, 31
+OUT_IDS_U16 = 64                 # ids as u16 (ids16) when every id of the vocabulary is < 65536
 OUT_OFFSETS_PACKED = 32          # one u16 per token (start | end << 8); falls back to OUT_OFFSETS when a pre-token has >= 256 bytes
 NORM_CFG_LOWER, NORM_BERT_STRUCT, NORM_LOWER_STRUCT = 1, 2, 3
 PT_WS_CFG, PT_BERT_CFG, PT_WS_STRUCT, PT_BERT_STRUCT, PT_BYTELEVEL_STRUCT = 1, 2, 3, 4, 5
@@ -92,6 +93,23 @@ class BatchResult(C.Structure):
         ("special_tokens_mask", C.c_void_p),
         ("err_doc", C.c_int64),
         ("offsets_packed", C.c_void_p),
+        ("ids16", C.c_void_p),
+    ]
+
+
+class CompactResult(C.Structure):
+    """tkz_compact_result: kept real tokens only; padding / masks are rebuilt on the host (tkz_compact_expand)."""
+    _fields_ = [
+        ("n_docs", C.c_uint64),
+        ("n_kept", C.c_uint64),
+        ("n_real_tokens", C.c_uint64),
+        ("doc_kept_off", C.c_void_p),
+        ("ids", C.c_void_p),
+        ("ids16", C.c_void_p),
+        ("offsets_packed", C.c_void_p),
+        ("offsets", C.c_void_p),
+        ("params", EncodeParams),
+        ("err_doc", C.c_int64),
     ]
 
 
@@ -109,7 +127,7 @@ class Stats(C.Structure):
 # every symbol include/tokzig_b200.h declares (checked by tests/test_cabi_symbols.py)
 EXPORTED_SYMBOLS = [
     "tkz_ctx_create", "tkz_ctx_destroy", "tkz_last_error", "tkz_ctx_get_stats", "tkz_model_upload", "tkz_encode_batch",
-    "tkz_encode_batch_device", "tkz_decode_upload", "tkz_decode_batch",
+    "tkz_encode_batch_device", "tkz_encode_batch_compact", "tkz_compact_slots", "tkz_compact_expand", "tkz_decode_upload", "tkz_decode_batch",
     "tkzh_from_json", "tkzh_from_file", "tkzh_free", "tkzh_last_error", "tkzh_ctx", "tkzh_set_truncation", "tkzh_set_padding",
     "tkzh_set_normalizer", "tkzh_set_pretokenizer", "tkzh_encode_batch", "tkzh_decode", "tkzh_decode_batch", "tkzh_get_vocab_size", "tkzh_token_to_id",
     "tkzh_id_to_token", "tkzh_add_special_tokens", "tkzh_model_vocab_count", "tkzh_merge_count", "tkzh_has_normalizer",
@@ -137,6 +155,10 @@ def lib():
     L.tkz_model_upload.argtypes = [vp, C.POINTER(ModelDesc)]
     L.tkz_encode_batch.argtypes = [vp, vp, vp, u64, C.POINTER(EncodeParams), C.POINTER(BatchResult)]
     L.tkz_encode_batch_device.argtypes = [vp, vp, vp, u64, u64, C.POINTER(EncodeParams), C.POINTER(BatchResult)]
+    L.tkz_encode_batch_compact.argtypes = [vp, vp, vp, u64, C.POINTER(EncodeParams), i32, C.POINTER(CompactResult)]
+    L.tkz_compact_slots.argtypes = [C.POINTER(CompactResult), u64, u64]
+    L.tkz_compact_slots.restype = u64
+    L.tkz_compact_expand.argtypes = [C.POINTER(CompactResult), u64, u64, vp, vp, vp, vp, vp, vp]
     L.tkzh_from_json.argtypes = [C.c_char_p, u64, i32, vp, C.POINTER(vp)]
     L.tkzh_from_file.argtypes = [C.c_char_p, i32, vp, C.POINTER(vp)]
     L.tkzh_free.argtypes = [vp]
@@ -233,7 +255,7 @@ def _result_to_batch(r: BatchResult) -> BatchEncoding:
     offs = _copy(r.offsets, 2 * T, np.uint32).reshape(-1, 2) if r.offsets else None
     return BatchEncoding(
         doc_tok_off=_copy(r.doc_tok_off, n + 1, np.uint64),
-        ids=_copy(r.ids, T, np.uint32),
+        ids=_copy(r.ids16, T, np.uint16).astype(np.uint32) if r.ids16 else _copy(r.ids, T, np.uint32),
         offsets=offs,
         attention_mask=_copy(r.attention_mask, T, np.uint32) if r.attention_mask else None,
         type_ids=_copy(r.type_ids, T, np.uint32) if r.type_ids else None,
@@ -241,6 +263,22 @@ def _result_to_batch(r: BatchResult) -> BatchEncoding:
         n_real_tokens=int(r.n_real_tokens),
         offsets_packed=_copy(r.offsets_packed, T, np.uint16) if r.offsets_packed else None,
     )
+
+
+def expand_compact(r: CompactResult, d0: int = 0, d1: Optional[int] = None) -> BatchEncoding:
+    """tkz_compact_expand for documents [d0, d1): the six arrays of the reference's Encoding (src/encoding.zig:231-243), CSR."""
+    L = lib()
+    d1 = int(r.n_docs) if d1 is None else d1
+    n = int(L.tkz_compact_slots(C.byref(r), d0, d1))
+    off = np.zeros(d1 - d0 + 1, np.uint64)
+    ids, attn, typ, sp = (np.zeros(n, np.uint32) for _ in range(4))
+    has_off = bool(r.offsets_packed or r.offsets)
+    offs = np.zeros((n, 2), np.uint32) if has_off else None
+    rc = L.tkz_compact_expand(C.byref(r), d0, d1, off.ctypes.data, ids.ctypes.data, offs.ctypes.data if has_off else None, attn.ctypes.data,
+                              typ.ctypes.data, sp.ctypes.data)
+    if rc != OK:
+        raise TokzigError(rc, "tkz_compact_expand")
+    return BatchEncoding(off, ids, offs, attn, typ, sp, int(r.n_real_tokens))
 
 
 def pack_docs(docs: Sequence[bytes]):
@@ -299,6 +337,18 @@ class Context:
         if rc != OK:
             raise TokzigError(rc, self._err(), int(r.err_doc))
         return _result_to_batch(r)
+
+    def encode_batch_compact(self, text: np.ndarray, doc_off: np.ndarray, params: Optional[EncodeParams] = None, want_offsets: bool = True) -> CompactResult:
+        """tkz_encode_batch_compact: the raw struct (its arrays belong to the context until the next encode); see expand_compact."""
+        text = np.ascontiguousarray(text, dtype=np.uint8)
+        doc_off = np.ascontiguousarray(doc_off, dtype=np.uint64)
+        r = CompactResult()
+        p = params if params is not None else EncodeParams()
+        rc = self._L.tkz_encode_batch_compact(self._h, text.ctypes.data if text.size else None, doc_off.ctypes.data, len(doc_off) - 1,
+                                              C.byref(p), 1 if want_offsets else 0, C.byref(r))
+        if rc != OK:
+            raise TokzigError(rc, self._err(), int(r.err_doc))
+        return r
 
     def encode_batch_device(self, d_text_ptr: int, d_doc_off_ptr: int, n_docs: int, text_bytes: int,
                             params: Optional[EncodeParams] = None) -> BatchResult:
@@ -395,6 +445,30 @@ class Tokenizer:
         if rc != OK:
             raise TokzigError(rc, (self._L.tkzh_last_error(self._h) or b"").decode(), int(r.err_doc))
         return _result_to_batch(r)
+
+    def params(self, outputs: int = OUT_ALL) -> EncodeParams:
+        """the public fields truncation / padding as the tkz_encode_params of a device-layer call"""
+        p = EncodeParams()
+        if self.truncation is not None:
+            p.has_truncation, p.max_length = 1, int(self.truncation.get("max_length", 512))
+        if self.padding is not None and self.padding.get("length") is not None:
+            p.has_padding, p.pad_length = 1, int(self.padding["length"])
+            p.pad_id, p.pad_type_id = int(self.padding.get("pad_id", 0)), int(self.padding.get("pad_type_id", 0))
+            p.pad_left = 1 if self.padding.get("direction", "right") == "left" else 0
+        p.outputs = outputs
+        return p
+
+    def encode_compact(self, text: np.ndarray, doc_off: np.ndarray, want_offsets: bool = True) -> CompactResult:
+        """tkz_encode_batch_compact with this tokenizer's truncation / padding (what crosses PCIe: kept ids + packed offsets)."""
+        text = np.ascontiguousarray(text, dtype=np.uint8)
+        doc_off = np.ascontiguousarray(doc_off, dtype=np.uint64)
+        r = CompactResult()
+        p = self.params()
+        rc = self._L.tkz_encode_batch_compact(self.context_handle(), text.ctypes.data if text.size else None, doc_off.ctypes.data, len(doc_off) - 1,
+                                              C.byref(p), 1 if want_offsets else 0, C.byref(r))
+        if rc != OK:
+            raise TokzigError(rc, (self._L.tkz_last_error(self.context_handle()) or b"").decode(), int(r.err_doc))
+        return r
 
     def encode_batch(self, docs: Sequence, add_special_tokens: bool = True, outputs: int = OUT_ALL) -> BatchEncoding:
         text, off = pack_docs([d if isinstance(d, (bytes, bytearray)) else d.encode("utf-8") for d in docs])

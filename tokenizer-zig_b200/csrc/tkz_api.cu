@@ -58,7 +58,7 @@ struct tkz_ctx {
     DevBuf a_text, a_doc_off, a_norm_text, a_norm_doc_off, a_chunk, a_tiles, a_word_start, a_word_end, a_word_doc, a_doc_word_off,
         a_word_ntok, a_pool_id, a_pool_s, a_pool_e, a_pool_rk, a_scan_tmp, a_ctrl;
     // output arrays, double-buffered so that the D2H copy of one chunk overlaps the kernels of the next (tkz_encode_batch)
-    struct OutSet { DevBuf doc_tok_off, ids, off, attn, type, special, off16; } outs[2];
+    struct OutSet { DevBuf doc_tok_off, ids, off, attn, type, special, off16, ids16; } outs[2];
     int out_sel = 0;
     OutSet& O() { return outs[out_sel]; }
     DevBuf in_text[2], in_doc_off[2];
@@ -84,7 +84,8 @@ struct tkz_ctx {
     uint64_t tw_uniq_hist = 0;            // most unique words seen in one batch: sizes the next batch's word table
     uint64_t tw_upool_hist = 0;           // most token records used by one batch
     double tw_tok_per_byte = 0.0;         // densest batch so far: sizes the token stream
-    HostBuf h_ctrl, h_doc_tok_off, h_ids, h_off, h_attn, h_type, h_special, h_off16;
+    HostBuf h_ctrl, h_doc_tok_off, h_ids, h_off, h_attn, h_type, h_special, h_off16, h_ids16;
+    bool ids16_ok = false;                // every id the model can emit is below 65536 (TKZ_OUT_IDS_U16)
     // decode direction (tkz_decode.cuh)
     bool has_decode = false;
     DecodeTables dt{};
@@ -282,9 +283,9 @@ extern "C" void tkz_ctx_destroy(tkz_ctx* ctx) {
                       &ctx->a_huge_w, &ctx->a_huge_base, &ctx->a_huge_done, &ctx->a_grid_state, &ctx->a_grid_words,
                       &ctx->t_dec_bytes, &ctx->t_dec_off, &ctx->t_dec_special, &ctx->a_dec_ids, &ctx->a_dec_seq_off, &ctx->a_dec_len, &ctx->a_dec_raw,
                       &ctx->a_dec_out, &ctx->a_dec_olen, &ctx->a_dec_boff};
-    for (auto& os : ctx->outs) for (DevBuf* b : {&os.doc_tok_off, &os.ids, &os.off, &os.attn, &os.type, &os.special, &os.off16}) release(*b);
+    for (auto& os : ctx->outs) for (DevBuf* b : {&os.doc_tok_off, &os.ids, &os.off, &os.attn, &os.type, &os.special, &os.off16, &os.ids16}) release(*b);
     for (DevBuf* b : bufs) release(*b);
-    HostBuf* hb[] = {&ctx->h_ctrl, &ctx->h_doc_tok_off, &ctx->h_ids, &ctx->h_off, &ctx->h_attn, &ctx->h_type, &ctx->h_special, &ctx->h_off16,
+    HostBuf* hb[] = {&ctx->h_ctrl, &ctx->h_doc_tok_off, &ctx->h_ids, &ctx->h_off, &ctx->h_attn, &ctx->h_type, &ctx->h_special, &ctx->h_off16, &ctx->h_ids16,
                      &ctx->h_doc_stage[0], &ctx->h_doc_stage[1], &ctx->h_dec_bytes, &ctx->h_dec_off};
     for (HostBuf* b : hb) release_host(*b);
     if (ctx->s_h2d) cudaStreamDestroy(ctx->s_h2d);
@@ -507,6 +508,12 @@ extern "C" int tkz_model_upload(tkz_ctx* ctx, const tkz_model_desc* d) {
         m.wp_tab = (const WpEnt*)ctx->t_wp_tab.p; m.wp_mask = wcap - 1; m.wp_pool = (const uint8_t*)ctx->t_wp_pool.p;
         m.max_key_first = max_first; m.max_key_cont = max_cont;
     }
+    {
+        uint32_t max_id = d->has_unk ? d->unk_id : 0u;
+        for (uint32_t i = 0; i < d->vocab_n; i++) max_id = std::max(max_id, d->vocab_ids[i]);
+        if (d->model_kind == TKZ_MODEL_BPE) for (uint32_t i = 0; i < d->merges_n; i++) max_id = std::max(max_id, d->merge_new[i]);
+        ctx->ids16_ok = max_id < 65536u;
+    }
     CK(cudaStreamSynchronize(ctx->stream));      // host staging vectors die at return
     ctx->dm = m;
     ctx->dm_post = m;
@@ -654,6 +661,8 @@ void launch_slice_emit(const SliceEmitArgs& ea, const EmitParams& ep, const Emit
     if (o == TKZ_OUT_IDS) slice_emit_kernel<PLAIN, 1u><<<blocks, TW_THREADS, 0, st>>>(ea, ep, eo);
     else if (o == (TKZ_OUT_IDS | TKZ_OUT_OFFSETS | TKZ_OUT_ATTENTION)) slice_emit_kernel<PLAIN, 7u><<<blocks, TW_THREADS, 0, st>>>(ea, ep, eo);
     else if (o == (TKZ_OUT_IDS | TKZ_OUT_OFFSETS_PACKED)) slice_emit_kernel<PLAIN, 33u><<<blocks, TW_THREADS, 0, st>>>(ea, ep, eo);
+    else if (o == (TKZ_OUT_IDS | TKZ_OUT_IDS_U16 | TKZ_OUT_OFFSETS_PACKED)) slice_emit_kernel<PLAIN, 97u><<<blocks, TW_THREADS, 0, st>>>(ea, ep, eo);
+    else if (o == (TKZ_OUT_IDS | TKZ_OUT_IDS_U16)) slice_emit_kernel<PLAIN, 65u><<<blocks, TW_THREADS, 0, st>>>(ea, ep, eo);
     else slice_emit_kernel<PLAIN, 0u><<<blocks, TW_THREADS, 0, st>>>(ea, ep, eo);
 }
 
@@ -794,14 +803,14 @@ int encode_slices(tkz_ctx* ctx, const DevModel& m, const ClassRanges& cr, const 
     CK(cudaEventRecord(ctx->ev[3], st));
 
     // ---- pass B
-    TRY(ensure(ctx, ctx->O().ids, (T + 4) * 4));
+    if (P.outputs & TKZ_OUT_IDS_U16) TRY(ensure(ctx, ctx->O().ids16, (T + 4) * 2)); else TRY(ensure(ctx, ctx->O().ids, (T + 4) * 4));
     if (P.outputs & TKZ_OUT_OFFSETS) TRY(ensure(ctx, ctx->O().off, (T + 4) * 8));
     if (P.outputs & TKZ_OUT_ATTENTION) TRY(ensure(ctx, ctx->O().attn, (T + 4) * 4));
     if (P.outputs & TKZ_OUT_TYPE_IDS) TRY(ensure(ctx, ctx->O().type, (T + 4) * 4));
     if (P.outputs & TKZ_OUT_SPECIAL) TRY(ensure(ctx, ctx->O().special, (T + 4) * 4));
     if (P.outputs & TKZ_OUT_OFFSETS_PACKED) TRY(ensure(ctx, ctx->O().off16, (T + 4) * 2));
     EmitOut eo{(uint32_t*)ctx->O().ids.p, (uint32_t*)ctx->O().off.p, (uint32_t*)ctx->O().attn.p, (uint32_t*)ctx->O().type.p,
-               (uint32_t*)ctx->O().special.p, (uint16_t*)ctx->O().off16.p};
+               (uint32_t*)ctx->O().special.p, (uint16_t*)ctx->O().off16.p, (uint16_t*)ctx->O().ids16.p};
     const uint32_t big_cap = (uint32_t)(N / EMIT_BIG + 16);
     TRY(ensure(ctx, ctx->a_big, (size_t)big_cap * sizeof(uint4)));
     SliceEmitArgs ea{};
@@ -836,7 +845,8 @@ int encode_slices(tkz_ctx* ctx, const DevModel& m, const ClassRanges& cr, const 
     cudaEventElapsedTime(&ctx->stats.ms_total, ctx->ev[0], ctx->ev[4]);
     out->n_docs = n_docs; out->n_tokens = T; out->n_real_tokens = T_real;
     out->doc_tok_off = (const uint64_t*)doc_tok_off;
-    out->ids = eo.ids;
+    out->ids = (P.outputs & TKZ_OUT_IDS_U16) ? nullptr : eo.ids;
+    out->ids16 = (P.outputs & TKZ_OUT_IDS_U16) ? eo.ids16 : nullptr;
     out->offsets = (P.outputs & TKZ_OUT_OFFSETS) ? eo.offsets : nullptr;
     out->attention_mask = (P.outputs & TKZ_OUT_ATTENTION) ? eo.attention : nullptr;
     out->type_ids = (P.outputs & TKZ_OUT_TYPE_IDS) ? eo.type_ids : nullptr;
@@ -860,6 +870,7 @@ int encode_device_impl(tkz_ctx* ctx, const uint8_t* d_text, const uint64_t* d_do
     if (params) P = *params;
     if (P.outputs == 0) P.outputs = TKZ_OUT_ALL;
     P.outputs |= TKZ_OUT_IDS;
+    if ((P.outputs & TKZ_OUT_IDS_U16) && (!ctx->ids16_ok || (P.has_padding && P.pad_id > 0xFFFFu))) P.outputs &= ~TKZ_OUT_IDS_U16;
     const uint32_t nd = (uint32_t)n_docs;
     DevModel m = ctx->dm;
 
@@ -992,13 +1003,13 @@ int encode_device_impl(tkz_ctx* ctx, const uint8_t* d_text, const uint64_t* d_do
 
     CK(cudaEventRecord(ctx->ev[3], st));
     // ---- K5: emit
-    TRY(ensure(ctx, ctx->O().ids, T * 4));
+    if (P.outputs & TKZ_OUT_IDS_U16) TRY(ensure(ctx, ctx->O().ids16, T * 2)); else TRY(ensure(ctx, ctx->O().ids, T * 4));
     if (P.outputs & TKZ_OUT_OFFSETS) TRY(ensure(ctx, ctx->O().off, T * 8));
     if (P.outputs & TKZ_OUT_ATTENTION) TRY(ensure(ctx, ctx->O().attn, T * 4));
     if (P.outputs & TKZ_OUT_TYPE_IDS) TRY(ensure(ctx, ctx->O().type, T * 4));
     if (P.outputs & TKZ_OUT_SPECIAL) TRY(ensure(ctx, ctx->O().special, T * 4));
     EmitOut eo{(uint32_t*)ctx->O().ids.p, (uint32_t*)ctx->O().off.p, (uint32_t*)ctx->O().attn.p, (uint32_t*)ctx->O().type.p,
-               (uint32_t*)ctx->O().special.p, nullptr};
+               (uint32_t*)ctx->O().special.p, nullptr, (uint16_t*)ctx->O().ids16.p};
     if (nw) {
         const uint32_t big_cap = (uint32_t)(N / EMIT_BIG + 16);
         TRY(ensure(ctx, ctx->a_big, (size_t)big_cap * sizeof(uint4)));
@@ -1023,7 +1034,8 @@ int encode_device_impl(tkz_ctx* ctx, const uint8_t* d_text, const uint64_t* d_do
     cudaEventElapsedTime(&ctx->stats.ms_total, ctx->ev[0], ctx->ev[4]);
     out->n_docs = n_docs; out->n_tokens = T; out->n_real_tokens = T_real;
     out->doc_tok_off = (const uint64_t*)doc_tok_off;
-    out->ids = eo.ids;
+    out->ids = (P.outputs & TKZ_OUT_IDS_U16) ? nullptr : eo.ids;
+    out->ids16 = (P.outputs & TKZ_OUT_IDS_U16) ? eo.ids16 : nullptr;
     out->offsets = (P.outputs & TKZ_OUT_OFFSETS) ? eo.offsets : nullptr;
     out->attention_mask = (P.outputs & TKZ_OUT_ATTENTION) ? eo.attention : nullptr;
     out->type_ids = (P.outputs & TKZ_OUT_TYPE_IDS) ? eo.type_ids : nullptr;
@@ -1068,7 +1080,7 @@ int encode_host_single(tkz_ctx* ctx, const uint8_t* text, const uint64_t* doc_of
     int rc = encode_device_impl(ctx, (const uint8_t*)ctx->a_text.p, (const uint64_t*)ctx->a_doc_off.p, n_docs, N, params, &dev);
     *out = dev;
     out->doc_tok_off = nullptr; out->ids = nullptr; out->offsets = nullptr; out->attention_mask = nullptr; out->type_ids = nullptr;
-    out->special_tokens_mask = nullptr; out->offsets_packed = nullptr;
+    out->special_tokens_mask = nullptr; out->offsets_packed = nullptr; out->ids16 = nullptr;
     if (rc != TKZ_OK) return rc;
     const uint64_t T = dev.n_tokens;
     cudaStream_t st = ctx->stream;
@@ -1079,7 +1091,7 @@ int encode_host_single(tkz_ctx* ctx, const uint8_t* text, const uint64_t* doc_of
         {dev.ids, &ctx->h_ids, (const void**)&out->ids, 4}, {dev.offsets, &ctx->h_off, (const void**)&out->offsets, 8},
         {dev.attention_mask, &ctx->h_attn, (const void**)&out->attention_mask, 4}, {dev.type_ids, &ctx->h_type, (const void**)&out->type_ids, 4},
         {dev.special_tokens_mask, &ctx->h_special, (const void**)&out->special_tokens_mask, 4},
-        {dev.offsets_packed, &ctx->h_off16, (const void**)&out->offsets_packed, 2}};
+        {dev.offsets_packed, &ctx->h_off16, (const void**)&out->offsets_packed, 2}, {dev.ids16, &ctx->h_ids16, (const void**)&out->ids16, 2}};
     for (auto& c : cp) {
         if (!c.src) continue;
         TRY(ensure_host(ctx, *c.hb, T * c.elem));
@@ -1126,6 +1138,7 @@ int encode_host_chunked(tkz_ctx* ctx, const uint8_t* text, const uint64_t* doc_o
         CK(cudaEventRecord(ctx->ev_h2d[b], ctx->s_h2d));
         return TKZ_OK;
     };
+    bool used_ids16 = false;
 restart:
     TRY(stage_in(0));
     uint64_t T_total = 0, T_real = 0;
@@ -1155,6 +1168,7 @@ restart:
             P.outputs = (P.outputs & ~TKZ_OUT_OFFSETS_PACKED) | TKZ_OUT_OFFSETS;
             goto restart;
         }
+        used_ids16 = dev.ids16 != nullptr;                      // (the same decision in every chunk: it depends on the model and the parameters)
         const uint64_t T = dev.n_tokens;
         tok_base[i] = T_total;
         // size the host arrays from the first chunk's token density
@@ -1163,7 +1177,8 @@ restart:
         if (est < T_total + T) est = T_total + T;
         struct { const void* src; HostBuf* hb; size_t elem; } cp[] = {
             {dev.ids, &ctx->h_ids, 4}, {dev.offsets, &ctx->h_off, 8}, {dev.attention_mask, &ctx->h_attn, 4},
-            {dev.type_ids, &ctx->h_type, 4}, {dev.special_tokens_mask, &ctx->h_special, 4}, {dev.offsets_packed, &ctx->h_off16, 2}};
+            {dev.type_ids, &ctx->h_type, 4}, {dev.special_tokens_mask, &ctx->h_special, 4}, {dev.offsets_packed, &ctx->h_off16, 2},
+            {dev.ids16, &ctx->h_ids16, 2}};
         for (auto& c : cp) {
             if (!c.src) continue;
             TRY(ensure_host_keep(ctx, *c.hb, est * c.elem, T_total * c.elem));
@@ -1180,10 +1195,12 @@ restart:
     for (size_t i = 1; i < nc; i++) { const uint64_t base = tok_base[i]; for (uint64_t d = cb[i]; d < cb[i + 1]; d++) h_dto[d] += base; }
     h_dto[n_docs] = T_total;
     ctx->out_sel = 0;
-    const uint32_t outputs = P.outputs;
+    uint32_t outputs = P.outputs;
+    if ((outputs & TKZ_OUT_IDS_U16) && !used_ids16) outputs &= ~TKZ_OUT_IDS_U16;
     out->n_docs = n_docs; out->n_tokens = T_total; out->n_real_tokens = T_real;
     out->doc_tok_off = h_dto;
-    out->ids = (const uint32_t*)ctx->h_ids.p;
+    out->ids = (outputs & TKZ_OUT_IDS_U16) ? nullptr : (const uint32_t*)ctx->h_ids.p;
+    out->ids16 = (outputs & TKZ_OUT_IDS_U16) ? (const uint16_t*)ctx->h_ids16.p : nullptr;
     out->offsets = (outputs & TKZ_OUT_OFFSETS) ? (const uint32_t*)ctx->h_off.p : nullptr;
     out->attention_mask = (outputs & TKZ_OUT_ATTENTION) ? (const uint32_t*)ctx->h_attn.p : nullptr;
     out->type_ids = (outputs & TKZ_OUT_TYPE_IDS) ? (const uint32_t*)ctx->h_type.p : nullptr;
@@ -1203,6 +1220,70 @@ extern "C" int tkz_encode_batch(tkz_ctx* ctx, const uint8_t* text, const uint64_
     CK(cudaSetDevice(ctx->device));
     if (n_docs >= 2 && N > ctx->chunk_bytes + ctx->chunk_bytes / 2) return encode_host_chunked(ctx, text, doc_off, n_docs, N, params, out);
     return encode_host_single(ctx, text, doc_off, n_docs, N, params, out);
+}
+
+// ------------------------------------------------------------------------------------------------ compact result
+extern "C" int tkz_encode_batch_compact(tkz_ctx* ctx, const uint8_t* text, const uint64_t* doc_off, uint64_t n_docs,
+                                        const tkz_encode_params* params, int want_offsets, tkz_compact_result* out) {
+    if (!ctx || !out) return TKZ_ERR_INVALID_ARG;
+    memset(out, 0, sizeof *out);
+    out->err_doc = -1;
+    tkz_encode_params P{};
+    if (params) P = *params;
+    out->params = P;
+    // on the device: truncation only; no padding slot and no constant array is materialised or copied
+    tkz_encode_params Q = P;
+    Q.has_padding = 0;
+    Q.outputs = TKZ_OUT_IDS | TKZ_OUT_IDS_U16 | (want_offsets ? TKZ_OUT_OFFSETS_PACKED : 0u);
+    tkz_batch_result r{};
+    const int rc = tkz_encode_batch(ctx, text, doc_off, n_docs, &Q, &r);
+    out->err_doc = r.err_doc;
+    if (rc != TKZ_OK) return rc;
+    out->n_docs = r.n_docs; out->n_kept = r.n_tokens; out->n_real_tokens = r.n_real_tokens;
+    out->doc_kept_off = r.doc_tok_off; out->ids = r.ids; out->ids16 = r.ids16;
+    out->offsets_packed = r.offsets_packed; out->offsets = r.offsets;
+    return TKZ_OK;
+}
+
+extern "C" uint64_t tkz_compact_slots(const tkz_compact_result* r, uint64_t d0, uint64_t d1) {
+    if (!r || d1 > r->n_docs || d0 > d1) return 0;
+    const tkz_encode_params& P = r->params;
+    if (!P.has_padding) return r->doc_kept_off[d1] - r->doc_kept_off[d0];
+    uint64_t n = 0;
+    for (uint64_t d = d0; d < d1; d++) { const uint64_t k = r->doc_kept_off[d + 1] - r->doc_kept_off[d]; n += k < P.pad_length ? P.pad_length : k; }
+    return n;
+}
+
+// Encoding.fromTokens (ids, type_ids 0, offsets, special_tokens_mask 0, attention_mask 1: src/encoding.zig:246-294) followed by
+// Encoding.pad (pad_id / pad_type_id / (0,0) / special 1 / attention 0, left or right: src/encoding.zig:385-463)
+extern "C" int tkz_compact_expand(const tkz_compact_result* r, uint64_t d0, uint64_t d1, uint64_t* doc_tok_off, uint32_t* ids, uint32_t* offsets,
+                                  uint32_t* attention_mask, uint32_t* type_ids, uint32_t* special_tokens_mask) {
+    if (!r || d1 > r->n_docs || d0 > d1) return TKZ_ERR_INVALID_ARG;
+    const tkz_encode_params& P = r->params;
+    uint64_t o = 0;
+    for (uint64_t d = d0; d < d1; d++) {
+        const uint64_t k0 = r->doc_kept_off[d], k = r->doc_kept_off[d + 1] - k0;
+        const uint64_t olen = (P.has_padding && k < P.pad_length) ? P.pad_length : k, npad = olen - k;
+        const uint64_t real0 = o + ((P.has_padding && P.pad_left) ? npad : 0), pad0 = (P.has_padding && P.pad_left) ? o : o + k;
+        if (doc_tok_off) doc_tok_off[d - d0] = o;
+        if (ids) {
+            if (r->ids16) for (uint64_t i = 0; i < k; i++) ids[real0 + i] = r->ids16[k0 + i];
+            else memcpy(ids + real0, r->ids + k0, k * 4);
+            for (uint64_t i = 0; i < npad; i++) ids[pad0 + i] = P.pad_id;
+        }
+        if (offsets) {
+            if (r->offsets_packed) for (uint64_t i = 0; i < k; i++) { const uint32_t v = r->offsets_packed[k0 + i]; offsets[2 * (real0 + i)] = v & 0xFFu; offsets[2 * (real0 + i) + 1] = v >> 8; }
+            else if (r->offsets) memcpy(offsets + 2 * real0, r->offsets + 2 * k0, k * 8);
+            else return TKZ_ERR_INVALID_ARG;
+            memset(offsets + 2 * pad0, 0, npad * 8);
+        }
+        if (attention_mask) { for (uint64_t i = 0; i < k; i++) attention_mask[real0 + i] = 1u; memset(attention_mask + pad0, 0, npad * 4); }
+        if (type_ids) { memset(type_ids + real0, 0, k * 4); for (uint64_t i = 0; i < npad; i++) type_ids[pad0 + i] = P.pad_type_id; }
+        if (special_tokens_mask) { memset(special_tokens_mask + real0, 0, k * 4); for (uint64_t i = 0; i < npad; i++) special_tokens_mask[pad0 + i] = 1u; }
+        o += olen;
+    }
+    if (doc_tok_off) doc_tok_off[d1 - d0] = o;
+    return TKZ_OK;
 }
 
 // ------------------------------------------------------------------------------------------------ decode

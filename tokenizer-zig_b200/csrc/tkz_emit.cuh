@@ -36,7 +36,8 @@ __global__ void doc_len_kernel(EmitParams p, const uint32_t* __restrict__ word_t
 }
 
 struct EmitOut { uint32_t* ids; uint32_t* offsets; uint32_t* attention; uint32_t* type_ids; uint32_t* special;
-                 uint16_t* offsets16; };     // offsets16: one u16 per token (start | end << 8), only when every pre-token is < 256 bytes
+                 uint16_t* offsets16;        // one u16 per token (start | end << 8), only when every pre-token is < 256 bytes
+                 uint16_t* ids16; };         // ids as u16 instead of `ids` (outputs & 64: every id of the vocabulary is < 65536)
 
 // words with more than EMIT_BIG tokens (whole documents, MiB-long unbroken words) are not copied by one warp: they are
 // queued here and copied by the whole grid (emit_big_kernel)
@@ -49,8 +50,11 @@ __device__ __forceinline__ bool big_push(const BigList& b, uint32_t src, uint32_
     return true;
 }
 
+__device__ __forceinline__ void emit_id(const EmitParams& p, const EmitOut& o, unsigned long long dst, uint32_t id) {
+    if (p.outputs & 64u) o.ids16[dst] = (uint16_t)id; else o.ids[dst] = id;
+}
 __device__ __forceinline__ void emit_real(const EmitParams& p, const EmitOut& o, unsigned long long dst, uint32_t id, uint32_t s, uint32_t e) {
-    o.ids[dst] = id;
+    emit_id(p, o, dst, id);
     if (p.outputs & 2u) reinterpret_cast<uint2*>(o.offsets)[dst] = make_uint2(s, e);
     if (p.outputs & 4u) o.attention[dst] = 1u;
     if (p.outputs & 8u) o.type_ids[dst] = 0u;
@@ -127,7 +131,7 @@ __global__ void __launch_bounds__(256) emit_pad_kernel(EmitParams p, EmitOut o, 
     const unsigned long long npad = olen - kept;
     for (unsigned long long k = lane; k < npad; k += 32) {
         const unsigned long long dst = base + k;
-        o.ids[dst] = p.pad_id;
+        emit_id(p, o, dst, p.pad_id);
         if (p.outputs & 2u) reinterpret_cast<uint2*>(o.offsets)[dst] = make_uint2(0u, 0u);
         if (p.outputs & 4u) o.attention[dst] = 0u;
         if (p.outputs & 8u) o.type_ids[dst] = p.pad_type_id;

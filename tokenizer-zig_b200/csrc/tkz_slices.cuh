@@ -1016,7 +1016,7 @@ struct SliceEmitArgs {
 template <uint32_t OUTS>
 __device__ __forceinline__ void te_put(const EmitParams& p, const EmitOut& o, unsigned long long dst, uint32_t id, uint32_t of) {
     const uint32_t outputs = OUTS ? OUTS : p.outputs;
-    o.ids[dst] = id;
+    if (outputs & 64u) o.ids16[dst] = (uint16_t)id; else o.ids[dst] = id;
     if (outputs & 2u) reinterpret_cast<uint2*>(o.offsets)[dst] = make_uint2(of & 0xFFu, of >> 8);
     if (outputs & 4u) o.attention[dst] = 1u;
     if (outputs & 8u) o.type_ids[dst] = 0u;
@@ -1184,7 +1184,8 @@ __global__ void __launch_bounds__(256) emit_pad_real_kernel(EmitParams p, EmitOu
     if (olen == kept) return;
     const unsigned long long base = doc_tok_off[d] + (p.pad_left ? 0 : kept);
     const unsigned long long npad = olen - kept;
-    warp_fill_u32(o.ids + base, npad, p.pad_id);
+    if (p.outputs & 64u) { uint16_t* q = o.ids16 + base; for (unsigned long long i = lane_id(); i < npad; i += 32) q[i] = (uint16_t)p.pad_id; }
+    else warp_fill_u32(o.ids + base, npad, p.pad_id);
     if (p.outputs & 2u) warp_fill_u32(o.offsets + 2 * base, 2 * npad, 0u);
     if (p.outputs & 4u) warp_fill_u32(o.attention + base, npad, 0u);
     if (p.outputs & 8u) warp_fill_u32(o.type_ids + base, npad, p.pad_type_id);
