@@ -159,6 +159,7 @@ int tkz_ctx_create(int device, void* stream, uint64_t arena_hint_bytes, tkz_ctx*
 void tkz_ctx_destroy(tkz_ctx* ctx);
 const char* tkz_last_error(tkz_ctx* ctx);           /* NULL ctx: last error of a failed tkz_ctx_create */
 int tkz_ctx_get_stats(tkz_ctx* ctx, tkz_stats* out);
+int tkz_ctx_numa_node(tkz_ctx* ctx);                /* NUMA node of the context's GPU (sysfs), -1 if unknown */
 
 /* replaces BPE.init / WordPiece.init table construction (src/model/bpe.zig:84-110, src/model/wordpiece.zig:51-74) */
 int tkz_model_upload(tkz_ctx* ctx, const tkz_model_desc* desc);
@@ -199,6 +200,32 @@ int tkz_compact_expand(const tkz_compact_result* r, uint64_t d0, uint64_t d1, ui
  * values).  All work is enqueued on the context's stream; the call returns after the stream has drained. */
 int tkz_encode_batch_device(tkz_ctx* ctx, const void* d_text, const void* d_doc_off, uint64_t n_docs,
                             uint64_t text_bytes, const tkz_encode_params* params, tkz_batch_result* out);
+
+/* ------------------------------------------------------------------ several GPUs of one box
+ * N contexts on N GPUs, one host thread per GPU; documents are cut into N contiguous shards with NO collective on the data
+ * path (they are independent); model tables are replicated.  Closest reference analogue: the per-thread arena pool,
+ * src/arena.zig:252-335.  Every entry point below leaves the caller's current CUDA device unchanged. */
+typedef struct tkzm_pool tkzm_pool;
+int tkzm_create(const int32_t* devices, int32_t n, tkzm_pool** out);         /* devices[i] = CUDA ordinal of shard i's GPU */
+void tkzm_destroy(tkzm_pool* pool);
+int32_t tkzm_size(tkzm_pool* pool);
+tkz_ctx* tkzm_ctx(tkzm_pool* pool, int32_t i);
+const char* tkzm_last_error(tkzm_pool* pool);
+int tkzm_model_upload(tkzm_pool* pool, const tkz_model_desc* desc);          /* the same tables on every GPU */
+/* shard k = documents [bounds[k], bounds[k+1]), cut at the document boundary nearest to k / n_shards of the total of the
+ * measure: bytes when cost is NULL ("byte-balanced ranges"), else cost[d] per document.  bounds has n_shards + 1 entries. */
+int tkzm_shard_bounds(const uint64_t* doc_off, uint64_t n_docs, int32_t n_shards, const double* cost, uint64_t* bounds);
+/* modelled encode cost per document in units of "one byte of ordinary text": its bytes, with the bytes inside pre-tokens of
+ * 65..12288 bytes counted 20x and inside longer ones 36x (the measured per-byte times of the long-word kernels).
+ * raw_class[256] = TKZ_CLS_* of every RAW byte, NULL = no pre-tokenizer.  One pass over the text on `threads` host threads
+ * (0 = all).  For corpora with skewed document and word lengths (BASELINE config 5). */
+int tkzm_document_costs(const uint8_t* text, const uint64_t* doc_off, uint64_t n_docs, const uint8_t* raw_class, int32_t threads, double* cost);
+/* The batch over all GPUs of the pool: cuts it (by bytes, or by tkzm_document_costs when cost_balanced), runs one
+ * tkz_encode_batch_compact per shard concurrently, and returns the cut (bounds[n + 1]) and the n compact results (arrays owned
+ * by the shard's context; err_doc is a document index of the whole batch).  shard_ms (n entries, may be NULL) = wall time of
+ * every shard's call. */
+int tkzm_encode_batch_compact(tkzm_pool* pool, const uint8_t* text, const uint64_t* doc_off, uint64_t n_docs, const tkz_encode_params* params,
+                              int want_offsets, int cost_balanced, uint64_t* bounds, tkz_compact_result* results, double* shard_ms);
 
 /* ------------------------------------------------------------------ decode (the inverse direction) */
 /* Tables of Tokenizer.decode (src/lib.zig:163-189): token strings come from the MODEL vocabulary by id

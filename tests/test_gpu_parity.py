@@ -898,3 +898,38 @@ def test_packed_formats_fall_back_when_they_cannot_hold_the_values(monkeypatch):
     assert r.offsets and not r.offsets_packed
     assert_same(tz.expand_compact(r), o4.encode_batch(docs))
     t4.close()
+
+
+# ----------------------------------------------------------------------------- several contexts, one host thread each (tkzm_*)
+@pytest.mark.parametrize("cost_balanced", [False, True])
+def test_multi_context_pool_matches_the_oracle(cost_balanced):
+    """tkzm_encode_batch_compact: the batch cut into shards (by bytes / by the cost model), one context and one host thread
+    per shard running concurrently (here: three contexts on the same GPU), shard results expanded and concatenated in
+    document order == the oracle; the caller's current device is left alone; errors carry the batch-wide document index."""
+    import torch
+    text, off = corpus.generate("c5", 12 << 20, seed=5)
+    for name, trunc, pad in (("gpt2_whitespace", None, None), ("bert_wordpiece", 16, {"length": 24, "pad_id": 0, "direction": "left"})):
+        js = tokenizers_io.tokenizer_json(name)
+        cfg = tz.Tokenizer.from_json(js, device=None)
+        cfg.truncation = None if trunc is None else {"max_length": trunc}
+        cfg.padding = pad
+        o = orc.OracleTokenizer.from_json(js)
+        o.truncation = trunc; o.padding = pad
+        pool = tz.MultiPool(cfg, [0, 0, 0])
+        before = torch.cuda.current_device()
+        got = pool.encode_expanded(text, off, cost_balanced=cost_balanced)
+        assert torch.cuda.current_device() == before
+        assert_same(got, o.encode_packed(text, off, algo=1, threads=8), f"{name} cost_balanced={cost_balanced}")
+        bounds, results, ms = pool.encode_compact(text, off, cost_balanced=cost_balanced)
+        assert bounds[0] == 0 and bounds[-1] == len(off) - 1 and np.all(np.diff(bounds.astype(np.int64)) >= 0) and np.all(ms > 0)
+        pool.close(); cfg.close()
+    # error in the last shard: document index of the whole batch
+    js = json.dumps({"model": {"type": "BPE", "vocab": {"a": 0, "b": 1, "ab": 2}, "merges": ["a b"]}, "pre_tokenizer": {"type": "Whitespace"}})
+    cfg = tz.Tokenizer.from_json(js, device=None)
+    pool = tz.MultiPool(cfg, [0, 0])
+    docs = [b"ab ab"] * 50 + [b"ab \xffab"] + [b"ab"] * 3
+    t_, o_ = tz.pack_docs(docs)
+    with pytest.raises(tz.TokzigError) as e:
+        pool.encode_compact(t_, o_)
+    assert e.value.code == tz.ERR_INVALID_UTF8 and e.value.doc == 50
+    pool.close(); cfg.close()

@@ -116,3 +116,29 @@ def test_two_rank_gloo_sharded_encode_matches_single():
         p.join(180)
         assert p.exitcode == 0
     assert q.get(timeout=10) is True
+
+
+def test_c_shard_cut_and_cost_model_equal_the_numpy_statement():
+    """tkzm_shard_bounds / tkzm_document_costs (the product's multi-GPU cut, C++) against the numpy statements above: random
+    documents incl. empty ones, long words across the 64 / 12288-byte thresholds, with and without a pre-tokenizer."""
+    import tokzig_b200 as tz
+    rng = np.random.default_rng(5)
+    for trial in range(6):
+        nd = int(rng.integers(1, 4000))
+        lens = rng.integers(0, 200, nd).astype(np.uint64)
+        lens[rng.random(nd) < 0.05] = 0
+        big = rng.random(nd) < 0.01
+        lens[big] = rng.integers(1000, 40000, int(big.sum()))
+        off = np.zeros(nd + 1, np.uint64); np.cumsum(lens, out=off[1:])
+        text = rng.choice(np.frombuffer(b"abcdefghij \n\t\r", np.uint8), int(off[-1]), p=[0.09] * 10 + [0.07, 0.01, 0.01, 0.01]).astype(np.uint8)
+        for d in np.flatnonzero(big)[::2]:                      # unbroken runs inside some long documents
+            a, b = int(off[d]), int(off[d + 1])
+            text[a + 10: b - 10] = ord("x")
+        raw_class = np.zeros(256, np.uint8); raw_class[list(b" \t\n\r")] = 1
+        for rc_, delim in ((raw_class, b" \t\n\r"), (None, b"")):
+            ref = tz.document_costs(text, off, delimiters=delim)
+            got = tz.document_costs_c(text, off, rc_, threads=[0, 1, 3][trial % 3])
+            assert np.allclose(got, ref), f"trial {trial} delim {delim!r}"
+            for n in (1, 2, 3, 8):
+                assert np.array_equal(tz.shard_bounds_c(off, n), tz.shard_bounds(off, n))
+                assert np.array_equal(tz.shard_bounds_c(off, n, got), tz.shard_bounds(off, n, ref))

@@ -127,6 +127,8 @@ class Stats(C.Structure):
 # every symbol include/tokzig_b200.h declares (checked by tests/test_cabi_symbols.py)
 EXPORTED_SYMBOLS = [
     "tkz_ctx_create", "tkz_ctx_destroy", "tkz_last_error", "tkz_ctx_get_stats", "tkz_model_upload", "tkz_encode_batch",
+    "tkz_ctx_numa_node", "tkzm_create", "tkzm_destroy", "tkzm_size", "tkzm_ctx", "tkzm_last_error", "tkzm_model_upload", "tkzm_shard_bounds",
+    "tkzm_document_costs", "tkzm_encode_batch_compact",
     "tkz_encode_batch_device", "tkz_encode_batch_compact", "tkz_compact_slots", "tkz_compact_expand", "tkz_decode_upload", "tkz_decode_batch",
     "tkzh_from_json", "tkzh_from_file", "tkzh_free", "tkzh_last_error", "tkzh_ctx", "tkzh_set_truncation", "tkzh_set_padding",
     "tkzh_set_normalizer", "tkzh_set_pretokenizer", "tkzh_encode_batch", "tkzh_decode", "tkzh_decode_batch", "tkzh_get_vocab_size", "tkzh_token_to_id",
@@ -159,6 +161,19 @@ def lib():
     L.tkz_compact_slots.argtypes = [C.POINTER(CompactResult), u64, u64]
     L.tkz_compact_slots.restype = u64
     L.tkz_compact_expand.argtypes = [C.POINTER(CompactResult), u64, u64, vp, vp, vp, vp, vp, vp]
+    L.tkz_ctx_numa_node.argtypes = [vp]
+    L.tkzm_create.argtypes = [vp, C.c_int32, C.POINTER(vp)]
+    L.tkzm_destroy.argtypes = [vp]
+    L.tkzm_size.argtypes = [vp]
+    L.tkzm_size.restype = C.c_int32
+    L.tkzm_ctx.argtypes = [vp, C.c_int32]
+    L.tkzm_ctx.restype = vp
+    L.tkzm_last_error.argtypes = [vp]
+    L.tkzm_last_error.restype = C.c_char_p
+    L.tkzm_model_upload.argtypes = [vp, C.POINTER(ModelDesc)]
+    L.tkzm_shard_bounds.argtypes = [vp, u64, C.c_int32, vp, vp]
+    L.tkzm_document_costs.argtypes = [vp, vp, u64, vp, C.c_int32, vp]
+    L.tkzm_encode_batch_compact.argtypes = [vp, vp, vp, u64, C.POINTER(EncodeParams), i32, i32, vp, vp, vp]
     L.tkzh_from_json.argtypes = [C.c_char_p, u64, i32, vp, C.POINTER(vp)]
     L.tkzh_from_file.argtypes = [C.c_char_p, i32, vp, C.POINTER(vp)]
     L.tkzh_free.argtypes = [vp]
@@ -589,6 +604,89 @@ class Tokenizer:
         s = Stats()
         self._L.tkz_ctx_get_stats(self.context_handle(), C.byref(s))
         return s
+
+
+# --------------------------------------------------------------------------- several GPUs of one box (tkzm_*)
+class MultiPool:
+    """tkzm_pool: one context per entry of `devices` (a GPU may be named more than once), one host thread per context; the model
+    of `tokenizer` (a Tokenizer loaded with device=None is enough) is replicated on all of them."""
+
+    def __init__(self, tokenizer: "Tokenizer", devices: Sequence[int]):
+        self._L = lib()
+        dv = np.asarray(list(devices), dtype=np.int32)
+        h = C.c_void_p()
+        rc = self._L.tkzm_create(dv.ctypes.data, len(dv), C.byref(h))
+        if rc != OK:
+            raise TokzigError(rc, (self._L.tkz_last_error(None) or b"").decode())
+        self._h = h
+        self.n = len(dv)
+        self.tokenizer = tokenizer
+        d = ModelDesc()
+        self._L.tkzh_model_desc(tokenizer._h, C.byref(d))
+        rc = self._L.tkzm_model_upload(self._h, C.byref(d))
+        if rc != OK:
+            msg = (self._L.tkzm_last_error(self._h) or b"").decode()
+            self.close()
+            raise TokzigError(rc, msg)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.tkzm_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def encode_compact(self, text: np.ndarray, doc_off: np.ndarray, want_offsets: bool = True, cost_balanced: bool = False):
+        """tkzm_encode_batch_compact with the tokenizer's truncation / padding: (bounds, [CompactResult per shard], shard_ms)."""
+        text = np.ascontiguousarray(text, dtype=np.uint8)
+        doc_off = np.ascontiguousarray(doc_off, dtype=np.uint64)
+        bounds = np.zeros(self.n + 1, np.uint64)
+        results = (CompactResult * self.n)()
+        ms = np.zeros(self.n, np.float64)
+        p = self.tokenizer.params()
+        rc = self._L.tkzm_encode_batch_compact(self._h, text.ctypes.data if text.size else None, doc_off.ctypes.data, len(doc_off) - 1, C.byref(p),
+                                               1 if want_offsets else 0, 1 if cost_balanced else 0, bounds.ctypes.data, C.cast(results, C.c_void_p), ms.ctypes.data)
+        if rc != OK:
+            docs = [int(r.err_doc) for r in results if int(r.err_doc) >= 0]
+            raise TokzigError(rc, (self._L.tkzm_last_error(self._h) or b"").decode(), min(docs) if docs else -1)
+        return bounds, list(results), ms
+
+    def encode_expanded(self, text, doc_off, cost_balanced: bool = False) -> BatchEncoding:
+        """the whole batch as one BatchEncoding (verification: results are gathered to the host in document order)"""
+        bounds, results, _ = self.encode_compact(text, doc_off, True, cost_balanced)
+        parts = [expand_compact(r) for r in results]
+        base = np.cumsum([0] + [int(p.doc_tok_off[-1]) for p in parts])
+        off = np.concatenate([p.doc_tok_off[:-1] + np.uint64(b) for p, b in zip(parts, base)] + [np.array([base[-1]], np.uint64)])
+        cat = lambda f: np.concatenate([getattr(p, f) for p in parts])
+        return BatchEncoding(off.astype(np.uint64), cat("ids"), np.concatenate([p.offsets for p in parts]), cat("attention_mask"), cat("type_ids"),
+                             cat("special_tokens_mask"), sum(p.n_real_tokens for p in parts))
+
+
+def shard_bounds_c(doc_off: np.ndarray, n_shards: int, cost: np.ndarray = None) -> np.ndarray:
+    """tkzm_shard_bounds (the product's cut; `shard_bounds` below is the numpy statement of the same rule)"""
+    doc_off = np.ascontiguousarray(doc_off, dtype=np.uint64)
+    b = np.zeros(n_shards + 1, np.uint64)
+    c = None if cost is None else np.ascontiguousarray(cost, dtype=np.float64)
+    rc = lib().tkzm_shard_bounds(doc_off.ctypes.data, len(doc_off) - 1, n_shards, None if c is None else c.ctypes.data, b.ctypes.data)
+    if rc != OK:
+        raise TokzigError(rc)
+    return b.astype(np.int64)
+
+
+def document_costs_c(text: np.ndarray, doc_off: np.ndarray, raw_class: Optional[np.ndarray], threads: int = 0) -> np.ndarray:
+    """tkzm_document_costs; raw_class = 256 x TKZ_CLS_* (None: no pre-tokenizer)"""
+    text = np.ascontiguousarray(text, dtype=np.uint8)
+    doc_off = np.ascontiguousarray(doc_off, dtype=np.uint64)
+    out = np.zeros(len(doc_off) - 1, np.float64)
+    rcl = None if raw_class is None else np.ascontiguousarray(raw_class, dtype=np.uint8)
+    rc = lib().tkzm_document_costs(text.ctypes.data if text.size else None, doc_off.ctypes.data, len(doc_off) - 1, None if rcl is None else rcl.ctypes.data, threads, out.ctypes.data)
+    if rc != OK:
+        raise TokzigError(rc)
+    return out
 
 
 # --------------------------------------------------------------------------- multi-GPU sharding (host logic, no collective)

@@ -14,7 +14,7 @@ NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 
 CU_SRCS = [os.path.join(HERE, "csrc", "tkz_api.cu")]
-CXX_SRCS = [os.path.join(HERE, "host", "tokzig_host.cpp")]
+CXX_SRCS = [os.path.join(HERE, "host", "tokzig_host.cpp"), os.path.join(HERE, "host", "tokzig_multi.cpp")]
 
 
 def _deps():
@@ -47,7 +47,7 @@ def build(force=False, verbose=False):
         objs.append(obj)
     for src in CXX_SRCS:
         obj = os.path.join(LIB_DIR, os.path.basename(src) + ".o")
-        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-Wall", "-c", src, "-o", obj])
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-Wall", "-pthread", "-c", src, "-o", obj])
         objs.append(obj)
     # the CUDA runtime is linked dynamically (the image and torch both ship libcudart.so.12): nothing of the runtime is embedded in the artefact
     subprocess.check_call([NVCC, *ARCH, "-shared", "-o", SO, *objs, "-cudart", "shared", "-Xlinker", "-rpath=/usr/local/cuda/lib64"])

@@ -140,6 +140,17 @@ void release_host(HostBuf& b) { if (b.p) cudaFreeHost(b.p); b.p = nullptr; b.cap
 
 #define TRY(x) do { int rc__ = (x); if (rc__ != TKZ_OK) return rc__; } while (0)
 
+// every entry point runs on its context's device and gives the caller's current device back on every return path
+struct DeviceGuard {
+    int prev = -1; bool ok = true;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev != dev) ok = cudaSetDevice(dev) == cudaSuccess; else prev = -1;
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+#define ON_DEVICE(ctx) DeviceGuard guard__((ctx)->device); if (!guard__.ok) { (ctx)->err = "cudaSetDevice failed"; return TKZ_ERR_CUDA; }
+
 int upload(tkz_ctx* ctx, DevBuf& b, const void* src, size_t bytes) {
     TRY(ensure(ctx, b, bytes));
     if (bytes) CK(cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
@@ -204,8 +215,8 @@ extern "C" int tkz_ctx_create(int device, void* stream, uint64_t arena_hint_byte
         return TKZ_ERR_CUDA;
     }
     if (device < 0 || device >= n) { g_create_error = "invalid device ordinal"; return TKZ_ERR_INVALID_ARG; }
-    e = cudaSetDevice(device);
-    if (e != cudaSuccess) { g_create_error = std::string("cudaSetDevice: ") + cudaGetErrorString(e); return TKZ_ERR_CUDA; }
+    DeviceGuard guard__(device);
+    if (!guard__.ok) { g_create_error = "cudaSetDevice failed"; return TKZ_ERR_CUDA; }
     tkz_ctx* ctx = new tkz_ctx();
     ctx->device = device;
     cudaDeviceProp prop;
@@ -270,7 +281,7 @@ extern "C" int tkz_ctx_create(int device, void* stream, uint64_t arena_hint_byte
 
 extern "C" void tkz_ctx_destroy(tkz_ctx* ctx) {
     if (!ctx) return;
-    cudaSetDevice(ctx->device);
+    DeviceGuard guard__(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     DevBuf* bufs[] = {&ctx->t_lut, &ctx->t_lut_post, &ctx->t_char_ascii, &ctx->t_char_tab, &ctx->t_merges, &ctx->t_merge_win, &ctx->t_wp_tab, &ctx->t_wp_pool,
                       &ctx->a_text, &ctx->a_doc_off, &ctx->a_norm_text, &ctx->a_norm_doc_off, &ctx->a_chunk, &ctx->a_tiles, &ctx->a_word_start,
@@ -298,6 +309,20 @@ extern "C" void tkz_ctx_destroy(tkz_ctx* ctx) {
 
 extern "C" const char* tkz_last_error(tkz_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
 
+extern "C" int tkz_ctx_numa_node(tkz_ctx* ctx) {
+    if (!ctx) return -1;
+    char bus[32] = {0};
+    if (cudaDeviceGetPCIBusId(bus, sizeof bus, ctx->device) != cudaSuccess) return -1;
+    for (char* c = bus; *c; c++) if (*c >= 'A' && *c <= 'Z') *c = (char)(*c - 'A' + 'a');
+    const std::string path = std::string("/sys/bus/pci/devices/") + bus + "/numa_node";
+    FILE* f = fopen(path.c_str(), "r");
+    if (!f) return -1;
+    int node = -1;
+    if (fscanf(f, "%d", &node) != 1) node = -1;
+    fclose(f);
+    return node;
+}
+
 extern "C" int tkz_ctx_get_stats(tkz_ctx* ctx, tkz_stats* out) {
     if (!ctx || !out) return TKZ_ERR_INVALID_ARG;
     *out = ctx->stats; out->arena_bytes = ctx->arena_bytes;
@@ -308,7 +333,7 @@ extern "C" int tkz_ctx_get_stats(tkz_ctx* ctx, tkz_stats* out) {
 // ------------------------------------------------------------------------------------------------ model upload
 extern "C" int tkz_model_upload(tkz_ctx* ctx, const tkz_model_desc* d) {
     if (!ctx || !d) return TKZ_ERR_INVALID_ARG;
-    CK(cudaSetDevice(ctx->device));
+    ON_DEVICE(ctx);
     if (d->model_kind != TKZ_MODEL_BPE && d->model_kind != TKZ_MODEL_WORDPIECE) { ctx->err = "unknown model_kind"; return TKZ_ERR_INVALID_ARG; }
     if (d->vocab_n && (!d->vocab_bytes || !d->vocab_off || !d->vocab_ids)) { ctx->err = "vocab arrays missing"; return TKZ_ERR_INVALID_ARG; }
     DevModel m{};
@@ -863,7 +888,7 @@ int encode_device_impl(tkz_ctx* ctx, const uint8_t* d_text, const uint64_t* d_do
     ctx->grid_used = false; ctx->retried = false;
     if (N >= 0xFFFFF000ull) { ctx->err = "batch text must be < 4 GiB (u32 offsets, types.zig:4-6): split the batch"; return TKZ_ERR_INVALID_ARG; }
     if (n_docs >= 0xFFFFFFF0ull) { ctx->err = "too many documents in one batch"; return TKZ_ERR_INVALID_ARG; }
-    CK(cudaSetDevice(ctx->device));
+    ON_DEVICE(ctx);
     cudaStream_t st = ctx->stream;
     uint64_t launches = 0;
     tkz_encode_params P{};
@@ -1217,7 +1242,7 @@ extern "C" int tkz_encode_batch(tkz_ctx* ctx, const uint8_t* text, const uint64_
     if (doc_off[0] != 0) { ctx->err = "doc_off[0] must be 0"; return TKZ_ERR_INVALID_ARG; }
     const uint64_t N = doc_off[n_docs];
     if (N && !text) return TKZ_ERR_INVALID_ARG;
-    CK(cudaSetDevice(ctx->device));
+    ON_DEVICE(ctx);
     if (n_docs >= 2 && N > ctx->chunk_bytes + ctx->chunk_bytes / 2) return encode_host_chunked(ctx, text, doc_off, n_docs, N, params, out);
     return encode_host_single(ctx, text, doc_off, n_docs, N, params, out);
 }
@@ -1290,7 +1315,7 @@ extern "C" int tkz_compact_expand(const tkz_compact_result* r, uint64_t d0, uint
 extern "C" int tkz_decode_upload(tkz_ctx* ctx, const tkz_decode_desc* d) {
     if (!ctx || !d || (d->n_ids && (!d->tok_off || (!d->tok_bytes && d->tok_off[d->n_ids])))) return TKZ_ERR_INVALID_ARG;
     if (d->decoder_kind < 0 || d->decoder_kind > 3) { ctx->err = "unknown decoder_kind"; return TKZ_ERR_INVALID_ARG; }
-    CK(cudaSetDevice(ctx->device));
+    ON_DEVICE(ctx);
     const uint64_t nb = d->n_ids ? d->tok_off[d->n_ids] : 0;
     TRY(upload(ctx, ctx->t_dec_bytes, d->tok_bytes, (size_t)nb));
     std::vector<unsigned long long> off(d->n_ids + 1, 0);
@@ -1317,7 +1342,7 @@ extern "C" int tkz_decode_batch(tkz_ctx* ctx, const uint32_t* ids, const uint64_
     const uint64_t n_tok = seq_off[n_seqs];
     if (n_tok && !ids) return TKZ_ERR_INVALID_ARG;
     if (n_tok >= 0xFFFFFFF0ull || n_seqs >= 0xFFFFFFF0ull) { ctx->err = "too many ids in one decode batch"; return TKZ_ERR_INVALID_ARG; }
-    CK(cudaSetDevice(ctx->device));
+    ON_DEVICE(ctx);
     cudaStream_t st = ctx->stream;
     unsigned long long* hctrl = (unsigned long long*)ctx->h_ctrl.p;
     const DecodeTables& t = ctx->dt;
