@@ -356,6 +356,53 @@ def roofline_of(W, agg, ms_step_max, outputs, peak, peak_src, size_mib):
             "stage_ms_per_step": dict(zip(["split", "model", "scan", "emit", "total_kernels"], [round(x, 4) for x in st]))}
 
 
+def strong_scaling(n_gpus, total_mib, workload="c5b"):
+    """tkzm_encode_batch_compact over n_gpus GPUs on one seed-fixed corpus, two cuts; wall time per shard (host buffers in,
+    compact result out: an e2e figure), slowest over mean = the load imbalance the cut leaves"""
+    import tokzig_b200 as tz
+    from tools import tokenizers_io
+    tok_name, cname, desc, trunc, pad, _, _ = WORKLOADS[workload]
+    t0 = time.time()
+    text, off = make_corpus(cname, total_mib << 20, 99, pinned=True)
+    t_gen = time.time() - t0
+    cfg = tz.Tokenizer.from_json(tokenizers_io.tokenizer_json(tok_name), device=None)
+    pool = tz.MultiPool(cfg, list(range(n_gpus)))
+    out = {"workload": f"{workload}: {desc}", "corpus_bytes": int(off[-1]), "docs": len(off) - 1, "n_gpus": n_gpus, "corpus_generated_s": round(t_gen, 1),
+           "api": "tkzm_encode_batch_compact (rank 0 drives every GPU: one context + one host thread per GPU; pinned text in, compact results out)", "cuts": {}}
+    o = oracle_for(tok_name, trunc, pad)
+    rc_ = pool.raw_class()
+    for label, cb in (("bytes", False), ("cost_model", True)):
+        # the cut, timed on its own (bytes: a few binary searches; cost model: one sparse pass over the text on all host threads)
+        t0 = time.perf_counter()
+        cut = tz.shard_bounds_c(off, n_gpus, tz.document_costs_c(text, off, rc_) if cb else None)
+        cut_ms = (time.perf_counter() - t0) * 1e3
+        pool.encode_compact(text, off, bounds=cut)                     # warm-up: arenas, pinned buffers
+        best = None
+        for _ in range(2):
+            t0 = time.perf_counter()
+            bounds, results, ms = pool.encode_compact(text, off, bounds=cut)
+            wall = time.perf_counter() - t0
+            if best is None or wall < best[0]:
+                best = (wall, bounds.copy(), ms.copy(), sum(int(r.n_kept) for r in results))
+        wall, bounds, ms, kept = best
+        shard_bytes = [int(off[int(bounds[k + 1])] - off[int(bounds[k])]) for k in range(n_gpus)]
+        # parity of the sharded path: the first and the last documents of every shard against the oracle
+        ok = True
+        for k in range(n_gpus):
+            d0, d1 = int(bounds[k]), int(bounds[k + 1])
+            for lo, hi in ((d0, min(d1, d0 + 40)), (max(d0, d1 - 40), d1)):
+                if hi <= lo:
+                    continue
+                ref = o.encode_packed(text[int(off[lo]):int(off[hi])], off[lo:hi + 1] - off[lo], algo=1, threads=os.cpu_count() or 1)
+                got = tz.expand_compact(results[k], lo - d0, hi - d0)
+                ok = ok and np.array_equal(got.ids, ref.ids) and np.array_equal(got.offsets, ref.offsets) and np.array_equal(got.doc_tok_off, ref.doc_tok_off)
+        out["cuts"][label] = {"value": int(off[-1]) / wall / 1e9, "unit": "GB/s", "wall_ms": wall * 1e3, "shard_ms": [round(float(x), 2) for x in ms],
+                              "imbalance_slowest_over_mean": float(ms.max() / ms.mean()), "shard_bytes": shard_bytes, "kept_tokens": kept,
+                              "cut_ms": cut_ms, "parity_checked_vs_oracle": bool(ok)}
+    pool.close(); cfg.close()
+    return out
+
+
 def run_ours(args, rank, local_rank, world):
     import torch
     import torch.distributed as dist
@@ -512,6 +559,18 @@ def run_ours(args, rank, local_rank, world):
             W2.close(); del W2
             torch.cuda.empty_cache()
 
+    # ---- strong scaling + skew through the product's multi-GPU entry point (tkzm_*): ONE fixed corpus (BASELINE config 5: 4 GiB,
+    # documents 1 B .. 4 MiB with long unbroken words) cut over the N GPUs by bytes and by the cost model; rank 0 drives all GPUs
+    # (one context + one host thread each) while the other ranks wait on a CPU barrier with their GPUs idle
+    strong = None
+    if world > 1 and not args.no_strong and args.workload == "c2b":
+        gloo = dist.new_group(backend="gloo")
+        torch.cuda.synchronize()
+        dist.barrier(group=gloo)
+        if rank == 0:
+            strong = strong_scaling(world, args.strong_mib)
+        dist.barrier(group=gloo)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -527,7 +586,7 @@ def run_ours(args, rank, local_rank, world):
             "roofline": head["roofline"], "device_variants": head.get("device_variants"), "cpu_baseline": cb, "e2e": head["e2e"],
             "gpu_launches": int(round(head["gpu_launches_per_step"] * args.steps)), "clocks": clocks,
             "parity_checked_vs_oracle": None if head["parity_checked_vs_oracle"] is None else head["parity_checked_vs_oracle"]["ok"],
-            "parity": head["parity_checked_vs_oracle"], "configs": configs}
+            "parity": head["parity_checked_vs_oracle"], "configs": configs, "strong_scaling": strong}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -550,6 +609,9 @@ def main():
     ap.add_argument("--no-verify", action="store_true")
     ap.add_argument("--no-configs", action="store_true", help="headline workload only")
     ap.add_argument("--no-materialise", action="store_true")
+    ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling / skew measurement (N > 1 only)")
+    ap.add_argument("--strong-mib", type=int, default=4096, help="size of the fixed corpus of the strong-scaling measurement")
+    ap.add_argument("--multi", type=int, default=0, help="single process: only the strong-scaling measurement over this many GPUs (tkzm_*)")
     args = ap.parse_args()
     if args.size_mib <= 0:
         args.size_mib = DEFAULT_MIB[args.workload]
@@ -568,6 +630,9 @@ def main():
         g.build()
     elif world > 1:
         time.sleep(0.5)
+    if args.multi > 0:
+        print(json.dumps({"strong_scaling": strong_scaling(args.multi, args.strong_mib, "c5b" if args.workload == "c2b" else args.workload)}), flush=True)
+        return
     run_ours(args, rank, local_rank, world)
 
 

@@ -220,7 +220,7 @@ int tkzm_shard_bounds(const uint64_t* doc_off, uint64_t n_docs, int32_t n_shards
  * raw_class[256] = TKZ_CLS_* of every RAW byte, NULL = no pre-tokenizer.  One pass over the text on `threads` host threads
  * (0 = all).  For corpora with skewed document and word lengths (BASELINE config 5). */
 int tkzm_document_costs(const uint8_t* text, const uint64_t* doc_off, uint64_t n_docs, const uint8_t* raw_class, int32_t threads, double* cost);
-/* The batch over all GPUs of the pool: cuts it (by bytes, or by tkzm_document_costs when cost_balanced), runs one
+/* The batch over all GPUs of the pool: cuts it (cost_balanced 0: by bytes, 1: by tkzm_document_costs, 2: bounds as given), runs one
  * tkz_encode_batch_compact per shard concurrently, and returns the cut (bounds[n + 1]) and the n compact results (arrays owned
  * by the shard's context; err_doc is a document index of the whole batch).  shard_ms (n entries, may be NULL) = wall time of
  * every shard's call. */

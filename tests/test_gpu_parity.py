@@ -915,7 +915,8 @@ def test_multi_context_pool_matches_the_oracle(cost_balanced):
         cfg.padding = pad
         o = orc.OracleTokenizer.from_json(js)
         o.truncation = trunc; o.padding = pad
-        pool = tz.MultiPool(cfg, [0, 0, 0])
+        ng = torch.cuda.device_count()
+        pool = tz.MultiPool(cfg, [k % ng for k in range(3)])            # distinct GPUs when the box has them
         before = torch.cuda.current_device()
         got = pool.encode_expanded(text, off, cost_balanced=cost_balanced)
         assert torch.cuda.current_device() == before

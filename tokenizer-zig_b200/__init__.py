@@ -640,16 +640,29 @@ class MultiPool:
         except Exception:
             pass
 
-    def encode_compact(self, text: np.ndarray, doc_off: np.ndarray, want_offsets: bool = True, cost_balanced: bool = False):
-        """tkzm_encode_batch_compact with the tokenizer's truncation / padding: (bounds, [CompactResult per shard], shard_ms)."""
+    def raw_class(self) -> Optional[np.ndarray]:
+        """TKZ_CLS_* of every raw byte under the tokenizer's normalizer + pre-tokenizer (None: no pre-tokenizer), for document_costs_c"""
+        d = self.tokenizer.model_desc()
+        if d["class_lut"] is None:
+            return None
+        nl = d["norm_lut"] if d["norm_lut"] is not None else np.arange(256, dtype=np.uint16)
+        return np.where(nl == 0xFFFF, 1, d["class_lut"][nl & 0xFF]).astype(np.uint8)
+
+    def encode_compact(self, text: np.ndarray, doc_off: np.ndarray, want_offsets: bool = True, cost_balanced: bool = False, bounds: np.ndarray = None):
+        """tkzm_encode_batch_compact with the tokenizer's truncation / padding: (bounds, [CompactResult per shard], shard_ms).
+        `bounds` (n + 1 document indices) = the caller's own cut."""
         text = np.ascontiguousarray(text, dtype=np.uint8)
         doc_off = np.ascontiguousarray(doc_off, dtype=np.uint64)
-        bounds = np.zeros(self.n + 1, np.uint64)
+        if bounds is not None:
+            bounds = np.ascontiguousarray(bounds, dtype=np.uint64).copy()
+            cost_balanced = 2
+        else:
+            bounds = np.zeros(self.n + 1, np.uint64)
         results = (CompactResult * self.n)()
         ms = np.zeros(self.n, np.float64)
         p = self.tokenizer.params()
         rc = self._L.tkzm_encode_batch_compact(self._h, text.ctypes.data if text.size else None, doc_off.ctypes.data, len(doc_off) - 1, C.byref(p),
-                                               1 if want_offsets else 0, 1 if cost_balanced else 0, bounds.ctypes.data, C.cast(results, C.c_void_p), ms.ctypes.data)
+                                               1 if want_offsets else 0, int(cost_balanced), bounds.ctypes.data, C.cast(results, C.c_void_p), ms.ctypes.data)
         if rc != OK:
             docs = [int(r.err_doc) for r in results if int(r.err_doc) >= 0]
             raise TokzigError(rc, (self._L.tkzm_last_error(self._h) or b"").decode(), min(docs) if docs else -1)

@@ -145,13 +145,18 @@ extern "C" int tkzm_document_costs(const uint8_t* text, const uint64_t* doc_off,
             const uint64_t a = doc_off[d], b = doc_off[d + 1];
             double c = (double)(b - a);
             if (!raw_class) c += extra(b - a);
-            else {
-                uint64_t run = 0;
-                for (uint64_t i = a; i < b; i++) {
-                    if (raw_class[text[i]] == TKZ_CLS_WORD) run++;
-                    else { if (run >= LONG_MIN) c += extra(run); run = 0; }
+            else if (b - a >= LONG_MIN) {
+                // only runs of LONG_MIN or more WORD bytes matter: every such run holds a byte at a multiple of LONG_MIN from the
+                // document start, so only those bytes are looked at, and a WORD byte there is extended to its run
+                uint64_t i = a + LONG_MIN - 1;
+                while (i < b) {
+                    if (raw_class[text[i]] != TKZ_CLS_WORD) { i += LONG_MIN; continue; }
+                    uint64_t lo = i, hi = i + 1;
+                    while (lo > a && raw_class[text[lo - 1]] == TKZ_CLS_WORD) lo--;
+                    while (hi < b && raw_class[text[hi]] == TKZ_CLS_WORD) hi++;
+                    if (hi - lo >= LONG_MIN) c += extra(hi - lo);
+                    i = hi + LONG_MIN;                             // the next run starts behind hi
                 }
-                if (run >= LONG_MIN) c += extra(run);
             }
             cost[d] = c;
         }
@@ -170,7 +175,11 @@ extern "C" int tkzm_encode_batch_compact(tkzm_pool* p, const uint8_t* text, cons
                                          int want_offsets, int cost_balanced, uint64_t* bounds, tkz_compact_result* results, double* shard_ms) {
     if (!p || !doc_off || !bounds || !results) return TKZ_ERR_INVALID_ARG;
     const int32_t n = (int32_t)p->ctx.size();
-    if (cost_balanced) {
+    if (cost_balanced == 2) {
+        // the caller's cut
+        if (bounds[0] != 0 || bounds[n] != n_docs) { p->err = "bounds must run from 0 to n_docs"; return TKZ_ERR_INVALID_ARG; }
+        for (int32_t k = 0; k < n; k++) if (bounds[k] > bounds[k + 1]) { p->err = "bounds must not decrease"; return TKZ_ERR_INVALID_ARG; }
+    } else if (cost_balanced) {
         std::vector<double> cost(n_docs);
         int rc = tkzm_document_costs(text, doc_off, n_docs, p->has_pretok ? p->raw_class : nullptr, 0, cost.data());
         if (rc == TKZ_OK) rc = tkzm_shard_bounds(doc_off, n_docs, n, cost.data(), bounds);
