@@ -296,6 +296,8 @@ int tkzh_decode_batch(tkzh_tokenizer* t, const uint32_t* ids, const uint64_t* se
 uint64_t tkzh_get_vocab_size(tkzh_tokenizer* t);
 int tkzh_token_to_id(tkzh_tokenizer* t, const uint8_t* token, uint64_t len, uint32_t* id);       /* 1 found, 0 not */
 int tkzh_id_to_token(tkzh_tokenizer* t, uint32_t id, const uint8_t** token, uint64_t* len);       /* 1 found, 0 not */
+/* the model's own map only (src/model/bpe.zig:258): the strings of Encoding.tokens, which ignore the added vocabulary */
+int tkzh_model_id_to_token(tkzh_tokenizer* t, uint32_t id, const uint8_t** token, uint64_t* len);
 int tkzh_add_special_tokens(tkzh_tokenizer* t, const uint8_t* contents, const uint64_t* off, uint64_t n, uint64_t* added);
 /* loader facts used by the parity tests */
 uint64_t tkzh_model_vocab_count(tkzh_tokenizer* t);

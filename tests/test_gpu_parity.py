@@ -83,6 +83,19 @@ def test_example_basic_tokenize_call_sequence(tmp_path):
     t.close()
 
 
+def test_encoding_tokens_come_from_the_model_vocabulary_not_the_added_one():
+    """Encoding.tokens[i] = the MODEL's vocab_r[id] (bpe.zig:258), while idToToken consults the added vocabulary first
+    (lib.zig:217-223): an added token that shares an id with a model token must not change Encoding.tokens."""
+    js = json.dumps({"model": {"type": "BPE", "vocab": {"a": 0, "b": 1, "ab": 2}, "merges": ["a b"]}, "pre_tokenizer": {"type": "Whitespace"},
+                     "added_tokens": [{"id": 2, "content": "<special>", "special": True}, {"id": 7, "content": "<only-added>", "special": True}]})
+    t = tz.Tokenizer.from_json(js, device=0)
+    e = t.encode("ab a", True)
+    assert e.ids.tolist() == [2, 0]
+    assert e.get_tokens() == [b"ab", b"a"]
+    assert t.id_to_token(2) == b"<special>" and t.id_to_token(7) == b"<only-added>" and t._model_id_to_token(7) is None
+    t.close()
+
+
 # ----------------------------------------------------------------------------- random property tests
 @pytest.mark.parametrize("seed", range(48))
 def test_bpe_random(seed):
@@ -934,3 +947,17 @@ def test_multi_context_pool_matches_the_oracle(cost_balanced):
         pool.encode_compact(t_, o_)
     assert e.value.code == tz.ERR_INVALID_UTF8 and e.value.doc == 50
     pool.close(); cfg.close()
+
+
+def test_decode_batch_refuses_a_batch_that_decodes_to_4gib_or_more():
+    """token byte offsets of the decode path are 32-bit: a batch whose decoded bytes reach 4 GiB (here 4100 ids of a 1 MiB
+    token) must be refused with the request to split it, not wrapped; the same ids in two halves decode."""
+    big = "x" * (1 << 20)
+    js = json.dumps({"model": {"type": "WordPiece", "vocab": {"[UNK]": 0, big: 1, "ab": 2}, "unk_token": "[UNK]"}})
+    t = tz.Tokenizer.from_json(js, device=0)
+    with pytest.raises(tz.TokzigError) as e:
+        t.decode_batch([[1] * 2050, [2], [1] * 2050])
+    assert e.value.code == tz.ERR_INVALID_ARG and "split" in str(e.value)
+    out = t.decode_batch([[1] * 40, [2, 1, 2]])
+    assert len(out[0]) == 40 << 20 and out[1] == b"ab" + big.encode() + b"ab"
+    t.close()

@@ -132,7 +132,7 @@ EXPORTED_SYMBOLS = [
     "tkz_encode_batch_device", "tkz_encode_batch_compact", "tkz_compact_slots", "tkz_compact_expand", "tkz_decode_upload", "tkz_decode_batch",
     "tkzh_from_json", "tkzh_from_file", "tkzh_free", "tkzh_last_error", "tkzh_ctx", "tkzh_set_truncation", "tkzh_set_padding",
     "tkzh_set_normalizer", "tkzh_set_pretokenizer", "tkzh_encode_batch", "tkzh_decode", "tkzh_decode_batch", "tkzh_get_vocab_size", "tkzh_token_to_id",
-    "tkzh_id_to_token", "tkzh_add_special_tokens", "tkzh_model_vocab_count", "tkzh_merge_count", "tkzh_has_normalizer",
+    "tkzh_id_to_token", "tkzh_model_id_to_token", "tkzh_add_special_tokens", "tkzh_model_vocab_count", "tkzh_merge_count", "tkzh_has_normalizer",
     "tkzh_has_pretokenizer", "tkzh_has_post_processor", "tkzh_added_token_count", "tkzh_added_token", "tkzh_model_desc",
 ]
 
@@ -194,6 +194,7 @@ def lib():
     L.tkzh_get_vocab_size.restype = u64
     L.tkzh_token_to_id.argtypes = [vp, C.c_char_p, u64, C.POINTER(u32)]
     L.tkzh_id_to_token.argtypes = [vp, u32, C.POINTER(vp), C.POINTER(u64)]
+    L.tkzh_model_id_to_token.argtypes = [vp, u32, C.POINTER(vp), C.POINTER(u64)]
     L.tkzh_add_special_tokens.argtypes = [vp, C.c_char_p, vp, u64, C.POINTER(u64)]
     L.tkzh_model_vocab_count.argtypes = [vp]
     L.tkzh_model_vocab_count.restype = u64
@@ -540,7 +541,11 @@ class Tokenizer:
         return C.string_at(p.value, n.value) if n.value else b""
 
     def _model_id_to_token(self, i: int) -> Optional[bytes]:
-        return self.id_to_token(i)
+        """the model's own id -> token map (bpe.zig:258): an added token with the same id does not change Encoding.tokens"""
+        p, n = C.c_void_p(), C.c_uint64(0)
+        if not self._L.tkzh_model_id_to_token(self._h, i, C.byref(p), C.byref(n)):
+            return None
+        return C.string_at(p.value, n.value) if n.value else b""
 
     def add_special_tokens(self, tokens: Sequence) -> int:
         bs = [t.encode() if isinstance(t, str) else t for t in tokens]

@@ -1357,7 +1357,13 @@ extern "C" int tkz_decode_batch(tkz_ctx* ctx, const uint32_t* ids, const uint64_
     uint32_t* tok_len = (uint32_t*)ctx->a_dec_len.p;
     const uint32_t* d_ids = (const uint32_t*)ctx->a_dec_ids.p;
     const unsigned long long* d_seq = (const unsigned long long*)ctx->a_dec_seq_off.p;
-    if (n_tok) dec_len_kernel<<<(unsigned)((n_tok + 255) / 256), 256, 0, st>>>(t, d_ids, n_tok, skip_special_tokens, tok_len);
+    unsigned long long* ctrl = (unsigned long long*)ctx->a_ctrl.p;
+    ctrl_reset_kernel<<<1, 1, 0, st>>>(ctrl);
+    if (n_tok) dec_len_kernel<<<(unsigned)((n_tok + 255) / 256), 256, 0, st>>>(t, d_ids, n_tok, skip_special_tokens, tok_len, ctrl + 1);
+    TRY(readback(ctx, hctrl + 42, ctrl + 1, 8));
+    CK(cudaStreamSynchronize(st));
+    // token byte offsets are u32: a batch that decodes to 4 GiB or more (the round trip of a 4 GiB encode) must be split
+    if (hctrl[42] >= 0xFFFFF000ull) { ctx->err = "decoded batch must be < 4 GiB (u32 byte offsets): split the batch"; return TKZ_ERR_INVALID_ARG; }
     exclusive_scan<uint32_t>(tok_len, n_tok, tok_len, (unsigned long long*)ctx->a_scan_tmp.p, st);      // tok_len[n_tok] = raw bytes
     TRY(readback(ctx, hctrl + 40, tok_len + n_tok, 4));
     CK(cudaStreamSynchronize(st));

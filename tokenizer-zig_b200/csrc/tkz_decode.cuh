@@ -23,14 +23,21 @@ struct DecodeTables {
     int decoder_kind;
 };
 
-__global__ void dec_len_kernel(DecodeTables t, const uint32_t* __restrict__ ids, uint64_t n_tok, int skip_special, uint32_t* __restrict__ tok_len) {
+// total = the raw bytes of the whole batch in 64 bits: the per-token offsets are 32-bit (the scan would wrap silently), so the
+// host refuses a batch whose total does not fit
+__global__ void dec_len_kernel(DecodeTables t, const uint32_t* __restrict__ ids, uint64_t n_tok, int skip_special, uint32_t* __restrict__ tok_len,
+                               unsigned long long* __restrict__ total) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_tok) return;
-    const uint32_t id = ids[i];
     uint32_t len = 0;
-    if (id < t.n_ids) len = (uint32_t)(t.tok_off[id + 1] - t.tok_off[id]);
-    if (skip_special && (id >> 5) < t.n_special_words && ((t.special_bits[id >> 5] >> (id & 31u)) & 1u)) len = 0;
-    tok_len[i] = len;
+    if (i < n_tok) {
+        const uint32_t id = ids[i];
+        if (id < t.n_ids) len = (uint32_t)(t.tok_off[id + 1] - t.tok_off[id]);
+        if (skip_special && (id >> 5) < t.n_special_words && ((t.special_bits[id >> 5] >> (id & 31u)) & 1u)) len = 0;
+        tok_len[i] = len;
+    }
+    unsigned long long s = len;
+    for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(0xFFFFFFFFu, s, d);
+    if ((threadIdx.x & 31) == 0 && s) atomicAdd(total, s);
 }
 
 __global__ void dec_gather_kernel(DecodeTables t, const uint32_t* __restrict__ ids, uint64_t n_tok, const uint32_t* __restrict__ tok_boff,

@@ -413,6 +413,14 @@ extern "C" int tkzh_id_to_token(tkzh_tokenizer* t, uint32_t id, const uint8_t** 
     if (m != t->vocab_r.end()) { *token = (const uint8_t*)m->second.data(); *len = m->second.size(); return 1; }
     return 0;
 }
+// the MODEL's own id -> token map only: what Tokenizer.encode puts into Encoding.tokens (bpe.zig:258 `vocab_r.get(id) orelse ""`);
+// an added token that shares the id does not change it
+extern "C" int tkzh_model_id_to_token(tkzh_tokenizer* t, uint32_t id, const uint8_t** token, uint64_t* len) {
+    auto m = t->vocab_r.find(id);
+    if (m == t->vocab_r.end()) return 0;
+    *token = (const uint8_t*)m->second.data(); *len = m->second.size();
+    return 1;
+}
 extern "C" int tkzh_add_special_tokens(tkzh_tokenizer* t, const uint8_t* contents, const uint64_t* off, uint64_t n, uint64_t* added) {   // lib.zig:192-200
     uint64_t c = 0;
     for (uint64_t i = 0; i < n; i++) {
