@@ -81,7 +81,8 @@ struct DevModel {
     uint64_t max_chars;
 };
 
-// error word: ((word_index + 1) << 8 | code) so that atomicMin keeps the first failing word; 0xFF.. = none
+// error word: (word index or byte position of the failing word) << 8 | code, so that atomicMin keeps the first failing word in
+// text order; 0xFF.. = none
 #define TKZ_ERRW_NONE 0xFFFFFFFFFFFFFFFFULL
 #define TKZ_ECODE_UTF8 3
 #define TKZ_ECODE_UNK 2

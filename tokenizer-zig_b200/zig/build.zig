@@ -20,10 +20,8 @@ pub fn build(b: *std.Build) void {
     mod.addLibraryPath(.{ .cwd_relative = tokzig_lib });
     mod.addLibraryPath(.{ .cwd_relative = b.fmt("{s}/lib64", .{cuda_home}) });
     mod.linkSystemLibrary("tokzig_b200", .{ .preferred_link_mode = .static });
-    mod.linkSystemLibrary("cudart_static", .{});
+    mod.linkSystemLibrary("cudart", .{}); // the CUDA runtime is linked dynamically, as the shared library of the Python / C++ harness does
     mod.linkSystemLibrary("stdc++", .{});
-    mod.linkSystemLibrary("dl", .{});
-    mod.linkSystemLibrary("rt", .{});
     mod.linkSystemLibrary("pthread", .{});
 
     const example = b.addExecutable(.{

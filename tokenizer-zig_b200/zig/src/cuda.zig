@@ -26,6 +26,8 @@ pub const OUT_ATTENTION: u32 = 4;
 pub const OUT_TYPE_IDS: u32 = 8;
 pub const OUT_SPECIAL: u32 = 16;
 pub const OUT_ALL: u32 = 31;
+pub const OUT_OFFSETS_PACKED: u32 = 32; // one u16 per token (start | end << 8) when every pre-token is < 256 bytes
+pub const OUT_IDS_U16: u32 = 64; // ids as u16 when every vocabulary id is < 65536
 
 pub const ModelDesc = extern struct {
     model_kind: i32,
@@ -69,6 +71,22 @@ pub const BatchResult = extern struct {
     type_ids: ?[*]const u32,
     special_tokens_mask: ?[*]const u32,
     err_doc: i64,
+    offsets_packed: ?[*]const u16,
+    ids16: ?[*]const u16,
+};
+
+/// tkz_compact_result: kept real tokens only; masks and padding slots are rebuilt on the host (tkz_compact_expand)
+pub const CompactResult = extern struct {
+    n_docs: u64,
+    n_kept: u64,
+    n_real_tokens: u64,
+    doc_kept_off: ?[*]const u64, // n_docs + 1
+    ids: ?[*]const u32, // null when ids16 is delivered
+    ids16: ?[*]const u16,
+    offsets_packed: ?[*]const u16, // null when a pre-token has 256+ bytes (then `offsets`)
+    offsets: ?[*]const u32,
+    params: EncodeParams,
+    err_doc: i64,
 };
 
 pub const Stats = extern struct {
@@ -83,7 +101,7 @@ pub const Stats = extern struct {
     ms_emit: f32,
     ms_total: f32,
     model_flags: u32,
-    path: u32, // pipeline of the last encode: 0 per-occurrence, 1 dedup multi-pass, 2 slice pipeline
+    path: u32, // pipeline of the last encode: 0 per-occurrence, 2 slice pipeline
 };
 
 pub const DecodeDesc = extern struct {
@@ -108,5 +126,21 @@ pub extern fn tkz_ctx_get_stats(ctx: *Ctx, out: *Stats) c_int;
 pub extern fn tkz_model_upload(ctx: *Ctx, desc: *const ModelDesc) c_int;
 pub extern fn tkz_encode_batch(ctx: *Ctx, text: ?[*]const u8, doc_off: [*]const u64, n_docs: u64, params: *const EncodeParams, out: *BatchResult) c_int;
 pub extern fn tkz_encode_batch_device(ctx: *Ctx, d_text: ?*const anyopaque, d_doc_off: *const anyopaque, n_docs: u64, text_bytes: u64, params: *const EncodeParams, out: *BatchResult) c_int;
+pub extern fn tkz_ctx_numa_node(ctx: *Ctx) c_int;
+pub extern fn tkz_encode_batch_compact(ctx: *Ctx, text: ?[*]const u8, doc_off: [*]const u64, n_docs: u64, params: *const EncodeParams, want_offsets: c_int, out: *CompactResult) c_int;
+pub extern fn tkz_compact_slots(r: *const CompactResult, d0: u64, d1: u64) u64;
+pub extern fn tkz_compact_expand(r: *const CompactResult, d0: u64, d1: u64, doc_tok_off: ?[*]u64, ids: ?[*]u32, offsets: ?[*]u32, attention_mask: ?[*]u32, type_ids: ?[*]u32, special_tokens_mask: ?[*]u32) c_int;
+
+// several GPUs of one box: one context + one host thread per GPU, no collective (include/tokzig_b200.h, tkzm_*)
+pub const Pool = opaque {};
+pub extern fn tkzm_create(devices: [*]const i32, n: i32, out: *?*Pool) c_int;
+pub extern fn tkzm_destroy(pool: ?*Pool) void;
+pub extern fn tkzm_size(pool: *Pool) i32;
+pub extern fn tkzm_ctx(pool: *Pool, i: i32) ?*Ctx;
+pub extern fn tkzm_last_error(pool: ?*Pool) [*:0]const u8;
+pub extern fn tkzm_model_upload(pool: *Pool, desc: *const ModelDesc) c_int;
+pub extern fn tkzm_shard_bounds(doc_off: [*]const u64, n_docs: u64, n_shards: i32, cost: ?[*]const f64, bounds: [*]u64) c_int;
+pub extern fn tkzm_document_costs(text: ?[*]const u8, doc_off: [*]const u64, n_docs: u64, raw_class: ?[*]const u8, threads: i32, cost: [*]f64) c_int;
+pub extern fn tkzm_encode_batch_compact(pool: *Pool, text: ?[*]const u8, doc_off: [*]const u64, n_docs: u64, params: *const EncodeParams, want_offsets: c_int, cost_balanced: c_int, bounds: [*]u64, results: [*]CompactResult, shard_ms: ?[*]f64) c_int;
 pub extern fn tkz_decode_upload(ctx: *Ctx, desc: *const DecodeDesc) c_int;
 pub extern fn tkz_decode_batch(ctx: *Ctx, ids: ?[*]const u32, seq_off: [*]const u64, n_seqs: u64, skip_special_tokens: c_int, out: *DecodeResult) c_int;

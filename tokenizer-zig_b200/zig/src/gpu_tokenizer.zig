@@ -175,7 +175,64 @@ pub const GpuTokenizer = struct {
         return encs[0];
     }
 
-    /// The batch form the GPU path exists for: all documents in one C-ABI call.
+    /// Replaces the byte tables derived from the JSON component types: for callers that hand-wire `normalizer_impl` /
+    /// `pretokenizer_impl` (public fields, src/lib.zig:37-38) with the struct variants of src/normalizer/normalizer.zig and
+    /// src/pretokenizer/pretokenizer.zig.  Every such component is byte-wise, so any chain composes into one byte map
+    /// (norm_lut[b] = normalised byte or cuda.NORM_DROP) and one class table over normalised bytes; null = component absent.
+    /// (The C++ host mirror composes these tables itself, tkzh_set_normalizer / tkzh_set_pretokenizer; this Zig layer reads
+    /// only the JSON types, see INTEGRATION.md "Known divergences".)
+    pub fn setByteTables(self: *Self, desc_base: *cuda.ModelDesc, norm_lut: ?*const [256]u16, class_lut: ?*const [256]u8) !void {
+        desc_base.norm_lut = if (norm_lut) |p| p else null;
+        desc_base.class_lut = if (class_lut) |p| p else null;
+        try check(cuda.tkz_model_upload(self.ctx, desc_base));
+    }
+
+    /// Borrowed view of a batch encoding: the arrays belong to the context's pinned buffers and stay valid until the next
+    /// encode on this tokenizer -- the contract of FastTokenizer.encode / SpanEncoding (src/lib.zig:353-356).  Nothing is
+    /// allocated per document; masks and padding slots are not stored at all (they are constants of `kept` and the padding
+    /// parameters) and come out of `expandInto`.
+    pub const BatchView = struct {
+        r: cuda.CompactResult,
+
+        pub fn len(self: *const BatchView) usize {
+            return @intCast(self.r.n_docs);
+        }
+        /// kept real tokens of document d (after truncation, before padding)
+        pub fn kept(self: *const BatchView, d: usize) usize {
+            return @intCast(self.r.doc_kept_off.?[d + 1] - self.r.doc_kept_off.?[d]);
+        }
+        pub fn id(self: *const BatchView, d: usize, i: usize) u32 {
+            const k: usize = @intCast(self.r.doc_kept_off.?[d]);
+            return if (self.r.ids16) |p| p[k + i] else self.r.ids.?[k + i];
+        }
+        pub fn offset(self: *const BatchView, d: usize, i: usize) lib.Offset {
+            const k: usize = @intCast(self.r.doc_kept_off.?[d]);
+            if (self.r.offsets_packed) |p| return lib.Offset.init(p[k + i] & 0xFF, p[k + i] >> 8);
+            return lib.Offset.init(self.r.offsets.?[2 * (k + i)], self.r.offsets.?[2 * (k + i) + 1]);
+        }
+        /// slots of document d after Encoding.pad (src/encoding.zig:385-463)
+        pub fn slots(self: *const BatchView, d: usize) usize {
+            return @intCast(cuda.tkz_compact_slots(&self.r, d, d + 1));
+        }
+        /// Encoding.fromTokens + pad of document d into caller-owned arrays of `slots(d)` entries (offsets: 2 u32 per slot)
+        pub fn expandInto(self: *const BatchView, d: usize, ids: []u32, offsets: []u32, attention: []u32, type_ids: []u32, special: []u32) !void {
+            try check(cuda.tkz_compact_expand(&self.r, d, d + 1, null, ids.ptr, offsets.ptr, attention.ptr, type_ids.ptr, special.ptr));
+        }
+    };
+
+    /// The batch form the GPU path exists for.  `flat` = all documents back to back, `off[n_docs + 1]` byte offsets (no copy
+    /// of the text is made; pinned memory is fastest, pageable memory works).  Only kept ids (u16 when the vocabulary fits)
+    /// and packed offsets cross PCIe.
+    pub fn encodeBatchView(self: *Self, flat: []const u8, off: []const u64, want_offsets: bool) !BatchView {
+        var v: BatchView = undefined;
+        const p = self.params();
+        try check(cuda.tkz_encode_batch_compact(self.ctx, flat.ptr, off.ptr, off.len - 1, &p, if (want_offsets) 1 else 0, &v.r));
+        return v;
+    }
+
+    /// Source-compatible batch form: one owned `Encoding` per document, exactly what a loop over Tokenizer.encode returns
+    /// (src/lib.zig:109-160).  Costs six allocations per document and one per token string, as the reference does
+    /// (src/encoding.zig:246-294); callers that can live with borrowed data should use `encodeBatchView`.
     pub fn encodeBatch(self: *Self, texts: []const []const u8, add_special_tokens: bool) ![]lib.Encoding {
         _ = add_special_tokens; // every post-processor of the reference is a no-op (config.zig:551-555)
         const a = self.base.allocator;
@@ -193,54 +250,68 @@ pub const GpuTokenizer = struct {
         }
         off[texts.len] = pos;
 
-        var res: cuda.BatchResult = undefined;
-        const p = self.params();
-        try check(cuda.tkz_encode_batch(self.ctx, flat.ptr, off.ptr, texts.len, &p, &res));
+        const view = try self.encodeBatchView(flat, off, true);
 
         const out = try a.alloc(lib.Encoding, texts.len);
-        errdefer a.free(out);
+        var built: usize = 0;
+        // an allocation failure in the middle of the batch gives back everything built so far
+        errdefer {
+            for (out[0..built]) |*e| e.deinit();
+            a.free(out);
+        }
         for (0..texts.len) |d| {
-            const lo: usize = @intCast(res.doc_tok_off.?[d]);
-            const hi: usize = @intCast(res.doc_tok_off.?[d + 1]);
-            const n = hi - lo;
-            if (n == 0) {
-                out[d] = lib.Encoding.empty(a);
-                continue;
-            }
-            const e_ids = try a.alloc(u32, n);
-            const e_type = try a.alloc(u32, n);
-            const e_tok = try a.alloc([]const u8, n);
-            const e_off = try a.alloc(lib.Offset, n);
-            const e_spec = try a.alloc(u32, n);
-            const e_attn = try a.alloc(u32, n);
-            for (0..n) |i| {
-                const s = lo + i;
-                e_ids[i] = res.ids.?[s];
-                e_type[i] = res.type_ids.?[s];
-                e_off[i] = lib.Offset.init(res.offsets.?[2 * s], res.offsets.?[2 * s + 1]);
-                e_spec[i] = res.special_tokens_mask.?[s];
-                e_attn[i] = res.attention_mask.?[s];
-                // tokens[i] == idToToken(ids[i]) always (bpe.zig:258, wordpiece.zig:200-205); pad slots carry pad_token
-                const str: []const u8 = if (e_attn[i] == 0)
-                    (if (self.base.padding) |pd| pd.pad_token else "[PAD]")
-                else
-                    (self.base.model_impl.idToToken(e_ids[i]) orelse "");
-                e_tok[i] = try a.dupe(u8, str);
-            }
-            out[d] = .{
-                .allocator = a,
-                .ids = e_ids,
-                .type_ids = e_type,
-                .tokens = e_tok,
-                .offsets = e_off,
-                .special_token_mask = e_spec,
-                .attention_mask = e_attn,
-                .words = null,
-                .overflowing = &.{},
-                .owns_token_strs = true,
-            };
+            out[d] = try self.materialise(&view, d);
+            built = d + 1;
         }
         return out;
+    }
+
+    /// one owned Encoding from the view (src/encoding.zig:246-294 + 385-463); frees its partial arrays on failure
+    fn materialise(self: *Self, view: *const BatchView, d: usize) !lib.Encoding {
+        const a = self.base.allocator;
+        const n = view.slots(d);
+        if (n == 0) return lib.Encoding.empty(a);
+        const e_ids = try a.alloc(u32, n);
+        errdefer a.free(e_ids);
+        const e_type = try a.alloc(u32, n);
+        errdefer a.free(e_type);
+        const e_off2 = try a.alloc(u32, 2 * n);
+        defer a.free(e_off2);
+        const e_off = try a.alloc(lib.Offset, n);
+        errdefer a.free(e_off);
+        const e_spec = try a.alloc(u32, n);
+        errdefer a.free(e_spec);
+        const e_attn = try a.alloc(u32, n);
+        errdefer a.free(e_attn);
+        const e_tok = try a.alloc([]const u8, n);
+        var n_tok: usize = 0;
+        errdefer {
+            for (e_tok[0..n_tok]) |t| a.free(t);
+            a.free(e_tok);
+        }
+        try view.expandInto(d, e_ids, e_off2, e_attn, e_type, e_spec);
+        for (0..n) |i| {
+            e_off[i] = lib.Offset.init(e_off2[2 * i], e_off2[2 * i + 1]);
+            // tokens[i] = the MODEL's vocab_r[id] (bpe.zig:258, wordpiece.zig:200-205); pad slots carry pad_token (encoding.zig:410,421)
+            const str: []const u8 = if (e_attn[i] == 0)
+                (if (self.base.padding) |pd| pd.pad_token else "[PAD]")
+            else
+                (self.base.model_impl.idToToken(e_ids[i]) orelse "");
+            e_tok[i] = try a.dupe(u8, str);
+            n_tok = i + 1;
+        }
+        return .{
+            .allocator = a,
+            .ids = e_ids,
+            .type_ids = e_type,
+            .tokens = e_tok,
+            .offsets = e_off,
+            .special_token_mask = e_spec,
+            .attention_mask = e_attn,
+            .words = null,
+            .overflowing = &.{},
+            .owns_token_strs = true,
+        };
     }
 };
 
