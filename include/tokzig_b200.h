@@ -102,6 +102,9 @@ typedef struct tkz_model_desc {
 /* Ids as u16 in tkz_batch_result.ids16 instead of u32 in ids: honoured when every id of the uploaded vocabulary is below
  * 65536 (GPT-2- and BERT-sized vocabularies), ignored otherwise: exactly one of ids / ids16 is non-NULL. */
 #define TKZ_OUT_IDS_U16 64u
+/* SpanToken records (src/token.zig:11-76): 16 bytes per slot {id u32, start u32, end u32, type_id u8, flags u8, pad u16} in
+ * tkz_batch_result.span_tokens; flags bit 2 = is_padding (SpanToken.initPadding), the other flags are never set by the path */
+#define TKZ_OUT_SPAN_TOKENS 128u
 
 /* Per-call knobs = the public fields Tokenizer.truncation / Tokenizer.padding (src/lib.zig:41-42,149-157;
  * src/types.zig:39-45,55-59).  stride / strategy / pad_token are ignored by the reference's encode. */
@@ -114,6 +117,13 @@ typedef struct tkz_encode_params {
     uint32_t pad_type_id;
     int32_t pad_left;
     uint32_t outputs;                   /* TKZ_OUT_* mask; 0 means TKZ_OUT_ALL */
+    /* FastTokenizer.encode (src/lib.zig:356-422) instead of Tokenizer.encode: BPE.tokenizeFast / WordPiece.tokenizeFast
+     * (heap pop order, stale entries, src/model/bpe.zig:285-430, src/model/wordpiece.zig:233-301) with the caps of the arena
+     * (src/arena.zig:140-245): at most fast_max_sequence_length symbols per pre-token and / 4 pre-tokens per document, at most
+     * fast_max_tokens tokens per document; truncation / padding above are ignored (FastTokenizer.encode applies none). */
+    int32_t fast;
+    uint32_t fast_max_sequence_length;  /* ArenaConfig.max_sequence_length (default 8192); 4 .. 65535 */
+    uint32_t fast_max_tokens;           /* ArenaConfig.max_tokens (default 512) */
 } tkz_encode_params;
 
 /* CSR batch encoding = n_docs Encodings (src/encoding.zig:231-243) back to back.  Document d owns slots
@@ -133,6 +143,7 @@ typedef struct tkz_batch_result {
     int64_t err_doc;                    /* document index of the first error, -1 if none */
     const uint16_t* offsets_packed;     /* n_tokens x (start | end << 8), see TKZ_OUT_OFFSETS_PACKED; padding slots are 0 */
     const uint16_t* ids16;              /* n_tokens, see TKZ_OUT_IDS_U16 */
+    const uint32_t* span_tokens;        /* 4 u32 per slot, see TKZ_OUT_SPAN_TOKENS */
 } tkz_batch_result;
 
 /* counters of the last encode (FastTokenizer.arenaMemoryUsage analogue, src/lib.zig:451-453) */
@@ -284,6 +295,12 @@ int tkzh_set_pretokenizer(tkzh_tokenizer* t, const int32_t* kinds, int32_t n);
  * accepted and has no effect: every post-processor of the reference is a no-op (src/config.zig:551-555). */
 int tkzh_encode_batch(tkzh_tokenizer* t, const uint8_t* text, const uint64_t* doc_off, uint64_t n_docs,
                       int add_special_tokens, uint32_t outputs, tkz_batch_result* out);
+
+/* FastTokenizer.encode src/lib.zig:356-422 for a batch (FastTokenizerOptions.arena_config = {max_sequence_length, max_tokens},
+ * src/lib.zig:240-246; 0 = the defaults 8192 / 512).  The result is the SpanEncoding of every document back to back: ids,
+ * offsets, attention_mask 1, type_ids 0 and, with TKZ_OUT_SPAN_TOKENS, the 16-byte SpanToken records. */
+int tkzh_encode_batch_fast(tkzh_tokenizer* t, const uint8_t* text, const uint64_t* doc_off, uint64_t n_docs,
+                           uint32_t max_sequence_length, uint32_t max_tokens, uint32_t outputs, tkz_batch_result* out);
 
 /* Tokenizer.decode  src/lib.zig:163-189 with the config-path decoders (src/config.zig:459-530): host side only (the
  * decode direction is outside the GPU hot path).  *out points into the tokenizer and is valid until the next decode. */

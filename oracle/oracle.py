@@ -322,6 +322,10 @@ class OracleTokenizer:
         except Exception:
             pass
 
+    def set_fast_options(self, max_sequence_length: int = 8192, max_tokens: int = 512):
+        """FastTokenizerOptions.arena_config (lib.zig:240-246, arena.zig:140-145) for algo 2"""
+        self._L.orc_model_set_fast_options(self._m, max_sequence_length, max_tokens)
+
     def _sync(self):
         L, m = self._L, self._m
         L.orc_model_clear_pipeline(m)

@@ -961,3 +961,66 @@ def test_decode_batch_refuses_a_batch_that_decodes_to_4gib_or_more():
     out = t.decode_batch([[1] * 40, [2, 1, 2]])
     assert len(out[0]) == 40 << 20 and out[1] == b"ab" + big.encode() + b"ab"
     t.close()
+
+
+# ----------------------------------------------------------------------------- FastTokenizer mode (tkz_fast.cuh)
+@pytest.mark.parametrize("c", [c for c in CASES if c["kind"] in ("json", "model") and 2 in c["algos"]], ids=lambda c: c["id"])
+def test_reference_fast_kats_on_gpu(c):
+    """the reference's own known answers for tokenizeFast / FastTokenizer (bpe.zig:709-866, wordpiece.zig tests, lib.zig:957-1174)"""
+    js = c["json"] if c["kind"] == "json" else model_case_to_json(c["model"])
+    t = tz.Tokenizer.from_json(js, device=0)
+    text = bytes.fromhex(c["input_hex"])
+    if c.get("error"):
+        t.close()
+        pytest.skip("error cases belong to Tokenizer.encode (the arena variants do not raise)")
+    e = t.encode_fast_batch([text])
+    check_encoding_against_case(c, e.ids, e.offsets, e.attention_mask, e.type_ids, np.zeros(len(e.ids), np.uint32))
+    t.close()
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_fast_mode_random_against_the_arena_oracle(seed):
+    """FastTokenizer.encode on the GPU == the oracle's restatement of the arena variants (algo 2): heap pop order with equal
+    ranks, stale entries merged at their old priority, improper / aliased / degenerate tables, the symbol / pre-token / token
+    caps of the arena (small values so that they bind), the WordPiece word that crosses max_tokens before it turns out bad,
+    and the 16-byte SpanToken records."""
+    rng = random.Random(8100 + seed)
+    if seed % 3 == 2:
+        js, alpha = rand_wp_json(rng, n_words=rng.choice([20, 80]), with_unk=seed % 6 != 5)
+    else:
+        js, alpha = rand_bpe_json(rng, n_merges=rng.choice([5, 40, 120]), improper=[0.0, 0.3][seed % 2], degenerate=[0.0, 0.1][(seed // 2) % 2],
+                                  alias=[0.0, 0.2][(seed // 4) % 2], pretok=[None, "Whitespace"][(seed // 3) % 2], unk="<unk>" if seed % 5 == 0 else None)
+    t = tz.Tokenizer.from_json(js, device=0)
+    o = orc.OracleTokenizer.from_json(js)
+    docs = rand_docs(rng, alpha, 300, max_len=120) + [b"", b"aaaaa", b"dabc", b"a" * 300, (b"ab " * 200)]
+    for max_seq, max_tok in ((8192, 512), (64, 7), (16, 3), (400, 1), (8, 100)):
+        o.set_fast_options(max_seq, max_tok)
+        ref = o.encode_batch(docs, algo=2, threads=4)
+        got = t.encode_fast_batch(docs, max_sequence_length=max_seq, max_tokens=max_tok)
+        assert np.array_equal(got.doc_tok_off, ref.doc_tok_off), f"seed {seed} caps {max_seq}/{max_tok}: doc_tok_off"
+        assert np.array_equal(got.ids, ref.ids), f"seed {seed} caps {max_seq}/{max_tok}: ids"
+        assert np.array_equal(got.offsets, ref.offsets), f"seed {seed} caps {max_seq}/{max_tok}: offsets"
+        assert np.all(got.attention_mask == 1) and np.all(got.type_ids == 0)
+        sp = got.span_tokens
+        assert np.array_equal(sp[:, 0], ref.ids) and np.array_equal(sp[:, 1:3], ref.offsets) and np.all(sp[:, 3] == 0)
+    t.close()
+
+
+def test_span_token_records_of_the_padded_encoding():
+    """TKZ_OUT_SPAN_TOKENS next to the CSR arrays of Tokenizer.encode: real slots {id, start, end, 0}, padding slots
+    SpanToken.initPadding(pad_id) = {pad_id, 0, 0, flags.is_padding} (token.zig:52-54)."""
+    rng = random.Random(3)
+    js, alpha = rand_wp_json(rng)
+    t, o = pair(js)
+    t.truncation = {"max_length": 6}; o.truncation = 6
+    pad = {"length": 9, "pad_id": 5, "pad_type_id": 2, "direction": "right"}
+    t.padding = pad; o.padding = pad
+    docs = rand_docs(rng, alpha, 200, max_len=60)
+    got = t.encode_batch(docs, outputs=tz.OUT_ALL | tz.OUT_SPAN_TOKENS)
+    ref = o.encode_batch(docs)
+    assert_same(got, ref)
+    sp = got.span_tokens
+    real = ref.attention_mask == 1
+    assert np.array_equal(sp[:, 0], ref.ids) and np.array_equal(sp[:, 1:3], ref.offsets)
+    assert np.all(sp[real, 3] == 0) and np.all(sp[~real, 3] == 0x0400)
+    t.close()

@@ -89,8 +89,9 @@ def literal_rounds(t: Table, word):
                 i += 1
 
 
-def windowed_schedule(t: Table, word, win, walk=4, local_aa=True):
-    """The kernels' steps.  Returns (tokens, number of steps)."""
+def windowed_schedule(t: Table, word, win, walk=4, local_aa=True, lazy_long_runs=False):
+    """The kernels' steps.  Returns (tokens, number of steps).  lazy_long_runs: an equal-symbol run beyond the walk limit is paired
+    up only in a step in which nothing else can merge (bpe_block_kernel: the word's minimum rank is only computed then)."""
     w = list(word)
     steps = 0
     while True:
@@ -100,6 +101,7 @@ def windowed_schedule(t: Table, word, win, walk=4, local_aa=True):
             return w, steps
         gmin = min(rk)
         heads = [False] * n
+        late = []
         for i in range(n - 1):
             r = rk[i]
             if r == NONE:
@@ -120,7 +122,13 @@ def windowed_schedule(t: Table, word, win, walk=4, local_aa=True):
                     lo, hi = max(0, s - wl), min(n - 2, e - 2 + wr)
                     heads[i] = all(rk[j] >= r for j in range(lo, s)) and all(rk[j] >= r for j in range(e - 1, hi + 1))
             elif r == gmin:                              # the reference round of the word: every run of A pairs up from its start
-                heads[i] = (i - s) % 2 == 0
+                if lazy_long_runs:
+                    late.append((i, (i - s) % 2 == 0))
+                else:
+                    heads[i] = (i - s) % 2 == 0
+        if lazy_long_runs and not any(heads):
+            for i, h in late:
+                heads[i] = h
         assert any(heads), "the schedule must make progress (the global minimum always qualifies)"
         assert not any(heads[i] and heads[i + 1] for i in range(n - 1)), "two heads never overlap"
         out, i = [], 0
@@ -162,6 +170,11 @@ def test_windowed_schedule_equals_the_reference_rounds(seed):
                 assert got == lit, f"seed {seed} word {k} {name} windows, walk limit {walk}"
             got, _ = windowed_schedule(t, w, win, local_aa=False)
             assert got == lit, f"seed {seed} word {k} {name} windows, (A,A) only at the word's minimum"
+            for walk in (0, 2):
+                got, _ = windowed_schedule(t, w, win, walk=walk, lazy_long_runs=True)
+                assert got == lit, f"seed {seed} word {k} {name} windows, walk limit {walk}, long runs only when nothing else merges"
+            got, _ = windowed_schedule(t, w, win, local_aa=False, lazy_long_runs=True)
+            assert got == lit, f"seed {seed} word {k} {name} windows, (A,A) only when nothing else merges"
 
 
 def test_why_windows_are_needed():

@@ -30,6 +30,7 @@ _ERR_NAMES = {ERR_OOM: "OutOfMemory", ERR_MISSING_UNK: "MissingUnkToken", ERR_IN
               ERR_INVALID_VOCAB_ENTRY: "InvalidVocabEntry", ERR_IO: "IoError"}
 
 OUT_IDS, OUT_OFFSETS, OUT_ATTENTION, OUT_TYPE_IDS, OUT_SPECIAL, OUT_ALL = 1, 2, 4, 8, 16, 31
+OUT_SPAN_TOKENS = 128            # 16-byte SpanToken records (src/token.zig:19-33)
 OUT_IDS_U16 = 64                 # ids as u16 (ids16) when every id of the vocabulary is < 65536
 OUT_OFFSETS_PACKED = 32          # one u16 per token (start | end << 8); falls back to OUT_OFFSETS when a pre-token has >= 256 bytes
 NORM_CFG_LOWER, NORM_BERT_STRUCT, NORM_LOWER_STRUCT = 1, 2, 3
@@ -77,6 +78,9 @@ class EncodeParams(C.Structure):
         ("pad_type_id", C.c_uint32),
         ("pad_left", C.c_int32),
         ("outputs", C.c_uint32),
+        ("fast", C.c_int32),
+        ("fast_max_sequence_length", C.c_uint32),
+        ("fast_max_tokens", C.c_uint32),
     ]
 
 
@@ -94,6 +98,7 @@ class BatchResult(C.Structure):
         ("err_doc", C.c_int64),
         ("offsets_packed", C.c_void_p),
         ("ids16", C.c_void_p),
+        ("span_tokens", C.c_void_p),
     ]
 
 
@@ -131,7 +136,7 @@ EXPORTED_SYMBOLS = [
     "tkzm_document_costs", "tkzm_encode_batch_compact",
     "tkz_encode_batch_device", "tkz_encode_batch_compact", "tkz_compact_slots", "tkz_compact_expand", "tkz_decode_upload", "tkz_decode_batch",
     "tkzh_from_json", "tkzh_from_file", "tkzh_free", "tkzh_last_error", "tkzh_ctx", "tkzh_set_truncation", "tkzh_set_padding",
-    "tkzh_set_normalizer", "tkzh_set_pretokenizer", "tkzh_encode_batch", "tkzh_decode", "tkzh_decode_batch", "tkzh_get_vocab_size", "tkzh_token_to_id",
+    "tkzh_set_normalizer", "tkzh_set_pretokenizer", "tkzh_encode_batch", "tkzh_encode_batch_fast", "tkzh_decode", "tkzh_decode_batch", "tkzh_get_vocab_size", "tkzh_token_to_id",
     "tkzh_id_to_token", "tkzh_model_id_to_token", "tkzh_add_special_tokens", "tkzh_model_vocab_count", "tkzh_merge_count", "tkzh_has_normalizer",
     "tkzh_has_pretokenizer", "tkzh_has_post_processor", "tkzh_added_token_count", "tkzh_added_token", "tkzh_model_desc",
 ]
@@ -186,6 +191,7 @@ def lib():
     L.tkzh_set_normalizer.argtypes = [vp, vp, vp, C.c_int32]
     L.tkzh_set_pretokenizer.argtypes = [vp, vp, C.c_int32]
     L.tkzh_encode_batch.argtypes = [vp, vp, vp, u64, i32, u32, C.POINTER(BatchResult)]
+    L.tkzh_encode_batch_fast.argtypes = [vp, vp, vp, u64, u32, u32, u32, C.POINTER(BatchResult)]
     L.tkzh_decode.argtypes = [vp, vp, u64, i32, C.POINTER(vp), C.POINTER(u64)]
     L.tkzh_decode_batch.argtypes = [vp, vp, vp, u64, i32, C.POINTER(DecodeResult)]
     L.tkz_decode_upload.argtypes = [vp, vp]
@@ -252,6 +258,7 @@ class BatchEncoding:
     special_tokens_mask: Optional[np.ndarray]
     n_real_tokens: int = 0
     offsets_packed: Optional[np.ndarray] = None     # u16 per token: start | end << 8 (OUT_OFFSETS_PACKED)
+    span_tokens: Optional[np.ndarray] = None        # (n, 4) u32: id, start, end, type_id | flags << 8 (OUT_SPAN_TOKENS)
 
     def __len__(self):
         return len(self.doc_tok_off) - 1
@@ -278,6 +285,7 @@ def _result_to_batch(r: BatchResult) -> BatchEncoding:
         special_tokens_mask=_copy(r.special_tokens_mask, T, np.uint32) if r.special_tokens_mask else None,
         n_real_tokens=int(r.n_real_tokens),
         offsets_packed=_copy(r.offsets_packed, T, np.uint16) if r.offsets_packed else None,
+        span_tokens=_copy(r.span_tokens, 4 * T, np.uint32).reshape(-1, 4) if r.span_tokens else None,
     )
 
 
@@ -485,6 +493,23 @@ class Tokenizer:
         if rc != OK:
             raise TokzigError(rc, (self._L.tkz_last_error(self.context_handle()) or b"").decode(), int(r.err_doc))
         return r
+
+    def encode_fast_packed(self, text: np.ndarray, doc_off: np.ndarray, max_sequence_length: int = 8192, max_tokens: int = 512,
+                           outputs: int = OUT_IDS | OUT_OFFSETS | OUT_ATTENTION | OUT_TYPE_IDS | OUT_SPAN_TOKENS) -> BatchEncoding:
+        """FastTokenizer.encode (src/lib.zig:356-422) for a batch: arena variants of the models and the arena's caps
+        (FastTokenizerOptions.arena_config, src/lib.zig:240-246); truncation / padding fields are not applied."""
+        text = np.ascontiguousarray(text, dtype=np.uint8)
+        doc_off = np.ascontiguousarray(doc_off, dtype=np.uint64)
+        r = BatchResult()
+        rc = self._L.tkzh_encode_batch_fast(self._h, text.ctypes.data if text.size else None, doc_off.ctypes.data, len(doc_off) - 1,
+                                            max_sequence_length, max_tokens, outputs, C.byref(r))
+        if rc != OK:
+            raise TokzigError(rc, (self._L.tkzh_last_error(self._h) or b"").decode(), int(r.err_doc))
+        return _result_to_batch(r)
+
+    def encode_fast_batch(self, docs: Sequence, **kw) -> BatchEncoding:
+        text, off = pack_docs([d if isinstance(d, (bytes, bytearray)) else d.encode("utf-8") for d in docs])
+        return self.encode_fast_packed(text, off, **kw)
 
     def encode_batch(self, docs: Sequence, add_special_tokens: bool = True, outputs: int = OUT_ALL) -> BatchEncoding:
         text, off = pack_docs([d if isinstance(d, (bytes, bytearray)) else d.encode("utf-8") for d in docs])

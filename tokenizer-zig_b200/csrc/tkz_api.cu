@@ -22,6 +22,7 @@
 #include "tkz_common.cuh"
 #include "tkz_decode.cuh"
 #include "tkz_emit.cuh"
+#include "tkz_fast.cuh"
 #include "tkz_slices.cuh"
 #include "tkz_scan.cuh"
 #include "tkz_split.cuh"
@@ -58,7 +59,7 @@ struct tkz_ctx {
     DevBuf a_text, a_doc_off, a_norm_text, a_norm_doc_off, a_chunk, a_tiles, a_word_start, a_word_end, a_word_doc, a_doc_word_off,
         a_word_ntok, a_pool_id, a_pool_s, a_pool_e, a_pool_rk, a_scan_tmp, a_ctrl;
     // output arrays, double-buffered so that the D2H copy of one chunk overlaps the kernels of the next (tkz_encode_batch)
-    struct OutSet { DevBuf doc_tok_off, ids, off, attn, type, special, off16, ids16; } outs[2];
+    struct OutSet { DevBuf doc_tok_off, ids, off, attn, type, special, off16, ids16, spans; } outs[2];
     int out_sel = 0;
     OutSet& O() { return outs[out_sel]; }
     DevBuf in_text[2], in_doc_off[2];
@@ -84,7 +85,8 @@ struct tkz_ctx {
     uint64_t tw_uniq_hist = 0;            // most unique words seen in one batch: sizes the next batch's word table
     uint64_t tw_upool_hist = 0;           // most token records used by one batch
     double tw_tok_per_byte = 0.0;         // densest batch so far: sizes the token stream
-    HostBuf h_ctrl, h_doc_tok_off, h_ids, h_off, h_attn, h_type, h_special, h_off16, h_ids16;
+    HostBuf h_ctrl, h_doc_tok_off, h_ids, h_off, h_attn, h_type, h_special, h_off16, h_ids16, h_spans;
+    DevBuf a_fast_heap, a_word_aux;       // FastTokenizer mode (tkz_fast.cuh)
     bool ids16_ok = false;                // every id the model can emit is below 65536 (TKZ_OUT_IDS_U16)
     // decode direction (tkz_decode.cuh)
     bool has_decode = false;
@@ -290,13 +292,13 @@ extern "C" void tkz_ctx_destroy(tkz_ctx* ctx) {
                       &ctx->in_doc_off[1], &ctx->a_ctrl, &ctx->a_long_start, &ctx->a_long_end, &ctx->a_long_ntok, &ctx->a_long_slice, &ctx->a_long_ins,
                       &ctx->a_tile_ntok, &ctx->a_tile_ntok_inline, &ctx->a_tile_tok_off, &ctx->a_tile_long, &ctx->a_doc_tok_local,
                       &ctx->a_doc_tok_start, &ctx->a_doc_real, &ctx->a_upool, &ctx->a_tile_doc_lo, &ctx->a_g_first, &ctx->a_g_win, &ctx->a_g_flag, &ctx->a_big,
-                      &ctx->a_wtable, &ctx->a_lscratch, &ctx->a_tok_id,
+                      &ctx->a_wtable, &ctx->a_lscratch, &ctx->a_tok_id, &ctx->a_fast_heap, &ctx->a_word_aux,
                       &ctx->a_huge_w, &ctx->a_huge_base, &ctx->a_huge_done, &ctx->a_grid_state, &ctx->a_grid_words,
                       &ctx->t_dec_bytes, &ctx->t_dec_off, &ctx->t_dec_special, &ctx->a_dec_ids, &ctx->a_dec_seq_off, &ctx->a_dec_len, &ctx->a_dec_raw,
                       &ctx->a_dec_out, &ctx->a_dec_olen, &ctx->a_dec_boff};
-    for (auto& os : ctx->outs) for (DevBuf* b : {&os.doc_tok_off, &os.ids, &os.off, &os.attn, &os.type, &os.special, &os.off16, &os.ids16}) release(*b);
+    for (auto& os : ctx->outs) for (DevBuf* b : {&os.doc_tok_off, &os.ids, &os.off, &os.attn, &os.type, &os.special, &os.off16, &os.ids16, &os.spans}) release(*b);
     for (DevBuf* b : bufs) release(*b);
-    HostBuf* hb[] = {&ctx->h_ctrl, &ctx->h_doc_tok_off, &ctx->h_ids, &ctx->h_off, &ctx->h_attn, &ctx->h_type, &ctx->h_special, &ctx->h_off16, &ctx->h_ids16,
+    HostBuf* hb[] = {&ctx->h_ctrl, &ctx->h_doc_tok_off, &ctx->h_ids, &ctx->h_off, &ctx->h_attn, &ctx->h_type, &ctx->h_special, &ctx->h_off16, &ctx->h_ids16, &ctx->h_spans,
                      &ctx->h_doc_stage[0], &ctx->h_doc_stage[1], &ctx->h_dec_bytes, &ctx->h_dec_off};
     for (HostBuf* b : hb) release_host(*b);
     if (ctx->s_h2d) cudaStreamDestroy(ctx->s_h2d);
@@ -834,8 +836,9 @@ int encode_slices(tkz_ctx* ctx, const DevModel& m, const ClassRanges& cr, const 
     if (P.outputs & TKZ_OUT_TYPE_IDS) TRY(ensure(ctx, ctx->O().type, (T + 4) * 4));
     if (P.outputs & TKZ_OUT_SPECIAL) TRY(ensure(ctx, ctx->O().special, (T + 4) * 4));
     if (P.outputs & TKZ_OUT_OFFSETS_PACKED) TRY(ensure(ctx, ctx->O().off16, (T + 4) * 2));
+    if (P.outputs & TKZ_OUT_SPAN_TOKENS) TRY(ensure(ctx, ctx->O().spans, (T + 4) * 16));
     EmitOut eo{(uint32_t*)ctx->O().ids.p, (uint32_t*)ctx->O().off.p, (uint32_t*)ctx->O().attn.p, (uint32_t*)ctx->O().type.p,
-               (uint32_t*)ctx->O().special.p, (uint16_t*)ctx->O().off16.p, (uint16_t*)ctx->O().ids16.p};
+               (uint32_t*)ctx->O().special.p, (uint16_t*)ctx->O().off16.p, (uint16_t*)ctx->O().ids16.p, (uint4*)ctx->O().spans.p};
     const uint32_t big_cap = (uint32_t)(N / EMIT_BIG + 16);
     TRY(ensure(ctx, ctx->a_big, (size_t)big_cap * sizeof(uint4)));
     SliceEmitArgs ea{};
@@ -877,6 +880,7 @@ int encode_slices(tkz_ctx* ctx, const DevModel& m, const ClassRanges& cr, const 
     out->type_ids = (P.outputs & TKZ_OUT_TYPE_IDS) ? eo.type_ids : nullptr;
     out->special_tokens_mask = (P.outputs & TKZ_OUT_SPECIAL) ? eo.special : nullptr;
     out->offsets_packed = (P.outputs & TKZ_OUT_OFFSETS_PACKED) ? eo.offsets16 : nullptr;
+    out->span_tokens = (P.outputs & TKZ_OUT_SPAN_TOKENS) ? (const uint32_t*)eo.spans : nullptr;
     return TKZ_OK;
 }
 
@@ -895,6 +899,13 @@ int encode_device_impl(tkz_ctx* ctx, const uint8_t* d_text, const uint64_t* d_do
     if (params) P = *params;
     if (P.outputs == 0) P.outputs = TKZ_OUT_ALL;
     P.outputs |= TKZ_OUT_IDS;
+    if (P.fast) {
+        // FastTokenizer.encode: no truncation / padding parameters; the token buffer of the arena caps every document
+        if (P.fast_max_sequence_length == 0) P.fast_max_sequence_length = 8192;        // ArenaConfig defaults (arena.zig:140-145)
+        if (P.fast_max_tokens == 0) P.fast_max_tokens = 512;
+        if (P.fast_max_sequence_length < 4 || P.fast_max_sequence_length > 65535) { ctx->err = "fast_max_sequence_length must be 4 .. 65535 (16-bit symbol indices, arena.zig:17-42)"; return TKZ_ERR_INVALID_ARG; }
+        P.has_truncation = 1; P.max_length = P.fast_max_tokens; P.has_padding = 0;
+    }
     if ((P.outputs & TKZ_OUT_IDS_U16) && (!ctx->ids16_ok || (P.has_padding && P.pad_id > 0xFFFFu))) P.outputs &= ~TKZ_OUT_IDS_U16;
     const uint32_t nd = (uint32_t)n_docs;
     DevModel m = ctx->dm;
@@ -933,7 +944,7 @@ int encode_device_impl(tkz_ctx* ctx, const uint8_t* d_text, const uint64_t* d_do
     // ---- slice pipeline (tkz_slices.cuh) whenever there is a pre-tokenizer; TKZ_NO_DEDUP=1 keeps the per-occurrence
     //      pipeline below for A/B tests
     ctx->stats.path = 0;
-    if (m.has_pretok && ctx->use_dedup) {
+    if (m.has_pretok && ctx->use_dedup && !P.fast) {
         const ClassRanges& cr = ctx->dm.norm_has_drop ? ctx->cr_post : ctx->cr;      // (K0 ran: the text is already normalised)
         int rc = encode_slices(ctx, m, cr, d_text, d_doc_off, nd, N, P, false, out, launches);
         if (rc != TKZ_RETRY_WORST) return rc;
@@ -986,7 +997,20 @@ int encode_device_impl(tkz_ctx* ctx, const uint8_t* d_text, const uint64_t* d_do
     TRY(ensure(ctx, ctx->a_pool_e, N * 4));
     uint32_t* word_ntok = (uint32_t*)ctx->a_word_ntok.p;
     unsigned int* work_counter = (unsigned int*)(ctrl + 1);
-    if (nw) {
+    if (nw && P.fast) {
+        // FastTokenizer mode: one thread per pre-token replays tokenizeFast (tkz_fast.cuh)
+        TRY(ensure(ctx, ctx->a_pool_rk, N * 4));
+        TRY(ensure(ctx, ctx->a_fast_heap, N * 16 + 64));
+        TRY(ensure(ctx, ctx->a_word_aux, (W + 2) * 4));
+        FastArgs fa{d_text, word_start, word_end, word_doc, doc_word_off, nw, P.fast_max_sequence_length, P.fast_max_tokens,
+                    (uint32_t*)ctx->a_pool_id.p, (uint32_t*)ctx->a_pool_s.p, (uint32_t*)ctx->a_pool_e.p, (uint32_t*)ctx->a_pool_rk.p,
+                    (unsigned long long*)ctx->a_fast_heap.p, word_ntok, (uint32_t*)ctx->a_word_aux.p, ctrl};
+        if (m.kind == TKZ_MODEL_BPE) { fast_bpe_kernel<<<(nw + 127) / 128, 128, 0, st>>>(m, fa); launches++; }
+        else {
+            fast_wp_kernel<<<(nw + 127) / 128, 128, 0, st>>>(m, fa); launches++;
+            if (nd) { fast_wp_fix_kernel<<<(unsigned)(((uint64_t)nd * 32 + 255) / 256), 256, 0, st>>>(fa, nd); launches++; }
+        }
+    } else     if (nw) {
         if (m.kind == TKZ_MODEL_BPE) {
             len_class_count_kernel<<<128, 256, 0, st>>>(word_start, word_end, nw, nullptr, ctrl + 13); launches++;
             TRY(readback(ctx, hctrl + 24, ctrl + 13, 3 * 8));
@@ -1033,8 +1057,9 @@ int encode_device_impl(tkz_ctx* ctx, const uint8_t* d_text, const uint64_t* d_do
     if (P.outputs & TKZ_OUT_ATTENTION) TRY(ensure(ctx, ctx->O().attn, T * 4));
     if (P.outputs & TKZ_OUT_TYPE_IDS) TRY(ensure(ctx, ctx->O().type, T * 4));
     if (P.outputs & TKZ_OUT_SPECIAL) TRY(ensure(ctx, ctx->O().special, T * 4));
+    if (P.outputs & TKZ_OUT_SPAN_TOKENS) TRY(ensure(ctx, ctx->O().spans, T * 16));
     EmitOut eo{(uint32_t*)ctx->O().ids.p, (uint32_t*)ctx->O().off.p, (uint32_t*)ctx->O().attn.p, (uint32_t*)ctx->O().type.p,
-               (uint32_t*)ctx->O().special.p, nullptr, (uint16_t*)ctx->O().ids16.p};
+               (uint32_t*)ctx->O().special.p, nullptr, (uint16_t*)ctx->O().ids16.p, (uint4*)ctx->O().spans.p};
     if (nw) {
         const uint32_t big_cap = (uint32_t)(N / EMIT_BIG + 16);
         TRY(ensure(ctx, ctx->a_big, (size_t)big_cap * sizeof(uint4)));
@@ -1066,6 +1091,7 @@ int encode_device_impl(tkz_ctx* ctx, const uint8_t* d_text, const uint64_t* d_do
     out->type_ids = (P.outputs & TKZ_OUT_TYPE_IDS) ? eo.type_ids : nullptr;
     out->special_tokens_mask = (P.outputs & TKZ_OUT_SPECIAL) ? eo.special : nullptr;
     out->offsets_packed = nullptr;
+    out->span_tokens = (P.outputs & TKZ_OUT_SPAN_TOKENS) ? (const uint32_t*)eo.spans : nullptr;
     return TKZ_OK;
 }
 
@@ -1105,7 +1131,7 @@ int encode_host_single(tkz_ctx* ctx, const uint8_t* text, const uint64_t* doc_of
     int rc = encode_device_impl(ctx, (const uint8_t*)ctx->a_text.p, (const uint64_t*)ctx->a_doc_off.p, n_docs, N, params, &dev);
     *out = dev;
     out->doc_tok_off = nullptr; out->ids = nullptr; out->offsets = nullptr; out->attention_mask = nullptr; out->type_ids = nullptr;
-    out->special_tokens_mask = nullptr; out->offsets_packed = nullptr; out->ids16 = nullptr;
+    out->special_tokens_mask = nullptr; out->offsets_packed = nullptr; out->ids16 = nullptr; out->span_tokens = nullptr;
     if (rc != TKZ_OK) return rc;
     const uint64_t T = dev.n_tokens;
     cudaStream_t st = ctx->stream;
@@ -1116,7 +1142,8 @@ int encode_host_single(tkz_ctx* ctx, const uint8_t* text, const uint64_t* doc_of
         {dev.ids, &ctx->h_ids, (const void**)&out->ids, 4}, {dev.offsets, &ctx->h_off, (const void**)&out->offsets, 8},
         {dev.attention_mask, &ctx->h_attn, (const void**)&out->attention_mask, 4}, {dev.type_ids, &ctx->h_type, (const void**)&out->type_ids, 4},
         {dev.special_tokens_mask, &ctx->h_special, (const void**)&out->special_tokens_mask, 4},
-        {dev.offsets_packed, &ctx->h_off16, (const void**)&out->offsets_packed, 2}, {dev.ids16, &ctx->h_ids16, (const void**)&out->ids16, 2}};
+        {dev.offsets_packed, &ctx->h_off16, (const void**)&out->offsets_packed, 2}, {dev.ids16, &ctx->h_ids16, (const void**)&out->ids16, 2},
+        {dev.span_tokens, &ctx->h_spans, (const void**)&out->span_tokens, 16}};
     for (auto& c : cp) {
         if (!c.src) continue;
         TRY(ensure_host(ctx, *c.hb, T * c.elem));
@@ -1203,7 +1230,7 @@ restart:
         struct { const void* src; HostBuf* hb; size_t elem; } cp[] = {
             {dev.ids, &ctx->h_ids, 4}, {dev.offsets, &ctx->h_off, 8}, {dev.attention_mask, &ctx->h_attn, 4},
             {dev.type_ids, &ctx->h_type, 4}, {dev.special_tokens_mask, &ctx->h_special, 4}, {dev.offsets_packed, &ctx->h_off16, 2},
-            {dev.ids16, &ctx->h_ids16, 2}};
+            {dev.ids16, &ctx->h_ids16, 2}, {dev.span_tokens, &ctx->h_spans, 16}};
         for (auto& c : cp) {
             if (!c.src) continue;
             TRY(ensure_host_keep(ctx, *c.hb, est * c.elem, T_total * c.elem));
@@ -1231,6 +1258,7 @@ restart:
     out->type_ids = (outputs & TKZ_OUT_TYPE_IDS) ? (const uint32_t*)ctx->h_type.p : nullptr;
     out->special_tokens_mask = (outputs & TKZ_OUT_SPECIAL) ? (const uint32_t*)ctx->h_special.p : nullptr;
     out->offsets_packed = (outputs & TKZ_OUT_OFFSETS_PACKED) ? (const uint16_t*)ctx->h_off16.p : nullptr;
+    out->span_tokens = (outputs & TKZ_OUT_SPAN_TOKENS) ? (const uint32_t*)ctx->h_spans.p : nullptr;
     return TKZ_OK;
 }
 

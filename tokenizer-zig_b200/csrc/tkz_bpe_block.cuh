@@ -22,8 +22,8 @@
 //     within wr pairs from the pair of its last A on, where the entry's wl / wr also cover nsym(A) -- the span from which an A
 //     that would join the run and shift the pairing could still be built.  Then the run is the same run in round r and is
 //     paired up now, every second pair from its start;
-//   * longer runs wait for the step in which (A,A) is the minimum rank of the whole word: exactly the reference round (run
-//     starts by a block-wide max-scan; every other pair waits that step).
+//   * longer runs wait for a step in which nothing else can merge; (A,A) is then the minimum rank of the whole word and its runs
+//     are paired up by the reference round (run starts by a block-wide max-scan).  The word's minimum is only computed then.
 // Tables that are not proper (or have windows > 250) never reach this kernel: bpe_warp_kernel keeps the literal rounds.
 //
 // State per current symbol: id, index of its first initial symbol, cached rank + window of the pair with its right
@@ -170,56 +170,54 @@ __global__ void __launch_bounds__(NT, MINB) bpe_block_kernel(DevModel m, BlockBp
 
         // ---------------- merge steps
         while (n > 1) {
-            // global minimum rank of the word (equal-symbol pairs may only merge at the global minimum)
-            uint32_t lmin = TKZ_NONE;
-            for (uint32_t i = t; i + 1 < n; i += NT) { const uint32_t r = rk[i]; lmin = r < lmin ? r : lmin; }
-            const uint32_t gmin = block_min_u32<NT>(lmin, red);
-            if (gmin == TKZ_NONE) break;                                   // bpe.zig:232-234
-            // does the global-minimum pair consist of two equal symbols?  then run parity is needed
-            if (t == 0) s_cnt[2] = 0;
-            __syncthreads();
-            for (uint32_t i = t; i + 1 < n; i += NT) if (rk[i] == gmin && ids[i] == ids[i + 1]) s_cnt[2] = 1;
-            __syncthreads();
-            const bool gmin_same = s_cnt[2] != 0;
-            // A. heads
-            if (!gmin_same) {
-                for (uint32_t i = t; i < n; i += NT) {
-                    bool head = false;
-                    if (i + 1 < n) {
-                        const uint32_t r = rk[i];
-                        if (r != TKZ_NONE && ids[i] != ids[i + 1]) {
+            // A. heads by the window rules.  The word's minimum rank is NOT needed for them; it is only computed when no pair
+            // qualifies, which means the minimum is an equal-symbol pair in a run beyond the walk limit (the global minimum of any
+            // other kind always qualifies).  The runs of that pair are then paired up in a step of their own -- exactly the
+            // reference round for them; everything near them has been waiting (their rank is inside its window), everything else
+            // was free to go first (tests/test_windowed_schedule_model.py: lazy_long_runs).
+            bool any_ranked = false, any_head = false;
+            for (uint32_t i = t; i < n; i += NT) {
+                bool head = false;
+                if (i + 1 < n) {
+                    const uint32_t r = rk[i];
+                    any_ranked |= r != TKZ_NONE;
+                    if (r != TKZ_NONE && ids[i] != ids[i + 1]) {
+                        const uint32_t wv = win[i], wl = wv & 0xFFu, wr = wv >> 8;
+                        const uint32_t lo = i > wl ? i - wl : 0;
+                        uint32_t hi = i + wr; if (hi > n - 2) hi = n - 2;
+                        head = true;
+                        for (uint32_t j = lo; j < i && head; j++) head = rk[j] >= r;
+                        for (uint32_t j = i + 1; j <= hi && head; j++) head = rk[j] >= r;
+                        // an equal rank inside the window is another occurrence of the same pair: it cannot overlap (a != b)
+                    } else if (r != TKZ_NONE && m.local_aa) {
+                        // (A, A): the window goes around the whole run of A (its extent is part of the decision: the run
+                        // pairs up from its start).  Nothing of lower rank left of the run within wl pairs, nor from the pair
+                        // of its last A on within wr pairs => no A of the run is consumed and no A joins it before round r
+                        // (the entry's window also covers nsym(A), see tkz_api.cu), so the run pairs up NOW as it will then.
+                        const uint32_t x = ids[i];
+                        uint32_t s0 = i, e0 = i + 2, c = 0;
+                        while (c < BB_RUN_WALK && s0 > 0 && ids[s0 - 1] == x) { s0--; c++; }
+                        c = 0;
+                        while (c < BB_RUN_WALK && e0 < n && ids[e0] == x) { e0++; c++; }
+                        if (!(s0 > 0 && ids[s0 - 1] == x) && !(e0 < n && ids[e0] == x) && ((i - s0) & 1u) == 0) {
                             const uint32_t wv = win[i], wl = wv & 0xFFu, wr = wv >> 8;
-                            const uint32_t lo = i > wl ? i - wl : 0;
-                            uint32_t hi = i + wr; if (hi > n - 2) hi = n - 2;
+                            const uint32_t lo = s0 > wl ? s0 - wl : 0;
+                            uint32_t hi = e0 - 2 + wr; if (hi > n - 2) hi = n - 2;
                             head = true;
-                            for (uint32_t j = lo; j < i && head; j++) head = rk[j] >= r;
-                            for (uint32_t j = i + 1; j <= hi && head; j++) head = rk[j] >= r;
-                            // an equal rank inside the window is another occurrence of the same pair: it cannot overlap (a != b)
-                        } else if (r != TKZ_NONE && m.local_aa) {
-                            // (A, A): the window goes around the whole run of A (its extent is part of the decision: the run
-                            // pairs up from its start).  Nothing of lower rank left of the run within wl pairs, nor from the pair
-                            // of its last A on within wr pairs => no A of the run is consumed and no A joins it before round r
-                            // (the entry's window also covers nsym(A), see tkz_api.cu), so the run pairs up NOW as it will then.
-                            // Runs longer than BB_RUN_WALK wait for the round in which (A, A) is the word's minimum (below).
-                            const uint32_t x = ids[i];
-                            uint32_t s0 = i, e0 = i + 2, c = 0;
-                            while (c < BB_RUN_WALK && s0 > 0 && ids[s0 - 1] == x) { s0--; c++; }
-                            c = 0;
-                            while (c < BB_RUN_WALK && e0 < n && ids[e0] == x) { e0++; c++; }
-                            if (!(s0 > 0 && ids[s0 - 1] == x) && !(e0 < n && ids[e0] == x) && ((i - s0) & 1u) == 0) {
-                                const uint32_t wv = win[i], wl = wv & 0xFFu, wr = wv >> 8;
-                                const uint32_t lo = s0 > wl ? s0 - wl : 0;
-                                uint32_t hi = e0 - 2 + wr; if (hi > n - 2) hi = n - 2;
-                                head = true;
-                                for (uint32_t j = s0; j > lo && head;) { --j; head = rk[j] >= r; }
-                                for (uint32_t j = e0 - 1; j <= hi && head; j++) head = rk[j] >= r;
-                            }
+                            for (uint32_t j = s0; j > lo && head;) { --j; head = rk[j] >= r; }
+                            for (uint32_t j = e0 - 1; j <= hi && head; j++) head = rk[j] >= r;
                         }
                     }
-                    flag[i] = head ? 1 : 0;
                 }
-            } else {
-                // the reference round for (A,A): every run of A pairs up from its start; all other pairs wait this step
+                flag[i] = head ? 1 : 0;
+                any_head |= head;
+            }
+            if (!__syncthreads_or(any_ranked)) break;                      // bpe.zig:232-234: no pair has a rank
+            if (!__syncthreads_or(any_head)) {
+                // the reference round for the word's minimum-rank pair (A, A): every run of A pairs up from its start
+                uint32_t lmin = TKZ_NONE;
+                for (uint32_t i = t; i + 1 < n; i += NT) { const uint32_t r = rk[i]; lmin = r < lmin ? r : lmin; }
+                const uint32_t gmin = block_min_u32<NT>(lmin, red);
                 uint32_t A = 0;
                 if (t == 0) s_cnt[3] = TKZ_NONE;
                 __syncthreads();

@@ -37,7 +37,8 @@ __global__ void doc_len_kernel(EmitParams p, const uint32_t* __restrict__ word_t
 
 struct EmitOut { uint32_t* ids; uint32_t* offsets; uint32_t* attention; uint32_t* type_ids; uint32_t* special;
                  uint16_t* offsets16;        // one u16 per token (start | end << 8), only when every pre-token is < 256 bytes
-                 uint16_t* ids16; };         // ids as u16 instead of `ids` (outputs & 64: every id of the vocabulary is < 65536)
+                 uint16_t* ids16;            // ids as u16 instead of `ids` (outputs & 64: every id of the vocabulary is < 65536)
+                 uint4* spans; };            // SpanToken records (token.zig:19-33): {id, start, end, type_id | flags << 8} (outputs & 128)
 
 // words with more than EMIT_BIG tokens (whole documents, MiB-long unbroken words) are not copied by one warp: they are
 // queued here and copied by the whole grid (emit_big_kernel)
@@ -59,6 +60,7 @@ __device__ __forceinline__ void emit_real(const EmitParams& p, const EmitOut& o,
     if (p.outputs & 4u) o.attention[dst] = 1u;
     if (p.outputs & 8u) o.type_ids[dst] = 0u;
     if (p.outputs & 16u) o.special[dst] = 0u;
+    if (p.outputs & 128u) o.spans[dst] = make_uint4(id, s, e, 0u);
 }
 
 // one lane per word; words with many tokens are copied by the whole warp
@@ -136,6 +138,7 @@ __global__ void __launch_bounds__(256) emit_pad_kernel(EmitParams p, EmitOut o, 
         if (p.outputs & 4u) o.attention[dst] = 0u;
         if (p.outputs & 8u) o.type_ids[dst] = p.pad_type_id;
         if (p.outputs & 16u) o.special[dst] = 1u;
+        if (p.outputs & 128u) o.spans[dst] = make_uint4(p.pad_id, 0u, 0u, 0x0400u);     // initPadding: flags.is_padding (bit 2)
     }
 }
 

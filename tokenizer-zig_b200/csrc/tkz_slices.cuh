@@ -1022,6 +1022,7 @@ __device__ __forceinline__ void te_put(const EmitParams& p, const EmitOut& o, un
     if (outputs & 8u) o.type_ids[dst] = 0u;
     if (outputs & 16u) o.special[dst] = 0u;
     if (outputs & 32u) o.offsets16[dst] = (uint16_t)of;
+    if (outputs & 128u) o.spans[dst] = make_uint4(id, of & 0xFFu, of >> 8, 0u);
 }
 
 // copies the stream tokens [j0, j1) of a slice (stream position src + j) to dst0 + (j - j0); 4 loads in flight per lane
@@ -1191,6 +1192,7 @@ __global__ void __launch_bounds__(256) emit_pad_real_kernel(EmitParams p, EmitOu
     if (p.outputs & 8u) warp_fill_u32(o.type_ids + base, npad, p.pad_type_id);
     if (p.outputs & 16u) warp_fill_u32(o.special + base, npad, 1u);
     if (p.outputs & 32u) { uint16_t* q = o.offsets16 + base; for (unsigned long long i = lane_id(); i < npad; i += 32) q[i] = 0; }
+    if (p.outputs & 128u) { uint4* q = o.spans + base; for (unsigned long long i = lane_id(); i < npad; i += 32) q[i] = make_uint4(p.pad_id, 0u, 0u, 0x0400u); }
 }
 
 // document of the first failing word (byte position in the error word) -> ctrl[4]

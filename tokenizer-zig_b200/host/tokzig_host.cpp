@@ -346,6 +346,20 @@ extern "C" int tkzh_encode_batch(tkzh_tokenizer* t, const uint8_t* text, const u
     if (rc != TKZ_OK) t->err = tkz_last_error(t->ctx);
     return rc;
 }
+// FastTokenizer.encode (src/lib.zig:356-422) for a batch: same components, arena variants of the models, arena caps; no
+// truncation / padding.  One tkz_encode_batch call in fast mode (csrc/tkz_fast.cuh).
+extern "C" int tkzh_encode_batch_fast(tkzh_tokenizer* t, const uint8_t* text, const uint64_t* doc_off, uint64_t n_docs,
+                                      uint32_t max_sequence_length, uint32_t max_tokens, uint32_t outputs, tkz_batch_result* out) {
+    if (!t || !out) return TKZ_ERR_INVALID_ARG;
+    int rc = sync_device(t);
+    if (rc != TKZ_OK) return rc;
+    tkz_encode_params p{};
+    p.outputs = outputs;
+    p.fast = 1; p.fast_max_sequence_length = max_sequence_length; p.fast_max_tokens = max_tokens;   // FastTokenizerOptions, lib.zig:240-246
+    rc = tkz_encode_batch(t->ctx, text, doc_off, n_docs, &p, out);
+    if (rc != TKZ_OK) t->err = tkz_last_error(t->ctx);
+    return rc;
+}
 
 extern "C" int tkzh_decode(tkzh_tokenizer* t, const uint32_t* ids, uint64_t n, int skip_special_tokens, const uint8_t** out, uint64_t* out_len) {
     if (!t || !out || !out_len || (n && !ids)) return TKZ_ERR_INVALID_ARG;

@@ -27,7 +27,8 @@ pub const OUT_TYPE_IDS: u32 = 8;
 pub const OUT_SPECIAL: u32 = 16;
 pub const OUT_ALL: u32 = 31;
 pub const OUT_OFFSETS_PACKED: u32 = 32; // one u16 per token (start | end << 8) when every pre-token is < 256 bytes
-pub const OUT_IDS_U16: u32 = 64; // ids as u16 when every vocabulary id is < 65536
+pub const OUT_IDS_U16: u32 = 64;
+pub const OUT_SPAN_TOKENS: u32 = 128; // 16-byte SpanToken records // ids as u16 when every vocabulary id is < 65536
 
 pub const ModelDesc = extern struct {
     model_kind: i32,
@@ -58,6 +59,9 @@ pub const EncodeParams = extern struct {
     pad_type_id: u32 = 0,
     pad_left: i32 = 0,
     outputs: u32 = OUT_ALL,
+    fast: i32 = 0, // FastTokenizer.encode semantics (src/lib.zig:356-422)
+    fast_max_sequence_length: u32 = 0, // 0 = 8192
+    fast_max_tokens: u32 = 0, // 0 = 512
 };
 
 pub const BatchResult = extern struct {
@@ -73,6 +77,7 @@ pub const BatchResult = extern struct {
     err_doc: i64,
     offsets_packed: ?[*]const u16,
     ids16: ?[*]const u16,
+    span_tokens: ?[*]const u32, // 4 u32 per slot = SpanToken (src/token.zig:19-33)
 };
 
 /// tkz_compact_result: kept real tokens only; masks and padding slots are rebuilt on the host (tkz_compact_expand)
