@@ -383,8 +383,8 @@ def strong_scaling(n_gpus, total_mib, workload="c5b"):
             bounds, results, ms = pool.encode_compact(text, off, bounds=cut)
             wall = time.perf_counter() - t0
             if best is None or wall < best[0]:
-                best = (wall, bounds.copy(), ms.copy(), sum(int(r.n_kept) for r in results))
-        wall, bounds, ms, kept = best
+                best = (wall, bounds.copy(), ms.copy(), sum(int(r.n_kept) for r in results), pool.shard_kernel_ms())
+        wall, bounds, ms, kept, kms = best
         shard_bytes = [int(off[int(bounds[k + 1])] - off[int(bounds[k])]) for k in range(n_gpus)]
         # parity of the sharded path: the first and the last documents of every shard against the oracle
         ok = True
@@ -397,7 +397,8 @@ def strong_scaling(n_gpus, total_mib, workload="c5b"):
                 got = tz.expand_compact(results[k], lo - d0, hi - d0)
                 ok = ok and np.array_equal(got.ids, ref.ids) and np.array_equal(got.offsets, ref.offsets) and np.array_equal(got.doc_tok_off, ref.doc_tok_off)
         out["cuts"][label] = {"value": int(off[-1]) / wall / 1e9, "unit": "GB/s", "wall_ms": wall * 1e3, "shard_ms": [round(float(x), 2) for x in ms],
-                              "imbalance_slowest_over_mean": float(ms.max() / ms.mean()), "shard_bytes": shard_bytes, "kept_tokens": kept,
+                              "imbalance_slowest_over_mean": float(ms.max() / ms.mean()),
+                              "shard_kernel_ms": [round(float(x), 2) for x in kms], "kernel_imbalance_slowest_over_mean": float(kms.max() / max(kms.mean(), 1e-9)), "shard_bytes": shard_bytes, "kept_tokens": kept,
                               "cut_ms": cut_ms, "parity_checked_vs_oracle": bool(ok)}
     pool.close(); cfg.close()
     return out

@@ -160,6 +160,8 @@ typedef struct tkz_stats {
     float ms_emit;                      /* K5: fused truncate / pad / output write */
     float ms_total;                     /* first kernel to last kernel */
     uint32_t model_flags;               /* bit 0: merge table proven "proper" -> long words use the windowed block kernels; bit 1: the last encode ran the grid-wide kernel on huge words; bit 2: it re-ran the slice pipeline with worst-case capacities */
+    float ms_call_kernels;              /* host-buffer calls: device time of ALL chunks of the last call (sum of their ms_total) */
+    uint32_t reserved0;
     uint32_t path;                      /* pipeline of the last encode: 0 per-occurrence, 2 slice pipeline
                                            (then ms_split = pass A, ms_model = word-list kernels, ms_emit = pass B) */
 } tkz_stats;

@@ -126,7 +126,7 @@ class Stats(C.Structure):
     _fields_ = [("arena_bytes", C.c_uint64), ("n_words", C.c_uint64), ("n_unique_words", C.c_uint64),
                 ("n_long_words", C.c_uint64), ("kernel_launches", C.c_uint64),
                 ("ms_split", C.c_float), ("ms_model", C.c_float), ("ms_scan", C.c_float), ("ms_emit", C.c_float), ("ms_total", C.c_float),
-                ("model_flags", C.c_uint32), ("path", C.c_uint32)]
+                ("model_flags", C.c_uint32), ("ms_call_kernels", C.c_float), ("reserved0", C.c_uint32), ("path", C.c_uint32)]
 
 
 # every symbol include/tokzig_b200.h declares (checked by tests/test_cabi_symbols.py)
@@ -697,6 +697,15 @@ class MultiPool:
             docs = [int(r.err_doc) for r in results if int(r.err_doc) >= 0]
             raise TokzigError(rc, (self._L.tkzm_last_error(self._h) or b"").decode(), min(docs) if docs else -1)
         return bounds, list(results), ms
+
+    def shard_kernel_ms(self) -> np.ndarray:
+        """device time of every shard's last call (all chunks), from the contexts' stage events"""
+        out = np.zeros(self.n)
+        for k in range(self.n):
+            s = Stats()
+            self._L.tkz_ctx_get_stats(self._L.tkzm_ctx(self._h, k), C.byref(s))
+            out[k] = s.ms_call_kernels
+        return out
 
     def encode_expanded(self, text, doc_off, cost_balanced: bool = False) -> BatchEncoding:
         """the whole batch as one BatchEncoding (verification: results are gathered to the host in document order)"""

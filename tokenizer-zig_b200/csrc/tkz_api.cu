@@ -1151,6 +1151,7 @@ int encode_host_single(tkz_ctx* ctx, const uint8_t* text, const uint64_t* doc_of
         *c.dst = c.hb->p;
     }
     CK(cudaStreamSynchronize(st));
+    ctx->stats.ms_call_kernels = ctx->stats.ms_total;
     return TKZ_OK;
 }
 
@@ -1161,22 +1162,26 @@ int encode_host_chunked(tkz_ctx* ctx, const uint8_t* text, const uint64_t* doc_o
                         const tkz_encode_params* params_in, tkz_batch_result* out) {
     memset(out, 0, sizeof *out);
     out->err_doc = -1;
-    // chunk boundaries (document indices)
+    // chunk boundaries (document indices) are decided as the call goes: a chunk of `target` bytes ends at the last document
+    // boundary not beyond it (at least one document).  The target starts at chunk_bytes; when the kernels of a chunk take longer
+    // than its transfers would (long-word corpora: the block / grid kernels want many words in flight) it doubles, up to 8x
     std::vector<uint64_t> cb; cb.push_back(0);
-    while (cb.back() < n_docs) {
-        const uint64_t d0 = cb.back(), target = doc_off[d0] + ctx->chunk_bytes;
+    auto next_boundary = [&](uint64_t d0, uint64_t target_bytes) -> uint64_t {
+        const uint64_t target = doc_off[d0] + target_bytes;
         uint64_t lo = d0 + 1, hi = n_docs;                       // last boundary with doc_off <= target, at least one document
         while (lo < hi) { const uint64_t mid = lo + (hi - lo + 1) / 2; if (doc_off[mid] <= target) lo = mid; else hi = mid - 1; }
-        cb.push_back(lo);
-    }
-    const size_t nc = cb.size() - 1;
+        return lo;
+    };
+    uint64_t chunk_target = ctx->chunk_bytes;
+    const uint64_t chunk_max = std::min<uint64_t>(ctx->chunk_bytes * 8, 1ull << 30);
+    cb.push_back(next_boundary(0, chunk_target));
     tkz_encode_params P{};
     if (params_in) P = *params_in;
     if (P.outputs == 0) P.outputs = TKZ_OUT_ALL;
     P.outputs |= TKZ_OUT_IDS;
     TRY(ensure_host(ctx, ctx->h_doc_tok_off, (n_docs + 1) * 8));
     uint64_t* h_dto = (uint64_t*)ctx->h_doc_tok_off.p;
-    std::vector<uint64_t> tok_base(nc + 1, 0);
+    std::vector<uint64_t> tok_base;
     auto stage_in = [&](size_t i) -> int {
         const int b = (int)(i & 1);
         const uint64_t d0 = cb[i], d1 = cb[i + 1], base = doc_off[d0], nb = doc_off[d1] - base, nd = d1 - d0;
@@ -1192,12 +1197,15 @@ int encode_host_chunked(tkz_ctx* ctx, const uint8_t* text, const uint64_t* doc_o
     };
     bool used_ids16 = false;
 restart:
+    cb.resize(2); tok_base.clear(); chunk_target = ctx->chunk_bytes;
     TRY(stage_in(0));
     uint64_t T_total = 0, T_real = 0;
-    for (size_t i = 0; i < nc; i++) {
+    float ms_kernels = 0.f;
+    for (size_t i = 0; cb[i] < n_docs; i++) {
         const int b = (int)(i & 1);
         const uint64_t d0 = cb[i], d1 = cb[i + 1], nd = d1 - d0, nb = doc_off[d1] - doc_off[d0];
-        if (i + 1 < nc) {
+        if (d1 < n_docs) {
+            cb.push_back(next_boundary(d1, chunk_target));
             // buffer (i+1)&1 was read by the kernels of chunk i-1 (finished: the device path drains its stream) and its staging
             // area by the H2D of chunk i-1 (same stream as the copy about to be enqueued)
             CK(cudaStreamSynchronize(ctx->s_h2d));
@@ -1220,9 +1228,12 @@ restart:
             P.outputs = (P.outputs & ~TKZ_OUT_OFFSETS_PACKED) | TKZ_OUT_OFFSETS;
             goto restart;
         }
+        ms_kernels += ctx->stats.ms_total;
+        // kernel-bound chunk (its device time exceeds what ~45 GB/s of PCIe needs for its text): larger chunks from now on
+        if ((double)ctx->stats.ms_total * 1e-3 > 1.5 * (double)nb / 45e9 && chunk_target < chunk_max) chunk_target *= 2;
         used_ids16 = dev.ids16 != nullptr;                      // (the same decision in every chunk: it depends on the model and the parameters)
         const uint64_t T = dev.n_tokens;
-        tok_base[i] = T_total;
+        tok_base.push_back(T_total);
         // size the host arrays from the first chunk's token density
         uint64_t est = T_total + T;
         if (i == 0 && nb) est = (uint64_t)((double)T * ((double)N / (double)nb) * 1.03) + 4096;
@@ -1240,13 +1251,14 @@ restart:
         CK(cudaEventRecord(ctx->ev_d2h[b], ctx->s_d2h));
         T_total += T; T_real += dev.n_real_tokens;
     }
-    tok_base[nc] = T_total;
+    const size_t nc = cb.size() - 1;
     CK(cudaStreamSynchronize(ctx->s_d2h));
     CK(cudaStreamSynchronize(ctx->s_h2d));
     // chunk-relative CSR offsets -> global
     for (size_t i = 1; i < nc; i++) { const uint64_t base = tok_base[i]; for (uint64_t d = cb[i]; d < cb[i + 1]; d++) h_dto[d] += base; }
     h_dto[n_docs] = T_total;
     ctx->out_sel = 0;
+    ctx->stats.ms_call_kernels = ms_kernels;
     uint32_t outputs = P.outputs;
     if ((outputs & TKZ_OUT_IDS_U16) && !used_ids16) outputs &= ~TKZ_OUT_IDS_U16;
     out->n_docs = n_docs; out->n_tokens = T_total; out->n_real_tokens = T_real;

@@ -106,6 +106,8 @@ pub const Stats = extern struct {
     ms_emit: f32,
     ms_total: f32,
     model_flags: u32,
+    ms_call_kernels: f32, // host-buffer calls: device time of all chunks of the last call
+    reserved0: u32,
     path: u32, // pipeline of the last encode: 0 per-occurrence, 2 slice pipeline
 };
 

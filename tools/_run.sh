@@ -1,5 +1,7 @@
-B="python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline --no-verify --no-configs"
-$B > gpurun_out/plain.log 2>&1 && ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r02_v6_launches_c2b_1GiB.csv $B > gpurun_out/ncu1.log 2>&1; tail -1 gpurun_out/ncu1.log
-$B > gpurun_out/plain.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:slice_emit -s 3 -c 1 -o gpurun_out/r02_v6_passB $B > gpurun_out/ncu2.log 2>&1; tail -1 gpurun_out/ncu2.log
-C="python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu-baseline --no-verify --no-configs --workload c2a --size-mib 256"
-$C > gpurun_out/plain.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:bpe_block -s 15 -c 5 -o gpurun_out/r02_v6_block_c2a $C > gpurun_out/ncu3.log 2>&1; tail -1 gpurun_out/ncu3.log
+timeout 900 python -m pytest tests -x -q -m gpu -k "chunked or compact or packed_formats or multi_context or grid_kernel_on_the_skewed" 2>&1 | tail -3
+for w in c2b c5b c2a; do
+python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-verify --no-configs --no-materialise --workload $w | python -c "
+import sys,json
+d=json.loads(sys.stdin.read()); e=d['e2e']
+print('$w', 'device', round(d['value'],1), 'e2e', round(e['value'],2), round(e['ms_per_step'],1))"
+done
