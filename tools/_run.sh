@@ -1,7 +1,5 @@
-timeout 900 python -m pytest tests -x -q -m gpu -k "chunked or compact or packed_formats or multi_context or grid_kernel_on_the_skewed" 2>&1 | tail -3
-for w in c2b c5b c2a; do
-python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-verify --no-configs --no-materialise --workload $w | python -c "
-import sys,json
-d=json.loads(sys.stdin.read()); e=d['e2e']
-print('$w', 'device', round(d['value'],1), 'e2e', round(e['value'],2), round(e['ms_per_step'],1))"
-done
+N=8
+( time python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps 5 --warmup 3 > gpurun_out/bench_n$N.json 2> gpurun_out/bench_n$N.err ) 2>&1 | grep real
+tail -3 gpurun_out/bench_n$N.err
+python tools/pcie_probe.py --gpus 1,2,4,8 --mib 256 | tee gpurun_out/r02_pcie_probe_8gpu.json
+nvidia-smi topo -m 2>/dev/null | head -14 > gpurun_out/r02_topo_8gpu.txt
