@@ -140,7 +140,7 @@ __global__ void __launch_bounds__(NT, MINB) bpe_block_kernel(DevModel m, BlockBp
                 if (bad) s_cnt[0] = 1;
             }
             uint32_t tot;
-            const uint32_t ex = block_excl_scan32<NT / 32>(id != TKZ_NONE ? 1u : 0u, sc, phase, &tot);
+            const uint32_t ex = block_excl_scan_bit<NT / 32>(id != TKZ_NONE, sc, phase, &tot);
             if (id != TKZ_NONE) { const uint32_t k = n + ex; ids[k] = id; first[k] = k; ps[k] = p; pe[k] = p + (uint32_t)L; }
             n += tot;
         }
@@ -254,7 +254,7 @@ __global__ void __launch_bounds__(NT, MINB) bpe_block_kernel(DevModel m, BlockBp
                     x = ids[i]; f = first[i]; r = rk[i]; wv = win[i];
                 }
                 uint32_t tot;
-                const uint32_t ex = block_excl_scan32<NT / 32>(keep ? 1u : 0u, sc, phase, &tot);   // barrier: all reads done
+                const uint32_t ex = block_excl_scan_bit<NT / 32>(keep, sc, phase, &tot);          // barrier: all reads done
                 if (keep) {
                     const uint32_t q = wpos + ex;
                     ids[q] = head ? r : x;                                  // r holds the new id for heads

@@ -183,4 +183,25 @@ __device__ __forceinline__ uint32_t block_excl_scan32(uint32_t v, uint32_t* sh, 
     return base + inc - v;
 }
 
+// the same for one-bit values: ballot + popc instead of five shuffle steps; a one-warp block needs neither shared memory
+// nor the barrier
+template <int NW>
+__device__ __forceinline__ uint32_t block_excl_scan_bit(bool v, uint32_t* sh, uint32_t phase, uint32_t* total) {
+    const uint32_t lane = lane_id(), wid = threadIdx.x >> 5;
+    const uint32_t mk = __ballot_sync(0xFFFFFFFFu, v);
+    const uint32_t ex = (uint32_t)__popc(mk & ((1u << lane) - 1u));
+    if (NW == 1) { *total = (uint32_t)__popc(mk); __syncwarp(); return ex; }
+    uint32_t* s = sh + (phase & 1u) * (NW + 1);
+    if (lane == 0) s[wid] = (uint32_t)__popc(mk);
+    __syncthreads();
+    static_assert(NW <= 32, "one lane per warp total");
+    const uint32_t x = lane < NW ? s[lane] : 0u;
+    uint32_t xi = x;
+#pragma unroll
+    for (int d = 1; d < NW; d <<= 1) { const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, xi, d); if (lane >= (uint32_t)d) xi += y; }
+    *total = __shfl_sync(0xFFFFFFFFu, xi, NW - 1);
+    const uint32_t base = __shfl_sync(0xFFFFFFFFu, xi - x, wid);
+    return base + ex;
+}
+
 }  // namespace tkz
