@@ -124,7 +124,23 @@ typedef struct tkz_encode_params {
     int32_t fast;
     uint32_t fast_max_sequence_length;  /* ArenaConfig.max_sequence_length (default 8192); 4 .. 65535 */
     uint32_t fast_max_tokens;           /* ArenaConfig.max_tokens (default 512) */
+    /* hf_compat -- BEYOND the reference, opt-in, 0 = the reference's behaviour.  What
+     * src/processor/processor.zig:41-152 declares (BertProcessing, TemplateProcessing) and leaves as TODO, with the semantics of
+     * Hugging Face tokenizers 0.22 (tests/golden/hf_compat_vectors.json): TKZ_HF_TEMPLATE puts tpl_n_prefix special tokens
+     * before and tpl_n_suffix after every document's kept tokens (offsets (0,0), special 1, attention 1, their own type id),
+     * gives the document's tokens tpl_seq_type, lets the added tokens count against max_length and towards pad_length;
+     * TKZ_HF_DOC_OFFSETS reports offsets relative to the (normalised) document instead of the pre-token.  A caller passes the
+     * prefix / suffix only when it encodes with add_special_tokens (tokenizers keeps the type id either way).  Served by the
+     * per-occurrence pipeline (not the slice pipeline of the headline numbers); not available in the FastTokenizer mode and
+     * the compact result. */
+    uint32_t hf_flags;                  /* TKZ_HF_* */
+    uint32_t tpl_n_prefix, tpl_n_suffix;             /* <= TKZ_TPL_MAX each */
+    uint32_t tpl_prefix_id[4], tpl_prefix_type[4], tpl_suffix_id[4], tpl_suffix_type[4];
+    uint32_t tpl_seq_type;
 } tkz_encode_params;
+#define TKZ_HF_TEMPLATE 1u
+#define TKZ_HF_DOC_OFFSETS 2u
+#define TKZ_TPL_MAX 4u
 
 /* CSR batch encoding = n_docs Encodings (src/encoding.zig:231-243) back to back.  Document d owns slots
  * [doc_tok_off[d], doc_tok_off[d+1]).  offsets holds (start,end) pairs (Offset, src/types.zig:4-11), byte offsets into
@@ -317,6 +333,11 @@ int tkzh_token_to_id(tkzh_tokenizer* t, const uint8_t* token, uint64_t len, uint
 int tkzh_id_to_token(tkzh_tokenizer* t, uint32_t id, const uint8_t** token, uint64_t* len);       /* 1 found, 0 not */
 /* the model's own map only (src/model/bpe.zig:258): the strings of Encoding.tokens, which ignore the added vocabulary */
 int tkzh_model_id_to_token(tkzh_tokenizer* t, uint32_t id, const uint8_t** token, uint64_t* len);
+/* hf_compat switch of the host mirror (TKZ_HF_* flags; 0 = the reference's behaviour, the default): with TKZ_HF_TEMPLATE the
+ * single-sequence template of the tokenizer.json post_processor (BertProcessing, TemplateProcessing  specials* $A specials*)
+ * is applied, its special tokens only when tkzh_encode_batch is called with add_special_tokens != 0.  Returns 1 when such a
+ * template was found at load time, 0 when there is none to apply. */
+int tkzh_set_hf_compat(tkzh_tokenizer* t, uint32_t flags);
 int tkzh_add_special_tokens(tkzh_tokenizer* t, const uint8_t* contents, const uint64_t* off, uint64_t n, uint64_t* added);
 /* loader facts used by the parity tests */
 uint64_t tkzh_model_vocab_count(tkzh_tokenizer* t);

@@ -83,6 +83,8 @@ def lib():
         L.orc_model_set_truncation.argtypes = [C.c_void_p, C.c_int, C.c_uint64]
         L.orc_model_set_padding.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_uint64, C.c_uint32, C.c_uint32, C.c_int]
         L.orc_model_set_fast_options.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32]
+        L.orc_model_set_hf.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32]
+        L.orc_model_set_hf.restype = C.c_int
         L.orc_model_token_to_id.argtypes = [C.c_void_p, C.c_char_p, C.c_uint32, C.POINTER(C.c_uint32)]
         L.orc_model_vocab_count.restype = C.c_uint64
         L.orc_model_vocab_count.argtypes = [C.c_void_p]
@@ -279,6 +281,39 @@ def pack_docs(docs: Sequence[bytes]):
     return np.ascontiguousarray(text), off
 
 
+def hf_template_from_json(json_content):
+    """The single-sequence template of a tokenizer.json post_processor as (prefix, suffix, seq_type) with prefix / suffix =
+    [(special id, type id)], or None when there is none or it is not of the form  specials* $A specials*.  Shapes as tokenizers
+    0.22 serialises them: TemplateProcessing {single: [{SpecialToken: {id, type_id}} | {Sequence: {id, type_id}}], special_tokens:
+    {name: {ids: [...]}}} and BertProcessing {sep: [token, id], cls: [token, id]}.  hf_compat only (the reference's processors
+    are no-ops, processor.zig:69-74, 147-152)."""
+    j = json.loads(json_content) if isinstance(json_content, (str, bytes)) else json_content
+    pp = j.get("post_processor")
+    if not isinstance(pp, dict):
+        return None
+    if pp.get("type") == "BertProcessing":
+        return [(int(pp["cls"][1]), 0)], [(int(pp["sep"][1]), 0)], 0
+    if pp.get("type") != "TemplateProcessing":
+        return None
+    prefix, suffix, seq_type, seen = [], [], 0, False
+    for piece in pp.get("single", []):
+        if "Sequence" in piece:
+            if seen or piece["Sequence"].get("id") != "A":
+                return None
+            seen, seq_type = True, int(piece["Sequence"].get("type_id", 0))
+        elif "SpecialToken" in piece:
+            st = piece["SpecialToken"]
+            ids = pp.get("special_tokens", {}).get(st["id"], {}).get("ids")
+            if ids is None:
+                return None
+            (suffix if seen else prefix).extend((int(i), int(st.get("type_id", 0))) for i in ids)
+        else:
+            return None
+    if not seen or len(prefix) > 4 or len(suffix) > 4:
+        return None
+    return prefix, suffix, seq_type
+
+
 class OracleTokenizer:
     """Mirrors Tokenizer (lib.zig:32-224) for the encode direction, on the CPU oracle."""
 
@@ -321,6 +356,17 @@ class OracleTokenizer:
             self._L.orc_model_free(self._m)
         except Exception:
             pass
+
+    def set_hf_compat(self, flags: int = 0, prefix=(), suffix=(), seq_type: int = 0):
+        """hf_compat (not reference behaviour): flags 1 = single-sequence template, prefix / suffix = [(special id, type id)];
+        2 = offsets relative to the document."""
+        def arr(v):
+            return (C.c_uint32 * max(1, len(v)))(*v)
+        pi, pt = arr([a for a, _ in prefix]), arr([b for _, b in prefix])
+        si, st_ = arr([a for a, _ in suffix]), arr([b for _, b in suffix])
+        rc = self._L.orc_model_set_hf(self._m, flags, len(prefix), pi, pt, len(suffix), si, st_, seq_type)
+        if rc:
+            raise ValueError("at most 4 special tokens on either side of the sequence")
 
     def set_fast_options(self, max_sequence_length: int = 8192, max_tokens: int = 512):
         """FastTokenizerOptions.arena_config (lib.zig:240-246, arena.zig:140-145) for algo 2"""

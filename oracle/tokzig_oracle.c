@@ -38,6 +38,7 @@
 
 #define ORC_OK 0
 #define ORC_ERR_OOM (-1)
+#define ORC_ERR_ARG (-5)
 #define ORC_ERR_MISSING_UNK (-2)   /* error.MissingUnkToken  wordpiece.zig:150,212 */
 #define ORC_ERR_INVALID_UTF8 (-3)  /* reference: unreachable/UB */
 
@@ -157,6 +158,10 @@ typedef struct orc_model {
     int has_pad; int pad_has_length; uint64_t pad_length; uint32_t pad_id, pad_type_id; int pad_left;
     /* FastTokenizerOptions lib.zig:237-242 (algo 2 only) */
     uint32_t fast_max_seq, fast_max_tokens;
+    /* hf_compat (NOT reference behaviour; pinned against Hugging Face tokenizers 0.22.2 by tests/golden/hf_compat_vectors.json):
+     * what processor.zig:41-152 declares and leaves as TODO */
+    uint32_t hf_flags;             /* 1: single-sequence template; 2: offsets relative to the document */
+    uint32_t tpl_n_pre, tpl_n_suf, tpl_pre_id[4], tpl_pre_type[4], tpl_suf_id[4], tpl_suf_type[4], tpl_seq_type;
 } orc_model;
 
 orc_model* orc_model_new(int kind) {
@@ -218,6 +223,17 @@ void orc_model_set_padding(orc_model* m, int has, int has_length, uint64_t lengt
     m->pad_type_id = pad_type_id; m->pad_left = left;
 }
 void orc_model_set_fast_options(orc_model* m, uint32_t max_seq, uint32_t max_tokens) { m->fast_max_seq = max_seq; m->fast_max_tokens = max_tokens; }
+/* hf_compat: flags 1 = apply the template (special ids before / after the sequence, each with its type id; the sequence's own
+ * tokens get seq_type), 2 = offsets relative to the document.  Truncation then keeps max_length minus the added tokens
+ * (tokenizers' TokenizerImpl::post_process), padding counts the added tokens. */
+int orc_model_set_hf(orc_model* m, uint32_t flags, uint32_t n_pre, const uint32_t* pre_id, const uint32_t* pre_type,
+                     uint32_t n_suf, const uint32_t* suf_id, const uint32_t* suf_type, uint32_t seq_type) {
+    if (n_pre > 4 || n_suf > 4) return ORC_ERR_ARG;
+    m->hf_flags = flags; m->tpl_n_pre = n_pre; m->tpl_n_suf = n_suf; m->tpl_seq_type = seq_type;
+    for (uint32_t i = 0; i < n_pre; i++) { m->tpl_pre_id[i] = pre_id[i]; m->tpl_pre_type[i] = pre_type[i]; }
+    for (uint32_t i = 0; i < n_suf; i++) { m->tpl_suf_id[i] = suf_id[i]; m->tpl_suf_type[i] = suf_type[i]; }
+    return ORC_OK;
+}
 int orc_model_token_to_id(const orc_model* m, const uint8_t* s, uint32_t len, uint32_t* out) {
     smap_ent* e = smap_find(&m->vocab, s, len); if (!e) return 0; *out = e->val; return 1;
 }
@@ -707,25 +723,39 @@ static int encode_doc(const orc_model* m, const uint8_t* text, size_t n, int alg
     tb->n = 0;
     for (size_t q = 0; q < pt->n; q += 2) {
         const uint8_t* w = cur + pt->v[q]; size_t wl = (size_t)(pt->v[q + 1] - pt->v[q]);
-        int rc;
+        int rc; const size_t t0 = tb->n;
         if (m->kind == ORC_BPE) rc = (algo == 1) ? bpe_tokenize_fast_exact(m, w, wl, s, tb) : bpe_tokenize_literal(m, w, wl, s, tb);
         else rc = wordpiece_tokenize(m, w, wl, tb);
         if (rc) return rc;
+        if (m->hf_flags & 2u) for (size_t i = t0; i < tb->n; i++) { tb->t[i].start += (uint32_t)pt->v[q]; tb->t[i].end += (uint32_t)pt->v[q]; }
     }
     /* step 4 Encoding.fromTokens  encoding.zig:246-294 ; step 5 post-process: no-op (config.zig:551-555,
      * processor.zig:69-74,108-113,147-152) ; step 6 truncate encoding.zig:363-380 ; step 7 pad encoding.zig:385-463 */
     size_t len = tb->n;
-    if (m->has_trunc && len > m->max_length) len = (size_t)m->max_length;
-    size_t target = len; size_t pad_len = 0;
-    if (m->has_pad && m->pad_has_length && len < m->pad_length) { target = (size_t)m->pad_length; pad_len = target - len; }
+    const size_t n_pre = (m->hf_flags & 1u) ? m->tpl_n_pre : 0, n_suf = (m->hf_flags & 1u) ? m->tpl_n_suf : 0, n_add = n_pre + n_suf;
+    if (m->has_trunc) {                          /* hf_compat: the added tokens count against max_length */
+        const size_t budget = m->max_length > n_add ? (size_t)m->max_length - n_add : 0;
+        if (len > budget) len = budget;
+    }
+    const size_t full = len + n_add;
+    size_t target = full; size_t pad_len = 0;
+    if (m->has_pad && m->pad_has_length && full < m->pad_length) { target = (size_t)m->pad_length; pad_len = target - full; }
     if (encbuf_reserve(enc, target)) return ORC_ERR_OOM;
     enc_tok* o = enc->t + enc->n;
     size_t real0 = (pad_len && m->pad_left) ? pad_len : 0;
-    for (size_t i = 0; i < len; i++) {
+    for (size_t i = 0; i < n_pre; i++) {
         enc_tok* e = &o[real0 + i];
-        e->id = tb->t[i].id; e->s = tb->t[i].start; e->e = tb->t[i].end; e->type_id = 0; e->special = 0; e->attn = 1;
+        e->id = m->tpl_pre_id[i]; e->s = 0; e->e = 0; e->type_id = m->tpl_pre_type[i]; e->special = 1; e->attn = 1;
     }
-    size_t p0 = m->pad_left ? 0 : len;
+    for (size_t i = 0; i < len; i++) {
+        enc_tok* e = &o[real0 + n_pre + i];
+        e->id = tb->t[i].id; e->s = tb->t[i].start; e->e = tb->t[i].end; e->type_id = (m->hf_flags & 1u) ? m->tpl_seq_type : 0; e->special = 0; e->attn = 1;
+    }
+    for (size_t i = 0; i < n_suf; i++) {
+        enc_tok* e = &o[real0 + n_pre + len + i];
+        e->id = m->tpl_suf_id[i]; e->s = 0; e->e = 0; e->type_id = m->tpl_suf_type[i]; e->special = 1; e->attn = 1;
+    }
+    size_t p0 = m->pad_left ? 0 : full;
     for (size_t i = 0; i < pad_len; i++) {
         enc_tok* e = &o[p0 + i];
         e->id = m->pad_id; e->s = 0; e->e = 0; e->type_id = m->pad_type_id; e->special = 1; e->attn = 0;

@@ -81,7 +81,18 @@ class EncodeParams(C.Structure):
         ("fast", C.c_int32),
         ("fast_max_sequence_length", C.c_uint32),
         ("fast_max_tokens", C.c_uint32),
+        ("hf_flags", C.c_uint32),
+        ("tpl_n_prefix", C.c_uint32),
+        ("tpl_n_suffix", C.c_uint32),
+        ("tpl_prefix_id", C.c_uint32 * 4),
+        ("tpl_prefix_type", C.c_uint32 * 4),
+        ("tpl_suffix_id", C.c_uint32 * 4),
+        ("tpl_suffix_type", C.c_uint32 * 4),
+        ("tpl_seq_type", C.c_uint32),
     ]
+
+
+HF_TEMPLATE, HF_DOC_OFFSETS = 1, 2
 
 
 class BatchResult(C.Structure):
@@ -138,7 +149,7 @@ EXPORTED_SYMBOLS = [
     "tkzh_from_json", "tkzh_from_file", "tkzh_free", "tkzh_last_error", "tkzh_ctx", "tkzh_set_truncation", "tkzh_set_padding",
     "tkzh_set_normalizer", "tkzh_set_pretokenizer", "tkzh_encode_batch", "tkzh_encode_batch_fast", "tkzh_decode", "tkzh_decode_batch", "tkzh_get_vocab_size", "tkzh_token_to_id",
     "tkzh_id_to_token", "tkzh_model_id_to_token", "tkzh_add_special_tokens", "tkzh_model_vocab_count", "tkzh_merge_count", "tkzh_has_normalizer",
-    "tkzh_has_pretokenizer", "tkzh_has_post_processor", "tkzh_added_token_count", "tkzh_added_token", "tkzh_model_desc",
+    "tkzh_has_pretokenizer", "tkzh_has_post_processor", "tkzh_set_hf_compat", "tkzh_added_token_count", "tkzh_added_token", "tkzh_model_desc",
 ]
 
 _lib = None
@@ -187,6 +198,8 @@ def lib():
     L.tkzh_ctx.argtypes = [vp]
     L.tkzh_ctx.restype = vp
     L.tkzh_set_truncation.argtypes = [vp, i32, u64]
+    L.tkzh_set_hf_compat.argtypes = [vp, C.c_uint32]
+    L.tkzh_set_hf_compat.restype = C.c_int
     L.tkzh_set_padding.argtypes = [vp, i32, i32, u64, u32, u32, i32]
     L.tkzh_set_normalizer.argtypes = [vp, vp, vp, C.c_int32]
     L.tkzh_set_pretokenizer.argtypes = [vp, vp, C.c_int32]
@@ -445,6 +458,15 @@ class Tokenizer:
             return
         k = np.array(list(ops), dtype=np.int32)
         self._L.tkzh_set_pretokenizer(self._h, k.ctypes.data if len(ops) else None, len(ops))
+
+    def set_hf_compat(self, flags: int) -> bool:
+        """hf_compat (beyond the reference, off by default): HF_TEMPLATE applies the post_processor's single-sequence template
+        (its special tokens only when encode is called with add_special_tokens), HF_DOC_OFFSETS reports document-relative
+        offsets.  Returns whether the tokenizer.json carried a template this mode can apply."""
+        rc = self._L.tkzh_set_hf_compat(self._h, int(flags))
+        if rc < 0:
+            raise TokzigError(rc, "tkzh_set_hf_compat", -1)
+        return rc == 1
 
     def _push_params(self):
         if self.truncation is None:

@@ -906,6 +906,13 @@ int encode_device_impl(tkz_ctx* ctx, const uint8_t* d_text, const uint64_t* d_do
         if (P.fast_max_sequence_length < 4 || P.fast_max_sequence_length > 65535) { ctx->err = "fast_max_sequence_length must be 4 .. 65535 (16-bit symbol indices, arena.zig:17-42)"; return TKZ_ERR_INVALID_ARG; }
         P.has_truncation = 1; P.max_length = P.fast_max_tokens; P.has_padding = 0;
     }
+    if (P.hf_flags) {
+        // hf_compat (beyond the reference, opt-in): served by the per-occurrence pipeline only
+        if (P.hf_flags & ~(uint32_t)(TKZ_HF_TEMPLATE | TKZ_HF_DOC_OFFSETS)) { ctx->err = "unknown hf_flags bit"; return TKZ_ERR_INVALID_ARG; }
+        if (P.fast) { ctx->err = "hf_flags cannot be combined with the FastTokenizer mode"; return TKZ_ERR_INVALID_ARG; }
+        if (P.tpl_n_prefix > TKZ_TPL_MAX || P.tpl_n_suffix > TKZ_TPL_MAX) { ctx->err = "at most TKZ_TPL_MAX special tokens on either side of the sequence"; return TKZ_ERR_INVALID_ARG; }
+        if (!(P.hf_flags & TKZ_HF_TEMPLATE)) { P.tpl_n_prefix = P.tpl_n_suffix = 0; P.tpl_seq_type = 0; }
+    }
     if ((P.outputs & TKZ_OUT_IDS_U16) && (!ctx->ids16_ok || (P.has_padding && P.pad_id > 0xFFFFu))) P.outputs &= ~TKZ_OUT_IDS_U16;
     const uint32_t nd = (uint32_t)n_docs;
     DevModel m = ctx->dm;
@@ -944,7 +951,7 @@ int encode_device_impl(tkz_ctx* ctx, const uint8_t* d_text, const uint64_t* d_do
     // ---- slice pipeline (tkz_slices.cuh) whenever there is a pre-tokenizer; TKZ_NO_DEDUP=1 keeps the per-occurrence
     //      pipeline below for A/B tests
     ctx->stats.path = 0;
-    if (m.has_pretok && ctx->use_dedup && !P.fast) {
+    if (m.has_pretok && ctx->use_dedup && !P.fast && !P.hf_flags) {
         const ClassRanges& cr = ctx->dm.norm_has_drop ? ctx->cr_post : ctx->cr;      // (K0 ran: the text is already normalised)
         int rc = encode_slices(ctx, m, cr, d_text, d_doc_off, nd, N, P, false, out, launches);
         if (rc != TKZ_RETRY_WORST) return rc;
@@ -1034,6 +1041,13 @@ int encode_device_impl(tkz_ctx* ctx, const uint8_t* d_text, const uint64_t* d_do
     TRY(ensure(ctx, ctx->O().doc_tok_off, (n_docs + 1) * 8));
     unsigned long long* doc_tok_off = (unsigned long long*)ctx->O().doc_tok_off.p;
     EmitParams ep{P.has_truncation, P.max_length, P.has_padding, P.pad_length, P.pad_id, P.pad_type_id, P.pad_left, P.outputs};
+    if (P.hf_flags) {
+        ep.hf_flags = P.hf_flags; ep.n_pre = P.tpl_n_prefix; ep.n_suf = P.tpl_n_suffix; ep.seq_type = P.tpl_seq_type;
+        for (uint32_t i = 0; i < TKZ_TPL_MAX; i++) {
+            ep.pre_id[i] = P.tpl_prefix_id[i]; ep.pre_type[i] = P.tpl_prefix_type[i]; ep.suf_id[i] = P.tpl_suffix_id[i]; ep.suf_type[i] = P.tpl_suffix_type[i];
+            if ((P.outputs & TKZ_OUT_IDS_U16) && ((i < ep.n_pre && ep.pre_id[i] > 0xFFFFu) || (i < ep.n_suf && ep.suf_id[i] > 0xFFFFu))) { ctx->err = "template id above 65535 with TKZ_OUT_IDS_U16"; return TKZ_ERR_INVALID_ARG; }
+        }
+    }
     if (nd) { doc_len_kernel<<<(nd + 255) / 256, 256, 0, st>>>(ep, word_tok_off, doc_word_off, nd, doc_tok_off); launches++; }
     launches += exclusive_scan<unsigned long long>(doc_tok_off, n_docs, doc_tok_off, (unsigned long long*)ctx->a_scan_tmp.p, st);
     gather_scalars_kernel<<<1, 1, 0, st>>>(ctrl, word_tok_off, nw, doc_tok_off, nd, word_doc); launches++;
@@ -1062,15 +1076,15 @@ int encode_device_impl(tkz_ctx* ctx, const uint8_t* d_text, const uint64_t* d_do
                (uint32_t*)ctx->O().special.p, nullptr, (uint16_t*)ctx->O().ids16.p, (uint4*)ctx->O().spans.p};
     if (nw) {
         const uint32_t big_cap = (uint32_t)(N / EMIT_BIG + 16);
-        TRY(ensure(ctx, ctx->a_big, (size_t)big_cap * sizeof(uint4)));
-        BigList bl{(uint4*)ctx->a_big.p, (unsigned int*)(ctrl + 9) + 1, big_cap};
+        TRY(ensure(ctx, ctx->a_big, (size_t)big_cap * (sizeof(uint4) + sizeof(uint32_t))));
+        BigList bl{(uint4*)ctx->a_big.p, (unsigned int*)(ctrl + 9) + 1, big_cap, (uint32_t*)((uint4*)ctx->a_big.p + big_cap)};
         emit_words_kernel<<<(nw + 255) / 256, 256, 0, st>>>(ep, eo, nw, word_start, word_doc, word_tok_off, doc_word_off, doc_tok_off,
                                                             (const uint32_t*)ctx->a_pool_id.p, (const uint32_t*)ctx->a_pool_s.p,
-                                                            (const uint32_t*)ctx->a_pool_e.p, bl); launches++;
+                                                            (const uint32_t*)ctx->a_pool_e.p, bl, d_doc_off); launches++;
         emit_big_kernel<<<ctx->sm_count * 4, 256, 0, st>>>(ep, eo, bl, (const uint32_t*)ctx->a_pool_id.p, (const uint32_t*)ctx->a_pool_s.p,
                                                            (const uint32_t*)ctx->a_pool_e.p); launches++;
     }
-    if (P.has_padding && nd) {
+    if ((P.has_padding || ((ep.hf_flags & 1u) && ep.n_pre + ep.n_suf)) && nd) {
         emit_pad_kernel<<<(unsigned)(((uint64_t)nd * 32 + 255) / 256), 256, 0, st>>>(ep, eo, nd, word_tok_off, doc_word_off, doc_tok_off); launches++;
     }
     CK(cudaGetLastError());
@@ -1296,6 +1310,7 @@ extern "C" int tkz_encode_batch_compact(tkz_ctx* ctx, const uint8_t* text, const
     tkz_encode_params P{};
     if (params) P = *params;
     out->params = P;
+    if (P.hf_flags) { ctx->err = "the compact result does not carry hf_compat (template / document offsets): use tkz_encode_batch"; return TKZ_ERR_INVALID_ARG; }
     // on the device: truncation only; no padding slot and no constant array is materialised or copied
     tkz_encode_params Q = P;
     Q.has_padding = 0;

@@ -15,14 +15,22 @@ struct EmitParams {
     int has_pad; unsigned long long pad_length;
     uint32_t pad_id, pad_type_id; int pad_left;
     uint32_t outputs;
+    // hf_compat (tkz_encode_params.hf_flags; 0 = the reference): single-sequence template -- what processor.zig:41-152 declares
+    // and leaves as TODO -- and offsets relative to the document.  Only the per-occurrence pipeline serves it.
+    uint32_t hf_flags;
+    uint32_t n_pre, n_suf, pre_id[4], pre_type[4], suf_id[4], suf_type[4], seq_type;
 };
+__device__ __forceinline__ uint32_t tpl_added(const EmitParams& p) { return (p.hf_flags & 1u) ? p.n_pre + p.n_suf : 0u; }
 
 // slots a document occupies after truncate + pad
+// (*kept = real tokens kept; with a template the added tokens count against max_length, as tokenizers' post_process does,
+// and towards the padded length)
 __device__ __forceinline__ unsigned long long doc_out_len(const EmitParams& p, unsigned long long t, unsigned long long* kept) {
     unsigned long long k = t;
-    if (p.has_trunc && k > p.max_length) k = p.max_length;
+    const unsigned long long add = tpl_added(p);
+    if (p.has_trunc) { const unsigned long long budget = p.max_length > add ? p.max_length - add : 0; if (k > budget) k = budget; }
     *kept = k;
-    return (p.has_pad && k < p.pad_length) ? p.pad_length : k;
+    return (p.has_pad && k + add < p.pad_length) ? p.pad_length : k + add;
 }
 
 // per document: real token count -> output slot count
@@ -43,11 +51,12 @@ struct EmitOut { uint32_t* ids; uint32_t* offsets; uint32_t* attention; uint32_t
 // words with more than EMIT_BIG tokens (whole documents, MiB-long unbroken words) are not copied by one warp: they are
 // queued here and copied by the whole grid (emit_big_kernel)
 constexpr uint32_t EMIT_BIG = 2048;
-struct BigList { uint4* items; unsigned int* count; uint32_t cap; };     // item = {src pool position, token count, dst lo, dst hi}
-__device__ __forceinline__ bool big_push(const BigList& b, uint32_t src, uint32_t cnt, unsigned long long dst) {
+struct BigList { uint4* items; unsigned int* count; uint32_t cap; uint32_t* shift; };   // item = {src pool position, token count, dst lo, dst hi}; shift[] = offset base (hf_compat)
+__device__ __forceinline__ bool big_push(const BigList& b, uint32_t src, uint32_t cnt, unsigned long long dst, uint32_t shift = 0) {
     const uint32_t i = atomicAdd(b.count, 1u);
     if (i >= b.cap) return false;
     b.items[i] = make_uint4(src, cnt, (uint32_t)dst, (uint32_t)(dst >> 32));
+    if (b.shift) b.shift[i] = shift;
     return true;
 }
 
@@ -58,9 +67,19 @@ __device__ __forceinline__ void emit_real(const EmitParams& p, const EmitOut& o,
     emit_id(p, o, dst, id);
     if (p.outputs & 2u) reinterpret_cast<uint2*>(o.offsets)[dst] = make_uint2(s, e);
     if (p.outputs & 4u) o.attention[dst] = 1u;
-    if (p.outputs & 8u) o.type_ids[dst] = 0u;
+    const uint32_t ty = (p.hf_flags & 1u) ? p.seq_type : 0u;
+    if (p.outputs & 8u) o.type_ids[dst] = ty;
     if (p.outputs & 16u) o.special[dst] = 0u;
-    if (p.outputs & 128u) o.spans[dst] = make_uint4(id, s, e, 0u);
+    if (p.outputs & 128u) o.spans[dst] = make_uint4(id, s, e, ty & 0xFFu);
+}
+// a special token of the template: offsets (0, 0), special 1, attention 1 (SpanToken.initSpecial: flags.is_special, bit 0)
+__device__ __forceinline__ void emit_special(const EmitParams& p, const EmitOut& o, unsigned long long dst, uint32_t id, uint32_t ty) {
+    emit_id(p, o, dst, id);
+    if (p.outputs & 2u) reinterpret_cast<uint2*>(o.offsets)[dst] = make_uint2(0u, 0u);
+    if (p.outputs & 4u) o.attention[dst] = 1u;
+    if (p.outputs & 8u) o.type_ids[dst] = ty;
+    if (p.outputs & 16u) o.special[dst] = 1u;
+    if (p.outputs & 128u) o.spans[dst] = make_uint4(id, 0u, 0u, (ty & 0xFFu) | 0x0100u);
 }
 
 // one lane per word; words with many tokens are copied by the whole warp
@@ -69,11 +88,11 @@ __global__ void __launch_bounds__(256) emit_words_kernel(EmitParams p, EmitOut o
                                                          const uint32_t* __restrict__ word_tok_off, const uint32_t* __restrict__ doc_word_off,
                                                          const unsigned long long* __restrict__ doc_tok_off,
                                                          const uint32_t* __restrict__ pool_id, const uint32_t* __restrict__ pool_s,
-                                                         const uint32_t* __restrict__ pool_e, BigList bl) {
+                                                         const uint32_t* __restrict__ pool_e, BigList bl, const uint64_t* __restrict__ doc_off) {
     const uint32_t FULL = 0xFFFFFFFFu;
     const uint32_t lane = lane_id();
     const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
-    uint32_t cnt = 0, src = 0; unsigned long long dst = 0; unsigned long long room = 0;
+    uint32_t cnt = 0, src = 0, sh = 0; unsigned long long dst = 0; unsigned long long room = 0;
     if (w < n_words) {
         const uint32_t t0 = word_tok_off[w];
         cnt = word_tok_off[w + 1] - t0;
@@ -85,25 +104,26 @@ __global__ void __launch_bounds__(256) emit_words_kernel(EmitParams p, EmitOut o
             const unsigned long long olen = doc_out_len(p, doc_t, &kept);
             const unsigned long long j0 = (unsigned long long)t0 - doc_t0;          // index of the word's first token in its document
             room = j0 < kept ? kept - j0 : 0;                                       // truncation: tokens j >= kept are dropped
-            const unsigned long long shift = (p.has_pad && p.pad_left) ? olen - kept : 0;
+            const unsigned long long shift = ((p.has_pad && p.pad_left) ? olen - kept - tpl_added(p) : 0) + ((p.hf_flags & 1u) ? p.n_pre : 0u);
             dst = doc_tok_off[d] + shift + j0;
             src = word_start[w];
+            if (p.hf_flags & 2u) sh = src - (uint32_t)doc_off[d];                   // pre-token start within its document
             if ((unsigned long long)cnt > room) cnt = (uint32_t)room;
         }
     }
     // short words: each lane copies its own tokens
     if (cnt > 0 && cnt <= 4) {
-        for (uint32_t k = 0; k < cnt; k++) emit_real(p, o, dst + k, pool_id[src + k], pool_s[src + k], pool_e[src + k]);
+        for (uint32_t k = 0; k < cnt; k++) emit_real(p, o, dst + k, pool_id[src + k], pool_s[src + k] + sh, pool_e[src + k] + sh);
     }
     // very long words: queued for the grid-wide copy
-    if (cnt > EMIT_BIG && big_push(bl, src, cnt, dst)) cnt = 0;
+    if (cnt > EMIT_BIG && big_push(bl, src, cnt, dst, sh)) cnt = 0;
     // long words: warp-cooperative copy
     uint32_t big = __ballot_sync(FULL, cnt > 4);
     while (big) {
         const int l = __ffs(big) - 1; big &= big - 1;
-        const uint32_t c = __shfl_sync(FULL, cnt, l), s = __shfl_sync(FULL, src, l);
+        const uint32_t c = __shfl_sync(FULL, cnt, l), s = __shfl_sync(FULL, src, l), hs = __shfl_sync(FULL, sh, l);
         const unsigned long long dd = __shfl_sync(FULL, dst, l);
-        for (uint32_t k = lane; k < c; k += 32) emit_real(p, o, dd + k, pool_id[s + k], pool_s[s + k], pool_e[s + k]);
+        for (uint32_t k = lane; k < c; k += 32) emit_real(p, o, dd + k, pool_id[s + k], pool_s[s + k] + hs, pool_e[s + k] + hs);
     }
 }
 
@@ -113,9 +133,10 @@ __global__ void __launch_bounds__(256) emit_big_kernel(EmitParams p, EmitOut o, 
     uint32_t n = *bl.count; if (n > bl.cap) n = bl.cap;
     for (uint32_t k = 0; k < n; k++) {
         const uint4 it = bl.items[k];
+        const uint32_t sh = bl.shift ? bl.shift[k] : 0u;
         const unsigned long long dst = (unsigned long long)it.z | ((unsigned long long)it.w << 32);
         for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < it.y; i += gridDim.x * blockDim.x)
-            emit_real(p, o, dst + i, pool_id[it.x + i], pool_s[it.x + i], pool_e[it.x + i]);
+            emit_real(p, o, dst + i, pool_id[it.x + i], pool_s[it.x + i] + sh, pool_e[it.x + i] + sh);
     }
 }
 
@@ -128,9 +149,16 @@ __global__ void __launch_bounds__(256) emit_pad_kernel(EmitParams p, EmitOut o, 
     const unsigned long long t = word_tok_off[doc_word_off[d + 1]] - word_tok_off[doc_word_off[d]];
     unsigned long long kept;
     const unsigned long long olen = doc_out_len(p, t, &kept);
-    if (olen == kept) return;
-    const unsigned long long base = doc_tok_off[d] + (p.pad_left ? 0 : kept);
-    const unsigned long long npad = olen - kept;
+    const unsigned long long full = kept + tpl_added(p);
+    if (p.hf_flags & 1u) {
+        // the template's special tokens around the kept tokens
+        const unsigned long long b0 = doc_tok_off[d] + ((p.has_pad && p.pad_left) ? olen - full : 0);
+        if (lane < p.n_pre) emit_special(p, o, b0 + lane, p.pre_id[lane], p.pre_type[lane]);
+        if (lane >= 8 && lane - 8 < p.n_suf) emit_special(p, o, b0 + p.n_pre + kept + (lane - 8), p.suf_id[lane - 8], p.suf_type[lane - 8]);
+    }
+    if (olen == full) return;
+    const unsigned long long base = doc_tok_off[d] + (p.pad_left ? 0 : full);
+    const unsigned long long npad = olen - full;
     for (unsigned long long k = lane; k < npad; k += 32) {
         const unsigned long long dst = base + k;
         emit_id(p, o, dst, p.pad_id);

@@ -66,6 +66,10 @@ struct tkzh_tokenizer {
     bool has_norm = false; std::vector<Op> norm_ops;
     bool has_pretok = false; std::vector<Op> pt_ops;
     bool has_post = false;
+    // hf_compat (beyond the reference): the post-processor's single-sequence template, parsed but only applied when the caller
+    // switches the mode on (tkzh_set_hf_compat); the reference's processors are no-ops (processor.zig:69-74, 147-152)
+    bool has_template = false; uint32_t hf_flags = 0;
+    std::vector<std::pair<uint32_t, uint32_t>> tpl_prefix, tpl_suffix; uint32_t tpl_seq_type = 0;    // (special id, type id)
     int decoder_kind = 0;
     std::vector<AddedToken> added_tokens;
     SideVocab added_vocab;
@@ -153,6 +157,43 @@ void build_desc(tkzh_tokenizer* t) {
 }
 
 int fail(tkzh_tokenizer* t, int code, const char* msg) { g_load_error = msg; delete t; return code; }
+
+int64_t int_of(const Value* v, int64_t dflt) { return (v && v->kind == Value::Integer) ? v->i : dflt; }
+// hf_compat: the single-sequence template  specials* $A specials*  of a post_processor as tokenizers 0.22 serialises it --
+// TemplateProcessing {single: [{SpecialToken: {id, type_id}} | {Sequence: {id, type_id}}], special_tokens: {name: {ids}}} or
+// BertProcessing {sep: [token, id], cls: [token, id]}.  Anything else (a second sequence, an unknown special token, more than
+// TKZ_TPL_MAX ids on a side) leaves has_template false.
+void parse_template(tkzh_tokenizer* t, const Value* pp, const std::string& type) {
+    std::vector<std::pair<uint32_t, uint32_t>> pre, suf; uint32_t seq_type = 0;
+    if (type == "BertProcessing") {
+        const Value* cls = pp->get("cls"); const Value* sep = pp->get("sep");
+        if (!cls || !sep || cls->kind != Value::Array || sep->kind != Value::Array || cls->arr.size() != 2 || sep->arr.size() != 2) return;
+        if (cls->arr[1]->kind != Value::Integer || sep->arr[1]->kind != Value::Integer) return;
+        pre.push_back({(uint32_t)cls->arr[1]->i, 0u}); suf.push_back({(uint32_t)sep->arr[1]->i, 0u});
+    } else if (type == "TemplateProcessing") {
+        const Value* single = pp->get("single"); const Value* specials = pp->get("special_tokens");
+        if (!single || single->kind != Value::Array) return;
+        bool seen = false;
+        for (const auto& piece : single->arr) {
+            if (piece->kind != Value::Object) return;
+            if (const Value* sq = piece->get("Sequence")) {
+                const std::string* id = str_field(sq, "id");
+                if (seen || !id || *id != "A") return;
+                seen = true; seq_type = (uint32_t)int_of(sq->get("type_id"), 0);
+            } else if (const Value* sp = piece->get("SpecialToken")) {
+                const std::string* id = str_field(sp, "id");
+                const Value* def = (id && specials) ? specials->get(*id) : nullptr;
+                const Value* ids = def ? def->get("ids") : nullptr;
+                if (!ids || ids->kind != Value::Array) return;
+                const uint32_t ty = (uint32_t)int_of(sp->get("type_id"), 0);
+                for (const auto& x : ids->arr) { if (x->kind != Value::Integer) return; (seen ? suf : pre).push_back({(uint32_t)x->i, ty}); }
+            } else return;
+        }
+        if (!seen) return;
+    } else return;
+    if (pre.size() > TKZ_TPL_MAX || suf.size() > TKZ_TPL_MAX) return;
+    t->has_template = true; t->tpl_prefix = pre; t->tpl_suffix = suf; t->tpl_seq_type = seq_type;
+}
 
 int load(const char* json, uint64_t len, tkzh_tokenizer** out) {
     tkzh_tokenizer* t = new tkzh_tokenizer();
@@ -255,6 +296,7 @@ int load(const char* json, uint64_t len, tkzh_tokenizer** out) {
     if (ppv && ppv->kind == Value::Object) {
         const std::string* ty = str_field(ppv, "type");
         if (ty && (*ty == "TemplateProcessing" || *ty == "BertProcessing")) t->has_post = true;
+        if (ty) parse_template(t, ppv, *ty);
     }
     for (const AddedToken& a : t->added_tokens) t->added_vocab.add(a, a.special);                          // lib.zig:66-72
     build_desc(t);
@@ -335,13 +377,23 @@ extern "C" int tkzh_set_pretokenizer(tkzh_tokenizer* t, const int32_t* kinds, in
 extern "C" int tkzh_encode_batch(tkzh_tokenizer* t, const uint8_t* text, const uint64_t* doc_off, uint64_t n_docs, int add_special_tokens,
                                  uint32_t outputs, tkz_batch_result* out) {
     if (!t || !out) return TKZ_ERR_INVALID_ARG;
-    (void)add_special_tokens;        // lib.zig:143-147 -> config.zig:551-555: every post-processor is a no-op
+    // lib.zig:143-147 -> config.zig:551-555: every post-processor is a no-op, add_special_tokens changes nothing -- unless the
+    // caller opted into hf_compat (tkzh_set_hf_compat), where it decides whether the template's special tokens go in
     int rc = sync_device(t);
     if (rc != TKZ_OK) return rc;
     tkz_encode_params p{};
     p.has_truncation = t->has_trunc; p.max_length = t->max_length;                // lib.zig:150-152
     p.has_padding = t->has_pad && t->pad_has_length; p.pad_length = t->pad_length; // lib.zig:155-157, encoding.zig:386
     p.pad_id = t->pad_id; p.pad_type_id = t->pad_type_id; p.pad_left = t->pad_left; p.outputs = outputs;
+    p.hf_flags = t->hf_flags & TKZ_HF_DOC_OFFSETS;
+    if ((t->hf_flags & TKZ_HF_TEMPLATE) && t->has_template) {
+        p.hf_flags |= TKZ_HF_TEMPLATE; p.tpl_seq_type = t->tpl_seq_type;
+        if (add_special_tokens) {
+            p.tpl_n_prefix = (uint32_t)t->tpl_prefix.size(); p.tpl_n_suffix = (uint32_t)t->tpl_suffix.size();
+            for (size_t i = 0; i < t->tpl_prefix.size(); i++) { p.tpl_prefix_id[i] = t->tpl_prefix[i].first; p.tpl_prefix_type[i] = t->tpl_prefix[i].second; }
+            for (size_t i = 0; i < t->tpl_suffix.size(); i++) { p.tpl_suffix_id[i] = t->tpl_suffix[i].first; p.tpl_suffix_type[i] = t->tpl_suffix[i].second; }
+        }
+    }
     rc = tkz_encode_batch(t->ctx, text, doc_off, n_docs, &p, out);
     if (rc != TKZ_OK) t->err = tkz_last_error(t->ctx);
     return rc;
@@ -450,6 +502,13 @@ extern "C" uint64_t tkzh_merge_count(tkzh_tokenizer* t) { return t->merge_pairs.
 extern "C" int tkzh_has_normalizer(tkzh_tokenizer* t) { return t->has_norm; }
 extern "C" int tkzh_has_pretokenizer(tkzh_tokenizer* t) { return t->has_pretok; }
 extern "C" int tkzh_has_post_processor(tkzh_tokenizer* t) { return t->has_post; }
+// hf_compat switch (TKZ_HF_* flags; 0 = the reference's behaviour, the default).  Returns 1 when the tokenizer.json carried a
+// single-sequence template this mode can apply, 0 when TKZ_HF_TEMPLATE will have no effect.
+extern "C" int tkzh_set_hf_compat(tkzh_tokenizer* t, uint32_t flags) {
+    if (!t) return TKZ_ERR_INVALID_ARG;
+    t->hf_flags = flags & (TKZ_HF_TEMPLATE | TKZ_HF_DOC_OFFSETS);
+    return t->has_template ? 1 : 0;
+}
 extern "C" uint64_t tkzh_added_token_count(tkzh_tokenizer* t) { return t->added_tokens.size(); }
 extern "C" int tkzh_added_token(tkzh_tokenizer* t, uint64_t i, const uint8_t** content, uint64_t* len, int64_t* id, int* special) {
     if (i >= t->added_tokens.size()) return TKZ_ERR_INVALID_ARG;

@@ -62,7 +62,18 @@ pub const EncodeParams = extern struct {
     fast: i32 = 0, // FastTokenizer.encode semantics (src/lib.zig:356-422)
     fast_max_sequence_length: u32 = 0, // 0 = 8192
     fast_max_tokens: u32 = 0, // 0 = 512
+    // hf_compat (beyond the reference, opt-in; 0 = reference behaviour): single-sequence template + document-relative offsets
+    hf_flags: u32 = 0, // HF_TEMPLATE | HF_DOC_OFFSETS
+    tpl_n_prefix: u32 = 0,
+    tpl_n_suffix: u32 = 0,
+    tpl_prefix_id: [4]u32 = .{ 0, 0, 0, 0 },
+    tpl_prefix_type: [4]u32 = .{ 0, 0, 0, 0 },
+    tpl_suffix_id: [4]u32 = .{ 0, 0, 0, 0 },
+    tpl_suffix_type: [4]u32 = .{ 0, 0, 0, 0 },
+    tpl_seq_type: u32 = 0,
 };
+pub const HF_TEMPLATE: u32 = 1;
+pub const HF_DOC_OFFSETS: u32 = 2;
 
 pub const BatchResult = extern struct {
     n_docs: u64,

@@ -1,6 +1,2 @@
-timeout 900 python -m pytest tests -m gpu -x -q -k "windowed or grid or long_words or cascades or skewed or synthesised or bytelevel or whole or huge or malformed" 2>&1 | tail -3
-for w in c2a c5a; do
-  timeout 300 python bench.py --workload $w --no-configs --no-e2e --no-cpu-baseline --no-strong --steps 5 --warmup 3 > gpurun_out/bit_$w.json 2> gpurun_out/bit_$w.err; python - <<PY
-import json; d=json.loads(open("gpurun_out/bit_$w.json").read().strip().splitlines()[-1]); print("$w", d["value"], d["roofline"]["stage_ms_per_step"], d["parity"] and d["parity"]["ok"])
-PY
-done
+timeout 900 python -m pytest tests/test_gpu_hf_compat.py -x -q 2>&1 | tail -15
+timeout 1200 python -m pytest tests -m gpu -x -q -k "not hf_compat and (truncation or padding or kats or occurrence or struct or span)" 2>&1 | tail -3
