@@ -568,6 +568,8 @@ def run_ours(args, rank, local_rank, world):
             c["roofline"] = {"frac": o2["roofline"]["frac"], "achieved": o2["roofline"]["achieved"], "algorithmic_bytes_per_step": o2["roofline"]["algorithmic_bytes_per_step"],
                              "stage_ms_per_step": o2["roofline"]["stage_ms_per_step"]}
             c["e2e"] = None if o2["e2e"] is None else {k: o2["e2e"][k] for k in ("value", "unit", "ms_per_step", "h2d_bytes_per_step", "d2h_bytes_per_step", "wire_format")}
+            if "hf_compat" in o2:
+                c["hf_compat"] = o2["hf_compat"]
             configs[name] = c
             W2.close(); del W2
             torch.cuda.empty_cache()
