@@ -75,6 +75,7 @@ struct tkz_ctx {
     bool has_iso = false;                 // the class table isolates some byte (punctuation split)
     ClassRanges cr{}, cr_post{};          // byte classes as ranges (raw bytes / bytes already normalised by K0)
     bool stage_bulk = true;               // TKZ_STAGE=ldg: pass A stages its slices with plain loads instead of bulk copies (A/B switch)
+    bool pad_fill = true;                 // TKZ_PAD_FILL=0: padding slots always by one warp per document (A/B switch)
     bool force_lut = false;               // TKZ_CLASSIFY=lut: per-byte look-up even when the class table fits ranges (A/B switch)
     DevBuf a_huge_w, a_huge_base, a_huge_done, a_grid_state, a_grid_words;   // bpe_grid_kernel (tkz_bpe_grid.cuh)
     bool use_grid = true;                 // TKZ_NO_GRID=1: huge words stay with one block each (A/B switch of the parity tests)
@@ -259,6 +260,7 @@ extern "C" int tkz_ctx_create(int device, void* stream, uint64_t arena_hint_byte
     if (const char* e = getenv("TKZ_NO_DEDUP")) ctx->use_dedup = !(e[0] == '1');     // A/B switch for the parity tests
     if (const char* e = getenv("TKZ_CLASSIFY")) ctx->force_lut = (e[0] == 'l');
     if (const char* e = getenv("TKZ_STAGE")) ctx->stage_bulk = !(e[0] == 'l');
+    if (const char* e = getenv("TKZ_PAD_FILL")) ctx->pad_fill = e[0] != '0';
     if (const char* e = getenv("TKZ_NO_GRID")) ctx->use_grid = !(e[0] == '1');
     if (const char* e = getenv("TKZ_GRID_MIN_LEN")) { const long long v = atoll(e); if (v > (long long)BB_WARP_MAX) ctx->grid_min_len = (uint32_t)v; }
     {
@@ -850,12 +852,27 @@ int encode_slices(tkz_ctx* ctx, const DevModel& m, const ClassRanges& cr, const 
     ea.doc_tok_local = ta.doc_tok_local; ea.doc_tok_start = (const uint32_t*)ctx->a_doc_tok_start.p;
     ea.doc_tok_off = doc_tok_off; ea.errw = ctrl; ea.err_code = m.kind == TKZ_MODEL_BPE ? TKZ_ECODE_UTF8 : TKZ_ECODE_UNK;
     ea.big = BigList{(uint4*)ctx->a_big.p, (unsigned int*)(ctrl + 16), big_cap};
+    // mostly padding (pad to 512 around a few dozen tokens): fill every array with its padding value first, at streaming-store
+    // speed, and let pass B overwrite the real tokens; else one warp per document fills the gaps afterwards
+    const bool pad_fill = P.has_padding && nd && ctx->pad_fill && T >= 2 * T_real;
+    if (pad_fill) {
+        const unsigned fg = (unsigned)ctx->sm_count * 8;
+        auto fill = [&](void* p, uint64_t bytes, uint4 v) { fill16_kernel<<<fg, 256, 0, st>>>((uint4*)p, bytes, v); launches++; };
+        auto rep = [](uint32_t x) { return make_uint4(x, x, x, x); };
+        if (P.outputs & TKZ_OUT_IDS_U16) fill(eo.ids16, T * 2, rep(P.pad_id | (P.pad_id << 16))); else fill(eo.ids, T * 4, rep(P.pad_id));
+        if (P.outputs & TKZ_OUT_OFFSETS) fill(eo.offsets, T * 8, rep(0u));
+        if (P.outputs & TKZ_OUT_ATTENTION) fill(eo.attention, T * 4, rep(0u));
+        if (P.outputs & TKZ_OUT_TYPE_IDS) fill(eo.type_ids, T * 4, rep(P.pad_type_id));
+        if (P.outputs & TKZ_OUT_SPECIAL) fill(eo.special, T * 4, rep(1u));
+        if (P.outputs & TKZ_OUT_OFFSETS_PACKED) fill(eo.offsets16, T * 2, rep(0u));
+        if (P.outputs & TKZ_OUT_SPAN_TOKENS) fill(eo.spans, T * 16, make_uint4(P.pad_id, 0u, 0u, 0x0400u));
+    }
     const uint32_t egrid = (uint32_t)std::min<uint64_t>(((uint64_t)n_slices + TW_WARPS - 1) / TW_WARPS, (uint64_t)ctx->sm_count * 16);
     if (plain) launch_slice_emit<true>(ea, ep, eo, egrid, st);
     else launch_slice_emit<false>(ea, ep, eo, egrid, st);
     launches++;
     if (n_long) { emit_big_kernel<<<ctx->sm_count * 4, 256, 0, st>>>(ep, eo, ea.big, ea.pool_id, ea.pool_s, ea.pool_e); launches++; }
-    if (P.has_padding && nd) {
+    if (P.has_padding && nd && !pad_fill) {
         emit_pad_real_kernel<<<(unsigned)(((uint64_t)nd * 32 + 255) / 256), 256, 0, st>>>(ep, eo, nd, (const uint32_t*)ctx->a_doc_real.p, doc_tok_off); launches++;
     }
     CK(cudaGetLastError());

@@ -170,4 +170,18 @@ __global__ void __launch_bounds__(256) emit_pad_kernel(EmitParams p, EmitOut o, 
     }
 }
 
+// whole-array fill with one 16-byte pattern (grid-stride 16-byte stores; the last partial 16 bytes in 2-byte steps by one
+// thread).  When most slots of a batch are padding (BERT-style pad to 512 around ~30 tokens), filling the arrays with the
+// padding values at streaming-store speed BEFORE the real tokens are written beats one warp per document writing the gaps.
+__global__ void __launch_bounds__(256) fill16_kernel(uint4* __restrict__ p, unsigned long long nbytes, uint4 v) {
+    const unsigned long long n16 = nbytes >> 4;
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += stride) __stcs(p + i, v);
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        const uint16_t h[8] = {(uint16_t)v.x, (uint16_t)(v.x >> 16), (uint16_t)v.y, (uint16_t)(v.y >> 16), (uint16_t)v.z, (uint16_t)(v.z >> 16), (uint16_t)v.w, (uint16_t)(v.w >> 16)};
+        uint16_t* q = reinterpret_cast<uint16_t*>(p + n16);
+        for (uint32_t k = 0; k < (uint32_t)((nbytes & 15ull) >> 1); k++) q[k] = h[k];
+    }
+}
+
 }  // namespace tkz
