@@ -470,7 +470,7 @@ def run_ours(args, rank, local_rank, world):
             out["device_variants"] = extra
         if workload == "c3":
             # the same batch in hf_compat mode (beyond the reference, opt-in: [CLS] $A [SEP] from the JSON's TemplateProcessing and
-            # document-relative offsets); served by the per-occurrence pipeline.  Parity: tests/test_gpu_hf_compat.py
+            # document-relative offsets) through the same slice pipeline.  Parity: tests/test_gpu_hf_compat.py
             ph = W.tok.params(outputs)
             ph.hf_flags = tz.HF_TEMPLATE | tz.HF_DOC_OFFSETS
             ph.tpl_n_prefix, ph.tpl_n_suffix = 1, 1
@@ -478,7 +478,8 @@ def run_ours(args, rank, local_rank, world):
             a3 = W.time_device(outputs, max(2, steps // 2), 1, stream, barrier, params=ph)
             ms3 = allmax(a3["ms_step"])
             out["hf_compat"] = {"ms_per_step": ms3, "value": all_bytes / (ms3 * 1e-3) / 1e9, "unit": "GB/s", "flags": "TKZ_HF_TEMPLATE | TKZ_HF_DOC_OFFSETS",
-                                "pipeline": "per-occurrence pipeline", "stage_ms_per_step": dict(zip(["split", "model", "scan", "emit", "total_kernels"], [round(x, 4) for x in a3["stage_ms"]]))}
+                                "pipeline": {0: "per-occurrence pipeline", 2: "slice pipeline (2 passes)"}.get(a3.get("path"), "?"),
+                                "stage_ms_per_step": dict(zip(["split", "model", "scan", "emit", "total_kernels"], [round(x, 4) for x in a3["stage_ms"]]))}
         e2e = None
         if not args.no_e2e:
             e_steps = max(1, min(steps, args.e2e_steps))
@@ -598,7 +599,7 @@ def run_ours(args, rank, local_rank, world):
             "config": config_of(args.workload, args.size_mib),
             "workload_stats": {k: head[k] for k in ("bytes_per_gpu", "docs_per_gpu", "words_per_gpu", "tokens_per_gpu", "unique_words_last_batch", "long_words_last_batch",
                                                     "sub_batches", "outputs_mask", "pipeline")},
-            "roofline": head["roofline"], "device_variants": head.get("device_variants"), "cpu_baseline": cb, "e2e": head["e2e"],
+            "roofline": head["roofline"], "device_variants": head.get("device_variants"), "hf_compat": head.get("hf_compat"), "cpu_baseline": cb, "e2e": head["e2e"],
             "gpu_launches": int(round(head["gpu_launches_per_step"] * args.steps)), "clocks": clocks,
             "parity_checked_vs_oracle": None if head["parity_checked_vs_oracle"] is None else head["parity_checked_vs_oracle"]["ok"],
             "parity": head["parity_checked_vs_oracle"], "configs": configs, "strong_scaling": strong}

@@ -16,17 +16,26 @@ from test_hf_compat_oracle import CASES, VEC, expected_arrays, oracle_for
 pytestmark = pytest.mark.gpu
 
 
-def gpu_for(suite, case):
-    t = tz.Tokenizer.from_json(suite["tokenizer_json"], device=0)
+MODES = ("slices", "occurrence")
+
+
+def gpu_for(suite, case, mode="slices"):
+    """both device pipelines serve the mode: the slice pipeline (default) and the per-occurrence pipeline (TKZ_NO_DEDUP=1)"""
+    os.environ["TKZ_NO_DEDUP"] = "1" if mode == "occurrence" else "0"
+    try:
+        t = tz.Tokenizer.from_json(suite["tokenizer_json"], device=0)
+    finally:
+        os.environ["TKZ_NO_DEDUP"] = "0"
     assert t.set_hf_compat(tz.HF_TEMPLATE | tz.HF_DOC_OFFSETS)
     t.truncation = None if case["truncation"] is None else {"max_length": case["truncation"]}
     t.padding = case["padding"]
     return t
 
 
+@pytest.mark.parametrize("mode", MODES)
 @pytest.mark.parametrize("suite,case", CASES, ids=[f"{s['name']}-{c['name']}" for s, c in CASES])
-def test_gpu_hf_mode_equals_tokenizers(suite, case):
-    t = gpu_for(suite, case)
+def test_gpu_hf_mode_equals_tokenizers(suite, case, mode):
+    t = gpu_for(suite, case, mode)
     r = t.encode_batch([x.encode() for x in suite["texts"]], add_special_tokens=case["add_special_tokens"])
     doc_off, ids, offs, attn, tids, spec = expected_arrays(case)
     assert r.doc_tok_off.tolist() == doc_off.tolist()
@@ -59,7 +68,8 @@ def ascii_corpus(seed, n_docs, words, long_word_every=0):
 @pytest.mark.parametrize("si", [0, 2, 3])
 @pytest.mark.parametrize("trunc,pad", [(None, None), (32, {"length": 40, "pad_id": 0, "pad_type_id": 0, "direction": "right"}),
                                        (20, {"length": 33, "pad_id": 1, "pad_type_id": 1, "direction": "left"})])
-def test_gpu_hf_mode_equals_oracle_on_random_corpora(si, trunc, pad):
+@pytest.mark.parametrize("mode", MODES)
+def test_gpu_hf_mode_equals_oracle_on_random_corpora(si, trunc, pad, mode):
     suite = VEC["suites"][si]
     js = suite["tokenizer_json"]
     vocab = json.loads(js)["model"]["vocab"]
@@ -68,9 +78,10 @@ def test_gpu_hf_mode_equals_oracle_on_random_corpora(si, trunc, pad):
     for add in (True, False):
         case = {"add_special_tokens": add, "truncation": trunc, "padding": pad}
         o = oracle_for(suite, case)
-        t = gpu_for(suite, case)
+        t = gpu_for(suite, case, mode)
         ref = o.encode_batch(docs, algo=1)
         got = t.encode_batch(docs, add_special_tokens=add)
+        assert t.stats().path == (0 if mode == "occurrence" else 2)
         assert np.array_equal(got.doc_tok_off, ref.doc_tok_off)
         assert np.array_equal(got.ids, ref.ids)
         assert np.array_equal(got.offsets, ref.offsets)
@@ -80,10 +91,11 @@ def test_gpu_hf_mode_equals_oracle_on_random_corpora(si, trunc, pad):
         t.close()
 
 
-def test_span_tokens_carry_the_template():
+@pytest.mark.parametrize("mode", MODES)
+def test_span_tokens_carry_the_template(mode):
     suite = VEC["suites"][2]                                      # [CLS]:0 [MASK]:1 $A:1 [SEP]:1 [SEP]:0
     case = {"add_special_tokens": True, "truncation": 8, "padding": {"length": 12, "pad_id": 0, "pad_type_id": 0, "direction": "right"}}
-    t = gpu_for(suite, case)
+    t = gpu_for(suite, case, mode)
     r = t.encode_batch([b"ka lo mi", b""], outputs=tz.OUT_ALL | tz.OUT_SPAN_TOKENS)
     sp = r.span_tokens.reshape(-1, 4)
     assert len(sp) == 24

@@ -672,6 +672,15 @@ int launch_bpe(tkz_ctx* ctx, const DevModel& m, const uint8_t* d_text, const uin
     return TKZ_OK;
 }
 
+// hf_compat fields of the emit parameters (tkz_encode_params.hf_flags / tpl_*; validated in encode_device_impl)
+void emit_params_hf(EmitParams& ep, const tkz_encode_params& P) {
+    if (!P.hf_flags) return;
+    ep.hf_flags = P.hf_flags; ep.n_pre = P.tpl_n_prefix; ep.n_suf = P.tpl_n_suffix; ep.seq_type = P.tpl_seq_type;
+    for (uint32_t i = 0; i < TKZ_TPL_MAX; i++) {
+        ep.pre_id[i] = P.tpl_prefix_id[i]; ep.pre_type[i] = P.tpl_prefix_type[i]; ep.suf_id[i] = P.tpl_suffix_id[i]; ep.suf_type[i] = P.tpl_suffix_type[i];
+    }
+}
+
 // The slice pipeline (tkz_slices.cuh).  Capacities that depend on the text (token stream, record pool, word table) are
 // estimated from the batch and from what earlier batches of the context needed; when pass A runs out of one of them the
 // call returns TKZ_RETRY_WORST and the caller runs it again with worst-case capacities (tokens <= bytes), never truncated.
@@ -702,7 +711,7 @@ int encode_slices(tkz_ctx* ctx, const DevModel& m, const ClassRanges& cr, const 
     unsigned long long* hctrl = (unsigned long long*)ctx->h_ctrl.p;
     const uint64_t n_docs = nd;
     const uint32_t n_slices = (uint32_t)(N / TW_SLICE + 1);
-    const bool plain = !P.has_truncation && !P.has_padding;
+    const bool plain = !P.has_truncation && !P.has_padding && !P.hf_flags;        // (hf_compat: per-document destinations and offsets)
     // ---- capacities: from the text size and from what earlier batches of this context needed
     uint64_t want = N / 32; if (want < (1u << 16)) want = 1u << 16; if (want > (1u << 22)) want = 1u << 22;
     if (want < ctx->tw_uniq_hist * 4) want = ctx->tw_uniq_hist * 4;          // load factor <= 1/4
@@ -804,6 +813,7 @@ int encode_slices(tkz_ctx* ctx, const DevModel& m, const ClassRanges& cr, const 
 
     // ---- tokens per tile -> token base per tile; CSR offsets
     EmitParams ep{P.has_truncation, P.max_length, P.has_padding, P.pad_length, P.pad_id, P.pad_type_id, P.pad_left, P.outputs};
+    emit_params_hf(ep, P);
     launches += exclusive_scan<uint32_t>(ta.slice_ntok, n_slices, ta.slice_ntok, (unsigned long long*)ctx->a_scan_tmp.p, st);
     unsigned long long* doc_tok_off = (unsigned long long*)ctx->O().doc_tok_off.p;
     if (!plain) {
@@ -842,7 +852,7 @@ int encode_slices(tkz_ctx* ctx, const DevModel& m, const ClassRanges& cr, const 
     EmitOut eo{(uint32_t*)ctx->O().ids.p, (uint32_t*)ctx->O().off.p, (uint32_t*)ctx->O().attn.p, (uint32_t*)ctx->O().type.p,
                (uint32_t*)ctx->O().special.p, (uint16_t*)ctx->O().off16.p, (uint16_t*)ctx->O().ids16.p, (uint4*)ctx->O().spans.p};
     const uint32_t big_cap = (uint32_t)(N / EMIT_BIG + 16);
-    TRY(ensure(ctx, ctx->a_big, (size_t)big_cap * sizeof(uint4)));
+    TRY(ensure(ctx, ctx->a_big, (size_t)big_cap * (sizeof(uint4) + sizeof(uint32_t))));
     SliceEmitArgs ea{};
     ea.doc_off = d_doc_off; ea.n_docs = nd; ea.n_slices = n_slices; ea.slice_doc_lo = ta.slice_doc_lo;
     ea.tok_id = ta.tok_id; ea.tok2 = ta.tok2;
@@ -851,7 +861,7 @@ int encode_slices(tkz_ctx* ctx, const DevModel& m, const ClassRanges& cr, const 
     ea.pool_id = (const uint32_t*)ctx->a_pool_id.p; ea.pool_s = (const uint32_t*)ctx->a_pool_s.p; ea.pool_e = (const uint32_t*)ctx->a_pool_e.p;
     ea.doc_tok_local = ta.doc_tok_local; ea.doc_tok_start = (const uint32_t*)ctx->a_doc_tok_start.p;
     ea.doc_tok_off = doc_tok_off; ea.errw = ctrl; ea.err_code = m.kind == TKZ_MODEL_BPE ? TKZ_ECODE_UTF8 : TKZ_ECODE_UNK;
-    ea.big = BigList{(uint4*)ctx->a_big.p, (unsigned int*)(ctrl + 16), big_cap};
+    ea.big = BigList{(uint4*)ctx->a_big.p, (unsigned int*)(ctrl + 16), big_cap, (uint32_t*)((uint4*)ctx->a_big.p + big_cap)};
     // mostly padding (pad to 512 around a few dozen tokens): fill every array with its padding value first, at streaming-store
     // speed, and let pass B overwrite the real tokens; else one warp per document fills the gaps afterwards
     const bool pad_fill = P.has_padding && nd && ctx->pad_fill && T >= 2 * T_real;
@@ -872,8 +882,9 @@ int encode_slices(tkz_ctx* ctx, const DevModel& m, const ClassRanges& cr, const 
     else launch_slice_emit<false>(ea, ep, eo, egrid, st);
     launches++;
     if (n_long) { emit_big_kernel<<<ctx->sm_count * 4, 256, 0, st>>>(ep, eo, ea.big, ea.pool_id, ea.pool_s, ea.pool_e); launches++; }
-    if (P.has_padding && nd && !pad_fill) {
-        emit_pad_real_kernel<<<(unsigned)(((uint64_t)nd * 32 + 255) / 256), 256, 0, st>>>(ep, eo, nd, (const uint32_t*)ctx->a_doc_real.p, doc_tok_off); launches++;
+    const bool frame = (ep.hf_flags & 1u) && ep.n_pre + ep.n_suf;                     // hf_compat: the template's special tokens
+    if (((P.has_padding && !pad_fill) || frame) && nd) {
+        emit_pad_real_kernel<<<(unsigned)(((uint64_t)nd * 32 + 255) / 256), 256, 0, st>>>(ep, eo, nd, (const uint32_t*)ctx->a_doc_real.p, doc_tok_off, P.has_padding && !pad_fill); launches++;
     }
     CK(cudaGetLastError());
     CK(cudaEventRecord(ctx->ev[4], st));
@@ -924,11 +935,16 @@ int encode_device_impl(tkz_ctx* ctx, const uint8_t* d_text, const uint64_t* d_do
         P.has_truncation = 1; P.max_length = P.fast_max_tokens; P.has_padding = 0;
     }
     if (P.hf_flags) {
-        // hf_compat (beyond the reference, opt-in): served by the per-occurrence pipeline only
+        // hf_compat (beyond the reference, opt-in)
         if (P.hf_flags & ~(uint32_t)(TKZ_HF_TEMPLATE | TKZ_HF_DOC_OFFSETS)) { ctx->err = "unknown hf_flags bit"; return TKZ_ERR_INVALID_ARG; }
         if (P.fast) { ctx->err = "hf_flags cannot be combined with the FastTokenizer mode"; return TKZ_ERR_INVALID_ARG; }
         if (P.tpl_n_prefix > TKZ_TPL_MAX || P.tpl_n_suffix > TKZ_TPL_MAX) { ctx->err = "at most TKZ_TPL_MAX special tokens on either side of the sequence"; return TKZ_ERR_INVALID_ARG; }
         if (!(P.hf_flags & TKZ_HF_TEMPLATE)) { P.tpl_n_prefix = P.tpl_n_suffix = 0; P.tpl_seq_type = 0; }
+        if (P.outputs & TKZ_OUT_IDS_U16)
+            for (uint32_t i = 0; i < TKZ_TPL_MAX; i++)
+                if ((i < P.tpl_n_prefix && P.tpl_prefix_id[i] > 0xFFFFu) || (i < P.tpl_n_suffix && P.tpl_suffix_id[i] > 0xFFFFu)) { ctx->err = "template id above 65535 with TKZ_OUT_IDS_U16"; return TKZ_ERR_INVALID_ARG; }
+        // document-relative offsets do not fit the one-u16-per-token form
+        if ((P.hf_flags & TKZ_HF_DOC_OFFSETS) && (P.outputs & TKZ_OUT_OFFSETS_PACKED)) P.outputs = (P.outputs & ~TKZ_OUT_OFFSETS_PACKED) | TKZ_OUT_OFFSETS;
     }
     if ((P.outputs & TKZ_OUT_IDS_U16) && (!ctx->ids16_ok || (P.has_padding && P.pad_id > 0xFFFFu))) P.outputs &= ~TKZ_OUT_IDS_U16;
     const uint32_t nd = (uint32_t)n_docs;
@@ -968,7 +984,7 @@ int encode_device_impl(tkz_ctx* ctx, const uint8_t* d_text, const uint64_t* d_do
     // ---- slice pipeline (tkz_slices.cuh) whenever there is a pre-tokenizer; TKZ_NO_DEDUP=1 keeps the per-occurrence
     //      pipeline below for A/B tests
     ctx->stats.path = 0;
-    if (m.has_pretok && ctx->use_dedup && !P.fast && !P.hf_flags) {
+    if (m.has_pretok && ctx->use_dedup && !P.fast) {
         const ClassRanges& cr = ctx->dm.norm_has_drop ? ctx->cr_post : ctx->cr;      // (K0 ran: the text is already normalised)
         int rc = encode_slices(ctx, m, cr, d_text, d_doc_off, nd, N, P, false, out, launches);
         if (rc != TKZ_RETRY_WORST) return rc;
@@ -1058,13 +1074,7 @@ int encode_device_impl(tkz_ctx* ctx, const uint8_t* d_text, const uint64_t* d_do
     TRY(ensure(ctx, ctx->O().doc_tok_off, (n_docs + 1) * 8));
     unsigned long long* doc_tok_off = (unsigned long long*)ctx->O().doc_tok_off.p;
     EmitParams ep{P.has_truncation, P.max_length, P.has_padding, P.pad_length, P.pad_id, P.pad_type_id, P.pad_left, P.outputs};
-    if (P.hf_flags) {
-        ep.hf_flags = P.hf_flags; ep.n_pre = P.tpl_n_prefix; ep.n_suf = P.tpl_n_suffix; ep.seq_type = P.tpl_seq_type;
-        for (uint32_t i = 0; i < TKZ_TPL_MAX; i++) {
-            ep.pre_id[i] = P.tpl_prefix_id[i]; ep.pre_type[i] = P.tpl_prefix_type[i]; ep.suf_id[i] = P.tpl_suffix_id[i]; ep.suf_type[i] = P.tpl_suffix_type[i];
-            if ((P.outputs & TKZ_OUT_IDS_U16) && ((i < ep.n_pre && ep.pre_id[i] > 0xFFFFu) || (i < ep.n_suf && ep.suf_id[i] > 0xFFFFu))) { ctx->err = "template id above 65535 with TKZ_OUT_IDS_U16"; return TKZ_ERR_INVALID_ARG; }
-        }
-    }
+    emit_params_hf(ep, P);
     if (nd) { doc_len_kernel<<<(nd + 255) / 256, 256, 0, st>>>(ep, word_tok_off, doc_word_off, nd, doc_tok_off); launches++; }
     launches += exclusive_scan<unsigned long long>(doc_tok_off, n_docs, doc_tok_off, (unsigned long long*)ctx->a_scan_tmp.p, st);
     gather_scalars_kernel<<<1, 1, 0, st>>>(ctrl, word_tok_off, nw, doc_tok_off, nd, word_doc); launches++;

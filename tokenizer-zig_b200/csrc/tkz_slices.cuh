@@ -601,7 +601,7 @@ __device__ __forceinline__ void tw_flush_pooled(const SliceArgs& a, const uint4*
         const uint4 q = plist[e];
         for (uint32_t i = lane & 3u; i < q.y; i += 4) {
             const unsigned long long r = __ldcg(a.upool + q.x + i);       // written in THIS launch by the word's owner: L2, not the read-only path
-            const uint32_t of = ((uint32_t)(r >> 32) & 0xFFu) | ((uint32_t)(r >> 48) << 8);
+            const uint32_t of = ((uint32_t)(r >> 32) & 0xFFu) | (((uint32_t)(r >> 48) & 0xFFu) << 8) | q.w;
             if (a.tok2) a.tok2[q.z + i] = make_uint2((uint32_t)r, of);
             else a.tok_id[q.z + i] = (uint32_t)r;
         }
@@ -918,7 +918,9 @@ __global__ void __launch_bounds__(TW_THREADS, TW_BLOCKS_PER_SM) slice_words_kern
             else { const uint32_t inc = warp_incl_scan(nt); ex = inc - nt; tot = __shfl_sync(FULL, inc, 31); }
             const uint32_t dst = tbase + run + ex;                  // stream position of the word's first token
             if (can_store && nt && !(flags & TW_POOLF)) {
-                if (a.tok2) { a.tok2[dst] = make_uint2(v.a, v.b & 0xFFFFu); if (nt == 2) a.tok2[dst + 1] = make_uint2(v.c, v.d & 0xFFFFu); }
+                // (record: id, start | end << 8 | the word's position in the slice << 16 -- the position is only read by the hf_compat
+                // mode of pass B, which reports offsets relative to the document)
+                if (a.tok2) { const uint32_t ph = p << 16; a.tok2[dst] = make_uint2(v.a, (v.b & 0xFFFFu) | ph); if (nt == 2) a.tok2[dst + 1] = make_uint2(v.c, (v.d & 0xFFFFu) | ph); }
                 else { a.tok_id[dst] = v.a; if (nt == 2) a.tok_id[dst + 1] = v.c; }
             }
             // words with three or more tokens: listed now, copied from the pool at the end of the slice
@@ -926,7 +928,7 @@ __global__ void __launch_bounds__(TW_THREADS, TW_BLOCKS_PER_SM) slice_words_kern
             if (pooled) {
                 const uint32_t np = __popc(pooled);
                 if (n_pl + np > 32) { tw_flush_pooled(a, sh.plist, n_pl); n_pl = 0; }
-                if ((pooled >> lane) & 1u) sh.plist[n_pl + __popc(pooled & lt_mask)] = make_uint4(v.a, nt, dst, 0u);
+                if ((pooled >> lane) & 1u) sh.plist[n_pl + __popc(pooled & lt_mask)] = make_uint4(v.a, nt, dst, p << 16);
                 n_pl += np;
             }
             if (__any_sync(FULL, flags & (TW_ERRF | TW_LONGF))) {
@@ -1014,21 +1016,26 @@ struct SliceEmitArgs {
 // one token of the stream -> the arrays the call asked for.  OUTS = the TKZ_OUT_* mask when known at compile time
 // (ids only / ids + offsets + attention), 0 = read it from the parameters.
 template <uint32_t OUTS>
-__device__ __forceinline__ void te_put(const EmitParams& p, const EmitOut& o, unsigned long long dst, uint32_t id, uint32_t of) {
+__device__ __forceinline__ void te_put(const EmitParams& p, const EmitOut& o, unsigned long long dst, uint32_t id, uint32_t of, uint32_t hs) {
     const uint32_t outputs = OUTS ? OUTS : p.outputs;
+    uint32_t s = of & 0xFFu, e = (of >> 8) & 0xFFu, ty = 0u;
+    if (p.hf_flags) {                                            // hf_compat (tkz_emit.cuh): document-relative offsets, the sequence's type id
+        if (p.hf_flags & 2u) { const uint32_t b = hs + (of >> 16); s += b; e += b; }
+        if (p.hf_flags & 1u) ty = p.seq_type;
+    }
     if (outputs & 64u) o.ids16[dst] = (uint16_t)id; else o.ids[dst] = id;
-    if (outputs & 2u) reinterpret_cast<uint2*>(o.offsets)[dst] = make_uint2(of & 0xFFu, of >> 8);
+    if (outputs & 2u) reinterpret_cast<uint2*>(o.offsets)[dst] = make_uint2(s, e);
     if (outputs & 4u) o.attention[dst] = 1u;
-    if (outputs & 8u) o.type_ids[dst] = 0u;
+    if (outputs & 8u) o.type_ids[dst] = ty;
     if (outputs & 16u) o.special[dst] = 0u;
     if (outputs & 32u) o.offsets16[dst] = (uint16_t)of;
-    if (outputs & 128u) o.spans[dst] = make_uint4(id, of & 0xFFu, of >> 8, 0u);
+    if (outputs & 128u) o.spans[dst] = make_uint4(id, s, e, ty & 0xFFu);
 }
 
 // copies the stream tokens [j0, j1) of a slice (stream position src + j) to dst0 + (j - j0); 4 loads in flight per lane
 template <uint32_t OUTS>
 __device__ __forceinline__ void te_copy(const SliceEmitArgs& a, const EmitParams& p, const EmitOut& o, size_t src, uint32_t j0, uint32_t j1,
-                                        unsigned long long dst0) {
+                                        unsigned long long dst0, uint32_t hs = 0) {
     const uint32_t lane = lane_id();
     const uint32_t outputs = OUTS ? OUTS : p.outputs;
     const bool want_of = (outputs & (2u | 32u)) != 0;
@@ -1040,7 +1047,7 @@ __device__ __forceinline__ void te_copy(const SliceEmitArgs& a, const EmitParams
             else id[u] = __ldg(a.tok_id + src + j + 32 * u);
         }
 #pragma unroll
-        for (int u = 0; u < 4; u++) if (j + 32 * u < j1) te_put<OUTS>(p, o, dst0 + (j + 32 * u - j0), id[u], of[u]);
+        for (int u = 0; u < 4; u++) if (j + 32 * u < j1) te_put<OUTS>(p, o, dst0 + (j + 32 * u - j0), id[u], of[u], hs);
     }
 }
 
@@ -1100,6 +1107,7 @@ __global__ void __launch_bounds__(TW_THREADS, PLAIN ? 8 : 5) slice_emit_kernel(c
                 const uint32_t dl = dc + lane;
                 const uint32_t my_ds = dl <= a.n_docs ? __ldg(a.doc_tok_start + dl) : 0xFFFFFFFFu;
                 const unsigned long long my_dto = dl < a.n_docs ? a.doc_tok_off[dl] : 0ull;
+                const uint32_t my_dbyte = (p.hf_flags & 2u) && dl < a.n_docs ? (uint32_t)a.doc_off[dl] : 0u;     // hf_compat: byte position of the document
                 const uint32_t nd_here = min(31u, min(d_hi, a.n_docs) - dc);
                 for (uint32_t e = 0; e < nd_here; e++) {
                     const uint32_t ds = __shfl_sync(FULL, my_ds, e), dn = __shfl_sync(FULL, my_ds, e + 1);
@@ -1108,11 +1116,13 @@ __global__ void __launch_bounds__(TW_THREADS, PLAIN ? 8 : 5) slice_emit_kernel(c
                     if (g0 >= g1) continue;
                     unsigned long long kept;
                     const unsigned long long olen = doc_out_len(p, (unsigned long long)(dn - ds), &kept);
-                    const unsigned long long shift = (p.has_pad && p.pad_left) ? olen - kept : 0;
+                    const unsigned long long shift = ((p.has_pad && p.pad_left) ? olen - kept - tpl_added(p) : 0) + ((p.hf_flags & 1u) ? p.n_pre : 0u);
                     if ((unsigned long long)(g1 - ds) > kept) g1 = ds + (uint32_t)kept;             // truncation
                     if (g0 >= g1) continue;
                     const unsigned long long dbase = dto + shift;                                    // destination of the document's token 0
-                    if (ln == 0) te_copy<OUTS>(a, p, o, src, g0 - base, g1 - base, dbase + (g0 - ds));
+                    const uint32_t dbyte = __shfl_sync(FULL, my_dbyte, e);
+                    const uint32_t hs = s * TW_SLICE - dbyte;                                        // (mod 2^32) slice start relative to the document
+                    if (ln == 0) te_copy<OUTS>(a, p, o, src, g0 - base, g1 - base, dbase + (g0 - ds), hs);
                     else {
                         // slice-local real index r = g - base; pieces as in the PLAIN case, cut to [g0, g1)
                         uint32_t j = 0, r = 0;
@@ -1120,7 +1130,7 @@ __global__ void __launch_bounds__(TW_THREADS, PLAIN ? 8 : 5) slice_emit_kernel(c
                             const uint32_t jn = i < ln ? __ldg(a.long_ins + lf + i) : ntok;
                             {   // inline piece: stream tokens [j, jn) = real indices [r, r + jn - j)
                                 const uint32_t lo = max(g0 - base, r), hi2 = min(g1 - base, r + (jn - j));
-                                if (lo < hi2) te_copy<OUTS>(a, p, o, src, j + (lo - r), j + (hi2 - r), dbase + (base + lo - ds));
+                                if (lo < hi2) te_copy<OUTS>(a, p, o, src, j + (lo - r), j + (hi2 - r), dbase + (base + lo - ds), hs);
                             }
                             r += jn - j; j = jn;
                             if (i < ln) {
@@ -1132,8 +1142,9 @@ __global__ void __launch_bounds__(TW_THREADS, PLAIN ? 8 : 5) slice_emit_kernel(c
                                     const uint32_t c2 = hi2 - lo, sp2 = sp + (lo - r);
                                     const unsigned long long dd = dbase + (base + lo - ds);
                                     bool queued = false;
-                                    if (c2 > EMIT_BIG) { if (lane == 0) queued = big_push(a.big, sp2, c2, dd); queued = __shfl_sync(FULL, queued, 0); }
-                                    if (!queued) for (uint32_t q = lane; q < c2; q += 32) emit_real(p, o, dd + q, a.pool_id[sp2 + q], a.pool_s[sp2 + q], a.pool_e[sp2 + q]);
+                                    const uint32_t ls = (p.hf_flags & 2u) ? sp - dbyte : 0u;         // the long word's start within its document
+                                    if (c2 > EMIT_BIG) { if (lane == 0) queued = big_push(a.big, sp2, c2, dd, ls); queued = __shfl_sync(FULL, queued, 0); }
+                                    if (!queued) for (uint32_t q = lane; q < c2; q += 32) emit_real(p, o, dd + q, a.pool_id[sp2 + q], a.pool_s[sp2 + q] + ls, a.pool_e[sp2 + q] + ls);
                                 }
                                 r += cnt;
                             }
@@ -1177,14 +1188,22 @@ __device__ __forceinline__ void warp_fill_u32(uint32_t* p, unsigned long long n,
 
 // padding slots from per-document real counts (src/encoding.zig:407-414, 418-425), one warp per document
 __global__ void __launch_bounds__(256) emit_pad_real_kernel(EmitParams p, EmitOut o, uint32_t n_docs, const uint32_t* __restrict__ doc_real,
-                                                            const unsigned long long* __restrict__ doc_tok_off) {
+                                                            const unsigned long long* __restrict__ doc_tok_off, bool pads) {
     const uint32_t d = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (d >= n_docs) return;
     unsigned long long kept;
     const unsigned long long olen = doc_out_len(p, doc_real[d], &kept);
-    if (olen == kept) return;
-    const unsigned long long base = doc_tok_off[d] + (p.pad_left ? 0 : kept);
-    const unsigned long long npad = olen - kept;
+    const unsigned long long full = kept + tpl_added(p);
+    if (p.hf_flags & 1u) {
+        // hf_compat: the template's special tokens around the kept tokens (lanes 0-3 prefix, 8-11 suffix)
+        const uint32_t lane = lane_id();
+        const unsigned long long b0 = doc_tok_off[d] + ((p.has_pad && p.pad_left) ? olen - full : 0);
+        if (lane < p.n_pre) emit_special(p, o, b0 + lane, p.pre_id[lane], p.pre_type[lane]);
+        if (lane >= 8 && lane - 8 < p.n_suf) emit_special(p, o, b0 + p.n_pre + kept + (lane - 8), p.suf_id[lane - 8], p.suf_type[lane - 8]);
+    }
+    if (olen == full || !pads) return;
+    const unsigned long long base = doc_tok_off[d] + (p.pad_left ? 0 : full);
+    const unsigned long long npad = olen - full;
     if (p.outputs & 64u) { uint16_t* q = o.ids16 + base; for (unsigned long long i = lane_id(); i < npad; i += 32) q[i] = (uint16_t)p.pad_id; }
     else warp_fill_u32(o.ids + base, npad, p.pad_id);
     if (p.outputs & 2u) warp_fill_u32(o.offsets + 2 * base, 2 * npad, 0u);
