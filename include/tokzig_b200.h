@@ -130,9 +130,8 @@ typedef struct tkz_encode_params {
      * before and tpl_n_suffix after every document's kept tokens (offsets (0,0), special 1, attention 1, their own type id),
      * gives the document's tokens tpl_seq_type, lets the added tokens count against max_length and towards pad_length;
      * TKZ_HF_DOC_OFFSETS reports offsets relative to the (normalised) document instead of the pre-token.  A caller passes the
-     * prefix / suffix only when it encodes with add_special_tokens (tokenizers keeps the type id either way).  Served by the
-     * per-occurrence pipeline (not the slice pipeline of the headline numbers); not available in the FastTokenizer mode and
-     * the compact result. */
+     * prefix / suffix only when it encodes with add_special_tokens (tokenizers keeps the type id either way).  Not available in
+     * the FastTokenizer mode and the compact result. */
     uint32_t hf_flags;                  /* TKZ_HF_* */
     uint32_t tpl_n_prefix, tpl_n_suffix;             /* <= TKZ_TPL_MAX each */
     uint32_t tpl_prefix_id[4], tpl_prefix_type[4], tpl_suffix_id[4], tpl_suffix_type[4];

@@ -883,8 +883,10 @@ int encode_slices(tkz_ctx* ctx, const DevModel& m, const ClassRanges& cr, const 
     launches++;
     if (n_long) { emit_big_kernel<<<ctx->sm_count * 4, 256, 0, st>>>(ep, eo, ea.big, ea.pool_id, ea.pool_s, ea.pool_e); launches++; }
     const bool frame = (ep.hf_flags & 1u) && ep.n_pre + ep.n_suf;                     // hf_compat: the template's special tokens
-    if (((P.has_padding && !pad_fill) || frame) && nd) {
-        emit_pad_real_kernel<<<(unsigned)(((uint64_t)nd * 32 + 255) / 256), 256, 0, st>>>(ep, eo, nd, (const uint32_t*)ctx->a_doc_real.p, doc_tok_off, P.has_padding && !pad_fill); launches++;
+    if (frame && !(P.has_padding && !pad_fill) && nd) {
+        emit_frame_kernel<<<(nd + 255) / 256, 256, 0, st>>>(ep, eo, nd, (const uint32_t*)ctx->a_doc_real.p, doc_tok_off); launches++;
+    } else if (P.has_padding && !pad_fill && nd) {
+        emit_pad_real_kernel<<<(unsigned)(((uint64_t)nd * 32 + 255) / 256), 256, 0, st>>>(ep, eo, nd, (const uint32_t*)ctx->a_doc_real.p, doc_tok_off, true); launches++;
     }
     CK(cudaGetLastError());
     CK(cudaEventRecord(ctx->ev[4], st));

@@ -1214,6 +1214,18 @@ __global__ void __launch_bounds__(256) emit_pad_real_kernel(EmitParams p, EmitOu
     if (p.outputs & 128u) { uint4* q = o.spans + base; for (unsigned long long i = lane_id(); i < npad; i += 32) q[i] = make_uint4(p.pad_id, 0u, 0u, 0x0400u); }
 }
 
+// hf_compat: only the template's special tokens (the padding slots were filled array-wide), one thread per document
+__global__ void __launch_bounds__(256) emit_frame_kernel(EmitParams p, EmitOut o, uint32_t n_docs, const uint32_t* __restrict__ doc_real,
+                                                         const unsigned long long* __restrict__ doc_tok_off) {
+    const uint32_t d = blockIdx.x * blockDim.x + threadIdx.x;
+    if (d >= n_docs) return;
+    unsigned long long kept;
+    const unsigned long long olen = doc_out_len(p, doc_real[d], &kept);
+    const unsigned long long b0 = doc_tok_off[d] + ((p.has_pad && p.pad_left) ? olen - kept - tpl_added(p) : 0);
+    for (uint32_t i = 0; i < p.n_pre; i++) emit_special(p, o, b0 + i, p.pre_id[i], p.pre_type[i]);
+    for (uint32_t i = 0; i < p.n_suf; i++) emit_special(p, o, b0 + p.n_pre + kept + i, p.suf_id[i], p.suf_type[i]);
+}
+
 // document of the first failing word (byte position in the error word) -> ctrl[4]
 __global__ void err_doc_kernel(unsigned long long* ctrl, const uint64_t* doc_off, uint32_t n_docs) {
     const unsigned long long ew = ctrl[0];
