@@ -449,7 +449,7 @@ __device__ __forceinline__ WholeWarpOut tw_whole_warp_word(const DevModel& m, co
         // WordPiece only needs the LENGTH of a word above max_input_chars_per_word (wordpiece.zig:149-158)
         uint64_t q = start + 32;
         bool found = false;
-        for (int round = 0; round < 3 && !found; round++) {       // the first 96 bytes one per lane (most words end here)
+        for (int round = 0; round < 7 && !found; round++) {       // the next 224 bytes one per lane: every word that stays inline (<= 255 bytes) ends here
             const uint64_t qq = q + lane;
             const bool stop = qq >= limit || ((lut[__ldg(a.text + qq)] >> 8) & 1u) == 0;
             const uint32_t sm = __ballot_sync(FULL, stop);
