@@ -271,7 +271,12 @@ class Work:
         """one pass through the host-buffer C ABI; returns (h2d bytes, d2h bytes).  mode: compact | compact_ids | full16"""
         tz, L = self.tz, self.L
         h2d = d2h = 0
-        for (a, b), ob in zip(self.batches, self.h_offs):
+        # the compact result has no padding slots, so the whole shard is ONE call (the device-resident steps of a padded workload
+        # are cut into sub-batches only because their padded slot count would pass 2^32)
+        whole = mode != "full16" and len(self.batches) > 1 and self.nbytes < (1 << 32) - (1 << 20)
+        if whole and not hasattr(self, "h_off_all"):
+            self.h_off_all = self.off.astype(np.uint64)
+        for (a, b), ob in ([((0, self.nd), self.h_off_all)] if whole else zip(self.batches, self.h_offs)):
             base = int(self.off[a])
             h2d += int(ob[-1]) + ob.nbytes
             if mode == "full16":
@@ -285,7 +290,7 @@ class Work:
                 rc = L.tkz_encode_batch_compact(self.ctx, C.c_void_p(self.text.ctypes.data + base), C.c_void_p(ob.ctypes.data), b - a, C.byref(p),
                                                 1 if mode == "compact" else 0, C.byref(r))
                 per = (2 if r.ids16 else 4) + (2 if r.offsets_packed else (8 if r.offsets else 0))
-                d2h += int(r.n_kept) * per + (b - a + 1) * 8
+                d2h += int(r.n_kept) * per + (b - a + 1) * 8 + int(r.n_wide) * 16
             if rc != 0:
                 raise RuntimeError(f"host encode rc={rc}: {L.tkz_last_error(self.ctx)}")
             self.last = r
@@ -490,7 +495,8 @@ def run_ours(args, rank, local_rank, world):
                    "tokens_per_s": all_real / dt,
                    "api": "tkz_encode_batch_compact (host pointers; pinned text H2D + kept ids and packed offsets D2H inside the timed region; "
                           "attention / type / special masks and padding slots are constants of (kept count, parameters) and are rebuilt by tkz_compact_expand)",
-                   "wire_format": {"ids": "u16" if r.ids16 else "u32", "offsets": "u16 (start | end << 8)" if r.offsets_packed else ("2 x u32" if r.offsets else None)}}
+                   "wire_format": {"ids": "u16" if r.ids16 else "u32", "offsets": "u16 (start | end << 8)" if r.offsets_packed else ("2 x u32" if r.offsets else None),
+                                   "wide_offset_records": int(r.n_wide)}}
             if headline:
                 dt2, _, d2h2 = W.time_host("full16", max(1, e_steps - 1), barrier)
                 e2e["full_arrays"] = {"value": W.nbytes / dt2 / 1e9, "unit": "GB/s", "ms_per_step": dt2 * 1e3, "d2h_bytes_per_step": d2h2,

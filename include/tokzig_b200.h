@@ -95,9 +95,11 @@ typedef struct tkz_model_desc {
 #define TKZ_OUT_SPECIAL 16u
 #define TKZ_OUT_ALL 31u
 /* Offsets as ONE u16 per token (start | end << 8) in tkz_batch_result.offsets_packed instead of two u32: possible because
- * the reference's offsets are relative to the pre-token (src/lib.zig:133-137), delivered when every pre-token of the batch
- * is shorter than 256 bytes.  A batch with a longer pre-token (or a tokenizer without pre-tokenizer) falls back to
- * TKZ_OUT_OFFSETS for the whole call: exactly one of offsets / offsets_packed is then non-NULL. */
+ * the reference's offsets are relative to the pre-token (src/lib.zig:133-137).  The few tokens of pre-tokens of 256 bytes
+ * or more get the value 0xFFFF (no real token has start = end = 255) and their offsets travel in a side list
+ * (tkz_batch_result.n_wide / wide_tokens).  A batch where those tokens are many (above an eighth of all tokens or 4 M), a
+ * tokenizer without pre-tokenizer, and TKZ_HF_DOC_OFFSETS fall back to TKZ_OUT_OFFSETS for the whole call: exactly one of
+ * offsets / offsets_packed is then non-NULL. */
 #define TKZ_OUT_OFFSETS_PACKED 32u
 /* Ids as u16 in tkz_batch_result.ids16 instead of u32 in ids: honoured when every id of the uploaded vocabulary is below
  * 65536 (GPT-2- and BERT-sized vocabularies), ignored otherwise: exactly one of ids / ids16 is non-NULL. */
@@ -159,6 +161,12 @@ typedef struct tkz_batch_result {
     const uint16_t* offsets_packed;     /* n_tokens x (start | end << 8), see TKZ_OUT_OFFSETS_PACKED; padding slots are 0 */
     const uint16_t* ids16;              /* n_tokens, see TKZ_OUT_IDS_U16 */
     const uint32_t* span_tokens;        /* 4 u32 per slot, see TKZ_OUT_SPAN_TOKENS */
+    /* TKZ_OUT_OFFSETS_PACKED, tokens of pre-tokens of 256 bytes or more: their u16 is 0xFFFF and their offsets are here,
+     * n_wide records of four u32 {slot low, slot high, start, end}; sorted by slot in host-buffer results, in no particular
+     * order in device-resident results.  (A call with too many of them -- above an eighth of its tokens or 4 M -- delivers
+     * 32-bit offsets for every token instead, as a call without pre-tokenizer does.) */
+    uint64_t n_wide;
+    const uint32_t* wide_tokens;
 } tkz_batch_result;
 
 /* counters of the last encode (FastTokenizer.arenaMemoryUsage analogue, src/lib.zig:451-453) */
@@ -210,10 +218,12 @@ typedef struct tkz_compact_result {
     const uint64_t* doc_kept_off;       /* n_docs + 1: document d keeps tokens [doc_kept_off[d], doc_kept_off[d+1]) */
     const uint32_t* ids;                /* n_kept, or NULL when ids16 is delivered */
     const uint16_t* ids16;
-    const uint16_t* offsets_packed;     /* n_kept x (start | end << 8), or NULL (a pre-token of 256+ bytes: see offsets) */
+    const uint16_t* offsets_packed;     /* n_kept x (start | end << 8), 0xFFFF = see wide_tokens; or NULL (then offsets) */
     const uint32_t* offsets;            /* 2 * n_kept, or NULL */
     tkz_encode_params params;           /* truncation / padding the expanded Encodings have */
     int64_t err_doc;
+    uint64_t n_wide;                    /* offsets_packed: kept tokens whose u16 is 0xFFFF, sorted by kept index */
+    const uint32_t* wide_tokens;        /* {kept index low, high, start, end} each */
 } tkz_compact_result;
 int tkz_encode_batch_compact(tkz_ctx* ctx, const uint8_t* text, const uint64_t* doc_off, uint64_t n_docs,
                              const tkz_encode_params* params, int want_offsets, tkz_compact_result* out);

@@ -870,14 +870,17 @@ def test_compact_result_expands_to_the_reference_encoding(seed):
 
 
 def test_packed_formats_fall_back_when_they_cannot_hold_the_values(monkeypatch):
-    """offsets_packed needs every pre-token below 256 bytes (else the whole call -- every chunk of the host path -- delivers
-    32-bit offsets); ids16 needs every vocabulary id below 65536."""
+    """offsets_packed: tokens of pre-tokens of 256 bytes or more carry 0xFFFF and their offsets travel in a side list; when
+    such tokens are many (an eighth of the call's tokens) the whole call -- every chunk of the host path -- delivers 32-bit
+    offsets; ids16 needs every vocabulary id below 65536."""
     rng = random.Random(77)
     js, alpha = rand_bpe_json(rng, n_merges=40, alphabet=list("abcdefg"), pretok="Whitespace", dead_merges=0.0)
     t, o = pair(js)
     short = [b" ".join(bytes(rng.choice(b"abcdefg") for _ in range(rng.randint(1, 40))) for _ in range(rng.randint(1, 30))) for _ in range(2000)]
     long_doc = b"ab " + bytes(rng.choice(b"abcdefg") for _ in range(300)) + b" cd"
-    for docs, packed in ((short, True), (short[:1000] + [long_doc] + short[1000:], False)):
+    many_long = [b"x " + bytes(rng.choice(b"abcdefg") for _ in range(rng.randint(256, 2000))) for _ in range(1500)]
+    for docs, packed, wide in ((short, True, False), (short[:1000] + [long_doc] + short[1000:] + [long_doc, b"", long_doc[3:]], True, True),
+                               (short[:50] + many_long + short[50:100], False, False)):
         for chunk in (1 << 31, 16384):
             monkeypatch.setenv("TKZ_CHUNK_BYTES", str(chunk))
             t2 = tz.Tokenizer.from_json(js, device=0)
@@ -885,10 +888,21 @@ def test_packed_formats_fall_back_when_they_cannot_hold_the_values(monkeypatch):
             got = t2.encode_packed(text, off, outputs=tz.OUT_IDS | tz.OUT_OFFSETS_PACKED | tz.OUT_IDS_U16)
             ref = o.encode_batch(docs, threads=4)
             assert (got.offsets_packed is not None) == packed and (got.offsets is not None) == (not packed)
+            assert (got.wide_tokens is not None and len(got.wide_tokens) > 0) == wide
+            if wide:
+                slots = got.wide_tokens[:, 0].astype(np.int64) | (got.wide_tokens[:, 1].astype(np.int64) << 32)
+                assert np.all(np.diff(slots) > 0)                       # sorted by slot, no duplicates
+                assert int((got.offsets_packed == 0xFFFF).sum()) == len(slots)
             assert np.array_equal(got.ids, ref.ids) and np.array_equal(got.unpacked_offsets(), ref.offsets) and np.array_equal(got.doc_tok_off, ref.doc_tok_off)
             r = t2.encode_compact(text, off)
-            assert bool(r.offsets_packed) == packed
+            assert bool(r.offsets_packed) == packed and (r.n_wide > 0) == wide
             assert_same(tz.expand_compact(r), ref, f"packed={packed} chunk={chunk}")
+            if wide:                                                    # expansion of document ranges that start behind a wide token
+                nd = len(docs)
+                for d0, d1 in ((1001, nd), (nd - 3, nd - 1), (nd - 1, nd), (0, 1000)):
+                    part = tz.expand_compact(r, d0, d1)
+                    a, b = int(ref.doc_tok_off[d0]), int(ref.doc_tok_off[d1])
+                    assert np.array_equal(part.ids, ref.ids[a:b]) and np.array_equal(part.offsets, ref.offsets[a:b])
             t2.close()
     t.close()
     # vocabulary ids above 65535: ids stay u32

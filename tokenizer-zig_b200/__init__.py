@@ -110,6 +110,8 @@ class BatchResult(C.Structure):
         ("offsets_packed", C.c_void_p),
         ("ids16", C.c_void_p),
         ("span_tokens", C.c_void_p),
+        ("n_wide", C.c_uint64),
+        ("wide_tokens", C.c_void_p),
     ]
 
 
@@ -126,6 +128,8 @@ class CompactResult(C.Structure):
         ("offsets", C.c_void_p),
         ("params", EncodeParams),
         ("err_doc", C.c_int64),
+        ("n_wide", C.c_uint64),
+        ("wide_tokens", C.c_void_p),
     ]
 
 
@@ -270,7 +274,8 @@ class BatchEncoding:
     type_ids: Optional[np.ndarray]
     special_tokens_mask: Optional[np.ndarray]
     n_real_tokens: int = 0
-    offsets_packed: Optional[np.ndarray] = None     # u16 per token: start | end << 8 (OUT_OFFSETS_PACKED)
+    offsets_packed: Optional[np.ndarray] = None     # u16 per token: start | end << 8 (OUT_OFFSETS_PACKED); 0xFFFF = see wide_tokens
+    wide_tokens: Optional[np.ndarray] = None        # (n_wide, 4) u32: slot low, slot high, start, end -- tokens of pre-tokens of 256+ bytes
     span_tokens: Optional[np.ndarray] = None        # (n, 4) u32: id, start, end, type_id | flags << 8 (OUT_SPAN_TOKENS)
 
     def __len__(self):
@@ -280,7 +285,13 @@ class BatchEncoding:
         """(n, 2) u32 offsets whichever form the call delivered."""
         if self.offsets is not None or self.offsets_packed is None:
             return self.offsets
-        return np.stack([self.offsets_packed & 0xFF, self.offsets_packed >> 8], axis=1).astype(np.uint32)
+        o = np.stack([self.offsets_packed & 0xFF, self.offsets_packed >> 8], axis=1).astype(np.uint32)
+        if self.wide_tokens is not None and len(self.wide_tokens):
+            slots = self.wide_tokens[:, 0].astype(np.uint64) | (self.wide_tokens[:, 1].astype(np.uint64) << np.uint64(32))
+            assert np.all(self.offsets_packed[slots] == 0xFFFF)
+            o[slots] = self.wide_tokens[:, 2:4]
+        assert not np.any((self.offsets_packed == 0xFFFF) & (o[:, 0] == 255) & (o[:, 1] == 255))
+        return o
 
     def doc_slice(self, i):
         return slice(int(self.doc_tok_off[i]), int(self.doc_tok_off[i + 1]))
@@ -298,6 +309,7 @@ def _result_to_batch(r: BatchResult) -> BatchEncoding:
         special_tokens_mask=_copy(r.special_tokens_mask, T, np.uint32) if r.special_tokens_mask else None,
         n_real_tokens=int(r.n_real_tokens),
         offsets_packed=_copy(r.offsets_packed, T, np.uint16) if r.offsets_packed else None,
+        wide_tokens=_copy(r.wide_tokens, 4 * int(r.n_wide), np.uint32).reshape(-1, 4) if (r.wide_tokens and r.n_wide) else None,
         span_tokens=_copy(r.span_tokens, 4 * T, np.uint32).reshape(-1, 4) if r.span_tokens else None,
     )
 

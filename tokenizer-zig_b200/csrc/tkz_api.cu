@@ -11,6 +11,8 @@
 #include <cstdio>
 #include <cstring>
 #include <algorithm>
+#include <array>
+#include <chrono>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -59,7 +61,7 @@ struct tkz_ctx {
     DevBuf a_text, a_doc_off, a_norm_text, a_norm_doc_off, a_chunk, a_tiles, a_word_start, a_word_end, a_word_doc, a_doc_word_off,
         a_word_ntok, a_pool_id, a_pool_s, a_pool_e, a_pool_rk, a_scan_tmp, a_ctrl;
     // output arrays, double-buffered so that the D2H copy of one chunk overlaps the kernels of the next (tkz_encode_batch)
-    struct OutSet { DevBuf doc_tok_off, ids, off, attn, type, special, off16, ids16, spans; } outs[2];
+    struct OutSet { DevBuf doc_tok_off, ids, off, attn, type, special, off16, ids16, spans, wide; } outs[2];
     int out_sel = 0;
     OutSet& O() { return outs[out_sel]; }
     DevBuf in_text[2], in_doc_off[2];
@@ -75,6 +77,14 @@ struct tkz_ctx {
     bool has_iso = false;                 // the class table isolates some byte (punctuation split)
     ClassRanges cr{}, cr_post{};          // byte classes as ranges (raw bytes / bytes already normalised by K0)
     bool stage_bulk = true;               // TKZ_STAGE=ldg: pass A stages its slices with plain loads instead of bulk copies (A/B switch)
+    // chunks of ONE host-buffer call share the word table and the record pool of the slice pipeline: the first chunk starts from an
+    // empty table, the later ones find the call's frequent words already tokenized (every call starts cold; TKZ_KEEP_TABLE=0
+    // gives every chunk its own table)
+    bool keep_table = true;               // switch
+    bool call_keep = false;               // inside a chunked host-buffer call
+    bool kept_valid = false;              // the table of the previous chunk can be reused
+    uint64_t call_bytes = 0;              // text bytes of the whole call (sizes the shared table)
+    uint32_t kept_tcap = 0, kept_upool_count = 0; uint64_t kept_upool_cap = 0, call_uniq = 0;
     bool pad_fill = true;                 // TKZ_PAD_FILL=0: padding slots always by one warp per document (A/B switch)
     bool force_lut = false;               // TKZ_CLASSIFY=lut: per-byte look-up even when the class table fits ranges (A/B switch)
     DevBuf a_huge_w, a_huge_base, a_huge_done, a_grid_state, a_grid_words;   // bpe_grid_kernel (tkz_bpe_grid.cuh)
@@ -86,7 +96,7 @@ struct tkz_ctx {
     uint64_t tw_uniq_hist = 0;            // most unique words seen in one batch: sizes the next batch's word table
     uint64_t tw_upool_hist = 0;           // most token records used by one batch
     double tw_tok_per_byte = 0.0;         // densest batch so far: sizes the token stream
-    HostBuf h_ctrl, h_doc_tok_off, h_ids, h_off, h_attn, h_type, h_special, h_off16, h_ids16, h_spans;
+    HostBuf h_ctrl, h_doc_tok_off, h_ids, h_off, h_attn, h_type, h_special, h_off16, h_ids16, h_spans, h_wide;
     DevBuf a_fast_heap, a_word_aux;       // FastTokenizer mode (tkz_fast.cuh)
     bool ids16_ok = false;                // every id the model can emit is below 65536 (TKZ_OUT_IDS_U16)
     // decode direction (tkz_decode.cuh)
@@ -167,12 +177,18 @@ __global__ void ctrl_reset_kernel(unsigned long long* ctrl) {
     // dedup: ctrl[5] second work counter, [6] n_uniq, [7] n_long, [8] overflow, [9] upool_count, [10] n_words
     // slice pipeline: [5] entry count, [6] n_uniq | n_uncached << 32, [7] n_long, [8] abort, [9] upool | lscratch << 32,
     //                [10] n_words, [11..12], [17], [20..21] block-kernel work counters, [13..15] long-word length classes,
-    //                [16] big-copy list, [18..19] huge-word list (count, bytes)
+    //                [16] big-copy list, [18..19] huge-word list (count, bytes), [22] tokens of the long words, [23] wide-offset list
     ctrl[0] = TKZ_ERRW_NONE;
     for (int i = 1; i < 32; i++) ctrl[i] = 0;
 }
 // scalars -> mapped host memory, in stream order (replaces small D2H memcpys: those share the copy engine's queue with the
 // multi-megabyte result copies of the previous chunk and would stall the kernels of this one behind them)
+// chunk-relative CSR offsets -> call-relative (host path: a chunk's doc_tok_off is shifted on the device before it is copied out)
+__global__ void add_base_u64_kernel(unsigned long long* __restrict__ p, uint64_t n, unsigned long long base) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] += base;
+}
+__global__ void set_u32_kernel(unsigned int* p, unsigned int v) { *p = v; }
 __global__ void publish_kernel(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, uint32_t n) {
     for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i];
     __threadfence_system();
@@ -261,6 +277,7 @@ extern "C" int tkz_ctx_create(int device, void* stream, uint64_t arena_hint_byte
     if (const char* e = getenv("TKZ_CLASSIFY")) ctx->force_lut = (e[0] == 'l');
     if (const char* e = getenv("TKZ_STAGE")) ctx->stage_bulk = !(e[0] == 'l');
     if (const char* e = getenv("TKZ_PAD_FILL")) ctx->pad_fill = e[0] != '0';
+    if (const char* e = getenv("TKZ_KEEP_TABLE")) ctx->keep_table = e[0] != '0';
     if (const char* e = getenv("TKZ_NO_GRID")) ctx->use_grid = !(e[0] == '1');
     if (const char* e = getenv("TKZ_GRID_MIN_LEN")) { const long long v = atoll(e); if (v > (long long)BB_WARP_MAX) ctx->grid_min_len = (uint32_t)v; }
     {
@@ -298,9 +315,9 @@ extern "C" void tkz_ctx_destroy(tkz_ctx* ctx) {
                       &ctx->a_huge_w, &ctx->a_huge_base, &ctx->a_huge_done, &ctx->a_grid_state, &ctx->a_grid_words,
                       &ctx->t_dec_bytes, &ctx->t_dec_off, &ctx->t_dec_special, &ctx->a_dec_ids, &ctx->a_dec_seq_off, &ctx->a_dec_len, &ctx->a_dec_raw,
                       &ctx->a_dec_out, &ctx->a_dec_olen, &ctx->a_dec_boff};
-    for (auto& os : ctx->outs) for (DevBuf* b : {&os.doc_tok_off, &os.ids, &os.off, &os.attn, &os.type, &os.special, &os.off16, &os.ids16, &os.spans}) release(*b);
+    for (auto& os : ctx->outs) for (DevBuf* b : {&os.doc_tok_off, &os.ids, &os.off, &os.attn, &os.type, &os.special, &os.off16, &os.ids16, &os.spans, &os.wide}) release(*b);
     for (DevBuf* b : bufs) release(*b);
-    HostBuf* hb[] = {&ctx->h_ctrl, &ctx->h_doc_tok_off, &ctx->h_ids, &ctx->h_off, &ctx->h_attn, &ctx->h_type, &ctx->h_special, &ctx->h_off16, &ctx->h_ids16, &ctx->h_spans,
+    HostBuf* hb[] = {&ctx->h_ctrl, &ctx->h_doc_tok_off, &ctx->h_ids, &ctx->h_off, &ctx->h_attn, &ctx->h_type, &ctx->h_special, &ctx->h_off16, &ctx->h_ids16, &ctx->h_spans, &ctx->h_wide,
                      &ctx->h_doc_stage[0], &ctx->h_doc_stage[1], &ctx->h_dec_bytes, &ctx->h_dec_off};
     for (HostBuf* b : hb) release_host(*b);
     if (ctx->s_h2d) cudaStreamDestroy(ctx->s_h2d);
@@ -713,16 +730,19 @@ int encode_slices(tkz_ctx* ctx, const DevModel& m, const ClassRanges& cr, const 
     const uint32_t n_slices = (uint32_t)(N / TW_SLICE + 1);
     const bool plain = !P.has_truncation && !P.has_padding && !P.hf_flags;        // (hf_compat: per-document destinations and offsets)
     // ---- capacities: from the text size and from what earlier batches of this context needed
-    uint64_t want = N / 32; if (want < (1u << 16)) want = 1u << 16; if (want > (1u << 22)) want = 1u << 22;
+    const bool keep = ctx->call_keep && ctx->kept_valid && !worst;           // reuse the table + pool of this call's previous chunk
+    const uint64_t Nsz = ctx->call_keep ? std::max<uint64_t>(N, ctx->call_bytes) : N;
+    uint64_t want = Nsz / 32; if (want < (1u << 16)) want = 1u << 16; if (want > (1u << 22)) want = 1u << 22;
     if (want < ctx->tw_uniq_hist * 4) want = ctx->tw_uniq_hist * 4;          // load factor <= 1/4
     if (want > (1u << 26)) want = 1u << 26;
-    const uint32_t tcap = pow2_at_least(want);
+    const uint32_t tcap = keep ? ctx->kept_tcap : pow2_at_least(want);
     uint32_t tbits = 0; while ((1u << tbits) < tcap) tbits++;
     const uint32_t mcap = tcap >= (1u << 17) ? tcap / 8 : (1u << 14);
     const uint32_t m32cap = tcap >= (1u << 16) ? tcap / 4 : (1u << 14);        // 64-byte slots for words of 16..31 bytes
-    uint64_t upool_cap = worst ? N + (1u << 16) : N / 8 + (1u << 20);
+    uint64_t upool_cap = worst ? N + (1u << 16) : Nsz / 8 + (1u << 20);
     if (upool_cap < ctx->tw_upool_hist * 2) upool_cap = ctx->tw_upool_hist * 2;
     if (upool_cap > 0xFFFFFF00ull) upool_cap = 0xFFFFFF00ull;
+    if (keep) upool_cap = ctx->kept_upool_cap;
     // persistent grid: every warp keeps a private chunk of the token stream and a private model scratch
     const uint32_t grid = (uint32_t)std::min<uint64_t>(((uint64_t)n_slices + TW_WARPS - 1) / TW_WARPS, (uint64_t)ctx->sm_count * TW_BLOCKS_PER_SM);
     const uint64_t warps = (uint64_t)grid * TW_WARPS;
@@ -749,7 +769,8 @@ int encode_slices(tkz_ctx* ctx, const DevModel& m, const ClassRanges& cr, const 
     TRY(ensure(ctx, ctx->a_long_ins, (size_t)long_cap * 4));
     TRY(ensure(ctx, ctx->O().doc_tok_off, (n_docs + 1) * 8));
     TRY(ensure(ctx, ctx->a_scan_tmp, (scan_tmp_elems(n_slices) + scan_tmp_elems(n_docs)) * 8));
-    CK(cudaMemsetAsync(ctx->a_wtable.p, 0, ((size_t)tcap + mcap) * sizeof(WordSlot) + (size_t)m32cap * sizeof(WordSlot32), st));
+    if (!keep) CK(cudaMemsetAsync(ctx->a_wtable.p, 0, ((size_t)tcap + mcap) * sizeof(WordSlot) + (size_t)m32cap * sizeof(WordSlot32), st));
+    else { set_u32_kernel<<<1, 1, 0, st>>>((unsigned int*)(ctrl + 9), ctx->kept_upool_count); launches++; }   // (ctrl was reset: the pool goes on where it was)
     tile_doc_index_kernel<<<(n_slices + 1 + 255) / 256, 256, 0, st>>>(d_doc_off, nd, n_slices, TW_SLICE, (uint32_t*)ctx->a_tile_doc_lo.p); launches++;
     SliceArgs ta{};
     ta.text = d_text; ta.n = N; ta.doc_off = d_doc_off; ta.n_docs = nd; ta.n_slices = n_slices; ta.slice_doc_lo = (const uint32_t*)ctx->a_tile_doc_lo.p;
@@ -779,17 +800,19 @@ int encode_slices(tkz_ctx* ctx, const DevModel& m, const ClassRanges& cr, const 
     CK(cudaEventRecord(ctx->ev[1], st));
     CK(cudaStreamSynchronize(st));
     const uint32_t n_uniq = (uint32_t)hctrl[6], n_unc = (uint32_t)(hctrl[6] >> 32), n_long = (uint32_t)hctrl[7];
+    if (ctx->call_keep) { ctx->call_uniq += n_uniq; ctx->tw_uniq_hist = std::max<uint64_t>(ctx->tw_uniq_hist, ctx->call_uniq); }
     ctx->tw_uniq_hist = std::max<uint64_t>(ctx->tw_uniq_hist, n_uniq);
     ctx->tw_upool_hist = std::max<uint64_t>(ctx->tw_upool_hist, (uint32_t)hctrl[9]);
+    ctx->kept_valid = false;
     if ((uint32_t)hctrl[8] != 0) {
+        ctx->call_keep = false;                              // (the retry and the rest of the call work with tables of their own)
         if (worst) { ctx->err = "internal: slice pipeline ran out of a worst-case capacity"; return TKZ_ERR_CUDA; }
         ctx->tw_tok_per_byte = 1.0;                         // later batches of this context get the worst-case token stream at once
         return TKZ_RETRY_WORST;
     }
     ctx->stats.n_unique_words = n_uniq + n_unc; ctx->stats.n_long_words = n_long;
     ctx->stats.path = 2;
-    // packed (one byte each) offsets exist only when no pre-token reaches 256 bytes: otherwise the call delivers 32-bit pairs
-    if ((P.outputs & TKZ_OUT_OFFSETS_PACKED) && n_long) P.outputs = (P.outputs & ~TKZ_OUT_OFFSETS_PACKED) | TKZ_OUT_OFFSETS;
+    if (ctx->call_keep && !worst) { ctx->kept_valid = true; ctx->kept_tcap = tcap; ctx->kept_upool_cap = upool_cap; ctx->kept_upool_count = (uint32_t)hctrl[9]; }
 
     // ---- the few pre-tokens longer than TW_MAX_INLINE bytes: per-occurrence word-list kernels, counts folded back in
     TRY(ensure(ctx, ctx->a_long_ntok, ((size_t)n_long + 2) * 4));
@@ -807,7 +830,7 @@ int encode_slices(tkz_ctx* ctx, const DevModel& m, const ClassRanges& cr, const 
             wordpiece_warp_kernel<<<(unsigned)blocks, WP_WARPS * 32, 0, st>>>(m, a); launches++;
         }
         long_fix_kernel<<<(n_long + 255) / 256, 256, 0, st>>>(ta.long_start, ta.long_slice, (const uint32_t*)ctx->a_long_ntok.p, n_long, ta.slice_doc_lo,
-                                                               d_doc_off, ta.slice_ntok, ta.doc_tok_local); launches++;
+                                                               d_doc_off, ta.slice_ntok, ta.doc_tok_local, ctrl + 22); launches++;
     }
     CK(cudaEventRecord(ctx->ev[2], st));
 
@@ -826,8 +849,17 @@ int encode_slices(tkz_ctx* ctx, const DevModel& m, const ClassRanges& cr, const 
     }
     TRY(readback(ctx, hctrl + 32, ta.slice_ntok + n_slices, 4));
     TRY(readback(ctx, hctrl, ctrl, 8));
+    if (n_long) TRY(readback(ctx, hctrl + 22, ctrl + 22, 8));
     CK(cudaStreamSynchronize(st));
     const uint64_t T_real = (uint32_t)hctrl[32], T = plain ? T_real : hctrl[3];
+    // one-u16 offsets: only the tokens of pre-tokens of 256 bytes or more can fail to fit; they go to a side list sized for all
+    // of them -- unless they are many (skewed corpora with MiB-long words): then the call delivers 32-bit pairs
+    uint32_t wide_cap = 0;
+    if ((P.outputs & TKZ_OUT_OFFSETS_PACKED) && n_long) {
+        const uint64_t lt = hctrl[22];
+        if (lt > T_real / 8 + 4096 || lt > (4u << 20)) { P.outputs = (P.outputs & ~TKZ_OUT_OFFSETS_PACKED) | TKZ_OUT_OFFSETS; ep.outputs = P.outputs; }
+        else wide_cap = (uint32_t)lt;
+    }
     auto fail = [&](unsigned long long errw) -> int {
         err_doc_kernel<<<1, 1, 0, st>>>(ctrl, d_doc_off, nd); launches++;
         readback(ctx, hctrl + 4, ctrl + 4, 8);
@@ -849,8 +881,10 @@ int encode_slices(tkz_ctx* ctx, const DevModel& m, const ClassRanges& cr, const 
     if (P.outputs & TKZ_OUT_SPECIAL) TRY(ensure(ctx, ctx->O().special, (T + 4) * 4));
     if (P.outputs & TKZ_OUT_OFFSETS_PACKED) TRY(ensure(ctx, ctx->O().off16, (T + 4) * 2));
     if (P.outputs & TKZ_OUT_SPAN_TOKENS) TRY(ensure(ctx, ctx->O().spans, (T + 4) * 16));
+    if (wide_cap) TRY(ensure(ctx, ctx->O().wide, (size_t)wide_cap * 16));
     EmitOut eo{(uint32_t*)ctx->O().ids.p, (uint32_t*)ctx->O().off.p, (uint32_t*)ctx->O().attn.p, (uint32_t*)ctx->O().type.p,
-               (uint32_t*)ctx->O().special.p, (uint16_t*)ctx->O().off16.p, (uint16_t*)ctx->O().ids16.p, (uint4*)ctx->O().spans.p};
+               (uint32_t*)ctx->O().special.p, (uint16_t*)ctx->O().off16.p, (uint16_t*)ctx->O().ids16.p, (uint4*)ctx->O().spans.p,
+               (uint4*)ctx->O().wide.p, (unsigned int*)(ctrl + 23), wide_cap};
     const uint32_t big_cap = (uint32_t)(N / EMIT_BIG + 16);
     TRY(ensure(ctx, ctx->a_big, (size_t)big_cap * (sizeof(uint4) + sizeof(uint32_t))));
     SliceEmitArgs ea{};
@@ -891,8 +925,10 @@ int encode_slices(tkz_ctx* ctx, const DevModel& m, const ClassRanges& cr, const 
     CK(cudaGetLastError());
     CK(cudaEventRecord(ctx->ev[4], st));
     TRY(readback(ctx, hctrl, ctrl, 11 * 8));
+    if (wide_cap) TRY(readback(ctx, hctrl + 23, ctrl + 23, 8));
     CK(cudaStreamSynchronize(st));
     if (hctrl[0] != TKZ_ERRW_NONE) return fail(hctrl[0]);
+    if (wide_cap && (uint32_t)hctrl[23] > wide_cap) { ctx->err = "internal: more wide offsets than tokens of long pre-tokens"; return TKZ_ERR_CUDA; }
     ctx->stats.n_words = hctrl[10];
     if (N) ctx->tw_tok_per_byte = std::max(ctx->tw_tok_per_byte, (double)T_real / (double)N);
     ctx->stats.kernel_launches = launches;
@@ -910,6 +946,7 @@ int encode_slices(tkz_ctx* ctx, const DevModel& m, const ClassRanges& cr, const 
     out->type_ids = (P.outputs & TKZ_OUT_TYPE_IDS) ? eo.type_ids : nullptr;
     out->special_tokens_mask = (P.outputs & TKZ_OUT_SPECIAL) ? eo.special : nullptr;
     out->offsets_packed = (P.outputs & TKZ_OUT_OFFSETS_PACKED) ? eo.offsets16 : nullptr;
+    out->n_wide = wide_cap ? (uint32_t)hctrl[23] : 0; out->wide_tokens = out->n_wide ? (const uint32_t*)eo.wide : nullptr;
     out->span_tokens = (P.outputs & TKZ_OUT_SPAN_TOKENS) ? (const uint32_t*)eo.spans : nullptr;
     return TKZ_OK;
 }
@@ -1102,7 +1139,7 @@ int encode_device_impl(tkz_ctx* ctx, const uint8_t* d_text, const uint64_t* d_do
     if (P.outputs & TKZ_OUT_SPECIAL) TRY(ensure(ctx, ctx->O().special, T * 4));
     if (P.outputs & TKZ_OUT_SPAN_TOKENS) TRY(ensure(ctx, ctx->O().spans, T * 16));
     EmitOut eo{(uint32_t*)ctx->O().ids.p, (uint32_t*)ctx->O().off.p, (uint32_t*)ctx->O().attn.p, (uint32_t*)ctx->O().type.p,
-               (uint32_t*)ctx->O().special.p, nullptr, (uint16_t*)ctx->O().ids16.p, (uint4*)ctx->O().spans.p};
+               (uint32_t*)ctx->O().special.p, nullptr, (uint16_t*)ctx->O().ids16.p, (uint4*)ctx->O().spans.p, nullptr, nullptr, 0u};
     if (nw) {
         const uint32_t big_cap = (uint32_t)(N / EMIT_BIG + 16);
         TRY(ensure(ctx, ctx->a_big, (size_t)big_cap * (sizeof(uint4) + sizeof(uint32_t))));
@@ -1162,6 +1199,14 @@ int ensure_host_keep(tkz_ctx* ctx, HostBuf& b, size_t bytes, size_t keep) {
     return TKZ_OK;
 }
 
+// wide-offset records {slot lo, slot hi, start, end}: add a base to the slots of [first, first + n) and sort the whole list by slot
+struct WideRec { uint32_t lo, hi, s, e; };
+void wide_finish(WideRec* w, uint64_t n_total, const std::vector<std::array<uint64_t, 3>>& parts) {
+    for (const auto& pt : parts)
+        for (uint64_t k = pt[0]; k < pt[0] + pt[1]; k++) { const uint64_t v = (((uint64_t)w[k].hi << 32) | w[k].lo) + pt[2]; w[k].lo = (uint32_t)v; w[k].hi = (uint32_t)(v >> 32); }
+    std::sort(w, w + n_total, [](const WideRec& a, const WideRec& b) { return a.hi != b.hi ? a.hi < b.hi : a.lo < b.lo; });
+}
+
 // one shot: H2D everything, encode, D2H everything (small batches)
 int encode_host_single(tkz_ctx* ctx, const uint8_t* text, const uint64_t* doc_off, uint64_t n_docs, uint64_t N,
                        const tkz_encode_params* params, tkz_batch_result* out) {
@@ -1193,7 +1238,13 @@ int encode_host_single(tkz_ctx* ctx, const uint8_t* text, const uint64_t* doc_of
         if (T) CK(cudaMemcpyAsync(c.hb->p, c.src, T * c.elem, cudaMemcpyDeviceToHost, st));
         *c.dst = c.hb->p;
     }
+    out->n_wide = 0; out->wide_tokens = nullptr;
+    if (dev.n_wide) {
+        TRY(ensure_host(ctx, ctx->h_wide, dev.n_wide * 16));
+        CK(cudaMemcpyAsync(ctx->h_wide.p, dev.wide_tokens, dev.n_wide * 16, cudaMemcpyDeviceToHost, st));
+    }
     CK(cudaStreamSynchronize(st));
+    if (dev.n_wide) { wide_finish((WideRec*)ctx->h_wide.p, dev.n_wide, {}); out->n_wide = dev.n_wide; out->wide_tokens = (const uint32_t*)ctx->h_wide.p; }
     ctx->stats.ms_call_kernels = ctx->stats.ms_total;
     return TKZ_OK;
 }
@@ -1217,6 +1268,8 @@ int encode_host_chunked(tkz_ctx* ctx, const uint8_t* text, const uint64_t* doc_o
     };
     uint64_t chunk_target = ctx->chunk_bytes;
     const uint64_t chunk_max = std::min<uint64_t>(ctx->chunk_bytes * 8, 1ull << 30);
+    struct KeepGuard { tkz_ctx* c; ~KeepGuard() { c->call_keep = false; c->kept_valid = false; c->call_bytes = 0; } } keep_guard{ctx};
+    ctx->call_keep = ctx->keep_table; ctx->kept_valid = false; ctx->call_bytes = N; ctx->call_uniq = 0;
     cb.push_back(next_boundary(0, chunk_target));
     tkz_encode_params P{};
     if (params_in) P = *params_in;
@@ -1224,7 +1277,6 @@ int encode_host_chunked(tkz_ctx* ctx, const uint8_t* text, const uint64_t* doc_o
     P.outputs |= TKZ_OUT_IDS;
     TRY(ensure_host(ctx, ctx->h_doc_tok_off, (n_docs + 1) * 8));
     uint64_t* h_dto = (uint64_t*)ctx->h_doc_tok_off.p;
-    std::vector<uint64_t> tok_base;
     auto stage_in = [&](size_t i) -> int {
         const int b = (int)(i & 1);
         const uint64_t d0 = cb[i], d1 = cb[i + 1], base = doc_off[d0], nb = doc_off[d1] - base, nd = d1 - d0;
@@ -1240,25 +1292,34 @@ int encode_host_chunked(tkz_ctx* ctx, const uint8_t* text, const uint64_t* doc_o
     };
     bool used_ids16 = false;
 restart:
-    cb.resize(2); tok_base.clear(); chunk_target = ctx->chunk_bytes;
+    cb.resize(2); chunk_target = ctx->chunk_bytes; ctx->kept_valid = false; ctx->call_uniq = 0;
+    uint64_t W_total = 0; std::vector<std::array<uint64_t, 3>> wide_parts;
     TRY(stage_in(0));
     uint64_t T_total = 0, T_real = 0;
     float ms_kernels = 0.f;
     for (size_t i = 0; cb[i] < n_docs; i++) {
         const int b = (int)(i & 1);
         const uint64_t d0 = cb[i], d1 = cb[i + 1], nd = d1 - d0, nb = doc_off[d1] - doc_off[d0];
+        const auto tr0 = std::chrono::steady_clock::now();
         if (d1 < n_docs) {
             cb.push_back(next_boundary(d1, chunk_target));
-            // buffer (i+1)&1 was read by the kernels of chunk i-1 (finished: the device path drains its stream) and its staging
-            // area by the H2D of chunk i-1 (same stream as the copy about to be enqueued)
-            CK(cudaStreamSynchronize(ctx->s_h2d));
+            // buffer (i+1)&1 was read by the kernels of chunk i-1 and its staging area by the H2D of chunk i-1, which those kernels
+            // waited for: both finished when the device path of chunk i-1 drained its stream.  No host wait for the copy of
+            // chunk i: its kernels wait for it on the device (event below).
             TRY(stage_in(i + 1));
         }
+        const auto tr1 = std::chrono::steady_clock::now();
         CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_h2d[b], 0));
         CK(cudaEventSynchronize(ctx->ev_d2h[b]));              // output set b is free once chunk i-2 has been copied out
+        const auto tr2 = std::chrono::steady_clock::now();
         ctx->out_sel = b;
         tkz_batch_result dev{};
         int rc = encode_device_impl(ctx, (const uint8_t*)ctx->in_text[b].p, (const uint64_t*)ctx->in_doc_off[b].p, nd, nb, &P, &dev);
+        const auto tr3 = std::chrono::steady_clock::now();
+        if (getenv("TKZ_HOST_TRACE")) {
+            auto ms = [](auto a, auto b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+            fprintf(stderr, "[trace] chunk %zu docs %llu bytes %llu stage %.3f wait_d2h %.3f device_call %.3f (kernels %.3f: split %.3f model %.3f scan %.3f emit %.3f)\n", i, (unsigned long long)nd, (unsigned long long)nb, ms(tr0, tr1), ms(tr1, tr2), ms(tr2, tr3), ctx->stats.ms_total, ctx->stats.ms_split, ctx->stats.ms_model, ctx->stats.ms_scan, ctx->stats.ms_emit);
+        }
         if (rc != TKZ_OK) {
             cudaStreamSynchronize(ctx->s_h2d); cudaStreamSynchronize(ctx->s_d2h);
             out->err_doc = dev.err_doc >= 0 ? (int64_t)d0 + dev.err_doc : -1;
@@ -1273,10 +1334,9 @@ restart:
         }
         ms_kernels += ctx->stats.ms_total;
         // kernel-bound chunk (its device time exceeds what ~45 GB/s of PCIe needs for its text): larger chunks from now on
-        if ((double)ctx->stats.ms_total * 1e-3 > 1.5 * (double)nb / 45e9 && chunk_target < chunk_max) chunk_target *= 2;
+        if ((double)ctx->stats.ms_total * 1e-3 > (double)nb / 45e9 && chunk_target < chunk_max) chunk_target *= 2;
         used_ids16 = dev.ids16 != nullptr;                      // (the same decision in every chunk: it depends on the model and the parameters)
         const uint64_t T = dev.n_tokens;
-        tok_base.push_back(T_total);
         // size the host arrays from the first chunk's token density
         uint64_t est = T_total + T;
         if (i == 0 && nb) est = (uint64_t)((double)T * ((double)N / (double)nb) * 1.03) + 4096;
@@ -1290,16 +1350,22 @@ restart:
             TRY(ensure_host_keep(ctx, *c.hb, est * c.elem, T_total * c.elem));
             if (T) CK(cudaMemcpyAsync((uint8_t*)c.hb->p + T_total * c.elem, c.src, T * c.elem, cudaMemcpyDeviceToHost, ctx->s_d2h));
         }
+        if (dev.n_wide) {
+            TRY(ensure_host_keep(ctx, ctx->h_wide, (W_total + dev.n_wide) * 16, W_total * 16));
+            CK(cudaMemcpyAsync((uint8_t*)ctx->h_wide.p + W_total * 16, dev.wide_tokens, dev.n_wide * 16, cudaMemcpyDeviceToHost, ctx->s_d2h));
+            wide_parts.push_back({W_total, dev.n_wide, T_total});
+            W_total += dev.n_wide;
+        }
+        // chunk-relative CSR offsets -> call-relative on the device (same stream as the copy; the chunk's kernels have finished)
+        if (T_total) add_base_u64_kernel<<<(unsigned)((nd + 1 + 255) / 256), 256, 0, ctx->s_d2h>>>((unsigned long long*)dev.doc_tok_off, nd + 1, T_total);
         CK(cudaMemcpyAsync(h_dto + d0, dev.doc_tok_off, (nd + 1) * 8, cudaMemcpyDeviceToHost, ctx->s_d2h));
         CK(cudaEventRecord(ctx->ev_d2h[b], ctx->s_d2h));
         T_total += T; T_real += dev.n_real_tokens;
     }
-    const size_t nc = cb.size() - 1;
     CK(cudaStreamSynchronize(ctx->s_d2h));
     CK(cudaStreamSynchronize(ctx->s_h2d));
-    // chunk-relative CSR offsets -> global
-    for (size_t i = 1; i < nc; i++) { const uint64_t base = tok_base[i]; for (uint64_t d = cb[i]; d < cb[i + 1]; d++) h_dto[d] += base; }
     h_dto[n_docs] = T_total;
+    if (W_total) wide_finish((WideRec*)ctx->h_wide.p, W_total, wide_parts);
     ctx->out_sel = 0;
     ctx->stats.ms_call_kernels = ms_kernels;
     uint32_t outputs = P.outputs;
@@ -1314,6 +1380,7 @@ restart:
     out->special_tokens_mask = (outputs & TKZ_OUT_SPECIAL) ? (const uint32_t*)ctx->h_special.p : nullptr;
     out->offsets_packed = (outputs & TKZ_OUT_OFFSETS_PACKED) ? (const uint16_t*)ctx->h_off16.p : nullptr;
     out->span_tokens = (outputs & TKZ_OUT_SPAN_TOKENS) ? (const uint32_t*)ctx->h_spans.p : nullptr;
+    out->n_wide = (outputs & TKZ_OUT_OFFSETS_PACKED) ? W_total : 0; out->wide_tokens = out->n_wide ? (const uint32_t*)ctx->h_wide.p : nullptr;
     return TKZ_OK;
 }
 
@@ -1351,6 +1418,7 @@ extern "C" int tkz_encode_batch_compact(tkz_ctx* ctx, const uint8_t* text, const
     out->n_docs = r.n_docs; out->n_kept = r.n_tokens; out->n_real_tokens = r.n_real_tokens;
     out->doc_kept_off = r.doc_tok_off; out->ids = r.ids; out->ids16 = r.ids16;
     out->offsets_packed = r.offsets_packed; out->offsets = r.offsets;
+    out->n_wide = r.n_wide; out->wide_tokens = r.wide_tokens;
     return TKZ_OK;
 }
 
@@ -1381,7 +1449,27 @@ extern "C" int tkz_compact_expand(const tkz_compact_result* r, uint64_t d0, uint
             for (uint64_t i = 0; i < npad; i++) ids[pad0 + i] = P.pad_id;
         }
         if (offsets) {
-            if (r->offsets_packed) for (uint64_t i = 0; i < k; i++) { const uint32_t v = r->offsets_packed[k0 + i]; offsets[2 * (real0 + i)] = v & 0xFFu; offsets[2 * (real0 + i) + 1] = v >> 8; }
+            if (r->offsets_packed) {
+                // 0xFFFF: the token's offsets are in the side list (sorted by kept index); the first one of the document by binary
+                // search, the following ones in order
+                const WideRec* wt = (const WideRec*)r->wide_tokens; uint64_t wi = r->n_wide;
+                for (uint64_t i = 0; i < k; i++) {
+                    const uint32_t v = r->offsets_packed[k0 + i];
+                    uint32_t s0 = v & 0xFFu, e0 = v >> 8;
+                    if (v == 0xFFFFu) {
+                        const uint64_t slot = k0 + i;
+                        if (wi == r->n_wide) {
+                            uint64_t lo = 0, hi = r->n_wide;
+                            while (lo < hi) { const uint64_t mid = (lo + hi) / 2; const uint64_t sv = ((uint64_t)wt[mid].hi << 32) | wt[mid].lo; if (sv < slot) lo = mid + 1; else hi = mid; }
+                            wi = lo;
+                        }
+                        while (wi < r->n_wide && ((((uint64_t)wt[wi].hi << 32) | wt[wi].lo) < slot)) wi++;
+                        if (wi >= r->n_wide || ((((uint64_t)wt[wi].hi << 32) | wt[wi].lo) != slot)) return TKZ_ERR_INVALID_ARG;
+                        s0 = wt[wi].s; e0 = wt[wi].e;
+                    }
+                    offsets[2 * (real0 + i)] = s0; offsets[2 * (real0 + i) + 1] = e0;
+                }
+            }
             else if (r->offsets) memcpy(offsets + 2 * real0, r->offsets + 2 * k0, k * 8);
             else return TKZ_ERR_INVALID_ARG;
             memset(offsets + 2 * pad0, 0, npad * 8);

@@ -46,7 +46,8 @@ __global__ void doc_len_kernel(EmitParams p, const uint32_t* __restrict__ word_t
 struct EmitOut { uint32_t* ids; uint32_t* offsets; uint32_t* attention; uint32_t* type_ids; uint32_t* special;
                  uint16_t* offsets16;        // one u16 per token (start | end << 8), only when every pre-token is < 256 bytes
                  uint16_t* ids16;            // ids as u16 instead of `ids` (outputs & 64: every id of the vocabulary is < 65536)
-                 uint4* spans; };            // SpanToken records (token.zig:19-33): {id, start, end, type_id | flags << 8} (outputs & 128)
+                 uint4* spans;               // SpanToken records (token.zig:19-33): {id, start, end, type_id | flags << 8} (outputs & 128)
+                 uint4* wide; unsigned int* wide_count; uint32_t wide_cap; };   // offsets16: tokens that do not fit a byte pair {slot lo, hi, start, end}
 
 // words with more than EMIT_BIG tokens (whole documents, MiB-long unbroken words) are not copied by one warp: they are
 // queued here and copied by the whole grid (emit_big_kernel)
@@ -66,6 +67,15 @@ __device__ __forceinline__ void emit_id(const EmitParams& p, const EmitOut& o, u
 __device__ __forceinline__ void emit_real(const EmitParams& p, const EmitOut& o, unsigned long long dst, uint32_t id, uint32_t s, uint32_t e) {
     emit_id(p, o, dst, id);
     if (p.outputs & 2u) reinterpret_cast<uint2*>(o.offsets)[dst] = make_uint2(s, e);
+    if (p.outputs & 32u) {
+        // one u16 per token; a token of a long pre-token that does not fit goes to the side list (sized for all of them)
+        if (e < 256u && (s | (e << 8)) != 0xFFFFu) o.offsets16[dst] = (uint16_t)(s | (e << 8));
+        else {
+            o.offsets16[dst] = 0xFFFFu;
+            const uint32_t k = atomicAdd(o.wide_count, 1u);
+            if (k < o.wide_cap) o.wide[k] = make_uint4((uint32_t)dst, (uint32_t)(dst >> 32), s, e);
+        }
+    }
     if (p.outputs & 4u) o.attention[dst] = 1u;
     const uint32_t ty = (p.hf_flags & 1u) ? p.seq_type : 0u;
     if (p.outputs & 8u) o.type_ids[dst] = ty;

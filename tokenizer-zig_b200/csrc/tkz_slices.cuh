@@ -987,13 +987,14 @@ __global__ void __launch_bounds__(TW_THREADS, TW_BLOCKS_PER_SM) slice_words_kern
 // that start behind it in the same tile
 __global__ void long_fix_kernel(const uint32_t* __restrict__ long_start, const uint32_t* __restrict__ long_slice, const uint32_t* __restrict__ long_ntok,
                                 uint32_t n_long, const uint32_t* __restrict__ tile_doc_lo, const uint64_t* __restrict__ doc_off,
-                                uint32_t* tile_ntok, uint32_t* doc_tok_local) {
+                                uint32_t* tile_ntok, uint32_t* doc_tok_local, unsigned long long* long_tok_total) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_long) return;
     const uint32_t n = long_ntok[i];
     if (n == TKZ_NONE || n == 0) return;
     const uint32_t tile = long_slice[i];
     atomicAdd(tile_ntok + tile, n);
+    atomicAdd(long_tok_total, (unsigned long long)n);
     const uint64_t pos = long_start[i];
     for (uint32_t d = tile_doc_lo[tile]; d < tile_doc_lo[tile + 1]; d++) if (doc_off[d] > pos) atomicAdd(doc_tok_local + d, n);
 }

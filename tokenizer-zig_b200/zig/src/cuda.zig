@@ -89,6 +89,8 @@ pub const BatchResult = extern struct {
     offsets_packed: ?[*]const u16,
     ids16: ?[*]const u16,
     span_tokens: ?[*]const u32, // 4 u32 per slot = SpanToken (src/token.zig:19-33)
+    n_wide: u64, // offsets_packed: tokens whose u16 is 0xFFFF (pre-tokens of 256+ bytes)
+    wide_tokens: ?[*]const u32, // {slot low, slot high, start, end} each, sorted by slot in host-buffer results
 };
 
 /// tkz_compact_result: kept real tokens only; masks and padding slots are rebuilt on the host (tkz_compact_expand)
@@ -99,10 +101,12 @@ pub const CompactResult = extern struct {
     doc_kept_off: ?[*]const u64, // n_docs + 1
     ids: ?[*]const u32, // null when ids16 is delivered
     ids16: ?[*]const u16,
-    offsets_packed: ?[*]const u16, // null when a pre-token has 256+ bytes (then `offsets`)
+    offsets_packed: ?[*]const u16, // 0xFFFF = look the token up in wide_tokens; null when the call fell back to `offsets`
     offsets: ?[*]const u32,
     params: EncodeParams,
     err_doc: i64,
+    n_wide: u64,
+    wide_tokens: ?[*]const u32, // {kept index low, high, start, end}, sorted by kept index
 };
 
 pub const Stats = extern struct {

@@ -207,7 +207,21 @@ pub const GpuTokenizer = struct {
         }
         pub fn offset(self: *const BatchView, d: usize, i: usize) lib.Offset {
             const k: usize = @intCast(self.r.doc_kept_off.?[d]);
-            if (self.r.offsets_packed) |p| return lib.Offset.init(p[k + i] & 0xFF, p[k + i] >> 8);
+            if (self.r.offsets_packed) |p| {
+                const v = p[k + i];
+                if (v != 0xFFFF) return lib.Offset.init(v & 0xFF, v >> 8);
+                // a token of a pre-token of 256+ bytes: binary search in the side list (sorted by kept index)
+                const w = self.r.wide_tokens.?;
+                var lo: usize = 0;
+                var hi: usize = @intCast(self.r.n_wide);
+                const slot: u64 = k + i;
+                while (lo < hi) {
+                    const mid = (lo + hi) / 2;
+                    const sv = (@as(u64, w[4 * mid + 1]) << 32) | w[4 * mid];
+                    if (sv < slot) lo = mid + 1 else hi = mid;
+                }
+                return lib.Offset.init(w[4 * lo + 2], w[4 * lo + 3]);
+            }
             return lib.Offset.init(self.r.offsets.?[2 * (k + i)], self.r.offsets.?[2 * (k + i) + 1]);
         }
         /// slots of document d after Encoding.pad (src/encoding.zig:385-463)
