@@ -347,6 +347,9 @@ int tkzh_model_id_to_token(tkzh_tokenizer* t, uint32_t id, const uint8_t** token
  * is applied, its special tokens only when tkzh_encode_batch is called with add_special_tokens != 0.  Returns 1 when such a
  * template was found at load time, 0 when there is none to apply. */
 int tkzh_set_hf_compat(tkzh_tokenizer* t, uint32_t flags);
+/* the template found at load time (arrays of TKZ_TPL_MAX entries; any pointer may be NULL): 1 and the outputs filled, or 0 */
+int tkzh_hf_template(tkzh_tokenizer* t, uint32_t* n_prefix, uint32_t* prefix_id, uint32_t* prefix_type, uint32_t* n_suffix,
+                     uint32_t* suffix_id, uint32_t* suffix_type, uint32_t* seq_type);
 int tkzh_add_special_tokens(tkzh_tokenizer* t, const uint8_t* contents, const uint64_t* off, uint64_t n, uint64_t* added);
 /* loader facts used by the parity tests */
 uint64_t tkzh_model_vocab_count(tkzh_tokenizer* t);

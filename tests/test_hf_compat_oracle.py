@@ -68,3 +68,29 @@ def test_mode_off_is_the_reference():
     t.set_hf_compat(0, [(2, 0)], [(3, 0)], 0)
     b = t.encode_batch([x.encode() for x in s["texts"]])
     assert a.ids.tolist() == b.ids.tolist() and a.offsets.tolist() == b.offsets.tolist() and a.special_tokens_mask.tolist() == b.special_tokens_mask.tolist()
+
+
+def test_host_mirror_parses_the_same_templates():
+    """the C++ host mirror (tkzh_*; loads without a GPU) against the Python reading used by the oracle"""
+    import tokzig_b200 as tz
+    for s in VEC["suites"]:
+        t = tz.Tokenizer.from_json(s["tokenizer_json"], device=None)
+        assert t.hf_template() == orc.hf_template_from_json(s["tokenizer_json"])
+        assert t.set_hf_compat(tz.HF_TEMPLATE) is True
+        t.close()
+    base = json.loads(VEC["suites"][0]["tokenizer_json"])
+    for pp in (None, {"type": "ByteLevel", "trim_offsets": True},
+               {"type": "TemplateProcessing", "single": [{"Sequence": {"id": "A", "type_id": 0}}, {"Sequence": {"id": "B", "type_id": 1}}], "pair": [], "special_tokens": {}},
+               {"type": "TemplateProcessing", "single": [{"SpecialToken": {"id": "[NOPE]", "type_id": 0}}, {"Sequence": {"id": "A", "type_id": 0}}], "pair": [], "special_tokens": {}},
+               {"type": "TemplateProcessing", "single": [{"SpecialToken": {"id": "[CLS]", "type_id": 0}}] * 5 + [{"Sequence": {"id": "A", "type_id": 0}}], "pair": [],
+                "special_tokens": {"[CLS]": {"id": "[CLS]", "ids": [2], "tokens": ["[CLS]"]}}}):
+        base["post_processor"] = pp
+        js = json.dumps(base)
+        t = tz.Tokenizer.from_json(js, device=None)
+        assert t.hf_template() is None and orc.hf_template_from_json(js) is None
+        assert t.set_hf_compat(tz.HF_TEMPLATE | tz.HF_DOC_OFFSETS) is False
+        t.close()
+    base["post_processor"] = {"type": "TemplateProcessing", "single": [{"Sequence": {"id": "A", "type_id": 1}}], "pair": [], "special_tokens": {}}
+    t = tz.Tokenizer.from_json(json.dumps(base), device=None)
+    assert t.hf_template() == ([], [], 1)
+    t.close()

@@ -153,7 +153,7 @@ EXPORTED_SYMBOLS = [
     "tkzh_from_json", "tkzh_from_file", "tkzh_free", "tkzh_last_error", "tkzh_ctx", "tkzh_set_truncation", "tkzh_set_padding",
     "tkzh_set_normalizer", "tkzh_set_pretokenizer", "tkzh_encode_batch", "tkzh_encode_batch_fast", "tkzh_decode", "tkzh_decode_batch", "tkzh_get_vocab_size", "tkzh_token_to_id",
     "tkzh_id_to_token", "tkzh_model_id_to_token", "tkzh_add_special_tokens", "tkzh_model_vocab_count", "tkzh_merge_count", "tkzh_has_normalizer",
-    "tkzh_has_pretokenizer", "tkzh_has_post_processor", "tkzh_set_hf_compat", "tkzh_added_token_count", "tkzh_added_token", "tkzh_model_desc",
+    "tkzh_has_pretokenizer", "tkzh_has_post_processor", "tkzh_set_hf_compat", "tkzh_hf_template", "tkzh_added_token_count", "tkzh_added_token", "tkzh_model_desc",
 ]
 
 _lib = None
@@ -204,6 +204,8 @@ def lib():
     L.tkzh_set_truncation.argtypes = [vp, i32, u64]
     L.tkzh_set_hf_compat.argtypes = [vp, C.c_uint32]
     L.tkzh_set_hf_compat.restype = C.c_int
+    L.tkzh_hf_template.argtypes = [vp] + [vp] * 7
+    L.tkzh_hf_template.restype = C.c_int
     L.tkzh_set_padding.argtypes = [vp, i32, i32, u64, u32, u32, i32]
     L.tkzh_set_normalizer.argtypes = [vp, vp, vp, C.c_int32]
     L.tkzh_set_pretokenizer.argtypes = [vp, vp, C.c_int32]
@@ -479,6 +481,15 @@ class Tokenizer:
         if rc < 0:
             raise TokzigError(rc, "tkzh_set_hf_compat", -1)
         return rc == 1
+
+    def hf_template(self):
+        """(prefix, suffix, seq_type) of the single-sequence template parsed from the tokenizer.json, prefix / suffix =
+        [(special id, type id)], or None when there is none this mode can apply."""
+        n1, n2, st = C.c_uint32(), C.c_uint32(), C.c_uint32()
+        a, b, c, d = ((C.c_uint32 * 4)() for _ in range(4))
+        if self._L.tkzh_hf_template(self._h, C.byref(n1), a, b, C.byref(n2), c, d, C.byref(st)) != 1:
+            return None
+        return [(a[i], b[i]) for i in range(n1.value)], [(c[i], d[i]) for i in range(n2.value)], st.value
 
     def _push_params(self):
         if self.truncation is None:

@@ -504,6 +504,19 @@ extern "C" int tkzh_has_pretokenizer(tkzh_tokenizer* t) { return t->has_pretok; 
 extern "C" int tkzh_has_post_processor(tkzh_tokenizer* t) { return t->has_post; }
 // hf_compat switch (TKZ_HF_* flags; 0 = the reference's behaviour, the default).  Returns 1 when the tokenizer.json carried a
 // single-sequence template this mode can apply, 0 when TKZ_HF_TEMPLATE will have no effect.
+// the parsed single-sequence template (what TKZ_HF_TEMPLATE will apply): ids / type ids into arrays of TKZ_TPL_MAX entries.
+// Returns 1 and fills the outputs when the tokenizer.json carried one, 0 otherwise.
+extern "C" int tkzh_hf_template(tkzh_tokenizer* t, uint32_t* n_prefix, uint32_t* prefix_id, uint32_t* prefix_type, uint32_t* n_suffix,
+                                uint32_t* suffix_id, uint32_t* suffix_type, uint32_t* seq_type) {
+    if (!t) return TKZ_ERR_INVALID_ARG;
+    if (!t->has_template) return 0;
+    if (n_prefix) *n_prefix = (uint32_t)t->tpl_prefix.size();
+    if (n_suffix) *n_suffix = (uint32_t)t->tpl_suffix.size();
+    for (size_t i = 0; i < t->tpl_prefix.size(); i++) { if (prefix_id) prefix_id[i] = t->tpl_prefix[i].first; if (prefix_type) prefix_type[i] = t->tpl_prefix[i].second; }
+    for (size_t i = 0; i < t->tpl_suffix.size(); i++) { if (suffix_id) suffix_id[i] = t->tpl_suffix[i].first; if (suffix_type) suffix_type[i] = t->tpl_suffix[i].second; }
+    if (seq_type) *seq_type = t->tpl_seq_type;
+    return 1;
+}
 extern "C" int tkzh_set_hf_compat(tkzh_tokenizer* t, uint32_t flags) {
     if (!t) return TKZ_ERR_INVALID_ARG;
     t->hf_flags = flags & (TKZ_HF_TEMPLATE | TKZ_HF_DOC_OFFSETS);
