@@ -1327,7 +1327,8 @@ restart:
             return rc;
         }
         if ((P.outputs & TKZ_OUT_OFFSETS_PACKED) && !dev.offsets_packed) {
-            // a pre-token of 256 bytes or more in this chunk: the whole call delivers 32-bit offsets, start again
+            // this chunk has too many tokens of 256-byte-or-longer pre-tokens for the side list: the whole call delivers 32-bit
+            // offsets, start again
             CK(cudaStreamSynchronize(ctx->s_h2d)); CK(cudaStreamSynchronize(ctx->s_d2h));
             P.outputs = (P.outputs & ~TKZ_OUT_OFFSETS_PACKED) | TKZ_OUT_OFFSETS;
             goto restart;
