@@ -1033,22 +1033,28 @@ __device__ __forceinline__ void te_put(const EmitParams& p, const EmitOut& o, un
     if (outputs & 128u) o.spans[dst] = make_uint4(id, s, e, ty & 0xFFu);
 }
 
-// copies the stream tokens [j0, j1) of a slice (stream position src + j) to dst0 + (j - j0); 4 loads in flight per lane
+#ifndef TKZ_TE_UNROLL
+#define TKZ_TE_UNROLL 4
+#endif
+// copies the stream tokens [j0, j1) of a slice (stream position src + j) to dst0 + (j - j0); TKZ_TE_UNROLL loads in flight per lane
 template <uint32_t OUTS>
 __device__ __forceinline__ void te_copy(const SliceEmitArgs& a, const EmitParams& p, const EmitOut& o, size_t src, uint32_t j0, uint32_t j1,
                                         unsigned long long dst0, uint32_t hs = 0) {
     const uint32_t lane = lane_id();
     const uint32_t outputs = OUTS ? OUTS : p.outputs;
     const bool want_of = (outputs & (2u | 32u)) != 0;
-    for (uint32_t j = j0 + lane; j < j1; j += 128) {
-        uint32_t id[4], of[4] = {0, 0, 0, 0};
+    constexpr int TE_U = TKZ_TE_UNROLL;
+    for (uint32_t j = j0 + lane; j < j1; j += 32 * TE_U) {
+        uint32_t id[TE_U], of[TE_U];
 #pragma unroll
-        for (int u = 0; u < 4; u++) if (j + 32 * u < j1) {
+        for (int u = 0; u < TE_U; u++) { id[u] = 0; of[u] = 0; }
+#pragma unroll
+        for (int u = 0; u < TE_U; u++) if (j + 32 * u < j1) {
             if (want_of) { const uint2 r = __ldg(a.tok2 + src + j + 32 * u); id[u] = r.x; of[u] = r.y; }
             else id[u] = __ldg(a.tok_id + src + j + 32 * u);
         }
 #pragma unroll
-        for (int u = 0; u < 4; u++) if (j + 32 * u < j1) te_put<OUTS>(p, o, dst0 + (j + 32 * u - j0), id[u], of[u], hs);
+        for (int u = 0; u < TE_U; u++) if (j + 32 * u < j1) te_put<OUTS>(p, o, dst0 + (j + 32 * u - j0), id[u], of[u], hs);
     }
 }
 
